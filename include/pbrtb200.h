@@ -1,0 +1,252 @@
+/*
+ * pbrtb200.h — C ABI of the B200 rendering back end for pbrt_rust.
+ *
+ * This is the drop-in boundary.  The reference-side interface it replaces is
+ *     trait Renderer { fn render(&mut self, scene: &Scene); ... }      (src/renderer.rs:8-26)
+ * as implemented by SamplerRenderer (src/sampler_renderer.rs:26-54, 147-182): a host crate
+ * `GpuRenderer: Renderer` flattens its Scene/Camera/Sampler/Film into the plain structs below and
+ * calls pbrtb200_render(); see INTEGRATION.md for the Rust `extern "C"` block and the flatten shim.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; pbrtb200_last_error(ctx) gives the text
+ *     (panics of the reference become error codes: NaN radiance — sampler_renderer.rs:105 intent;
+ *     singular matrix — transform/matrix4x4.rs:157; traversal-stack overflow).
+ *   - the caller owns every input array; the library copies during the call and keeps no host
+ *     pointer.  Device memory is owned by the ctx.  Output buffers are caller-allocated.
+ *   - a ctx is bound to one CUDA device, is not thread-safe, and every call is synchronous.
+ *   - all structs are POD with fixed layout (`#[repr(C)]` on the Rust side).
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails with PBRTB200_ENODEV.
+ */
+#ifndef PBRTB200_H
+#define PBRTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBRTB200_OK 0
+#define PBRTB200_EINVAL (-1)    /* bad argument / malformed scene */
+#define PBRTB200_ENODEV (-2)    /* no CUDA device / CUDA failure */
+#define PBRTB200_ENAN (-3)      /* "Invalid radiance value!" (sampler_renderer.rs:105) */
+#define PBRTB200_ESTACK (-4)    /* traversal stack deeper than PBRTB200_STACK_DEPTH */
+#define PBRTB200_ESINGULAR (-5) /* "Singular matrix!" (matrix4x4.rs:157) */
+#define PBRTB200_ENOMEM (-6)
+
+#define PBRTB200_STACK_DEPTH 64 /* bvh.rs:386 Vec::with_capacity(64) is a hint; here a hard bound */
+#define PBRTB200_MISS 0xFFFFFFFFu
+
+typedef struct pbrtb200_ctx pbrtb200_ctx;
+
+/* ---- flattened scene --------------------------------------------------------------------- */
+
+/* One PackedBVHNode (src/primitive/aggregates/bvh.rs:260-272), in the reference's depth-first
+ * order: the first child of inner node i is i+1, the second is `offset`.                        */
+typedef struct {
+  float bmin[3];
+  float bmax[3];
+  uint32_t offset;  /* Leaf: prim_offset into the ordered primitive list; Inner: second child  */
+  uint16_t count;   /* Leaf: num_prims (1..65535); Inner: 0                                     */
+  uint8_t axis;     /* Inner: split axis 0..2                                                   */
+  uint8_t is_leaf;  /* 1 = Leaf, 0 = Inner                                                      */
+} pbrtb200_node32;
+
+/* One Triangle (src/shape/mesh.rs:27-39) with world-space vertices pre-gathered in the
+ * refine-reversed order (p1,p2,p3) = (P[vi[3j+2]], P[vi[3j+1]], P[vi[3j]]) (mesh.rs:329-331).   */
+typedef struct {
+  float p1[3];
+  uint32_t mesh;   /* index into pbrtb200_scene.meshes */
+  float p2[3];
+  uint32_t attr;   /* index into tri_uv / tri_n / tri_s (per-triangle attribute records) */
+  float p3[3];
+  uint32_t user;   /* caller's id for this triangle (e.g. Rust prim_id); echoed, never read */
+} pbrtb200_tri48;
+
+/* One Sphere (src/shape/sphere.rs:17-25): world-to-object rows 0..2 of the 4x4 (affine) + params */
+typedef struct {
+  float w2o[12];
+  float radius, z_min, z_max, phi_max, theta_min, theta_max;
+  uint32_t material;
+  uint32_t flip;   /* reverse_orientation ^ transform_swaps_handedness */
+} pbrtb200_sphere80;
+
+/* Per-mesh shading data (ShapeBase of the mesh, src/shape/mod.rs:33-54) */
+typedef struct {
+  float o2w[12];     /* rows 0..2 of object2world.m      */
+  float o2w_inv[12]; /* rows 0..2 of object2world.m_inv  */
+  uint32_t material;
+  int32_t area_light;  /* index into lights (kind AREA) or -1 */
+  uint32_t flip;       /* reverse_orientation ^ transform_swaps_handedness */
+  uint32_t has_uv, has_n, has_s;
+} pbrtb200_mesh;
+
+#define PBRTB200_TEX_CONSTANT 0
+#define PBRTB200_TEX_CHECKER2D 1
+#define PBRTB200_TEX_UV 2
+#define PBRTB200_MAP_UV 0      /* UVMapping2D(su,sv,du,dv): map[0..3]                      */
+#define PBRTB200_MAP_PLANAR 1  /* PlanarMapping2D(vs,vt,ds,dt): map[0..2],map[3..5],map[6..7] */
+typedef struct {
+  int32_t kind;
+  float value[3];  /* Constant (float textures use value[0]) */
+  int32_t map_kind;
+  float map[8];
+  int32_t tex1, tex2;  /* Checkerboard children */
+  int32_t aa;          /* 0 NONE, 1 CLOSEDFORM (texture/checkerboard.rs:10-14) */
+} pbrtb200_texture;
+
+#define PBRTB200_MAT_MATTE 0
+#define PBRTB200_MAT_PLASTIC 1
+typedef struct {
+  int32_t kind;
+  int32_t kd, sigma, ks, roughness;  /* texture indices */
+} pbrtb200_material;
+
+#define PBRTB200_LIGHT_POINT 0
+#define PBRTB200_LIGHT_SPOT 1
+#define PBRTB200_LIGHT_AREA 2 /* extension: the reference's AreaLight is a stub (area_light.rs) */
+typedef struct {
+  int32_t kind;
+  float pos[3];
+  float intensity[3];  /* point/spot: I ; area: emitted radiance L */
+  float w2l[12];       /* world_to_light rows 0..2 (spot falloff) */
+  float cos_total_width, cos_falloff_start;
+  int32_t num_samples;
+  uint32_t first_tri, n_tris; /* area: range in pbrtb200_scene.area_prims */
+  float total_area;           /* filled by the library at upload */
+} pbrtb200_light;
+
+typedef struct {
+  const pbrtb200_node32* nodes;
+  uint32_t n_nodes;
+  /* ordered primitive list (BVHAccelerator.primitives, bvh.rs:331): entry i is a triangle
+   * (bit31 = 0, index into tris) or a sphere (bit31 = 1, index into spheres).               */
+  const uint32_t* leaf_prim;
+  uint32_t n_prims;
+  const pbrtb200_tri48* tris;
+  uint32_t n_tris;
+  const pbrtb200_sphere80* spheres;
+  const float* sphere_o2w; /* 12 floats per sphere: object2world rows 0..2 */
+  uint32_t n_spheres;
+  const pbrtb200_mesh* meshes;
+  uint32_t n_meshes;
+  const float* tri_uv; /* 6 floats per attr record (uv of p1,p2,p3) or NULL */
+  const float* tri_n;  /* 9 floats per attr record or NULL */
+  const float* tri_s;  /* 9 floats per attr record or NULL */
+  uint32_t n_attr;
+  const pbrtb200_material* materials;
+  uint32_t n_materials;
+  const pbrtb200_texture* textures;
+  uint32_t n_textures;
+  const pbrtb200_light* lights;
+  uint32_t n_lights;
+  /* emissive triangles of the area lights: indices into the ordered primitive list, grouped per
+   * light (pbrtb200_light.first_tri / n_tris), in BVH-input (refined) order.                   */
+  const uint32_t* area_prims;
+  uint32_t n_area_prims;
+} pbrtb200_scene;
+
+/* ---- camera / sampler / film / integrator -------------------------------------------------- */
+
+/* Camera::Perspective (src/camera/mod.rs:105-135, projective.rs:48-72), static camera-to-world */
+typedef struct {
+  float raster_to_camera[16]; /* Projection::raster_to_camera().m, row-major */
+  float camera_to_world[16];
+  float dx_camera[3], dy_camera[3];
+  float shutter_open, shutter_close;
+  float lens_radius, focal_distance;
+} pbrtb200_camera;
+
+#define PBRTB200_SAMPLER_STRATIFIED 0
+#define PBRTB200_SAMPLER_LD 1
+/* Sampler::stratified / low_discrepancy (src/sampler/mod.rs:30-50) over the full sample extent,
+ * plus SamplerRenderer.num_tasks (sampler_renderer.rs:41-44), which fixes the per-task sub-windows
+ * (sampler/base.rs:29-48) and RNG seeds (sampler_renderer.rs:74).                               */
+typedef struct {
+  int32_t kind;
+  int32_t x_start, x_end, y_start, y_end;
+  int32_t xs, ys;  /* stratified strata; LD: xs = samples per pixel (rounded up to 2^k) */
+  int32_t jitter;
+  float shutter_open, shutter_close;
+  int32_t num_tasks;
+} pbrtb200_sampler;
+
+/* Film::Image (src/camera/film.rs:55-122) */
+typedef struct {
+  int32_t x_res, y_res;
+  int32_t x_pixel_start, y_pixel_start, x_pixel_count, y_pixel_count;
+  float filter_xw, filter_yw;
+  float filter_table[256]; /* FILTER_TABLE_DIM = 16 */
+} pbrtb200_film;
+
+typedef struct {
+  int32_t kind;       /* 0 = Whitted light loop (integrator/whitted.rs:30-66) */
+  int32_t max_depth;  /* specular recursion contributes 0 for matte/plastic (BSDF::sample_f is
+                         unimplemented in the reference), so any depth renders the same */
+  int32_t strict_flags; /* 1 = reproduce BSDF::f's as-written flag test (always black) */
+} pbrtb200_integrator;
+
+/* Film pixel rectangles this call renders (multi-GPU tile partition); NULL = whole film. */
+typedef struct {
+  const int32_t* rects; /* n_rects x (x0, y0, x1, y1), half-open, in film pixel coordinates */
+  uint32_t n_rects;
+} pbrtb200_tileset;
+
+typedef struct {
+  uint64_t camera_rays, camera_hits, shadow_rays;
+  float ms_total;   /* device time of the whole call (CUDA events) */
+  float ms_raygen, ms_trace, ms_shade, ms_shadow, ms_film;
+  uint32_t kernel_launches;
+  uint32_t nan_samples;
+  uint32_t stack_overflows;
+} pbrtb200_stats;
+
+/* ---- wavefront records (also the unit-level parity hooks) ---------------------------------- */
+typedef struct {
+  float o[3], mint;
+  float d[3], maxt;
+} pbrtb200_ray32;
+typedef struct {
+  uint32_t prim; /* index into the ordered primitive list, or PBRTB200_MISS */
+  float t;
+  float b1, b2; /* triangle barycentrics; sphere: b1 = phi */
+} pbrtb200_hit16;
+
+/* ---- entry points -------------------------------------------------------------------------- */
+int pbrtb200_create(int device, pbrtb200_ctx** out);
+void pbrtb200_destroy(pbrtb200_ctx* ctx);
+const char* pbrtb200_last_error(const pbrtb200_ctx* ctx); /* ctx may be NULL (create errors) */
+
+int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* scene);
+
+/* Renderer::render.  out_xyzw: 4 floats per film pixel (x_pixel_count*y_pixel_count, row-major):
+ * sum(w*X), sum(w*Y), sum(w*Z), sum(w) — the contents of Film::Image.pixels (film.rs:35-41).
+ * `out_is_device` != 0: out_xyzw is a device pointer on the ctx's device (no D2H copy).        */
+int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb200_sampler* smp,
+                    const pbrtb200_film* film, const pbrtb200_integrator* integ,
+                    const pbrtb200_tileset* tiles, float* out_xyzw, int out_is_device,
+                    pbrtb200_stats* stats);
+
+/* Scene::intersect for a batch of rays (src/scene.rs:60-63).  *_is_device: pointers are device
+ * memory on the ctx's device (used by bench.py's resident-input arm).                           */
+int pbrtb200_trace_closest(pbrtb200_ctx* ctx, const pbrtb200_ray32* rays, uint64_t n,
+                           pbrtb200_hit16* hits, int is_device, pbrtb200_stats* stats);
+/* Scene::intersect_p (src/scene.rs:65-67): occluded[i] = 1 iff any hit in [mint, maxt] */
+int pbrtb200_trace_any(pbrtb200_ctx* ctx, const pbrtb200_ray32* rays, uint64_t n,
+                       uint8_t* occluded, int is_device, pbrtb200_stats* stats);
+
+/* Camera samples -> primary rays -> closest hit, one record per camera sample over the sampler
+ * extent, laid out [((y - y_start) * width + (x - x_start)) * spp + i].  out_* may be NULL.
+ * out_samples: 5 floats per sample (image_x, image_y, lens_u, lens_v, time).                    */
+int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam,
+                          const pbrtb200_sampler* smp, pbrtb200_hit16* out_hits,
+                          float* out_samples, pbrtb200_ray32* out_rays, int is_device,
+                          pbrtb200_stats* stats);
+
+/* Per-ray traversal counters of the last trace/primary call are not kept on device; the
+ * algorithmic node/primitive counts used by the roofline come from the CPU oracle.              */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBRTB200_H */

@@ -1,0 +1,89 @@
+/*
+ * pbrtb200_host.h — host-side mirror of the pbrt_rust constructors that sit ABOVE the drop-in
+ * boundary (Scene / Primitive::bvh / Camera::perspective / Film::image / Sampler::stratified).
+ *
+ * In a real integration these objects stay in the Rust crate and only the flatten shim talks to
+ * pbrtb200.h.  The Rust toolchain is absent from this image, so this C/C++
+ * stand-in plays the crate's part for tests and benchmarks: same constructor names, argument
+ * meaning and error behaviour, and — for the BVH — the same tree, node for node, built by an
+ * in-place builder (the reference moves Vecs at every level, bvh.rs:189-258).
+ *
+ * Everything here is plain host code (no CUDA); it never calls the CPU oracle.
+ */
+#ifndef PBRTB200_HOST_H
+#define PBRTB200_HOST_H
+
+#include "pbrtb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Transform (src/transform/transform.rs); matrices are row-major float[16] pairs (m, m_inv) */
+void pbh_translate(const float v[3], float m[16], float minv[16]);
+void pbh_scale(float x, float y, float z, float m[16], float minv[16]);
+void pbh_rotate_x(float deg, float m[16], float minv[16]);
+void pbh_rotate_y(float deg, float m[16], float minv[16]);
+void pbh_rotate_z(float deg, float m[16], float minv[16]);
+void pbh_mul(const float am[16], const float aminv[16], const float bm[16], const float bminv[16],
+             float m[16], float minv[16]);
+int pbh_invert(const float m[16], float out[16]); /* PBRTB200_ESINGULAR on "Singular matrix!" */
+int pbh_look_at(const float pos[3], const float look[3], const float up[3], float m[16],
+                float minv[16]);
+
+/* ---- Scene description ---------------------------------------------------------------------- */
+typedef struct pbh_scene pbh_scene;
+pbh_scene* pbh_scene_new(void);
+void pbh_scene_free(pbh_scene* s);
+const char* pbh_last_error(const pbh_scene* s);
+
+/* texture constructors (src/texture/*): return the texture id */
+int pbh_texture_constant(pbh_scene* s, const float rgb[3]);
+int pbh_texture_checkerboard(pbh_scene* s, int map_kind, const float map[8], int tex1, int tex2,
+                             int antialiased);
+int pbh_texture_uv(pbh_scene* s, int map_kind, const float map[8]);
+/* Material::matte(kd, sigma) / Material::plastic(kd, ks, roughness) (src/material/mod.rs:88-99) */
+int pbh_material_matte(pbh_scene* s, int kd, int sigma);
+int pbh_material_plastic(pbh_scene* s, int kd, int ks, int roughness);
+/* PointLight::new / SpotLight::new (src/light/point.rs:21-25, spot.rs:24-35); area = extension */
+int pbh_light_point(pbh_scene* s, const float l2w[16], const float l2w_inv[16], const float I[3]);
+int pbh_light_spot(pbh_scene* s, const float l2w[16], const float l2w_inv[16], const float I[3],
+                   float width_deg, float falloff_deg);
+int pbh_light_area(pbh_scene* s, const float L[3], int num_samples);
+/* Primitive::geometric(Shape::triangle_mesh(o2w, w2o, ro, vi, P, N, S, uv, None), material)
+ * N, S, UV may be NULL.  area_light = id from pbh_light_area or -1.  Returns the object ordinal. */
+int pbh_add_triangle_mesh(pbh_scene* s, const float o2w[16], const float o2w_inv[16], int ro,
+                          const uint32_t* vi, uint64_t n_vi, const float* P, uint64_t n_p,
+                          const float* N, const float* S, const float* UV, int material,
+                          int area_light);
+/* Primitive::geometric(Shape::sphere(o2w, w2o, ro, rad, z0, z1, phi_max_deg), material) */
+int pbh_add_sphere(pbh_scene* s, const float o2w[16], const float o2w_inv[16], int ro, float rad,
+                   float z0, float z1, float phi_max_deg, int material);
+/* Primitive::bvh(prims, max_prims, sm) with sm in {"sah","middle","equal"}; unknown -> "sah" with
+ * a warning, as BVHAccelerator::new does (bvh.rs:340-348).  Then flattens. */
+int pbh_build_bvh(pbh_scene* s, uint32_t max_prims, const char* split_method);
+/* The flatten shim's output; pointers are owned by `s` and live until it is freed / rebuilt. */
+const pbrtb200_scene* pbh_flat_scene(const pbh_scene* s);
+/* per ordered primitive i: (kind 0 tri / 1 sphere, source object ordinal, index within object) */
+void pbh_prim_order(const pbh_scene* s, uint32_t* out3);
+
+/* ---- Camera / Film / Sampler / Renderer ----------------------------------------------------- */
+/* Camera::perspective(cam2world, screen_window, sopen, sclose, lensr, focald, fov, film) */
+int pbh_camera_perspective(const float cam2world[16], const float screen_window[4], float sopen,
+                           float sclose, float lensr, float focald, float fov_deg, int x_res,
+                           int y_res, pbrtb200_camera* out);
+/* Film::image(xres, yres, filter, crop, ..); filter_type 0 box(mean) 1 triangle 2 gaussian(p0=alpha)
+ * 3 mitchell(p0=b,p1=c) 4 lanczos(p0=tau) (src/filter.rs) */
+int pbh_film_image(int x_res, int y_res, int filter_type, float xw, float yw, float p0, float p1,
+                   const float crop[4], pbrtb200_film* out);
+void pbh_film_sample_extent(const pbrtb200_film* f, int32_t out[4]); /* film.rs:271-289 */
+/* SamplerRenderer::new's task count (sampler_renderer.rs:41-44) */
+uint32_t pbh_num_tasks(uint32_t num_cpus, uint32_t num_pixels);
+/* Film::write_image's pixel conversion as intended (film.rs:331-346):
+ * rgb = max(0, xyz_to_rgb(xyz) / weight_sum) */
+void pbh_film_to_rgb(const float* xyzw, uint64_t n_pixels, float* rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBRTB200_HOST_H */

@@ -1,0 +1,577 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+//
+// extern "C" surface of the CPU oracle, loaded with ctypes by tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs (nothing else may load it).
+#include <chrono>
+#include <cstdio>
+#include <string>
+
+#include "render.hpp"
+
+using namespace orc;
+
+namespace {
+thread_local std::string g_err;
+Transform xf_from(const float* m, const float* minv) {
+  Transform t;
+  std::memcpy(t.m.m, m, 64);
+  std::memcpy(t.m_inv.m, minv, 64);
+  return t;
+}
+template <class F>
+int guarded(F f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+}  // namespace
+
+struct OrcScene {
+  Scene sc;
+  bool built = false;
+};
+
+// Plain-data render description (mirrors the arguments of Camera::perspective, Film::image,
+// Sampler::stratified / low_discrepancy and SamplerRenderer::new in the reference).
+struct OrcRenderConfig {
+  float cam_to_world[16];
+  float cam_to_world_inv[16];
+  float screen_window[4];
+  float sopen, sclose, lensr, focald, fov;
+  int32_t x_res, y_res;
+  float crop[4];
+  int32_t filter_type;
+  float filter_xw, filter_yw, filter_p0, filter_p1;
+  int32_t sampler_kind, xs, ys, jitter;
+  int32_t num_tasks;  // 0 -> num_tasks_for(num_cpus, x_res*y_res)
+  int32_t num_cpus;
+  int32_t mode;  // 0 default, 1 strict
+  int32_t n_threads;
+  int32_t count_traversal;
+  int32_t primary_only;
+};
+
+struct OrcRenderStats {
+  uint64_t camera_rays, camera_hits, shadow_rays;
+  uint64_t nodes_visited, tris_tested, spheres_tested;
+  uint64_t sh_nodes_visited, sh_tris_tested, sh_spheres_tested;
+  uint64_t nan_samples;
+  double seconds;
+  int32_t num_tasks;
+  int32_t sample_ext[4];
+  int32_t pixel_ext[4];
+};
+
+extern "C" {
+
+const char* orc_last_error() { return g_err.c_str(); }
+
+OrcScene* orc_scene_new() { return new OrcScene(); }
+void orc_scene_free(OrcScene* s) { delete s; }
+
+// Shape::triangle_mesh + Primitive::geometric[_area_light]
+int orc_add_mesh(OrcScene* s, const float* o2w, const float* o2w_inv, int ro, const uint32_t* idx,
+                 uint64_t n_idx, const float* P, uint64_t n_p, const float* N, const float* S,
+                 const float* UV, uint32_t material, int32_t area_light) {
+  return guarded([&] {
+    Transform t = xf_from(o2w, o2w_inv);
+    auto m = std::make_unique<Mesh>(t, t.inverse(), ro != 0, idx, n_idx, P, n_p, N, S, UV);
+    m->material = material;
+    m->area_light = area_light;
+    s->sc.geom.add_mesh(std::move(m));
+  });
+}
+// Shape::sphere(o2w, w2o, ro, rad, z0, z1, pm)
+int orc_add_sphere(OrcScene* s, const float* o2w, const float* o2w_inv, int ro, float rad,
+                   float z0, float z1, float pm, uint32_t material) {
+  return guarded([&] {
+    Transform t = xf_from(o2w, o2w_inv);
+    auto sp = std::make_unique<Sphere>(t, t.inverse(), ro != 0, rad, z0, z1, pm);
+    sp->material = material;
+    s->sc.geom.add_sphere(std::move(sp));
+  });
+}
+int orc_add_texture(OrcScene* s, int kind, const float* value, int map_kind, const float* map8,
+                    int tex1, int tex2, int aa) {
+  Texture t;
+  t.kind = kind;
+  t.value = RGB(value[0], value[1], value[2]);
+  t.mapping.kind = map_kind;
+  if (map_kind == 0) {
+    t.mapping.su = map8[0];
+    t.mapping.sv = map8[1];
+    t.mapping.du = map8[2];
+    t.mapping.dv = map8[3];
+  } else {
+    t.mapping.vs = V3(map8[0], map8[1], map8[2]);
+    t.mapping.vt = V3(map8[3], map8[4], map8[5]);
+    t.mapping.du = map8[6];
+    t.mapping.dv = map8[7];
+  }
+  t.tex1 = tex1;
+  t.tex2 = tex2;
+  t.aa = aa;
+  s->sc.textures.t.push_back(t);
+  return (int)s->sc.textures.t.size() - 1;
+}
+int orc_add_material(OrcScene* s, int kind, int kd, int sigma, int ks, int roughness) {
+  Material m;
+  m.kind = kind;
+  m.kd = kd;
+  m.sigma = sigma;
+  m.ks = ks;
+  m.roughness = roughness;
+  s->sc.materials.push_back(m);
+  return (int)s->sc.materials.size() - 1;
+}
+// PointLight::new(l2w, intensity) / SpotLight::new(l2w, intensity, width, fall)
+int orc_add_point_light(OrcScene* s, const float* l2w, const float* l2w_inv, const float* I) {
+  Transform t = xf_from(l2w, l2w_inv);
+  Light l;
+  l.kind = 0;
+  l.pos = t.pt(V3());
+  l.intensity = RGB(I[0], I[1], I[2]);
+  l.world_to_light = t.inverse();
+  s->sc.lights.push_back(l);
+  return (int)s->sc.lights.size() - 1;
+}
+int orc_add_spot_light(OrcScene* s, const float* l2w, const float* l2w_inv, const float* I,
+                       float width, float fall) {
+  Transform t = xf_from(l2w, l2w_inv);
+  Light l;
+  l.kind = 1;
+  l.pos = t.pt(V3());
+  l.intensity = RGB(I[0], I[1], I[2]);
+  l.world_to_light = t.inverse();
+  l.cos_total_width = std::cos(as_radians(width));
+  l.cos_falloff_start = std::cos(as_radians(fall));
+  s->sc.lights.push_back(l);
+  return (int)s->sc.lights.size() - 1;
+}
+// Oracle-defined diffuse area light; meshes added with area_light == the returned id emit.
+int orc_add_area_light(OrcScene* s, const float* L, int num_samples) {
+  Light l;
+  l.kind = 2;
+  l.intensity = RGB(L[0], L[1], L[2]);
+  l.num_samples = num_samples;
+  s->sc.lights.push_back(l);
+  return (int)s->sc.lights.size() - 1;
+}
+
+// BVHAccelerator::new(prims, max_prims, sm) ; sm: 0 middle, 1 equal, 2 sah
+int orc_build(OrcScene* s, uint32_t max_prims, int split_method) {
+  return guarded([&] {
+    Scene& sc = s->sc;
+    sc.bvh.build(sc.geom.refined, max_prims, (SplitMethod)split_method);
+    // collect emissive triangles per area light, in BVH-input (refined) order
+    for (Light& l : sc.lights) {
+      l.tris.clear();
+      l.cdf.clear();
+    }
+    for (const Prim& p : sc.geom.refined) {
+      if (p.kind != Prim::TRI || p.mesh->area_light < 0) continue;
+      Light& l = sc.lights.at((size_t)p.mesh->area_light);
+      if (l.kind != 2) throw std::runtime_error("mesh refers to a non-area light");
+      Light::Tri t;
+      t.p1 = p.mesh->p[p.v[0]];
+      t.p2 = p.mesh->p[p.v[1]];
+      t.p3 = p.mesh->p[p.v[2]];
+      Ray dummy(V3(), V3(0, 0, 1), 0.f);
+      DiffGeom dg = tri_dg(p, dummy, 0.f, 0.f, 0.f);
+      t.nn = dg.nn;
+      t.area = 0.5f * length(cross(t.p2 - t.p1, t.p3 - t.p1));  // mesh.rs:100-103
+      l.tris.push_back(t);
+    }
+    for (Light& l : sc.lights) {
+      if (l.kind != 2) continue;
+      if (l.tris.empty()) throw std::runtime_error("area light without emissive triangles");
+      float total = 0.f;
+      for (const auto& t : l.tris) total += t.area;
+      l.total_area = total;
+      l.cdf.resize(l.tris.size() + 1);
+      l.cdf[0] = 0.f;
+      float acc = 0.f;
+      for (size_t i = 0; i < l.tris.size(); ++i) {
+        acc += l.tris[i].area;
+        l.cdf[i + 1] = acc / total;
+      }
+      l.cdf.back() = 1.0f;
+    }
+    s->built = true;
+  });
+}
+
+uint64_t orc_num_nodes(const OrcScene* s) { return s->sc.bvh.nodes.size(); }
+uint64_t orc_num_prims(const OrcScene* s) { return s->sc.bvh.prims.size(); }
+// bounds: 6 floats/node ; meta: (offset, count_or_axis, is_leaf) u32 triples
+void orc_get_nodes(const OrcScene* s, float* bounds, uint32_t* meta) {
+  const auto& n = s->sc.bvh.nodes;
+  for (size_t i = 0; i < n.size(); ++i) {
+    bounds[6 * i + 0] = n[i].bounds.p_min.x;
+    bounds[6 * i + 1] = n[i].bounds.p_min.y;
+    bounds[6 * i + 2] = n[i].bounds.p_min.z;
+    bounds[6 * i + 3] = n[i].bounds.p_max.x;
+    bounds[6 * i + 4] = n[i].bounds.p_max.y;
+    bounds[6 * i + 5] = n[i].bounds.p_max.z;
+    meta[3 * i + 0] = n[i].offset;
+    meta[3 * i + 1] = n[i].count;
+    meta[3 * i + 2] = n[i].leaf ? 1u : 0u;
+  }
+}
+// per ordered primitive: (kind, source_object, source_index)
+void orc_get_prim_order(const OrcScene* s, uint32_t* out) {
+  const auto& p = s->sc.bvh.prims;
+  for (size_t i = 0; i < p.size(); ++i) {
+    out[3 * i + 0] = (uint32_t)p[i].kind;
+    out[3 * i + 1] = p[i].source_object;
+    out[3 * i + 2] = p[i].source_index;
+  }
+}
+
+// rays: 8 floats each (ox,oy,oz,mint, dx,dy,dz,maxt).  hits: (prim u32, t, b1, b2) as 4x u32/f32.
+// counters (optional): 3 u32 per ray (nodes, tris, spheres).  maxt_out (optional): final ray.maxt.
+int orc_trace_closest(const OrcScene* s, const float* rays, uint64_t n, uint32_t* hit_prim,
+                      float* hit_tbb, uint32_t* counters, int n_threads) {
+  return guarded([&] {
+    auto work = [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) {
+        const float* r = rays + 8 * i;
+        Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3]);
+        ray.maxt = r[7];
+        Hit h;
+        TraceCounters tc;
+        bool f = s->sc.bvh.intersect(ray, &h, counters ? &tc : nullptr);
+        hit_prim[i] = f ? h.prim : 0xFFFFFFFFu;
+        hit_tbb[3 * i + 0] = f ? h.t : 0.f;
+        hit_tbb[3 * i + 1] = f ? h.b1 : 0.f;
+        hit_tbb[3 * i + 2] = f ? h.b2 : 0.f;
+        if (counters) {
+          counters[3 * i + 0] = (uint32_t)tc.nodes_visited;
+          counters[3 * i + 1] = (uint32_t)tc.tris_tested;
+          counters[3 * i + 2] = (uint32_t)tc.spheres_tested;
+        }
+      }
+    };
+    int nt = std::max(1, n_threads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+    for (auto& t : th) t.join();
+  });
+}
+// occluded[i] = 1 iff any hit in [mint, maxt]  (== Scene::intersect_p)
+int orc_trace_any(const OrcScene* s, const float* rays, uint64_t n, uint8_t* occluded,
+                  uint32_t* counters, int early_exit, int n_threads) {
+  return guarded([&] {
+    auto work = [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) {
+        const float* r = rays + 8 * i;
+        Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3]);
+        ray.maxt = r[7];
+        TraceCounters tc;
+        occluded[i] = s->sc.bvh.intersect_p(ray, early_exit != 0, counters ? &tc : nullptr) ? 1 : 0;
+        if (counters) {
+          counters[3 * i + 0] = (uint32_t)tc.nodes_visited;
+          counters[3 * i + 1] = (uint32_t)tc.tris_tested;
+          counters[3 * i + 2] = (uint32_t)tc.spheres_tested;
+        }
+      }
+    };
+    int nt = std::max(1, n_threads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+    for (auto& t : th) t.join();
+  });
+}
+
+static RenderConfig make_config(const OrcScene* s, const OrcRenderConfig* c) {
+  RenderConfig cfg;
+  Transform c2w = xf_from(c->cam_to_world, c->cam_to_world_inv);
+  cfg.camera = PerspectiveCamera(c2w, c->screen_window, c->sopen, c->sclose, c->lensr, c->focald,
+                                 c->fov, c->x_res, c->y_res);
+  Filter f(c->filter_type, c->filter_xw, c->filter_yw, c->filter_p0, c->filter_p1);
+  cfg.film = Film(c->x_res, c->y_res, f, c->crop);
+  cfg.sampler.kind = c->sampler_kind;
+  cfg.film.sample_extent(cfg.sampler.ext);  // Sampler built from film.get_sample_extent()
+  cfg.sampler.xs = c->xs;
+  cfg.sampler.ys = c->ys;
+  cfg.sampler.jitter = c->jitter != 0;
+  cfg.sampler.sopen = c->sopen;
+  cfg.sampler.sclose = c->sclose;
+  cfg.sampler.light_samples = s ? s->sc.light_sample_pairs() : 0;
+  cfg.num_tasks = c->num_tasks > 0
+                      ? (uint32_t)c->num_tasks
+                      : num_tasks_for((uint32_t)std::max(1, c->num_cpus),
+                                      (uint32_t)(c->x_res * c->y_res));
+  cfg.mode = c->mode;
+  cfg.n_threads = c->n_threads;
+  cfg.count_traversal = c->count_traversal != 0;
+  cfg.primary_only = c->primary_only != 0;
+  return cfg;
+}
+
+// Fills stats->sample_ext / pixel_ext / num_tasks without rendering.
+int orc_render_layout(const OrcRenderConfig* c, OrcRenderStats* stats) {
+  return guarded([&] {
+    RenderConfig cfg = make_config(nullptr, c);
+    std::memset(stats, 0, sizeof *stats);
+    stats->num_tasks = (int32_t)cfg.num_tasks;
+    for (int i = 0; i < 4; ++i) stats->sample_ext[i] = cfg.sampler.ext[i];
+    cfg.film.pixel_extent(stats->pixel_ext);
+  });
+}
+
+// film_xyzw: 4 floats per film pixel (pixel extent, row-major): xyz sums + weight_sum.
+// rgb (optional): 3 floats per pixel, D6 conversion.  hit_ids/hit_ts (optional): per camera sample
+// over the sampler extent.
+int orc_render(OrcScene* s, const OrcRenderConfig* c, float* film_xyzw, float* rgb,
+               uint32_t* hit_ids, float* hit_ts, OrcRenderStats* stats) {
+  return guarded([&] {
+    if (!s->built) throw std::runtime_error("scene not built");
+    RenderConfig cfg = make_config(s, c);
+    RenderStats st;
+    auto t0 = std::chrono::steady_clock::now();
+    render(s->sc, cfg, &st, hit_ids, hit_ts);
+    auto t1 = std::chrono::steady_clock::now();
+    if (film_xyzw)
+      for (size_t i = 0; i < cfg.film.pixels.size(); ++i) {
+        film_xyzw[4 * i + 0] = cfg.film.pixels[i].xyz[0];
+        film_xyzw[4 * i + 1] = cfg.film.pixels[i].xyz[1];
+        film_xyzw[4 * i + 2] = cfg.film.pixels[i].xyz[2];
+        film_xyzw[4 * i + 3] = cfg.film.pixels[i].weight_sum;
+      }
+    if (rgb) cfg.film.to_rgb(rgb);
+    if (stats) {
+      std::memset(stats, 0, sizeof *stats);
+      stats->camera_rays = st.camera_rays;
+      stats->camera_hits = st.camera_hits;
+      stats->shadow_rays = st.shadow_rays;
+      stats->nodes_visited = st.nodes_visited;
+      stats->tris_tested = st.tris_tested;
+      stats->spheres_tested = st.spheres_tested;
+      stats->sh_nodes_visited = st.sh_nodes_visited;
+      stats->sh_tris_tested = st.sh_tris_tested;
+      stats->sh_spheres_tested = st.sh_spheres_tested;
+      stats->nan_samples = st.nan_samples;
+      stats->seconds = std::chrono::duration<double>(t1 - t0).count();
+      stats->num_tasks = (int32_t)cfg.num_tasks;
+      for (int i = 0; i < 4; ++i) stats->sample_ext[i] = cfg.sampler.ext[i];
+      cfg.film.pixel_extent(stats->pixel_ext);
+    }
+    if (st.nan_samples) throw std::runtime_error("Invalid radiance value!");  // D4
+  });
+}
+void orc_set_strict_flags(OrcScene* s, int on) { s->sc.strict_flags = on != 0; }
+
+// Camera samples + rays for the pixels of one row range (unit-level checks of A1-A3).
+// out_cs: 5 floats per sample; out_rays: 8 floats per sample (o, mint, d, maxt);
+// out_diff (optional): 12 floats (rx_origin, ry_origin, rx_dir, ry_dir) after scale_differentials.
+int orc_camera_samples(const OrcRenderConfig* c, int light_pairs, int x0, int x1, int y0, int y1,
+                       float* out_cs, float* out_rays, float* out_diff, float* out_light_u) {
+  return guarded([&] {
+    RenderConfig cfg = make_config(nullptr, c);
+    cfg.sampler.light_samples = light_pairs;
+    const SamplerDesc& sd = cfg.sampler;
+    auto tw = task_windows(sd, cfg.num_tasks);
+    size_t spp = sd.spp(), W = sd.words_per_pixel();
+    std::vector<CameraSample> cs;
+    std::vector<float> lu;
+    size_t k = 0;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        const TaskWindow* w = nullptr;
+        for (auto& t : tw)
+          if (!t.empty && x >= t.ext[0] && x < t.ext[1] && y >= t.ext[2] && y < t.ext[3]) w = &t;
+        if (!w) throw std::runtime_error("pixel outside every task window");
+        RNG rng = RNG::from_key(w->key);
+        size_t pk = (size_t)(y - w->ext[2]) * (size_t)(w->ext[1] - w->ext[0]) + (size_t)(x - w->ext[0]);
+        rng.seek(pk * W);
+        pixel_samples(sd, x, y, rng, cs, lu);
+        if (rng.tell() != (pk + 1) * W) throw std::runtime_error("words_per_pixel mismatch");
+        for (size_t i = 0; i < spp; ++i, ++k) {
+          float* o = out_cs + 5 * k;
+          o[0] = cs[i].image_x;
+          o[1] = cs[i].image_y;
+          o[2] = cs[i].lens_u;
+          o[3] = cs[i].lens_v;
+          o[4] = cs[i].time;
+          RayDifferential rd = cfg.camera.generate_ray_differential(cs[i]);
+          rd.scale_differentials(1.0f / std::sqrt((float)spp));
+          if (out_rays) {
+            float* r = out_rays + 8 * k;
+            r[0] = rd.ray.o.x; r[1] = rd.ray.o.y; r[2] = rd.ray.o.z; r[3] = rd.ray.mint;
+            r[4] = rd.ray.d.x; r[5] = rd.ray.d.y; r[6] = rd.ray.d.z; r[7] = rd.ray.maxt;
+          }
+          if (out_diff) {
+            float* d = out_diff + 12 * k;
+            const V3* v[4] = {&rd.rx_origin, &rd.ry_origin, &rd.rx_dir, &rd.ry_dir};
+            for (int q = 0; q < 4; ++q) {
+              d[3 * q] = v[q]->x; d[3 * q + 1] = v[q]->y; d[3 * q + 2] = v[q]->z;
+            }
+          }
+          if (out_light_u)
+            for (int q = 0; q < 2 * light_pairs; ++q)
+              out_light_u[(size_t)(2 * light_pairs) * k + q] = lu[(size_t)(2 * light_pairs) * i + q];
+        }
+      }
+  });
+}
+
+// ---- small known-answer hooks (each mirrors one reference function) ----
+int orc_quadratic(float a, float b, float c, float* t0, float* t1) {
+  return quadratic(a, b, c, t0, t1) ? 1 : 0;
+}
+int orc_solve_2x2(const float* a4, const float* b2, float* x) {
+  float a[2][2] = {{a4[0], a4[1]}, {a4[2], a4[3]}};
+  return solve_linear_system_2x2(a, b2, &x[0], &x[1]) ? 1 : 0;
+}
+void orc_partition_by_i32(int32_t* v, uint64_t n) {
+  partition_by(
+      0, (size_t)n, [&](size_t i) { return v[i]; }, [&](size_t i, size_t j) { std::swap(v[i], v[j]); });
+}
+void orc_get_crop_window(uint64_t num, uint64_t count, float aspect, float* out4) {
+  get_crop_window(num, count, aspect, out4);
+}
+void orc_compute_sub_window(const int32_t* ext4, uint64_t num, uint64_t count, int32_t* out4) {
+  int e[4] = {ext4[0], ext4[1], ext4[2], ext4[3]}, o[4];
+  compute_sub_window(e, num, count, o);
+  for (int i = 0; i < 4; ++i) out4[i] = o[i];
+}
+uint32_t orc_num_tasks_for(uint32_t ncpu, uint32_t npix) { return num_tasks_for(ncpu, npix); }
+// BBox::intersect: box = 6 floats, ray = 8 floats. returns 1 and (t0,t1) on hit.
+int orc_bbox_intersect(const float* box, const float* r, float* t01) {
+  BBox b(V3(box[0], box[1], box[2]), V3(box[3], box[4], box[5]));
+  Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3]);
+  ray.maxt = r[7];
+  return b.intersect(ray, &t01[0], &t01[1]) ? 1 : 0;
+}
+void orc_bbox_props(const float* box, float* area, float* volume, int32_t* max_extent,
+                    int32_t* empty) {
+  BBox b(V3(box[0], box[1], box[2]), V3(box[3], box[4], box[5]));
+  *area = b.surface_area();
+  *volume = b.volume();
+  *max_extent = b.max_extent();
+  *empty = b.empty() ? 1 : 0;
+}
+int orc_tri_intersect(const float* p9, const float* r, float* tbb) {
+  Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3]);
+  ray.maxt = r[7];
+  return tri_intersection_point(V3(p9[0], p9[1], p9[2]), V3(p9[3], p9[4], p9[5]),
+                                V3(p9[6], p9[7], p9[8]), ray, &tbb[0], &tbb[1], &tbb[2])
+             ? 1
+             : 0;
+}
+// Sphere::intersect: returns 1 + (t_hit, ray_epsilon, phi) and the dg (p,nn,u,v,dpdu,dpdv = 14 f)
+int orc_sphere_intersect(const float* o2w, const float* o2w_inv, int ro, float rad, float z0,
+                         float z1, float pm, const float* r, float* out3, float* dg14) {
+  Transform t = xf_from(o2w, o2w_inv);
+  Sphere s(t, t.inverse(), ro != 0, rad, z0, z1, pm);
+  Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3]);
+  ray.maxt = r[7];
+  Ray oray = xf_ray(s.base.w2o, ray);
+  float th, phi;
+  if (!s.intersection_point(oray, &th, &phi)) return 0;
+  out3[0] = th;
+  out3[1] = th * 5e-4f;
+  out3[2] = phi;
+  if (dg14) {
+    DiffGeom dg = sphere_dg(s, ray, th, phi);
+    float v[14] = {dg.p.x, dg.p.y, dg.p.z, dg.nn.x, dg.nn.y, dg.nn.z, dg.u, dg.v,
+                   dg.dpdu.x, dg.dpdu.y, dg.dpdu.z, dg.dpdv.x, dg.dpdv.y, dg.dpdv.z};
+    std::memcpy(dg14, v, sizeof v);
+  }
+  return 1;
+}
+void orc_sphere_props(float rad, float z0, float z1, float pm, float* out6) {
+  Sphere s(Transform(), Transform(), false, rad, z0, z1, pm);
+  out6[0] = s.z_min;
+  out6[1] = s.z_max;
+  out6[2] = s.theta_min;
+  out6[3] = s.theta_max;
+  out6[4] = s.phi_max;
+  out6[5] = s.phi_max * s.radius * (s.z_max - s.z_min);  // area, sphere.rs:119-121
+}
+int orc_invert(const float* m16, float* out16) {
+  return guarded([&] {
+    M44 a;
+    std::memcpy(a.m, m16, 64);
+    M44 r = invert(a);
+    std::memcpy(out16, r.m, 64);
+  });
+}
+void orc_look_at(const float* pos, const float* look, const float* up, float* m16, float* minv16) {
+  Transform t = Transform::look_at(V3(pos[0], pos[1], pos[2]), V3(look[0], look[1], look[2]),
+                                   V3(up[0], up[1], up[2]));
+  std::memcpy(m16, t.m.m, 64);
+  std::memcpy(minv16, t.m_inv.m, 64);
+}
+// Projection::new matrices for a perspective camera: raster_to_camera (m, m_inv), dx, dy.
+int orc_perspective(const OrcRenderConfig* c, float* r2c16, float* r2c_inv16, float* dxdy6) {
+  return guarded([&] {
+    RenderConfig cfg = make_config(nullptr, c);
+    std::memcpy(r2c16, cfg.camera.raster_to_camera.m.m, 64);
+    std::memcpy(r2c_inv16, cfg.camera.raster_to_camera.m_inv.m, 64);
+    dxdy6[0] = cfg.camera.dx_camera.x;
+    dxdy6[1] = cfg.camera.dx_camera.y;
+    dxdy6[2] = cfg.camera.dx_camera.z;
+    dxdy6[3] = cfg.camera.dy_camera.x;
+    dxdy6[4] = cfg.camera.dy_camera.y;
+    dxdy6[5] = cfg.camera.dy_camera.z;
+  });
+}
+float orc_filter_eval(int type, float xw, float yw, float p0, float p1, float x, float y) {
+  return Filter(type, xw, yw, p0, p1).evaluate(x, y);
+}
+void orc_filter_table(int type, float xw, float yw, float p0, float p1, float* out256) {
+  float crop[4] = {0, 1, 0, 1};
+  Film f(4, 4, Filter(type, xw, yw, p0, p1), crop);
+  std::memcpy(out256, f.table, sizeof f.table);
+}
+void orc_film_extents(int xres, int yres, float xw, float yw, const float* crop, int32_t* sample4,
+                      int32_t* pixel4) {
+  Film f(xres, yres, Filter(0, xw, yw, 0, 0), crop);
+  int a[4], b[4];
+  f.sample_extent(a);
+  f.pixel_extent(b);
+  for (int i = 0; i < 4; ++i) {
+    sample4[i] = a[i];
+    pixel4[i] = b[i];
+  }
+}
+void orc_chacha_block(const uint32_t* in16, int rounds, uint32_t* out16) {
+  chacha_block(in16, rounds, out16);
+}
+void orc_seed_from_u64(uint64_t seed, uint32_t* key8) { seed_from_u64(seed, key8); }
+// first n stream words of StdRng::from_seed(key)
+void orc_stream_words(const uint32_t* key8, uint64_t start, uint64_t n, uint32_t* out) {
+  RNG r = RNG::from_key(key8);
+  r.seek(start);
+  for (uint64_t i = 0; i < n; ++i) out[i] = r.s.next_u32();
+}
+void orc_rng_floats(uint64_t seed, uint64_t n, float* out) {
+  RNG r(seed);
+  for (uint64_t i = 0; i < n; ++i) out[i] = r.random_float();
+}
+void orc_rng_shuffle(uint64_t seed, float* v, uint64_t len, uint64_t dims) {
+  RNG r(seed);
+  r.shuffle(v, len, dims);
+}
+void orc_stratified_2d(uint64_t seed, uint64_t nx, uint64_t ny, int jitter, float* out) {
+  RNG r(seed);
+  stratified_sample_2d(out, nx, ny, r, jitter != 0);
+}
+void orc_stratified_1d(uint64_t seed, uint64_t n, int jitter, float* out) {
+  RNG r(seed);
+  stratified_sample_1d(out, n, r, jitter != 0);
+}
+void orc_latin_hypercube(uint64_t seed, uint64_t num, uint64_t dim, float* out) {
+  RNG r(seed);
+  latin_hypercube(out, num, dim, r);
+}
+float orc_van_der_corput(uint32_t n, uint32_t scramble) { return van_der_corput(n, scramble); }
+float orc_sobol2(uint32_t n, uint32_t scramble) { return sobol2(n, scramble); }
+
+}  // extern "C"

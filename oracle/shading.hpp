@@ -1,0 +1,563 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+//
+// Surface-interaction construction, textures, matte/plastic BSDFs, lights and the Whitted light
+// loop of pbrt_rust, restated line-faithfully, with the SURVEY §0.2 decisions (D2, D3, D7, D8, D9,
+// D10, D11, D17).  Citations are relative to the reference root.
+#pragma once
+#include "accel.hpp"
+#include "camera.hpp"
+
+namespace orc {
+
+// spectrum.rs — RGB variant only (Spectrum::from(f32) -> RGB, spectrum.rs:495-499).
+struct RGB {
+  float c[3] = {0.f, 0.f, 0.f};
+  RGB() = default;
+  explicit RGB(float f) { c[0] = c[1] = c[2] = f; }
+  RGB(float r, float g, float b) {
+    c[0] = r;
+    c[1] = g;
+    c[2] = b;
+  }
+  bool is_black() const { return c[0] == 0.0f && c[1] == 0.0f && c[2] == 0.0f; }  // :425
+  bool has_nans() const { return std::isnan(c[0]) || std::isnan(c[1]) || std::isnan(c[2]); }
+  RGB clamp(float a, float b) const {
+    return RGB(rclamp(c[0], a, b), rclamp(c[1], a, b), rclamp(c[2], a, b));
+  }
+};
+inline RGB operator+(const RGB& a, const RGB& b) {
+  return RGB(a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2]);
+}
+inline RGB operator-(const RGB& a, const RGB& b) {
+  return RGB(a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2]);
+}
+inline RGB operator*(const RGB& a, const RGB& b) {
+  return RGB(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2]);
+}
+inline RGB operator/(const RGB& a, const RGB& b) {
+  return RGB(a.c[0] / b.c[0], a.c[1] / b.c[1], a.c[2] / b.c[2]);
+}
+inline RGB operator*(const RGB& a, float s) { return RGB(a.c[0] * s, a.c[1] * s, a.c[2] * s); }
+inline RGB operator*(float s, const RGB& a) { return a * s; }
+inline RGB operator/(const RGB& a, float s) { return RGB(a.c[0] / s, a.c[1] / s, a.c[2] / s); }
+
+// ---------------------------------------------------------------------------------------------
+// Textures (texture/mod.rs:52-66, checkerboard.rs:24-95, uv.rs:20-26, mapping2d.rs:49-77,175-210)
+struct Mapping2D {
+  int kind = 0;  // 0 = UVMapping2D(su,sv,du,dv) ; 1 = PlanarMapping2D(vs,vt,ds,dt)
+  float su = 1.f, sv = 1.f, du = 0.f, dv = 0.f;
+  V3 vs{1, 0, 0}, vt{0, 1, 0};
+  void map(const DiffGeom& dg, float o[6]) const {  // (s, t, dsdx, dtdx, dsdy, dtdy)
+    if (kind == 0) {
+      o[0] = su * dg.u + du;
+      o[1] = sv * dg.v + dv;
+      o[2] = su * dg.dudx;
+      o[3] = sv * dg.dvdx;
+      o[4] = su * dg.dudy;
+      o[5] = sv * dg.dvdy;
+    } else {
+      V3 vec = dg.p;
+      o[0] = du + dot(vec, vs);
+      o[1] = dv + dot(vec, vt);
+      o[2] = dot(vs, dg.dpdx);
+      o[3] = dot(vt, dg.dpdx);
+      o[4] = dot(vs, dg.dpdy);
+      o[5] = dot(vt, dg.dpdy);
+    }
+  }
+};
+struct Texture {
+  int kind = 0;  // 0 = Constant, 1 = Checkerboard2D, 2 = UV
+  RGB value;     // Constant (float textures use c[0])
+  Mapping2D mapping;
+  int tex1 = 0, tex2 = 0;  // Checkerboard children (indices)
+  int aa = 0;              // 0 = NONE, 1 = CLOSEDFORM
+};
+struct TextureTable {
+  std::vector<Texture> t;
+  RGB eval(int id, const DiffGeom& dg) const {
+    const Texture& tx = t[(size_t)id];
+    switch (tx.kind) {
+      case 0:
+        return tx.value;
+      case 2: {
+        float m[6];
+        tx.mapping.map(dg, m);
+        return RGB(m[0] - std::floor(m[0]), m[1] - std::floor(m[1]), 0.0f);
+      }
+      default: {
+        float m[6];
+        tx.mapping.map(dg, m);
+        float s = m[0], t_ = m[1];
+        auto point_sample = [&]() {
+          int32_t a = f2i(std::floor(s)), b = f2i(std::floor(t_));
+          int32_t sum = (int32_t)((uint32_t)a + (uint32_t)b);
+          return (sum % 2 == 0) ? eval(tx.tex1, dg) : eval(tx.tex2, dg);
+        };
+        if (tx.aa == 0) return point_sample();
+        float ds = rmax(std::fabs(m[2]), std::fabs(m[4]));
+        float dt = rmax(std::fabs(m[3]), std::fabs(m[5]));
+        float s0 = s - ds, t0 = t_ - dt, s1 = s + ds, t1 = t_ + dt;
+        if (std::floor(s0) == std::floor(s1) && std::floor(t0) == std::floor(t1))
+          return point_sample();
+        auto bump_int = [](float x) {
+          float half_x = x / 2.0f;
+          return std::floor(half_x) + 2.0f * rmax(half_x - std::floor(half_x) - 0.5f, 0.0f);
+        };
+        float sint = ds > 0.0f ? (bump_int(s1) - bump_int(s0)) / (2.0f * ds) : 0.0f;
+        float tint = dt > 0.0f ? (bump_int(t1) - bump_int(t0)) / (2.0f * dt) : 0.0f;
+        float area_sq = (ds > 1.0f || dt > 1.0f) ? 0.5f : sint + tint - 2.0f * sint * tint;
+        RGB a = eval(tx.tex1, dg), b = eval(tx.tex2, dg);
+        return a * (1.0f - area_sq) + b * area_sq;  // Lerp::lerp_with
+      }
+    }
+  }
+};
+
+struct Material {
+  int kind = 0;  // 0 = Matte(kd, sigma), 1 = Plastic(kd, ks, roughness)
+  int kd = 0, sigma = 0, ks = 0, roughness = 0;  // texture ids
+};
+
+// ---------------------------------------------------------------------------------------------
+// bsdf/*
+namespace bx {
+inline float abs_cos_theta(const V3& v) { return std::fabs(v.z); }
+inline float sin_theta2(const V3& v) { return rmax(0.f, 1.0f - v.z * v.z); }
+inline float sin_theta(const V3& v) { return std::sqrt(sin_theta2(v)); }
+inline float cos_phi(const V3& v) {
+  float st = sin_theta(v);
+  return st == 0.0f ? 1.0f : rclamp(v.x / st, -1.0f, 1.0f);
+}
+inline float sin_phi(const V3& v) {
+  float st = sin_theta(v);
+  return st == 0.0f ? 0.0f : rclamp(v.y / st, -1.0f, 1.0f);
+}
+}  // namespace bx
+
+enum BxDFType : uint32_t {
+  BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16,
+  BSDF_ALL = 31
+};
+
+struct BxDF {
+  int kind = 0;  // 0 Lambertian, 1 OrenNayar, 2 Microfacet(Blinn, dielectric 1.5/1.0)
+  RGB r;
+  float a = 0.f, b = 0.f;  // OrenNayar A,B ; Microfacet: a = blinn exponent
+  uint32_t type() const {
+    return kind == 2 ? (BSDF_REFLECTION | BSDF_GLOSSY) : (BSDF_REFLECTION | BSDF_DIFFUSE);
+  }
+  // fresnel.rs:62-91 (Dielectric arm), all three channels equal
+  static float fresnel_dielectric(float cosi, float eta_i, float eta_t) {
+    float ci = rclamp(cosi, -1.0f, 1.0f);
+    float ei = eta_i, et = eta_t;
+    if (cosi <= 0.0f) std::swap(ei, et);
+    float sint = (ei / et) * std::sqrt(rmax(1.0f - ci * ci, 0.0f));
+    if (sint >= 1.0f) return 1.0f;
+    float cost = std::sqrt(rmax(1.0f - sint * sint, 0.0f));
+    float aci = std::fabs(ci);
+    float rparl = ((et * aci) - (ei * cost)) / ((et * aci) + (ei * cost));
+    float rperp = ((ei * aci) - (et * cost)) / ((ei * aci) + (et * cost));
+    return (rparl * rparl + rperp * rperp) / 2.0f;
+  }
+  RGB f(const V3& wo, const V3& wi) const {
+    using namespace bx;
+    if (kind == 0) {  // lambertian.rs:20-23
+      float invpi = 1.0f / PI_F;
+      return r * invpi;
+    }
+    if (kind == 1) {  // orennayar.rs:36-60
+      float sinthetai = sin_theta(wi), sinthetao = sin_theta(wo);
+      float maxcos = 0.0f;
+      if (!(sinthetai < 1e-4f || sinthetao < 1e-4f)) {
+        float sinphii = sin_phi(wi), cosphii = cos_phi(wi);
+        float sinphio = sin_phi(wo), cosphio = cos_phi(wo);
+        maxcos = rmax(cosphii * cosphio + sinphii * sinphio, 0.0f);
+      }
+      float sinalpha, tanbeta;
+      if (abs_cos_theta(wi) > abs_cos_theta(wo)) {
+        sinalpha = sinthetao;
+        tanbeta = sinthetai / abs_cos_theta(wi);
+      } else {
+        sinalpha = sinthetai;
+        tanbeta = sinthetao / abs_cos_theta(wo);
+      }
+      float invpi = 1.0f / PI_F;
+      return r * invpi * (a + b * maxcos * sinalpha * tanbeta);
+    }
+    // microfacet.rs:86-99
+    float cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);
+    if (cos_o == 0.0f || cos_i == 0.0f) return RGB(0.0f);
+    V3 wh = normalize(wo + wi);
+    float cos_h = dot(wi, wh);
+    float F = fresnel_dielectric(cos_h, 1.5f, 1.0f);
+    float invtwopi = 1.0f / (2.0f * PI_F);
+    float D = (a + 2.0f) * invtwopi * std::pow(abs_cos_theta(wh), a);  // microfacet.rs:32-38
+    float ndotwh = abs_cos_theta(wh), ndotwo = abs_cos_theta(wo), ndotwi = abs_cos_theta(wi);
+    float wodotwh = abs_dot(wo, wh);
+    float G = rmin(rmin(2.0f * ndotwh * ndotwo / wodotwh, 2.0f * ndotwh * ndotwi / wodotwh), 1.0f);
+    return (r * D * G * RGB(F)) / (4.0f * cos_i * cos_o);
+  }
+};
+
+struct BSDF {  // bsdf/mod.rs:58-149
+  DiffGeom dg_shading;
+  V3 nn, ng, sn, tn;
+  BxDF bxdfs[2];
+  int n_bxdfs = 0;
+  BSDF(const DiffGeom& dgs, const V3& n_geom) : dg_shading(dgs) {  // :70-86
+    nn = dgs.nn;
+    tn = normalize(dgs.dpdu);
+    sn = cross(nn, tn);
+    ng = n_geom;
+  }
+  V3 world_to_local(const V3& v) const { return V3(dot(v, sn), dot(v, tn), dot(v, nn)); }
+  // :132-149.  `strict_flags` reproduces the as-written matches_flags (D7 -> always black).
+  RGB f(const V3& wo_w, const V3& wi_w, bool strict_flags) const {
+    uint32_t flags = (dot(wi_w, ng) * dot(wo_w, ng) > 0.0f) ? (BSDF_ALL & ~BSDF_TRANSMISSION)
+                                                             : (BSDF_ALL & ~BSDF_REFLECTION);
+    V3 wo = world_to_local(wo_w), wi = world_to_local(wi_w);
+    RGB acc(0.0f);
+    for (int i = 0; i < n_bxdfs; ++i) {
+      uint32_t ty = bxdfs[i].type();
+      bool match = strict_flags ? ((ty & flags) == flags)   // bxdf_type.contains(flags)
+                                : ((ty & flags) == ty);     // pbrt semantics
+      if (match) acc = acc + bxdfs[i].f(wo, wi);
+    }
+    return acc;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Lights.  kind 0 = PointLight (light/point.rs), 1 = SpotLight (light/spot.rs),
+// 2 = diffuse area light over emissive triangles (ORACLE-DEFINED, SURVEY D9/A13: the reference's
+// AreaLight is a stub; pbrt-v2 DiffuseAreaLight semantics; parity unpinned).
+struct Light {
+  int kind = 0;
+  V3 pos;
+  RGB intensity;  // point/spot: I ; area: emitted radiance L
+  Transform world_to_light;
+  float cos_total_width = 0.f, cos_falloff_start = 0.f;
+  int num_samples = 1;
+  // area light: emissive triangles in world space (refine-reversed vertex order) + area CDF
+  struct Tri {
+    V3 p1, p2, p3, nn;
+    float area;
+  };
+  std::vector<Tri> tris;
+  std::vector<float> cdf;  // size tris+1, cdf[0] = 0, cdf.back() = 1
+  float total_area = 0.f;
+};
+
+struct ShadowQuery {  // visibility_tester.rs:16-24
+  Ray ray;
+};
+inline Ray vis_segment(const V3& p1, float eps1, const V3& p2, float eps2, float time) {
+  float dist = distance(p1, p2);
+  V3 dir = (p2 - p1) / dist;
+  Ray r(p1, dir, eps1);
+  r.maxt = (1.0f - eps2) * dist;
+  r.time = time;
+  return r;
+}
+
+// Returns false when the sample contributes nothing before visibility (li black or pdf == 0).
+inline bool light_sample_l(const Light& lt, const V3& p, float p_eps, float u1, float u2,
+                           float time, RGB* li, V3* wi, float* pdf, Ray* vis) {
+  if (lt.kind == 0) {  // point.rs:28-35 (D17: wi un-normalised)
+    V3 w = lt.pos - p;
+    *pdf = 1.0f;
+    *vis = vis_segment(p, p_eps, lt.pos, 0.0f, time);
+    *li = lt.intensity / length_squared(w);
+    *wi = w;
+  } else if (lt.kind == 1) {  // spot.rs:37-65
+    V3 w = normalize(lt.pos - p);
+    *pdf = 1.0f;
+    *vis = vis_segment(p, p_eps, lt.pos, 0.0f, time);
+    V3 wl = lt.world_to_light.vec(-w);
+    float cos_theta = wl.z, fall;
+    if (cos_theta < lt.cos_total_width)
+      fall = 0.0f;
+    else if (cos_theta > lt.cos_falloff_start)
+      fall = 1.0f;
+    else {
+      float delta = (cos_theta - lt.cos_total_width) / (lt.cos_falloff_start - lt.cos_total_width);
+      fall = delta * delta * delta * delta;
+    }
+    RGB i = lt.intensity * fall;
+    *li = i / length_squared(w);
+    *wi = w;
+  } else {
+    // ORACLE-DEFINED area light sampling (A13): triangle k by area CDF on u1 (u1 re-stretched),
+    // uniform point b0 = 1 - sqrt(u1'), b1 = u2 * sqrt(u1'); pdf wrt solid angle.
+    size_t k = 0;
+    while (k + 1 < lt.tris.size() && u1 >= lt.cdf[k + 1]) ++k;
+    float u1p = (u1 - lt.cdf[k]) / (lt.cdf[k + 1] - lt.cdf[k]);
+    float su = std::sqrt(u1p);
+    float b0 = 1.0f - su, b1 = u2 * su;
+    const Light::Tri& t = lt.tris[k];
+    V3 ps = b0 * t.p1 + b1 * t.p2 + (1.0f - b0 - b1) * t.p3;
+    V3 w = normalize(ps - p);
+    float cos_l = dot(t.nn, -w);
+    float d2 = length_squared(ps - p);
+    *wi = w;
+    *vis = vis_segment(p, p_eps, ps, 1e-3f, time);
+    if (!(cos_l > 0.0f)) {
+      *li = RGB(0.0f);
+      *pdf = 0.0f;
+    } else {
+      *li = lt.intensity;
+      *pdf = d2 / (std::fabs(cos_l) * lt.total_area);
+    }
+  }
+  return !(li->is_black() || *pdf == 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Scene {
+  Geometry geom;
+  BVH bvh;
+  std::vector<Material> materials;
+  TextureTable textures;
+  std::vector<Light> lights;
+  bool strict_flags = false;  // Appendix C `as_written_flags`
+  uint32_t max_depth = 1;
+
+  // Total light-sample pairs per camera sample (D11 extension).
+  int light_sample_pairs() const {
+    int s = 0;
+    for (const Light& l : lights)
+      if (l.kind == 2) s += l.num_samples;
+    return s;
+  }
+};
+
+// Full surface interaction at a final hit: Triangle::intersect dg part (mesh.rs:220-262),
+// Sphere::intersect dg part (sphere.rs:143-180 + helpers.rs:17-43), compute_differentials,
+// get_shading_geometry (mesh.rs:105-193).
+struct SurfacePoint {
+  DiffGeom dg;   // geometric, with differentials
+  DiffGeom dgs;  // shading
+  float ray_epsilon = 0.f;
+  const Prim* prim = nullptr;
+};
+
+inline void tri_uvs(const Prim& pr, float uv[3][2]) {  // mesh.rs:74-87
+  const Mesh& m = *pr.mesh;
+  if (!m.uvs.empty()) {
+    for (int k = 0; k < 3; ++k) {
+      uv[k][0] = m.uvs[2 * pr.v[k]];
+      uv[k][1] = m.uvs[2 * pr.v[k] + 1];
+    }
+  } else {
+    uv[0][0] = 0.f; uv[0][1] = 0.f;
+    uv[1][0] = 1.f; uv[1][1] = 0.f;
+    uv[2][0] = 1.f; uv[2][1] = 1.f;
+  }
+}
+
+inline DiffGeom tri_dg(const Prim& pr, const Ray& r, float t, float b1, float b2) {
+  const Mesh& m = *pr.mesh;
+  const V3 &p1 = m.p[pr.v[0]], &p2 = m.p[pr.v[1]], &p3 = m.p[pr.v[2]];
+  float uvs[3][2];
+  tri_uvs(pr, uvs);
+  float du1 = uvs[0][0] - uvs[2][0];
+  float du2 = uvs[1][0] - uvs[2][0];
+  float dv1 = uvs[0][1] - uvs[2][1];
+  float dv2 = uvs[1][1] - uvs[2][1];
+  V3 dp1 = p1 - p3, dp2 = p2 - p3;
+  V3 dpdu, dpdv;
+  float determinant = du1 * dv2 - dv1 * du2;
+  if (determinant == 0.0f) {
+    coordinate_system(normalize(cross(p3 - p1, p2 - p1)), &dpdu, &dpdv);
+  } else {
+    float inv_det = 1.0f / determinant;
+    dpdu = (dv2 * dp1 - dv1 * dp2) * inv_det;
+    dpdv = (-du2 * dp1 + du1 * dp2) * inv_det;
+  }
+  float b0 = 1.0f - b1 - b2;
+  float tu = b0 * uvs[0][0] + b1 * uvs[1][0] + b2 * uvs[2][0];
+  float tv = b0 * uvs[0][1] + b1 * uvs[1][1] + b2 * uvs[2][1];
+  return DiffGeom(r.at(t), dpdu, dpdv, V3(), V3(), tu, tv, &m.base);
+}
+
+inline DiffGeom sphere_dg(const Sphere& s, const Ray& world_ray, float t_hit, float phi) {
+  Ray ray = xf_ray(s.base.w2o, world_ray);
+  V3 p_hit = ray.at(t_hit);
+  float u = phi / s.phi_max;
+  float theta = std::acos(rclamp(p_hit.z / s.radius, -1.0f, 1.0f));
+  float v = (theta - s.theta_min) / (s.theta_max - s.theta_min);
+  float zradius = std::sqrt(p_hit.x * p_hit.x + p_hit.y * p_hit.y);
+  float inv_zradius = 1.0f / zradius;
+  float cos_phi = p_hit.x * inv_zradius;
+  float sin_phi = p_hit.y * inv_zradius;
+  V3 dpdu(-s.phi_max * p_hit.y, s.phi_max * p_hit.x, 0.0f);
+  V3 dpdv = (s.theta_max - s.theta_min) *
+            V3(p_hit.z * cos_phi, p_hit.z * sin_phi, -s.radius * std::sin(theta));
+  V3 d2pduu = -s.phi_max * s.phi_max * V3(p_hit.x, p_hit.y, 0.0f);
+  V3 d2pduv = (s.theta_max - s.theta_min) * p_hit.z * s.phi_max * V3(-sin_phi, cos_phi, 0.0f);
+  V3 d2pdvv = -(s.theta_max - s.theta_min) * (s.theta_max - s.theta_min) * p_hit;
+  // helpers.rs:17-43
+  float ee = dot(dpdu, dpdu), ff = dot(dpdu, dpdv), gg = dot(dpdv, dpdv);
+  V3 nn = normalize(cross(dpdu, dpdv));
+  float e = dot(nn, d2pduu), f = dot(nn, d2pduv), g = dot(nn, d2pdvv);
+  float inveeggff2 = 1.0f / (ee * gg - ff * ff);
+  V3 dndu = (f * ff - e * gg) * inveeggff2 * dpdu + (e * ff - f * ee) * inveeggff2 * dpdv;
+  V3 dndv = (g * ff - f * gg) * inveeggff2 * dpdu + (f * ff - g * ee) * inveeggff2 * dpdv;
+  const Transform& o2w = s.base.o2w;
+  return DiffGeom(o2w.pt(p_hit), o2w.vec(dpdu), o2w.vec(dpdv), o2w.nrm(dndu), o2w.nrm(dndv), u, v,
+                  &s.base);
+}
+
+// mesh.rs:105-193
+inline DiffGeom tri_shading_geometry(const Prim& pr, const DiffGeom& dg) {
+  const Mesh& m = *pr.mesh;
+  if (m.n.empty() && m.s.empty()) return dg;
+  const Transform& o2w = m.base.o2w;
+  float uv[3][2];
+  tri_uvs(pr, uv);
+  float b[3];
+  {
+    float a[2][2] = {{uv[1][0] - uv[0][0], uv[2][0] - uv[0][0]},
+                     {uv[1][1] - uv[0][1], uv[2][1] - uv[0][1]}};
+    float c[2] = {dg.u - uv[0][0], dg.v - uv[0][1]};
+    float x0, x1;
+    if (solve_linear_system_2x2(a, c, &x0, &x1)) {
+      b[0] = 1.0f - x0 - x1;
+      b[1] = x0;
+      b[2] = x1;
+    } else {
+      float third = 1.f / 3.f;
+      b[0] = b[1] = b[2] = third;
+    }
+  }
+  V3 ns = !m.n.empty()
+              ? normalize(o2w.vec(b[0] * m.n[pr.v[0]] + b[1] * m.n[pr.v[1]] + b[2] * m.n[pr.v[2]]))
+              : dg.nn;
+  V3 ss = !m.s.empty()
+              ? normalize(o2w.vec(b[0] * m.s[pr.v[0]] + b[1] * m.s[pr.v[1]] + b[2] * m.s[pr.v[2]]))
+              : normalize(dg.dpdu);
+  V3 ts = cross(ss, ns);
+  if (length_squared(ts) > 0.f) {
+    ss = normalize(ts);     // as written: the tuple (ts.normalize(), ns x ts) is bound to (ss, ts)
+    ts = cross(ns, ts);
+  } else {
+    coordinate_system(ns, &ss, &ts);
+  }
+  V3 dndu, dndv;
+  if (!m.n.empty()) {
+    float du1 = uv[0][0] - uv[2][0], du2 = uv[1][0] - uv[2][0];
+    float dv1 = uv[0][1] - uv[2][1], dv2 = uv[1][1] - uv[2][1];
+    V3 dn1 = m.n[pr.v[0]] - m.n[pr.v[2]];
+    V3 dn2 = m.n[pr.v[1]] - m.n[pr.v[2]];
+    float determinant = du1 * dv2 - dv1 * du2;
+    if (determinant != 0.0f) {
+      float inv_det = 1.0f / determinant;
+      dndu = (dv2 * dn1 - dv1 * dn2) * inv_det;
+      dndv = (-du2 * dn1 + du1 * dn2) * inv_det;
+    }
+  }
+  return DiffGeom(dg.p, ss, ts, o2w.nrm(dndu), o2w.nrm(dndv), dg.u, dg.v, &m.base);
+}
+
+struct ShadeCounters {
+  uint64_t shadow_rays = 0;
+  TraceCounters shadow_trace;  // early-exit any-hit counts (roofline definition)
+};
+
+// Oracle-defined Le for emissive triangles (A13): L if n . w > 0.
+inline RGB emitted(const Scene& sc, const Prim& pr, const V3& nn, const V3& w) {
+  if (pr.kind != Prim::TRI || pr.mesh->area_light < 0) return RGB(0.0f);
+  const Light& l = sc.lights[(size_t)pr.mesh->area_light];
+  return dot(nn, w) > 0.0f ? l.intensity : RGB(0.0f);
+}
+
+// WhittedIntegrator::li (integrator/whitted.rs:30-77) for a ray that hit `hit`; light_u holds the
+// D11 light-sample floats for this camera sample (2 per area-light sample, in light order).
+inline RGB whitted_li(const Scene& sc, const RayDifferential& rayd, const Hit& hit,
+                      const float* light_u, ShadeCounters* cnt) {
+  const Prim& pr = sc.bvh.prims[hit.prim];
+  const Ray& ray = rayd.ray;
+  // Intersection::get_bsdf (intersection.rs:40-47)
+  DiffGeom dg = pr.kind == Prim::TRI ? tri_dg(pr, ray, hit.t, hit.b1, hit.b2)
+                                     : sphere_dg(*pr.sphere, ray, hit.t, hit.b1);
+  float ray_epsilon = hit.t * 5e-4f;  // mesh.rs:262 / sphere.rs:180
+  dg.compute_differentials(rayd);
+  DiffGeom dgs = pr.kind == Prim::TRI ? tri_shading_geometry(pr, dg) : dg;
+  const Material& mat = sc.materials[pr.material()];
+  BSDF bsdf(dgs, dg.nn);
+  if (mat.kind == 0) {  // matte.rs:30-51
+    RGB r = sc.textures.eval(mat.kd, dgs).clamp(0.0f, F32_MAX);
+    float sig = rclamp(sc.textures.eval(mat.sigma, dgs).c[0], 0.0f, 90.0f);
+    BxDF b;
+    b.r = r;
+    if (sig == 0.0f) {
+      b.kind = 0;
+    } else {  // orennayar.rs:16-29
+      b.kind = 1;
+      float sigma = as_radians(sig);
+      float sigma2 = sigma * sigma;
+      b.a = 1.0f - (sigma2 / (2.0f * (sigma + 0.33f)));
+      b.b = 0.45f * sigma2 / (sigma2 + 0.09f);
+    }
+    bsdf.bxdfs[bsdf.n_bxdfs++] = b;
+  } else {  // plastic.rs:32-55
+    RGB kd = sc.textures.eval(mat.kd, dgs).clamp(0.0f, F32_MAX);
+    RGB ks = sc.textures.eval(mat.ks, dgs).clamp(0.0f, F32_MAX);
+    float rough = sc.textures.eval(mat.roughness, dgs).c[0];
+    float e = 1.0f / rough;
+    if (e > 1000.0f || std::isnan(e)) e = 1000.0f;  // microfacet.rs:18-24
+    BxDF d;
+    d.kind = 0;
+    d.r = kd;
+    BxDF s;
+    s.kind = 2;
+    s.r = ks;
+    s.a = e;
+    bsdf.bxdfs[bsdf.n_bxdfs++] = d;
+    bsdf.bxdfs[bsdf.n_bxdfs++] = s;
+  }
+  const V3& p = bsdf.dg_shading.p;
+  const V3& n = bsdf.dg_shading.nn;
+  V3 wo = -ray.d;
+  RGB L = emitted(sc, pr, dg.nn, wo);  // isect.le(wo): 0 in the reference (intersection.rs:58)
+  size_t lu = 0;
+  for (const Light& lt : sc.lights) {
+    int ns = lt.kind == 2 ? lt.num_samples : 1;
+    RGB Ld(0.0f);
+    bool any = false;
+    for (int s = 0; s < ns; ++s) {
+      float u1 = 0.f, u2 = 0.f;
+      if (lt.kind == 2) {
+        u1 = light_u[lu++];
+        u2 = light_u[lu++];
+      }
+      RGB li;
+      V3 wi;
+      float pdf;
+      Ray vis;
+      if (!light_sample_l(lt, p, ray_epsilon, u1, u2, ray.time, &li, &wi, &pdf, &vis)) continue;
+      RGB f = bsdf.f(wo, wi, sc.strict_flags);
+      if (f.is_black()) continue;
+      if (cnt) cnt->shadow_rays++;
+      if (cnt) {  // count the early-exit traversal for the roofline, answer with the same boolean
+        Ray probe = vis;
+        (void)sc.bvh.intersect_p(probe, true, &cnt->shadow_trace);
+      }
+      if (sc.bvh.intersect_p(vis, false)) continue;  // !visibility.unoccluded(scene)
+      // whitted.rs:60-63 with T = 1 (D3)
+      RGB c = f * li * abs_dot(wi, n) * RGB(1.0f) / pdf;
+      if (lt.kind == 2) {
+        Ld = Ld + c;
+        any = true;
+      } else {
+        L = L + c;
+      }
+    }
+    if (any) L = L + Ld / (float)ns;  // D10: average over the light's samples
+  }
+  // D8: matte/plastic have no specular lobe -> specular_reflect/transmit contribute 0.
+  return L;
+}
+
+}  // namespace orc

@@ -1,0 +1,1040 @@
+// C-ABI implementation of the B200 back end (include/pbrtb200.h).  Host orchestration of the
+// wavefront pipeline:  raygen -> trace(closest) -> shade -> trace(any) -> resolve -> film.
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "film.cuh"
+#include "host_logic.hpp"
+#include "raygen.cuh"
+#include "shade.cuh"
+#include "trace.cuh"
+
+static_assert(sizeof(pbrtb200_node32) == 32, "node32 layout");
+static_assert(sizeof(pbrtb200_tri48) == 48, "tri48 layout");
+static_assert(sizeof(pbrtb200_sphere80) == 80, "sphere80 layout");
+static_assert(sizeof(pbrtb200_ray32) == 32, "ray32 layout");
+static_assert(sizeof(pbrtb200_hit16) == 16, "hit16 layout");
+static_assert(sizeof(DAreaTri) == 64, "DAreaTri layout");
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  // grow-only
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    release();
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct CtrlBlock {  // small device-side control words, zeroed per use
+  unsigned long long counter;
+  unsigned long long shadow_total;
+  unsigned long long hit_total;
+  uint32_t flags;
+  uint32_t sq_count;
+  uint32_t nan_count;
+  uint32_t pad;
+};
+
+std::string g_create_err;
+
+}  // namespace
+
+struct pbrtb200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // scene
+  bool has_scene = false, has_spheres = false, multi_leaf = false;
+  DScene sc{};
+  std::vector<pbrtb200_light> h_lights;
+  DevBuf d_nodes, d_tris, d_leaf_prim, d_leaf_count, d_spheres, d_sphere_o2w, d_meshes, d_tri_uv,
+      d_tri_n, d_tri_s, d_materials, d_textures, d_lights, d_area_tris;
+  // per-frame work buffers (grow-only)
+  DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_xyz, d_hits, d_Le, d_contrib,
+      d_sq_rays, d_sq_slots, d_film, d_rects, d_rect_prefix, d_ctrl, d_rays_in, d_occ, d_out_a,
+      d_out_b, d_out_c;
+  // cached pixel work list
+  struct ListKey {
+    pbrtb200_sampler smp{};
+    int32_t film_ext[4] = {0, 0, 0, 0};
+    float xw = 0, yw = 0;
+    std::vector<int32_t> rects;
+    bool whole = true;
+    bool valid = false;
+  } list_key;
+  uint64_t n_list_pixels = 0;
+  uint32_t n_film_pixels = 0;
+  uint32_t n_rects = 0;
+  std::vector<cudaEvent_t> events;
+};
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+      (void)cudaGetLastError();                                                           \
+      return e_ == cudaErrorMemoryAllocation ? PBRTB200_ENOMEM : PBRTB200_ENODEV;         \
+    }                                                                                     \
+  } while (0)
+
+#define FAIL(code, msg) \
+  do {                  \
+    ctx->err = (msg);   \
+    return (code);      \
+  } while (0)
+
+namespace {
+
+template <class T>
+int upload(pbrtb200_ctx* ctx, DevBuf& buf, const T* src, size_t n) {
+  if (n == 0) return 0;
+  CK(buf.ensure(n * sizeof(T)));
+  CK(cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+bool affine_ok(const float* m16) {
+  return m16[12] == 0.f && m16[13] == 0.f && m16[14] == 0.f && m16[15] == 1.f;
+}
+
+int tex_depth(const pbrtb200_scene* s, int id, int depth) {
+  if (id < 0 || (uint32_t)id >= s->n_textures) return -1;
+  const pbrtb200_texture& t = s->textures[id];
+  if (t.kind != PBRTB200_TEX_CHECKER2D) return 0;
+  if (depth > 3) return -1;
+  int a = tex_depth(s, t.tex1, depth + 1), b = tex_depth(s, t.tex2, depth + 1);
+  if (a < 0 || b < 0) return -1;
+  return 1 + std::max(a, b);
+}
+
+int trace_grid(pbrtb200_ctx* ctx, const void* kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PB_TRACE_THREADS, 0) !=
+          cudaSuccess ||
+      per_sm < 1)
+    per_sm = 4;
+  return ctx->sm_count * per_sm;
+}
+
+// Dispatch on (ANY, SPH, MULTI, SRC).
+template <bool ANY, int SRC>
+int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a) {
+  const DScene& sc = ctx->sc;
+#define PB_LAUNCH(SPH, MULTI)                                                              \
+  {                                                                                        \
+    auto kfn = k_trace<ANY, SPH, MULTI, SRC>;                                              \
+    const int grid = trace_grid(ctx, (const void*)kfn);                                    \
+    kfn<<<grid, PB_TRACE_THREADS, 0, ctx->stream>>>(sc, cam, a);                           \
+  }
+  if (ctx->has_spheres) {
+    if (ctx->multi_leaf) PB_LAUNCH(true, true) else PB_LAUNCH(true, false)
+  } else {
+    if (ctx->multi_leaf) PB_LAUNCH(false, true) else PB_LAUNCH(false, false)
+  }
+#undef PB_LAUNCH
+  CK(cudaGetLastError());
+  return 0;
+}
+
+CtrlBlock* ctrl(pbrtb200_ctx* ctx) { return ctx->d_ctrl.as<CtrlBlock>(); }
+
+void fill_camera(const pbrtb200_camera* c, int spp, DCamera* out) {
+  std::memcpy(out->r2c, c->raster_to_camera, 64);
+  std::memcpy(out->c2w, c->camera_to_world, 64);
+  for (int i = 0; i < 3; ++i) {
+    out->dx[i] = c->dx_camera[i];
+    out->dy[i] = c->dy_camera[i];
+  }
+  out->sopen = c->shutter_open;
+  out->sclose = c->shutter_close;
+  out->lens_radius = c->lens_radius;
+  out->focal_distance = c->focal_distance;
+  out->diff_scale = 1.0f / std::sqrt((float)spp);  // sampler_renderer.rs:96
+}
+
+int sampler_spp(const pbrtb200_sampler* s) {
+  if (s->kind == PBRTB200_SAMPLER_STRATIFIED) return s->xs * s->ys;
+  int p = 1;
+  while (p < s->xs) p <<= 1;  // lds.rs:18 next_power_of_two
+  return p;
+}
+
+int check_sampler(pbrtb200_ctx* ctx, const pbrtb200_sampler* s) {
+  if (!s) FAIL(PBRTB200_EINVAL, "sampler is NULL");
+  if (s->kind != PBRTB200_SAMPLER_STRATIFIED && s->kind != PBRTB200_SAMPLER_LD)
+    FAIL(PBRTB200_EINVAL, "unsupported sampler kind");
+  if (s->xs < 1 || (s->kind == PBRTB200_SAMPLER_STRATIFIED && s->ys < 1))
+    FAIL(PBRTB200_EINVAL, "sampler needs >= 1 sample per pixel");
+  if (s->x_end <= s->x_start || s->y_end <= s->y_start)
+    FAIL(PBRTB200_EINVAL, "empty sampler extent");
+  if (s->num_tasks < 1 || s->num_tasks > 4096) FAIL(PBRTB200_EINVAL, "num_tasks out of range");
+  if (s->x_start < -32768 || s->y_start < -32768 || s->x_end > 32767 || s->y_end > 32767)
+    FAIL(PBRTB200_EINVAL, "sampler extent exceeds 16-bit pixel coordinates");
+  return 0;
+}
+
+void fill_sampler(pbrtb200_ctx* ctx, const pbrtb200_sampler* s, DSampler* out) {
+  out->kind = s->kind;
+  out->xs = s->xs;
+  out->ys = s->kind == PBRTB200_SAMPLER_STRATIFIED ? s->ys : 1;
+  out->jitter = s->jitter;
+  out->spp = sampler_spp(s);
+  const uint32_t n = (uint32_t)out->spp;
+  // RNG words per pixel (SURVEY §8a A1 / A1'): stratified 5n floats (+4n shuffle words), LD
+  // (5 + 6n) u64 draws; the light-sample floats follow (D11).
+  out->cam_words = s->kind == PBRTB200_SAMPLER_STRATIFIED ? (s->jitter ? 9u * n : 4u * n)
+                                                          : 2u * (5u + 6u * n);
+  out->words_per_pixel = out->cam_words + 2u * n * ctx->sc.area_sample_pairs;
+  out->sopen = s->shutter_open;
+  out->sclose = s->shutter_close;
+  out->task_keys = ctx->d_task_keys.as<uint32_t>();
+}
+
+// Builds (or reuses) the pixel work list: the sampler pixels whose samples can reach the film
+// pixels of `rects`, in 8x4-tile-major order, each with its task id and in-window index.
+int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb200_film* film,
+                     const pbrtb200_tileset* tiles) {
+  const bool whole = !(tiles && tiles->n_rects > 0 && tiles->rects);
+  std::vector<int32_t> rects;
+  const int32_t fx0 = film ? film->x_pixel_start : 0, fy0 = film ? film->y_pixel_start : 0;
+  const int32_t fx1 = film ? fx0 + film->x_pixel_count : 0, fy1 = film ? fy0 + film->y_pixel_count : 0;
+  if (!whole) {
+    rects.assign(tiles->rects, tiles->rects + 4 * (size_t)tiles->n_rects);
+    for (uint32_t r = 0; r < tiles->n_rects; ++r) {
+      const int32_t* q = &rects[4 * r];
+      if (q[0] < fx0 || q[1] < fy0 || q[2] > fx1 || q[3] > fy1 || q[2] <= q[0] || q[3] <= q[1])
+        FAIL(PBRTB200_EINVAL, "tile rect outside the film pixel extent or empty");
+    }
+  } else if (film) {
+    rects = {fx0, fy0, fx1, fy1};
+  }
+  auto& key = ctx->list_key;
+  const float xw = film ? film->filter_xw : 0.f, yw = film ? film->filter_yw : 0.f;
+  if (key.valid && std::memcmp(&key.smp, smp, sizeof *smp) == 0 && key.whole == whole &&
+      key.rects == rects && key.xw == xw && key.yw == yw && key.film_ext[0] == fx0 &&
+      key.film_ext[1] == fy0 && key.film_ext[2] == fx1 && key.film_ext[3] == fy1)
+    return 0;
+  key.valid = false;
+
+  const int32_t ext[4] = {smp->x_start, smp->x_end, smp->y_start, smp->y_end};
+  const int sw = ext[1] - ext[0], sh = ext[3] - ext[2];
+  const size_t n_ext = (size_t)sw * (size_t)sh;
+  std::vector<uint16_t> task_of(n_ext, 0xFFFF);
+  std::vector<uint32_t> k_of(n_ext, 0);
+  std::vector<uint32_t> keys(8 * (size_t)smp->num_tasks);
+  for (int t = 0; t < smp->num_tasks; ++t) {
+    pbh::task_key((uint64_t)t, &keys[8 * (size_t)t]);
+    int32_t w[4];
+    pbh::sampler_sub_window(ext, (uint64_t)t, (uint64_t)smp->num_tasks, w);
+    if (w[0] == w[1] || w[2] == w[3]) continue;  // get_sub_sampler -> None
+    if (w[0] < ext[0] || w[1] > ext[1] || w[2] < ext[2] || w[3] > ext[3] || w[1] < w[0] || w[3] < w[2])
+      FAIL(PBRTB200_EINVAL, "task window outside the sampler extent");
+    const uint32_t tw = (uint32_t)(w[1] - w[0]);
+    for (int y = w[2]; y < w[3]; ++y)
+      for (int x = w[0]; x < w[1]; ++x) {
+        const size_t e = (size_t)(y - ext[2]) * sw + (size_t)(x - ext[0]);
+        task_of[e] = (uint16_t)t;
+        k_of[e] = (uint32_t)(y - w[2]) * tw + (uint32_t)(x - w[0]);
+      }
+  }
+  // which sampler pixels are needed
+  std::vector<uint8_t> need(n_ext, whole ? 1 : 0);
+  if (!whole) {
+    for (size_t r = 0; r < rects.size() / 4; ++r) {
+      const int32_t* q = &rects[4 * r];
+      int qx0 = (int)std::ceil(((float)q[0] - 0.5f) - xw) - 1, qx1 = (int)std::floor(((float)(q[2] - 1) + 0.5f) + xw) + 1;
+      int qy0 = (int)std::ceil(((float)q[1] - 0.5f) - yw) - 1, qy1 = (int)std::floor(((float)(q[3] - 1) + 0.5f) + yw) + 1;
+      qx0 = std::max(qx0, ext[0]);
+      qx1 = std::min(qx1, ext[1] - 1);
+      qy0 = std::max(qy0, ext[2]);
+      qy1 = std::min(qy1, ext[3] - 1);
+      for (int y = qy0; y <= qy1; ++y)
+        for (int x = qx0; x <= qx1; ++x) need[(size_t)(y - ext[2]) * sw + (size_t)(x - ext[0])] = 1;
+    }
+  }
+  std::vector<DPixel> list;
+  list.reserve(n_ext);
+  std::vector<int32_t> index(n_ext, -1);
+  const int TW = 8, TH = 4;
+  for (int ty = 0; ty < sh; ty += TH)
+    for (int tx = 0; tx < sw; tx += TW)
+      for (int yy = ty; yy < std::min(ty + TH, sh); ++yy)
+        for (int xx = tx; xx < std::min(tx + TW, sw); ++xx) {
+          const size_t e = (size_t)yy * sw + (size_t)xx;
+          if (!need[e] || task_of[e] == 0xFFFF) continue;
+          DPixel p;
+          const int x = ext[0] + xx, y = ext[2] + yy;
+          p.xy = (int32_t)(((uint32_t)(uint16_t)(int16_t)x) | ((uint32_t)(uint16_t)(int16_t)y << 16));
+          p.k = k_of[e];
+          p.task = task_of[e];
+          index[e] = (int32_t)list.size();
+          list.push_back(p);
+        }
+  if (list.empty()) FAIL(PBRTB200_EINVAL, "no sampler pixel to evaluate");
+  if (upload(ctx, ctx->d_pixels, list.data(), list.size())) return PBRTB200_ENODEV;
+  if (upload(ctx, ctx->d_pix_index, index.data(), index.size())) return PBRTB200_ENODEV;
+  if (upload(ctx, ctx->d_task_keys, keys.data(), keys.size())) return PBRTB200_ENODEV;
+  std::vector<uint32_t> prefix(rects.size() / 4 + 1, 0);
+  for (size_t r = 0; r < rects.size() / 4; ++r)
+    prefix[r + 1] = prefix[r] + (uint32_t)((rects[4 * r + 2] - rects[4 * r]) * (rects[4 * r + 3] - rects[4 * r + 1]));
+  if (!rects.empty()) {
+    if (upload(ctx, ctx->d_rects, rects.data(), rects.size())) return PBRTB200_ENODEV;
+    if (upload(ctx, ctx->d_rect_prefix, prefix.data(), prefix.size())) return PBRTB200_ENODEV;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));  // host vectors die at scope exit
+  ctx->n_list_pixels = list.size();
+  ctx->n_film_pixels = prefix.back();
+  ctx->n_rects = (uint32_t)(rects.size() / 4);
+  key.smp = *smp;
+  key.whole = whole;
+  key.rects = rects;
+  key.xw = xw;
+  key.yw = yw;
+  key.film_ext[0] = fx0;
+  key.film_ext[1] = fy0;
+  key.film_ext[2] = fx1;
+  key.film_ext[3] = fy1;
+  key.valid = true;
+  return 0;
+}
+
+struct StageTimer {
+  pbrtb200_ctx* ctx;
+  bool on;
+  size_t used = 0;
+  struct Span {
+    size_t a, b;
+    int stage;
+  };
+  std::vector<Span> spans;
+  cudaEvent_t get() {
+    if (used == ctx->events.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ctx->events.push_back(e);
+    }
+    return ctx->events[used++];
+  }
+  size_t mark() {
+    if (!on) return 0;
+    cudaEvent_t e = get();
+    cudaEventRecord(e, ctx->stream);
+    return used - 1;
+  }
+  void span(size_t a, size_t b, int stage) {
+    if (on) spans.push_back({a, b, stage});
+  }
+  void collect(float ms[6]) {
+    for (int i = 0; i < 6; ++i) ms[i] = 0.f;
+    if (!on) return;
+    for (auto& s : spans) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ctx->events[s.a], ctx->events[s.b]);
+      ms[s.stage] += t;
+    }
+  }
+};
+
+// Samples per wavefront chunk: bounds the chunk-local buffers (hits, Le, contrib, shadow queue).
+constexpr uint64_t kChunkSamples = 1ull << 22;
+
+}  // namespace
+
+extern "C" {
+
+const char* pbrtb200_last_error(const pbrtb200_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+int pbrtb200_create(int device, pbrtb200_ctx** out) {
+  if (!out) return PBRTB200_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    (void)cudaGetLastError();
+    return PBRTB200_ENODEV;
+  }
+  if (device < 0 || device >= n) {
+    g_create_err = "device index out of range";
+    return PBRTB200_EINVAL;
+  }
+  pbrtb200_ctx* ctx = new pbrtb200_ctx();
+  ctx->device = device;
+  auto bail = [&](const char* what, cudaError_t err) {
+    g_create_err = std::string(what) + ": " + cudaGetErrorString(err);
+    (void)cudaGetLastError();
+    delete ctx;
+    return PBRTB200_ENODEV;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail("cudaStreamCreate", e);
+  if ((e = ctx->d_ctrl.ensure(sizeof(CtrlBlock))) != cudaSuccess) return bail("cudaMalloc", e);
+  *out = ctx;
+  return PBRTB200_OK;
+}
+
+void pbrtb200_destroy(pbrtb200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
+  if (!ctx) return PBRTB200_EINVAL;
+  if (!s) FAIL(PBRTB200_EINVAL, "scene is NULL");
+  CK(cudaSetDevice(ctx->device));
+  ctx->has_scene = false;
+  ctx->list_key.valid = false;
+  if (s->n_nodes == 0 || !s->nodes) FAIL(PBRTB200_EINVAL, "scene has no BVH nodes");
+  if (s->n_prims == 0) FAIL(PBRTB200_EINVAL, "scene has no primitives");
+  if (s->n_prims >= 0x7FFFFFFFu) FAIL(PBRTB200_EINVAL, "too many primitives");
+  if (s->n_spheres && (!s->leaf_prim || !s->spheres || !s->sphere_o2w))
+    FAIL(PBRTB200_EINVAL, "spheres need leaf_prim, spheres and sphere_o2w");
+  if (!s->n_spheres && s->n_tris != s->n_prims && !s->leaf_prim)
+    FAIL(PBRTB200_EINVAL, "n_tris != n_prims without leaf_prim");
+  if (s->n_tris && !s->tris) FAIL(PBRTB200_EINVAL, "tris is NULL");
+  if (s->n_tris && (!s->meshes || !s->n_meshes)) FAIL(PBRTB200_EINVAL, "triangles need meshes");
+
+  // ---- BVH: reference linear nodes -> 64-byte pair nodes ----
+  const uint32_t nn = s->n_nodes;
+  std::vector<uint32_t> pair_index(nn, 0xFFFFFFFFu);
+  uint32_t n_inner = 0;
+  for (uint32_t i = 0; i < nn; ++i)
+    if (!s->nodes[i].is_leaf) pair_index[i] = n_inner++;
+  std::vector<uint16_t> leaf_count(s->n_prims, 0);
+  bool multi = false;
+  uint64_t covered = 0;
+  auto child_ref = [&](uint32_t c, uint32_t* ref) -> bool {
+    if (c >= nn) return false;
+    const pbrtb200_node32& nd = s->nodes[c];
+    if (nd.is_leaf) {
+      if (nd.count == 0 || (uint64_t)nd.offset + nd.count > s->n_prims) return false;
+      *ref = PB_LEAF_BIT | nd.offset;
+    } else {
+      *ref = pair_index[c];
+    }
+    return true;
+  };
+  std::vector<float4> pairs(4ull * n_inner);
+  for (uint32_t i = 0; i < nn; ++i) {
+    const pbrtb200_node32& nd = s->nodes[i];
+    if (nd.is_leaf) {
+      if (nd.count == 0 || (uint64_t)nd.offset + nd.count > s->n_prims)
+        FAIL(PBRTB200_EINVAL, "leaf node range outside the primitive list");
+      leaf_count[nd.offset] = nd.count;
+      if (nd.count > 1) multi = true;
+      covered += nd.count;
+      continue;
+    }
+    if (nd.axis > 2) FAIL(PBRTB200_EINVAL, "inner node axis > 2");
+    uint32_t r0, r1;
+    if (i + 1 >= nn || nd.offset <= i + 1 || !child_ref(i + 1, &r0) || !child_ref(nd.offset, &r1))
+      FAIL(PBRTB200_EINVAL, "inner node child index invalid");
+    const pbrtb200_node32 &c0 = s->nodes[i + 1], &c1 = s->nodes[nd.offset];
+    float4* q = &pairs[4ull * pair_index[i]];
+    q[0] = make_float4(c0.bmin[0], c0.bmin[1], c0.bmin[2], c0.bmax[0]);
+    q[1] = make_float4(c0.bmax[1], c0.bmax[2], c1.bmin[0], c1.bmin[1]);
+    q[2] = make_float4(c1.bmin[2], c1.bmax[0], c1.bmax[1], c1.bmax[2]);
+    float4 m;
+    std::memcpy(&m.x, &r0, 4);
+    std::memcpy(&m.y, &r1, 4);
+    m.z = 0.f;
+    uint32_t ax = nd.axis;
+    std::memcpy(&m.w, &ax, 4);
+    q[3] = m;
+  }
+  if (covered != s->n_prims) FAIL(PBRTB200_EINVAL, "leaves do not cover the primitive list exactly once");
+
+  // ---- validation of the shading tables ----
+  for (uint32_t i = 0; i < s->n_materials; ++i) {
+    const pbrtb200_material& m = s->materials[i];
+    if (m.kind != PBRTB200_MAT_MATTE && m.kind != PBRTB200_MAT_PLASTIC)
+      FAIL(PBRTB200_EINVAL, "unsupported material kind");
+    if (tex_depth(s, m.kd, 0) < 0) FAIL(PBRTB200_EINVAL, "material kd texture invalid or nested too deep");
+    if (m.kind == PBRTB200_MAT_MATTE && tex_depth(s, m.sigma, 0) < 0)
+      FAIL(PBRTB200_EINVAL, "material sigma texture invalid");
+    if (m.kind == PBRTB200_MAT_PLASTIC && (tex_depth(s, m.ks, 0) < 0 || tex_depth(s, m.roughness, 0) < 0))
+      FAIL(PBRTB200_EINVAL, "material ks/roughness texture invalid");
+  }
+  for (uint32_t i = 0; i < s->n_meshes; ++i) {
+    if (s->n_materials && s->meshes[i].material >= s->n_materials) FAIL(PBRTB200_EINVAL, "mesh material out of range");
+    if (s->meshes[i].area_light >= (int32_t)s->n_lights) FAIL(PBRTB200_EINVAL, "mesh area_light out of range");
+    if (s->meshes[i].area_light >= 0 && s->lights[s->meshes[i].area_light].kind != PBRTB200_LIGHT_AREA)
+      FAIL(PBRTB200_EINVAL, "mesh refers to a non-area light");
+  }
+  for (uint32_t i = 0; i < s->n_tris; ++i) {
+    if (s->tris[i].mesh >= s->n_meshes) FAIL(PBRTB200_EINVAL, "triangle mesh index out of range");
+    if ((s->tri_uv || s->tri_n || s->tri_s) && s->tris[i].attr >= s->n_attr)
+      FAIL(PBRTB200_EINVAL, "triangle attr index out of range");
+  }
+  for (uint32_t i = 0; i < s->n_spheres; ++i)
+    if (s->n_materials && s->spheres[i].material >= s->n_materials) FAIL(PBRTB200_EINVAL, "sphere material out of range");
+  if (s->leaf_prim)
+    for (uint32_t i = 0; i < s->n_prims; ++i) {
+      const uint32_t p = s->leaf_prim[i];
+      if ((p & PB_LEAF_BIT) ? ((p & ~PB_LEAF_BIT) >= s->n_spheres) : (p >= s->n_tris))
+        FAIL(PBRTB200_EINVAL, "leaf_prim entry out of range");
+    }
+
+  // ---- upload ----
+  if (upload(ctx, ctx->d_nodes, pairs.data(), pairs.size())) return PBRTB200_ENODEV;
+  if (upload(ctx, ctx->d_tris, s->tris, s->n_tris)) return PBRTB200_ENODEV;
+  const bool need_leaf_prim = s->n_spheres > 0 || (s->leaf_prim != nullptr);
+  if (need_leaf_prim && upload(ctx, ctx->d_leaf_prim, s->leaf_prim, s->n_prims)) return PBRTB200_ENODEV;
+  if (multi && upload(ctx, ctx->d_leaf_count, leaf_count.data(), leaf_count.size())) return PBRTB200_ENODEV;
+  if (upload(ctx, ctx->d_spheres, s->spheres, s->n_spheres)) return PBRTB200_ENODEV;
+  if (upload(ctx, ctx->d_sphere_o2w, s->sphere_o2w, 12ull * s->n_spheres)) return PBRTB200_ENODEV;
+  if (upload(ctx, ctx->d_meshes, s->meshes, s->n_meshes)) return PBRTB200_ENODEV;
+  if (s->tri_uv && upload(ctx, ctx->d_tri_uv, s->tri_uv, 6ull * s->n_attr)) return PBRTB200_ENODEV;
+  if (s->tri_n && upload(ctx, ctx->d_tri_n, s->tri_n, 9ull * s->n_attr)) return PBRTB200_ENODEV;
+  if (s->tri_s && upload(ctx, ctx->d_tri_s, s->tri_s, 9ull * s->n_attr)) return PBRTB200_ENODEV;
+  if (upload(ctx, ctx->d_materials, s->materials, s->n_materials)) return PBRTB200_ENODEV;
+  if (upload(ctx, ctx->d_textures, s->textures, s->n_textures)) return PBRTB200_ENODEV;
+
+  DScene& sc = ctx->sc;
+  std::memset(&sc, 0, sizeof sc);
+  sc.nodes = ctx->d_nodes.as<float4>();
+  sc.tris = ctx->d_tris.as<float4>();
+  sc.leaf_prim = need_leaf_prim ? ctx->d_leaf_prim.as<uint32_t>() : nullptr;
+  sc.leaf_count = multi ? ctx->d_leaf_count.as<uint16_t>() : nullptr;
+  sc.spheres = ctx->d_spheres.as<pbrtb200_sphere80>();
+  sc.sphere_o2w = ctx->d_sphere_o2w.as<float>();
+  sc.meshes = ctx->d_meshes.as<pbrtb200_mesh>();
+  sc.tri_uv = s->tri_uv ? ctx->d_tri_uv.as<float>() : nullptr;
+  sc.tri_n = s->tri_n ? ctx->d_tri_n.as<float>() : nullptr;
+  sc.tri_s = s->tri_s ? ctx->d_tri_s.as<float>() : nullptr;
+  sc.materials = ctx->d_materials.as<pbrtb200_material>();
+  sc.textures = ctx->d_textures.as<pbrtb200_texture>();
+  sc.n_prims = s->n_prims;
+  sc.n_lights = s->n_lights;
+  {
+    const pbrtb200_node32& root = s->nodes[0];
+    sc.root_ref = root.is_leaf ? (PB_LEAF_BIT | root.offset) : 0u;
+    for (int i = 0; i < 3; ++i) {
+      sc.root_bmin[i] = root.bmin[i];
+      sc.root_bmax[i] = root.bmax[i];
+    }
+  }
+  ctx->has_spheres = need_leaf_prim;
+  ctx->multi_leaf = multi;
+
+  // ---- lights; area-light triangle records are derived on the device (same arithmetic as a hit
+  // on that triangle), their CDF is accumulated here in f32, sequentially. ----
+  ctx->h_lights.assign(s->lights, s->lights + s->n_lights);
+  sc.light_slots = 0;
+  sc.area_sample_pairs = 0;
+  for (auto& l : ctx->h_lights) {
+    if (l.kind == PBRTB200_LIGHT_AREA) {
+      if (l.num_samples < 1) FAIL(PBRTB200_EINVAL, "area light needs num_samples >= 1");
+      if (l.n_tris == 0 || (uint64_t)l.first_tri + l.n_tris > s->n_area_prims)
+        FAIL(PBRTB200_EINVAL, "area light triangle range invalid");
+      sc.light_slots += (uint32_t)l.num_samples;
+      sc.area_sample_pairs += (uint32_t)l.num_samples;
+    } else if (l.kind == PBRTB200_LIGHT_POINT || l.kind == PBRTB200_LIGHT_SPOT) {
+      sc.light_slots += 1;
+    } else {
+      FAIL(PBRTB200_EINVAL, "unsupported light kind");
+    }
+  }
+  if (s->n_area_prims) {
+    for (uint32_t i = 0; i < s->n_area_prims; ++i) {
+      const uint32_t p = s->area_prims[i];
+      if (p >= s->n_prims || (s->leaf_prim && (s->leaf_prim[p] & PB_LEAF_BIT)))
+        FAIL(PBRTB200_EINVAL, "area_prims entry is not a triangle of the primitive list");
+    }
+    DevBuf d_idx;
+    CK(d_idx.ensure(sizeof(uint32_t) * s->n_area_prims));
+    CK(cudaMemcpyAsync(d_idx.p, s->area_prims, sizeof(uint32_t) * s->n_area_prims,
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_area_tris.ensure(sizeof(DAreaTri) * s->n_area_prims));
+    k_area_tri_setup<<<(s->n_area_prims + 127) / 128, 128, 0, ctx->stream>>>(
+        sc, d_idx.as<uint32_t>(), s->n_area_prims, ctx->d_area_tris.as<DAreaTri>());
+    CK(cudaGetLastError());
+    std::vector<DAreaTri> at(s->n_area_prims);
+    CK(cudaMemcpyAsync(at.data(), ctx->d_area_tris.p, sizeof(DAreaTri) * at.size(),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& l : ctx->h_lights) {
+      if (l.kind != PBRTB200_LIGHT_AREA) continue;
+      float total = 0.f;
+      for (uint32_t k = 0; k < l.n_tris; ++k) total += at[l.first_tri + k].area;
+      l.total_area = total;
+      float acc = 0.f, lo = 0.f;
+      for (uint32_t k = 0; k < l.n_tris; ++k) {
+        acc += at[l.first_tri + k].area;
+        float hi = acc / total;
+        if (k + 1 == l.n_tris) hi = 1.0f;
+        at[l.first_tri + k].cdf_lo = lo;
+        at[l.first_tri + k].cdf_hi = hi;
+        lo = hi;
+      }
+    }
+    CK(cudaMemcpyAsync(ctx->d_area_tris.p, at.data(), sizeof(DAreaTri) * at.size(),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (upload(ctx, ctx->d_lights, ctx->h_lights.data(), ctx->h_lights.size())) return PBRTB200_ENODEV;
+  sc.lights = ctx->d_lights.as<pbrtb200_light>();
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->has_scene = true;
+  return PBRTB200_OK;
+}
+
+static int run_trace_buffer(pbrtb200_ctx* ctx, bool any, const pbrtb200_ray32* d_rays, uint64_t n,
+                            pbrtb200_hit16* d_hits, uint8_t* d_occ) {
+  CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
+  TraceArgs a{};
+  a.rays = d_rays;
+  a.hits = d_hits;
+  a.occluded = d_occ;
+  a.n = n;
+  a.counter = &ctrl(ctx)->counter;
+  a.flags = &ctrl(ctx)->flags;
+  DCamera cam{};
+  return any ? launch_trace_t<true, 0>(ctx, cam, a) : launch_trace_t<false, 0>(ctx, cam, a);
+}
+
+static int finish_flags(pbrtb200_ctx* ctx, CtrlBlock* h) {
+  CK(cudaMemcpyAsync(h, ctx->d_ctrl.p, sizeof(CtrlBlock), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (h->flags & 1u) FAIL(PBRTB200_ESTACK, "BVH traversal stack overflow (depth > 64)");
+  return 0;
+}
+
+int pbrtb200_trace_closest(pbrtb200_ctx* ctx, const pbrtb200_ray32* rays, uint64_t n,
+                           pbrtb200_hit16* hits, int is_device, pbrtb200_stats* stats) {
+  if (!ctx) return PBRTB200_EINVAL;
+  if (!ctx->has_scene) FAIL(PBRTB200_EINVAL, "no scene uploaded");
+  if (n && (!rays || !hits)) FAIL(PBRTB200_EINVAL, "rays/hits is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  if (n == 0) return PBRTB200_OK;
+  const pbrtb200_ray32* d_rays = rays;
+  pbrtb200_hit16* d_hits = hits;
+  if (!is_device) {
+    CK(ctx->d_rays_in.ensure(n * sizeof(pbrtb200_ray32)));
+    CK(ctx->d_hits.ensure(n * sizeof(pbrtb200_hit16)));
+    CK(cudaMemcpyAsync(ctx->d_rays_in.p, rays, n * sizeof(pbrtb200_ray32), cudaMemcpyHostToDevice, ctx->stream));
+    d_rays = ctx->d_rays_in.as<pbrtb200_ray32>();
+    d_hits = ctx->d_hits.as<pbrtb200_hit16>();
+  }
+  StageTimer tm{ctx, stats != nullptr};
+  size_t e0 = tm.mark();
+  if (int rc = run_trace_buffer(ctx, false, d_rays, n, d_hits, nullptr)) return rc;
+  size_t e1 = tm.mark();
+  tm.span(e0, e1, 1);
+  if (!is_device)
+    CK(cudaMemcpyAsync(hits, d_hits, n * sizeof(pbrtb200_hit16), cudaMemcpyDeviceToHost, ctx->stream));
+  CtrlBlock h;
+  if (int rc = finish_flags(ctx, &h)) return rc;
+  if (stats) {
+    float ms[6];
+    tm.collect(ms);
+    stats->camera_rays = n;
+    stats->ms_trace = ms[1];
+    stats->ms_total = ms[1];
+    stats->kernel_launches = 1;
+  }
+  return PBRTB200_OK;
+}
+
+int pbrtb200_trace_any(pbrtb200_ctx* ctx, const pbrtb200_ray32* rays, uint64_t n, uint8_t* occluded,
+                       int is_device, pbrtb200_stats* stats) {
+  if (!ctx) return PBRTB200_EINVAL;
+  if (!ctx->has_scene) FAIL(PBRTB200_EINVAL, "no scene uploaded");
+  if (n && (!rays || !occluded)) FAIL(PBRTB200_EINVAL, "rays/occluded is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  if (n == 0) return PBRTB200_OK;
+  const pbrtb200_ray32* d_rays = rays;
+  uint8_t* d_occ = occluded;
+  if (!is_device) {
+    CK(ctx->d_rays_in.ensure(n * sizeof(pbrtb200_ray32)));
+    CK(ctx->d_occ.ensure(n));
+    CK(cudaMemcpyAsync(ctx->d_rays_in.p, rays, n * sizeof(pbrtb200_ray32), cudaMemcpyHostToDevice, ctx->stream));
+    d_rays = ctx->d_rays_in.as<pbrtb200_ray32>();
+    d_occ = ctx->d_occ.as<uint8_t>();
+  }
+  StageTimer tm{ctx, stats != nullptr};
+  size_t e0 = tm.mark();
+  if (int rc = run_trace_buffer(ctx, true, d_rays, n, nullptr, d_occ)) return rc;
+  size_t e1 = tm.mark();
+  tm.span(e0, e1, 3);
+  if (!is_device) CK(cudaMemcpyAsync(occluded, d_occ, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CtrlBlock h;
+  if (int rc = finish_flags(ctx, &h)) return rc;
+  if (stats) {
+    float ms[6];
+    tm.collect(ms);
+    stats->shadow_rays = n;
+    stats->ms_shadow = ms[3];
+    stats->ms_total = ms[3];
+    stats->kernel_launches = 1;
+  }
+  return PBRTB200_OK;
+}
+
+// list order -> raster order ([(y - y0) * w + (x - x0)] * spp + i)
+__global__ void k_scatter_raster(const DPixel* __restrict__ pixels, uint64_t n_samples, int spp,
+                                 int x0, int y0, int w, const float2* __restrict__ img,
+                                 const float2* __restrict__ lens, const float* __restrict__ time,
+                                 const pbrtb200_hit16* __restrict__ hits, const DCamera cam,
+                                 pbrtb200_hit16* __restrict__ out_hits, float* __restrict__ out_samples,
+                                 pbrtb200_ray32* __restrict__ out_rays) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_samples) return;
+  const uint64_t p = s / (uint32_t)spp;
+  const uint32_t i = (uint32_t)(s - p * (uint32_t)spp);
+  const DPixel px = pixels[p];
+  const uint64_t o = ((uint64_t)(px_y(px) - y0) * (uint64_t)w + (uint64_t)(px_x(px) - x0)) * (uint32_t)spp + i;
+  if (out_hits) out_hits[o] = hits[s];
+  const float2 im = img[s];
+  const float2 ln = lens ? lens[s] : make_float2(0.f, 0.f);
+  if (out_samples) {
+    float* q = out_samples + 5 * o;
+    q[0] = im.x;
+    q[1] = im.y;
+    q[2] = ln.x;
+    q[3] = ln.y;
+    q[4] = time ? time[s] : 0.f;
+  }
+  if (out_rays) {
+    f3 ro, rd;
+    camera_ray(cam, im.x, im.y, ln.x, ln.y, &ro, &rd, nullptr);
+    pbrtb200_ray32 r;
+    r.o[0] = ro.x; r.o[1] = ro.y; r.o[2] = ro.z; r.mint = 0.f;
+    r.d[0] = rd.x; r.d[1] = rd.y; r.d[2] = rd.z; r.maxt = PB_F32_MAX;
+    out_rays[o] = r;
+  }
+}
+
+static int run_raygen(pbrtb200_ctx* ctx, const DSampler& ds, bool full, uint64_t pix0, uint64_t npix,
+                      uint64_t sample0) {
+  const DPixel* px = ctx->d_pixels.as<DPixel>() + pix0;
+  const uint64_t ns = npix * (uint64_t)ds.spp;
+  if (full) {
+    k_raygen_full<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(
+        ds, px, npix, ctx->d_img.as<float2>() + sample0, ctx->d_lens.as<float2>() + sample0,
+        ctx->d_time.as<float>() + sample0);
+  } else {
+    k_raygen_image<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(
+        ds, px, ns, ctx->d_img.as<float2>() + sample0);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb200_sampler* smp,
+                          pbrtb200_hit16* out_hits, float* out_samples, pbrtb200_ray32* out_rays,
+                          int is_device, pbrtb200_stats* stats) {
+  if (!ctx) return PBRTB200_EINVAL;
+  if (!ctx->has_scene) FAIL(PBRTB200_EINVAL, "no scene uploaded");
+  if (!cam) FAIL(PBRTB200_EINVAL, "camera is NULL");
+  if (int rc = check_sampler(ctx, smp)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  if (int rc = build_pixel_list(ctx, smp, nullptr, nullptr)) return rc;
+  DSampler ds;
+  fill_sampler(ctx, smp, &ds);
+  DCamera dc;
+  fill_camera(cam, ds.spp, &dc);
+  const uint64_t npix = ctx->n_list_pixels, ns = npix * (uint64_t)ds.spp;
+  const bool full = out_samples != nullptr || cam->lens_radius > 0.0f || smp->kind != PBRTB200_SAMPLER_STRATIFIED;
+  CK(ctx->d_img.ensure(ns * sizeof(float2)));
+  if (full) {
+    CK(ctx->d_lens.ensure(ns * sizeof(float2)));
+    CK(ctx->d_time.ensure(ns * sizeof(float)));
+  }
+  CK(ctx->d_hits.ensure(ns * sizeof(pbrtb200_hit16)));
+  StageTimer tm{ctx, stats != nullptr};
+  size_t e0 = tm.mark();
+  if (int rc = run_raygen(ctx, ds, full, 0, npix, 0)) return rc;
+  size_t e1 = tm.mark();
+  CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
+  TraceArgs a{};
+  a.img = ctx->d_img.as<float2>();
+  a.lens = (full && cam->lens_radius > 0.0f) ? ctx->d_lens.as<float2>() : nullptr;
+  a.hits = ctx->d_hits.as<pbrtb200_hit16>();
+  a.n = ns;
+  a.counter = &ctrl(ctx)->counter;
+  a.flags = &ctrl(ctx)->flags;
+  if (int rc = launch_trace_t<false, 1>(ctx, dc, a)) return rc;
+  size_t e2 = tm.mark();
+  // outputs in raster order
+  pbrtb200_hit16* d_oh = nullptr;
+  float* d_os = nullptr;
+  pbrtb200_ray32* d_or = nullptr;
+  if (is_device) {
+    d_oh = out_hits;
+    d_os = out_samples;
+    d_or = out_rays;
+  } else {
+    if (out_hits) {
+      CK(ctx->d_out_a.ensure(ns * sizeof(pbrtb200_hit16)));
+      d_oh = ctx->d_out_a.as<pbrtb200_hit16>();
+    }
+    if (out_samples) {
+      CK(ctx->d_out_b.ensure(ns * 5 * sizeof(float)));
+      d_os = ctx->d_out_b.as<float>();
+    }
+    if (out_rays) {
+      CK(ctx->d_out_c.ensure(ns * sizeof(pbrtb200_ray32)));
+      d_or = ctx->d_out_c.as<pbrtb200_ray32>();
+    }
+  }
+  if (d_oh || d_os || d_or) {
+    k_scatter_raster<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->d_pixels.as<DPixel>(), ns, ds.spp, smp->x_start, smp->y_start, smp->x_end - smp->x_start,
+        ctx->d_img.as<float2>(), full ? ctx->d_lens.as<float2>() : nullptr,
+        full ? ctx->d_time.as<float>() : nullptr, ctx->d_hits.as<pbrtb200_hit16>(), dc, d_oh, d_os, d_or);
+    CK(cudaGetLastError());
+  }
+  size_t e3 = tm.mark();
+  tm.span(e0, e1, 0);
+  tm.span(e1, e2, 1);
+  tm.span(e2, e3, 4);
+  tm.span(e0, e3, 5);
+  if (!is_device) {
+    if (out_hits) CK(cudaMemcpyAsync(out_hits, d_oh, ns * sizeof(pbrtb200_hit16), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_samples) CK(cudaMemcpyAsync(out_samples, d_os, ns * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_rays) CK(cudaMemcpyAsync(out_rays, d_or, ns * sizeof(pbrtb200_ray32), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CtrlBlock h;
+  if (int rc = finish_flags(ctx, &h)) return rc;
+  if (stats) {
+    float ms[6];
+    tm.collect(ms);
+    stats->camera_rays = ns;
+    stats->ms_raygen = ms[0];
+    stats->ms_trace = ms[1];
+    stats->ms_film = ms[4];
+    stats->ms_total = ms[5];
+    stats->kernel_launches = 2 + ((d_oh || d_os || d_or) ? 1 : 0);
+  }
+  return PBRTB200_OK;
+}
+
+int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb200_sampler* smp,
+                    const pbrtb200_film* film, const pbrtb200_integrator* integ,
+                    const pbrtb200_tileset* tiles, float* out_xyzw, int out_is_device,
+                    pbrtb200_stats* stats) {
+  if (!ctx) return PBRTB200_EINVAL;
+  if (!ctx->has_scene) FAIL(PBRTB200_EINVAL, "no scene uploaded");
+  if (!cam || !film || !integ || !out_xyzw) FAIL(PBRTB200_EINVAL, "NULL argument");
+  if (int rc = check_sampler(ctx, smp)) return rc;
+  if (integ->kind != 0) FAIL(PBRTB200_EINVAL, "unsupported integrator kind");
+  if (film->x_pixel_count < 1 || film->y_pixel_count < 1) FAIL(PBRTB200_EINVAL, "empty film");
+  if (!(film->filter_xw > 0.f) || !(film->filter_yw > 0.f)) FAIL(PBRTB200_EINVAL, "filter width must be > 0");
+  if (ctx->sc.n_lights && !ctx->d_materials.p) FAIL(PBRTB200_EINVAL, "scene has no materials");
+  CK(cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  if (int rc = build_pixel_list(ctx, smp, film, tiles)) return rc;
+
+  DSampler ds;
+  fill_sampler(ctx, smp, &ds);
+  DCamera dc;
+  fill_camera(cam, ds.spp, &dc);
+  const uint64_t npix = ctx->n_list_pixels, ns = npix * (uint64_t)ds.spp;
+  const bool full = cam->lens_radius > 0.0f || smp->kind != PBRTB200_SAMPLER_STRATIFIED;
+  const uint32_t slots = std::max(1u, ctx->sc.light_slots);
+
+  uint64_t chunk_pix = std::max<uint64_t>(1, kChunkSamples / (uint64_t)ds.spp);
+  chunk_pix = std::min(chunk_pix, npix);
+  const uint64_t chunk_ns = chunk_pix * (uint64_t)ds.spp;
+  if (chunk_ns * slots >= 0xFFFFFFFFull) FAIL(PBRTB200_EINVAL, "too many light samples per chunk");
+
+  CK(ctx->d_img.ensure(ns * sizeof(float2)));
+  if (full) {
+    CK(ctx->d_lens.ensure(ns * sizeof(float2)));
+    CK(ctx->d_time.ensure(ns * sizeof(float)));
+  }
+  CK(ctx->d_xyz.ensure(ns * sizeof(float4)));
+  CK(ctx->d_hits.ensure(chunk_ns * sizeof(pbrtb200_hit16)));
+  CK(ctx->d_Le.ensure(chunk_ns * sizeof(float4)));
+  CK(ctx->d_contrib.ensure(chunk_ns * slots * sizeof(float4)));
+  CK(ctx->d_sq_rays.ensure(chunk_ns * slots * sizeof(pbrtb200_ray32)));
+  CK(ctx->d_sq_slots.ensure(chunk_ns * slots * sizeof(uint32_t)));
+  const size_t film_px = (size_t)film->x_pixel_count * (size_t)film->y_pixel_count;
+  float4* d_film = nullptr;
+  if (out_is_device) {
+    d_film = reinterpret_cast<float4*>(out_xyzw);
+  } else {
+    CK(ctx->d_film.ensure(film_px * sizeof(float4)));
+    d_film = ctx->d_film.as<float4>();
+  }
+  CK(cudaMemcpyToSymbolAsync(c_filter_table, film->filter_table, sizeof(float) * 256, 0,
+                             cudaMemcpyHostToDevice, ctx->stream));
+
+  StageTimer tm{ctx, stats != nullptr};
+  uint32_t launches = 0;
+  size_t eA = tm.mark();
+  CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
+  if (!tiles || !tiles->n_rects)
+    ;  // every film pixel is written by k_film
+  else
+    CK(cudaMemsetAsync(d_film, 0, film_px * sizeof(float4), ctx->stream));
+
+  for (uint64_t p0 = 0; p0 < npix; p0 += chunk_pix) {
+    const uint64_t cp = std::min(chunk_pix, npix - p0);
+    const uint64_t s0 = p0 * (uint64_t)ds.spp, cn = cp * (uint64_t)ds.spp;
+    size_t e0 = tm.mark();
+    if (int rc = run_raygen(ctx, ds, full, p0, cp, s0)) return rc;
+    size_t e1 = tm.mark();
+    CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(&ctrl(ctx)->sq_count, 0, sizeof(uint32_t), ctx->stream));
+    TraceArgs ta{};
+    ta.img = ctx->d_img.as<float2>() + s0;
+    ta.lens = full && cam->lens_radius > 0.0f ? ctx->d_lens.as<float2>() + s0 : nullptr;
+    ta.hits = ctx->d_hits.as<pbrtb200_hit16>();
+    ta.n = cn;
+    ta.counter = &ctrl(ctx)->counter;
+    ta.flags = &ctrl(ctx)->flags;
+    if (int rc = launch_trace_t<false, 1>(ctx, dc, ta)) return rc;
+    size_t e2 = tm.mark();
+    launches += 2;
+    if (ctx->sc.n_lights) {
+      ShadeArgs sa{};
+      sa.img = ta.img;
+      sa.lens = ta.lens;
+      sa.hits = ta.hits;
+      sa.pixels = ctx->d_pixels.as<DPixel>() + p0;
+      sa.area_tris = ctx->d_area_tris.as<DAreaTri>();
+      sa.Le = ctx->d_Le.as<float4>();
+      sa.contrib = ctx->d_contrib.as<float4>();
+      sa.sq_rays = ctx->d_sq_rays.as<pbrtb200_ray32>();
+      sa.sq_slots = ctx->d_sq_slots.as<uint32_t>();
+      sa.sq_count = &ctrl(ctx)->sq_count;
+      sa.n = cn;
+      sa.strict_flags = integ->strict_flags;
+      k_shade<<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, ds, sa);
+      CK(cudaGetLastError());
+      size_t e3 = tm.mark();
+      CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));
+      TraceArgs sh{};
+      sh.rays = sa.sq_rays;
+      sh.contrib = sa.contrib;
+      sh.slots = sa.sq_slots;
+      sh.n_dyn = &ctrl(ctx)->sq_count;
+      sh.counter = &ctrl(ctx)->counter;
+      sh.flags = &ctrl(ctx)->flags;
+      if (int rc = launch_trace_t<true, 0>(ctx, dc, sh)) return rc;
+      size_t e4 = tm.mark();
+      tm.span(e2, e3, 2);
+      tm.span(e3, e4, 3);
+      launches += 2;
+    }
+    size_t e5 = tm.mark();
+    ResolveArgs ra{};
+    ra.hits = ta.hits;
+    ra.Le = ctx->d_Le.as<float4>();
+    ra.contrib = ctx->d_contrib.as<float4>();
+    ra.xyz = ctx->d_xyz.as<float4>();
+    ra.n = cn;
+    ra.out_base = s0;
+    ra.nan_count = &ctrl(ctx)->nan_count;
+    ra.hit_total = &ctrl(ctx)->hit_total;
+    ra.shadow_total = &ctrl(ctx)->shadow_total;
+    ra.sq_count = &ctrl(ctx)->sq_count;
+    ra.shaded = ctx->sc.n_lights ? 1 : 0;
+    k_resolve<<<(unsigned)((cn + 255) / 256), 256, 0, ctx->stream>>>(ctx->sc, ra);
+    CK(cudaGetLastError());
+    size_t e6 = tm.mark();
+    launches += 1;
+    tm.span(e0, e1, 0);
+    tm.span(e1, e2, 1);
+    tm.span(e5, e6, 2);
+  }
+  size_t eF0 = tm.mark();
+  {
+    DFilm df;
+    df.x_start = film->x_pixel_start;
+    df.y_start = film->y_pixel_start;
+    df.x_count = film->x_pixel_count;
+    df.y_count = film->y_pixel_count;
+    df.xw = film->filter_xw;
+    df.yw = film->filter_yw;
+    df.inv_xw = 1.0f / film->filter_xw;  // filter.rs:12-19
+    df.inv_yw = 1.0f / film->filter_yw;
+    df.sx0 = smp->x_start;
+    df.sx1 = smp->x_end;
+    df.sy0 = smp->y_start;
+    df.sy1 = smp->y_end;
+    df.spp = ds.spp;
+    FilmArgs fa{};
+    fa.img = ctx->d_img.as<float2>();
+    fa.xyz = ctx->d_xyz.as<float4>();
+    fa.pix_index = ctx->d_pix_index.as<int32_t>();
+    fa.rects = ctx->d_rects.as<int32_t>();
+    fa.rect_prefix = ctx->d_rect_prefix.as<uint32_t>();
+    fa.n_rects = ctx->n_rects;
+    fa.n_pixels = ctx->n_film_pixels;
+    fa.out = d_film;
+    k_film<<<(fa.n_pixels + 127) / 128, 128, 0, ctx->stream>>>(df, fa);
+    CK(cudaGetLastError());
+    launches += 1;
+  }
+  size_t eF1 = tm.mark();
+  tm.span(eF0, eF1, 4);
+  tm.span(eA, eF1, 5);
+  if (!out_is_device)
+    CK(cudaMemcpyAsync(out_xyzw, d_film, film_px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CtrlBlock h;
+  if (int rc = finish_flags(ctx, &h)) return rc;
+  if (stats) {
+    float ms[6];
+    tm.collect(ms);
+    stats->camera_rays = ns;
+    stats->camera_hits = h.hit_total;
+    stats->shadow_rays = h.shadow_total;
+    stats->ms_raygen = ms[0];
+    stats->ms_trace = ms[1];
+    stats->ms_shade = ms[2];
+    stats->ms_shadow = ms[3];
+    stats->ms_film = ms[4];
+    stats->ms_total = ms[5];
+    stats->kernel_launches = launches;
+    stats->nan_samples = h.nan_count;
+  }
+  if (h.nan_count) FAIL(PBRTB200_ENAN, "Invalid radiance value!");
+  return PBRTB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Device-side scene layout (HBM) for the B200 back end.  See DESIGN.md §"Data layout in HBM".
+#pragma once
+#include "../../include/pbrtb200.h"
+#include "dmath.cuh"
+
+#define PB_LEAF_BIT 0x80000000u
+#define PB_SM_STACK 24                                   // traversal-stack entries kept in smem
+#define PB_LM_STACK (PBRTB200_STACK_DEPTH - PB_SM_STACK) // deeper entries spill to local memory
+#define PB_TRACE_THREADS 128
+
+// BVH "pair node", 64 B = 4 x float4, built at upload from the reference's linear PackedBVHNode
+// array (pbrtb200_node32).  An inner node stores BOTH children's boxes so one 64-byte fetch
+// (4 x LDG.128) replaces the two dependent 32-byte fetches of a test-at-pop traversal:
+//   q0 = (c0.min.x, c0.min.y, c0.min.z, c0.max.x)
+//   q1 = (c0.max.y, c0.max.z, c1.min.x, c1.min.y)
+//   q2 = (c1.min.z, c1.max.x, c1.max.y, c1.max.z)
+//   q3 = bits(ref0, ref1, unused, axis)
+// c0 is the reference's first child (node i+1), c1 its second child (second_child_offset).
+// ref: bit31 = 0 -> index of another pair node; bit31 = 1 -> leaf, low 31 bits = prim_offset into
+// the ordered primitive list (leaf sizes live in `leaf_count`, only read when some leaf holds >1).
+struct DScene {
+  const float4* __restrict__ nodes;
+  const float4* __restrict__ tris;            // 3 x float4 per triangle (pbrtb200_tri48)
+  const uint32_t* __restrict__ leaf_prim;     // NULL when the scene has no spheres (prim i == tri i)
+  const uint16_t* __restrict__ leaf_count;    // NULL when every leaf holds exactly one primitive
+  const pbrtb200_sphere80* __restrict__ spheres;
+  const float* __restrict__ sphere_o2w;
+  const pbrtb200_mesh* __restrict__ meshes;
+  const float* __restrict__ tri_uv;
+  const float* __restrict__ tri_n;
+  const float* __restrict__ tri_s;
+  const pbrtb200_material* __restrict__ materials;
+  const pbrtb200_texture* __restrict__ textures;
+  const pbrtb200_light* __restrict__ lights;
+  uint32_t root_ref;
+  uint32_t n_prims;
+  uint32_t n_lights;
+  uint32_t light_slots;        // sum over lights of (area ? num_samples : 1)
+  uint32_t area_sample_pairs;  // sum over area lights of num_samples (RNG pairs per camera sample)
+  float root_bmin[3], root_bmax[3];
+};
+
+struct DCamera {
+  float r2c[16];
+  float c2w[16];
+  float dx[3], dy[3];
+  float sopen, sclose, lens_radius, focal_distance;
+  float diff_scale;  // 1 / sqrt(samples_per_pixel)  (sampler_renderer.rs:96)
+};
+
+// One sampler pixel to evaluate: position, owning task and index within the task's sub-window
+// (which fixes its offset in the task's RNG word stream).
+struct DPixel {
+  int32_t xy;     // x | y << 16 (signed 16-bit each; sample extents can start at -radius)
+  uint32_t k;     // raster index of the pixel inside its task window
+  uint32_t task;  // task index -> key
+};
+PB_DEV int px_x(DPixel p) { return (int)(short)(p.xy & 0xFFFF); }
+PB_DEV int px_y(DPixel p) { return (int)(short)((p.xy >> 16) & 0xFFFF); }
+
+struct DSampler {
+  int kind;  // 0 stratified, 1 LD
+  int xs, ys, jitter;
+  int spp;
+  uint32_t words_per_pixel;
+  uint32_t cam_words;  // words of the camera-sample block (light-sample floats follow)
+  float sopen, sclose;
+  const uint32_t* __restrict__ task_keys;  // 8 words per task
+};

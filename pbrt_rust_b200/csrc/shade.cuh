@@ -1,0 +1,682 @@
+// Surface interaction, material/texture evaluation, light sampling and the Whitted light loop
+// (sm_100a), one thread per camera sample that hit something.
+//
+// Replaces WhittedIntegrator::li (src/integrator/whitted.rs:30-66), Intersection::get_bsdf
+// (src/intersection.rs:40-47), DifferentialGeometry::{new_with, compute_differentials}
+// (src/diff_geom.rs:52-152), Triangle::intersect's dg part and get_shading_geometry
+// (src/shape/mesh.rs:105-193, 220-262), Sphere::intersect's dg part (src/shape/sphere.rs:143-180)
+// with compute_dg (src/shape/helpers.rs:17-43), MatteMaterial / PlasticMaterial::get_bsdf
+// (src/material/matte.rs:30-51, plastic.rs:32-55), BSDF::{new_with_eta, world_to_local, f}
+// (src/bsdf/mod.rs:70-149), Lambertian / OrenNayar / Microfacet(Blinn) / Fresnel::Dielectric
+// (src/bsdf/{lambertian,orennayar,microfacet,fresnel}.rs), Constant / Checkerboard / UV textures
+// with UVMapping2D / PlanarMapping2D (src/texture/*), PointLight / SpotLight::sample_l
+// (src/light/{point,spot}.rs) and VisibilityTester::segment (src/visibility_tester.rs:16-24).
+// Deviations from the as-written reference are exactly those of SURVEY §0.2 (D2, D3, D7, D8, D9,
+// D10, D11) and are listed in DESIGN.md.
+#pragma once
+#include "scene.cuh"
+#include "trace.cuh"
+
+struct DG {
+  f3 p, nn;
+  float u, v;
+  f3 dpdu, dpdv, dndu, dndv, dpdx, dpdy;
+  float dudx, dudy, dvdx, dvdy;
+};
+
+// diff_geom.rs:52-79
+PB_DEV DG dg_new(f3 p, f3 dpdu, f3 dpdv, f3 dndu, f3 dndv, float u, float v, bool flip) {
+  DG g;
+  f3 norm = normalize3(cross3(dpdu, dpdv));
+  if (flip) norm = norm * -1.f;
+  g.p = p;
+  g.nn = norm;
+  g.u = u;
+  g.v = v;
+  g.dpdu = dpdu;
+  g.dpdv = dpdv;
+  g.dndu = dndu;
+  g.dndv = dndv;
+  g.dpdx = mk3(0, 0, 0);
+  g.dpdy = mk3(0, 0, 0);
+  g.dudx = g.dudy = g.dvdx = g.dvdy = 0.f;
+  return g;
+}
+
+// diff_geom.rs:81-152 (has_differentials is always true for camera rays, camera/mod.rs:215)
+PB_DEV void dg_compute_differentials(DG& g, f3 rxo, f3 ryo, f3 rxd, f3 ryd) {
+  const f3 nvec = g.nn;
+  const float d = -(dot3(nvec, g.p));
+  f3 px, py;
+  {
+    const float ndrx = -(dot3(nvec, rxo) + d);
+    const float ndrd = dot3(nvec, rxd);
+    const float tx = ndrx / ndrd;
+    px = rxo + tx * rxd;
+  }
+  {
+    const float ndry = -(dot3(nvec, ryo) + d);
+    const float ndrd = dot3(nvec, ryd);
+    const float ty = ndry / ndrd;
+    py = ryo + ty * ryd;
+  }
+  g.dpdx = px - g.p;
+  g.dpdy = py - g.p;
+  int ax0, ax1;
+  if (fabsf(g.nn.x) > fabsf(g.nn.y) && fabsf(g.nn.x) > fabsf(g.nn.z)) {
+    ax0 = 1;
+    ax1 = 2;
+  } else if (fabsf(g.nn.y) > fabsf(g.nn.z)) {
+    ax0 = 0;
+    ax1 = 2;
+  } else {
+    ax0 = 0;
+    ax1 = 1;
+  }
+  const float a00 = comp(g.dpdu, ax0), a01 = comp(g.dpdv, ax0);
+  const float a10 = comp(g.dpdu, ax1), a11 = comp(g.dpdv, ax1);
+  if (!solve2x2_(a00, a01, a10, a11, comp(g.dpdx, ax0), comp(g.dpdx, ax1), &g.dudx, &g.dvdx))
+    g.dudx = g.dvdx = 0.f;
+  if (!solve2x2_(a00, a01, a10, a11, comp(g.dpdy, ax0), comp(g.dpdy, ax1), &g.dudy, &g.dvdy))
+    g.dudy = g.dvdy = 0.f;
+}
+
+struct TriData {
+  f3 p1, p2, p3;
+  uint32_t mesh, attr;
+  float uv[3][2];
+};
+PB_DEV TriData load_tri(const DScene& sc, uint32_t tri) {
+  TriData t;
+  const float4* tp = sc.tris + 3ull * tri;
+  const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+  t.p1 = mk3(a.x, a.y, a.z);
+  t.p2 = mk3(b.x, b.y, b.z);
+  t.p3 = mk3(c.x, c.y, c.z);
+  t.mesh = __float_as_uint(a.w);
+  t.attr = __float_as_uint(b.w);
+  if (sc.tri_uv && sc.meshes[t.mesh].has_uv) {  // mesh.rs:74-87
+    const float* q = sc.tri_uv + 6ull * t.attr;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      t.uv[k][0] = __ldg(q + 2 * k);
+      t.uv[k][1] = __ldg(q + 2 * k + 1);
+    }
+  } else {
+    t.uv[0][0] = 0.f; t.uv[0][1] = 0.f;
+    t.uv[1][0] = 1.f; t.uv[1][1] = 0.f;
+    t.uv[2][0] = 1.f; t.uv[2][1] = 1.f;
+  }
+  return t;
+}
+
+// mesh.rs:220-262
+PB_DEV DG tri_dg(const TriData& t, f3 o, f3 d, float th, float b1, float b2, bool flip) {
+  const float du1 = t.uv[0][0] - t.uv[2][0];
+  const float du2 = t.uv[1][0] - t.uv[2][0];
+  const float dv1 = t.uv[0][1] - t.uv[2][1];
+  const float dv2 = t.uv[1][1] - t.uv[2][1];
+  const f3 dp1 = t.p1 - t.p3, dp2 = t.p2 - t.p3;
+  f3 dpdu, dpdv;
+  const float determinant = du1 * dv2 - dv1 * du2;
+  if (determinant == 0.0f) {
+    coordinate_system_(normalize3(cross3(t.p3 - t.p1, t.p2 - t.p1)), &dpdu, &dpdv);
+  } else {
+    const float inv_det = 1.0f / determinant;
+    dpdu = (dv2 * dp1 - dv1 * dp2) * inv_det;
+    dpdv = (-du2 * dp1 + du1 * dp2) * inv_det;
+  }
+  const float b0 = 1.0f - b1 - b2;
+  const float tu = b0 * t.uv[0][0] + b1 * t.uv[1][0] + b2 * t.uv[2][0];
+  const float tv = b0 * t.uv[0][1] + b1 * t.uv[1][1] + b2 * t.uv[2][1];
+  return dg_new(o + (d * th), dpdu, dpdv, mk3(0, 0, 0), mk3(0, 0, 0), tu, tv, flip);
+}
+
+// mesh.rs:105-193 (as written, including the (ss, ts) tuple binding and the zeroed differentials)
+PB_DEV DG tri_shading_geometry(const DScene& sc, const TriData& t, const pbrtb200_mesh& m,
+                               const DG& dg) {
+  const bool has_n = sc.tri_n && m.has_n, has_s = sc.tri_s && m.has_s;
+  if (!has_n && !has_s) return dg;
+  float b[3];
+  {
+    float x0, x1;
+    if (solve2x2_(t.uv[1][0] - t.uv[0][0], t.uv[2][0] - t.uv[0][0], t.uv[1][1] - t.uv[0][1],
+                  t.uv[2][1] - t.uv[0][1], dg.u - t.uv[0][0], dg.v - t.uv[0][1], &x0, &x1)) {
+      b[0] = 1.0f - x0 - x1;
+      b[1] = x0;
+      b[2] = x1;
+    } else {
+      const float third = 1.f / 3.f;
+      b[0] = b[1] = b[2] = third;
+    }
+  }
+  f3 n0, n1, n2;
+  if (has_n) {
+    const float* q = sc.tri_n + 9ull * t.attr;
+    n0 = mk3(q[0], q[1], q[2]);
+    n1 = mk3(q[3], q[4], q[5]);
+    n2 = mk3(q[6], q[7], q[8]);
+  }
+  f3 ns = has_n ? normalize3(xf_vec(m.o2w, b[0] * n0 + b[1] * n1 + b[2] * n2)) : dg.nn;
+  f3 ss;
+  if (has_s) {
+    const float* q = sc.tri_s + 9ull * t.attr;
+    ss = normalize3(xf_vec(
+        m.o2w, b[0] * mk3(q[0], q[1], q[2]) + b[1] * mk3(q[3], q[4], q[5]) + b[2] * mk3(q[6], q[7], q[8])));
+  } else {
+    ss = normalize3(dg.dpdu);
+  }
+  f3 ts = cross3(ss, ns);
+  if (len2(ts) > 0.f) {
+    ss = normalize3(ts);
+    ts = cross3(ns, ts);
+  } else {
+    coordinate_system_(ns, &ss, &ts);
+  }
+  f3 dndu = mk3(0, 0, 0), dndv = mk3(0, 0, 0);
+  if (has_n) {
+    const float du1 = t.uv[0][0] - t.uv[2][0], du2 = t.uv[1][0] - t.uv[2][0];
+    const float dv1 = t.uv[0][1] - t.uv[2][1], dv2 = t.uv[1][1] - t.uv[2][1];
+    const f3 dn1 = n0 - n2, dn2 = n1 - n2;
+    const float determinant = du1 * dv2 - dv1 * du2;
+    if (determinant != 0.0f) {
+      const float inv_det = 1.0f / determinant;
+      dndu = (dv2 * dn1 - dv1 * dn2) * inv_det;
+      dndv = (-du2 * dn1 + du1 * dn2) * inv_det;
+    }
+  }
+  return dg_new(dg.p, ss, ts, xf_nrm(m.o2w_inv, dndu), xf_nrm(m.o2w_inv, dndv), dg.u, dg.v,
+                m.flip != 0);
+}
+
+// sphere.rs:143-180 + helpers.rs:17-43
+PB_DEV DG sphere_dg(const pbrtb200_sphere80& s, const float* o2w, f3 ow, f3 dw, float t_hit,
+                    float phi) {
+  const f3 o = xf_pt(s.w2o, ow), d = xf_vec(s.w2o, dw);
+  const f3 p_hit = o + (d * t_hit);
+  const float u = phi / s.phi_max;
+  const float theta = acosf(rclampf(p_hit.z / s.radius, -1.0f, 1.0f));
+  const float v = (theta - s.theta_min) / (s.theta_max - s.theta_min);
+  const float zradius = sqrtf(p_hit.x * p_hit.x + p_hit.y * p_hit.y);
+  const float inv_zradius = 1.0f / zradius;
+  const float cos_phi = p_hit.x * inv_zradius;
+  const float sin_phi = p_hit.y * inv_zradius;
+  const f3 dpdu = mk3(-s.phi_max * p_hit.y, s.phi_max * p_hit.x, 0.0f);
+  const f3 dpdv = (s.theta_max - s.theta_min) *
+                  mk3(p_hit.z * cos_phi, p_hit.z * sin_phi, -s.radius * sinf(theta));
+  const f3 d2pduu = -s.phi_max * s.phi_max * mk3(p_hit.x, p_hit.y, 0.0f);
+  const f3 d2pduv = (s.theta_max - s.theta_min) * p_hit.z * s.phi_max * mk3(-sin_phi, cos_phi, 0.0f);
+  const f3 d2pdvv = -(s.theta_max - s.theta_min) * (s.theta_max - s.theta_min) * p_hit;
+  const float ee = dot3(dpdu, dpdu), ff = dot3(dpdu, dpdv), gg = dot3(dpdv, dpdv);
+  const f3 nn = normalize3(cross3(dpdu, dpdv));
+  const float e = dot3(nn, d2pduu), f = dot3(nn, d2pduv), g = dot3(nn, d2pdvv);
+  const float inveeggff2 = 1.0f / (ee * gg - ff * ff);
+  const f3 dndu = (f * ff - e * gg) * inveeggff2 * dpdu + (e * ff - f * ee) * inveeggff2 * dpdv;
+  const f3 dndv = (g * ff - f * gg) * inveeggff2 * dpdu + (f * ff - g * ee) * inveeggff2 * dpdv;
+  // Normal transform uses (o2w).m_inv == w2o
+  return dg_new(xf_pt(o2w, p_hit), xf_vec(o2w, dpdu), xf_vec(o2w, dpdv), xf_nrm(s.w2o, dndu),
+                xf_nrm(s.w2o, dndv), u, v, s.flip != 0);
+}
+
+// ---- textures ---------------------------------------------------------------------------------
+PB_DEV void tex_map(const pbrtb200_texture& tx, const DG& dg, float m[6]) {
+  if (tx.map_kind == PBRTB200_MAP_UV) {  // mapping2d.rs:66-76
+    m[0] = tx.map[0] * dg.u + tx.map[2];
+    m[1] = tx.map[1] * dg.v + tx.map[3];
+    m[2] = tx.map[0] * dg.dudx;
+    m[3] = tx.map[1] * dg.dvdx;
+    m[4] = tx.map[0] * dg.dudy;
+    m[5] = tx.map[1] * dg.dvdy;
+  } else {  // mapping2d.rs:199-210
+    const f3 vs = mk3(tx.map[0], tx.map[1], tx.map[2]), vt = mk3(tx.map[3], tx.map[4], tx.map[5]);
+    m[0] = tx.map[6] + dot3(dg.p, vs);
+    m[1] = tx.map[7] + dot3(dg.p, vt);
+    m[2] = dot3(vs, dg.dpdx);
+    m[3] = dot3(vt, dg.dpdx);
+    m[4] = dot3(vs, dg.dpdy);
+    m[5] = dot3(vt, dg.dpdy);
+  }
+}
+PB_DEV float bump_int_(float x) {  // checkerboard.rs:62-66
+  const float half_x = x / 2.0f;
+  return floorf(half_x) + 2.0f * fmaxf(half_x - floorf(half_x) - 0.5f, 0.0f);
+}
+// Nested checkerboards are supported to depth 3 (validated at upload).
+template <int DEPTH>
+PB_DEV f3 tex_eval(const DScene& sc, int id, const DG& dg) {
+  const pbrtb200_texture tx = sc.textures[id];
+  if (tx.kind == PBRTB200_TEX_CONSTANT) return mk3(tx.value[0], tx.value[1], tx.value[2]);
+  float m[6];
+  tex_map(tx, dg, m);
+  if (tx.kind == PBRTB200_TEX_UV)  // uv.rs:20-26
+    return mk3(m[0] - floorf(m[0]), m[1] - floorf(m[1]), 0.0f);
+  if constexpr (DEPTH == 0) {
+    return mk3(0.f, 0.f, 0.f);
+  } else {
+    const float s = m[0], t = m[1];
+    // checkerboard.rs:38-44 (i32 arithmetic wraps in release builds)
+    const int sum = (int)((uint32_t)f2i_sat(floorf(s)) + (uint32_t)f2i_sat(floorf(t)));
+    const bool first = (sum % 2) == 0;
+    bool point = tx.aa == 0;
+    float ds = 0.f, dt = 0.f, s0 = 0.f, t0 = 0.f, s1 = 0.f, t1 = 0.f;
+    if (!point) {
+      ds = fmaxf(fabsf(m[2]), fabsf(m[4]));
+      dt = fmaxf(fabsf(m[3]), fabsf(m[5]));
+      s0 = s - ds;
+      t0 = t - dt;
+      s1 = s + ds;
+      t1 = t + dt;
+      if (floorf(s0) == floorf(s1) && floorf(t0) == floorf(t1)) point = true;
+    }
+    if (point) return tex_eval<DEPTH - 1>(sc, first ? tx.tex1 : tx.tex2, dg);
+    const float sint = ds > 0.0f ? (bump_int_(s1) - bump_int_(s0)) / (2.0f * ds) : 0.0f;
+    const float tint = dt > 0.0f ? (bump_int_(t1) - bump_int_(t0)) / (2.0f * dt) : 0.0f;
+    const float area_sq = (ds > 1.0f || dt > 1.0f) ? 0.5f : sint + tint - 2.0f * sint * tint;
+    const f3 a = tex_eval<DEPTH - 1>(sc, tx.tex1, dg), b = tex_eval<DEPTH - 1>(sc, tx.tex2, dg);
+    return a * (1.0f - area_sq) + b * area_sq;  // Lerp::lerp_with, utils/mod.rs:20
+  }
+}
+
+// ---- BxDFs (local shading frame) ---------------------------------------------------------------
+PB_DEV float abs_cos_theta_(f3 v) { return fabsf(v.z); }
+PB_DEV float sin_theta_(f3 v) { return sqrtf(fmaxf(0.f, 1.0f - v.z * v.z)); }  // bsdf/utils.rs:7-8
+PB_DEV float cos_phi_(f3 v) {
+  const float st = sin_theta_(v);
+  return st == 0.0f ? 1.0f : rclampf(v.x / st, -1.0f, 1.0f);
+}
+PB_DEV float sin_phi_(f3 v) {
+  const float st = sin_theta_(v);
+  return st == 0.0f ? 0.0f : rclampf(v.y / st, -1.0f, 1.0f);
+}
+PB_DEV f3 mul3(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+PB_DEV f3 div3s(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }  // Spectrum / f32
+PB_DEV bool is_black(f3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
+
+// fresnel.rs:62-91 Dielectric arm (all channels equal)
+PB_DEV float fresnel_dielectric_(float cosi, float eta_i, float eta_t) {
+  const float ci = rclampf(cosi, -1.0f, 1.0f);
+  float ei = eta_i, et = eta_t;
+  if (cosi <= 0.0f) {
+    const float tmp = ei;
+    ei = et;
+    et = tmp;
+  }
+  const float sint = (ei / et) * sqrtf(fmaxf(1.0f - ci * ci, 0.0f));
+  if (sint >= 1.0f) return 1.0f;
+  const float cost = sqrtf(fmaxf(1.0f - sint * sint, 0.0f));
+  const float aci = fabsf(ci);
+  const float rparl = ((et * aci) - (ei * cost)) / ((et * aci) + (ei * cost));
+  const float rperp = ((ei * aci) - (et * cost)) / ((ei * aci) + (et * cost));
+  return (rparl * rparl + rperp * rperp) / 2.0f;
+}
+PB_DEV f3 lambertian_f(f3 r) {  // lambertian.rs:20-23
+  const float invpi = 1.0f / PB_PI;
+  return r * invpi;
+}
+PB_DEV f3 orennayar_f(f3 r, float A, float B, f3 wo, f3 wi) {  // orennayar.rs:36-60
+  const float sinthetai = sin_theta_(wi), sinthetao = sin_theta_(wo);
+  float maxcos = 0.0f;
+  if (!(sinthetai < 1e-4f || sinthetao < 1e-4f)) {
+    const float sinphii = sin_phi_(wi), cosphii = cos_phi_(wi);
+    const float sinphio = sin_phi_(wo), cosphio = cos_phi_(wo);
+    maxcos = fmaxf(cosphii * cosphio + sinphii * sinphio, 0.0f);
+  }
+  float sinalpha, tanbeta;
+  if (abs_cos_theta_(wi) > abs_cos_theta_(wo)) {
+    sinalpha = sinthetao;
+    tanbeta = sinthetai / abs_cos_theta_(wi);
+  } else {
+    sinalpha = sinthetai;
+    tanbeta = sinthetao / abs_cos_theta_(wo);
+  }
+  const float invpi = 1.0f / PB_PI;
+  return r * invpi * (A + B * maxcos * sinalpha * tanbeta);
+}
+PB_DEV f3 microfacet_blinn_f(f3 r, float e, f3 wo, f3 wi) {  // microfacet.rs:32-38,71-99
+  const float cos_o = abs_cos_theta_(wo), cos_i = abs_cos_theta_(wi);
+  if (cos_o == 0.0f || cos_i == 0.0f) return mk3(0.f, 0.f, 0.f);
+  const f3 wh = normalize3(wo + wi);
+  const float cos_h = dot3(wi, wh);
+  const float F = fresnel_dielectric_(cos_h, 1.5f, 1.0f);
+  const float invtwopi = 1.0f / (2.0f * PB_PI);
+  const float D = (e + 2.0f) * invtwopi * powf(abs_cos_theta_(wh), e);
+  const float ndotwh = abs_cos_theta_(wh), ndotwo = abs_cos_theta_(wo), ndotwi = abs_cos_theta_(wi);
+  const float wodotwh = fabsf(dot3(wo, wh));
+  const float G =
+      fminf(fminf(2.0f * ndotwh * ndotwo / wodotwh, 2.0f * ndotwh * ndotwi / wodotwh), 1.0f);
+  return div3s(mul3(r * D * G, mk3(F, F, F)), 4.0f * cos_i * cos_o);
+}
+
+struct DBSDF {
+  f3 nn, ng, sn, tn;
+  int kind;      // 0 matte/Lambertian, 1 matte/OrenNayar, 2 plastic (Lambertian + Blinn microfacet)
+  f3 kd, ks;
+  float a, b;    // OrenNayar A,B ; plastic: a = Blinn exponent
+};
+PB_DEV f3 bsdf_f(const DBSDF& bs, f3 wo_w, f3 wi_w, bool strict_flags) {  // bsdf/mod.rs:132-149
+  const bool reflect = dot3(wi_w, bs.ng) * dot3(wo_w, bs.ng) > 0.0f;
+  // D7: with the as-written matches_flags no BxDF ever matches the wide mask -> black.
+  if (strict_flags || !reflect) return mk3(0.f, 0.f, 0.f);
+  const f3 wo = mk3(dot3(wo_w, bs.sn), dot3(wo_w, bs.tn), dot3(wo_w, bs.nn));
+  const f3 wi = mk3(dot3(wi_w, bs.sn), dot3(wi_w, bs.tn), dot3(wi_w, bs.nn));
+  f3 f = mk3(0.f, 0.f, 0.f);
+  if (bs.kind == 0) {
+    f = f + lambertian_f(bs.kd);
+  } else if (bs.kind == 1) {
+    f = f + orennayar_f(bs.kd, bs.a, bs.b, wo, wi);
+  } else {
+    f = f + lambertian_f(bs.kd);
+    f = f + microfacet_blinn_f(bs.ks, bs.a, wo, wi);
+  }
+  return f;
+}
+
+// visibility_tester.rs:16-24
+PB_DEV void vis_segment(f3 p1, float eps1, f3 p2, float eps2, pbrtb200_ray32* r) {
+  const float dist = len3(p1 - p2);
+  const f3 dir = (p2 - p1) / dist;
+  r->o[0] = p1.x;
+  r->o[1] = p1.y;
+  r->o[2] = p1.z;
+  r->mint = eps1;
+  r->d[0] = dir.x;
+  r->d[1] = dir.y;
+  r->d[2] = dir.z;
+  r->maxt = (1.0f - eps2) * dist;
+}
+
+// Internal record of one emissive triangle (built on device at upload from scene.area_prims).
+struct DAreaTri {
+  float p1[3], p2[3], p3[3], nn[3];
+  float area, cdf_lo, cdf_hi, pad;
+};
+
+// Warp-aggregated queue push: one atomicAdd per warp for all lanes that call it together.
+PB_DEV uint32_t warp_agg_inc(uint32_t* ctr) {
+  const unsigned mask = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(ctr, (uint32_t)__popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+struct ShadeArgs {
+  const float2* __restrict__ img;
+  const float2* __restrict__ lens;  // may be NULL
+  const pbrtb200_hit16* __restrict__ hits;
+  const DPixel* __restrict__ pixels;
+  const DAreaTri* __restrict__ area_tris;
+  float4* __restrict__ Le;       // per sample emitted radiance (rgb)
+  float4* __restrict__ contrib;  // per sample x light slot: f*Li*|wi.n|/pdf (rgb), 0 if none
+  pbrtb200_ray32* __restrict__ sq_rays;  // shadow-ray queue
+  uint32_t* __restrict__ sq_slots;       // contrib slot each shadow ray guards
+  uint32_t* sq_count;
+  uint64_t n;
+  int strict_flags;
+};
+
+__global__ void __launch_bounds__(128)
+k_shade(const DScene sc, const DCamera cam, const DSampler smp, const ShadeArgs a) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n) return;
+  const float4 hraw = __ldg(reinterpret_cast<const float4*>(a.hits) + idx);
+  const uint32_t prim = __float_as_uint(hraw.x);
+  if (prim == PBRTB200_MISS) return;  // miss: sum of light.le(ray) = 0 (light/mod.rs:50-52)
+  const float t_hit = hraw.y, hb1 = hraw.z, hb2 = hraw.w;
+
+  // Regenerate the camera ray and its differentials (camera/mod.rs:212-271, ray.rs:107-112;
+  // D15: the differential origins/directions stay in camera space).
+  const float2 im = __ldg(a.img + idx);
+  float2 ln = make_float2(0.f, 0.f);
+  if (a.lens) ln = __ldg(a.lens + idx);
+  f3 o, d, p_camera;
+  camera_ray(cam, im.x, im.y, ln.x, ln.y, &o, &d, &p_camera);
+  const f3 dxc = mk3(cam.dx[0], cam.dx[1], cam.dx[2]), dyc = mk3(cam.dy[0], cam.dy[1], cam.dy[2]);
+  f3 rxo = mk3(0.f, 0.f, 0.f), ryo = mk3(0.f, 0.f, 0.f);
+  f3 rxd = normalize3(p_camera + dxc), ryd = normalize3(p_camera + dyc);
+  const float s = cam.diff_scale;
+  rxo = o + (rxo - o) * s;
+  ryo = o + (ryo - o) * s;
+  rxd = d + (rxd - d) * s;
+  ryd = d + (ryd - d) * s;
+
+  // Intersection::get_bsdf
+  uint32_t pr = sc.leaf_prim ? __ldg(&sc.leaf_prim[prim]) : prim;
+  DG dg, dgs;
+  uint32_t material;
+  int32_t area_light = -1;
+  if (pr & PB_LEAF_BIT) {
+    const uint32_t si = pr & ~PB_LEAF_BIT;
+    const pbrtb200_sphere80 sp = sc.spheres[si];
+    dg = sphere_dg(sp, sc.sphere_o2w + 12ull * si, o, d, t_hit, hb1);
+    dg_compute_differentials(dg, rxo, ryo, rxd, ryd);
+    dgs = dg;
+    material = sp.material;
+  } else {
+    const TriData td = load_tri(sc, pr);
+    const pbrtb200_mesh m = sc.meshes[td.mesh];
+    dg = tri_dg(td, o, d, t_hit, hb1, hb2, m.flip != 0);
+    dg_compute_differentials(dg, rxo, ryo, rxd, ryd);
+    dgs = tri_shading_geometry(sc, td, m, dg);
+    material = m.material;
+    area_light = m.area_light;
+  }
+  const float ray_epsilon = t_hit * 5e-4f;  // mesh.rs:262, sphere.rs:180
+
+  // Material::get_bsdf
+  DBSDF bs;
+  bs.nn = dgs.nn;                      // bsdf/mod.rs:70-86
+  bs.tn = normalize3(dgs.dpdu);
+  bs.sn = cross3(bs.nn, bs.tn);
+  bs.ng = dg.nn;
+  bs.ks = mk3(0.f, 0.f, 0.f);
+  bs.a = bs.b = 0.f;
+  const pbrtb200_material mat = sc.materials[material];
+  {
+    f3 kd = tex_eval<3>(sc, mat.kd, dgs);
+    bs.kd = mk3(rclampf(kd.x, 0.0f, PB_F32_MAX), rclampf(kd.y, 0.0f, PB_F32_MAX),
+                rclampf(kd.z, 0.0f, PB_F32_MAX));
+  }
+  if (mat.kind == PBRTB200_MAT_MATTE) {  // matte.rs:30-51
+    const float sig = rclampf(tex_eval<3>(sc, mat.sigma, dgs).x, 0.0f, 90.0f);
+    if (sig == 0.0f) {
+      bs.kind = 0;
+    } else {  // orennayar.rs:16-29
+      bs.kind = 1;
+      const float sigma = sig * PB_PI / 180.0f;
+      const float sigma2 = sigma * sigma;
+      bs.a = 1.0f - (sigma2 / (2.0f * (sigma + 0.33f)));
+      bs.b = 0.45f * sigma2 / (sigma2 + 0.09f);
+    }
+  } else {  // plastic.rs:32-55
+    bs.kind = 2;
+    const f3 ks = tex_eval<3>(sc, mat.ks, dgs);
+    bs.ks = mk3(rclampf(ks.x, 0.0f, PB_F32_MAX), rclampf(ks.y, 0.0f, PB_F32_MAX),
+                rclampf(ks.z, 0.0f, PB_F32_MAX));
+    const float rough = tex_eval<3>(sc, mat.roughness, dgs).x;
+    float e = 1.0f / rough;
+    if (e > 1000.0f || isnan(e)) e = 1000.0f;  // microfacet.rs:18-24
+    bs.a = e;
+  }
+
+  const f3 p = dgs.p;
+  const f3 n = dgs.nn;
+  const f3 wo = -d;
+
+  // Emitted radiance at an emissive triangle (extension): L if n.w > 0.
+  f3 le = mk3(0.f, 0.f, 0.f);
+  if (area_light >= 0) {
+    const pbrtb200_light al = sc.lights[area_light];
+    if (dot3(dg.nn, wo) > 0.0f) le = mk3(al.intensity[0], al.intensity[1], al.intensity[2]);
+  }
+  a.Le[idx] = make_float4(le.x, le.y, le.z, 0.f);
+
+  // Light-sample floats: 2 per area-light sample, drawn from the pixel's stream after
+  // its camera-sample block, in (camera sample, light, light sample) order.
+  WordStream ws;
+  if (sc.area_sample_pairs) {
+    const uint32_t spp = (uint32_t)smp.spp;
+    const uint64_t pix = idx / spp;
+    const uint32_t i = (uint32_t)(idx - pix * spp);
+    const DPixel px = a.pixels[pix];
+    ws.init(smp.task_keys + 8u * px.task,
+            (uint64_t)px.k * smp.words_per_pixel + smp.cam_words +
+                2ull * sc.area_sample_pairs * i);
+  }
+
+  uint32_t slot = (uint32_t)(idx * sc.light_slots);
+  for (uint32_t li = 0; li < sc.n_lights; ++li) {
+    const pbrtb200_light lt = sc.lights[li];
+    const int ns = lt.kind == PBRTB200_LIGHT_AREA ? lt.num_samples : 1;
+    for (int sidx = 0; sidx < ns; ++sidx, ++slot) {
+      f3 Li, wi;
+      float pdf;
+      pbrtb200_ray32 vis;
+      if (lt.kind == PBRTB200_LIGHT_POINT) {  // point.rs:28-35 (D17: wi un-normalised)
+        const f3 lp = mk3(lt.pos[0], lt.pos[1], lt.pos[2]);
+        wi = lp - p;
+        pdf = 1.0f;
+        vis_segment(p, ray_epsilon, lp, 0.0f, &vis);
+        Li = div3s(mk3(lt.intensity[0], lt.intensity[1], lt.intensity[2]), len2(wi));
+      } else if (lt.kind == PBRTB200_LIGHT_SPOT) {  // spot.rs:37-65
+        const f3 lp = mk3(lt.pos[0], lt.pos[1], lt.pos[2]);
+        wi = normalize3(lp - p);
+        pdf = 1.0f;
+        vis_segment(p, ray_epsilon, lp, 0.0f, &vis);
+        const f3 wl = xf_vec(lt.w2l, -wi);
+        const float cos_theta = wl.z;
+        float fall;
+        if (cos_theta < lt.cos_total_width)
+          fall = 0.0f;
+        else if (cos_theta > lt.cos_falloff_start)
+          fall = 1.0f;
+        else {
+          const float delta =
+              (cos_theta - lt.cos_total_width) / (lt.cos_falloff_start - lt.cos_total_width);
+          fall = delta * delta * delta * delta;
+        }
+        const f3 I = mk3(lt.intensity[0], lt.intensity[1], lt.intensity[2]) * fall;
+        Li = div3s(I, len2(wi));
+      } else {
+        // Diffuse area light over emissive triangles (extension; pbrt-v2 semantics, A13)
+        const float u1 = ws.random_float();
+        const float u2 = ws.random_float();
+        uint32_t k = 0;
+        while (k + 1 < lt.n_tris && u1 >= a.area_tris[lt.first_tri + k].cdf_hi) ++k;
+        const DAreaTri at = a.area_tris[lt.first_tri + k];
+        const float u1p = (u1 - at.cdf_lo) / (at.cdf_hi - at.cdf_lo);
+        const float su = sqrtf(u1p);
+        const float b0 = 1.0f - su, b1 = u2 * su;
+        const f3 ps = b0 * mk3(at.p1[0], at.p1[1], at.p1[2]) + b1 * mk3(at.p2[0], at.p2[1], at.p2[2]) +
+                      (1.0f - b0 - b1) * mk3(at.p3[0], at.p3[1], at.p3[2]);
+        wi = normalize3(ps - p);
+        const float cos_l = dot3(mk3(at.nn[0], at.nn[1], at.nn[2]), -wi);
+        const float d2 = len2(ps - p);
+        vis_segment(p, ray_epsilon, ps, 1e-3f, &vis);
+        if (!(cos_l > 0.0f)) {
+          Li = mk3(0.f, 0.f, 0.f);
+          pdf = 0.0f;
+        } else {
+          Li = mk3(lt.intensity[0], lt.intensity[1], lt.intensity[2]);
+          pdf = d2 / (fabsf(cos_l) * lt.total_area);
+        }
+      }
+      f3 c = mk3(0.f, 0.f, 0.f);
+      bool shadow = false;
+      if (!(is_black(Li) || pdf == 0.0f)) {  // whitted.rs:55
+        const f3 f = bsdf_f(bs, wo, wi, a.strict_flags != 0);
+        if (!is_black(f)) {
+          // whitted.rs:60-63 with T = 1 (D3): ((f * li) * |wi.n|) * T / pdf
+          c = div3s(mul3(mul3(f, Li) * fabsf(dot3(wi, n)), mk3(1.0f, 1.0f, 1.0f)), pdf);
+          shadow = true;
+        }
+      }
+      a.contrib[slot] = make_float4(c.x, c.y, c.z, 0.f);
+      if (shadow) {
+        const uint32_t q = warp_agg_inc(a.sq_count);
+        float4* rq = reinterpret_cast<float4*>(a.sq_rays + q);
+        rq[0] = make_float4(vis.o[0], vis.o[1], vis.o[2], vis.mint);
+        rq[1] = make_float4(vis.d[0], vis.d[1], vis.d[2], vis.maxt);
+        a.sq_slots[q] = slot;
+      }
+    }
+  }
+}
+
+// L = Le + sum over lights (whitted.rs:49-66; area lights averaged over their samples, D10), then
+// Spectrum::to_xyz (spectrum.rs:37-41, 443-458) once per sample as Film::add_sample does.
+struct ResolveArgs {
+  const pbrtb200_hit16* __restrict__ hits;
+  const float4* __restrict__ Le;
+  const float4* __restrict__ contrib;
+  float4* __restrict__ xyz;  // output, indexed out_base + idx
+  uint64_t n;
+  uint64_t out_base;
+  uint32_t* nan_count;
+  unsigned long long* hit_total;     // += camera samples that hit geometry
+  unsigned long long* shadow_total;  // += this chunk's shadow-queue length
+  const uint32_t* sq_count;
+  int shaded;  // 0: no lights -> radiance is identically 0, Le/contrib were not produced
+};
+__global__ void __launch_bounds__(256)
+k_resolve(const DScene sc, const ResolveArgs a) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0 && a.shaded) atomicAdd(a.shadow_total, (unsigned long long)(*a.sq_count));
+  const bool in_range = idx < a.n;
+  const uint32_t prim = in_range ? __ldg(&a.hits[idx].prim) : PBRTB200_MISS;
+  {
+    const unsigned hits = __ballot_sync(0xffffffffu, prim != PBRTB200_MISS);
+    if ((threadIdx.x & 31) == 0 && hits) atomicAdd(a.hit_total, (unsigned long long)__popc(hits));
+  }
+  if (!in_range) return;
+  f3 L = mk3(0.f, 0.f, 0.f);
+  if (prim != PBRTB200_MISS && a.shaded) {
+    const float4 le = a.Le[idx];
+    L = mk3(le.x, le.y, le.z);
+    uint32_t slot = (uint32_t)(idx * sc.light_slots);
+    for (uint32_t li = 0; li < sc.n_lights; ++li) {
+      const int kind = sc.lights[li].kind;
+      if (kind == PBRTB200_LIGHT_AREA) {
+        const int ns = sc.lights[li].num_samples;
+        f3 Ld = mk3(0.f, 0.f, 0.f);
+        for (int s = 0; s < ns; ++s, ++slot) {
+          const float4 c = a.contrib[slot];
+          Ld = Ld + mk3(c.x, c.y, c.z);
+        }
+        L = L + div3s(Ld, (float)ns);
+      } else {
+        const float4 c = a.contrib[slot++];
+        L = L + mk3(c.x, c.y, c.z);
+      }
+    }
+  }
+  if (isnan(L.x) || isnan(L.y) || isnan(L.z)) atomicAdd(a.nan_count, 1u);  // D4
+  float4 o;
+  o.x = 0.412453f * L.x + 0.357580f * L.y + 0.180423f * L.z;
+  o.y = 0.212671f * L.x + 0.715160f * L.y + 0.072169f * L.z;
+  o.z = 0.019334f * L.x + 0.119193f * L.y + 0.950227f * L.z;
+  o.w = 0.f;
+  a.xyz[a.out_base + idx] = o;
+}
+
+// Upload-time helper: fill DAreaTri records from ordered-primitive indices (extension, A13).
+__global__ void k_area_tri_setup(const DScene sc, const uint32_t* __restrict__ prims, uint32_t n,
+                                 DAreaTri* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t prim = prims[i];
+  const uint32_t pr = sc.leaf_prim ? sc.leaf_prim[prim] : prim;
+  const TriData td = load_tri(sc, pr & ~PB_LEAF_BIT);
+  const pbrtb200_mesh m = sc.meshes[td.mesh];
+  const DG dg = tri_dg(td, mk3(0, 0, 0), mk3(0, 0, 1), 0.f, 0.f, 0.f, m.flip != 0);
+  DAreaTri t;
+  t.p1[0] = td.p1.x; t.p1[1] = td.p1.y; t.p1[2] = td.p1.z;
+  t.p2[0] = td.p2.x; t.p2[1] = td.p2.y; t.p2[2] = td.p2.z;
+  t.p3[0] = td.p3.x; t.p3[1] = td.p3.y; t.p3[2] = td.p3.z;
+  t.nn[0] = dg.nn.x; t.nn[1] = dg.nn.y; t.nn[2] = dg.nn.z;
+  t.area = 0.5f * len3(cross3(td.p2 - td.p1, td.p3 - td.p1));  // mesh.rs:100-103
+  t.cdf_lo = t.cdf_hi = t.pad = 0.f;
+  out[i] = t;
+}

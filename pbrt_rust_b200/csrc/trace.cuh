@@ -1,0 +1,316 @@
+// Closest-hit / any-hit BVH traversal kernels (sm_100a).
+//
+// Replaces, per ray: BVHAccelerator::intersect (src/primitive/aggregates/bvh.rs:375-422),
+// BBox::intersect (src/bbox.rs:185-209), Triangle::get_intersection_point (src/shape/mesh.rs:41-72),
+// Sphere::get_intersection_point (src/shape/sphere.rs:46-107) and GeometricPrimitive::intersect's
+// ray.maxt update (src/primitive/geometric.rs:62-73).
+//
+// Equivalence with the reference's test-at-pop order (proved in DESIGN.md §"Traversal"): the
+// reference pops a node and tests its box against the LIVE [mint,maxt]; the test passes iff
+// T0 <= F and T0 <= maxt_now with T0 = max(mint, near_xyz), F = min(far_xyz) (both independent of
+// maxt).  We evaluate both children's boxes when visiting the parent, push the far child together
+// with its T0 only if it passes then, and re-check T0 <= maxt when it is popped.  Because maxt
+// only shrinks, the set and ORDER of visited leaves — hence every accepted hit, including the
+// "equal t replaces" tie rule (mesh.rs:71, bvh.rs:401-404) — is identical.
+#pragma once
+#include "scene.cuh"
+
+PB_DEV float4 ldg4(const float4* p) { return __ldg(p); }
+
+// bbox.rs:185-209.  Returns pass/fail and T0 (the entry distance after all three axes).
+PB_DEV bool slab_test(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
+                      f3 o, f3 inv, float mint, float maxt, float* T0) {
+  float t0 = mint, t1 = maxt;
+  {
+    float ta = (bminx - o.x) * inv.x, tb = (bmaxx - o.x) * inv.x;
+    bool sw = ta > tb;  // NaN compares false: no swap, as in the reference
+    float tn = sw ? tb : ta, tf = sw ? ta : tb;
+    t0 = fmaxf(tn, t0);
+    t1 = fminf(tf, t1);
+  }
+  {
+    float ta = (bminy - o.y) * inv.y, tb = (bmaxy - o.y) * inv.y;
+    bool sw = ta > tb;
+    float tn = sw ? tb : ta, tf = sw ? ta : tb;
+    t0 = fmaxf(tn, t0);
+    t1 = fminf(tf, t1);
+  }
+  {
+    float ta = (bminz - o.z) * inv.z, tb = (bmaxz - o.z) * inv.z;
+    bool sw = ta > tb;
+    float tn = sw ? tb : ta, tf = sw ? ta : tb;
+    t0 = fmaxf(tn, t0);
+    t1 = fminf(tf, t1);
+  }
+  *T0 = t0;
+  return !(t0 > t1);
+}
+
+// mesh.rs:41-72
+PB_DEV bool tri_hit(f3 p1, f3 p2, f3 p3, f3 o, f3 d, float mint, float maxt, float* t_out,
+                    float* b1_out, float* b2_out) {
+  f3 e1 = p2 - p1;
+  f3 e2 = p3 - p1;
+  f3 s1 = cross3(d, e2);
+  float divisor = dot3(s1, e1);
+  if (divisor == 0.f) return false;
+  float inv_divisor = 1.0f / divisor;
+  f3 s = o - p1;
+  float b1 = dot3(s1, s) * inv_divisor;
+  if (b1 < 0.0f || b1 > 1.0f) return false;
+  f3 s2 = cross3(s, e1);
+  float b2 = dot3(d, s2) * inv_divisor;
+  if (b2 < 0.0f || (b1 + b2) > 1.0f) return false;
+  float t = dot3(e2, s2) * inv_divisor;
+  if (t < mint || t > maxt) return false;
+  *t_out = t;
+  *b1_out = b1;
+  *b2_out = b2;
+  return true;
+}
+
+// sphere.rs:46-107 (+ the world->object ray transform of sphere.rs:137)
+PB_DEV bool sphere_hit(const pbrtb200_sphere80* __restrict__ sp, f3 ow, f3 dw, float mint,
+                       float maxt, float* t_out, float* phi_out) {
+  float m[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) m[i] = __ldg(&sp->w2o[i]);
+  const float radius = __ldg(&sp->radius), z_min = __ldg(&sp->z_min), z_max = __ldg(&sp->z_max),
+              phi_max = __ldg(&sp->phi_max);
+  f3 o = xf_pt(m, ow), d = xf_vec(m, dw);
+  float a = len2(d);
+  float b = 2.0f * dot3(d, o);
+  float c = len2(o) - radius * radius;
+  float t0, t1;
+  if (!quadratic_(a, b, c, &t0, &t1)) return false;
+  if (t0 > maxt || t1 < mint) return false;
+  float t_hit = t0;
+  if (t0 < mint) {
+    t_hit = t1;
+    if (t_hit > maxt) return false;
+  }
+  f3 h = o + (d * t_hit);
+  if (h.x == 0.0f && h.y == 0.0f) h.x = 1e-5f * radius;
+  float ang = atan2f(h.y, h.x);
+  if (ang < 0.0f) ang += 2.0f * PB_PI;
+  bool invalid = (h.z > -radius && h.z < z_min) || (h.z < radius && h.z > z_max) || (ang > phi_max);
+  if (invalid) {
+    if (t_hit == t1) return false;
+    if (t1 > maxt) return false;
+    t_hit = t1;
+    h = o + (d * t_hit);
+    if (h.x == 0.0f && h.y == 0.0f) h.x = 1e-5f * radius;
+    ang = atan2f(h.y, h.x);
+    if (ang < 0.0f) ang += 2.0f * PB_PI;
+    invalid = (h.z > -radius && h.z < z_min) || (h.z < radius && h.z > z_max) || (ang > phi_max);
+    if (invalid) return false;
+  }
+  *t_out = t_hit;
+  *phi_out = ang;
+  return true;
+}
+
+struct TraceResult {
+  uint32_t prim;
+  float t, b1, b2;
+  bool overflow;
+};
+
+// One ray through the pair-node BVH.  s_ref / s_t0 point at this thread's column of the shared
+// stack (stride = blockDim.x).  ANY: stop at the first accepted hit (VisibilityTester).
+template <bool ANY, bool SPH, bool MULTI>
+PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, float mint, float maxt,
+                            uint32_t* s_ref, float* s_t0, int stride) {
+  TraceResult res;
+  res.prim = PBRTB200_MISS;
+  res.t = 0.f;
+  res.b1 = 0.f;
+  res.b2 = 0.f;
+  res.overflow = false;
+  // bvh.rs:382-383
+  const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+  const bool neg0 = inv.x < 0.0f, neg1 = inv.y < 0.0f, neg2 = inv.z < 0.0f;
+  uint32_t l_ref[PB_LM_STACK];
+  float l_t0[PB_LM_STACK];
+  int sp = 0;
+  float T0;
+  if (!slab_test(sc.root_bmin[0], sc.root_bmin[1], sc.root_bmin[2], sc.root_bmax[0],
+                 sc.root_bmax[1], sc.root_bmax[2], o, inv, mint, maxt, &T0))
+    return res;
+  uint32_t cur = sc.root_ref;
+  for (;;) {
+    bool need_pop = false;
+    if (!(cur & PB_LEAF_BIT)) {
+      const float4* n = sc.nodes + 4ull * cur;
+      const float4 q0 = ldg4(n), q1 = ldg4(n + 1), q2 = ldg4(n + 2), q3 = ldg4(n + 3);
+      float T00, T01;
+      const bool h0 = slab_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, mint, maxt, &T00);
+      const bool h1 = slab_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, inv, mint, maxt, &T01);
+      const uint32_t r0 = __float_as_uint(q3.x), r1 = __float_as_uint(q3.y);
+      if (h0 && h1) {
+        const uint32_t axis = __float_as_uint(q3.w);
+        // bvh.rs:409-415: dir_is_neg[axis] -> second child is popped first
+        const bool neg = axis == 0 ? neg0 : (axis == 1 ? neg1 : neg2);
+        const uint32_t far_ref = neg ? r0 : r1;
+        const float far_t0 = neg ? T00 : T01;
+        if (sp < PB_SM_STACK) {
+          s_ref[sp * stride] = far_ref;
+          s_t0[sp * stride] = far_t0;
+        } else if (sp < PBRTB200_STACK_DEPTH) {
+          l_ref[sp - PB_SM_STACK] = far_ref;
+          l_t0[sp - PB_SM_STACK] = far_t0;
+        } else {
+          res.overflow = true;
+          return res;
+        }
+        ++sp;
+        cur = neg ? r1 : r0;
+      } else if (h0) {
+        cur = r0;
+      } else if (h1) {
+        cur = r1;
+      } else {
+        need_pop = true;
+      }
+    } else {
+      // bvh.rs:398-405: test every primitive of the leaf in order; the last accepted hit wins
+      const uint32_t off = cur & ~PB_LEAF_BIT;
+      const uint32_t cnt = MULTI ? (uint32_t)__ldg(&sc.leaf_count[off]) : 1u;
+      for (uint32_t i = 0; i < cnt; ++i) {
+        const uint32_t pi = off + i;
+        uint32_t pr = SPH ? __ldg(&sc.leaf_prim[pi]) : pi;
+        bool hit;
+        float t, b1, b2 = 0.f;
+        if (SPH && (pr & PB_LEAF_BIT)) {
+          hit = sphere_hit(sc.spheres + (pr & ~PB_LEAF_BIT), o, d, mint, maxt, &t, &b1);
+        } else {
+          const float4* tp = sc.tris + 3ull * pr;
+          const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+          hit = tri_hit(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), o, d, mint,
+                        maxt, &t, &b1, &b2);
+        }
+        if (hit) {
+          maxt = t;  // geometric.rs:64
+          res.prim = pi;
+          res.t = t;
+          res.b1 = b1;
+          res.b2 = b2;
+          if (ANY) return res;
+        }
+      }
+      need_pop = true;
+    }
+    if (need_pop) {
+      bool got = false;
+      while (sp > 0) {
+        --sp;
+        uint32_t r;
+        float t0;
+        if (sp < PB_SM_STACK) {
+          r = s_ref[sp * stride];
+          t0 = s_t0[sp * stride];
+        } else {
+          r = l_ref[sp - PB_SM_STACK];
+          t0 = l_t0[sp - PB_SM_STACK];
+        }
+        if (!(t0 > maxt)) {  // the reference's box test at pop, with the live maxt
+          cur = r;
+          got = true;
+          break;
+        }
+      }
+      if (!got) break;
+    }
+  }
+  return res;
+}
+
+// camera/mod.rs:168-195, 212-271 (Perspective arm), projective.rs:79-97, animated.rs:275-284
+PB_DEV void camera_ray(const DCamera& cam, float ix, float iy, float lu, float lv, f3* o, f3* d,
+                       f3* p_camera_out) {
+  f3 p_camera = xf_pt44(cam.r2c, mk3(ix, iy, 0.0f));
+  f3 ro = mk3(0.f, 0.f, 0.f);
+  f3 rd = normalize3(p_camera);
+  if (cam.lens_radius > 0.0f) {  // handle_dof (concentric_sample_disk is the identity)
+    float u = lu * cam.lens_radius, v = lv * cam.lens_radius;
+    float ft = cam.focal_distance / rd.z;
+    f3 p_focus = ro + (rd * ft);
+    ro = mk3(u, v, 0.0f);
+    rd = normalize3(p_focus - ro);
+  }
+  *o = xf_pt44(cam.c2w, ro);
+  *d = xf_vec(cam.c2w, rd);
+  if (p_camera_out) *p_camera_out = p_camera;
+}
+
+// ---- kernels ---------------------------------------------------------------------------------
+// Persistent grid: each warp pulls 32-ray packets from a global counter (warp-aggregated: one
+// atomic per warp), so slow packets do not stall a whole block's worth of queued work.
+
+struct TraceArgs {
+  const pbrtb200_ray32* __restrict__ rays;  // SRC 0
+  const float2* __restrict__ img;           // SRC 1: camera samples (image_x, image_y)
+  const float2* __restrict__ lens;          // SRC 1, may be NULL (lens_radius == 0)
+  pbrtb200_hit16* __restrict__ hits;        // closest-hit output (may be NULL for ANY)
+  uint8_t* __restrict__ occluded;           // ANY output (API hook), may be NULL
+  float4* __restrict__ contrib;             // ANY in the render pipeline: zero slot if occluded
+  const uint32_t* __restrict__ slots;       // ANY in the render pipeline: slot index per ray
+  const uint32_t* __restrict__ n_dyn;       // if non-NULL the ray count is read from device memory
+  const uint64_t* __restrict__ out_index;   // optional scatter index for hits (NULL = identity)
+  uint64_t n;
+  unsigned long long* counter;  // work counter, zeroed by the host before launch
+  uint32_t* flags;              // bit0: stack overflow happened
+};
+
+template <bool ANY, bool SPH, bool MULTI, int SRC>
+__global__ void __launch_bounds__(PB_TRACE_THREADS)
+k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
+  __shared__ uint32_t sh_ref[PB_SM_STACK * PB_TRACE_THREADS];
+  __shared__ float sh_t0[PB_SM_STACK * PB_TRACE_THREADS];
+  uint32_t* s_ref = sh_ref + threadIdx.x;
+  float* s_t0 = sh_t0 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const uint64_t n = a.n_dyn ? (uint64_t)(*a.n_dyn) : a.n;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(a.counter, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;  // warp-uniform exit
+    const uint64_t idx = base + lane;
+    if (idx < n) {
+      f3 o, d;
+      float mint, maxt;
+      if (SRC == 0) {
+        const float4* rp = reinterpret_cast<const float4*>(a.rays + idx);
+        const float4 r0 = ldg4(rp), r1 = ldg4(rp + 1);
+        o = mk3(r0.x, r0.y, r0.z);
+        mint = r0.w;
+        d = mk3(r1.x, r1.y, r1.z);
+        maxt = r1.w;
+      } else {
+        const float2 im = __ldg(a.img + idx);
+        float2 ln = make_float2(0.f, 0.f);
+        if (a.lens) ln = __ldg(a.lens + idx);
+        camera_ray(cam, im.x, im.y, ln.x, ln.y, &o, &d, nullptr);
+        mint = 0.0f;         // ray.rs:30-38 Ray::new_with(.., start = 0)
+        maxt = PB_F32_MAX;
+      }
+      TraceResult r = traverse<ANY, SPH, MULTI>(sc, o, d, mint, maxt, s_ref, s_t0,
+                                                PB_TRACE_THREADS);
+      if (r.overflow) atomicOr(a.flags, 1u);
+      if (ANY) {
+        const bool occ = r.prim != PBRTB200_MISS;
+        if (a.occluded) a.occluded[idx] = occ ? 1 : 0;
+        if (a.contrib && occ) a.contrib[__ldg(a.slots + idx)] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        const uint64_t oi = a.out_index ? a.out_index[idx] : idx;
+        float4 h;
+        h.x = __uint_as_float(r.prim);
+        h.y = r.t;
+        h.z = r.b1;
+        h.w = r.b2;
+        reinterpret_cast<float4*>(a.hits)[oi] = h;
+      }
+    }
+  }
+}

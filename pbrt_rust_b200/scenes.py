@@ -1,0 +1,158 @@
+"""Synthetic, procedurally generated scenes of BASELINE.json's named sizes.
+
+Pure data: numpy arrays wrapped in the api.py mirror objects.  Both the CUDA product and the CPU
+oracle are fed from these same descriptions.  The generator PRNG is SplitMix64 (ours; unrelated to
+the renderer's StdRng)."""
+import numpy as np
+
+from .api import (AreaLight, Camera, Film, Filter, Light, Material, PlanarMapping2D, Primitive,
+                  Sampler, Scene, Shape, SurfaceIntegrator, Texture, Transform, UVMapping2D)
+
+
+def splitmix64(seed, n):
+    """n uniform floats in [0,1) from SplitMix64(seed), vectorised."""
+    with np.errstate(over="ignore"):
+        i = np.arange(1, n + 1, dtype=np.uint64)
+        z = np.uint64(seed) + i * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+
+
+def _matte(kd=0.5, sigma=0.0):
+    return Material.matte(Texture.constant(kd), Texture.constant(sigma))
+
+
+def _setup(scene, cam2world, fov, xres, yres, xs, ys, jitter, sampler="stratified", crop=(0, 1, 0, 1),
+           filt=None, max_depth=1, lensr=0.0, focald=1e6):
+    filt = filt or Filter.mean(0.5, 0.5)
+    film = Film.image(xres, yres, filt, crop)
+    aspect = xres / yres
+    sw = (-aspect, aspect, -1.0, 1.0) if aspect > 1 else (-1.0, 1.0, -1.0 / aspect, 1.0 / aspect)
+    cam = Camera.perspective(cam2world, sw, 0.0, 0.0, lensr, focald, fov, film)
+    e = film.get_sample_extent()
+    if sampler == "stratified":
+        smp = Sampler.stratified(e[0], e[1], e[2], e[3], xs, ys, jitter, 0.0, 0.0)
+    else:
+        smp = Sampler.low_discrepancy(e[0], e[1], e[2], e[3], xs * ys, 0.0, 0.0)
+    return dict(scene=scene, camera=cam, film=film, sampler=smp, integrator=SurfaceIntegrator.whitted(max_depth))
+
+
+def config1(xres=640, yres=480, sampler="stratified", crop=(0, 1, 0, 1), filt=None):
+    """the reference's own 8-sphere fixture (aggregates/mod.rs:82-91), matte
+    Kd 0.5, one point light I=50 at (5,6,-6), BVH sah/1, fov 60, 4 spp, Whitted depth 1."""
+    mat = _matte(0.5, 0.0)
+    prims = []
+    for v in [(0, 0, 0), (2, 0, 0), (0, 2, 0), (2, 2, 0), (0, 0, 2), (2, 0, 2), (0, 2, 2), (2, 2, 2)]:
+        t = Transform.translate(v)
+        prims.append(Primitive.geometric(Shape.sphere(t, t.inverse(), False, 1.0, -1.0, 1.0, 360.0), mat))
+    light = Light.point(Transform.translate((5.0, 6.0, -6.0)), 50.0)
+    scene = Scene.new_with(Primitive.bvh(prims, 1, "sah"), [light])
+    c2w = Transform.look_at((1, 1, -6), (1, 1, 1), (0, 1, 0)).inverse()
+    return _setup(scene, c2w, 60.0, xres, yres, 2, 2, True, sampler=sampler, crop=crop, filt=filt)
+
+
+def random_triangles(n=100_000, seed=1):
+    u = splitmix64(seed, n * 12).reshape(n, 12)
+    c = u[:, 0:3] * 20.0 - 10.0
+    off = (u[:, 3:12] * 0.6 - 0.3).reshape(n, 3, 3)
+    P = (c[:, None, :] + off).astype(np.float32).reshape(-1, 3)
+    vi = np.arange(3 * n, dtype=np.uint32)
+    return vi, P
+
+
+def config2(n=100_000, xres=1920, yres=1080, seed=1, crop=(0, 1, 0, 1)):
+    """BVH (sah/4) over n random triangles, pixel-centre samples, 1 spp."""
+    vi, P = random_triangles(n, seed)
+    mesh = Shape.triangle_mesh(Transform.new(), Transform.new(), False, vi, P)
+    scene = Scene.new_with(Primitive.bvh([Primitive.geometric(mesh, _matte())], 4, "sah"), [])
+    c2w = Transform.look_at((0, 0, -35), (0, 0, 0), (0, 1, 0)).inverse()
+    return _setup(scene, c2w, 40.0, xres, yres, 1, 1, False, crop=crop)
+
+
+def heightfield(nx, nz, x0=-20.0, x1=20.0, z0=-10.0, z1=10.0):
+    """(nx x nz) cells, 2 triangles per cell: y = 0.6 sin(0.9x) cos(1.1z) + 0.15 hash(i,j)."""
+    i = np.arange(nx + 1, dtype=np.float64)
+    j = np.arange(nz + 1, dtype=np.float64)
+    X, Z = np.meshgrid(x0 + (x1 - x0) * i / nx, z0 + (z1 - z0) * j / nz, indexing="ij")
+    ii, jj = np.meshgrid(np.arange(nx + 1, dtype=np.uint64), np.arange(nz + 1, dtype=np.uint64), indexing="ij")
+    with np.errstate(over="ignore"):
+        h = (ii * np.uint64(73856093)) ^ (jj * np.uint64(19349663))
+        h = (h ^ (h >> np.uint64(13))) * np.uint64(0x9E3779B97F4A7C15)
+        hv = (h >> np.uint64(40)).astype(np.float64) / float(1 << 24)
+    Y = 0.6 * np.sin(0.9 * X) * np.cos(1.1 * Z) + 0.15 * hv * (40.0 / nx)
+    P = np.stack([X, Y, Z], axis=-1).astype(np.float32).reshape(-1, 3)
+    a = (np.arange(nx)[:, None] * (nz + 1) + np.arange(nz)[None, :]).astype(np.uint32)
+    b, c, d = a + (nz + 1), a + 1, a + (nz + 1) + 1
+    vi = np.stack([np.stack([a, c, b], -1), np.stack([b, c, d], -1)], axis=2).reshape(-1).astype(np.uint32)
+    return vi, P
+
+
+def _quad_light(y=8.0, half=2.0, cx=0.0, cz=0.0):
+    P = np.array([[cx - half, y, cz - half], [cx + half, y, cz - half], [cx + half, y, cz + half],
+                  [cx - half, y, cz + half]], np.float32)
+    # winding chosen so that dg.nn (= normalize((p2-p1) x (p3-p2)) after the refine reversal,
+    # mesh.rs:220-262 with default uvs) points down (-y): the quad emits towards the ground.
+    vi = np.array([0, 2, 1, 0, 3, 2], np.uint32)
+    return vi, P
+
+
+def config3(nx=1000, nz=500, xres=1920, yres=1080, xs=4, ys=4, crop=(0, 1, 0, 1), n_lights=1,
+            light_samples=1):
+    """2*nx*nz-triangle heightfield (default 1 M), matte Kd 0.5, quad area
+    light(s) (4x4 at y=8, L=15), Stratified xs*ys jittered, box filter, direct lighting."""
+    vi, P = heightfield(nx, nz)
+    mat = _matte(0.5, 0.0)
+    prims = [Primitive.geometric(Shape.triangle_mesh(Transform.new(), Transform.new(), False, vi, P), mat)]
+    centres = [(0.0, 0.0), (-10.0, 4.0), (10.0, -4.0), (0.0, 6.0)][:n_lights]
+    for (cx, cz) in centres:
+        lvi, lP = _quad_light(cx=cx, cz=cz)
+        al = AreaLight(15.0, light_samples)
+        prims.append(Primitive.geometric_area_light(
+            Shape.triangle_mesh(Transform.new(), Transform.new(), False, lvi, lP), mat, al))
+    scene = Scene.new_with(Primitive.bvh(prims, 4, "sah"), [])
+    c2w = Transform.look_at((0, 9, -26), (0, 0, 0), (0, 1, 0)).inverse()
+    return _setup(scene, c2w, 45.0, xres, yres, xs, ys, True, crop=crop)
+
+
+def config4(n_ground=(500, 200), n_spheres=20_000, xres=3840, yres=2160, xs=8, ys=8, crop=(0, 1, 0, 1),
+            seed=4):
+    """textured ground (checkerboard matte, Oren-Nayar sigma 20) + jittered
+    grid of plastic spheres (checker/uv Kd, Ks .25, roughness .1), one point + one area light."""
+    gx, gz = n_ground
+    vi, P = heightfield(gx, gz)
+    uv = np.stack([(P[:, 0] + 20.0) / 40.0, (P[:, 2] + 10.0) / 20.0], -1).astype(np.float32)
+    checker = Texture.checkerboard(UVMapping2D(40.0, 40.0, 0.0, 0.0), Texture.constant(0.8),
+                                   Texture.constant(0.15), True)
+    ground = Primitive.geometric(Shape.triangle_mesh(Transform.new(), Transform.new(), False, vi, P, uv=uv),
+                                 Material.matte(checker, Texture.constant(20.0)))
+    prims = [ground]
+    side = max(1, int(np.ceil(np.sqrt(n_spheres * 2))))
+    rows = max(1, (n_spheres + side - 1) // side)
+    u = splitmix64(seed, 3 * max(n_spheres, 1)).reshape(-1, 3)
+    kd_a = Texture.checkerboard(PlanarMapping2D((2, 0, 0), (0, 0, 2), 0.0, 0.0),
+                                Texture.constant((0.7, 0.2, 0.2)), Texture.constant((0.2, 0.2, 0.7)), False)
+    kd_b = Texture.uv(UVMapping2D(4.0, 4.0, 0.0, 0.0))
+    mats = [Material.plastic(kd_a, Texture.constant(0.25), Texture.constant(0.1)),
+            Material.plastic(kd_b, Texture.constant(0.25), Texture.constant(0.1))]
+    for k in range(n_spheres):
+        gxk, gzk = k % side, k // side
+        r = 0.1 + 0.3 * u[k, 0]
+        x = -19.0 + 38.0 * (gxk + 0.2 + 0.6 * u[k, 1]) / side
+        z = -9.0 + 18.0 * (gzk + 0.2 + 0.6 * u[k, 2]) / rows
+        t = Transform.translate((float(x), float(1.0 + r), float(z)))
+        prims.append(Primitive.geometric(
+            Shape.sphere(t, t.inverse(), False, float(r), float(-r), float(r), 360.0), mats[k & 1]))
+    lvi, lP = _quad_light()
+    prims.append(Primitive.geometric_area_light(
+        Shape.triangle_mesh(Transform.new(), Transform.new(), False, lvi, lP), _matte(), AreaLight(10.0, 1)))
+    scene = Scene.new_with(Primitive.bvh(prims, 4, "sah"),
+                           [Light.point(Transform.translate((-8.0, 10.0, -12.0)), 120.0)])
+    c2w = Transform.look_at((0, 9, -26), (0, 0, 0), (0, 1, 0)).inverse()
+    return _setup(scene, c2w, 45.0, xres, yres, xs, ys, True, crop=crop)
+
+
+def config5(nx=5000, nz=5000, xres=1920, yres=1080, xs=16, ys=16, crop=(0, 1, 0, 1)):
+    """50 M-triangle heightfield, 4 area lights, 256 spp."""
+    return config3(nx, nz, xres, yres, xs, ys, crop=crop, n_lights=4)
