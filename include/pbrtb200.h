@@ -217,6 +217,11 @@ int pbrtb200_create(int device, pbrtb200_ctx** out);
 void pbrtb200_destroy(pbrtb200_ctx* ctx);
 const char* pbrtb200_last_error(const pbrtb200_ctx* ctx); /* ctx may be NULL (create errors) */
 
+/* Run all of this ctx's work on the caller's CUDA stream (a cudaStream_t, e.g. the host
+ * framework's current stream) so that the caller's events bracket it; NULL restores the ctx's own
+ * stream.  Calls stay synchronous. */
+int pbrtb200_set_stream(pbrtb200_ctx* ctx, void* cuda_stream);
+
 int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* scene);
 
 /* Renderer::render.  out_xyzw: 4 floats per film pixel (x_pixel_count*y_pixel_count, row-major):

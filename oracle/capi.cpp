@@ -575,3 +575,65 @@ float orc_van_der_corput(uint32_t n, uint32_t scramble) { return van_der_corput(
 float orc_sobol2(uint32_t n, uint32_t scramble) { return sobol2(n, scramble); }
 
 }  // extern "C"
+
+// ---- additional known-answer hooks ----
+extern "C" {
+// Projection::new(film(xres,yres), proj, screen_window) -> raster_to_screen.m, screen_to_raster.m,
+// raster_to_camera.m (camera/projective.rs:48-72)
+int orc_projection(int xres, int yres, const float* proj, const float* proj_inv, const float* sw,
+                   float* r2s16, float* s2r16, float* r2c16) {
+  return guarded([&] {
+    Transform p = xf_from(proj, proj_inv);
+    Transform screen_to_raster = Transform::scale((float)xres, (float)yres, 1.0f) *
+                                 Transform::scale(1.0f / (sw[1] - sw[0]), 1.0f / (sw[2] - sw[3]), 1.0f) *
+                                 Transform::translate(V3(-sw[0], -sw[3], 0.0f));
+    Transform raster_to_screen = screen_to_raster.inverse();
+    Transform raster_to_cam = p.inverse() * raster_to_screen;
+    std::memcpy(r2s16, raster_to_screen.m.m, 64);
+    std::memcpy(s2r16, screen_to_raster.m.m, 64);
+    std::memcpy(r2c16, raster_to_cam.m.m, 64);
+  });
+}
+// Mesh::refine order and vertex triples (shape/mesh.rs:324-335): out[3*k..] = tris[k].v
+void orc_mesh_refine(const uint32_t* vi, uint64_t n_vi, uint32_t* out) {
+  std::vector<uint32_t> idx(vi, vi + n_vi);
+  size_t k = 0;
+  while (idx.size() >= 3) {
+    out[3 * k + 0] = idx.back(); idx.pop_back();
+    out[3 * k + 1] = idx.back(); idx.pop_back();
+    out[3 * k + 2] = idx.back(); idx.pop_back();
+    ++k;
+  }
+}
+float orc_tri_area(const float* p9) {  // mesh.rs:100-103
+  V3 p1(p9[0], p9[1], p9[2]), p2(p9[3], p9[4], p9[5]), p3(p9[6], p9[7], p9[8]);
+  return 0.5f * length(cross(p2 - p1, p3 - p1));
+}
+void orc_xf_apply(const float* m, const float* minv, int kind, const float* v3, float* out3) {
+  Transform t = xf_from(m, minv);
+  V3 v(v3[0], v3[1], v3[2]);
+  V3 r = kind == 0 ? t.pt(v) : (kind == 1 ? t.vec(v) : t.nrm(v));
+  out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+void orc_transform(int kind, const float* a3, float* m16, float* minv16) {
+  Transform t;
+  switch (kind) {
+    case 0: t = Transform::translate(V3(a3[0], a3[1], a3[2])); break;
+    case 1: t = Transform::scale(a3[0], a3[1], a3[2]); break;
+    case 2: t = Transform::rotate_x(a3[0]); break;
+    case 3: t = Transform::rotate_y(a3[0]); break;
+    default: t = Transform::rotate_z(a3[0]); break;
+  }
+  std::memcpy(m16, t.m.m, 64);
+  std::memcpy(minv16, t.m_inv.m, 64);
+}
+void orc_task_windows(const int32_t* ext4, uint32_t num_tasks, int32_t* windows, uint32_t* keys) {
+  SamplerDesc sd;
+  for (int i = 0; i < 4; ++i) sd.ext[i] = ext4[i];
+  auto tw = task_windows(sd, num_tasks);
+  for (uint32_t t = 0; t < num_tasks; ++t) {
+    for (int i = 0; i < 4; ++i) windows[4 * t + i] = tw[t].ext[i];
+    for (int i = 0; i < 8; ++i) keys[8 * t + i] = tw[t].key[i];
+  }
+}
+}  // extern "C"

@@ -105,6 +105,7 @@ SYMBOLS = [
     ("pbrtb200_create", i32, [C.c_int, P(_vp)]),
     ("pbrtb200_destroy", None, [_vp]),
     ("pbrtb200_last_error", C.c_char_p, [_vp]),
+    ("pbrtb200_set_stream", i32, [_vp, _vp]),
     ("pbrtb200_upload_scene", i32, [_vp, P(Scene)]),
     ("pbrtb200_render", i32, [_vp, P(Camera), P(Sampler), P(Film), P(Integrator), P(TileSet), _vp,
                               C.c_int, P(Stats)]),

@@ -420,6 +420,10 @@ class Context:
         if rc:
             raise PbrtError(rc, lib().pbrtb200_last_error(self.h).decode())
 
+    def set_stream(self, cuda_stream):
+        """Issue this ctx's work on the given cudaStream_t (int handle), e.g. torch's current stream."""
+        self.check(lib().pbrtb200_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
     def upload(self, host_scene):
         self.check(lib().pbrtb200_upload_scene(self.h, host_scene.flat))
 

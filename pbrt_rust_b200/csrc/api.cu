@@ -69,7 +69,8 @@ std::string g_create_err;
 struct pbrtb200_ctx {
   int device = 0;
   int sm_count = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream all work is issued on
+  cudaStream_t own_stream = nullptr;  // created by the ctx
   std::string err;
   // scene
   bool has_scene = false, has_spheres = false, multi_leaf = false;
@@ -401,8 +402,9 @@ int pbrtb200_create(int device, pbrtb200_ctx** out) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
   ctx->sm_count = prop.multiProcessorCount;
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail("cudaStreamCreate", e);
+  ctx->stream = ctx->own_stream;
   if ((e = ctx->d_ctrl.ensure(sizeof(CtrlBlock))) != cudaSuccess) return bail("cudaMalloc", e);
   *out = ctx;
   return PBRTB200_OK;
@@ -413,8 +415,16 @@ void pbrtb200_destroy(pbrtb200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
+}
+
+int pbrtb200_set_stream(pbrtb200_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return PBRTB200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return PBRTB200_OK;
 }
 
 int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {

@@ -112,8 +112,9 @@ def config3(nx=1000, nz=500, xres=1920, yres=1080, xs=4, ys=4, crop=(0, 1, 0, 1)
         prims.append(Primitive.geometric_area_light(
             Shape.triangle_mesh(Transform.new(), Transform.new(), False, lvi, lP), mat, al))
     scene = Scene.new_with(Primitive.bvh(prims, 4, "sah"), [])
-    c2w = Transform.look_at((0, 9, -26), (0, 0, 0), (0, 1, 0)).inverse()
-    return _setup(scene, c2w, 45.0, xres, yres, xs, ys, True, crop=crop)
+    # camera chosen so that the terrain fills the frame (100 % of camera rays hit geometry)
+    c2w = Transform.look_at((0, 12, -13), (0, 0, -2), (0, 1, 0)).inverse()
+    return _setup(scene, c2w, 36.0, xres, yres, xs, ys, True, crop=crop)
 
 
 def config4(n_ground=(500, 200), n_spheres=20_000, xres=3840, yres=2160, xs=8, ys=8, crop=(0, 1, 0, 1),

@@ -1,0 +1,158 @@
+"""CPU tests of the product's host side (libpbrtb200.so `pbh_*` + the C-ABI surface) against the
+oracle: same BVH node for node, same camera/film/sampler descriptors.  No compute call needs a GPU."""
+import ctypes as C
+import re
+import os
+
+import numpy as np
+import pytest
+
+import pbrt_rust_b200 as pb
+from pbrt_rust_b200 import _ffi, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function the two public headers declare is exported by the .so and bound in _ffi."""
+    declared = set()
+    for h in ("pbrtb200.h", "pbrtb200_host.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        declared |= set(re.findall(r"\b(pbrtb200_[a-z_0-9]+|pbh_[a-z_0-9]+)\s*\(", src))
+    declared -= {"pbrtb200_ctx", "pbh_scene"}
+    L = pb.lib()
+    bound = {n for n, _, _ in _ffi.SYMBOLS}
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+        assert name in bound, f"{name} declared in include/ but not bound in _ffi.SYMBOLS"
+
+
+def test_struct_sizes_match_the_abi():
+    assert C.sizeof(_ffi.Node32) == 32 and C.sizeof(_ffi.Tri48) == 48 and C.sizeof(_ffi.Sphere80) == 80
+    assert C.sizeof(_ffi.Film) == 4 * 8 + 256 * 4
+
+
+def test_no_cpu_fallback_without_a_device():
+    """On a box without CUDA the product must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(pb.PbrtError) as e:
+        pb.Context(0)
+    assert e.value.code == _ffi.ENODEV
+
+
+@pytest.mark.parametrize("sm", ["sah", "middle", "equal"])
+@pytest.mark.parametrize("which", ["c1", "c2", "c3", "c4"])
+def test_host_bvh_equals_reference_tree(orc, which, sm):
+    """The in-place host builder must emit BVHAccelerator::new's tree (bvh.rs:189-362) node for node
+    and the same ordered primitive list; checked bit-exactly against the line-faithful oracle."""
+    cfg = {"c1": lambda: scenes.config1(), "c2": lambda: scenes.config2(n=20000),
+           "c3": lambda: scenes.config3(nx=80, nz=40),
+           "c4": lambda: scenes.config4(n_ground=(40, 20), n_spheres=200)}[which]()
+    cfg["scene"].aggregate.sm = sm
+    hs = pb.HostScene(cfg["scene"])
+    osc = orc.OracleScene(cfg["scene"])
+    hn = hs.nodes()
+    ob, om = osc.nodes()
+    assert len(hn) == len(ob)
+    assert np.array_equal(np.concatenate([hn["bmin"], hn["bmax"]], 1).view(np.uint32), ob.view(np.uint32))
+    assert np.array_equal(hn["offset"], om[:, 0])
+    assert np.array_equal(hn["is_leaf"], om[:, 2])
+    assert np.array_equal(np.where(hn["is_leaf"] == 1, hn["count"], hn["axis"]), om[:, 1])
+    assert np.array_equal(hs.prim_order(), osc.prim_order())
+
+
+def test_flatten_vertex_order_is_refine_reversed():
+    """shape/mesh.rs:329-331: triangle j has (p1,p2,p3) = (P[vi[3j+2]], P[vi[3j+1]], P[vi[3j]])."""
+    P = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    vi = np.array([0, 3, 2, 0, 1, 2, 0, 3, 1, 1, 2, 3], np.uint32)
+    mesh = pb.Shape.triangle_mesh(pb.Transform.new(), pb.Transform.new(), False, vi, P)
+    hs = pb.HostScene(pb.Scene.new_with(pb.Primitive.bvh([pb.Primitive.geometric(mesh, None)], 1, "sah"), []))
+    f = hs.flat.contents
+    order = hs.prim_order()
+    for i in range(f.n_prims):
+        j = int(order[i, 2])
+        t = f.tris[i]
+        assert list(t.p1) == P[vi[3 * j + 2]].tolist()
+        assert list(t.p2) == P[vi[3 * j + 1]].tolist()
+        assert list(t.p3) == P[vi[3 * j]].tolist()
+        assert t.user == j
+
+
+def test_bad_mesh_is_rejected():
+    mesh = pb.Shape.triangle_mesh(pb.Transform.new(), pb.Transform.new(), False, [0, 1], np.zeros((3, 3)))
+    with pytest.raises(pb.PbrtError):
+        pb.HostScene(pb.Scene.new_with(pb.Primitive.bvh([pb.Primitive.geometric(mesh, None)], 1, "sah"), []))
+
+
+def test_singular_matrix_is_an_error_code():
+    out = np.zeros(16, np.float32)
+    assert pb.lib().pbh_invert(np.zeros(16, np.float32).ctypes.data_as(C.POINTER(C.c_float)),
+                               out.ctypes.data_as(C.POINTER(C.c_float))) == _ffi.ESINGULAR
+
+
+def test_transforms_match_oracle(orc):
+    L = orc.lib()
+    for kind, args, mk in [(0, (1.5, -2.0, 3.25), lambda a: pb.Transform.translate(a)),
+                           (1, (2.0, 0.5, 4.0), lambda a: pb.Transform.scale(*a)),
+                           (2, (33.0, 0, 0), lambda a: pb.Transform.rotate_x(a[0])),
+                           (3, (90.0, 0, 0), lambda a: pb.Transform.rotate_y(a[0])),
+                           (4, (-17.5, 0, 0), lambda a: pb.Transform.rotate_z(a[0]))]:
+        m, mi = np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32)
+        L.orc_transform(kind, _p(np.array(args, np.float32)), _p(m), _p(mi))
+        t = mk(args)
+        assert np.array_equal(t.m.view(np.uint32), m.view(np.uint32))
+        assert np.array_equal(t.m_inv.view(np.uint32), mi.view(np.uint32))
+    m, mi = np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32)
+    a = [np.array(v, np.float32) for v in ((1, 1, -6), (1, 1, 1), (0, 1, 0))]
+    L.orc_look_at(_p(a[0]), _p(a[1]), _p(a[2]), _p(m), _p(mi))
+    t = pb.Transform.look_at(*a)
+    assert np.array_equal(t.m.view(np.uint32), m.view(np.uint32))
+    assert np.array_equal(t.m_inv.view(np.uint32), mi.view(np.uint32))
+
+
+def test_camera_film_sampler_descriptors_match_oracle(orc):
+    for cfg in (scenes.config1(), scenes.config2(n=10), scenes.config3(nx=4, nz=4),
+                scenes.config1(xres=142, yres=12, crop=(1 / 3, 2 / 3, 1 / 3, 2 / 3), filt=pb.Filter.mean(3.0, 3.0)),
+                scenes.config1(filt=pb.Filter.gaussian(2.0, 2.0, 1.5)),
+                scenes.config1(filt=pb.Filter.mitchell(2.0, 2.5, 1 / 3, 1 / 3)),
+                scenes.config1(filt=pb.Filter.lanczos(3.0, 3.0, 3.0)),
+                scenes.config1(filt=pb.Filter.triangle(1.5, 2.0))):
+        cam, film = cfg["camera"], cfg["film"]
+        oc = orc.render_config(cam, cfg["sampler"], num_cpus=8)
+        r2c, r2ci, dxdy = np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32), np.zeros(6, np.float32)
+        assert orc.lib().orc_perspective(C.byref(oc), _p(r2c), _p(r2ci), _p(dxdy)) == 0
+        d = cam.desc
+        assert np.array_equal(np.array(d.raster_to_camera, np.float32).view(np.uint32), r2c.reshape(-1).view(np.uint32))
+        assert np.array_equal(np.array(list(d.dx_camera) + list(d.dy_camera), np.float32).view(np.uint32), dxdy.view(np.uint32))
+        lay = orc.layout(oc)
+        assert tuple(lay["sample_ext"]) == film.get_sample_extent()
+        assert tuple(lay["pixel_ext"]) == film.get_pixel_extent()
+        tab = np.zeros(256, np.float32)
+        f = film.filter
+        orc.lib().orc_filter_table(f.ty, f.xw, f.yw, f.p0, f.p1, _p(tab))
+        assert np.array_equal(np.array(film.desc.filter_table, np.float32).view(np.uint32), tab.view(np.uint32))
+        r = pb.lib().pbh_num_tasks(8, film.x_res * film.y_res)
+        assert r == lay["num_tasks"]
+
+
+def test_film_extents_kat():
+    """camera/film.rs:374-408 through the product's host mirror."""
+    f = pb.Film.image(142, 12, pb.Filter.mean(3.0, 3.0), (np.float32(1) / np.float32(3), np.float32(2) / np.float32(3),
+                                                           np.float32(1) / np.float32(3), np.float32(2) / np.float32(3)))
+    assert f.get_sample_extent() == (45, 98, 1, 11) and f.get_pixel_extent() == (48, 95, 4, 8)
+    f = pb.Film.image(142, 12, pb.Filter.mean(3.0, 3.0), (0.0, np.float32(1) / np.float32(3),
+                                                           np.float32(1) / np.float32(3), np.float32(2) / np.float32(3)))
+    assert f.get_sample_extent() == (-3, 51, 1, 11) and f.get_pixel_extent() == (0, 48, 4, 8)
+
+
+def test_film_to_rgb_matches_oracle(orc):
+    cfg = scenes.config1(xres=32, yres=24)
+    osc = orc.OracleScene(cfg["scene"])
+    ref = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8))
+    assert np.array_equal(pb.film_to_rgb(ref["film"]).view(np.uint32), ref["rgb"].view(np.uint32))

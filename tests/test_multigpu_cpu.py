@@ -1,0 +1,58 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the tile partition + film gather."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pbrt_rust_b200 import multigpu
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("ext", [(0, 1920, 0, 1080), (48, 95, 4, 8), (0, 70, 0, 130)])
+def test_tiles_partition_the_film_exactly_once(world, ext):
+    cov = multigpu.coverage(ext, world)
+    assert cov.min() == 1 and cov.max() == 1
+    sizes = [sum((c - a) * (d - b) for a, b, c, d in multigpu.partition_tiles(ext, r, world)) for r in range(world)]
+    assert sum(sizes) == (ext[1] - ext[0]) * (ext[3] - ext[2])
+    if ext[1] - ext[0] >= 1024:
+        assert max(sizes) / (sum(sizes) / world) < 1.1      # near-even static split
+
+
+def _worker(rank, world, port, ext, ref_path, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ref = torch.from_numpy(np.load(ref_path))
+    x0, x1, y0, y1 = ext
+    mine = torch.zeros_like(ref)
+    for (a, b, c, d) in multigpu.partition_tiles(ext, rank, world, tile=16):
+        mine[b - y0:d - y0, a - x0:c - x0] = ref[b - y0:d - y0, a - x0:c - x0]
+    flat = mine.reshape(-1).contiguous()
+    multigpu.gather_film(flat, dist, dst=0)
+    if rank == 0:
+        np.save(out_path, flat.reshape(ref.shape).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather_is_bit_exact(tmp_path, orc):
+    """Each rank holds only its tiles of an (oracle-rendered) film; the reduce must rebuild the
+    whole film bit for bit — the property the NCCL gather in bench.py relies on."""
+    from pbrt_rust_b200 import scenes
+    cfg = scenes.config1(xres=80, yres=60)
+    osc = orc.OracleScene(cfg["scene"])
+    ref = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8))["film"]
+    ext = cfg["film"].get_pixel_extent()
+    ref_path, out_path = str(tmp_path / "ref.npy"), str(tmp_path / "out.npy")
+    np.save(ref_path, ref)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, ext, ref_path, out_path), nprocs=2, join=True)
+    out = np.load(out_path)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))

@@ -1,0 +1,579 @@
+"""Pins the CPU oracle against every known-answer test the reference's own unit tests hold for the
+hot path.  Each test names the reference test it transcribes (file:line)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+F32_MAX = float(np.finfo(np.float32).max)
+f32 = np.float32
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _ray(o, d, mint=0.0, maxt=F32_MAX):
+    return np.array([*o, mint, *d, maxt], np.float32)
+
+
+def _ident():
+    return np.eye(4, dtype=np.float32)
+
+
+# ---- utils/mod.rs ---------------------------------------------------------------------------
+def test_quadratic(orc):
+    """utils/mod.rs:366-388 it_can_solve_quadratic_equations"""
+    L = orc.lib()
+
+    def q(a, b, c):
+        t0, t1 = C.c_float(), C.c_float()
+        ok = L.orc_quadratic(a, b, c, C.byref(t0), C.byref(t1))
+        return (t0.value, t1.value) if ok else None
+
+    assert q(1.0, 0.0, 1.0) is None
+    assert q(-1.0, 4.0, -4.0) == (2.0, 2.0)
+    assert q(1.0, 0.0, 0.0) == (0.0, 0.0)
+    assert q(1.0, -2.0, 0.0) == (0.0, 2.0)
+    for i in range(2, 200):
+        assert q(1.0, -float(i), 0.0) == (0.0, float(i))
+    t0 = float(f32(np.sqrt(f32(3.0))) + f32(4.0))
+    t1 = float(-f32(np.sqrt(f32(3.0))) + f32(4.0))
+    assert q(-1.0, 8.0, -13.0) == (t1, t0)
+    assert q(0.0, 1.0, 1.0) is None
+    assert q(0.0, 0.0, 1.75) is None
+
+
+def test_solve_linear_system_2x2(orc):
+    """utils/mod.rs:392-437"""
+    L = orc.lib()
+
+    def s(a, b):
+        x = np.zeros(2, np.float32)
+        ok = L.orc_solve_2x2(_p(np.array(a, np.float32).reshape(-1)), _p(np.array(b, np.float32)), _p(x))
+        return tuple(x) if ok else None
+
+    nan = float("nan")
+    assert s([[1, 0], [0, 1]], [3.5, -4.2]) == (f32(3.5), f32(-4.2))
+    for a in ([[nan, 0], [0, 1]], [[1, nan], [0, 1]], [[1, 0], [nan, 1]], [[1, 0], [0, nan]]):
+        assert s(a, [3.5, -4.2]) is None
+    assert s([[1, 0], [0, 1]], [nan, -4.2]) is None
+    assert s([[1, 0], [0, 1]], [3.5, nan]) is None
+    for a in ([[0, 0], [0, 0]], [[1, 2], [1, 2]], [[3, 2], [6, 4]]):
+        assert s(a, [3.5, -4.2]) is None
+    h = 0.5 * math.sqrt(2.0)
+    ox, oy = s([[h, -h], [h, h]], [3.0, 1.0])
+    assert abs(ox - 2.0 * math.sqrt(2.0)) < 1e-6 and abs(oy + math.sqrt(2.0)) < 1e-6
+
+
+def test_partition_by(orc):
+    """utils/mod.rs:439-517 it_can_partition_slices"""
+    L = orc.lib()
+
+    def part(xs):
+        a = np.array(xs, np.int32)
+        L.orc_partition_by_i32(_p(a), C.c_uint64(len(a)))
+        return a.tolist()
+
+    def halves_ok(xs):
+        m = len(xs) // 2
+        return max(xs[:m]) <= min(xs[m:])
+
+    assert halves_ok(part([2, 5, 6, 1, 0, 4, 3, 2, 5, 1, 3, 3, 5]))
+    assert part([1, 2]) == [1, 2] and part([2, 1]) == [1, 2] and part([1]) == [1]
+    assert halves_ok(part([1, 0, 0, 0, -1, 0]))
+    assert part([3, 1, 1]) == [1, 1, 3]
+    assert part([3, 1, 2]) == [1, 2, 3]
+    assert part([3, 3, 1]) == [1, 3, 3]
+    assert part([2, 2, 2]) == [2, 2, 2]
+    assert halves_ok(part([-2, -4, 2, 2, 2, 4, 4, 4, 4, 4, 4, 4]))
+    assert halves_ok(part([-2, -4, 2, 2, 2, 4, 4, 4, 4, 4, 4, -5]))
+
+
+def test_get_crop_window(orc):
+    """utils/mod.rs:520-529"""
+    L = orc.lib()
+
+    def cw(num, count, aspect):
+        o = np.zeros(4, np.float32)
+        L.orc_get_crop_window(num, count, aspect, _p(o))
+        return tuple(float(x) for x in o)
+
+    assert cw(0, 2, 2.0) == (0.0, 0.5, 0.0, 1.0)
+    assert cw(1, 2, 2.0) == (0.5, 1.0, 0.0, 1.0)
+    assert cw(0, 2, 0.5) == (0.0, 1.0, 0.0, 0.5)
+    assert cw(1, 2, 0.5) == (0.0, 1.0, 0.5, 1.0)
+    assert cw(0, 4, 1.0) == (0.0, 0.5, 0.0, 0.5)
+    assert cw(1, 4, 1.0) == (0.5, 1.0, 0.0, 0.5)
+    assert cw(2, 4, 1.0) == (0.0, 0.5, 0.5, 1.0)
+    assert cw(3, 4, 1.0) == (0.5, 1.0, 0.5, 1.0)
+
+
+def test_sampler_sub_windows(orc):
+    """sampler/base.rs:68-89 its_base_can_tile_windows"""
+    L = orc.lib()
+
+    def sw(ext, num, count):
+        o = np.zeros(4, np.int32)
+        L.orc_compute_sub_window(_p(np.array(ext, np.int32)), C.c_uint64(num), C.c_uint64(count), _p(o))
+        return tuple(int(x) for x in o)
+
+    e = (0, 10, 0, 2)
+    assert sw(e, 0, 20) == (0, 1, 0, 1)
+    assert sw(e, 9, 20) == (9, 10, 0, 1)
+    assert sw(e, 10, 20) == (0, 1, 1, 2)
+    assert sw(e, 19, 20) == (9, 10, 1, 2)
+    assert sw(e, 4, 5) == (8, 10, 0, 2)
+    assert sw(e, 0, 1) == (0, 10, 0, 2)
+    e = (0, 2, 0, 10)
+    assert sw(e, 0, 20) == (0, 1, 0, 1)
+    assert sw(e, 9, 20) == (1, 2, 4, 5)
+    assert sw(e, 10, 20) == (0, 1, 5, 6)
+    assert sw(e, 19, 20) == (1, 2, 9, 10)
+    assert sw(e, 4, 5) == (0, 2, 8, 10)
+    assert sw(e, 0, 1) == (0, 2, 0, 10)
+
+
+def test_num_tasks_as_written(orc):
+    """sampler_renderer.rs:41-44: 1080p -> 13, 4K -> 15"""
+    L = orc.lib()
+    assert L.orc_num_tasks_for(8, 1920 * 1080) == 13
+    assert L.orc_num_tasks_for(8, 3840 * 2160) == 15
+    assert L.orc_num_tasks_for(8, 640 * 480) == 11   # max(256, 1200) = 1200 -> ceil(log2) = 11
+    assert L.orc_num_tasks_for(8, 16) == 8           # 256 = 2^8 exactly
+
+
+# ---- bbox.rs --------------------------------------------------------------------------------
+def _bbox_isect(orc, box, ray):
+    t = np.zeros(2, np.float32)
+    ok = orc.lib().orc_bbox_intersect(_p(np.array(box, np.float32)), _p(ray), _p(t))
+    return (float(t[0]), float(t[1])) if ok else None
+
+
+def test_bbox_intersect(orc):
+    """bbox.rs:553-615 it_can_be_intersected"""
+    b = [-1, -1, -1, 1, 1, 1]
+    for axis in range(3):
+        o = [0.0, 0.0, 0.0]
+        for sign in (1.0, -1.0):
+            o[axis] = 2.0 * sign
+            d = [0.0, 0.0, 0.0]
+            d[axis] = -sign
+            assert _bbox_isect(orc, b, _ray(o, d)) == (1.0, 3.0)
+            d[axis] = sign
+            assert _bbox_isect(orc, b, _ray(o, d)) is None
+    n = float(f32(1.0) / np.sqrt(f32(3.0)))
+    dn = (f32(1.0) * (f32(1.0) / np.sqrt(f32(3.0))))
+    d1, d2 = _bbox_isect(orc, b, _ray([-1, -1, -1], [dn, dn, dn]))
+    assert d1 == 0.0 and abs(d2 - math.sqrt(12.0)) < 1e-6
+    assert _bbox_isect(orc, b, _ray([1.5, 0.5, 0.5], [-0.5, 0.0, 0.5])) == (1.0, 1.0)
+    assert _bbox_isect(orc, b, _ray([1.5, 0.5, 0.5], [-0.5, -0.5, 0.5])) == (1.0, 1.0)
+    assert _bbox_isect(orc, b, _ray([2, 0, 0], [-1, 0, 0], mint=2.0)) == (2.0, 3.0)
+    del n
+
+
+def test_bbox_algebra(orc):
+    """bbox.rs:225-401: empty(), surface_area, volume, max_extent tie rules"""
+    L = orc.lib()
+
+    def props(box):
+        a, v, m, e = C.c_float(), C.c_float(), C.c_int32(), C.c_int32()
+        L.orc_bbox_props(_p(np.array(box, np.float32)), C.byref(a), C.byref(v), C.byref(m), C.byref(e))
+        return a.value, v.value, m.value, bool(e.value)
+
+    empty = [F32_MAX] * 3 + [-F32_MAX] * 3
+    assert props(empty)[3] and props(empty)[0] == 0.0 and props(empty)[2] == 2
+    assert props([0, 0, 0, 0, 0, 0])[3] and props([0, 0, 0, 1, 0, 4])[3]
+    assert props([2, 0, 0, 1, 3, 4])[3] and props([-2, 0, 0, 1, -3, 4])[3]
+    assert not props([0, 0, 0, 1, 3, 4])[3]
+    assert props([0, 0, 0, 1, 1, 1])[0] == 6.0
+    assert props([1, 0, 0, 1, 1, 1])[0] == 2.0
+    assert props([0, 0, 0, 2, 3, 4])[0] == 52.0
+    assert props([1, 0, 0, 1, 1, 1])[1] == 0.0 and props([0, 0, 0, 2, 3, 4])[1] == 24.0
+    assert props([0, 0, 0, 1, 1, 1])[2] == 2
+    assert props([0, 0, 0, 2, 3, 4])[2] == 2
+    assert props([0, 0, 0, 4, 5, 4])[2] == 1
+    assert props([0, 10, 0, 4, 5, 4])[2] == 2
+
+
+# ---- shape/mesh.rs --------------------------------------------------------------------------
+TET_PTS = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+TET_TRIS = np.array([0, 3, 2, 0, 1, 2, 0, 3, 1, 1, 2, 3], np.uint32)
+
+
+def _tet_tris(orc):
+    v = np.zeros(12, np.uint32)
+    orc.lib().orc_mesh_refine(_p(TET_TRIS), C.c_uint64(12), _p(v))
+    return v.reshape(4, 3)
+
+
+def test_mesh_refine_order_and_winding(orc):
+    """shape/mesh.rs:425-436 it_can_be_refined_to_triangles"""
+    v = _tet_tris(orc)
+    assert v[3].tolist() == [2, 3, 0]
+    assert v[2].tolist() == [2, 1, 0]
+    assert v[1].tolist() == [1, 3, 0]
+    assert v[0].tolist() == [3, 2, 1]
+
+
+def test_triangles_can_be_intersected(orc):
+    """shape/mesh.rs:478-497"""
+    v = _tet_tris(orc)
+    p9 = TET_PTS[v[0]].reshape(-1).copy()
+
+    def hit(o, d):
+        tbb = np.zeros(3, np.float32)
+        return bool(orc.lib().orc_tri_intersect(_p(p9), _p(_ray(o, d)), _p(tbb)))
+
+    assert hit([0, 0, 0], [1, 1, 1])
+    assert not hit([1.5, 1.5, 1.5], [1, 1, 1])
+    assert hit([1.5, 1.5, 1.5], [-1, -1, -1])
+    assert not hit([1, 1, -1], [-1, -1, 1])
+
+
+def test_triangle_areas(orc):
+    """shape/mesh.rs:507-524"""
+    L = orc.lib()
+    L.orc_tri_area.restype = C.c_float
+    v = _tet_tris(orc)
+    for k in (1, 2, 3):
+        assert L.orc_tri_area(_p(TET_PTS[v[k]].reshape(-1).copy())) == 0.5
+        assert L.orc_tri_area(_p((2.0 * TET_PTS[v[k]]).reshape(-1).copy())) == 2.0
+
+
+# ---- shape/sphere.rs ------------------------------------------------------------------------
+def _sphere_isect(orc, o2w, o2w_inv, rad, z0, z1, pm, ray, want_dg=False):
+    out3 = np.zeros(3, np.float32)
+    dg = np.zeros(14, np.float32)
+    ok = orc.lib().orc_sphere_intersect(_p(o2w), _p(o2w_inv), 0, rad, z0, z1, pm, _p(ray), _p(out3), _p(dg))
+    return (out3, dg) if ok else None
+
+
+def _translate(v):
+    m, mi = _ident(), _ident()
+    m[:3, 3] = v
+    mi[:3, 3] = -np.array(v, np.float32)
+    return m, mi
+
+
+def test_sphere_creation(orc):
+    """shape/sphere.rs:191-204 it_can_be_created"""
+    o = np.zeros(6, np.float32)
+    orc.lib().orc_sphere_props(1.0, -1.0, 1.0, 360.0, _p(o))
+    assert o[0] == -1.0 and o[1] == 1.0
+    assert o[2] == f32(np.arccos(f32(-1.0))) and o[3] == 0.0
+    assert o[4] == f32(f32(np.pi) * f32(2.0))
+
+
+def test_sphere_can_be_intersected(orc):
+    """shape/sphere.rs:206-263"""
+    m, mi = _translate([1.0, 2.0, 1.0])
+    hit = lambda d: _sphere_isect(orc, m, mi, 1.0, -1.0, 1.0, 360.0, _ray([0, 0, 0], d)) is not None
+    assert hit([1.0, 1.5, 1.0]) and hit([1.0, 1.0, 1.0]) and not hit([1.0, 0.5, 1.0])
+    assert hit([0.0, 2.0, 1.0]) and hit([1.0, 2.0, 0.0])
+    # partial sphere: translate(0,-3,0) * scale(2,2,2)
+    m2 = np.array([[2, 0, 0, 0], [0, 2, 0, -3], [0, 0, 2, 0], [0, 0, 0, 1]], np.float32)
+    m2i = np.zeros((4, 4), np.float32)
+    assert orc.lib().orc_invert(_p(m2), _p(m2i)) == 0
+    down = _ray([0, 0, 0], [0, -1, 0])
+    assert _sphere_isect(orc, m2, m2i, 0.75, -0.75, -0.5, 180.0, down) is None
+    assert _sphere_isect(orc, m2, m2i, 0.75, 0.5, 0.75, 180.0, down) is None
+    assert _sphere_isect(orc, m2, m2i, 0.75, -0.5, 0.75, 180.0, down) is not None
+    assert _sphere_isect(orc, m2, m2i, 0.75, -0.5, 0.75, 180.0, _ray([0, -3, 0], [0, -1, 0])) is None
+    assert _sphere_isect(orc, m2, m2i, 0.75, -0.5, 0.75, 180.0, _ray([0, -3, 0], [0, 1, 0])) is not None
+    assert _sphere_isect(orc, m2, m2i, 0.75, -0.5, 0.75, 180.0, _ray([0, -4, 10], [0, 0, -1])) is None
+
+
+def test_sphere_intersection_information(orc):
+    """shape/sphere.rs:266-292 it_has_intersection_information"""
+    m, mi = _translate([0.0, -1.0, 0.0])
+    out3, dg = _sphere_isect(orc, m, mi, 0.5, -0.5, 0.5, 360.0, _ray([0, 0, 0], [0, -1, 0]))
+    assert out3[0] == 0.5 and out3[1] == f32(0.5) * f32(5e-4)
+    assert dg[0:3].tolist() == [0.0, -0.5, 0.0]
+    assert dg[3] == 0.0 and abs(dg[4] - 1.0) < 1e-6 and dg[5] == 0.0
+    assert dg[6] == 0.25 and abs(dg[7] - 0.5) < 1e-6
+    assert abs(dg[8] + math.pi) < 1e-6 and dg[9] == 0.0 and dg[10] == 0.0
+    assert dg[11] == 0.0 and dg[12] == 0.0 and abs(dg[13] - math.pi / 2) < 1e-6
+
+
+def test_sphere_areas(orc):
+    """shape/sphere.rs:295-333 (transform-independent area)"""
+    def area(rad, z0, z1, pm):
+        o = np.zeros(6, np.float32)
+        orc.lib().orc_sphere_props(rad, z0, z1, pm, _p(o))
+        return float(o[5])
+    pi = float(f32(np.pi))
+    assert area(1.0, -1.0, 1.0, 360.0) == float(f32(4.0) * f32(np.pi))
+    assert area(0.5, -1.0, 1.0, 360.0) == pi
+    assert area(1.0, -1.0, 1.0, 180.0) == float(f32(2.0) * f32(np.pi))
+    assert area(0.5, 0.0, 1.0, 360.0) == float(f32(0.5) * f32(np.pi))
+    assert area(0.5, -1.0, 0.0, 360.0) == float(f32(0.5) * f32(np.pi))
+
+
+# ---- primitive/aggregates --------------------------------------------------------------------
+def _sphere_prims(pb, centres):
+    mat = pb.Material.matte(pb.Texture.constant(0.5), pb.Texture.constant(0.0))
+    out = []
+    for v in centres:
+        t = pb.Transform.translate(v)
+        out.append(pb.Primitive.geometric(pb.Shape.sphere(t, t.inverse(), False, 1.0, -1.0, 1.0, 360.0), mat))
+    return out
+
+
+GET_SPHERES = [(0, 0, 0), (2, 0, 0), (0, 2, 0), (2, 2, 0), (0, 0, 2), (2, 0, 2), (0, 2, 2), (2, 2, 2)]
+
+
+@pytest.mark.parametrize("sm", ["sah", "middle", "equal"])
+def test_bvh_leaf_coverage(orc, sm):
+    """bvh.rs:439-455 it_can_be_created"""
+    import pbrt_rust_b200 as pb
+    sc = pb.Scene.new_with(pb.Primitive.bvh(_sphere_prims(pb, GET_SPHERES), 1, sm), [])
+    b, m = orc.OracleScene(sc).nodes()
+    leaves = m[m[:, 2] == 1]
+    assert np.all(leaves[:, 1] == 1)
+    assert sorted(leaves[:, 0].tolist()) == list(range(8))
+
+
+def _node_box(b, i):
+    return b[i].tolist()
+
+
+def test_bvh_arrange_by_middle(orc):
+    """bvh.rs:490-511"""
+    import pbrt_rust_b200 as pb
+    cs = [(-4, 0, 0), (-2, 0, 0), (2, 0, 0), (4, 0, 0), (6, 0, 0), (8, 0, 0)]
+    b, _ = orc.OracleScene(pb.Scene.new_with(pb.Primitive.bvh(_sphere_prims(pb, cs), 1, "middle"), [])).nodes()
+    assert _node_box(b, 0) == [-5, -1, -1, 9, 1, 1]
+    assert _node_box(b, 1) == [-5, -1, -1, -1, 1, 1]
+    assert _node_box(b, 4) == [1, -1, -1, 9, 1, 1]
+
+
+def test_bvh_arrange_by_equal_counts(orc):
+    """bvh.rs:513-534"""
+    import pbrt_rust_b200 as pb
+    cs = [(-4, 0, 0), (-2, 0, 0), (2, 0, 0), (4, 0, 0), (6, 0, 0), (8, 0, 0)]
+    b, _ = orc.OracleScene(pb.Scene.new_with(pb.Primitive.bvh(_sphere_prims(pb, cs), 1, "equal"), [])).nodes()
+    assert _node_box(b, 0) == [-5, -1, -1, 9, 1, 1]
+    assert _node_box(b, 1) == [-5, -1, -1, 3, 1, 1]
+    assert _node_box(b, 6) == [3, -1, -1, 9, 1, 1]
+
+
+def test_bvh_arrange_by_sah(orc):
+    """bvh.rs:536-559"""
+    import pbrt_rust_b200 as pb
+    cs = [(-2, 2, 0), (-4, 0, 0), (2, 0, 0), (4, 2, -3), (4, 1.5, -1.5), (4, 1.5, 1.5), (4, 2, 3), (4, 0, 0)]
+    b, _ = orc.OracleScene(pb.Scene.new_with(pb.Primitive.bvh(_sphere_prims(pb, cs), 1, "sah"), [])).nodes()
+    assert _node_box(b, 0) == [-5, -1, -4, 5, 3, 4]
+    assert _node_box(b, 1) == [-5, -1, -1, 3, 3, 1]
+    assert _node_box(b, 6) == [3, -1, -4, 5, 3, 4]
+
+
+@pytest.mark.parametrize("sm", ["sah", "middle", "equal"])
+def test_aggregate_closest_hit_ids(orc, sm):
+    """primitive/aggregates/mod.rs:93-138 test_intersection (BVH x3): rays hit ids[0], ids[4], ids[6]"""
+    import pbrt_rust_b200 as pb
+    osc = orc.OracleScene(pb.Scene.new_with(pb.Primitive.bvh(_sphere_prims(pb, GET_SPHERES), 1, sm), []))
+    rays = np.stack([_ray([0, 0, -1], [0, 0, 1]), _ray([-1, 0, 2], [1, 0, 0]), _ray([4, 0, 0], [-2, 1, 1])])
+    prim, tbb, _ = osc.trace_closest(rays)
+    order = osc.prim_order()
+    assert order[prim, 1].tolist() == [0, 4, 6]
+
+
+def test_bvh_tetra_mesh_maxt(orc):
+    """bvh.rs:457-488 it_can_refine_primitives: ray (0.25,-1,0.25)+(0,1,0) hits at t = 1"""
+    import pbrt_rust_b200 as pb
+    for mp, sm in ((1, "sah"), (10, "middle")):
+        mesh = pb.Shape.triangle_mesh(pb.Transform.new(), pb.Transform.new(), False, TET_TRIS, TET_PTS)
+        osc = orc.OracleScene(pb.Scene.new_with(pb.Primitive.bvh([pb.Primitive.geometric(mesh, None)], mp, sm), []))
+        prim, tbb, _ = osc.trace_closest(_ray([0.25, -1.0, 0.25], [0, 1, 0])[None])
+        assert prim[0] != 0xFFFFFFFF and tbb[0, 0] == 1.0
+        occ, _ = osc.trace_any(_ray([0.25, -1.0, 0.25], [0, 1, 0])[None])
+        assert occ[0] == 1
+
+
+# ---- camera ---------------------------------------------------------------------------------
+def _projection(orc, proj, sw):
+    pi = np.zeros((4, 4), np.float32)
+    assert orc.lib().orc_invert(_p(proj), _p(pi)) == 0
+    r2s, s2r, r2c = (np.zeros((4, 4), np.float32) for _ in range(3))
+    assert orc.lib().orc_projection(640, 480, _p(proj), _p(pi), _p(np.array(sw, np.float32)), _p(r2s), _p(s2r), _p(r2c)) == 0
+    return r2s, s2r, r2c
+
+
+def test_projection_matrices(orc):
+    """camera/projective.rs:143-250"""
+    ortho = _ident()
+    ortho[2, 3] = -1.0
+    flip = np.array([[1, 0, 0, 0], [0, -1, 0, 480], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
+    for proj in (ortho, _ident()):
+        r2s, s2r, _ = _projection(orc, proj, [0, 640, 0, 480])
+        assert np.array_equal(r2s, flip)
+        fi = np.zeros((4, 4), np.float32)
+        orc.lib().orc_invert(_p(flip), _p(fi))
+        assert np.abs(s2r - fi).max() == 0.0 or np.allclose(s2r, fi, atol=0)
+    r2s, s2r, _ = _projection(orc, _ident(), [0, 1, 0, 1])
+    want = np.array([[1 / 640, 0, 0, 0], [0, -1 / 480, 0, 1], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
+    assert np.abs(r2s - want).max() < 5e-5
+    # raster_to_camera (projective.rs:226-244): Vector transforms
+    _, _, r2c = _projection(orc, ortho, [0, 1, 0, 1])
+    xfv = lambda m, v: (m[:3, :3] @ np.array(v, np.float32)).astype(np.float32)
+    assert xfv(r2c, [160, 120, 1]).tolist() == [0.25, -0.25, 1.0]
+    assert np.sum((xfv(r2c, [480, 360, 0]) - np.array([0.75, -0.75, 0.0])) ** 2) < 1e-5
+    _, _, r2c = _projection(orc, ortho, [-1, 1, -1, 1])
+    assert xfv(r2c, [160, 120, 1]).tolist() == [0.5, -0.5, 1.0]
+    assert np.sum((xfv(r2c, [480, 360, 0]) - np.array([1.5, -1.5, 0.0])) ** 2) < 1e-5
+
+
+def test_film_extents(orc):
+    """camera/film.rs:374-408 (cropped 142x12 film, 3x3 box filter)"""
+    L = orc.lib()
+
+    def ext(crop):
+        s, p = np.zeros(4, np.int32), np.zeros(4, np.int32)
+        L.orc_film_extents(142, 12, 3.0, 3.0, _p(np.array(crop, np.float32)), _p(s), _p(p))
+        return tuple(int(x) for x in s), tuple(int(x) for x in p)
+
+    ot, tt = float(f32(1.0) / f32(3.0)), float(f32(2.0) / f32(3.0))
+    s, p = ext([ot, tt, ot, tt])
+    assert s == (45, 98, 1, 11) and p == (48, 95, 4, 8)
+    s, p = ext([0.0, ot, ot, tt])
+    assert s == (-3, 51, 1, 11) and p == (0, 48, 4, 8)
+
+
+def test_filters(orc):
+    """filter.rs:136-210"""
+    ev = orc.lib().orc_filter_eval
+    for x in (0.0, 1.0, -1.0, 16.0, 0.001):
+        for y in (2.0, 0.0, -0.01, math.pi):
+            assert ev(0, 1.0, 1.0, 0, 0, x, y) == 1.0
+    tri = lambda x, y: ev(1, 2.0, 2.0, 0, 0, x, y)
+    assert tri(1, 0) == 0.5 and tri(0, 0) == 1.0 and tri(20, 0) == 0.0 and tri(-20, 0) == 0.0
+    assert tri(0, 20) == 0.0 and tri(0, -20) == 0.0 and tri(1, 1) == 0.25 and tri(0.5, 0.5) == 0.5625
+    assert tri(2, 0) == 0.0 and tri(0, -2) == 0.0
+    for ty, p0, p1, centre in ((2, 1.0, 0.0, 0.9), (4, 1.0, 0.0, 0.9), (3, 0.2, 0.4, 0.8)):
+        f = lambda x, y: ev(ty, 2.0, 2.0, p0, p1, x, y)
+        for (x, y) in ((20, 0), (-20, 0), (0, 20), (0, -20), (2, 0), (0, -2)):
+            assert f(x, y) == 0.0
+        assert f(0, 0) > centre
+    g = lambda x, y: ev(2, 2.0, 2.0, 1.0, 0, x, y)
+    assert g(1, 1) > 0 and g(0.5, 0) > 0 and g(1, -0.5) > 0 and g(-1, -1.5) > 0
+
+
+# ---- montecarlo.rs / rng.rs -------------------------------------------------------------------
+def test_stratified_non_jittered(orc):
+    """montecarlo.rs:194-249 (exact strata centres) + jittered strata bounds"""
+    L = orc.lib()
+    a = np.zeros(4, np.float32)
+    L.orc_stratified_1d(C.c_uint64(0), C.c_uint64(4), 0, _p(a))
+    assert a.tolist() == [0.5 / 4, 1.5 / 4, 2.5 / 4, 3.5 / 4]
+    L.orc_stratified_1d(C.c_uint64(0), C.c_uint64(4), 1, _p(a))
+    assert all(i / 4 <= a[i] <= (i + 1) / 4 for i in range(4))
+    b = np.zeros(8, np.float32)
+    L.orc_stratified_2d(C.c_uint64(0), C.c_uint64(2), C.c_uint64(2), 0, _p(b))
+    assert b.tolist() == [0.25, 0.25, 0.75, 0.25, 0.25, 0.75, 0.75, 0.75]
+    c = np.zeros(12, np.float32)
+    L.orc_stratified_2d(C.c_uint64(0), C.c_uint64(3), C.c_uint64(2), 1, _p(c))
+    for i in range(6):
+        x, y = i % 3, i // 3
+        assert x / 3 <= c[2 * i] <= (x + 1) / 3 and y / 2 <= c[2 * i + 1] <= (y + 1) / 2
+
+
+def test_rng_shuffle_properties(orc):
+    """rng.rs:49-87: shuffles are permutations; the lone 0 moves (seed 12), perm[0] != 0 (seed 120)"""
+    L = orc.lib()
+    xs = np.array([0] + [1] * 10, np.float32)
+    L.orc_rng_shuffle(C.c_uint64(12), _p(xs), C.c_uint64(11), C.c_uint64(1))
+    assert xs[0] == 1 and sorted(xs.tolist()) == [0.0] + [1.0] * 10
+    perm = np.arange(11, dtype=np.float32)
+    L.orc_rng_shuffle(C.c_uint64(120), _p(perm), C.c_uint64(11), C.c_uint64(1))
+    assert perm[0] != 0 and sorted(perm.tolist()) == list(range(11))
+
+
+def test_chacha_and_stdrng_known_answers(orc):
+    """Third-party arithmetic (rand 0.8.5 / rand_chacha 0.3.1 / rand_core 0.6.4, not vendored):
+    RFC 8439 §2.3.2 block, all-zero-key ChaCha20/ChaCha12 keystreams, rand 0.8's own
+    test_stdrng_construction value for StdRng::from_seed."""
+    L = orc.lib()
+
+    def block(state, rounds):
+        i, o = np.array(state, np.uint32), np.zeros(16, np.uint32)
+        L.orc_chacha_block(_p(i), rounds, _p(o))
+        return o
+
+    key = [int.from_bytes(bytes(range(4 * i, 4 * i + 4)), "little") for i in range(8)]
+    st = [0x61707865, 0x3320646e, 0x79622d32, 0x6b206574] + key + [1, 0x09000000, 0x4a000000, 0]
+    assert block(st, 20)[:4].tolist() == [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3]
+    z = [0x61707865, 0x3320646e, 0x79622d32, 0x6b206574] + [0] * 12
+    assert block(z, 20).tobytes().hex().startswith("76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7")
+    assert block(z, 12).tobytes().hex().startswith("9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f")
+    seed = bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16)
+    k = np.frombuffer(seed, dtype="<u4").copy()
+    w = np.zeros(2, np.uint32)
+    L.orc_stream_words(_p(k), C.c_uint64(0), C.c_uint64(2), _p(w))
+    assert int(w[0]) | (int(w[1]) << 32) == 10719222850664546238
+
+
+def test_rng_float_range_and_determinism(orc):
+    L = orc.lib()
+    a, b = np.zeros(4096, np.float32), np.zeros(4096, np.float32)
+    L.orc_rng_floats(C.c_uint64(3), C.c_uint64(4096), _p(a))
+    L.orc_rng_floats(C.c_uint64(3), C.c_uint64(4096), _p(b))
+    assert np.array_equal(a, b) and a.min() >= 0.0 and a.max() < 1.0 and 0.45 < a.mean() < 0.55
+    L.orc_rng_floats(C.c_uint64(4), C.c_uint64(4096), _p(b))
+    assert not np.array_equal(a, b)
+
+
+def test_van_der_corput_as_written(orc):
+    """sampler/utils.rs:6-35: the last bit-reversal step shifts by 2, not 1.  Checked
+    against an independent integer restatement of the Rust lines, plus a few hand values."""
+    L = orc.lib()
+    M = 0xFFFFFFFF
+
+    def vdc(n, scramble):
+        n = ((n << 16) | (n >> 16)) & M
+        n = (((n & 0x00ff00ff) << 8) | ((n & 0xff00ff00) >> 8)) & M
+        n = (((n & 0x0f0f0f0f) << 4) | ((n & 0xf0f0f0f0) >> 4)) & M
+        n = (((n & 0x33333333) << 2) | ((n & 0xCCCCCCCC) >> 2)) & M
+        n = (((n & 0x55555555) << 2) | ((n & 0xAAAAAAAA) >> 2)) & M   # as written
+        n ^= scramble
+        return float(np.float32(((n >> 8) & 0xffffff) / float(1 << 24)))
+
+    def sobol2(n, s):
+        v = 1 << 31
+        while n:
+            if (n & 1) == 0:
+                s ^= v
+            v ^= v >> 1
+            n >>= 1
+        return float(np.float32(((s >> 8) & 0xffffff) / float(1 << 24)))
+
+    assert L.orc_van_der_corput(0, 0) == 0.0
+    assert L.orc_van_der_corput(1, 0) == 0.0          # a true radical inverse would give 0.5
+    for n in list(range(64)) + [255, 1023, 65535, 123456789]:
+        for sc in (0, 0x9E3779B9, 0xFFFFFFFF):
+            assert L.orc_van_der_corput(n, sc) == vdc(n, sc)
+            assert L.orc_sobol2(n, sc) == sobol2(n, sc)
+
+
+def test_d7_strict_flags_black_and_fixed_nonblack(orc):
+    """BSDF::f as written is always black; the pbrt-semantics fix is not."""
+    from pbrt_rust_b200 import scenes
+    cfg = scenes.config1(xres=48, yres=36)
+    osc = orc.OracleScene(cfg["scene"])
+    oc = orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0)
+    black = orc.render(osc, oc, strict_flags=True)
+    lit = orc.render(osc, oc, strict_flags=False)
+    assert black["rgb"].max() == 0.0 and lit["rgb"].max() > 0.1
+
+
+def test_strict_and_default_modes_agree_for_box_filter(orc):
+    """with a 0.5 box filter the two film modes only differ at samples that
+    land exactly on a pixel boundary; images must agree everywhere else."""
+    from pbrt_rust_b200 import scenes
+    cfg = scenes.config3(nx=40, nz=20, xres=96, yres=54, xs=2, ys=2)
+    osc = orc.OracleScene(cfg["scene"])
+    a = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0))
+    b = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=1))
+    assert (np.abs(a["rgb"] - b["rgb"]).max(axis=-1) > 0).mean() <= 1e-3
+    assert a["stats"]["camera_rays"] == b["stats"]["camera_rays"]
