@@ -79,7 +79,7 @@ struct pbrtb200_ctx {
   DevBuf d_nodes, d_tris, d_leaf_prim, d_leaf_count, d_spheres, d_sphere_o2w, d_meshes, d_tri_uv,
       d_tri_n, d_tri_s, d_materials, d_textures, d_lights, d_area_tris;
   // per-frame work buffers (grow-only)
-  DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_xyz, d_hits, d_Le, d_contrib,
+  DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_lightu, d_edge, d_rad, d_hits,
       d_sq_rays, d_sq_slots, d_film, d_rects, d_rect_prefix, d_ctrl, d_rays_in, d_occ, d_out_a,
       d_out_b, d_out_c;
   // cached pixel work list
@@ -756,17 +756,31 @@ __global__ void k_scatter_raster(const DPixel* __restrict__ pixels, uint64_t n_s
   }
 }
 
+// `film` may be NULL (no edge flags / light floats needed: primary_hits).
 static int run_raygen(pbrtb200_ctx* ctx, const DSampler& ds, bool full, uint64_t pix0, uint64_t npix,
-                      uint64_t sample0) {
-  const DPixel* px = ctx->d_pixels.as<DPixel>() + pix0;
-  const uint64_t ns = npix * (uint64_t)ds.spp;
+                      uint64_t sample0, const pbrtb200_film* film) {
+  RaygenArgs ra{};
+  ra.pixels = ctx->d_pixels.as<DPixel>() + pix0;
+  ra.n_pixels = npix;
+  ra.img = ctx->d_img.as<float2>() + sample0;
+  ra.lens = full ? ctx->d_lens.as<float2>() + sample0 : nullptr;
+  ra.time = full ? ctx->d_time.as<float>() + sample0 : nullptr;
+  ra.light_pairs = ctx->sc.area_sample_pairs;
+  if (film) {
+    ra.lightu = ra.light_pairs ? ctx->d_lightu.as<float2>() + sample0 * ra.light_pairs : nullptr;
+    ra.edge = ctx->d_edge.as<uint32_t>() + pix0;
+    ra.fx_start = film->x_pixel_start;
+    ra.fy_start = film->y_pixel_start;
+    ra.fx_count = film->x_pixel_count;
+    ra.fy_count = film->y_pixel_count;
+    ra.xw = film->filter_xw;
+    ra.yw = film->filter_yw;
+  }
   if (full) {
-    k_raygen_full<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(
-        ds, px, npix, ctx->d_img.as<float2>() + sample0, ctx->d_lens.as<float2>() + sample0,
-        ctx->d_time.as<float>() + sample0);
+    k_raygen_full<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ds, ra);
   } else {
-    k_raygen_image<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(
-        ds, px, ns, ctx->d_img.as<float2>() + sample0);
+    const uint64_t nthreads = npix * (uint64_t)((ds.spp + 7) / 8);
+    k_raygen_groups<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(ds, ra);
   }
   CK(cudaGetLastError());
   return 0;
@@ -796,7 +810,7 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const p
   CK(ctx->d_hits.ensure(ns * sizeof(pbrtb200_hit16)));
   StageTimer tm{ctx, stats != nullptr};
   size_t e0 = tm.mark();
-  if (int rc = run_raygen(ctx, ds, full, 0, npix, 0)) return rc;
+  if (int rc = run_raygen(ctx, ds, full, 0, npix, 0, nullptr)) return rc;
   size_t e1 = tm.mark();
   CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
   TraceArgs a{};
@@ -885,21 +899,25 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   const uint64_t npix = ctx->n_list_pixels, ns = npix * (uint64_t)ds.spp;
   const bool full = cam->lens_radius > 0.0f || smp->kind != PBRTB200_SAMPLER_STRATIFIED;
   const uint32_t slots = std::max(1u, ctx->sc.light_slots);
+  const uint32_t le_slot = ctx->sc.area_sample_pairs ? 1u : 0u;
+  const uint32_t rad_slots = ctx->sc.n_lights ? ctx->sc.light_slots + le_slot : 0u;
+  if (ctx->sc.n_lights > PB_MAX_FOLD_LIGHTS) FAIL(PBRTB200_EINVAL, "more than 64 lights");
+  if (ns * (uint64_t)std::max(1u, rad_slots) >= 0xFFFFFFFFull)
+    FAIL(PBRTB200_EINVAL, "frame has more than 2^32 radiance terms; render it in tiles");
 
   uint64_t chunk_pix = std::max<uint64_t>(1, kChunkSamples / (uint64_t)ds.spp);
   chunk_pix = std::min(chunk_pix, npix);
   const uint64_t chunk_ns = chunk_pix * (uint64_t)ds.spp;
-  if (chunk_ns * slots >= 0xFFFFFFFFull) FAIL(PBRTB200_EINVAL, "too many light samples per chunk");
 
   CK(ctx->d_img.ensure(ns * sizeof(float2)));
   if (full) {
     CK(ctx->d_lens.ensure(ns * sizeof(float2)));
     CK(ctx->d_time.ensure(ns * sizeof(float)));
   }
-  CK(ctx->d_xyz.ensure(ns * sizeof(float4)));
+  CK(ctx->d_edge.ensure(npix * sizeof(uint32_t)));
+  if (ctx->sc.area_sample_pairs) CK(ctx->d_lightu.ensure(ns * ctx->sc.area_sample_pairs * sizeof(float2)));
+  if (rad_slots) CK(ctx->d_rad.ensure(ns * rad_slots * sizeof(float4)));
   CK(ctx->d_hits.ensure(chunk_ns * sizeof(pbrtb200_hit16)));
-  CK(ctx->d_Le.ensure(chunk_ns * sizeof(float4)));
-  CK(ctx->d_contrib.ensure(chunk_ns * slots * sizeof(float4)));
   CK(ctx->d_sq_rays.ensure(chunk_ns * slots * sizeof(pbrtb200_ray32)));
   CK(ctx->d_sq_slots.ensure(chunk_ns * slots * sizeof(uint32_t)));
   const size_t film_px = (size_t)film->x_pixel_count * (size_t)film->y_pixel_count;
@@ -917,16 +935,15 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   uint32_t launches = 0;
   size_t eA = tm.mark();
   CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
-  if (!tiles || !tiles->n_rects)
-    ;  // every film pixel is written by k_film
-  else
+  CK(cudaMemsetAsync(ctx->d_edge.p, 0, npix * sizeof(uint32_t), ctx->stream));
+  if (tiles && tiles->n_rects)  // otherwise every film pixel is written by k_film
     CK(cudaMemsetAsync(d_film, 0, film_px * sizeof(float4), ctx->stream));
 
   for (uint64_t p0 = 0; p0 < npix; p0 += chunk_pix) {
     const uint64_t cp = std::min(chunk_pix, npix - p0);
     const uint64_t s0 = p0 * (uint64_t)ds.spp, cn = cp * (uint64_t)ds.spp;
     size_t e0 = tm.mark();
-    if (int rc = run_raygen(ctx, ds, full, p0, cp, s0)) return rc;
+    if (int rc = run_raygen(ctx, ds, full, p0, cp, s0, film)) return rc;
     size_t e1 = tm.mark();
     CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(&ctrl(ctx)->sq_count, 0, sizeof(uint32_t), ctx->stream));
@@ -940,29 +957,35 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     if (int rc = launch_trace_t<false, 1>(ctx, dc, ta)) return rc;
     size_t e2 = tm.mark();
     launches += 2;
+    tm.span(e0, e1, 0);
+    tm.span(e1, e2, 1);
     if (ctx->sc.n_lights) {
       ShadeArgs sa{};
       sa.img = ta.img;
       sa.lens = ta.lens;
+      sa.lightu = ctx->sc.area_sample_pairs ? ctx->d_lightu.as<float2>() : nullptr;
       sa.hits = ta.hits;
-      sa.pixels = ctx->d_pixels.as<DPixel>() + p0;
       sa.area_tris = ctx->d_area_tris.as<DAreaTri>();
-      sa.Le = ctx->d_Le.as<float4>();
-      sa.contrib = ctx->d_contrib.as<float4>();
+      sa.rad = ctx->d_rad.as<float4>();
       sa.sq_rays = ctx->d_sq_rays.as<pbrtb200_ray32>();
       sa.sq_slots = ctx->d_sq_slots.as<uint32_t>();
       sa.sq_count = &ctrl(ctx)->sq_count;
+      sa.hit_total = &ctrl(ctx)->hit_total;
       sa.n = cn;
+      sa.sample0 = s0;
+      sa.rad_slots = rad_slots;
+      sa.le_slot = le_slot;
       sa.strict_flags = integ->strict_flags;
-      k_shade<<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, ds, sa);
+      k_shade<<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
       CK(cudaGetLastError());
       size_t e3 = tm.mark();
       CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));
       TraceArgs sh{};
       sh.rays = sa.sq_rays;
-      sh.contrib = sa.contrib;
+      sh.contrib = sa.rad;
       sh.slots = sa.sq_slots;
       sh.n_dyn = &ctrl(ctx)->sq_count;
+      sh.shadow_total = &ctrl(ctx)->shadow_total;
       sh.counter = &ctrl(ctx)->counter;
       sh.flags = &ctrl(ctx)->flags;
       if (int rc = launch_trace_t<true, 0>(ctx, dc, sh)) return rc;
@@ -971,26 +994,6 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       tm.span(e3, e4, 3);
       launches += 2;
     }
-    size_t e5 = tm.mark();
-    ResolveArgs ra{};
-    ra.hits = ta.hits;
-    ra.Le = ctx->d_Le.as<float4>();
-    ra.contrib = ctx->d_contrib.as<float4>();
-    ra.xyz = ctx->d_xyz.as<float4>();
-    ra.n = cn;
-    ra.out_base = s0;
-    ra.nan_count = &ctrl(ctx)->nan_count;
-    ra.hit_total = &ctrl(ctx)->hit_total;
-    ra.shadow_total = &ctrl(ctx)->shadow_total;
-    ra.sq_count = &ctrl(ctx)->sq_count;
-    ra.shaded = ctx->sc.n_lights ? 1 : 0;
-    k_resolve<<<(unsigned)((cn + 255) / 256), 256, 0, ctx->stream>>>(ctx->sc, ra);
-    CK(cudaGetLastError());
-    size_t e6 = tm.mark();
-    launches += 1;
-    tm.span(e0, e1, 0);
-    tm.span(e1, e2, 1);
-    tm.span(e5, e6, 2);
   }
   size_t eF0 = tm.mark();
   {
@@ -1008,16 +1011,27 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     df.sy0 = smp->y_start;
     df.sy1 = smp->y_end;
     df.spp = ds.spp;
+    DFold fd{};
+    fd.rad_slots = rad_slots;
+    fd.le_slot = le_slot;
+    fd.n_lights = ctx->sc.n_lights;
+    for (uint32_t i = 0; i < ctx->sc.n_lights; ++i) {
+      const pbrtb200_light& l = ctx->h_lights[i];
+      fd.area[i] = l.kind == PBRTB200_LIGHT_AREA ? 1 : 0;
+      fd.ns[i] = (uint16_t)(fd.area[i] ? l.num_samples : 1);
+    }
     FilmArgs fa{};
     fa.img = ctx->d_img.as<float2>();
-    fa.xyz = ctx->d_xyz.as<float4>();
+    fa.rad = ctx->d_rad.as<float4>();
+    fa.edge = ctx->d_edge.as<uint32_t>();
     fa.pix_index = ctx->d_pix_index.as<int32_t>();
     fa.rects = ctx->d_rects.as<int32_t>();
     fa.rect_prefix = ctx->d_rect_prefix.as<uint32_t>();
     fa.n_rects = ctx->n_rects;
     fa.n_pixels = ctx->n_film_pixels;
     fa.out = d_film;
-    k_film<<<(fa.n_pixels + 127) / 128, 128, 0, ctx->stream>>>(df, fa);
+    fa.nan_count = &ctrl(ctx)->nan_count;
+    k_film<<<(fa.n_pixels + 127) / 128, 128, 0, ctx->stream>>>(df, fd, fa);
     CK(cudaGetLastError());
     launches += 1;
   }

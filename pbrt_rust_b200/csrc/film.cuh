@@ -1,11 +1,18 @@
-// Film accumulation kernel (sm_100a): deterministic per-pixel gather.
+// Film accumulation kernel (sm_100a): deterministic per-pixel gather, fused with the radiance fold.
 //
-// Replaces Film::add_sample (src/camera/film.rs:192-249) over all samples of a frame.  One thread
-// owns one film pixel and visits, in global raster order (sampler pixel row, column, sample index),
-// every camera sample whose filter footprint can reach it; for each it repeats add_sample's own
-// extent and table-index arithmetic and adds `filter_wt * xyz` / `filter_wt` in that order.  The
-// float summation order per pixel is therefore fixed — identical from run to run, for any tile
-// partition and any GPU count — and equals a sequential CPU add_sample sweep in raster order.
+// Replaces Film::add_sample (src/camera/film.rs:192-249) over all samples of a frame, the light
+// sum of WhittedIntegrator::li (src/integrator/whitted.rs:49-66) and Spectrum::to_xyz
+// (src/spectrum.rs:37-41,443-458).  One thread owns one film pixel and visits, in global raster
+// order (sampler pixel row, column, sample index), every camera sample whose filter footprint can
+// reach it; for each it repeats add_sample's own extent and table-index arithmetic and adds
+// `filter_wt * xyz` / `filter_wt` in that order.  The float summation order per pixel is therefore
+// fixed — identical from run to run, for any tile partition and any GPU count — and equals a
+// sequential CPU add_sample sweep in raster order.
+//
+// Neighbour skipping: raygen marks a sampler pixel in `edge` iff one of its samples has an
+// add_sample extent other than exactly its own pixel.  An unmarked neighbour cannot contribute, so
+// its samples are not even loaded; with the 0.5 box filter this reduces the gather to the pixel's
+// own samples plus eight flag loads.  Wide filters mark every pixel and take the full gather.
 #pragma once
 #include "scene.cuh"
 
@@ -16,26 +23,70 @@ struct DFilm {
   int spp;
 };
 
+#define PB_MAX_FOLD_LIGHTS 64
+struct DFold {  // how the per-sample radiance terms fold into L (light order)
+  uint32_t rad_slots, le_slot, n_lights;
+  uint16_t ns[PB_MAX_FOLD_LIGHTS];   // samples of light i (1 for point/spot)
+  uint8_t area[PB_MAX_FOLD_LIGHTS];  // 1 = area light (averaged over its samples)
+};
+
 __constant__ float c_filter_table[256];
 
 struct FilmArgs {
-  const float2* __restrict__ img;        // per sample, list order
-  const float4* __restrict__ xyz;        // per sample, list order
-  const int32_t* __restrict__ pix_index; // sampler-extent raster -> list position or -1
-  const int32_t* __restrict__ rects;     // film pixel rects to fill
+  const float2* __restrict__ img;         // per sample, list order
+  const float4* __restrict__ rad;         // per sample x rad_slots radiance terms (rgb)
+  const uint32_t* __restrict__ edge;      // per list pixel
+  const int32_t* __restrict__ pix_index;  // sampler-extent raster -> list position or -1
+  const int32_t* __restrict__ rects;      // film pixel rects to fill
   const uint32_t* __restrict__ rect_prefix;  // prefix sums of rect areas (n_rects + 1)
   uint32_t n_rects;
   uint32_t n_pixels;  // total pixels over all rects
   float4* __restrict__ out;  // film, row-major over the film pixel extent
+  uint32_t* nan_count;
 };
 
+// L = Le + sum over lights; to_xyz.  Returns true if L has a NaN (sampler_renderer.rs:105 intent).
+PB_DEV bool fold_radiance(const DFold& fd, const float4* __restrict__ r, float* X, float* Y,
+                          float* Z) {
+  f3 L = mk3(0.f, 0.f, 0.f);
+  uint32_t slot = 0;
+  if (fd.le_slot) {
+    const float4 le = __ldg(r);
+    L = mk3(le.x, le.y, le.z);
+    slot = 1;
+  }
+  for (uint32_t li = 0; li < fd.n_lights; ++li) {
+    if (fd.area[li]) {
+      const uint32_t ns = fd.ns[li];
+      f3 Ld = mk3(0.f, 0.f, 0.f);
+      for (uint32_t s = 0; s < ns; ++s) {
+        const float4 c = __ldg(r + slot++);
+        Ld = Ld + mk3(c.x, c.y, c.z);
+      }
+      const float fns = (float)ns;
+      L = L + mk3(Ld.x / fns, Ld.y / fns, Ld.z / fns);
+    } else {
+      const float4 c = __ldg(r + slot++);
+      L = L + mk3(c.x, c.y, c.z);
+    }
+  }
+  *X = 0.412453f * L.x + 0.357580f * L.y + 0.180423f * L.z;
+  *Y = 0.212671f * L.x + 0.715160f * L.y + 0.072169f * L.z;
+  *Z = 0.019334f * L.x + 0.119193f * L.y + 0.950227f * L.z;
+  return isnan(L.x) || isnan(L.y) || isnan(L.z);
+}
+
 __global__ void __launch_bounds__(128)
-k_film(const DFilm f, const FilmArgs a) {
+k_film(const DFilm f, const DFold fd, const FilmArgs a) {
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= a.n_pixels) return;
-  // locate the rect (few rects per GPU; linear scan)
-  uint32_t r = 0;
-  while (r + 1 < a.n_rects && gid >= a.rect_prefix[r + 1]) ++r;
+  // locate the rect (few rects per GPU; binary search over the prefix sums)
+  uint32_t lo = 0, hi = a.n_rects;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (gid >= a.rect_prefix[mid]) lo = mid; else hi = mid;
+  }
+  const uint32_t r = lo;
   const int rx0 = a.rects[4 * r], ry0 = a.rects[4 * r + 1], rx1 = a.rects[4 * r + 2];
   const uint32_t local = gid - a.rect_prefix[r];
   const int rw = rx1 - rx0;
@@ -50,6 +101,7 @@ k_film(const DFilm f, const FilmArgs a) {
   qy1 = min(qy1, f.sy1 - 1);
   const int sw = f.sx1 - f.sx0;
   float X = 0.f, Y = 0.f, Z = 0.f, Wt = 0.f;
+  uint32_t nans = 0;
   for (int qy = qy0; qy <= qy1; ++qy) {
     // A sample of sampler pixel q has image coordinate in [q, q+1]; all of add_sample's float ops
     // are monotonic, so its pixel extent lies inside [ceil((q-0.5)-w), floor((q+0.5)+w)].
@@ -62,6 +114,8 @@ k_film(const DFilm f, const FilmArgs a) {
         continue;
       const int32_t li = __ldg(&a.pix_index[(size_t)(qy - f.sy0) * (size_t)sw + (size_t)(qx - f.sx0)]);
       if (li < 0) continue;
+      const bool own = (qx == x) && (qy == y);
+      if (!own && __ldg(&a.edge[li]) == 0u) continue;  // cannot reach any pixel but its own
       const uint64_t base = (uint64_t)li * (uint64_t)f.spp;
       for (int i = 0; i < f.spp; ++i) {
         const float2 im = __ldg(a.img + base + i);
@@ -79,14 +133,17 @@ k_film(const DFilm f, const FilmArgs a) {
         const int ix = min(f2i_sat(floorf(fabsf(fx))), 15);
         const int iy = min(f2i_sat(floorf(fabsf(fy))), 15);
         const float wt = c_filter_table[iy * 16 + ix];
-        const float4 c = __ldg(a.xyz + base + i);
-        X += wt * c.x;  // film.rs:241-244
-        Y += wt * c.y;
-        Z += wt * c.z;
+        float cx, cy, cz;
+        const bool bad = fold_radiance(fd, a.rad + (base + i) * fd.rad_slots, &cx, &cy, &cz);
+        if (bad && own) ++nans;
+        X += wt * cx;  // film.rs:241-244
+        Y += wt * cy;
+        Z += wt * cz;
         Wt += wt;
       }
     }
   }
+  if (nans) atomicAdd(a.nan_count, nans);
   a.out[(size_t)(y - f.y_start) * (size_t)f.x_count + (size_t)(x - f.x_start)] =
       make_float4(X, Y, Z, Wt);
 }

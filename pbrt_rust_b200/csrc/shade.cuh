@@ -404,26 +404,42 @@ PB_DEV uint32_t warp_agg_inc(uint32_t* ctr) {
 
 struct ShadeArgs {
   const float2* __restrict__ img;
-  const float2* __restrict__ lens;  // may be NULL
+  const float2* __restrict__ lens;    // may be NULL
+  const float2* __restrict__ lightu;  // light-sample float pairs (raygen), NULL without area lights
   const pbrtb200_hit16* __restrict__ hits;
-  const DPixel* __restrict__ pixels;
   const DAreaTri* __restrict__ area_tris;
-  float4* __restrict__ Le;       // per sample emitted radiance (rgb)
-  float4* __restrict__ contrib;  // per sample x light slot: f*Li*|wi.n|/pdf (rgb), 0 if none
-  pbrtb200_ray32* __restrict__ sq_rays;  // shadow-ray queue
-  uint32_t* __restrict__ sq_slots;       // contrib slot each shadow ray guards
+  // Per camera sample `rad_slots` float4 radiance terms, frame-global index (sample0 + idx):
+  //   [0]                 Le            (only when the scene has area lights: le_slot == 1)
+  //   [le_slot + j]       f*Li*|wi.n|/pdf of light slot j (0 when nothing is reflected)
+  // The any-hit kernel zeroes a term whose shadow ray is occluded; the film kernel folds them.
+  float4* __restrict__ rad;
+  pbrtb200_ray32* __restrict__ sq_rays;  // shadow-ray queue (chunk-local)
+  uint32_t* __restrict__ sq_slots;       // rad term each shadow ray guards (frame-global index)
   uint32_t* sq_count;
+  unsigned long long* hit_total;
   uint64_t n;
+  uint64_t sample0;  // frame-global index of this chunk's first sample
+  uint32_t rad_slots, le_slot;
   int strict_flags;
 };
 
 __global__ void __launch_bounds__(128)
-k_shade(const DScene sc, const DCamera cam, const DSampler smp, const ShadeArgs a) {
+k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.n) return;
-  const float4 hraw = __ldg(reinterpret_cast<const float4*>(a.hits) + idx);
+  const bool in_range = idx < a.n;
+  float4 hraw = make_float4(__uint_as_float(PBRTB200_MISS), 0.f, 0.f, 0.f);
+  if (in_range) hraw = __ldg(reinterpret_cast<const float4*>(a.hits) + idx);
   const uint32_t prim = __float_as_uint(hraw.x);
-  if (prim == PBRTB200_MISS) return;  // miss: sum of light.le(ray) = 0 (light/mod.rs:50-52)
+  {
+    const unsigned hm = __ballot_sync(0xffffffffu, prim != PBRTB200_MISS);
+    if ((threadIdx.x & 31) == 0 && hm) atomicAdd(a.hit_total, (unsigned long long)__popc(hm));
+  }
+  if (!in_range) return;
+  float4* rad = a.rad + (a.sample0 + idx) * a.rad_slots;
+  if (prim == PBRTB200_MISS) {  // miss: sum of light.le(ray) = 0 (light/mod.rs:50-52)
+    for (uint32_t q = 0; q < a.rad_slots; ++q) rad[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   const float t_hit = hraw.y, hb1 = hraw.z, hb2 = hraw.w;
 
   // Regenerate the camera ray and its differentials (camera/mod.rs:212-271, ray.rs:107-112;
@@ -511,22 +527,14 @@ k_shade(const DScene sc, const DCamera cam, const DSampler smp, const ShadeArgs 
     const pbrtb200_light al = sc.lights[area_light];
     if (dot3(dg.nn, wo) > 0.0f) le = mk3(al.intensity[0], al.intensity[1], al.intensity[2]);
   }
-  a.Le[idx] = make_float4(le.x, le.y, le.z, 0.f);
+  if (a.le_slot) rad[0] = make_float4(le.x, le.y, le.z, 0.f);
 
-  // Light-sample floats: 2 per area-light sample, drawn from the pixel's stream after
-  // its camera-sample block, in (camera sample, light, light sample) order.
-  WordStream ws;
-  if (sc.area_sample_pairs) {
-    const uint32_t spp = (uint32_t)smp.spp;
-    const uint64_t pix = idx / spp;
-    const uint32_t i = (uint32_t)(idx - pix * spp);
-    const DPixel px = a.pixels[pix];
-    ws.init(smp.task_keys + 8u * px.task,
-            (uint64_t)px.k * smp.words_per_pixel + smp.cam_words +
-                2ull * sc.area_sample_pairs * i);
-  }
+  // Light-sample floats: 2 per area-light sample, drawn by raygen from the pixel's
+  // stream after its camera-sample block, in (camera sample, light, light sample) order.
+  const float2* lu = a.lightu ? a.lightu + (a.sample0 + idx) * sc.area_sample_pairs : nullptr;
 
-  uint32_t slot = (uint32_t)(idx * sc.light_slots);
+  uint32_t slot = a.le_slot;
+  const uint32_t gslot0 = (uint32_t)((a.sample0 + idx) * a.rad_slots);
   for (uint32_t li = 0; li < sc.n_lights; ++li) {
     const pbrtb200_light lt = sc.lights[li];
     const int ns = lt.kind == PBRTB200_LIGHT_AREA ? lt.num_samples : 1;
@@ -561,8 +569,8 @@ k_shade(const DScene sc, const DCamera cam, const DSampler smp, const ShadeArgs 
         Li = div3s(I, len2(wi));
       } else {
         // Diffuse area light over emissive triangles (extension; pbrt-v2 semantics, A13)
-        const float u1 = ws.random_float();
-        const float u2 = ws.random_float();
+        const float2 uu = __ldg(lu++);
+        const float u1 = uu.x, u2 = uu.y;
         uint32_t k = 0;
         while (k + 1 < lt.n_tris && u1 >= a.area_tris[lt.first_tri + k].cdf_hi) ++k;
         const DAreaTri at = a.area_tris[lt.first_tri + k];
@@ -593,72 +601,16 @@ k_shade(const DScene sc, const DCamera cam, const DSampler smp, const ShadeArgs 
           shadow = true;
         }
       }
-      a.contrib[slot] = make_float4(c.x, c.y, c.z, 0.f);
+      rad[slot] = make_float4(c.x, c.y, c.z, 0.f);
       if (shadow) {
         const uint32_t q = warp_agg_inc(a.sq_count);
         float4* rq = reinterpret_cast<float4*>(a.sq_rays + q);
         rq[0] = make_float4(vis.o[0], vis.o[1], vis.o[2], vis.mint);
         rq[1] = make_float4(vis.d[0], vis.d[1], vis.d[2], vis.maxt);
-        a.sq_slots[q] = slot;
+        a.sq_slots[q] = gslot0 + slot;
       }
     }
   }
-}
-
-// L = Le + sum over lights (whitted.rs:49-66; area lights averaged over their samples, D10), then
-// Spectrum::to_xyz (spectrum.rs:37-41, 443-458) once per sample as Film::add_sample does.
-struct ResolveArgs {
-  const pbrtb200_hit16* __restrict__ hits;
-  const float4* __restrict__ Le;
-  const float4* __restrict__ contrib;
-  float4* __restrict__ xyz;  // output, indexed out_base + idx
-  uint64_t n;
-  uint64_t out_base;
-  uint32_t* nan_count;
-  unsigned long long* hit_total;     // += camera samples that hit geometry
-  unsigned long long* shadow_total;  // += this chunk's shadow-queue length
-  const uint32_t* sq_count;
-  int shaded;  // 0: no lights -> radiance is identically 0, Le/contrib were not produced
-};
-__global__ void __launch_bounds__(256)
-k_resolve(const DScene sc, const ResolveArgs a) {
-  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0 && a.shaded) atomicAdd(a.shadow_total, (unsigned long long)(*a.sq_count));
-  const bool in_range = idx < a.n;
-  const uint32_t prim = in_range ? __ldg(&a.hits[idx].prim) : PBRTB200_MISS;
-  {
-    const unsigned hits = __ballot_sync(0xffffffffu, prim != PBRTB200_MISS);
-    if ((threadIdx.x & 31) == 0 && hits) atomicAdd(a.hit_total, (unsigned long long)__popc(hits));
-  }
-  if (!in_range) return;
-  f3 L = mk3(0.f, 0.f, 0.f);
-  if (prim != PBRTB200_MISS && a.shaded) {
-    const float4 le = a.Le[idx];
-    L = mk3(le.x, le.y, le.z);
-    uint32_t slot = (uint32_t)(idx * sc.light_slots);
-    for (uint32_t li = 0; li < sc.n_lights; ++li) {
-      const int kind = sc.lights[li].kind;
-      if (kind == PBRTB200_LIGHT_AREA) {
-        const int ns = sc.lights[li].num_samples;
-        f3 Ld = mk3(0.f, 0.f, 0.f);
-        for (int s = 0; s < ns; ++s, ++slot) {
-          const float4 c = a.contrib[slot];
-          Ld = Ld + mk3(c.x, c.y, c.z);
-        }
-        L = L + div3s(Ld, (float)ns);
-      } else {
-        const float4 c = a.contrib[slot++];
-        L = L + mk3(c.x, c.y, c.z);
-      }
-    }
-  }
-  if (isnan(L.x) || isnan(L.y) || isnan(L.z)) atomicAdd(a.nan_count, 1u);  // D4
-  float4 o;
-  o.x = 0.412453f * L.x + 0.357580f * L.y + 0.180423f * L.z;
-  o.y = 0.212671f * L.x + 0.715160f * L.y + 0.072169f * L.z;
-  o.z = 0.019334f * L.x + 0.119193f * L.y + 0.950227f * L.z;
-  o.w = 0.f;
-  a.xyz[a.out_base + idx] = o;
 }
 
 // Upload-time helper: fill DAreaTri records from ordered-primitive indices (extension, A13).

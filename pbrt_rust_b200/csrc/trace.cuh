@@ -256,7 +256,7 @@ struct TraceArgs {
   float4* __restrict__ contrib;             // ANY in the render pipeline: zero slot if occluded
   const uint32_t* __restrict__ slots;       // ANY in the render pipeline: slot index per ray
   const uint32_t* __restrict__ n_dyn;       // if non-NULL the ray count is read from device memory
-  const uint64_t* __restrict__ out_index;   // optional scatter index for hits (NULL = identity)
+  unsigned long long* shadow_total;         // if non-NULL: += ray count (stats)
   uint64_t n;
   unsigned long long* counter;  // work counter, zeroed by the host before launch
   uint32_t* flags;              // bit0: stack overflow happened
@@ -271,6 +271,7 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
   float* s_t0 = sh_t0 + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const uint64_t n = a.n_dyn ? (uint64_t)(*a.n_dyn) : a.n;
+  if (a.shadow_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.shadow_total, (unsigned long long)n);
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(a.counter, 32ull);
@@ -303,7 +304,7 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
         if (a.occluded) a.occluded[idx] = occ ? 1 : 0;
         if (a.contrib && occ) a.contrib[__ldg(a.slots + idx)] = make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
-        const uint64_t oi = a.out_index ? a.out_index[idx] : idx;
+        const uint64_t oi = idx;
         float4 h;
         h.x = __uint_as_float(r.prim);
         h.y = r.t;
