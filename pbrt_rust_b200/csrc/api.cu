@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -146,21 +147,38 @@ int trace_grid(pbrtb200_ctx* ctx, const void* kernel) {
   return ctx->sm_count * per_sm;
 }
 
-// Dispatch on (ANY, SPH, MULTI, SRC).
+// Dispatch on (ANY, SPH, MULTI, SRC, MODE).  MODE = SIMT loop shape (trace.cuh); the defaults were
+// chosen from measurements (profiles/), PBRTB200_TRACE_MODE / PBRTB200_SHADOW_MODE override them.
+int env_mode(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  if (!v || !*v) return dflt;
+  const int m = std::atoi(v);
+  return (m >= 0 && m <= 2) ? m : dflt;
+}
+
 template <bool ANY, int SRC>
 int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a) {
   const DScene& sc = ctx->sc;
-#define PB_LAUNCH(SPH, MULTI)                                                              \
+  static const int mode_closest = env_mode("PBRTB200_TRACE_MODE", 1);
+  static const int mode_any = env_mode("PBRTB200_SHADOW_MODE", 0);
+  const int mode = ANY ? mode_any : mode_closest;
+#define PB_LAUNCH(SPH, MULTI, MODE)                                                        \
   {                                                                                        \
-    auto kfn = k_trace<ANY, SPH, MULTI, SRC>;                                              \
+    auto kfn = k_trace<ANY, SPH, MULTI, SRC, MODE>;                                        \
     const int grid = trace_grid(ctx, (const void*)kfn);                                    \
     kfn<<<grid, PB_TRACE_THREADS, 0, ctx->stream>>>(sc, cam, a);                           \
   }
-  if (ctx->has_spheres) {
-    if (ctx->multi_leaf) PB_LAUNCH(true, true) else PB_LAUNCH(true, false)
-  } else {
-    if (ctx->multi_leaf) PB_LAUNCH(false, true) else PB_LAUNCH(false, false)
+#define PB_LAUNCH_M(SPH, MULTI)                                                            \
+  {                                                                                        \
+    if (mode == 0) PB_LAUNCH(SPH, MULTI, 0) else if (mode == 1) PB_LAUNCH(SPH, MULTI, 1)   \
+    else PB_LAUNCH(SPH, MULTI, 2)                                                          \
   }
+  if (ctx->has_spheres) {
+    if (ctx->multi_leaf) PB_LAUNCH_M(true, true) else PB_LAUNCH_M(true, false)
+  } else {
+    if (ctx->multi_leaf) PB_LAUNCH_M(false, true) else PB_LAUNCH_M(false, false)
+  }
+#undef PB_LAUNCH_M
 #undef PB_LAUNCH
   CK(cudaGetLastError());
   return 0;

@@ -116,11 +116,36 @@ struct TraceResult {
   bool overflow;
 };
 
+// Slab test for rays whose 1/d is finite on every axis.  No product (b - o) * inv can then be NaN,
+// so the reference's "swap if ta > tb" (bbox.rs:194-196) is exactly (min(ta,tb), max(ta,tb)):
+// two FMNMX per axis instead of FSETP + 2 FSEL, and the ALU pipe is this kernel's busiest unit.
+PB_DEV bool slab_test_finite(float bminx, float bminy, float bminz, float bmaxx, float bmaxy,
+                             float bmaxz, f3 o, f3 inv, float mint, float maxt, float* T0) {
+  const float tax = (bminx - o.x) * inv.x, tbx = (bmaxx - o.x) * inv.x;
+  const float tay = (bminy - o.y) * inv.y, tby = (bmaxy - o.y) * inv.y;
+  const float taz = (bminz - o.z) * inv.z, tbz = (bmaxz - o.z) * inv.z;
+  const float t0 = fmaxf(fmaxf(fmaxf(fminf(tax, tbx), mint), fminf(tay, tby)), fminf(taz, tbz));
+  const float t1 = fminf(fminf(fminf(fmaxf(tax, tbx), maxt), fmaxf(tay, tby)), fmaxf(taz, tbz));
+  *T0 = t0;
+  return !(t0 > t1);
+}
+
+#define PB_DONE 0xFFFFFFFFu  // traversal finished (has the leaf bit set, so it leaves the node loop)
+
 // One ray through the pair-node BVH.  s_ref / s_t0 point at this thread's column of the shared
-// stack (stride = blockDim.x).  ANY: stop at the first accepted hit (VisibilityTester).
-template <bool ANY, bool SPH, bool MULTI>
-PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, float mint, float maxt,
-                            uint32_t* s_ref, float* s_t0, int stride) {
+// stack (stride PB_TRACE_THREADS).  ANY: stop at the first accepted hit (VisibilityTester).
+// FINITE: every component of 1/d is finite (the common case; selects the cheaper slab test).
+// MODE selects the SIMT loop shape (all three visit the same leaves in the same order):
+//   0  if-if        : each iteration a lane does one node step OR one leaf
+//   1  while-while  : lanes run node steps until every lane of the warp holds a leaf
+//   2  speculative  : like 1, but a lane that found a leaf postpones it and keeps traversing
+//                     until the warp is ready; the postponed leaf is re-validated against the live
+//                     maxt with its own box entry distance (child T0 >= ancestor T0, so this is the
+//                     reference's test-at-pop), which keeps the result bit-identical.
+template <bool ANY, bool SPH, bool MULTI, bool FINITE, int MODE>
+PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, float maxt,
+                            uint32_t* s_ref, float* s_t0) {
+  constexpr int stride = PB_TRACE_THREADS;
   TraceResult res;
   res.prim = PBRTB200_MISS;
   res.t = 0.f;
@@ -128,101 +153,160 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, float mint, float maxt
   res.b2 = 0.f;
   res.overflow = false;
   // bvh.rs:382-383
-  const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
   const bool neg0 = inv.x < 0.0f, neg1 = inv.y < 0.0f, neg2 = inv.z < 0.0f;
   uint32_t l_ref[PB_LM_STACK];
   float l_t0[PB_LM_STACK];
   int sp = 0;
-  float T0;
-  if (!slab_test(sc.root_bmin[0], sc.root_bmin[1], sc.root_bmin[2], sc.root_bmax[0],
-                 sc.root_bmax[1], sc.root_bmax[2], o, inv, mint, maxt, &T0))
+  auto box = [&](float ax, float ay, float az, float bx, float by, float bz, float* T0) {
+    return FINITE ? slab_test_finite(ax, ay, az, bx, by, bz, o, inv, mint, maxt, T0)
+                  : slab_test(ax, ay, az, bx, by, bz, o, inv, mint, maxt, T0);
+  };
+  float curT0 = 0.f;  // box entry distance of `cur` (MODE 2)
+  // pop the next stack entry that still passes the reference's box test at pop (live maxt)
+  auto pop = [&]() -> uint32_t {
+    while (sp > 0) {
+      --sp;
+      uint32_t r;
+      float t0;
+      if (sp < PB_SM_STACK) {
+        r = s_ref[sp * stride];
+        t0 = s_t0[sp * stride];
+      } else {
+        r = l_ref[sp - PB_SM_STACK];
+        t0 = l_t0[sp - PB_SM_STACK];
+      }
+      if (!(t0 > maxt)) {
+        curT0 = t0;
+        return r;
+      }
+    }
+    return PB_DONE;
+  };
+  // one inner-node step: both children's boxes, descend near / push far / pop
+  auto node_step = [&](uint32_t cur) -> uint32_t {
+    const float4* n = sc.nodes + 4ull * cur;
+    const float4 q0 = ldg4(n), q1 = ldg4(n + 1), q2 = ldg4(n + 2), q3 = ldg4(n + 3);
+    float T00, T01;
+    const bool h0 = box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &T00);
+    const bool h1 = box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &T01);
+    const uint32_t r0 = __float_as_uint(q3.x), r1 = __float_as_uint(q3.y);
+    if (h0 & h1) {
+      const uint32_t axis = __float_as_uint(q3.w);
+      // bvh.rs:409-415: dir_is_neg[axis] -> the second child is visited first
+      const bool neg = axis == 0 ? neg0 : (axis == 1 ? neg1 : neg2);
+      const uint32_t far_ref = neg ? r0 : r1;
+      const float far_t0 = neg ? T00 : T01;
+      if (sp < PB_SM_STACK) {
+        s_ref[sp * stride] = far_ref;
+        s_t0[sp * stride] = far_t0;
+      } else if (sp < PBRTB200_STACK_DEPTH) {
+        l_ref[sp - PB_SM_STACK] = far_ref;
+        l_t0[sp - PB_SM_STACK] = far_t0;
+      } else {
+        res.overflow = true;
+        return PB_DONE;
+      }
+      ++sp;
+      curT0 = neg ? T01 : T00;
+      return neg ? r1 : r0;
+    }
+    if (h0 | h1) {
+      curT0 = h0 ? T00 : T01;
+      return h0 ? r0 : r1;
+    }
+    return pop();
+  };
+  // bvh.rs:398-405: every primitive of the leaf in order; the last accepted hit wins.
+  // Returns true when an ANY-hit query is answered.
+  auto leaf = [&](uint32_t ref) -> bool {
+    const uint32_t off = ref & ~PB_LEAF_BIT;
+    const uint32_t cnt = MULTI ? (uint32_t)__ldg(&sc.leaf_count[off]) : 1u;
+    for (uint32_t i = 0; i < cnt; ++i) {
+      const uint32_t pi = off + i;
+      uint32_t pr = SPH ? __ldg(&sc.leaf_prim[pi]) : pi;
+      bool hit;
+      float t, b1, b2 = 0.f;
+      if (SPH && (pr & PB_LEAF_BIT)) {
+        hit = sphere_hit(sc.spheres + (pr & ~PB_LEAF_BIT), o, d, mint, maxt, &t, &b1);
+      } else {
+        const float4* tp = sc.tris + 3ull * pr;
+        const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+        hit = tri_hit(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), o, d, mint,
+                      maxt, &t, &b1, &b2);
+      }
+      if (hit) {
+        maxt = t;  // geometric.rs:64
+        res.prim = pi;
+        res.t = t;
+        res.b1 = b1;
+        res.b2 = b2;
+        if (ANY) return true;
+      }
+    }
+    return false;
+  };
+
+  if (!box(sc.root_bmin[0], sc.root_bmin[1], sc.root_bmin[2], sc.root_bmax[0], sc.root_bmax[1],
+           sc.root_bmax[2], &curT0))
     return res;
   uint32_t cur = sc.root_ref;
-  for (;;) {
-    bool need_pop = false;
-    if (!(cur & PB_LEAF_BIT)) {
-      const float4* n = sc.nodes + 4ull * cur;
-      const float4 q0 = ldg4(n), q1 = ldg4(n + 1), q2 = ldg4(n + 2), q3 = ldg4(n + 3);
-      float T00, T01;
-      const bool h0 = slab_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, inv, mint, maxt, &T00);
-      const bool h1 = slab_test(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, inv, mint, maxt, &T01);
-      const uint32_t r0 = __float_as_uint(q3.x), r1 = __float_as_uint(q3.y);
-      if (h0 && h1) {
-        const uint32_t axis = __float_as_uint(q3.w);
-        // bvh.rs:409-415: dir_is_neg[axis] -> second child is popped first
-        const bool neg = axis == 0 ? neg0 : (axis == 1 ? neg1 : neg2);
-        const uint32_t far_ref = neg ? r0 : r1;
-        const float far_t0 = neg ? T00 : T01;
-        if (sp < PB_SM_STACK) {
-          s_ref[sp * stride] = far_ref;
-          s_t0[sp * stride] = far_t0;
-        } else if (sp < PBRTB200_STACK_DEPTH) {
-          l_ref[sp - PB_SM_STACK] = far_ref;
-          l_t0[sp - PB_SM_STACK] = far_t0;
-        } else {
-          res.overflow = true;
-          return res;
-        }
-        ++sp;
-        cur = neg ? r1 : r0;
-      } else if (h0) {
-        cur = r0;
-      } else if (h1) {
-        cur = r1;
+  if (MODE == 0) {
+    while (cur != PB_DONE) {
+      if (!(cur & PB_LEAF_BIT)) {
+        cur = node_step(cur);
       } else {
-        need_pop = true;
+        if (leaf(cur)) return res;
+        cur = pop();
       }
-    } else {
-      // bvh.rs:398-405: test every primitive of the leaf in order; the last accepted hit wins
-      const uint32_t off = cur & ~PB_LEAF_BIT;
-      const uint32_t cnt = MULTI ? (uint32_t)__ldg(&sc.leaf_count[off]) : 1u;
-      for (uint32_t i = 0; i < cnt; ++i) {
-        const uint32_t pi = off + i;
-        uint32_t pr = SPH ? __ldg(&sc.leaf_prim[pi]) : pi;
-        bool hit;
-        float t, b1, b2 = 0.f;
-        if (SPH && (pr & PB_LEAF_BIT)) {
-          hit = sphere_hit(sc.spheres + (pr & ~PB_LEAF_BIT), o, d, mint, maxt, &t, &b1);
-        } else {
-          const float4* tp = sc.tris + 3ull * pr;
-          const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
-          hit = tri_hit(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), o, d, mint,
-                        maxt, &t, &b1, &b2);
-        }
-        if (hit) {
-          maxt = t;  // geometric.rs:64
-          res.prim = pi;
-          res.t = t;
-          res.b1 = b1;
-          res.b2 = b2;
-          if (ANY) return res;
-        }
-      }
-      need_pop = true;
     }
-    if (need_pop) {
-      bool got = false;
-      while (sp > 0) {
-        --sp;
-        uint32_t r;
-        float t0;
-        if (sp < PB_SM_STACK) {
-          r = s_ref[sp * stride];
-          t0 = s_t0[sp * stride];
+  } else if (MODE == 1) {
+    for (;;) {
+      while (!(cur & PB_LEAF_BIT)) cur = node_step(cur);
+      if (cur == PB_DONE) break;
+      if (leaf(cur)) return res;
+      cur = pop();
+    }
+  } else {
+    uint32_t pend = PB_DONE;  // postponed leaf
+    float pendT0 = 0.f;
+    while (cur != PB_DONE || pend != PB_DONE) {
+      // traverse until this lane holds a postponed leaf AND a second leaf (or is done), or until
+      // no lane of the warp is still looking for its first leaf
+      for (;;) {
+        if (cur == PB_DONE) break;
+        if (cur & PB_LEAF_BIT) {
+          if (pend != PB_DONE) break;  // already holding one: must process in order
+          pend = cur;
+          pendT0 = curT0;
+          cur = pop();  // speculative: uses the maxt from before `pend` is tested
         } else {
-          r = l_ref[sp - PB_SM_STACK];
-          t0 = l_t0[sp - PB_SM_STACK];
+          cur = node_step(cur);
         }
-        if (!(t0 > maxt)) {  // the reference's box test at pop, with the live maxt
-          cur = r;
-          got = true;
-          break;
-        }
+        if (!__any_sync(__activemask(), pend == PB_DONE && cur != PB_DONE)) break;
       }
-      if (!got) break;
+      if (pend != PB_DONE) {
+        // the reference's box test for this leaf node, now with the live maxt
+        if (!(pendT0 > maxt)) {
+          if (leaf(pend)) return res;
+        }
+        pend = PB_DONE;
+      }
+      // `cur` was chosen with a possibly stale maxt: re-validate before continuing
+      if (cur != PB_DONE && curT0 > maxt) cur = pop();
     }
   }
   return res;
+}
+
+template <bool ANY, bool SPH, bool MULTI, int MODE>
+PB_DEV TraceResult trace_ray(const DScene& sc, f3 o, f3 d, float mint, float maxt, uint32_t* s_ref,
+                             float* s_t0) {
+  const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);  // bvh.rs:382
+  const float big = fmaxf(fmaxf(fabsf(inv.x), fabsf(inv.y)), fabsf(inv.z));
+  // (NaN-propagating test: a NaN or infinite component takes the exact-compare path)
+  if (big < __int_as_float(0x7f800000) && inv.x == inv.x && inv.y == inv.y && inv.z == inv.z)
+    return traverse<ANY, SPH, MULTI, true, MODE>(sc, o, d, inv, mint, maxt, s_ref, s_t0);
+  return traverse<ANY, SPH, MULTI, false, 0>(sc, o, d, inv, mint, maxt, s_ref, s_t0);
 }
 
 // camera/mod.rs:168-195, 212-271 (Perspective arm), projective.rs:79-97, animated.rs:275-284
@@ -262,7 +346,7 @@ struct TraceArgs {
   uint32_t* flags;              // bit0: stack overflow happened
 };
 
-template <bool ANY, bool SPH, bool MULTI, int SRC>
+template <bool ANY, bool SPH, bool MULTI, int SRC, int MODE>
 __global__ void __launch_bounds__(PB_TRACE_THREADS)
 k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
   __shared__ uint32_t sh_ref[PB_SM_STACK * PB_TRACE_THREADS];
@@ -296,8 +380,7 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
         mint = 0.0f;         // ray.rs:30-38 Ray::new_with(.., start = 0)
         maxt = PB_F32_MAX;
       }
-      TraceResult r = traverse<ANY, SPH, MULTI>(sc, o, d, mint, maxt, s_ref, s_t0,
-                                                PB_TRACE_THREADS);
+      TraceResult r = trace_ray<ANY, SPH, MULTI, MODE>(sc, o, d, mint, maxt, s_ref, s_t0);
       if (r.overflow) atomicOr(a.flags, 1u);
       if (ANY) {
         const bool occ = r.prim != PBRTB200_MISS;
