@@ -384,7 +384,15 @@ struct StageTimer {
 };
 
 // Samples per wavefront chunk: bounds the chunk-local buffers (hits, Le, contrib, shadow queue).
-constexpr uint64_t kChunkSamples = 1ull << 22;
+constexpr int kChunkLog2Default = 22;
+uint64_t chunk_samples() {
+  static const int lg = [] {
+    const char* v = std::getenv("PBRTB200_CHUNK_LOG2");
+    const int x = v ? std::atoi(v) : kChunkLog2Default;
+    return (x >= 16 && x <= 30) ? x : kChunkLog2Default;
+  }();
+  return 1ull << lg;
+}
 
 }  // namespace
 
@@ -923,7 +931,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   if (ns * (uint64_t)std::max(1u, rad_slots) >= 0xFFFFFFFFull)
     FAIL(PBRTB200_EINVAL, "frame has more than 2^32 radiance terms; render it in tiles");
 
-  uint64_t chunk_pix = std::max<uint64_t>(1, kChunkSamples / (uint64_t)ds.spp);
+  uint64_t chunk_pix = std::max<uint64_t>(1, chunk_samples() / (uint64_t)ds.spp);
   chunk_pix = std::min(chunk_pix, npix);
   const uint64_t chunk_ns = chunk_pix * (uint64_t)ds.spp;
 

@@ -1,0 +1,137 @@
+"""Turns gpurun_out/*.ncu-rep + launches.csv into the tracked summaries under profiles/ and dumps
+the SASS of every kernel the bench launches (cuobjdump -sass).  Run here (no GPU needed)."""
+import csv, io, json, os, re, subprocess, sys
+from collections import Counter, defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+GP = os.path.join(ROOT, "gpurun_out")
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+os.makedirs(OUT, exist_ok=True)
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum",
+        "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__sass_average_branch_targets_threads_uniform.pct",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+
+
+def raw(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    return rows[0], rows[1], rows[2:]
+
+
+summary = {}
+lines = [f"# ncu --set full summaries ({TAG}; B200, --clock-control none)\n"]
+for name in sorted(os.listdir(GP)):
+    if not name.endswith(".ncu-rep"):
+        continue
+    hdr, units, rows = raw(os.path.join(GP, name))
+    ci = {h: i for i, h in enumerate(hdr)}
+    for r in rows:
+        k = r[ci["Kernel Name"]]
+        lines.append(f"\n## {k}\n\n| metric | value |\n|---|---|")
+        d = {}
+        for w in WANT:
+            if w in ci:
+                lines.append(f"| {w} | {r[ci[w]]} {units[ci[w]]} |")
+                d[w] = r[ci[w]]
+        stalls = [(h, float(r[i])) for h, i in ci.items() if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and r[i] not in ("", "n/a")]
+        stalls.sort(key=lambda x: -x[1])
+        lines.append("| top stalls (warps per issue) | " + ", ".join(f"{h[34:-24]} {v:.2f}" for h, v in stalls[:5]) + " |")
+        summary.setdefault(k, []).append(d)
+open(os.path.join(OUT, f"{TAG}_ncu_full.md"), "w").write("\n".join(lines) + "\n")
+
+# launch list -> per-kernel share of one frame
+lp = os.path.join(GP, "launches.csv")
+if os.path.exists(lp):
+    rows = [r for r in csv.reader(l for l in open(lp) if not l.startswith("=="))]
+    hdr = rows[0]
+    ci = {h: i for i, h in enumerate(hdr)}
+    tot = defaultdict(float)
+    cnt = Counter()
+    for r in rows[1:]:
+        if len(r) <= ci["Metric Value"]:
+            continue
+        k = re.sub(r"\(.*", "", r[ci["Kernel Name"]])
+        k = re.sub(r"^void ", "", k)
+        v = float(r[ci["Metric Value"]].replace(",", ""))
+        unit = r[ci["Metric Unit"]]
+        v *= {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "nsecond": 1e-6, "msecond": 1.0}.get(unit, 1e-3)
+        tot[k] += v
+        cnt[k] += 1
+    all_ms = sum(tot.values())
+    with open(os.path.join(OUT, f"{TAG}_launches.md"), "w") as f:
+        f.write(f"# ncu launch list ({TAG}): 2 config-3 frames, serialised, cold caches — compare SHARES\n\n")
+        f.write("| kernel | launches | total ms | share |\n|---|---|---|---|\n")
+        for k, v in sorted(tot.items(), key=lambda x: -x[1]):
+            f.write(f"| {k} | {cnt[k]} | {v:.3f} | {100 * v / all_ms:.1f} % |\n")
+    import shutil
+    shutil.copy(lp, os.path.join(OUT, f"{TAG}_launches.csv"))
+
+for j in ("bench.json", "bench_ref.json"):
+    if os.path.exists(os.path.join(GP, j)):
+        import shutil
+        shutil.copy(os.path.join(GP, j), os.path.join(OUT, f"{TAG}_{j}"))
+
+# traffic for bench.py's roofline.traffic: DRAM bytes of the closest-hit kernel per frame
+try:
+    b = json.load(open(os.path.join(GP, "bench.json")))
+    launches_per_frame = 8
+    for k, ds in summary.items():
+        if "k_trace<(bool)0" in k or "k_trace<0" in k:
+            def tob(s, u):
+                return float(s)
+            rep = os.path.join(GP, "prof_k_trace.ncu-rep")
+            hdr, units, rows = raw(rep)
+            ci = {h: i for i, h in enumerate(hdr)}
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot = 0.0
+            for r in rows:
+                if r[ci["Kernel Name"]] != k:
+                    continue
+                for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(r[ci[m]]) * scale[units[ci[m]]]
+                break
+            json.dump({"k_trace_closest_bytes_per_launch": tot,
+                       "k_trace_closest_bytes_per_frame": tot * launches_per_frame,
+                       "source": f"profiles/{TAG}_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum)"},
+                      open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+except Exception as e:
+    print("traffic:", e)
+
+# SASS listings
+sass_dir = os.path.join(OUT, "sass")
+os.makedirs(sass_dir, exist_ok=True)
+lib = os.path.join(ROOT, "pbrt_rust_b200", "libpbrtb200.so")
+txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+parts = re.split(r"\n\s*Function : ", txt)
+keep = {"k_raygen_groups": "k_raygen_groups", "k_raygen_full": "k_raygen_full", "k_shade": "k_shade",
+        "k_film": "k_film", "k_area_tri_setup": "k_area_tri_setup", "k_scatter_raster": "k_scatter_raster",
+        "_Z7k_traceILb0ELb0ELb1ELi1ELi1EE": "k_trace_closest_tri_multi_camera_whilewhile",
+        "_Z7k_traceILb1ELb0ELb1ELi0ELi0EE": "k_trace_any_tri_multi_queue_ifif",
+        "_Z7k_traceILb0ELb1ELb1ELi1ELi1EE": "k_trace_closest_spheres_multi_camera_whilewhile",
+        "_Z7k_traceILb0ELb0ELb0ELi0ELi1EE": "k_trace_closest_tri_single_buffer_whilewhile"}
+index = []
+for p in parts[1:]:
+    fn = p.split("\n", 1)[0].strip()
+    for key, out in keep.items():
+        if key in fn:
+            body = "Function : " + p
+            ops = Counter(m.group(1).split(".")[0] for m in re.finditer(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]+)", body))
+            open(os.path.join(sass_dir, out + ".sass"), "w").write(body)
+            index.append((out, fn, sum(ops.values()), ops.most_common(8)))
+with open(os.path.join(sass_dir, "README.md"), "w") as f:
+    f.write("# SASS listings (cuobjdump -sass libpbrtb200.so, sm_100a)\n\nNo tensor-core (UTC*MMA/HMMA) and no TMA "
+            "instructions appear: nothing on this path is a dense contraction; node/triangle fetches are `LDG.E.128.CONSTANT`.\n\n")
+    f.write("| listing | mangled name | SASS instructions | top opcodes |\n|---|---|---|---|\n")
+    for out, fn, n, ops in sorted(index):
+        f.write(f"| {out}.sass | `{fn}` | {n} | {', '.join(f'{o} {c}' for o, c in ops)} |\n")
+print("profiles written")
