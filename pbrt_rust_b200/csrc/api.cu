@@ -153,7 +153,7 @@ int env_mode(const char* name, int dflt) {
   const char* v = std::getenv(name);
   if (!v || !*v) return dflt;
   const int m = std::atoi(v);
-  return (m >= 0 && m <= 2) ? m : dflt;
+  return (m >= 0 && m <= 1) ? m : dflt;
 }
 
 template <bool ANY, int SRC>
@@ -170,8 +170,7 @@ int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a) {
   }
 #define PB_LAUNCH_M(SPH, MULTI)                                                            \
   {                                                                                        \
-    if (mode == 0) PB_LAUNCH(SPH, MULTI, 0) else if (mode == 1) PB_LAUNCH(SPH, MULTI, 1)   \
-    else PB_LAUNCH(SPH, MULTI, 2)                                                          \
+    if (mode == 0) PB_LAUNCH(SPH, MULTI, 0) else PB_LAUNCH(SPH, MULTI, 1)                   \
   }
   if (ctx->has_spheres) {
     if (ctx->multi_leaf) PB_LAUNCH_M(true, true) else PB_LAUNCH_M(true, false)
@@ -384,7 +383,7 @@ struct StageTimer {
 };
 
 // Samples per wavefront chunk: bounds the chunk-local buffers (hits, Le, contrib, shadow queue).
-constexpr int kChunkLog2Default = 22;
+constexpr int kChunkLog2Default = 23;  // measured best of 2^21..2^26 (profiles/r01_notes.md)
 uint64_t chunk_samples() {
   static const int lg = [] {
     const char* v = std::getenv("PBRTB200_CHUNK_LOG2");
@@ -461,7 +460,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   ctx->list_key.valid = false;
   if (s->n_nodes == 0 || !s->nodes) FAIL(PBRTB200_EINVAL, "scene has no BVH nodes");
   if (s->n_prims == 0) FAIL(PBRTB200_EINVAL, "scene has no primitives");
-  if (s->n_prims >= 0x7FFFFFFFu) FAIL(PBRTB200_EINVAL, "too many primitives");
+  if (s->n_prims > PB_LEAF_OFF_MASK) FAIL(PBRTB200_EINVAL, "too many primitives (limit 134217727)");
   if (s->n_spheres && (!s->leaf_prim || !s->spheres || !s->sphere_o2w))
     FAIL(PBRTB200_EINVAL, "spheres need leaf_prim, spheres and sphere_o2w");
   if (!s->n_spheres && s->n_tris != s->n_prims && !s->leaf_prim)
@@ -476,14 +475,14 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   for (uint32_t i = 0; i < nn; ++i)
     if (!s->nodes[i].is_leaf) pair_index[i] = n_inner++;
   std::vector<uint16_t> leaf_count(s->n_prims, 0);
-  bool multi = false;
+  bool multi = false, big_leaf = false;
   uint64_t covered = 0;
   auto child_ref = [&](uint32_t c, uint32_t* ref) -> bool {
     if (c >= nn) return false;
     const pbrtb200_node32& nd = s->nodes[c];
     if (nd.is_leaf) {
       if (nd.count == 0 || (uint64_t)nd.offset + nd.count > s->n_prims) return false;
-      *ref = PB_LEAF_BIT | nd.offset;
+      *ref = PB_LEAF_BIT | ((std::min<uint32_t>(nd.count, 16u) - 1u) << PB_LEAF_CNT_SHIFT) | nd.offset;
     } else {
       *ref = pair_index[c];
     }
@@ -497,6 +496,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
         FAIL(PBRTB200_EINVAL, "leaf node range outside the primitive list");
       leaf_count[nd.offset] = nd.count;
       if (nd.count > 1) multi = true;
+      if (nd.count >= 16) big_leaf = true;
       covered += nd.count;
       continue;
     }
@@ -555,7 +555,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   if (upload(ctx, ctx->d_tris, s->tris, s->n_tris)) return PBRTB200_ENODEV;
   const bool need_leaf_prim = s->n_spheres > 0 || (s->leaf_prim != nullptr);
   if (need_leaf_prim && upload(ctx, ctx->d_leaf_prim, s->leaf_prim, s->n_prims)) return PBRTB200_ENODEV;
-  if (multi && upload(ctx, ctx->d_leaf_count, leaf_count.data(), leaf_count.size())) return PBRTB200_ENODEV;
+  if (big_leaf && upload(ctx, ctx->d_leaf_count, leaf_count.data(), leaf_count.size())) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_spheres, s->spheres, s->n_spheres)) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_sphere_o2w, s->sphere_o2w, 12ull * s->n_spheres)) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_meshes, s->meshes, s->n_meshes)) return PBRTB200_ENODEV;
@@ -570,7 +570,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   sc.nodes = ctx->d_nodes.as<float4>();
   sc.tris = ctx->d_tris.as<float4>();
   sc.leaf_prim = need_leaf_prim ? ctx->d_leaf_prim.as<uint32_t>() : nullptr;
-  sc.leaf_count = multi ? ctx->d_leaf_count.as<uint16_t>() : nullptr;
+  sc.leaf_count = big_leaf ? ctx->d_leaf_count.as<uint16_t>() : nullptr;
   sc.spheres = ctx->d_spheres.as<pbrtb200_sphere80>();
   sc.sphere_o2w = ctx->d_sphere_o2w.as<float>();
   sc.meshes = ctx->d_meshes.as<pbrtb200_mesh>();
@@ -583,7 +583,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   sc.n_lights = s->n_lights;
   {
     const pbrtb200_node32& root = s->nodes[0];
-    sc.root_ref = root.is_leaf ? (PB_LEAF_BIT | root.offset) : 0u;
+    sc.root_ref = root.is_leaf ? (PB_LEAF_BIT | ((std::min<uint32_t>(root.count, 16u) - 1u) << PB_LEAF_CNT_SHIFT) | root.offset) : 0u;
     for (int i = 0; i < 3; ++i) {
       sc.root_bmin[i] = root.bmin[i];
       sc.root_bmax[i] = root.bmax[i];

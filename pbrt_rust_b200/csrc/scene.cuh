@@ -4,6 +4,10 @@
 #include "dmath.cuh"
 
 #define PB_LEAF_BIT 0x80000000u
+// Leaf ref = bit31 | (min(count,16)-1) << 27 | prim_offset (27 bits: up to 134 M primitives).
+// A count field of 15 means "16 or more: read leaf_count[prim_offset]".
+#define PB_LEAF_CNT_SHIFT 27
+#define PB_LEAF_OFF_MASK 0x07FFFFFFu
 #define PB_SM_STACK 24                                   // traversal-stack entries kept in smem
 #define PB_LM_STACK (PBRTB200_STACK_DEPTH - PB_SM_STACK) // deeper entries spill to local memory
 #define PB_TRACE_THREADS 128
@@ -17,7 +21,7 @@
 //   q3 = bits(ref0, ref1, unused, axis)
 // c0 is the reference's first child (node i+1), c1 its second child (second_child_offset).
 // ref: bit31 = 0 -> index of another pair node; bit31 = 1 -> leaf, low 31 bits = prim_offset into
-// the ordered primitive list (leaf sizes live in `leaf_count`, only read when some leaf holds >1).
+// the ordered primitive list plus an inline primitive count (see PB_LEAF_CNT_SHIFT).
 struct DScene {
   const float4* __restrict__ nodes;
   const float4* __restrict__ tris;            // 3 x float4 per triangle (pbrtb200_tri48)

@@ -403,7 +403,7 @@ PB_DEV uint32_t warp_agg_inc(uint32_t* ctr) {
 }
 
 #ifndef PB_SHADE_MIN_BLOCKS
-#define PB_SHADE_MIN_BLOCKS 6  // 80 registers/thread: 37 % -> 47 % occupancy, measured faster (profiles/)
+#define PB_SHADE_MIN_BLOCKS 5  // 96 registers; forcing 80 (6 blocks) spills and measured slower
 #endif
 
 struct ShadeArgs {

@@ -135,13 +135,11 @@ PB_DEV bool slab_test_finite(float bminx, float bminy, float bminz, float bmaxx,
 // One ray through the pair-node BVH.  s_ref / s_t0 point at this thread's column of the shared
 // stack (stride PB_TRACE_THREADS).  ANY: stop at the first accepted hit (VisibilityTester).
 // FINITE: every component of 1/d is finite (the common case; selects the cheaper slab test).
-// MODE selects the SIMT loop shape (all three visit the same leaves in the same order):
-//   0  if-if        : each iteration a lane does one node step OR one leaf
-//   1  while-while  : lanes run node steps until every lane of the warp holds a leaf
-//   2  speculative  : like 1, but a lane that found a leaf postpones it and keeps traversing
-//                     until the warp is ready; the postponed leaf is re-validated against the live
-//                     maxt with its own box entry distance (child T0 >= ancestor T0, so this is the
-//                     reference's test-at-pop), which keeps the result bit-identical.
+// MODE selects the SIMT loop shape (both visit the same leaves in the same order):
+//   0  if-if        : each iteration a lane does one node step OR one leaf        (best for any-hit)
+//   1  while-while  : lanes run node steps until every lane of the warp holds a leaf (best closest)
+// Measured and dropped (profiles/r01_notes.md): speculative postponed-leaf traversal (no gain) and a
+// persistent kernel with per-lane ray refill (-30..-70 %: refilled lanes lose ray coherence).
 template <bool ANY, bool SPH, bool MULTI, bool FINITE, int MODE>
 PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, float maxt,
                             uint32_t* s_ref, float* s_t0) {
@@ -161,7 +159,6 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
     return FINITE ? slab_test_finite(ax, ay, az, bx, by, bz, o, inv, mint, maxt, T0)
                   : slab_test(ax, ay, az, bx, by, bz, o, inv, mint, maxt, T0);
   };
-  float curT0 = 0.f;  // box entry distance of `cur` (MODE 2)
   // pop the next stack entry that still passes the reference's box test at pop (live maxt)
   auto pop = [&]() -> uint32_t {
     while (sp > 0) {
@@ -175,10 +172,7 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
         r = l_ref[sp - PB_SM_STACK];
         t0 = l_t0[sp - PB_SM_STACK];
       }
-      if (!(t0 > maxt)) {
-        curT0 = t0;
-        return r;
-      }
+      if (!(t0 > maxt)) return r;
     }
     return PB_DONE;
   };
@@ -207,20 +201,20 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
         return PB_DONE;
       }
       ++sp;
-      curT0 = neg ? T01 : T00;
       return neg ? r1 : r0;
     }
-    if (h0 | h1) {
-      curT0 = h0 ? T00 : T01;
-      return h0 ? r0 : r1;
-    }
+    if (h0 | h1) return h0 ? r0 : r1;
     return pop();
   };
   // bvh.rs:398-405: every primitive of the leaf in order; the last accepted hit wins.
   // Returns true when an ANY-hit query is answered.
   auto leaf = [&](uint32_t ref) -> bool {
-    const uint32_t off = ref & ~PB_LEAF_BIT;
-    const uint32_t cnt = MULTI ? (uint32_t)__ldg(&sc.leaf_count[off]) : 1u;
+    const uint32_t off = ref & PB_LEAF_OFF_MASK;
+    uint32_t cnt = 1u;
+    if (MULTI) {
+      cnt = ((ref >> PB_LEAF_CNT_SHIFT) & 0xFu) + 1u;  // 1..15 inline; 16 = look it up
+      if (cnt == 16u) cnt = (uint32_t)__ldg(&sc.leaf_count[off]);
+    }
     for (uint32_t i = 0; i < cnt; ++i) {
       const uint32_t pi = off + i;
       uint32_t pr = SPH ? __ldg(&sc.leaf_prim[pi]) : pi;
@@ -246,8 +240,9 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
     return false;
   };
 
+  float T0root;
   if (!box(sc.root_bmin[0], sc.root_bmin[1], sc.root_bmin[2], sc.root_bmax[0], sc.root_bmax[1],
-           sc.root_bmax[2], &curT0))
+           sc.root_bmax[2], &T0root))
     return res;
   uint32_t cur = sc.root_ref;
   if (MODE == 0) {
@@ -265,34 +260,6 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
       if (cur == PB_DONE) break;
       if (leaf(cur)) return res;
       cur = pop();
-    }
-  } else {
-    uint32_t pend = PB_DONE;  // postponed leaf
-    float pendT0 = 0.f;
-    while (cur != PB_DONE || pend != PB_DONE) {
-      // traverse until this lane holds a postponed leaf AND a second leaf (or is done), or until
-      // no lane of the warp is still looking for its first leaf
-      for (;;) {
-        if (cur == PB_DONE) break;
-        if (cur & PB_LEAF_BIT) {
-          if (pend != PB_DONE) break;  // already holding one: must process in order
-          pend = cur;
-          pendT0 = curT0;
-          cur = pop();  // speculative: uses the maxt from before `pend` is tested
-        } else {
-          cur = node_step(cur);
-        }
-        if (!__any_sync(__activemask(), pend == PB_DONE && cur != PB_DONE)) break;
-      }
-      if (pend != PB_DONE) {
-        // the reference's box test for this leaf node, now with the live maxt
-        if (!(pendT0 > maxt)) {
-          if (leaf(pend)) return res;
-        }
-        pend = PB_DONE;
-      }
-      // `cur` was chosen with a possibly stale maxt: re-validate before continuing
-      if (cur != PB_DONE && curT0 > maxt) cur = pop();
     }
   }
   return res;
@@ -398,3 +365,4 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
     }
   }
 }
+
