@@ -49,7 +49,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -193,14 +193,16 @@ def main():
             r.render(cfg["scene"], tiles=tiles, out=d_film)
             if world > 1:  # film gather over NVLink: owned tiles are disjoint, the rest is zero
                 dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)
+        elif world == 1:
+            r.render(cfg["scene"], tiles=tiles, out=h_film)   # C ABI with a host film buffer (D2H inside)
         else:
-            r.render(cfg["scene"], tiles=tiles, out=h_film)
-            if world > 1:
-                d_film.copy_(h_film_t, non_blocking=True)
-                dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)
-                if rank == 0:
-                    h_film_t.copy_(d_film, non_blocking=True)
-                torch.cuda.synchronize()
+            # N > 1: each rank renders its tiles into HBM, the film is gathered over NVLink, and rank
+            # 0 brings the finished frame to pinned host memory — what a user of N GPUs receives.
+            r.render(cfg["scene"], tiles=tiles, out=d_film)
+            dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                h_film_t.copy_(d_film, non_blocking=True)
+            torch.cuda.synchronize()
         return r.last_stats
 
     def timed(resident, steps, warmup):
@@ -238,6 +240,9 @@ def main():
 
     clk = ClockSampler(local)
     clk.start()
+    t_wait = time.perf_counter()
+    while clk.proc and not clk.rows and time.perf_counter() - t_wait < 3.0:
+        time.sleep(0.02)  # nvidia-smi needs a moment before its first sample
     ms, rays_per_frame, acc = timed(True, args.steps, args.warmup)
     clocks = clk.stop()
     ms_e2e, rays_e2e, _ = timed(False, args.steps, 1)
