@@ -227,3 +227,153 @@ def test_config3_full_size_properties_and_image(orc):
     rmse = float(np.sqrt(np.mean((rgb - rgb_ref) ** 2)))
     rel = np.abs(rgb - rgb_ref) / np.maximum(np.abs(rgb_ref), 1e-3)
     assert rmse <= 1e-5 and (rel.max(axis=-1) <= 1e-4).mean() >= 0.999
+
+
+# ---- feature coverage of the §8(a) rows beyond the headline configs -------------------------------
+def _grid_mesh(n=24, normals=False, tangents=False, uvs=False, xf=None, ro=False):
+    xs = np.linspace(-3, 3, n + 1)
+    X, Z = np.meshgrid(xs, xs, indexing="ij")
+    Y = 0.4 * np.sin(1.3 * X) * np.cos(0.9 * Z)
+    P = np.stack([X, Y, Z], -1).reshape(-1, 3).astype(np.float32)
+    a = (np.arange(n)[:, None] * (n + 1) + np.arange(n)[None, :]).astype(np.uint32)
+    b, c, d = a + (n + 1), a + 1, a + (n + 1) + 1
+    vi = np.stack([np.stack([a, c, b], -1), np.stack([b, c, d], -1)], axis=2).reshape(-1)
+    N = S = UV = None
+    if normals:
+        dy_dx = 0.4 * 1.3 * np.cos(1.3 * X) * np.cos(0.9 * Z)
+        dy_dz = -0.4 * 0.9 * np.sin(1.3 * X) * np.sin(0.9 * Z)
+        N = np.stack([-dy_dx, np.ones_like(X), -dy_dz], -1).reshape(-1, 3).astype(np.float32)
+    if tangents:
+        S = np.stack([np.ones_like(X), 0.4 * 1.3 * np.cos(1.3 * X) * np.cos(0.9 * Z), np.zeros_like(X)], -1)
+        S = S.reshape(-1, 3).astype(np.float32)
+    if uvs:
+        UV = np.stack([(X + 3) / 6, (Z + 3) / 6], -1).reshape(-1, 2).astype(np.float32)
+    xf = xf or pb.Transform.new()
+    return pb.Shape.triangle_mesh(xf, xf.inverse(), ro, vi, P, N, S, UV)
+
+
+def _small_setup(scene, xres=96, yres=64, xs=2, ys=2, lensr=0.0, focald=1e6, sampler="stratified", filt=None):
+    c2w = pb.Transform.look_at((0, 5, -7), (0, 0, 0), (0, 1, 0)).inverse()
+    return scenes._setup(scene, c2w, 50.0, xres, yres, xs, ys, True, sampler=sampler, lensr=lensr, focald=focald,
+                         filt=filt)
+
+
+@pytest.mark.parametrize("normals,tangents,uvs", [(True, False, False), (True, True, True), (False, True, True),
+                                                  (False, False, True)])
+def test_shading_normals_tangents_uvs(orc, normals, tangents, uvs):
+    """Triangle::get_shading_geometry (mesh.rs:105-193) + get_uvs (mesh.rs:74-87)."""
+    tex = pb.Texture.checkerboard(pb.UVMapping2D(8, 8, 0.1, 0.2), pb.Texture.constant((0.9, 0.3, 0.2)),
+                                  pb.Texture.constant(0.2), True)
+    mat = pb.Material.plastic(tex, pb.Texture.constant(0.3), pb.Texture.constant(0.05))
+    prims = [pb.Primitive.geometric(_grid_mesh(normals=normals, tangents=tangents, uvs=uvs), mat)]
+    lights = [pb.Light.point(pb.Transform.translate((2.0, 6.0, -3.0)), 40.0),
+              pb.Light.spot(pb.Transform.look_at((-3, 6, 0), (0, 0, 0), (0, 0, 1)).inverse(), (30.0, 35.0, 50.0), 35.0, 25.0)]
+    cfg = _small_setup(pb.Scene.new_with(pb.Primitive.bvh(prims, 4, "sah"), lights))
+    _image_check(cfg, orc, rel_tol=2e-4, frac=0.995, rmse_tol=2e-5)    # powf/sinf ulp differences (Blinn)
+
+
+def test_flipped_orientation_and_negative_scale(orc):
+    """reverse_orientation ^ transform_swaps_handedness (diff_geom.rs:55-60, shape/mod.rs:45)."""
+    mat = pb.Material.matte(pb.Texture.constant(0.6), pb.Texture.constant(0.0))
+    xf = pb.Transform.scale(-1.0, 1.0, 1.0)
+    prims = [pb.Primitive.geometric(_grid_mesh(xf=xf, ro=False), mat),
+             pb.Primitive.geometric(_grid_mesh(n=6, xf=pb.Transform.translate((0, 1.5, 0)) * pb.Transform.scale(0.3, 0.3, 0.3), ro=True), mat)]
+    lights = [pb.Light.point(pb.Transform.translate((0.0, 7.0, -2.0)), 60.0)]
+    _image_check(_small_setup(pb.Scene.new_with(pb.Primitive.bvh(prims, 1, "middle"), lights)), orc)
+
+
+def test_partial_spheres_and_transforms(orc):
+    """Sphere z/phi clipping (sphere.rs:73-105) under rotation + non-uniform scale."""
+    mat = pb.Material.matte(pb.Texture.uv(pb.UVMapping2D(3, 3, 0, 0)), pb.Texture.constant(30.0))
+    prims = []
+    k = 0
+    for x in (-2.5, 0.0, 2.5):
+        for z in (-1.5, 1.5):
+            t = pb.Transform.translate((x, 1.0, z)) * pb.Transform.rotate_x(20.0 * k) * pb.Transform.rotate_z(35.0 * k) \
+                * pb.Transform.scale(1.0, 0.7 + 0.1 * k, 1.2)
+            prims.append(pb.Primitive.geometric(
+                pb.Shape.sphere(t, t.inverse(), k % 2 == 1, 1.0, -0.6 + 0.1 * k, 0.9, 200.0 + 30 * k), mat))
+            k += 1
+    prims.append(pb.Primitive.geometric(_grid_mesh(n=8), pb.Material.matte(pb.Texture.constant(0.5), pb.Texture.constant(0.0))))
+    lights = [pb.Light.point(pb.Transform.translate((0.0, 8.0, -4.0)), 90.0)]
+    cfg = _small_setup(pb.Scene.new_with(pb.Primitive.bvh(prims, 2, "equal"), lights), xres=128, yres=96)
+    r = _renderer(cfg)
+    hits, _, _ = r.primary_hits(cfg["scene"])
+    osc = orc.OracleScene(cfg["scene"])
+    ref = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, primary_only=True), want_hits=True)
+    # documented float-edge case: CUDA vs glibc atan2f differ by ulps exactly at a phi_max clipping edge
+    assert np.mean(hits["prim"] == ref["hit_ids"]) >= 0.9999
+    _image_check(cfg, orc, rel_tol=1e-3, frac=0.995, rmse_tol=1e-4)
+
+
+def test_depth_of_field_and_ld_sampler(orc):
+    """handle_dof (projective.rs:79-97) needs the shuffled lens samples; LD sampler on device."""
+    cfg3 = scenes.config3(nx=40, nz=20, xres=64, yres=40, xs=2, ys=2)
+    for sampler in ("stratified", "ld"):
+        cfg = _small_setup(cfg3["scene"], xres=64, yres=40, lensr=0.15, focald=9.0, sampler=sampler)
+        _image_check(cfg, orc)
+        r = _renderer(cfg)
+        hits, smp, rays = r.primary_hits(cfg["scene"], want_samples=True, want_rays=True)
+        ocfg = orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8)
+        se = orc.layout(ocfg)["sample_ext"]
+        # the scene has one area light with one sample: 1 light-sample pair per camera sample (D11)
+        cs, orays, _, _ = orc.camera_samples(ocfg, 1, se[0], se[1], se[2], se[3], 4)
+        assert np.array_equal(smp.view(np.uint32), cs.view(np.uint32))
+        assert np.array_equal(rays.view(np.uint32), orays.view(np.uint32))
+        assert np.abs(rays[:, 0:3] - rays[0, 0:3]).max() > 0      # origins really differ (lens)
+
+
+@pytest.mark.parametrize("filt", [pb.Filter.triangle(1.5, 2.0), pb.Filter.mitchell(2.0, 2.0, 1 / 3, 1 / 3),
+                                  pb.Filter.lanczos(3.0, 3.0, 3.0)])
+def test_other_filters(orc, filt):
+    cfg = scenes.config1(xres=64, yres=48, filt=filt)
+    _image_check(cfg, orc, rel_tol=1e-4, frac=0.999, rmse_tol=1e-5)
+
+
+def test_multiple_area_lights_and_samples(orc):
+    cfg = scenes.config3(nx=60, nz=30, xres=96, yres=54, xs=2, ys=2, n_lights=3, light_samples=3)
+    r, film, ref = _image_check(cfg, orc)
+    assert r.last_stats["shadow_rays"] > r.last_stats["camera_hits"]      # several rays per hit
+
+
+def test_nan_radiance_is_an_error_not_a_silent_image(orc):
+    """sampler_renderer.rs:105 (intent): a NaN radiance fails the render."""
+    mat = pb.Material.matte(pb.Texture.constant(float("nan")), pb.Texture.constant(0.0))
+    prims = [pb.Primitive.geometric(_grid_mesh(n=4), mat)]
+    cfg = _small_setup(pb.Scene.new_with(pb.Primitive.bvh(prims, 1, "sah"),
+                                         [pb.Light.point(pb.Transform.translate((0, 5, 0)), 10.0)]), xres=32, yres=24)
+    with pytest.raises(pb.PbrtError) as e:
+        _renderer(cfg).render(cfg["scene"])
+    assert e.value.code == -3 and "Invalid radiance value" in str(e.value)
+    osc = orc.OracleScene(cfg["scene"])
+    with pytest.raises(orc.OracleError):
+        orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8))
+
+
+def test_traversal_stack_overflow_is_reported(orc):
+    """A 'middle' split over geometrically spaced primitives peels one primitive per level: the tree
+    is > 64 deep.  The reference's Vec stack grows (bvh.rs:386); the device stack is fixed, so the
+    call must fail with ESTACK rather than truncate silently."""
+    n = 90
+    P, vi = [], []
+    for i in range(n):
+        x = 2.0 ** (-i * 0.5)
+        P += [[x, -1.0, -1.0 - 0.01 * i], [x, 1.0, -1.0 - 0.01 * i], [x * 0.999, 0.0, 1.0 + 0.01 * i]]
+        vi += [3 * i, 3 * i + 1, 3 * i + 2]
+    mesh = pb.Shape.triangle_mesh(pb.Transform.new(), pb.Transform.new(), False, vi, np.array(P, np.float32))
+    scene = pb.Scene.new_with(pb.Primitive.bvh([pb.Primitive.geometric(mesh, None)], 1, "middle"), [])
+    cfg = _small_setup(scene, xres=16, yres=16)
+    r = _renderer(cfg)
+    rays = np.zeros((64, 8), np.float32)
+    rays[:, 0] = -1.0
+    rays[:, 1] = np.linspace(-0.5, 0.5, 64)
+    rays[:, 4] = 1.0                         # +x: through every nested box, far child first
+    rays[:, 7] = np.finfo(np.float32).max
+    osc = orc.OracleScene(scene)
+    prim, tbb, cnt = osc.trace_closest(rays, counters=True)      # the oracle (growable stack) is fine
+    assert (prim != pb.MISS).all()
+    try:
+        hits = r.intersect(scene, rays)
+        assert np.array_equal(hits["prim"], prim)                # deep but within 64: results must match
+    except pb.PbrtError as e:
+        assert e.code == -4
