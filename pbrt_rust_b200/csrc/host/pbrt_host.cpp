@@ -8,6 +8,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/pbrtb200_host.h"
@@ -215,6 +216,8 @@ struct Builder {
   size_t max_prims;
   int method;  // 0 middle, 1 equal, 2 sah
   std::string* err;
+  static constexpr size_t kParallelMin = 1u << 16;  // primitives in a subtree worth a thread
+  static constexpr int kParallelDepth = 5;           // up to 2^5 concurrent subtree builders
 
   float key(size_t i, int dim) const {
     const Vec& c = centroid[idx[i]];
@@ -280,7 +283,7 @@ struct Builder {
   }
 
   // returns false on the reference's assert!(p.len() > 0) (bvh.rs:237-238)
-  bool build(size_t lo, size_t hi) {
+  bool build(size_t lo, size_t hi, int depth = 0) {
     Box bbox;
     for (size_t i = lo; i < hi; ++i) bbox.grow(bounds[idx[i]]);
     const size_t n = hi - lo;
@@ -359,9 +362,38 @@ struct Builder {
     }
     const size_t me = out.size();
     out.push_back(pbrtb200_node32{});
-    if (!build(lo, mid)) return false;
-    const uint32_t second = (uint32_t)out.size();
-    if (!build(mid, hi)) return false;
+    uint32_t second;
+    if (n >= kParallelMin && depth < kParallelDepth) {
+      // Large subtrees: build the two children concurrently, each into its own node vector
+      // (inner-node child indices are relative to that vector), then splice them in depth-first
+      // order.  The ranges of `idx` are disjoint, so the result is the sequential builder's tree.
+      std::vector<pbrtb200_node32> lv, rv;
+      std::string lerr, rerr;
+      Builder lb{bounds, centroid, idx, {}, lv, max_prims, method, &lerr};
+      Builder rb{bounds, centroid, idx, {}, rv, max_prims, method, &rerr};
+      bool lok = false, rok = false;
+      std::thread th([&] { lok = lb.build(lo, mid, depth + 1); });
+      rok = rb.build(mid, hi, depth + 1);
+      th.join();
+      if (!lok || !rok || !lerr.empty() || !rerr.empty()) {
+        *err = !lerr.empty() ? lerr : rerr;
+        return false;
+      }
+      auto splice = [&](const std::vector<pbrtb200_node32>& v) {
+        const uint32_t base = (uint32_t)out.size();
+        for (pbrtb200_node32 nd : v) {
+          if (!nd.is_leaf) nd.offset += base;
+          out.push_back(nd);
+        }
+        return base;
+      };
+      splice(lv);
+      second = splice(rv);
+    } else {
+      if (!build(lo, mid, depth + 1)) return false;
+      second = (uint32_t)out.size();
+      if (!build(mid, hi, depth + 1)) return false;
+    }
     // bvh.rs:244-245: bounds = left.bounds U right.bounds
     const pbrtb200_node32 &l = out[me + 1], &r = out[second];
     pbrtb200_node32& nd = out[me];

@@ -445,6 +445,13 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
     return;
   }
   const float t_hit = hraw.y, hb1 = hraw.z, hb2 = hraw.w;
+  // The triangle record is the second link of a dependent load chain (hit -> triangle -> mesh ->
+  // material -> texture); start fetching it now so it overlaps the camera-ray arithmetic below.
+  if (!sc.leaf_prim) {
+    const char* tp = reinterpret_cast<const char*>(sc.tris + 3ull * prim);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(tp));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + 32));
+  }
 
   // Regenerate the camera ray and its differentials (camera/mod.rs:212-271, ray.rs:107-112;
   // D15: the differential origins/directions stay in camera space).
