@@ -61,8 +61,7 @@ if world > 1:
     e = cfg["sampler"].ext
     frame_cam = (e[1] - e[0]) * (e[3] - e[2]) * cfg["sampler"].samples_per_pixel()
     rays = (float(s[0]) + float(s[1])) * frame_cam / float(s[0]); ms = float(m[2])
-info.update(ms_per_frame=ms, rays_per_frame=rays, mrays_per_s=rays / ms / 1e3, device_stage_ms={k: v for k, v in stats.items() if k.startswith("ms_")},
-            gpu_mem_gb=torch.cuda.max_memory_allocated() / 1e9)
+info.update(ms_per_frame=ms, rays_per_frame=rays, mrays_per_s=rays / ms / 1e3, device_stage_ms={k: v for k, v in stats.items() if k.startswith("ms_")})
 if rank == 0 and not args.no_oracle:
     from oracle import orc
     t0 = time.perf_counter(); osc = orc.OracleScene(cfg["scene"]); info["oracle_bvh_build_s"] = time.perf_counter() - t0
