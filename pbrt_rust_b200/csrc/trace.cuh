@@ -159,20 +159,22 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
     return FINITE ? slab_test_finite(ax, ay, az, bx, by, bz, o, inv, mint, maxt, T0)
                   : slab_test(ax, ay, az, bx, by, bz, o, inv, mint, maxt, T0);
   };
-  // pop the next stack entry that still passes the reference's box test at pop (live maxt)
+  // pop the next stack entry that still passes the reference's box test at pop (live maxt).
+  // ANY: an any-hit query returns at its first accepted hit, so maxt never shrinks while entries
+  // are on the stack; every pushed entry passed with this very maxt and T0 need not be kept.
   auto pop = [&]() -> uint32_t {
     while (sp > 0) {
       --sp;
       uint32_t r;
-      float t0;
+      float t0 = 0.f;
       if (sp < PB_SM_STACK) {
         r = s_ref[sp * stride];
-        t0 = s_t0[sp * stride];
+        if (!ANY) t0 = s_t0[sp * stride];
       } else {
         r = l_ref[sp - PB_SM_STACK];
-        t0 = l_t0[sp - PB_SM_STACK];
+        if (!ANY) t0 = l_t0[sp - PB_SM_STACK];
       }
-      if (!(t0 > maxt)) return r;
+      if (ANY || !(t0 > maxt)) return r;
     }
     return PB_DONE;
   };
@@ -192,10 +194,10 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
       const float far_t0 = neg ? T00 : T01;
       if (sp < PB_SM_STACK) {
         s_ref[sp * stride] = far_ref;
-        s_t0[sp * stride] = far_t0;
+        if (!ANY) s_t0[sp * stride] = far_t0;
       } else if (sp < PBRTB200_STACK_DEPTH) {
         l_ref[sp - PB_SM_STACK] = far_ref;
-        l_t0[sp - PB_SM_STACK] = far_t0;
+        if (!ANY) l_t0[sp - PB_SM_STACK] = far_t0;
       } else {
         res.overflow = true;
         return PB_DONE;
@@ -317,9 +319,9 @@ template <bool ANY, bool SPH, bool MULTI, int SRC, int MODE>
 __global__ void __launch_bounds__(PB_TRACE_THREADS)
 k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
   __shared__ uint32_t sh_ref[PB_SM_STACK * PB_TRACE_THREADS];
-  __shared__ float sh_t0[PB_SM_STACK * PB_TRACE_THREADS];
+  __shared__ float sh_t0[ANY ? 1 : PB_SM_STACK * PB_TRACE_THREADS];  // any-hit keeps no T0
   uint32_t* s_ref = sh_ref + threadIdx.x;
-  float* s_t0 = sh_t0 + threadIdx.x;
+  float* s_t0 = ANY ? sh_t0 : sh_t0 + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const uint64_t n = a.n_dyn ? (uint64_t)(*a.n_dyn) : a.n;
   if (a.shadow_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.shadow_total, (unsigned long long)n);
