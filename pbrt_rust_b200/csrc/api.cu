@@ -170,7 +170,7 @@ int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a) {
   }
 #define PB_LAUNCH_M(SPH, MULTI)                                                            \
   {                                                                                        \
-    if (mode == 0) PB_LAUNCH(SPH, MULTI, 0) else PB_LAUNCH(SPH, MULTI, 1)                   \
+    if (mode == 0) PB_LAUNCH(SPH, MULTI, 0) else PB_LAUNCH(SPH, MULTI, 1)              \
   }
   if (ctx->has_spheres) {
     if (ctx->multi_leaf) PB_LAUNCH_M(true, true) else PB_LAUNCH_M(true, false)

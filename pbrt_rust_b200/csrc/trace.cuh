@@ -139,7 +139,8 @@ PB_DEV bool slab_test_finite(float bminx, float bminy, float bminz, float bmaxx,
 //   0  if-if        : each iteration a lane does one node step OR one leaf        (best for any-hit)
 //   1  while-while  : lanes run node steps until every lane of the warp holds a leaf (best closest)
 // Measured and dropped (profiles/r01_notes.md): speculative postponed-leaf traversal (no gain) and a
-// persistent kernel with per-lane ray refill (-30..-70 %: refilled lanes lose ray coherence).
+// persistent kernel with per-lane ray refill (-30..-70 %: refilled lanes lose ray coherence), and a
+// warp-cooperative any-hit kernel with subtree stealing between lanes (-18 %).
 template <bool ANY, bool SPH, bool MULTI, bool FINITE, int MODE>
 PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, float maxt,
                             uint32_t* s_ref, float* s_t0) {
@@ -367,4 +368,5 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
     }
   }
 }
+
 
