@@ -78,7 +78,7 @@ struct pbrtb200_ctx {
   DScene sc{};
   std::vector<pbrtb200_light> h_lights;
   DevBuf d_nodes, d_tris, d_leaf_prim, d_leaf_count, d_spheres, d_sphere_o2w, d_meshes, d_tri_uv,
-      d_tri_n, d_tri_s, d_materials, d_textures, d_lights, d_area_tris;
+      d_tri_n, d_tri_s, d_materials, d_mat_flags, d_textures, d_lights, d_area_tris;
   // per-frame work buffers (grow-only)
   DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_lightu, d_edge, d_rad, d_hits,
       d_sq_rays, d_sq_slots, d_film, d_rects, d_rect_prefix, d_ctrl, d_rays_in, d_occ, d_out_a,
@@ -157,8 +157,16 @@ int env_mode(const char* name, int dflt) {
 }
 
 template <bool ANY, int SRC>
-int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a) {
+int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a_in) {
   const DScene& sc = ctx->sc;
+  // 32-ray packets a warp claims per work-counter atomic (same-address atomics retire at ~0.66 ns)
+  static const int batch = [] {
+    const char* v = std::getenv("PBRTB200_TRACE_BATCH");
+    const int b = v && *v ? std::atoi(v) : 1;
+    return b >= 1 && b <= 64 ? b : 1;
+  }();
+  TraceArgs a = a_in;
+  a.batch = (uint32_t)batch;
   static const int mode_closest = env_mode("PBRTB200_TRACE_MODE", 1);
   static const int mode_any = env_mode("PBRTB200_SHADOW_MODE", 0);
   const int mode = ANY ? mode_any : mode_closest;
@@ -564,6 +572,17 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   if (s->tri_s && upload(ctx, ctx->d_tri_s, s->tri_s, 9ull * s->n_attr)) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_materials, s->materials, s->n_materials)) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_textures, s->textures, s->n_textures)) return PBRTB200_ENODEV;
+  std::vector<uint8_t> mat_flags(std::max<uint32_t>(1u, s->n_materials), 0);
+  for (uint32_t i = 0; i < s->n_materials; ++i) {
+    const pbrtb200_material& m = s->materials[i];
+    auto varying = [&](int id) { return s->textures[id].kind != PBRTB200_TEX_CONSTANT; };
+    bool v = varying(m.kd);
+    if (m.kind == PBRTB200_MAT_MATTE) v = v || varying(m.sigma);
+    if (m.kind == PBRTB200_MAT_PLASTIC) v = v || varying(m.ks) || varying(m.roughness);
+    mat_flags[i] = v ? 1 : 0;
+  }
+  if (upload(ctx, ctx->d_mat_flags, mat_flags.data(), mat_flags.size())) return PBRTB200_ENODEV;
+  CK(cudaStreamSynchronize(ctx->stream));  // mat_flags is a local
 
   DScene& sc = ctx->sc;
   std::memset(&sc, 0, sizeof sc);
@@ -578,6 +597,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   sc.tri_n = s->tri_n ? ctx->d_tri_n.as<float>() : nullptr;
   sc.tri_s = s->tri_s ? ctx->d_tri_s.as<float>() : nullptr;
   sc.materials = ctx->d_materials.as<pbrtb200_material>();
+  sc.mat_flags = ctx->d_mat_flags.as<uint8_t>();
   sc.textures = ctx->d_textures.as<pbrtb200_texture>();
   sc.n_prims = s->n_prims;
   sc.n_lights = s->n_lights;
@@ -1002,7 +1022,19 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       sa.rad_slots = rad_slots;
       sa.le_slot = le_slot;
       sa.strict_flags = integ->strict_flags;
-      k_shade<<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
+      {
+        static const int occ = [] {
+          const char* v = std::getenv("PBRTB200_SHADE_OCC");
+          return v ? std::atoi(v) : PB_SHADE_MIN_BLOCKS;
+        }();
+        const unsigned grid = (unsigned)((cn + 127) / 128);
+        if (occ >= 8)
+          k_shade<8><<<grid, 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
+        else if (occ >= 6)
+          k_shade<6><<<grid, 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
+        else
+          k_shade<5><<<grid, 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
+      }
       CK(cudaGetLastError());
       size_t e3 = tm.mark();
       CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));

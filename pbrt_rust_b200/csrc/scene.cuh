@@ -34,6 +34,7 @@ struct DScene {
   const float* __restrict__ tri_n;
   const float* __restrict__ tri_s;
   const pbrtb200_material* __restrict__ materials;
+  const uint8_t* __restrict__ mat_flags;  // bit0: some texture of the material is not Constant
   const pbrtb200_texture* __restrict__ textures;
   const pbrtb200_light* __restrict__ lights;
   uint32_t root_ref;

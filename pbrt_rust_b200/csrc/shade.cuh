@@ -361,7 +361,7 @@ PB_DEV f3 bsdf_f(const DBSDF& bs, f3 wo_w, f3 wi_w, bool strict_flags) {  // bsd
   const f3 wi = mk3(dot3(wi_w, bs.sn), dot3(wi_w, bs.tn), dot3(wi_w, bs.nn));
   f3 f = mk3(0.f, 0.f, 0.f);
   if (bs.kind == 0) {
-    f = f + lambertian_f(bs.kd);
+    return f + lambertian_f(bs.kd);
   } else if (bs.kind == 1) {
     f = f + orennayar_f(bs.kd, bs.a, bs.b, wo, wi);
   } else {
@@ -427,23 +427,46 @@ struct ShadeArgs {
   int strict_flags;
 };
 
-__global__ void __launch_bounds__(128, PB_SHADE_MIN_BLOCKS)
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS)
 k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = idx < a.n;
   float4 hraw = make_float4(__uint_as_float(PBRTB200_MISS), 0.f, 0.f, 0.f);
-  if (in_range) hraw = __ldg(reinterpret_cast<const float4*>(a.hits) + idx);
+  if (in_range) {
+    hraw = __ldg(reinterpret_cast<const float4*>(a.hits) + idx);
+    // independent streams this thread will need later: start them now (no register cost)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.img + idx));
+    if (a.lightu) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.lightu + (a.sample0 + idx) * sc.area_sample_pairs));
+  }
   const uint32_t prim = __float_as_uint(hraw.x);
+  // Block-level bookkeeping. A same-address global atomic retires at ~0.66 ns on B200 (measured,
+  // scripts/micro/atomic_bench.cu), so one atomic per WARP for the hit count and one per warp and
+  // light slot for the shadow queue (2 M per config-3 frame) cost more than the shading arithmetic.
+  // Both are aggregated per block in shared memory instead: one global atomic per block.
+  __shared__ uint32_t s_hit_cnt[4];
+  __shared__ uint32_t s_warp_cnt[2][4];  // double-buffered by slot parity: two barriers per slot suffice
+  __shared__ uint32_t s_block_base[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {
     const unsigned hm = __ballot_sync(0xffffffffu, prim != PBRTB200_MISS);
-    if ((threadIdx.x & 31) == 0 && hm) atomicAdd(a.hit_total, (unsigned long long)__popc(hm));
+    if (lane == 0) s_hit_cnt[warp] = __popc(hm);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t t = s_hit_cnt[0] + s_hit_cnt[1] + s_hit_cnt[2] + s_hit_cnt[3];
+      if (t) atomicAdd(a.hit_total, (unsigned long long)t);
+    }
   }
-  if (!in_range) return;
-  float4* rad = a.rad + (a.sample0 + idx) * a.rad_slots;
-  if (prim == PBRTB200_MISS) {  // miss: sum of light.le(ray) = 0 (light/mod.rs:50-52)
+  // Every thread of the block walks the light loop below (its trip counts depend on the scene
+  // only) so the queue push can use block barriers; `alive` threads are the ones with a hit.
+  const bool alive = in_range && prim != PBRTB200_MISS;
+  float4* rad = a.rad + (a.sample0 + (in_range ? idx : 0)) * a.rad_slots;
+  if (in_range && !alive)  // miss: sum of light.le(ray) = 0 (light/mod.rs:50-52)
     for (uint32_t q = 0; q < a.rad_slots; ++q) rad[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
-  }
+  DBSDF bs;
+  f3 p = mk3(0.f, 0.f, 0.f), n = p, wo = p;
+  float ray_epsilon = 0.f;
+  if (alive) {
   const float t_hit = hraw.y, hb1 = hraw.z, hb2 = hraw.w;
   // The triangle record is the second link of a dependent load chain (hit -> triangle -> mesh ->
   // material -> texture); start fetching it now so it overlaps the camera-ray arithmetic below.
@@ -460,14 +483,20 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   if (a.lens) ln = __ldg(a.lens + idx);
   f3 o, d, p_camera;
   camera_ray(cam, im.x, im.y, ln.x, ln.y, &o, &d, &p_camera);
-  const f3 dxc = mk3(cam.dx[0], cam.dx[1], cam.dx[2]), dyc = mk3(cam.dy[0], cam.dy[1], cam.dy[2]);
-  f3 rxo = mk3(0.f, 0.f, 0.f), ryo = mk3(0.f, 0.f, 0.f);
-  f3 rxd = normalize3(p_camera + dxc), ryd = normalize3(p_camera + dyc);
-  const float s = cam.diff_scale;
-  rxo = o + (rxo - o) * s;
-  ryo = o + (ryo - o) * s;
-  rxd = d + (rxd - d) * s;
-  ryd = d + (ryd - d) * s;
+  // The screen-space differentials (dpdx, dudx, ...) feed texture mappings only; a material whose
+  // textures are all constant never reads them, so their value cannot influence the result and the
+  // ~10 IEEE divisions / square roots behind them are skipped (mat_flags bit 0, set at upload).
+  auto differentials = [&](DG& g) {
+    const f3 dxc = mk3(cam.dx[0], cam.dx[1], cam.dx[2]), dyc = mk3(cam.dy[0], cam.dy[1], cam.dy[2]);
+    f3 rxo = mk3(0.f, 0.f, 0.f), ryo = mk3(0.f, 0.f, 0.f);
+    f3 rxd = normalize3(p_camera + dxc), ryd = normalize3(p_camera + dyc);
+    const float s = cam.diff_scale;
+    rxo = o + (rxo - o) * s;
+    ryo = o + (ryo - o) * s;
+    rxd = d + (rxd - d) * s;
+    ryd = d + (ryd - d) * s;
+    dg_compute_differentials(g, rxo, ryo, rxd, ryd);
+  };
 
   // Intersection::get_bsdf
   uint32_t pr = sc.leaf_prim ? __ldg(&sc.leaf_prim[prim]) : prim;
@@ -477,26 +506,24 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   if (pr & PB_LEAF_BIT) {
     const uint32_t si = pr & ~PB_LEAF_BIT;
     const pbrtb200_sphere80 sp = sc.spheres[si];
-    dg = sphere_dg(sp, sc.sphere_o2w + 12ull * si, o, d, t_hit, hb1);
-    dg_compute_differentials(dg, rxo, ryo, rxd, ryd);
-    dgs = dg;
     material = sp.material;
+    dg = sphere_dg(sp, sc.sphere_o2w + 12ull * si, o, d, t_hit, hb1);
+    if (__ldg(&sc.mat_flags[material]) & 1u) differentials(dg);
+    dgs = dg;
   } else {
     const TriData td = load_tri(sc, pr);
     const pbrtb200_mesh m = sc.meshes[td.mesh];
-    dg = tri_dg(td, o, d, t_hit, hb1, hb2, m.flip != 0);
-    dg_compute_differentials(dg, rxo, ryo, rxd, ryd);
-    dgs = tri_shading_geometry(sc, td, m, dg);
     material = m.material;
     area_light = m.area_light;
+    dg = tri_dg(td, o, d, t_hit, hb1, hb2, m.flip != 0);
+    if (__ldg(&sc.mat_flags[material]) & 1u) differentials(dg);
+    dgs = tri_shading_geometry(sc, td, m, dg);
   }
-  const float ray_epsilon = t_hit * 5e-4f;  // mesh.rs:262, sphere.rs:180
+  ray_epsilon = t_hit * 5e-4f;  // mesh.rs:262, sphere.rs:180
 
   // Material::get_bsdf
-  DBSDF bs;
   bs.nn = dgs.nn;                      // bsdf/mod.rs:70-86
-  bs.tn = normalize3(dgs.dpdu);
-  bs.sn = cross3(bs.nn, bs.tn);
+  bs.tn = bs.sn = mk3(0.f, 0.f, 0.f);  // filled below for BxDFs that read the local frame
   bs.ng = dg.nn;
   bs.ks = mk3(0.f, 0.f, 0.f);
   bs.a = bs.b = 0.f;
@@ -527,10 +554,14 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
     if (e > 1000.0f || isnan(e)) e = 1000.0f;  // microfacet.rs:18-24
     bs.a = e;
   }
+  if (bs.kind != 0) {  // Lambertian::f ignores wo/wi (lambertian.rs:20-23): no frame needed
+    bs.tn = normalize3(dgs.dpdu);
+    bs.sn = cross3(bs.nn, bs.tn);
+  }
 
-  const f3 p = dgs.p;
-  const f3 n = dgs.nn;
-  const f3 wo = -d;
+  p = dgs.p;
+  n = dgs.nn;
+  wo = -d;
 
   // Emitted radiance at an emissive triangle (extension): L if n.w > 0.
   f3 le = mk3(0.f, 0.f, 0.f);
@@ -539,6 +570,7 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
     if (dot3(dg.nn, wo) > 0.0f) le = mk3(al.intensity[0], al.intensity[1], al.intensity[2]);
   }
   if (a.le_slot) rad[0] = make_float4(le.x, le.y, le.z, 0.f);
+  }  // alive
 
   // Light-sample floats: 2 per area-light sample, drawn by raygen from the pixel's
   // stream after its camera-sample block, in (camera sample, light, light sample) order.
@@ -550,9 +582,11 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
     const pbrtb200_light lt = sc.lights[li];
     const int ns = lt.kind == PBRTB200_LIGHT_AREA ? lt.num_samples : 1;
     for (int sidx = 0; sidx < ns; ++sidx, ++slot) {
+      pbrtb200_ray32 vis;
+      bool shadow = false;
+      if (alive) {
       f3 Li, wi;
       float pdf;
-      pbrtb200_ray32 vis;
       if (lt.kind == PBRTB200_LIGHT_POINT) {  // point.rs:28-35 (D17: wi un-normalised)
         const f3 lp = mk3(lt.pos[0], lt.pos[1], lt.pos[2]);
         wi = lp - p;
@@ -603,7 +637,6 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
         }
       }
       f3 c = mk3(0.f, 0.f, 0.f);
-      bool shadow = false;
       if (!(is_black(Li) || pdf == 0.0f)) {  // whitted.rs:55
         const f3 f = bsdf_f(bs, wo, wi, a.strict_flags != 0);
         if (!is_black(f)) {
@@ -613,8 +646,20 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
         }
       }
       rad[slot] = make_float4(c.x, c.y, c.z, 0.f);
+      }  // alive
+      // block-aggregated push: ballot per warp, one global atomic per block and slot
+      const unsigned sm = __ballot_sync(0xffffffffu, shadow);
+      const uint32_t* wc = s_warp_cnt[slot & 1u];
+      if (lane == 0) s_warp_cnt[slot & 1u][warp] = __popc(sm);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const uint32_t t = wc[0] + wc[1] + wc[2] + wc[3];
+        s_block_base[slot & 1u] = t ? atomicAdd(a.sq_count, t) : 0u;
+      }
+      __syncthreads();
       if (shadow) {
-        const uint32_t q = warp_agg_inc(a.sq_count);
+        uint32_t q = s_block_base[slot & 1u] + (uint32_t)__popc(sm & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) q += wc[w];
         float4* rq = reinterpret_cast<float4*>(a.sq_rays + q);
         rq[0] = make_float4(vis.o[0], vis.o[1], vis.o[2], vis.mint);
         rq[1] = make_float4(vis.d[0], vis.d[1], vis.d[2], vis.maxt);

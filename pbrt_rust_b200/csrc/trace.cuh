@@ -314,6 +314,7 @@ struct TraceArgs {
   uint64_t n;
   unsigned long long* counter;  // work counter, zeroed by the host before launch
   uint32_t* flags;              // bit0: stack overflow happened
+  uint32_t batch;               // 32-ray packets a warp claims per atomic (>= 1)
 };
 
 template <bool ANY, bool SPH, bool MULTI, int SRC, int MODE>
@@ -326,11 +327,13 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
   const int lane = threadIdx.x & 31;
   const uint64_t n = a.n_dyn ? (uint64_t)(*a.n_dyn) : a.n;
   if (a.shadow_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.shadow_total, (unsigned long long)n);
+  const unsigned long long claim = 32ull * a.batch;
   for (;;) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(a.counter, 32ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;  // warp-uniform exit
+    unsigned long long base0 = 0;
+    if (lane == 0) base0 = atomicAdd(a.counter, claim);
+    base0 = __shfl_sync(0xffffffffu, base0, 0);
+    if (base0 >= n) break;  // warp-uniform exit
+   for (unsigned long long base = base0; base < base0 + claim && base < n; base += 32ull) {
     const uint64_t idx = base + lane;
     if (idx < n) {
       f3 o, d;
@@ -366,6 +369,7 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
         reinterpret_cast<float4*>(a.hits)[oi] = h;
       }
     }
+   }
   }
 }
 
