@@ -72,6 +72,9 @@ struct pbrtb200_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;      // the stream all work is issued on
   cudaStream_t own_stream = nullptr;  // created by the ctx
+  cudaStream_t copy_stream = nullptr; // film bands travel to the host while later chunks render
+  std::vector<cudaEvent_t> band_events;
+  std::vector<uint32_t> rows_ready;   // per sampler row: list pixels that must be done (prefix max)
   std::string err;
   // scene
   bool has_scene = false, has_spheres = false, multi_leaf = false;
@@ -326,6 +329,17 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
           list.push_back(p);
         }
   if (list.empty()) FAIL(PBRTB200_EINVAL, "no sampler pixel to evaluate");
+  // rows_ready[r] = how many list pixels must be finished before every sample of sampler rows
+  // 0..r exists (lets k_film run on the finished top of the image while later chunks render)
+  ctx->rows_ready.assign((size_t)sh, 0u);
+  for (int yy = 0; yy < sh; ++yy) {
+    uint32_t m = yy ? ctx->rows_ready[(size_t)yy - 1] : 0u;
+    for (int xx = 0; xx < sw; ++xx) {
+      const int32_t li = index[(size_t)yy * sw + (size_t)xx];
+      if (li >= 0) m = std::max(m, (uint32_t)li + 1u);
+    }
+    ctx->rows_ready[(size_t)yy] = m;
+  }
   if (upload(ctx, ctx->d_pixels, list.data(), list.size())) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_pix_index, index.data(), index.size())) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_task_keys, keys.data(), keys.size())) return PBRTB200_ENODEV;
@@ -438,6 +452,8 @@ int pbrtb200_create(int device, pbrtb200_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail("cudaStreamCreate", e);
   ctx->stream = ctx->own_stream;
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail("cudaStreamCreate", e);
   if ((e = ctx->d_ctrl.ensure(sizeof(CtrlBlock))) != cudaSuccess) return bail("cudaMalloc", e);
   *out = ctx;
   return PBRTB200_OK;
@@ -449,6 +465,8 @@ void pbrtb200_destroy(pbrtb200_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (cudaEvent_t ev : ctx->band_events) cudaEventDestroy(ev);
   delete ctx;
 }
 
@@ -985,6 +1003,93 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   if (tiles && tiles->n_rects)  // otherwise every film pixel is written by k_film
     CK(cudaMemsetAsync(d_film, 0, film_px * sizeof(float4), ctx->stream));
 
+  // ---- film stage (launched per band, see below) ---------------------------------------------
+  DFilm df;
+  df.x_start = film->x_pixel_start;
+  df.y_start = film->y_pixel_start;
+  df.x_count = film->x_pixel_count;
+  df.y_count = film->y_pixel_count;
+  df.xw = film->filter_xw;
+  df.yw = film->filter_yw;
+  df.inv_xw = 1.0f / film->filter_xw;  // filter.rs:12-19
+  df.inv_yw = 1.0f / film->filter_yw;
+  df.sx0 = smp->x_start;
+  df.sx1 = smp->x_end;
+  df.sy0 = smp->y_start;
+  df.sy1 = smp->y_end;
+  df.spp = ds.spp;
+  DFold fd{};
+  fd.rad_slots = rad_slots;
+  fd.le_slot = le_slot;
+  fd.n_lights = ctx->sc.n_lights;
+  for (uint32_t i = 0; i < ctx->sc.n_lights; ++i) {
+    const pbrtb200_light& l = ctx->h_lights[i];
+    fd.area[i] = l.kind == PBRTB200_LIGHT_AREA ? 1 : 0;
+    fd.ns[i] = (uint16_t)(fd.area[i] ? l.num_samples : 1);
+  }
+  // Whole-film renders into host memory run k_film in bands: after each chunk the film rows whose
+  // every contributing sample exists are filtered and start their device->host copy on a second
+  // stream, so the PCIe transfer hides behind the remaining chunks.
+  static const int band_mode = [] {  // 0: one film launch + one copy; N > 0: N tail pieces
+    const char* v = std::getenv("PBRTB200_FILM_BANDS");
+    return v && *v ? std::atoi(v) : 2;
+  }();
+  const bool banded = band_mode > 0 && !out_is_device && !(tiles && tiles->n_rects);
+  struct Band {
+    uint32_t y0, y1;
+    size_t event;
+  };
+  std::vector<Band> bands;
+  uint32_t film_done = 0;  // film rows [0, film_done) are filtered
+  auto film_rows = [&](uint32_t y0, uint32_t y1) -> int {
+    size_t eF0 = tm.mark();
+    FilmArgs fa{};
+    fa.img = ctx->d_img.as<float2>();
+    fa.rad = ctx->d_rad.as<float4>();
+    fa.edge = ctx->d_edge.as<uint32_t>();
+    fa.pix_index = ctx->d_pix_index.as<int32_t>();
+    fa.rects = ctx->d_rects.as<int32_t>();
+    fa.rect_prefix = ctx->d_rect_prefix.as<uint32_t>();
+    fa.n_rects = ctx->n_rects;
+    fa.n_pixels = ctx->n_film_pixels;
+    fa.out = d_film;
+    fa.nan_count = &ctrl(ctx)->nan_count;
+    if (banded) {  // one rect = the whole film, row-major
+      fa.first = y0 * (uint32_t)film->x_pixel_count;
+      fa.count = (y1 - y0) * (uint32_t)film->x_pixel_count;
+    } else {
+      fa.first = 0;
+      fa.count = fa.n_pixels;
+    }
+    k_film<<<(fa.count + 127) / 128, 128, 0, ctx->stream>>>(df, fd, fa);
+    CK(cudaGetLastError());
+    launches += 1;
+    tm.span(eF0, tm.mark(), 4);
+    if (banded) {
+      if (bands.size() == ctx->band_events.size()) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->band_events.push_back(ev);
+      }
+      CK(cudaEventRecord(ctx->band_events[bands.size()], ctx->stream));
+      bands.push_back({y0, y1, bands.size()});
+      film_done = y1;
+    }
+    return 0;
+  };
+  // film rows [0, r) are final once `done` list pixels are finished
+  auto rows_final = [&](uint64_t done) -> uint32_t {
+    uint32_t r = film_done;
+    while (r < (uint32_t)film->y_pixel_count) {
+      const int y = film->y_pixel_start + (int)r;
+      int qy1 = (int)std::floor((float)y + 0.5f + film->filter_yw) + 1;  // k_film's gather extent
+      qy1 = std::min(qy1, smp->y_end - 1);
+      if (qy1 >= smp->y_start && (uint64_t)ctx->rows_ready[(size_t)(qy1 - smp->y_start)] > done) break;
+      ++r;
+    }
+    return r;
+  };
+
   for (uint64_t p0 = 0; p0 < npix; p0 += chunk_pix) {
     const uint64_t cp = std::min(chunk_pix, npix - p0);
     const uint64_t s0 = p0 * (uint64_t)ds.spp, cn = cp * (uint64_t)ds.spp;
@@ -1052,52 +1157,38 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       tm.span(e3, e4, 3);
       launches += 2;
     }
-  }
-  size_t eF0 = tm.mark();
-  {
-    DFilm df;
-    df.x_start = film->x_pixel_start;
-    df.y_start = film->y_pixel_start;
-    df.x_count = film->x_pixel_count;
-    df.y_count = film->y_pixel_count;
-    df.xw = film->filter_xw;
-    df.yw = film->filter_yw;
-    df.inv_xw = 1.0f / film->filter_xw;  // filter.rs:12-19
-    df.inv_yw = 1.0f / film->filter_yw;
-    df.sx0 = smp->x_start;
-    df.sx1 = smp->x_end;
-    df.sy0 = smp->y_start;
-    df.sy1 = smp->y_end;
-    df.spp = ds.spp;
-    DFold fd{};
-    fd.rad_slots = rad_slots;
-    fd.le_slot = le_slot;
-    fd.n_lights = ctx->sc.n_lights;
-    for (uint32_t i = 0; i < ctx->sc.n_lights; ++i) {
-      const pbrtb200_light& l = ctx->h_lights[i];
-      fd.area[i] = l.kind == PBRTB200_LIGHT_AREA ? 1 : 0;
-      fd.ns[i] = (uint16_t)(fd.area[i] ? l.num_samples : 1);
+    if (banded && p0 + cp < npix) {
+      const uint32_t r = rows_final(p0 + cp);
+      if (r > film_done)
+        if (int rc = film_rows(film_done, r)) return rc;
     }
-    FilmArgs fa{};
-    fa.img = ctx->d_img.as<float2>();
-    fa.rad = ctx->d_rad.as<float4>();
-    fa.edge = ctx->d_edge.as<uint32_t>();
-    fa.pix_index = ctx->d_pix_index.as<int32_t>();
-    fa.rects = ctx->d_rects.as<int32_t>();
-    fa.rect_prefix = ctx->d_rect_prefix.as<uint32_t>();
-    fa.n_rects = ctx->n_rects;
-    fa.n_pixels = ctx->n_film_pixels;
-    fa.out = d_film;
-    fa.nan_count = &ctrl(ctx)->nan_count;
-    k_film<<<(fa.n_pixels + 127) / 128, 128, 0, ctx->stream>>>(df, fd, fa);
-    CK(cudaGetLastError());
-    launches += 1;
   }
-  size_t eF1 = tm.mark();
-  tm.span(eF0, eF1, 4);
-  tm.span(eA, eF1, 5);
-  if (!out_is_device)
-    CK(cudaMemcpyAsync(out_xyzw, d_film, film_px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!banded) {
+    if (int rc = film_rows(0u, (uint32_t)film->y_pixel_count)) return rc;
+  } else {
+    // the rows left after the last chunk go out in a few pieces so that the copy of one piece
+    // overlaps the filtering of the next
+    const uint32_t H = (uint32_t)film->y_pixel_count;
+    const uint32_t step = std::max(16u, (H - film_done + (uint32_t)band_mode - 1u) / (uint32_t)band_mode);
+    while (film_done < H)
+      if (int rc = film_rows(film_done, std::min(H, film_done + step))) return rc;
+  }
+  tm.span(eA, tm.mark(), 5);
+  if (!out_is_device) {
+    if (banded) {
+      // every band: wait for its film launch on the copy stream, then move its rows to the host
+      for (const Band& b : bands) {
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->band_events[b.event], 0));
+        const size_t off = (size_t)b.y0 * (size_t)film->x_pixel_count;
+        CK(cudaMemcpyAsync(out_xyzw + 4 * off, d_film + off,
+                           (size_t)(b.y1 - b.y0) * (size_t)film->x_pixel_count * sizeof(float4),
+                           cudaMemcpyDeviceToHost, ctx->copy_stream));
+      }
+      CK(cudaStreamSynchronize(ctx->copy_stream));
+    } else {
+      CK(cudaMemcpyAsync(out_xyzw, d_film, film_px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
   CtrlBlock h;
   if (int rc = finish_flags(ctx, &h)) return rc;
   if (stats) {

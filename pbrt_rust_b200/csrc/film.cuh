@@ -41,6 +41,7 @@ struct FilmArgs {
   const uint32_t* __restrict__ rect_prefix;  // prefix sums of rect areas (n_rects + 1)
   uint32_t n_rects;
   uint32_t n_pixels;  // total pixels over all rects
+  uint32_t first, count;  // this launch covers pixel ordinals [first, first + count)
   float4* __restrict__ out;  // film, row-major over the film pixel extent
   uint32_t* nan_count;
 };
@@ -78,8 +79,9 @@ PB_DEV bool fold_radiance(const DFold& fd, const float4* __restrict__ r, float* 
 
 __global__ void __launch_bounds__(128)
 k_film(const DFilm f, const DFold fd, const FilmArgs a) {
-  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= a.n_pixels) return;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= a.count) return;
+  const uint32_t gid = a.first + tid;
   // locate the rect (few rects per GPU; binary search over the prefix sums)
   uint32_t lo = 0, hi = a.n_rects;
   while (hi - lo > 1) {

@@ -403,7 +403,7 @@ PB_DEV uint32_t warp_agg_inc(uint32_t* ctr) {
 }
 
 #ifndef PB_SHADE_MIN_BLOCKS
-#define PB_SHADE_MIN_BLOCKS 5  // 96 registers; forcing 80 (6 blocks) spills and measured slower
+#define PB_SHADE_MIN_BLOCKS 8  // 64 registers: the stage is latency-bound, occupancy wins (profiles/r01_notes.md)
 #endif
 
 struct ShadeArgs {
