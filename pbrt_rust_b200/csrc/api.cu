@@ -1127,19 +1127,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       sa.rad_slots = rad_slots;
       sa.le_slot = le_slot;
       sa.strict_flags = integ->strict_flags;
-      {
-        static const int occ = [] {
-          const char* v = std::getenv("PBRTB200_SHADE_OCC");
-          return v ? std::atoi(v) : PB_SHADE_MIN_BLOCKS;
-        }();
-        const unsigned grid = (unsigned)((cn + 127) / 128);
-        if (occ >= 8)
-          k_shade<8><<<grid, 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
-        else if (occ >= 6)
-          k_shade<6><<<grid, 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
-        else
-          k_shade<5><<<grid, 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
-      }
+      k_shade<PB_SHADE_MIN_BLOCKS><<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
       CK(cudaGetLastError());
       size_t e3 = tm.mark();
       CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));

@@ -84,7 +84,7 @@ for j in ("bench.json", "bench_ref.json"):
 # traffic for bench.py's roofline.traffic: DRAM bytes of the closest-hit kernel per frame
 try:
     b = json.load(open(os.path.join(GP, "bench.json")))
-    launches_per_frame = 8
+    launches_per_frame = max(1, round((b["gpu_launches"] / b["steps"] - 1) / 4))  # closest-hit launches = chunks per frame
     for k, ds in summary.items():
         if "k_trace<(bool)0" in k or "k_trace<0" in k:
             def tob(s, u):
@@ -125,8 +125,11 @@ for p in parts[1:]:
     for key, out in keep.items():
         if key in fn:
             body = "Function : " + p
-            ops = Counter(m.group(1).split(".")[0] for m in re.finditer(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]+)", body))
-            open(os.path.join(sass_dir, out + ".sass"), "w").write(body)
+            ops = Counter(m.group(1).split(".")[0] for m in re.finditer(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]+)", body))
+            # drop the hex encodings (second column and encoding-only lines): mnemonics are the evidence
+            lines = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", ln) for ln in body.split("\n")]
+            body_txt = "\n".join(ln for ln in lines if ln.strip())
+            open(os.path.join(sass_dir, out + ".sass"), "w").write(body_txt + "\n")
             index.append((out, fn, sum(ops.values()), ops.most_common(8)))
 with open(os.path.join(sass_dir, "README.md"), "w") as f:
     f.write("# SASS listings (cuobjdump -sass libpbrtb200.so, sm_100a)\n\nNo tensor-core (UTC*MMA/HMMA) and no TMA "
