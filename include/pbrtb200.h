@@ -248,6 +248,16 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam,
                           float* out_samples, pbrtb200_ray32* out_rays, int is_device,
                           pbrtb200_stats* stats);
 
+/* Film::write_image's pixel pipeline as intended (src/camera/film.rs:316-354 + write_img :15-33;
+ * the code as written allocates n_pix instead of 3*n_pix floats and overwrites rgb
+ * with the zero splat): per pixel  rgb = max(0, xyz_to_rgb(xyz) * (1/weight_sum)) if weight_sum
+ * != 0 (spectrum.rs:31-35), then byte = (255 * rgb^(1/2.2) + 0.5).clamp(0, 255) as u8.
+ * film_xyzw: n_pixels float4 (the layout pbrtb200_render produces).  out_rgb (3 floats per pixel)
+ * and out_rgb8 (3 bytes per pixel) may each be NULL.  *_is_device as above; with a host film the
+ * call uploads it, with host outputs only the developed image crosses PCIe (3 B/pixel).          */
+int pbrtb200_film_develop(pbrtb200_ctx* ctx, const float* film_xyzw, int film_is_device,
+                          uint64_t n_pixels, float* out_rgb, uint8_t* out_rgb8, int out_is_device);
+
 /* Per-ray traversal counters of the last trace/primary call are not kept on device; the
  * algorithmic node/primitive counts used by the roofline come from the CPU oracle.              */
 

@@ -82,6 +82,12 @@ uint32_t pbh_num_tasks(uint32_t num_cpus, uint32_t num_pixels);
 /* Film::write_image's pixel conversion as intended (film.rs:331-346):
  * rgb = max(0, xyz_to_rgb(xyz) / weight_sum) */
 void pbh_film_to_rgb(const float* xyzw, uint64_t n_pixels, float* rgb);
+/* write_img's quantisation (film.rs:21-23): (255 * p^(1/2.2) + 0.5).clamp(0,255) as u8, n values */
+void pbh_rgb_to_bytes(const float* rgb, uint64_t n, uint8_t* out);
+/* The file `img.save(filename)` leaves behind (film.rs:15-33): 8-bit RGB PNG, row-major rgb8 */
+int pbh_write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height);
+/* Linear float RGB as PFM (lossless companion; the crate's `exr` dependency is never called) */
+int pbh_write_pfm(const char* path, const float* rgb, uint32_t width, uint32_t height);
 
 #ifdef __cplusplus
 }

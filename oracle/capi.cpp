@@ -636,4 +636,14 @@ void orc_task_windows(const int32_t* ext4, uint32_t num_tasks, int32_t* windows,
     for (int i = 0; i < 8; ++i) keys[8 * t + i] = tw[t].key[i];
   }
 }
+// write_img's pixel quantisation (camera/film.rs:21-23):
+//   (255.0 * p.powf(1.0 / 2.2) + 0.5).clamp(0.0, 255.0) as u8      (`as u8` saturates, NaN -> 0)
+void orc_rgb_to_bytes(const float* rgb, uint64_t n, uint8_t* out) {
+  for (uint64_t i = 0; i < n; ++i) {
+    float v = 255.0f * std::pow(rgb[i], 1.0f / 2.2f) + 0.5f;
+    if (v < 0.0f) v = 0.0f;   // f32::clamp keeps NaN; the cast below maps it to 0
+    if (v > 255.0f) v = 255.0f;
+    out[i] = std::isnan(v) ? (uint8_t)0 : (uint8_t)v;
+  }
+}
 }  // extern "C"

@@ -6,6 +6,6 @@ device must be present to render."""
 from ._ffi import LIB_PATH, MISS, lib
 from .api import (HIT_DTYPE, AreaLight, Camera, Context, Film, Filter, GpuRenderer, HostScene, Light,
                   Material, PbrtError, PlanarMapping2D, Primitive, Sampler, Scene, Shape,
-                  SurfaceIntegrator, Texture, Transform, UVMapping2D, film_to_rgb)
+                  SurfaceIntegrator, Texture, Transform, UVMapping2D, film_to_rgb, rgb_to_bytes, write_image)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -143,6 +143,10 @@ SYMBOLS = [
     ("pbh_film_sample_extent", None, [P(Film), P(i32)]),
     ("pbh_num_tasks", u32, [u32, u32]),
     ("pbh_film_to_rgb", None, [_fp, u64, _fp]),
+    ("pbh_rgb_to_bytes", None, [_fp, u64, _vp]),
+    ("pbh_write_png", i32, [C.c_char_p, _vp, u32, u32]),
+    ("pbh_write_pfm", i32, [C.c_char_p, _fp, u32, u32]),
+    ("pbrtb200_film_develop", i32, [_vp, _vp, C.c_int, u64, _vp, _vp, C.c_int]),
 ]
 
 _lib = None

@@ -7,6 +7,7 @@ Tests and bench.py drive the product through these classes; the CPU oracle consu
 descriptions (oracle/orc.py), so both sides see identical inputs.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -544,7 +545,48 @@ class GpuRenderer:
         return occluded
 
 
+    def develop(self, film, want_rgb=False):
+        """Film::write_image's pixel pipeline on the device (film.rs:316-354 as intended, D6):
+        film (H, W, 4) host array or CUDA tensor -> (H, W, 3) uint8 [, (H, W, 3) float32 RGB]."""
+        pf, dev = _ptr(film)
+        shape = tuple(film.shape[:-1]) if len(film.shape) > 1 else (film.shape[0] // 4,)
+        n = int(np.prod(shape))
+        rgb8 = np.zeros(shape + (3,), np.uint8)
+        rgb = np.zeros(shape + (3,), np.float32) if want_rgb else None
+        rc = lib().pbrtb200_film_develop(self.ctx.h, pf, dev, n, None if rgb is None else C.c_void_p(rgb.ctypes.data),
+                                         C.c_void_p(rgb8.ctypes.data), 0)
+        self.ctx.check(rc)
+        return (rgb8, rgb) if want_rgb else rgb8
+
+
 HIT_DTYPE = np.dtype([("prim", "<u4"), ("t", "<f4"), ("b1", "<f4"), ("b2", "<f4")])
+
+
+def rgb_to_bytes(rgb):
+    """write_img's quantisation (film.rs:21-23): (255 * p^(1/2.2) + 0.5).clamp(0, 255) as u8."""
+    a = _f(rgb)
+    out = np.zeros(a.shape, np.uint8)
+    lib().pbh_rgb_to_bytes(_fp(a), a.size, C.c_void_p(out.ctypes.data))
+    return out
+
+
+def write_image(filename, film=None, rgb8=None):
+    """Film::write_image (film.rs:316-354 as intended): develop `film` (H, W, 4) on the host
+    mirror — or take an already developed (H, W, 3) uint8 image — and write an 8-bit PNG; a name
+    ending in .pfm stores the linear float RGB instead."""
+    name = os.fsencode(filename)
+    if filename.lower().endswith(".pfm"):
+        rgb = np.ascontiguousarray(film_to_rgb(film), np.float32)
+        h, w = rgb.shape[:2]
+        rc = lib().pbh_write_pfm(name, _fp(rgb), w, h)
+    else:
+        if rgb8 is None:
+            rgb8 = rgb_to_bytes(film_to_rgb(film))
+        rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+        h, w = rgb8.shape[:2]
+        rc = lib().pbh_write_png(name, C.c_void_p(rgb8.ctypes.data), w, h)
+    if rc != 0:
+        raise OSError(f"cannot write {filename} (rc={rc})")
 
 
 def film_to_rgb(xyzw):

@@ -1198,4 +1198,39 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   return PBRTB200_OK;
 }
 
+
+int pbrtb200_film_develop(pbrtb200_ctx* ctx, const float* film_xyzw, int film_is_device,
+                          uint64_t n_pixels, float* out_rgb, uint8_t* out_rgb8, int out_is_device) {
+  if (!ctx) return PBRTB200_EINVAL;
+  if (n_pixels && !film_xyzw) FAIL(PBRTB200_EINVAL, "film is NULL");
+  if (!out_rgb && !out_rgb8) FAIL(PBRTB200_EINVAL, "no output requested");
+  CK(cudaSetDevice(ctx->device));
+  if (n_pixels == 0) return PBRTB200_OK;
+  const float4* d_in = reinterpret_cast<const float4*>(film_xyzw);
+  if (!film_is_device) {
+    CK(ctx->d_film.ensure(n_pixels * sizeof(float4)));
+    CK(cudaMemcpyAsync(ctx->d_film.p, film_xyzw, n_pixels * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    d_in = ctx->d_film.as<float4>();
+  }
+  float* d_rgb = out_rgb;
+  uint8_t* d_rgb8 = out_rgb8;
+  if (!out_is_device) {
+    if (out_rgb) {
+      CK(ctx->d_out_b.ensure(n_pixels * 3 * sizeof(float)));
+      d_rgb = ctx->d_out_b.as<float>();
+    }
+    if (out_rgb8) {
+      CK(ctx->d_out_c.ensure(n_pixels * 3));
+      d_rgb8 = ctx->d_out_c.as<uint8_t>();
+    }
+  }
+  k_film_develop<<<(unsigned)((n_pixels + 255) / 256), 256, 0, ctx->stream>>>(d_in, n_pixels, d_rgb, d_rgb8);
+  CK(cudaGetLastError());
+  if (!out_is_device) {
+    if (out_rgb) CK(cudaMemcpyAsync(out_rgb, d_rgb, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_rgb8) CK(cudaMemcpyAsync(out_rgb8, d_rgb8, n_pixels * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PBRTB200_OK;
+}
 }  // extern "C"

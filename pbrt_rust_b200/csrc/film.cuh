@@ -149,3 +149,36 @@ k_film(const DFilm f, const DFold fd, const FilmArgs a) {
   a.out[(size_t)(y - f.y_start) * (size_t)f.x_count + (size_t)(x - f.x_start)] =
       make_float4(X, Y, Z, Wt);
 }
+
+// Film::write_image pixel pipeline (film.rs:331-340 as intended, write_img film.rs:21-23).
+__global__ void __launch_bounds__(256)
+k_film_develop(const float4* __restrict__ film, uint64_t n, float* __restrict__ out_rgb,
+               uint8_t* __restrict__ out_rgb8) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(film + i);
+  float r = 3.240479f * p.x - 1.37150f * p.y - 0.498535f * p.z;  // spectrum.rs:31-35
+  float g = -0.969256f * p.x + 1.875991f * p.y + 0.041556f * p.z;
+  float b = 0.055648f * p.x - 0.204043f * p.y + 1.057311f * p.z;
+  if (p.w != 0.0f) {
+    const float inv = 1.0f / p.w;
+    r = fmaxf(r * inv, 0.0f);
+    g = fmaxf(g * inv, 0.0f);
+    b = fmaxf(b * inv, 0.0f);
+  }
+  if (out_rgb) {
+    out_rgb[3 * i] = r;
+    out_rgb[3 * i + 1] = g;
+    out_rgb[3 * i + 2] = b;
+  }
+  if (out_rgb8) {
+    auto to_byte = [](float v) -> uint8_t {
+      float q = 255.0f * powf(v, 1.0f / 2.2f) + 0.5f;
+      q = q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q);
+      return isnan(q) ? (uint8_t)0 : (uint8_t)q;
+    };
+    out_rgb8[3 * i] = to_byte(r);
+    out_rgb8[3 * i + 1] = to_byte(g);
+    out_rgb8[3 * i + 2] = to_byte(b);
+  }
+}

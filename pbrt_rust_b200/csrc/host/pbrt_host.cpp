@@ -3,6 +3,8 @@
 // CUDA, never touches the CPU oracle.  Float arithmetic keeps the reference's operation order
 // (compile with -ffp-contract=off) because the BVH it builds must be the reference's tree.
 #include <algorithm>
+#include <zlib.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -995,4 +997,72 @@ void pbh_film_to_rgb(const float* xyzw, uint64_t n, float* rgb) {
   }
 }
 
+
+void pbh_rgb_to_bytes(const float* rgb, uint64_t n, uint8_t* out) {  // film.rs:21-23
+  for (uint64_t i = 0; i < n; ++i) {
+    float v = 255.0f * std::pow(rgb[i], 1.0f / 2.2f) + 0.5f;
+    v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);
+    out[i] = std::isnan(v) ? (uint8_t)0 : (uint8_t)v;  // Rust `as u8`: saturating, NaN -> 0
+  }
+}
+
+// 8-bit RGB PNG (what `image::ImageBuffer<Rgb<u8>>::save` writes for a .png name, film.rs:15-33):
+// one IDAT, filter type 0 on every scanline, zlib deflate.
+int pbh_write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height) {
+  if (!path || !rgb8 || width == 0 || height == 0) return PBRTB200_EINVAL;
+  const size_t stride = (size_t)width * 3;
+  std::vector<uint8_t> raw((stride + 1) * (size_t)height);
+  for (uint32_t y = 0; y < height; ++y) {
+    raw[(stride + 1) * y] = 0;
+    std::memcpy(&raw[(stride + 1) * y + 1], rgb8 + stride * y, stride);
+  }
+  uLongf zlen = compressBound((uLong)raw.size());
+  std::vector<uint8_t> z(zlen);
+  if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return PBRTB200_ENOMEM;
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return PBRTB200_EINVAL;
+  auto be32 = [](uint8_t* p, uint32_t v) {
+    p[0] = (uint8_t)(v >> 24);
+    p[1] = (uint8_t)(v >> 16);
+    p[2] = (uint8_t)(v >> 8);
+    p[3] = (uint8_t)v;
+  };
+  auto chunk = [&](const char type[4], const uint8_t* data, uint32_t len) {
+    uint8_t hdr[8];
+    be32(hdr, len);
+    std::memcpy(hdr + 4, type, 4);
+    std::fwrite(hdr, 1, 8, f);
+    if (len) std::fwrite(data, 1, len, f);
+    uLong c = crc32(0L, hdr + 4, 4);
+    if (len) c = crc32(c, data, len);
+    uint8_t crc[4];
+    be32(crc, (uint32_t)c);
+    std::fwrite(crc, 1, 4, f);
+  };
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  std::fwrite(sig, 1, 8, f);
+  uint8_t ihdr[13];
+  be32(ihdr, width);
+  be32(ihdr + 4, height);
+  ihdr[8] = 8;   // bit depth
+  ihdr[9] = 2;   // colour type: truecolour
+  ihdr[10] = ihdr[11] = ihdr[12] = 0;
+  chunk("IHDR", ihdr, 13);
+  chunk("IDAT", z.data(), (uint32_t)zlen);
+  chunk("IEND", nullptr, 0);
+  const bool ok = std::ferror(f) == 0;
+  return (std::fclose(f) == 0 && ok) ? PBRTB200_OK : PBRTB200_EINVAL;
+}
+
+// Linear float RGB as a little-endian PFM ("PF", bottom-to-top scanlines): the lossless companion
+// of the 8-bit file (the crate lists `exr` in Cargo.toml but never calls it).
+int pbh_write_pfm(const char* path, const float* rgb, uint32_t width, uint32_t height) {
+  if (!path || !rgb || width == 0 || height == 0) return PBRTB200_EINVAL;
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return PBRTB200_EINVAL;
+  std::fprintf(f, "PF\n%u %u\n-1.0\n", width, height);
+  for (uint32_t y = height; y-- > 0;) std::fwrite(rgb + (size_t)y * width * 3, sizeof(float), (size_t)width * 3, f);
+  const bool ok = std::ferror(f) == 0;
+  return (std::fclose(f) == 0 && ok) ? PBRTB200_OK : PBRTB200_EINVAL;
+}
 }  // extern "C"

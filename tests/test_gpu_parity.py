@@ -377,3 +377,32 @@ def test_traversal_stack_overflow_is_reported(orc):
         assert np.array_equal(hits["prim"], prim)                # deep but within 64: results must match
     except pb.PbrtError as e:
         assert e.code == -4
+
+
+def test_film_develop_matches_host_pipeline(orc):
+    """Film::write_image's pixel pipeline on the device ("next" row 3): float RGB bit-exact against
+    the oracle's to_rgb; bytes identical except where CUDA powf and glibc powf round to different
+    sides of a .5 boundary (tolerance: <= 1 LSB on <= 0.1 % of the values)."""
+    import ctypes as C
+    cfg = scenes.config3(nx=60, nz=30, xres=160, yres=96, xs=2, ys=2)
+    r = _renderer(cfg)
+    film = r.render(cfg["scene"])
+    rgb8, rgb = r.develop(film, want_rgb=True)
+    ref_rgb = pb.film_to_rgb(film)
+    assert np.array_equal(rgb.view(np.uint32), ref_rgb.view(np.uint32))
+    ref8 = np.zeros(ref_rgb.shape, np.uint8)
+    a = np.ascontiguousarray(ref_rgb)
+    orc.lib().orc_rgb_to_bytes(C.c_void_p(a.ctypes.data), C.c_uint64(a.size), C.c_void_p(ref8.ctypes.data))
+    diff = np.abs(rgb8.astype(np.int32) - ref8.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3, (diff.max(), (diff != 0).mean())
+    assert rgb8.max() > 100  # a lit image, not zeros
+    # the device-resident film gives the same bytes
+    import torch
+    d_film = torch.from_numpy(film).cuda()
+    assert np.array_equal(r.develop(d_film), rgb8)
+    # special values: zero weight keeps the raw rgb, NaN -> 0, negative -> 0
+    special = np.array([[[0.5, 0.5, 0.5, 0.0], [np.nan, 1.0, 1.0, 1.0], [-1.0, -1.0, -1.0, 1.0], [9.0, 9.0, 9.0, 1.0]]], np.float32)
+    s8 = r.develop(special)
+    h8 = pb.rgb_to_bytes(pb.film_to_rgb(special))
+    assert np.abs(s8.astype(int) - h8.astype(int)).max() <= 1
+    assert s8[0, 1].tolist() == [0, 0, 0] and s8[0, 2].tolist() == [0, 0, 0]

@@ -156,3 +156,77 @@ def test_film_to_rgb_matches_oracle(orc):
     osc = orc.OracleScene(cfg["scene"])
     ref = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8))
     assert np.array_equal(pb.film_to_rgb(ref["film"]).view(np.uint32), ref["rgb"].view(np.uint32))
+
+
+# ---- film output ("next" row 3: Film::write_image, camera/film.rs:15-33, 316-354) ------------
+
+def _oracle_bytes(orc, rgb):
+    a = np.ascontiguousarray(rgb, np.float32)
+    out = np.zeros(a.shape, np.uint8)
+    L = orc.lib()
+    L.orc_rgb_to_bytes(C.c_void_p(a.ctypes.data), C.c_uint64(a.size), C.c_void_p(out.ctypes.data))
+    return out
+
+
+def test_rgb_to_bytes_matches_oracle_and_hand_values(orc):
+    """write_img's to_byte (film.rs:21-23): known answers + the whole [0, 1.2] range against the
+    oracle restatement (same glibc powf on both sides: bit-exact)."""
+    hand = np.array([0.0, 1.0, 2.0, -1.0, np.nan, 0.5, 0.2140411], np.float32)
+    # 0 -> 0.5 -> 0; 1 -> 255.5 -> 255; 2 -> clamp 255; negative base -> NaN -> 0; NaN -> 0;
+    # 0.5^(1/2.2) = 0.72974 -> 186.58 -> 186; 0.2140411^(1/2.2) ~ 0.49626 -> 127.05 -> 127
+    assert pb.rgb_to_bytes(hand).tolist() == [0, 255, 255, 0, 0, 186, 127]
+    sweep = np.linspace(0.0, 1.2, 200001, dtype=np.float32)
+    assert np.array_equal(pb.rgb_to_bytes(sweep), _oracle_bytes(orc, sweep))
+
+
+def _decode_png(path):
+    """Minimal PNG reader (8-bit RGB, filter 0..4) — test-side check of the writer."""
+    import struct
+    import zlib
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(raw):
+        ln, ty = struct.unpack(">I4s", raw[pos:pos + 8])
+        body = raw[pos + 8:pos + 8 + ln]
+        crc, = struct.unpack(">I", raw[pos + 8 + ln:pos + 12 + ln])
+        assert crc == (zlib.crc32(ty + body) & 0xFFFFFFFF), ty
+        if ty == b"IHDR":
+            w, h, depth, ctype, comp, filt, inter = struct.unpack(">IIBBBBB", body)
+            assert (depth, ctype, comp, filt, inter) == (8, 2, 0, 0, 0)
+        elif ty == b"IDAT":
+            idat += body
+        pos += 12 + ln
+    data = zlib.decompress(idat)
+    stride = 3 * w
+    img = np.zeros((h, stride), np.uint8)
+    for y in range(h):
+        row = data[y * (stride + 1):(y + 1) * (stride + 1)]
+        assert row[0] == 0
+        img[y] = np.frombuffer(row[1:], np.uint8)
+    return img.reshape(h, w, 3)
+
+
+def test_write_image_png_round_trip(orc, tmp_path):
+    cfg = scenes.config1(xres=48, yres=20)
+    osc = orc.OracleScene(cfg["scene"])
+    ref = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8))
+    path = str(tmp_path / "frame.png")
+    pb.write_image(path, ref["film"])
+    img = _decode_png(path)
+    assert img.shape == (20, 48, 3)
+    assert np.array_equal(img, _oracle_bytes(orc, ref["rgb"]).reshape(20, 48, 3))
+    assert img.max() > 0  # the spheres are lit
+    # float companion
+    pfm = str(tmp_path / "frame.pfm")
+    pb.write_image(pfm, ref["film"])
+    raw = open(pfm, "rb").read()
+    head = b"PF\n48 20\n-1.0\n"
+    assert raw.startswith(head)
+    px = np.frombuffer(raw[len(head):], "<f4").reshape(20, 48, 3)[::-1]
+    assert np.array_equal(px.view(np.uint32), ref["rgb"].reshape(20, 48, 3).view(np.uint32))
+
+
+def test_write_image_rejects_bad_path():
+    with pytest.raises(OSError):
+        pb.write_image("/nonexistent-dir/x.png", np.ones((2, 2, 4), np.float32))
