@@ -84,6 +84,7 @@ typedef struct {
 #define PBRTB200_TEX_CONSTANT 0
 #define PBRTB200_TEX_CHECKER2D 1
 #define PBRTB200_TEX_UV 2
+#define PBRTB200_TEX_IMAGE 3   /* ImageTexture (texture/imagemap.rs:70-73): tex1 = mipmap index */
 #define PBRTB200_MAP_UV 0      /* UVMapping2D(su,sv,du,dv): map[0..3]                      */
 #define PBRTB200_MAP_PLANAR 1  /* PlanarMapping2D(vs,vt,ds,dt): map[0..2],map[3..5],map[6..7] */
 typedef struct {
@@ -94,6 +95,25 @@ typedef struct {
   int32_t tex1, tex2;  /* Checkerboard children */
   int32_t aa;          /* 0 NONE, 1 CLOSEDFORM (texture/checkerboard.rs:10-14) */
 } pbrtb200_texture;
+
+/* MIPMap (src/texture/mipmap.rs:143-151).  The pyramid (mipmap.rs:159-204: level 0 is the image
+ * resized to powers of two, level l halves level l-1 with the 2x2 box filter) lives in
+ * pbrtb200_scene.texels as RGB float4 texels, row-major per level, level l directly after level
+ * l-1; level l is max(width >> l, 1) x max(height >> l, 1).  The reference stores levels in a
+ * 32x32-blocked BlockedVec (utils/blocked_vec.rs) - a CPU cache layout that does not change any
+ * value; on the device a row-major level puts the 8 texels of a 128-byte line side by side.
+ * A float texture (TextureCache<f32>) is stored with three equal channels.                      */
+#define PBRTB200_WRAP_REPEAT 0 /* ImageWrap (texture/imagewrap.rs), same order */
+#define PBRTB200_WRAP_BLACK 1
+#define PBRTB200_WRAP_CLAMP 2
+typedef struct {
+  uint32_t width, height; /* level 0 */
+  uint32_t n_levels;
+  uint32_t do_trilinear;
+  float max_anisotropy;
+  uint32_t wrap;
+  uint64_t texel_offset; /* first texel of level 0 in pbrtb200_scene.texels */
+} pbrtb200_mipmap;
 
 #define PBRTB200_MAT_MATTE 0
 #define PBRTB200_MAT_PLASTIC 1
@@ -144,6 +164,11 @@ typedef struct {
    * light (pbrtb200_light.first_tri / n_tris), in BVH-input (refined) order.                   */
   const uint32_t* area_prims;
   uint32_t n_area_prims;
+  /* image textures: MIPMap headers + one texel pool (4 floats per texel: r, g, b, 0) */
+  const pbrtb200_mipmap* mipmaps;
+  uint32_t n_mipmaps;
+  const float* texels;
+  uint64_t n_texels;
 } pbrtb200_scene;
 
 /* ---- camera / sampler / film / integrator -------------------------------------------------- */

@@ -42,6 +42,16 @@ int pbh_texture_constant(pbh_scene* s, const float rgb[3]);
 int pbh_texture_checkerboard(pbh_scene* s, int map_kind, const float map[8], int tex1, int tex2,
                              int antialiased);
 int pbh_texture_uv(pbh_scene* s, int map_kind, const float map[8]);
+/* TextureCache::new_texture (src/texture/imagemap.rs:128-138 / 183-193) + MIPMap::new
+ * (src/texture/mipmap.rs:159-204).  rgb = what read_image returns (imagemap.rs:75-89): w*h RGB
+ * texels = byte / 255, row-major from the top-left; NULL = the file could not be read, which the
+ * reference turns into a 1x1 map of scale^gamma (:116-120).  spectrum != 0: TextureCache<Spectrum>
+ * ((s * scale).powf(gamma) per channel); 0: TextureCache<f32> ((s.y() * scale).powf(gamma)).
+ * wrap = PBRTB200_WRAP_*.  Every call builds its own MIPMap (the reference's per-file cache is a
+ * memory optimisation of its loader, not part of the evaluated function).                        */
+int pbh_texture_image(pbh_scene* s, int map_kind, const float map[8], const float* rgb, uint32_t w,
+                      uint32_t h, int spectrum, int do_trilinear, float max_aniso, int wrap,
+                      float scale, float gamma);
 /* Material::matte(kd, sigma) / Material::plastic(kd, ks, roughness) (src/material/mod.rs:88-99) */
 int pbh_material_matte(pbh_scene* s, int kd, int sigma);
 int pbh_material_plastic(pbh_scene* s, int kd, int ks, int roughness);

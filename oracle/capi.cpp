@@ -118,6 +118,18 @@ int orc_add_texture(OrcScene* s, int kind, const float* value, int map_kind, con
   s->sc.textures.t.push_back(t);
   return (int)s->sc.textures.t.size() - 1;
 }
+// TextureCache::new_texture (texture/imagemap.rs:128-138 / 183-193).  rgb = read_image's texels
+// (byte / 255, row-major) or NULL for an unreadable file (1x1 scale^gamma map, :116-120).
+int orc_add_image_texture(OrcScene* s, int map_kind, const float* map8, const float* rgb, uint32_t w,
+                          uint32_t h, int spectrum, int do_trilinear, float max_aniso, int wrap,
+                          float scale, float gamma) {
+  const float zero[3] = {0.f, 0.f, 0.f};
+  int id = orc_add_texture(s, 3, zero, map_kind, map8, 0, 0, 0);
+  s->sc.textures.mips.push_back(
+      make_image_mipmap(rgb, w, h, spectrum != 0, do_trilinear != 0, max_aniso, wrap, scale, gamma));
+  s->sc.textures.t[(size_t)id].tex1 = (int)s->sc.textures.mips.size() - 1;
+  return id;
+}
 int orc_add_material(OrcScene* s, int kind, int kd, int sigma, int ks, int roughness) {
   Material m;
   m.kind = kind;
@@ -646,4 +658,50 @@ void orc_rgb_to_bytes(const float* rgb, uint64_t n, uint8_t* out) {
     out[i] = std::isnan(v) ? (uint8_t)0 : (uint8_t)v;
   }
 }
+// ---- MIPMap known-answer hooks (texture/mipmap.rs) ----
+void* orc_mipmap_new(const float* rgb, uint32_t w, uint32_t h, int spectrum, int do_trilinear,
+                     float max_aniso, int wrap, float scale, float gamma) {
+  return new MIPMap(make_image_mipmap(rgb, w, h, spectrum != 0, do_trilinear != 0, max_aniso, wrap, scale, gamma));
+}
+void orc_mipmap_free(void* m) { delete static_cast<MIPMap*>(m); }
+uint32_t orc_mipmap_levels(void* m) { return (uint32_t)static_cast<MIPMap*>(m)->levels(); }
+void orc_mipmap_level_size(void* m, uint32_t level, uint32_t* wh) {
+  const MipLevel& l = static_cast<MIPMap*>(m)->pyramid[level];
+  wh[0] = (uint32_t)l.w;
+  wh[1] = (uint32_t)l.h;
+}
+void orc_mipmap_level(void* m, uint32_t level, float* out_rgb) {
+  const MipLevel& l = static_cast<MIPMap*>(m)->pyramid[level];
+  for (size_t i = 0; i < l.px.size(); ++i)
+    for (int c = 0; c < 3; ++c) out_rgb[3 * i + c] = l.px[i].c[c];
+}
+// n lookups: st6 = (s, t, dsdx, dtdx, dsdy, dtdy) per lookup
+void orc_mipmap_lookup(void* m, const float* st6, uint64_t n, float* out_rgb) {
+  const MIPMap* mm = static_cast<MIPMap*>(m);
+  for (uint64_t i = 0; i < n; ++i) {
+    const float* q = st6 + 6 * i;
+    RGB r = mm->lookup(q[0], q[1], q[2], q[3], q[4], q[5]);
+    for (int c = 0; c < 3; ++c) out_rgb[3 * i + c] = r.c[c];
+  }
+}
+// ImageTexture::eval through a PlanarMapping2D::new() ((1,0,0),(0,1,0),0,0) at points p with
+// dpdx/dpdy — the exact call the reference's imagemap.rs tests make.  pd9 = p, dpdx, dpdy.
+void orc_image_texture_eval_planar(void* m, const float* pd9, uint64_t n, float* out_rgb) {
+  const MIPMap* mm = static_cast<MIPMap*>(m);
+  Mapping2D mp;
+  mp.kind = 1;
+  for (uint64_t i = 0; i < n; ++i) {
+    DiffGeom dg;
+    const float* q = pd9 + 9 * i;
+    dg.p = V3(q[0], q[1], q[2]);
+    dg.dpdx = V3(q[3], q[4], q[5]);
+    dg.dpdy = V3(q[6], q[7], q[8]);
+    float o[6];
+    mp.map(dg, o);
+    RGB r = mm->lookup(o[0], o[1], o[2], o[3], o[4], o[5]);
+    for (int c = 0; c < 3; ++c) out_rgb[3 * i + c] = r.c[c];
+  }
+}
+float orc_sinc_1d(float x, float tau) { return sinc_1d(x, tau); }
+int32_t orc_modulo(int32_t a, int32_t b) { return modulo(a, b); }
 }  // extern "C"

@@ -73,8 +73,68 @@ def lib():
         L.orc_add_spot_light.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, f32, f32]
         L.orc_get_crop_window.argtypes = [u64, u64, f32, C.c_void_p]
         L.orc_film_extents.argtypes = [C.c_int, C.c_int, f32, f32, C.c_void_p, C.c_void_p, C.c_void_p]
+        i32 = C.c_int32
+        L.orc_add_image_texture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, u32, u32, C.c_int, C.c_int,
+                                            f32, C.c_int, f32, f32]
+        L.orc_mipmap_new.restype = C.c_void_p
+        L.orc_mipmap_new.argtypes = [C.c_void_p, u32, u32, C.c_int, C.c_int, f32, C.c_int, f32, f32]
+        L.orc_mipmap_free.argtypes = [C.c_void_p]
+        L.orc_mipmap_levels.restype = u32
+        L.orc_mipmap_levels.argtypes = [C.c_void_p]
+        L.orc_mipmap_level_size.argtypes = [C.c_void_p, u32, C.c_void_p]
+        L.orc_mipmap_level.argtypes = [C.c_void_p, u32, C.c_void_p]
+        L.orc_mipmap_lookup.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_void_p]
+        L.orc_image_texture_eval_planar.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_void_p]
+        L.orc_sinc_1d.restype = f32
+        L.orc_sinc_1d.argtypes = [f32, f32]
+        L.orc_modulo.restype = i32
+        L.orc_modulo.argtypes = [i32, i32]
+        L.orc_rgb_to_bytes.argtypes = [C.c_void_p, u64, C.c_void_p]
         _lib = L
     return _lib
+
+
+class OracleMIPMap:
+    """texture/mipmap.rs MIPMap built the way TextureCache::get_texture does (imagemap.rs:96-173).
+    texels: (h, w, 3) float32 = read_image's output, or None for an unreadable file."""
+
+    def __init__(self, texels, spectrum=True, do_trilinear=False, max_aniso=8.0, wrap=0, scale=1.0, gamma=1.0):
+        L = lib()
+        if texels is None:
+            self.h = C.c_void_p(L.orc_mipmap_new(None, 0, 0, int(spectrum), int(do_trilinear), max_aniso, wrap, scale, gamma))
+        else:
+            t = _f(texels)
+            self.h = C.c_void_p(L.orc_mipmap_new(_p(t), t.shape[1], t.shape[0], int(spectrum), int(do_trilinear),
+                                                 max_aniso, wrap, scale, gamma))
+
+    def __del__(self):
+        try:
+            lib().orc_mipmap_free(self.h)
+        except Exception:
+            pass
+
+    def levels(self):
+        return int(lib().orc_mipmap_levels(self.h))
+
+    def level(self, i):
+        wh = np.zeros(2, np.uint32)
+        lib().orc_mipmap_level_size(self.h, i, _p(wh))
+        out = np.zeros((int(wh[1]), int(wh[0]), 3), np.float32)
+        lib().orc_mipmap_level(self.h, i, _p(out))
+        return out
+
+    def lookup(self, st6):
+        q = _f(st6).reshape(-1, 6)
+        out = np.zeros((q.shape[0], 3), np.float32)
+        lib().orc_mipmap_lookup(self.h, _p(q), q.shape[0], _p(out))
+        return out
+
+    def eval_planar(self, p, dpdx=(0, 0, 0), dpdy=(0, 0, 0)):
+        """ImageTexture::eval with PlanarMapping2D::new() — the call in imagemap.rs's tests."""
+        q = _f(np.concatenate([np.ravel(p), np.ravel(dpdx), np.ravel(dpdy)])).reshape(1, 9)
+        out = np.zeros((1, 3), np.float32)
+        lib().orc_image_texture_eval_planar(self.h, _p(q), 1, _p(out))
+        return out[0]
 
 
 def _f(a):
@@ -111,6 +171,15 @@ class OracleScene:
             b = tex(t.tex2) if t.kind == 1 else 0
             mk = t.mapping.kind if t.mapping is not None else 0
             mp = _f(t.mapping.params if t.mapping is not None else [0] * 8)
+            if t.kind == 3:
+                im = t.image
+                tx = None if im["texels"] is None else _f(im["texels"])
+                i = L.orc_add_image_texture(self.h, mk, _p(mp), _p(tx), 0 if tx is None else tx.shape[1],
+                                            0 if tx is None else tx.shape[0], int(im["spectrum"]),
+                                            int(im["do_trilinear"]), im["max_aniso"], im["wrap"], im["scale"],
+                                            im["gamma"])
+                tex_ids[id(t)] = i
+                return i
             i = L.orc_add_texture(self.h, t.kind, _p(_f(t.value)), mk, _p(mp), a, b, t.aa)
             tex_ids[id(t)] = i
             return i

@@ -66,8 +66,11 @@ struct Mapping2D {
     }
   }
 };
+}  // namespace orc
+#include "mipmap.hpp"  // MIPMap over RGB texels (needs RGB above)
+namespace orc {
 struct Texture {
-  int kind = 0;  // 0 = Constant, 1 = Checkerboard2D, 2 = UV
+  int kind = 0;  // 0 = Constant, 1 = Checkerboard2D, 2 = UV, 3 = ImageTexture (tex1 = mipmap index)
   RGB value;     // Constant (float textures use c[0])
   Mapping2D mapping;
   int tex1 = 0, tex2 = 0;  // Checkerboard children (indices)
@@ -75,11 +78,17 @@ struct Texture {
 };
 struct TextureTable {
   std::vector<Texture> t;
+  std::vector<MIPMap> mips;
   RGB eval(int id, const DiffGeom& dg) const {
     const Texture& tx = t[(size_t)id];
     switch (tx.kind) {
       case 0:
         return tx.value;
+      case 3: {  // imagemap.rs:200-206
+        float m[6];
+        tx.mapping.map(dg, m);
+        return mips[(size_t)tx.tex1].lookup(m[0], m[1], m[2], m[3], m[4], m[5]);
+      }
       case 2: {
         float m[6];
         tx.mapping.map(dg, m);

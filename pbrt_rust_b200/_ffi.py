@@ -52,6 +52,11 @@ class Light(C.Structure):
                 ("first_tri", u32), ("n_tris", u32), ("total_area", f32)]
 
 
+class MipMap(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("n_levels", u32), ("do_trilinear", u32),
+                ("max_anisotropy", f32), ("wrap", u32), ("texel_offset", u64)]
+
+
 class Scene(C.Structure):
     _fields_ = [("nodes", P(Node32)), ("n_nodes", u32), ("leaf_prim", P(u32)), ("n_prims", u32),
                 ("tris", P(Tri48)), ("n_tris", u32), ("spheres", P(Sphere80)),
@@ -59,7 +64,8 @@ class Scene(C.Structure):
                 ("tri_uv", P(f32)), ("tri_n", P(f32)), ("tri_s", P(f32)), ("n_attr", u32),
                 ("materials", P(Material)), ("n_materials", u32), ("textures", P(Texture)),
                 ("n_textures", u32), ("lights", P(Light)), ("n_lights", u32),
-                ("area_prims", P(u32)), ("n_area_prims", u32)]
+                ("area_prims", P(u32)), ("n_area_prims", u32),
+                ("mipmaps", P(MipMap)), ("n_mipmaps", u32), ("texels", P(f32)), ("n_texels", u64)]
 
 
 class Camera(C.Structure):
@@ -126,6 +132,7 @@ SYMBOLS = [
     ("pbh_texture_constant", i32, [_vp, _fp]),
     ("pbh_texture_checkerboard", i32, [_vp, C.c_int, _fp, C.c_int, C.c_int, C.c_int]),
     ("pbh_texture_uv", i32, [_vp, C.c_int, _fp]),
+    ("pbh_texture_image", i32, [_vp, C.c_int, _fp, _fp, u32, u32, C.c_int, C.c_int, f32, C.c_int, f32, f32]),
     ("pbh_material_matte", i32, [_vp, C.c_int, C.c_int]),
     ("pbh_material_plastic", i32, [_vp, C.c_int, C.c_int, C.c_int]),
     ("pbh_light_point", i32, [_vp, _fp, _fp, _fp]),

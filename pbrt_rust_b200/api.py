@@ -117,6 +117,26 @@ class Texture:
     def uv(mapping):
         return Texture(2, mapping=mapping)
 
+    WRAP = {"repeat": 0, "black": 1, "clamp": 2}  # ImageWrap (texture/imagewrap.rs)
+
+    @staticmethod
+    def image(mapping, image, spectrum=True, do_trilinear=False, max_aniso=8.0, wrap="repeat", scale=1.0, gamma=1.0):
+        """TextureCache::<Spectrum | f32>::new_texture (texture/imagemap.rs:128-138, 183-193).
+        `image`: a PNG file name, or an (h, w, 3) array of read_image texels (byte / 255), or None
+        (unreadable file -> 1x1 map of scale^gamma, imagemap.rs:116-120)."""
+        if isinstance(image, str):
+            from .imageio import read_image
+            try:
+                image = read_image(image)
+            except (OSError, ValueError):
+                image = None
+        t = Texture(3, mapping=mapping)
+        t.image = dict(texels=None if image is None else _f(image).reshape(image.shape[0], image.shape[1], 3),
+                       spectrum=bool(spectrum), do_trilinear=bool(do_trilinear), max_aniso=float(max_aniso),
+                       wrap=Texture.WRAP[wrap] if isinstance(wrap, str) else int(wrap), scale=float(scale),
+                       gamma=float(gamma))
+        return t
+
 
 class Material:
     """src/material/mod.rs:79-99"""
@@ -337,6 +357,15 @@ class HostScene:
             elif t.kind == 1:
                 a, b = tex(t.tex1), tex(t.tex2)
                 i = L.pbh_texture_checkerboard(self.h, t.mapping.kind, _fp(_f(t.mapping.params)), a, b, t.aa)
+            elif t.kind == 3:
+                im = t.image
+                tx = im["texels"]
+                i = L.pbh_texture_image(self.h, t.mapping.kind, _fp(_f(t.mapping.params)),
+                                        None if tx is None else _fp(tx), 0 if tx is None else tx.shape[1],
+                                        0 if tx is None else tx.shape[0], int(im["spectrum"]),
+                                        int(im["do_trilinear"]), im["max_aniso"], im["wrap"], im["scale"], im["gamma"])
+                if i < 0:
+                    raise PbrtError(L.pbh_last_error(self.h).decode())
             else:
                 i = L.pbh_texture_uv(self.h, t.mapping.kind, _fp(_f(t.mapping.params)))
             tex_ids[id(t)] = i

@@ -81,7 +81,7 @@ struct pbrtb200_ctx {
   DScene sc{};
   std::vector<pbrtb200_light> h_lights;
   DevBuf d_nodes, d_tris, d_leaf_prim, d_leaf_count, d_spheres, d_sphere_o2w, d_meshes, d_tri_uv,
-      d_tri_n, d_tri_s, d_materials, d_mat_flags, d_textures, d_lights, d_area_tris;
+      d_tri_n, d_tri_s, d_materials, d_mat_flags, d_textures, d_lights, d_area_tris, d_mipmaps, d_texels;
   // per-frame work buffers (grow-only)
   DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_lightu, d_edge, d_rad, d_hits,
       d_sq_rays, d_sq_slots, d_film, d_rects, d_rect_prefix, d_ctrl, d_rays_in, d_occ, d_out_a,
@@ -134,6 +134,8 @@ bool affine_ok(const float* m16) {
 int tex_depth(const pbrtb200_scene* s, int id, int depth) {
   if (id < 0 || (uint32_t)id >= s->n_textures) return -1;
   const pbrtb200_texture& t = s->textures[id];
+  if (t.kind == PBRTB200_TEX_IMAGE) return (t.tex1 >= 0 && (uint32_t)t.tex1 < s->n_mipmaps) ? 0 : -1;
+  if (t.kind < 0 || t.kind > PBRTB200_TEX_IMAGE) return -1;
   if (t.kind != PBRTB200_TEX_CHECKER2D) return 0;
   if (depth > 3) return -1;
   int a = tex_depth(s, t.tex1, depth + 1), b = tex_depth(s, t.tex2, depth + 1);
@@ -556,6 +558,16 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
     if (m.kind == PBRTB200_MAT_PLASTIC && (tex_depth(s, m.ks, 0) < 0 || tex_depth(s, m.roughness, 0) < 0))
       FAIL(PBRTB200_EINVAL, "material ks/roughness texture invalid");
   }
+  for (uint32_t i = 0; i < s->n_mipmaps; ++i) {  // every level must lie inside the texel pool
+    const pbrtb200_mipmap& m = s->mipmaps[i];
+    if (m.width == 0 || m.height == 0 || (m.width & (m.width - 1)) || (m.height & (m.height - 1)))
+      FAIL(PBRTB200_EINVAL, "mipmap level 0 must have power-of-two sides (mipmap.rs:162-167)");
+    if (m.n_levels < 1 || m.n_levels > 32 || m.wrap > PBRTB200_WRAP_CLAMP) FAIL(PBRTB200_EINVAL, "bad mipmap header");
+    uint64_t need = 0;
+    for (uint32_t l = 0; l < m.n_levels; ++l)
+      need += (uint64_t)std::max(m.width >> l, 1u) * (uint64_t)std::max(m.height >> l, 1u);
+    if (!s->texels || m.texel_offset + need > s->n_texels) FAIL(PBRTB200_EINVAL, "mipmap texels out of range");
+  }
   for (uint32_t i = 0; i < s->n_meshes; ++i) {
     if (s->n_materials && s->meshes[i].material >= s->n_materials) FAIL(PBRTB200_EINVAL, "mesh material out of range");
     if (s->meshes[i].area_light >= (int32_t)s->n_lights) FAIL(PBRTB200_EINVAL, "mesh area_light out of range");
@@ -590,6 +602,10 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   if (s->tri_s && upload(ctx, ctx->d_tri_s, s->tri_s, 9ull * s->n_attr)) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_materials, s->materials, s->n_materials)) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_textures, s->textures, s->n_textures)) return PBRTB200_ENODEV;
+  if (s->n_mipmaps) {
+    if (upload(ctx, ctx->d_mipmaps, s->mipmaps, s->n_mipmaps)) return PBRTB200_ENODEV;
+    if (upload(ctx, ctx->d_texels, s->texels, 4ull * s->n_texels)) return PBRTB200_ENODEV;
+  }
   std::vector<uint8_t> mat_flags(std::max<uint32_t>(1u, s->n_materials), 0);
   for (uint32_t i = 0; i < s->n_materials; ++i) {
     const pbrtb200_material& m = s->materials[i];
@@ -617,6 +633,8 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   sc.materials = ctx->d_materials.as<pbrtb200_material>();
   sc.mat_flags = ctx->d_mat_flags.as<uint8_t>();
   sc.textures = ctx->d_textures.as<pbrtb200_texture>();
+  sc.mipmaps = s->n_mipmaps ? ctx->d_mipmaps.as<pbrtb200_mipmap>() : nullptr;
+  sc.texels = s->n_mipmaps ? ctx->d_texels.as<float4>() : nullptr;
   sc.n_prims = s->n_prims;
   sc.n_lights = s->n_lights;
   {
@@ -1127,7 +1145,10 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       sa.rad_slots = rad_slots;
       sa.le_slot = le_slot;
       sa.strict_flags = integ->strict_flags;
-      k_shade<PB_SHADE_MIN_BLOCKS><<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
+      if (ctx->sc.mipmaps)
+        k_shade<PB_SHADE_MIN_BLOCKS, true><<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
+      else
+        k_shade<PB_SHADE_MIN_BLOCKS, false><<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
       CK(cudaGetLastError());
       size_t e3 = tm.mark();
       CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));

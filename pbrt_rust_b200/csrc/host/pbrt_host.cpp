@@ -198,6 +198,8 @@ struct pbh_scene {
   std::vector<pbrtb200_mesh> fmeshes;
   std::vector<float> tri_uv, tri_n, tri_s;
   std::vector<uint32_t> area_prims;
+  std::vector<pbrtb200_mipmap> mipmaps;
+  std::vector<float> texels;  // 4 floats per texel, all levels of all mipmaps
   pbrtb200_scene flat{};
   bool built = false;
 };
@@ -605,6 +607,171 @@ int pbh_texture_uv(pbh_scene* s, int map_kind, const float map[8]) {
   s->textures.push_back(t);
   return (int)s->textures.size() - 1;
 }
+
+// ---- ImageTexture / MIPMap construction (texture/mipmap.rs, texture/imagemap.rs) ----------------
+namespace {
+struct Tex3 {
+  float r, g, b;
+};
+inline Tex3 operator+(Tex3 a, Tex3 b) { return {a.r + b.r, a.g + b.g, a.b + b.b}; }
+inline Tex3 operator*(Tex3 a, float s) { return {a.r * s, a.g * s, a.b * s}; }
+
+inline float mip_sinc(float x, float tau) {  // utils/mod.rs:207-217
+  float v = std::fabs(x);
+  if (v < 1e-5f) return 1.0f;
+  if (v >= 1.0f) return 0.0f;
+  v *= 3.14159265358979323846f;
+  const float vtau = v * tau;
+  const float s = std::sin(vtau) / vtau;
+  return s * std::sin(v) / v;
+}
+inline int32_t mip_mod(int32_t a, int32_t b) {  // utils/mod.rs:219-223
+  const int32_t x = a - (a / b) * b;
+  return x < 0 ? x + b : x;
+}
+// texel index under an ImageWrap, or -1 (Black outside / resampling tap outside)
+inline int32_t mip_wrap(int32_t i, int32_t dim, int wrap, bool black_is_raw) {
+  if (wrap == PBRTB200_WRAP_REPEAT) return mip_mod(i, dim);
+  if (wrap == PBRTB200_WRAP_CLAMP) return i < 0 ? 0 : (i > dim - 1 ? dim - 1 : i);
+  (void)black_is_raw;
+  return (i >= 0 && i < dim) ? i : -1;
+}
+struct Taps {
+  int32_t first;
+  float w[4];
+};
+std::vector<Taps> mip_resample_weights(size_t oldres, size_t newres) {  // mipmap.rs:22-43
+  std::vector<Taps> out(newres);
+  for (size_t i = 0; i < newres; ++i) {
+    const float center = ((float)i + 0.5f) * (float)oldres / (float)newres;
+    Taps t;
+    t.first = pbh::sat_i32(std::floor((center - 2.0f) + 0.5f));
+    for (int j = 0; j < 4; ++j) t.w[j] = mip_sinc((((float)(t.first + j) + 0.5f) - center) / 2.0f, 2.0f);
+    float sum = 0.0f;
+    for (int j = 0; j < 4; ++j) sum = sum + t.w[j];
+    const float inv = 1.0f / sum;
+    for (int j = 0; j < 4; ++j) t.w[j] *= inv;
+    out[i] = t;
+  }
+  return out;
+}
+// mipmap.rs:45-106.  The t pass is in place, like the reference: a row that was already
+// resampled is read back by the rows after it.
+void mip_resize_pot(size_t w, size_t h, const std::vector<Tex3>& px, int wrap, size_t* wp, size_t* hp,
+                    std::vector<Tex3>* out) {
+  size_t wpot = 1, hpot = 1;
+  while (wpot < w) wpot <<= 1;
+  while (hpot < h) hpot <<= 1;
+  std::vector<Tex3> np(wpot * hpot);
+  const auto sw = mip_resample_weights(w, wpot);
+  for (size_t t = 0; t < h; ++t)
+    for (size_t s = 0; s < wpot; ++s) {
+      Tex3 acc{0.f, 0.f, 0.f};
+      for (int j = 0; j < 4; ++j) {
+        const int32_t o = mip_wrap(sw[s].first + j, (int32_t)w, wrap, true);
+        if (o >= 0) acc = px[t * w + (size_t)o] * sw[s].w[j] + acc;
+      }
+      np[t * wpot + s] = acc;
+    }
+  for (size_t t = h; t < hpot; ++t)
+    for (size_t s = 0; s < wpot; ++s) np[t * wpot + s] = px[0];
+  const auto tw = mip_resample_weights(h, hpot);
+  for (size_t s = 0; s < wpot; ++s)
+    for (size_t t = 0; t < hpot; ++t) {
+      Tex3 acc{0.f, 0.f, 0.f};
+      for (int j = 0; j < 4; ++j) {
+        const int32_t o = mip_wrap(tw[t].first + j, (int32_t)h, wrap, true);
+        if (o >= 0) acc = np[(size_t)o * wpot + s] * tw[t].w[j] + acc;
+      }
+      np[t * wpot + s] = acc;
+    }
+  *wp = wpot;
+  *hp = hpot;
+  *out = std::move(np);
+}
+}  // namespace
+
+int pbh_texture_image(pbh_scene* s, int map_kind, const float map[8], const float* rgb, uint32_t w,
+                      uint32_t h, int spectrum, int do_trilinear, float max_aniso, int wrap,
+                      float scale, float gamma) {
+  if (wrap < 0 || wrap > 2) {
+    s->err = "image texture: bad wrap mode";
+    return PBRTB200_EINVAL;
+  }
+  // texel conversion (imagemap.rs:108-121 / 163-176)
+  std::vector<Tex3> px;
+  size_t W = w, H = h;
+  if (!rgb || w == 0 || h == 0) {
+    const float v = std::pow(scale, gamma);
+    px.push_back({v, v, v});
+    W = H = 1;
+  } else {
+    px.resize(W * H);
+    for (size_t i = 0; i < W * H; ++i) {
+      const float r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+      if (spectrum) {
+        px[i] = {std::pow(r * scale, gamma), std::pow(g * scale, gamma), std::pow(b * scale, gamma)};
+      } else {
+        const float y = 0.212671f * r + 0.715160f * g + 0.072169f * b;  // Spectrum::y, spectrum.rs:37-41,468
+        const float v = std::pow(y * scale, gamma);
+        px[i] = {v, v, v};
+      }
+    }
+  }
+  // MIPMap::new (mipmap.rs:159-204)
+  if ((W & (W - 1)) || (H & (H - 1))) {
+    std::vector<Tex3> pot;
+    mip_resize_pot(W, H, px, wrap, &W, &H, &pot);
+    px.swap(pot);
+  }
+  pbrtb200_mipmap mm{};
+  mm.width = (uint32_t)W;
+  mm.height = (uint32_t)H;
+  mm.do_trilinear = do_trilinear ? 1u : 0u;
+  mm.max_anisotropy = max_aniso;
+  mm.wrap = (uint32_t)wrap;
+  mm.texel_offset = s->texels.size() / 4;
+  auto append = [&](const std::vector<Tex3>& lv) {
+    for (const Tex3& t : lv) {
+      s->texels.push_back(t.r);
+      s->texels.push_back(t.g);
+      s->texels.push_back(t.b);
+      s->texels.push_back(0.0f);
+    }
+  };
+  append(px);
+  uint32_t levels = 0;  // ulog2(max(w, h)) = bits - leading_zeros (mipmap.rs:108-110)
+  for (size_t m = std::max(W, H); m; m >>= 1) ++levels;
+  size_t lw = W, lh = H;
+  std::vector<Tex3> last = std::move(px);
+  for (uint32_t i = 1; i < levels; ++i) {
+    const size_t nw = std::max<size_t>(lw / 2, 1), nh = std::max<size_t>(lh / 2, 1);
+    std::vector<Tex3> nl(nw * nh);
+    auto at = [&](int32_t si, int32_t ti) -> Tex3 {  // texel_at (mipmap.rs:112-138)
+      const int32_t a = mip_wrap(si, (int32_t)lw, wrap, false), b = mip_wrap(ti, (int32_t)lh, wrap, false);
+      if (a < 0 || b < 0) return Tex3{0.f, 0.f, 0.f};
+      return last[(size_t)b * lw + (size_t)a];
+    };
+    for (int32_t t = 0; t < (int32_t)nh; ++t)
+      for (int32_t si = 0; si < (int32_t)nw; ++si)
+        nl[(size_t)t * nw + (size_t)si] =
+            (((at(2 * si, 2 * t) + at(2 * si + 1, 2 * t)) + at(2 * si, 2 * t + 1)) + at(2 * si + 1, 2 * t + 1)) * 0.25f;
+    append(nl);
+    last.swap(nl);
+    lw = nw;
+    lh = nh;
+  }
+  mm.n_levels = levels;
+  s->mipmaps.push_back(mm);
+  pbrtb200_texture t{};
+  t.kind = PBRTB200_TEX_IMAGE;
+  t.map_kind = map_kind;
+  std::memcpy(t.map, map, 32);
+  t.tex1 = (int32_t)s->mipmaps.size() - 1;
+  s->textures.push_back(t);
+  return (int)s->textures.size() - 1;
+}
+
 int pbh_material_matte(pbh_scene* s, int kd, int sigma) {
   pbrtb200_material m{};
   m.kind = PBRTB200_MAT_MATTE;
@@ -891,6 +1058,10 @@ int pbh_build_bvh(pbh_scene* s, uint32_t max_prims, const char* split_method) {
   f.n_lights = (uint32_t)s->lights.size();
   f.area_prims = s->area_prims.data();
   f.n_area_prims = (uint32_t)s->area_prims.size();
+  f.mipmaps = s->mipmaps.data();
+  f.n_mipmaps = (uint32_t)s->mipmaps.size();
+  f.texels = s->texels.data();
+  f.n_texels = s->texels.size() / 4;
   s->built = true;
   return PBRTB200_OK;
 }

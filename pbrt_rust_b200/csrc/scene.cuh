@@ -37,6 +37,8 @@ struct DScene {
   const uint8_t* __restrict__ mat_flags;  // bit0: some texture of the material is not Constant
   const pbrtb200_texture* __restrict__ textures;
   const pbrtb200_light* __restrict__ lights;
+  const pbrtb200_mipmap* __restrict__ mipmaps;  // image textures: headers ...
+  const float4* __restrict__ texels;            // ... and the texel pool (rgb, 0)
   uint32_t root_ref;
   uint32_t n_prims;
   uint32_t n_lights;

@@ -154,6 +154,51 @@ def config4(n_ground=(500, 200), n_spheres=20_000, xres=3840, yres=2160, xs=8, y
     return _setup(scene, c2w, 45.0, xres, yres, xs, ys, True, crop=crop)
 
 
+def procedural_image(w=200, h=120, seed=11):
+    """A synthetic RGB image (what read_image would return: (h, w, 3) floats = byte / 255) with
+    smooth gradients, hard edges and noise, non-power-of-two on purpose (exercises the resize)."""
+    y, x = np.mgrid[0:h, 0:w]
+    r = (np.sin(x * 0.21) * 0.5 + 0.5) * 255
+    g = ((x // 16 + y // 12) % 2) * 200 + 30
+    b = (x * 255) // max(w - 1, 1)
+    img = np.stack([r, g, b], -1).astype(np.int64)
+    noise = (splitmix64(seed, w * h * 3).reshape(h, w, 3) * 24).astype(np.int64)
+    img = np.clip(img + noise, 0, 255).astype(np.uint8)
+    return img.astype(np.float32) / np.float32(255)
+
+
+def textured(image=None, xres=256, yres=160, xs=2, ys=2, do_trilinear=False, max_aniso=8.0, wrap="repeat",
+             gamma=2.2, nx=40, nz=20, n_spheres=24, seed=5):
+    """"Next" row 2 test scene: heightfield ground with an ImageTexture Kd (UV mapping, tiled 3x2)
+    and a float ImageTexture sigma, plastic spheres whose Kd is a planar-mapped image and whose
+    roughness is a float image; one point light + the quad area light."""
+    if image is None:
+        image = procedural_image()
+    vi, P = heightfield(nx, nz)
+    uv = np.stack([(P[:, 0] + 20.0) / 40.0, (P[:, 2] + 10.0) / 20.0], -1).astype(np.float32)
+    kw = dict(do_trilinear=do_trilinear, max_aniso=max_aniso, wrap=wrap)
+    kd_ground = Texture.image(UVMapping2D(3.0, 2.0, 0.1, 0.2), image, spectrum=True, scale=1.0, gamma=gamma, **kw)
+    sig_ground = Texture.image(UVMapping2D(1.0, 1.0, 0.0, 0.0), image, spectrum=False, scale=30.0, gamma=1.0, **kw)
+    prims = [Primitive.geometric(Shape.triangle_mesh(Transform.new(), Transform.new(), False, vi, P, uv=uv),
+                                 Material.matte(kd_ground, sig_ground))]
+    kd_sph = Texture.image(PlanarMapping2D((0.5, 0, 0), (0, 0.5, 0.25), 0.3, 0.1), image, spectrum=True,
+                           scale=0.9, gamma=gamma, **kw)
+    rough = Texture.image(UVMapping2D(2.0, 2.0, 0.0, 0.0), image, spectrum=False, scale=0.5, gamma=1.0, **kw)
+    m_sph = Material.plastic(kd_sph, Texture.constant(0.25), rough)
+    u = splitmix64(seed, 3 * n_spheres).reshape(-1, 3)
+    for k in range(n_spheres):
+        r = 0.4 + 0.5 * u[k, 0]
+        t = Transform.translate((float(-15 + 30 * u[k, 1]), float(1.2 + r), float(-7 + 14 * u[k, 2])))
+        prims.append(Primitive.geometric(Shape.sphere(t, t.inverse(), False, float(r), float(-r), float(r), 360.0), m_sph))
+    lvi, lP = _quad_light()
+    prims.append(Primitive.geometric_area_light(
+        Shape.triangle_mesh(Transform.new(), Transform.new(), False, lvi, lP), _matte(), AreaLight(10.0, 1)))
+    scene = Scene.new_with(Primitive.bvh(prims, 4, "sah"),
+                           [Light.point(Transform.translate((-8.0, 10.0, -12.0)), 120.0)])
+    c2w = Transform.look_at((0, 9, -26), (0, 0, 0), (0, 1, 0)).inverse()
+    return _setup(scene, c2w, 45.0, xres, yres, xs, ys, True)
+
+
 def config5(nx=5000, nz=5000, xres=1920, yres=1080, xs=16, ys=16, crop=(0, 1, 0, 1)):
     """50 M-triangle heightfield, 4 area lights, 256 spp."""
     return config3(nx, nz, xres, yres, xs, ys, crop=crop, n_lights=4)

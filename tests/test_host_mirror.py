@@ -230,3 +230,67 @@ def test_write_image_png_round_trip(orc, tmp_path):
 def test_write_image_rejects_bad_path():
     with pytest.raises(OSError):
         pb.write_image("/nonexistent-dir/x.png", np.ones((2, 2, 4), np.float32))
+
+
+# ---- ImageTexture / MIPMap ("next" row 2) -----------------------------------------------------
+
+def _host_pyramid(host, mip_index=0):
+    """Levels of MIPMap `mip_index` out of the flattened scene's texel pool."""
+    f = host.flat.contents
+    mm = f.mipmaps[mip_index]
+    tex = np.ctypeslib.as_array(f.texels, shape=(f.n_texels * 4,)).reshape(-1, 4)
+    off, w, h, out = mm.texel_offset, mm.width, mm.height, []
+    for _ in range(mm.n_levels):
+        out.append(tex[off:off + w * h, :3].reshape(h, w, 3).copy())
+        off += w * h
+        w, h = max(w >> 1, 1), max(h >> 1, 1)
+    return mm, out
+
+
+@pytest.mark.parametrize("wrap", ["repeat", "black", "clamp"])
+@pytest.mark.parametrize("spectrum", [True, False])
+def test_host_mipmap_pyramid_matches_oracle(orc, wrap, spectrum):
+    """The product's host-side MIPMap::new (pbh_texture_image) against the oracle's line-faithful
+    one: same level count, same sizes, every texel bit-identical — non-power-of-two input, so the
+    sinc resize (mipmap.rs:45-106, incl. its in-place t pass) is exercised for all wrap modes."""
+    img = scenes.procedural_image(200, 120)
+    t = pb.Texture.image(pb.UVMapping2D(1, 1, 0, 0), img, spectrum=spectrum, wrap=wrap, scale=0.9, gamma=2.2)
+    mat = pb.Material.matte(t, pb.Texture.constant(0.0))
+    tri = pb.Shape.triangle_mesh(pb.Transform.new(), pb.Transform.new(), False, [0, 1, 2],
+                                 [[0, 0, 0], [1, 0, 0], [0, 1, 0]])
+    scene = pb.Scene.new_with(pb.Primitive.bvh([pb.Primitive.geometric(tri, mat)], 1, "sah"), [])
+    host = pb.HostScene(scene)
+    mm, levels = _host_pyramid(host)
+    ref = orc.OracleMIPMap(img, spectrum=spectrum, wrap=pb.Texture.WRAP[wrap], scale=0.9, gamma=2.2)
+    assert (mm.width, mm.height, mm.n_levels) == (256, 128, 9) and ref.levels() == 9
+    for i, lv in enumerate(levels):
+        r = ref.level(i)
+        assert lv.shape == r.shape
+        assert np.array_equal(lv.view(np.uint32), r.view(np.uint32)), f"level {i}"
+    if not spectrum:
+        assert np.array_equal(levels[0][..., 0], levels[0][..., 1])
+
+
+def test_host_mipmap_unreadable_file_and_png_reader(orc, tmp_path):
+    """imagemap.rs:116-120: a file that cannot be read gives the 1x1 scale^gamma map; and the
+    package's PNG reader round-trips the product's own PNG writer."""
+    t = pb.Texture.image(pb.UVMapping2D(1, 1, 0, 0), str(tmp_path / "missing.png"), scale=0.5, gamma=2.0)
+    assert t.image["texels"] is None
+    mat = pb.Material.matte(t, pb.Texture.constant(0.0))
+    tri = pb.Shape.triangle_mesh(pb.Transform.new(), pb.Transform.new(), False, [0, 1, 2],
+                                 [[0, 0, 0], [1, 0, 0], [0, 1, 0]])
+    host = pb.HostScene(pb.Scene.new_with(pb.Primitive.bvh([pb.Primitive.geometric(tri, mat)], 1, "sah"), []))
+    mm, levels = _host_pyramid(host)
+    assert (mm.width, mm.height, mm.n_levels) == (1, 1, 1) and levels[0].ravel().tolist() == [0.25, 0.25, 0.25]
+    from pbrt_rust_b200.imageio import read_png_rgb8
+    rgb8 = (scenes.procedural_image(37, 21) * 255).round().astype(np.uint8)
+    pb.write_image(str(tmp_path / "a.png"), rgb8=rgb8)
+    assert np.array_equal(read_png_rgb8(str(tmp_path / "a.png")), rgb8)
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "checkerboard_stretched.npz"))["rgb8"]
+    pb.write_image(str(tmp_path / "b.png"), rgb8=golden)
+    assert np.array_equal(read_png_rgb8(str(tmp_path / "b.png")), golden)
+
+
+def test_upload_rejects_bad_mipmap_tables():
+    """Validation happens before any device call is needed for the table itself."""
+    assert C.sizeof(_ffi.MipMap) == 32

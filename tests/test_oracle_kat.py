@@ -577,3 +577,93 @@ def test_strict_and_default_modes_agree_for_box_filter(orc):
     b = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=1))
     assert (np.abs(a["rgb"] - b["rgb"]).max(axis=-1) > 0).mean() <= 1e-3
     assert a["stats"]["camera_rays"] == b["stats"]["camera_rays"]
+
+
+# ---- ImageTexture + MIPMap ("next" row 2): texture/imagemap.rs:211-418 -------------------------
+import os as _os
+
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+def _texels(name):
+    """read_image (imagemap.rs:75-89) of the reference's fixture; texels committed by
+    scripts/make_golden_textures.py."""
+    return np.load(_os.path.join(_GOLD, name + ".npz"))["rgb8"].astype(np.float32) / np.float32(255)
+
+
+def test_imagemap_rgb_textures(orc):  # imagemap.rs:222-244
+    tex = orc.OracleMIPMap(_texels("checkerboard_square"), spectrum=True, do_trilinear=False, max_aniso=1.0,
+                           wrap=0, scale=1.0, gamma=2.2)
+    assert tex.eval_planar((0.25, 0.25, 0)).tolist() == [0, 0, 0]
+    assert tex.eval_planar((0.75, 0.25, 0)).tolist() == [1, 1, 1]
+    assert tex.eval_planar((0.25, 0.75, 0)).tolist() == [1, 1, 1]
+    assert tex.eval_planar((0.75, 0.75, 0)).tolist() == [0, 0, 0]
+
+
+def test_imagemap_float_textures(orc):  # imagemap.rs:246-267
+    tex = orc.OracleMIPMap(_texels("checkerboard_stretched"), spectrum=False, do_trilinear=False, max_aniso=1.0,
+                           wrap=0, scale=1.0, gamma=2.2)
+    assert tex.eval_planar((0.25, 0.25, 0))[0] == 0.0
+    assert tex.eval_planar((0.75, 0.25, 0))[0] == 1.0
+    assert tex.eval_planar((0.25, 0.75, 0))[0] == 1.0
+    assert tex.eval_planar((0.75, 0.75, 0))[0] == 0.0
+
+
+def test_imagemap_repeat_wrap(orc):  # imagemap.rs:269-304
+    tex = orc.OracleMIPMap(_texels("checkerboard_square"), True, False, 1.0, 0, 1.0, 2.2)
+    x0 = tex.eval_planar((0.25, 0.25, 0)).tolist()
+    for i in range(3):
+        for j in range(3):
+            for sx, sy in ((1, 1), (-1, 1), (1, -1), (-1, -1)):
+                p = (np.float32(0.25) + np.float32(sx * i), np.float32(0.25) + np.float32(sy * j), 0)
+                assert tex.eval_planar(p).tolist() == x0
+
+
+def test_imagemap_black_wrap(orc):  # imagemap.rs:306-342
+    tex = orc.OracleMIPMap(_texels("checkerboard_square"), True, False, 1.0, 1, 1.0, 2.2)
+    for i in range(10):
+        for j in range(10):
+            dx = np.float32(1.0) + np.float32(i) * np.float32(0.1)
+            dy = np.float32(1.0) + np.float32(j) * np.float32(0.1)
+            for sx, sy in ((1, 1), (-1, 1), (1, -1), (-1, -1)):
+                p = (np.float32(0.25) + sx * dx, np.float32(0.25) + sy * dy, 0)
+                assert tex.eval_planar(p).tolist() == [0, 0, 0]
+
+
+def test_imagemap_clamp_wrap(orc):  # imagemap.rs:344-374
+    tex = orc.OracleMIPMap(_texels("checkerboard_square"), False, False, 1.0, 2, 1.0, 2.2)
+    for i in range(10):
+        for j in range(10):
+            dx = np.float32(1.0) + np.float32(i) * np.float32(0.1)
+            dy = np.float32(1.0) + np.float32(j) * np.float32(0.1)
+            assert abs(1.0 - tex.eval_planar((np.float32(0.25) + dx, 0.25, 0))[0]) < 1e-4
+            assert tex.eval_planar((np.float32(0.25) - dx, 0.25, 0))[0] == 0.0
+            assert abs(1.0 - tex.eval_planar((np.float32(0.25) + dx, np.float32(0.25) - dy, 0))[0]) < 1e-4
+            assert tex.eval_planar((np.float32(0.25) - dx, np.float32(0.25) - dy, 0))[0] == 0.0
+
+
+def test_imagemap_isotropic_sampling(orc):  # imagemap.rs:376-391
+    tex = orc.OracleMIPMap(_texels("checkerboard_stretched"), False, True, 1.0, 2, 1.0, 2.2)
+    v = tex.eval_planar((0.51, 0.25, 0), (0.02, 0, 0), (0, 0.02, 0))[0]
+    assert abs(v - 0.7) < 0.01, v
+
+
+def test_imagemap_anisotropic_sampling(orc):  # imagemap.rs:393-417
+    tex = orc.OracleMIPMap(_texels("checkerboard_stretched"), False, False, 100.0, 2, 1.0, 2.2)
+    v = tex.eval_planar((0.51, 0.48, 0), (0.02, 0, 0), (0, 0.02, 0))[0]
+    assert abs(v - 0.76) < 0.01, v
+    v = tex.eval_planar((0.51, 0.48, 0), (0.02, 0, 0), (0, 0.002, 0))[0]
+    assert abs(v - 0.88) < 0.01, v
+
+
+def test_mipmap_structure_and_unreadable_file(orc):
+    """mipmap.rs:159-204: 500x256 -> 512x256, ulog2(512) = 10 levels down to 1x1; an unreadable
+    file gives a 1x1 map of scale^gamma (imagemap.rs:116-120)."""
+    tex = orc.OracleMIPMap(_texels("checkerboard_stretched"), False, True, 1.0, 0, 1.0, 2.2)
+    assert tex.levels() == 10
+    assert [tex.level(i).shape[:2] for i in range(10)] == [(256 >> i if 256 >> i else 1, 512 >> i) for i in range(10)]
+    one = orc.OracleMIPMap(None, True, True, 1.0, 0, 0.5, 2.0)
+    assert one.levels() == 1 and one.level(0).ravel().tolist() == [0.25, 0.25, 0.25]
+    L = orc.lib()
+    assert [L.orc_modulo(a, 4) for a in (-5, -4, -1, 0, 3, 4, 9)] == [3, 0, 3, 0, 3, 0, 1]  # utils/mod.rs:219-223
+    assert L.orc_sinc_1d(0.0, 2.0) == 1.0 and L.orc_sinc_1d(1.0, 2.0) == 0.0
