@@ -188,20 +188,47 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1 film gather.  Default "p2p": rank 0 shares its film buffer over CUDA IPC and every
+    # rank's film kernel stores its owned tiles straight into it over NVLink (two buffers,
+    # alternating, so rank 0 can still read frame k while frame k+1 is written); the only other
+    # per-frame communication is a barrier.  PBRTB200_GATHER=nccl: reduce(SUM) of zero-padded films.
+    gather = os.environ.get("PBRTB200_GATHER", "p2p") if world > 1 else "none"
+    peers, frame_no = [], [0]
+    if gather == "p2p":
+        try:
+            peers = [multigpu.PeerFilm(r.ctx, h * w, dist, torch.device("cuda", local)) for _ in range(2)]
+        except Exception as e:  # no peer access between these GPUs
+            if rank == 0:
+                print(f"bench: CUDA IPC film sharing unavailable ({e}); using the NCCL gather", file=sys.stderr)
+            gather = "nccl"
+        ok = torch.tensor([1 if gather == "p2p" else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            gather = "nccl"
+    peer_views = [p.tensor() for p in peers] if (gather == "p2p" and rank == 0) else []
+    fence = torch.zeros(1, dtype=torch.int32, device="cuda")
+
     def frame(resident):
-        if resident:
-            r.render(cfg["scene"], tiles=tiles, out=d_film)
-            if world > 1:  # film gather over NVLink: owned tiles are disjoint, the rest is zero
-                dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)
-        elif world == 1:
-            r.render(cfg["scene"], tiles=tiles, out=h_film)   # C ABI with a host film buffer (D2H inside)
+        if world == 1:
+            # resident: film left in HBM; e2e: C ABI with a host film buffer (D2H inside the call)
+            r.render(cfg["scene"], tiles=tiles, out=d_film if resident else h_film)
+            return r.last_stats
+        k = frame_no[0] & 1
+        frame_no[0] += 1
+        if gather == "p2p":
+            r.render(cfg["scene"], tiles=tiles, out=peers[k].ptr, keep_others=True)
+            # frame fence: a 4-byte all-reduce ordered on the stream after this rank's film kernel;
+            # when it completes, every rank's stores have landed in rank 0's HBM (no host block)
+            dist.all_reduce(fence, op=dist.ReduceOp.SUM)
+            src = peer_views[k] if rank == 0 else None
         else:
-            # N > 1: each rank renders its tiles into HBM, the film is gathered over NVLink, and rank
-            # 0 brings the finished frame to pinned host memory — what a user of N GPUs receives.
             r.render(cfg["scene"], tiles=tiles, out=d_film)
             dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)
+            src = d_film
+        if not resident:
+            # what a user of N GPUs receives: the finished frame in (pinned) host memory on rank 0
             if rank == 0:
-                h_film_t.copy_(d_film, non_blocking=True)
+                h_film_t.copy_(src, non_blocking=True)
             torch.cuda.synchronize()
         return r.last_stats
 
@@ -308,7 +335,9 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_frame": rays_per_frame, "tiles": "64x64 cyclic" if world > 1 else "whole film",
                    "l2": "per-frame working set (112 MB scene + >2 GB wavefront buffers) exceeds the 126 MB L2; no explicit flush",
-                   "scene_build_upload_s": t_scene},
+                   "scene_build_upload_s": t_scene,
+                   "film_gather": {"none": "single GPU", "p2p": "film kernels store owned tiles into rank 0's HBM over NVLink (CUDA IPC) + barrier",
+                                   "nccl": "reduce(SUM) of zero-padded films (NCCL)"}[gather]},
         "clocks": clocks,
         "e2e": {"value": e2e_v, "unit": "Mrays/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": 1024 + 64 + 44 + 12 + 128 + (16 * len(tiles) if tiles else 0),

@@ -212,9 +212,11 @@ typedef struct {
 } pbrtb200_integrator;
 
 /* Film pixel rectangles this call renders (multi-GPU tile partition); NULL = whole film. */
+#define PBRTB200_TILES_KEEP_OTHERS 1u /* do not clear the film pixels outside the rects */
 typedef struct {
   const int32_t* rects; /* n_rects x (x0, y0, x1, y1), half-open, in film pixel coordinates */
   uint32_t n_rects;
+  uint32_t flags;       /* PBRTB200_TILES_* ; 0 = pixels outside the rects are written as zero */
 } pbrtb200_tileset;
 
 typedef struct {
@@ -256,6 +258,21 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
                     const pbrtb200_film* film, const pbrtb200_integrator* integ,
                     const pbrtb200_tileset* tiles, float* out_xyzw, int out_is_device,
                     pbrtb200_stats* stats);
+
+/* Multi-GPU film gather without a collective (ownership of film pixels is disjoint,
+ * the reference merges sub-films by pixel ownership, film.rs:149-186).  One process per GPU: the
+ * gathering rank creates a film buffer and exports a CUDA IPC handle; every other rank opens it
+ * and passes the mapped pointer as out_xyzw (out_is_device = 1) together with its tile set and
+ * PBRTB200_TILES_KEEP_OTHERS - its film kernel then stores the owned pixels straight into the
+ * gathering GPU's HBM over NVLink/NVSwitch.  The caller separates frames with a barrier.
+ *   create: *dev_ptr = new buffer of n_pixels float4 on ctx's device (freed by pbrtb200_destroy),
+ *           handle64 = cudaIpcMemHandle_t bytes to send to the peers
+ *   open:   *dev_ptr = that buffer mapped into this process (peer access enabled lazily)
+ *   close:  unmap a pointer returned by open                                                     */
+int pbrtb200_peer_film_create(pbrtb200_ctx* ctx, uint64_t n_pixels, void** dev_ptr,
+                              unsigned char handle64[64]);
+int pbrtb200_peer_film_open(pbrtb200_ctx* ctx, const unsigned char handle64[64], void** dev_ptr);
+int pbrtb200_peer_film_close(pbrtb200_ctx* ctx, void* dev_ptr);
 
 /* Scene::intersect for a batch of rays (src/scene.rs:60-63).  *_is_device: pointers are device
  * memory on the ctx's device (used by bench.py's resident-input arm).                           */

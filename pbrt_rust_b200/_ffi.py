@@ -91,7 +91,7 @@ class Integrator(C.Structure):
 
 
 class TileSet(C.Structure):
-    _fields_ = [("rects", P(i32)), ("n_rects", u32)]
+    _fields_ = [("rects", P(i32)), ("n_rects", u32), ("flags", u32)]
 
 
 class Stats(C.Structure):
@@ -153,6 +153,9 @@ SYMBOLS = [
     ("pbh_rgb_to_bytes", None, [_fp, u64, _vp]),
     ("pbh_write_png", i32, [C.c_char_p, _vp, u32, u32]),
     ("pbh_write_pfm", i32, [C.c_char_p, _fp, u32, u32]),
+    ("pbrtb200_peer_film_create", i32, [_vp, u64, P(_vp), C.c_char_p]),
+    ("pbrtb200_peer_film_open", i32, [_vp, C.c_char_p, P(_vp)]),
+    ("pbrtb200_peer_film_close", i32, [_vp, _vp]),
     ("pbrtb200_film_develop", i32, [_vp, _vp, C.c_int, u64, _vp, _vp, C.c_int]),
 ]
 

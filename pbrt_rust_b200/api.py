@@ -469,10 +469,19 @@ class Context:
             pass
 
 
+class DevicePtr:
+    """A raw device address (e.g. a peer GPU's film mapped with pbrtb200_peer_film_open)."""
+
+    def __init__(self, addr):
+        self.addr = int(addr)
+
+
 def _ptr(a):
-    """numpy array -> host pointer ; torch CUDA tensor -> device pointer"""
+    """numpy array -> host pointer ; torch CUDA tensor / DevicePtr -> device pointer"""
     if a is None:
         return None, 0
+    if isinstance(a, DevicePtr):
+        return C.c_void_p(a.addr), 1
     if isinstance(a, np.ndarray):
         return C.c_void_p(a.ctypes.data), 0
     return C.c_void_p(a.data_ptr()), (1 if a.is_cuda else 0)
@@ -505,9 +514,10 @@ class GpuRenderer:
             self.ctx.upload(self.host_scene)
             self._scene_key = scene
 
-    def render(self, scene, tiles=None, out=None):
+    def render(self, scene, tiles=None, out=None, keep_others=False):
         """Returns the film as an (H, W, 4) array: sum(w*XYZ), sum(w).  `out` may be a CUDA tensor
-        (float32, H*W*4) to keep the film in HBM."""
+        (float32, H*W*4) or a DevicePtr to keep the film in HBM.  keep_others: with `tiles`, leave
+        the pixels outside the tiles untouched (another GPU owns them) instead of zeroing them."""
         self.preprocess(scene)
         film = self.camera.film
         h, w = film.shape
@@ -516,7 +526,7 @@ class GpuRenderer:
         ts = None
         if tiles is not None:
             rects = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 4)
-            ts = _ffi.TileSet(rects.ctypes.data_as(C.POINTER(C.c_int32)), rects.shape[0])
+            ts = _ffi.TileSet(rects.ctypes.data_as(C.POINTER(C.c_int32)), rects.shape[0], 1 if keep_others else 0)
         integ = _ffi.Integrator(0, self.surf.max_depth, int(self.surf.strict_flags))
         st = _ffi.Stats()
         smp = self.sampler_desc()

@@ -81,7 +81,7 @@ struct pbrtb200_ctx {
   DScene sc{};
   std::vector<pbrtb200_light> h_lights;
   DevBuf d_nodes, d_tris, d_leaf_prim, d_leaf_count, d_spheres, d_sphere_o2w, d_meshes, d_tri_uv,
-      d_tri_n, d_tri_s, d_materials, d_mat_flags, d_textures, d_lights, d_area_tris, d_mipmaps, d_texels;
+      d_tri_n, d_tri_s, d_materials, d_mat_flags, d_textures, d_lights, d_area_tris, d_mipmaps, d_texels, d_peer_film;
   // per-frame work buffers (grow-only)
   DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_lightu, d_edge, d_rad, d_hits,
       d_sq_rays, d_sq_slots, d_film, d_rects, d_rect_prefix, d_ctrl, d_rays_in, d_occ, d_out_a,
@@ -1018,8 +1018,8 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   size_t eA = tm.mark();
   CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
   CK(cudaMemsetAsync(ctx->d_edge.p, 0, npix * sizeof(uint32_t), ctx->stream));
-  if (tiles && tiles->n_rects)  // otherwise every film pixel is written by k_film
-    CK(cudaMemsetAsync(d_film, 0, film_px * sizeof(float4), ctx->stream));
+  if (tiles && tiles->n_rects && !(tiles->flags & PBRTB200_TILES_KEEP_OTHERS))
+    CK(cudaMemsetAsync(d_film, 0, film_px * sizeof(float4), ctx->stream));  // else k_film writes every pixel
 
   // ---- film stage (launched per band, see below) ---------------------------------------------
   DFilm df;
@@ -1252,6 +1252,39 @@ int pbrtb200_film_develop(pbrtb200_ctx* ctx, const float* film_xyzw, int film_is
     if (out_rgb8) CK(cudaMemcpyAsync(out_rgb8, d_rgb8, n_pixels * 3, cudaMemcpyDeviceToHost, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
+  return PBRTB200_OK;
+}
+
+int pbrtb200_peer_film_create(pbrtb200_ctx* ctx, uint64_t n_pixels, void** dev_ptr, unsigned char handle64[64]) {
+  if (!ctx || !dev_ptr || !handle64 || n_pixels == 0) return PBRTB200_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CK(cudaSetDevice(ctx->device));
+  // a dedicated cudaMalloc allocation: IPC handles name whole allocations
+  CK(ctx->d_peer_film.ensure(n_pixels * sizeof(float4)));
+  CK(cudaMemsetAsync(ctx->d_peer_film.p, 0, n_pixels * sizeof(float4), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->d_peer_film.p));
+  std::memcpy(handle64, &h, 64);
+  *dev_ptr = ctx->d_peer_film.p;
+  return PBRTB200_OK;
+}
+
+int pbrtb200_peer_film_open(pbrtb200_ctx* ctx, const unsigned char handle64[64], void** dev_ptr) {
+  if (!ctx || !dev_ptr || !handle64) return PBRTB200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr = p;
+  return PBRTB200_OK;
+}
+
+int pbrtb200_peer_film_close(pbrtb200_ctx* ctx, void* dev_ptr) {
+  if (!ctx || !dev_ptr) return PBRTB200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaIpcCloseMemHandle(dev_ptr));
   return PBRTB200_OK;
 }
 }  // extern "C"

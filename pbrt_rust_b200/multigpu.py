@@ -3,9 +3,16 @@
 The scene is replicated per GPU; the film is cut into fixed 64x64 tiles assigned cyclically
 (tile -> gpu = tile_id mod G).  Every GPU evaluates all camera samples whose filter footprint touches
 its tiles (halo recompute — free with a counter-addressable RNG), so a film pixel is produced by
-exactly one GPU with a summation order that does not depend on G.  The gather is a single
-reduce(SUM) of full-size film buffers whose non-owned pixels are exactly zero (x + 0 == x), issued
-on NCCL over NVLink/NVSwitch (gloo in the CPU tests)."""
+exactly one GPU with a summation order that does not depend on G.
+
+Two gathers exist.  `PeerFilm` (the default on GPUs): rank 0 owns the film buffer and shares it by
+CUDA IPC; every rank's film kernel stores its owned pixels straight into that buffer over
+NVLink/NVSwitch, so the only per-frame communication besides those stores is a barrier.
+`gather_film`: a single reduce(SUM) of full-size film buffers whose non-owned pixels are exactly
+zero (x + 0 == x), on NCCL (gloo in the CPU tests) — the portable fallback and the CPU-testable
+statement of the same result."""
+import ctypes as C
+
 import numpy as np
 
 
@@ -36,3 +43,47 @@ def gather_film(film_tensor, dist, dst=0):
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.reduce(film_tensor, dst=dst, op=dist.ReduceOp.SUM)
     return film_tensor
+
+
+class PeerFilm:
+    """Film buffer on rank 0's GPU that every rank writes its owned tiles into (CUDA IPC + NVLink
+    stores from k_film; include/pbrtb200.h pbrtb200_peer_film_*).  One process per GPU."""
+
+    def __init__(self, ctx, n_pixels, dist, device):
+        import torch
+        from ._ffi import lib
+        from .api import DevicePtr
+        self.ctx, self.dist = ctx, dist
+        self.rank = dist.get_rank()
+        handle = torch.zeros(64, dtype=torch.uint8, device=device)
+        p = C.c_void_p()
+        if self.rank == 0:
+            buf = C.create_string_buffer(64)
+            ctx.check(lib().pbrtb200_peer_film_create(ctx.h, n_pixels, C.byref(p), buf))
+            handle.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(handle, src=0)
+        self.opened = False
+        if self.rank != 0:
+            raw = bytes(handle.cpu().numpy().tobytes())
+            ctx.check(lib().pbrtb200_peer_film_open(ctx.h, raw, C.byref(p)))
+            self.opened = True
+        self.ptr = DevicePtr(p.value)
+        self.n_pixels = n_pixels
+
+    def tensor(self):
+        """Rank 0: the gathered film as a CUDA tensor view (n_pixels * 4 floats)."""
+        import torch
+        assert self.rank == 0
+
+        class _Holder:
+            pass
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (self.n_pixels * 4,), "typestr": "<f4", "data": (self.ptr.addr, False),
+                                      "version": 3, "strides": None}
+        return torch.as_tensor(h, device="cuda")
+
+    def close(self):
+        from ._ffi import lib
+        if self.opened:
+            lib().pbrtb200_peer_film_close(self.ctx.h, C.c_void_p(self.ptr.addr))
+            self.opened = False
