@@ -299,17 +299,33 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
   }
   // which sampler pixels are needed
   std::vector<uint8_t> need(n_ext, whole ? 1 : 0);
+  std::vector<uint8_t> owned(whole ? 0 : n_ext, 0);  // sampler pixel lies inside a rect of this call
   if (!whole) {
     for (size_t r = 0; r < rects.size() / 4; ++r) {
       const int32_t* q = &rects[4 * r];
+      for (int y = std::max(q[1], ext[2]); y < std::min(q[3], ext[3]); ++y)
+        for (int x = std::max(q[0], ext[0]); x < std::min(q[2], ext[1]); ++x)
+          owned[(size_t)(y - ext[2]) * sw + (size_t)(x - ext[0])] = 1;
       int qx0 = (int)std::ceil(((float)q[0] - 0.5f) - xw) - 1, qx1 = (int)std::floor(((float)(q[2] - 1) + 0.5f) + xw) + 1;
       int qy0 = (int)std::ceil(((float)q[1] - 0.5f) - yw) - 1, qy1 = (int)std::floor(((float)(q[3] - 1) + 0.5f) + yw) + 1;
       qx0 = std::max(qx0, ext[0]);
       qx1 = std::min(qx1, ext[1] - 1);
       qy0 = std::max(qy0, ext[2]);
       qy1 = std::min(qy1, ext[3] - 1);
-      for (int y = qy0; y <= qy1; ++y)
-        for (int x = qx0; x <= qx1; ++x) need[(size_t)(y - ext[2]) * sw + (size_t)(x - ext[0])] = 1;
+      // Within that padded range keep exactly the sampler pixels k_film will accept for some pixel
+      // of the rect: a sample of pixel p has image coordinate in [p, p + 1], and add_sample's
+      // extent arithmetic is monotonic, so it can only reach [ceil((p-0.5)-w), floor((p+0.5)+w)]
+      // (the same float expressions k_film evaluates).
+      auto reaches = [](int p, float w, int lo, int hi) {  // can pixel column/row p reach [lo, hi]?
+        const int a = pbh::sat_i32(std::ceil(((float)p - 0.5f) - w));
+        const int b = pbh::sat_i32(std::floor((((float)p + 1.0f) - 0.5f) + w));
+        return a <= hi && b >= lo;
+      };
+      for (int y = qy0; y <= qy1; ++y) {
+        if (!reaches(y, yw, q[1], q[3] - 1)) continue;
+        for (int x = qx0; x <= qx1; ++x)
+          if (reaches(x, xw, q[0], q[2] - 1)) need[(size_t)(y - ext[2]) * sw + (size_t)(x - ext[0])] = 1;
+      }
     }
   }
   std::vector<DPixel> list;
@@ -327,6 +343,7 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
           p.xy = (int32_t)(((uint32_t)(uint16_t)(int16_t)x) | ((uint32_t)(uint16_t)(int16_t)y << 16));
           p.k = k_of[e];
           p.task = task_of[e];
+          if (!whole && !owned[e]) p.task |= PB_PIXEL_HALO_BIT;
           index[e] = (int32_t)list.size();
           list.push_back(p);
         }
@@ -1123,6 +1140,11 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     ta.n = cn;
     ta.counter = &ctrl(ctx)->counter;
     ta.flags = &ctrl(ctx)->flags;
+    if (tiles && tiles->n_rects) {  // halo pixels that cannot reach an owned pixel are not traced
+      ta.pixels = ctx->d_pixels.as<DPixel>() + p0;
+      ta.edge = ctx->d_edge.as<uint32_t>() + p0;
+      ta.spp = (uint32_t)ds.spp;
+    }
     if (int rc = launch_trace_t<false, 1>(ctx, dc, ta)) return rc;
     size_t e2 = tm.mark();
     launches += 2;

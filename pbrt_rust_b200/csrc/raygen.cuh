@@ -71,7 +71,7 @@ k_raygen_groups(const DSampler smp, const RaygenArgs a) {
   const uint64_t p = gid / groups;
   const uint32_t g = (uint32_t)(gid - p * groups);
   const DPixel px = a.pixels[p];
-  const uint32_t* key = smp.task_keys + 8u * px.task;
+  const uint32_t* key = smp.task_keys + 8u * (px.task & PB_PIXEL_TASK_MASK);
   const uint64_t base = (uint64_t)px.k * smp.words_per_pixel;
   const uint32_t i0 = 8u * g, cnt = min(8u, spp - i0);
   const int pxx = px_x(px), pxy = px_y(px);
@@ -162,7 +162,7 @@ k_raygen_full(const DSampler smp, const RaygenArgs a) {
   float2* ln = a.lens + p * n;
   float* tm = a.time + p * n;
   WordStream ws;
-  ws.init(smp.task_keys + 8u * px.task, (uint64_t)px.k * smp.words_per_pixel);
+  ws.init(smp.task_keys + 8u * (px.task & PB_PIXEL_TASK_MASK), (uint64_t)px.k * smp.words_per_pixel);
   const float xpos = (float)px_x(px), ypos = (float)px_y(px);
   if (smp.kind == 0) {
     const uint32_t nx = (uint32_t)smp.xs, ny = (uint32_t)smp.ys;

@@ -60,8 +60,11 @@ struct DCamera {
 struct DPixel {
   int32_t xy;     // x | y << 16 (signed 16-bit each; sample extents can start at -radius)
   uint32_t k;     // raster index of the pixel inside its task window
-  uint32_t task;  // task index -> key
+  uint32_t task;  // task index -> key; bit 31: halo pixel (needed for the filter footprint of an
+                  // owned tile, not itself inside a tile this call renders)
 };
+#define PB_PIXEL_HALO_BIT 0x80000000u
+#define PB_PIXEL_TASK_MASK 0x7FFFFFFFu
 PB_DEV int px_x(DPixel p) { return (int)(short)(p.xy & 0xFFFF); }
 PB_DEV int px_y(DPixel p) { return (int)(short)((p.xy >> 16) & 0xFFFF); }
 

@@ -315,6 +315,12 @@ struct TraceArgs {
   unsigned long long* counter;  // work counter, zeroed by the host before launch
   uint32_t* flags;              // bit0: stack overflow happened
   uint32_t batch;               // 32-ray packets a warp claims per atomic (>= 1)
+  // SRC 1, tiled renders: a halo pixel whose samples all stay inside their own pixel (edge flag 0,
+  // set by raygen with add_sample's own arithmetic) cannot reach a pixel this call owns, so its
+  // rays are not traced (hit = MISS).  With the box filter that is practically every halo pixel.
+  const DPixel* __restrict__ pixels;   // may be NULL: trace everything
+  const uint32_t* __restrict__ edge;
+  uint32_t spp;
 };
 
 template <bool ANY, bool SPH, bool MULTI, int SRC, int MODE>
@@ -346,6 +352,13 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
         d = mk3(r1.x, r1.y, r1.z);
         maxt = r1.w;
       } else {
+        if (a.pixels) {
+          const uint64_t pix = idx / a.spp;
+          if ((__ldg(&a.pixels[pix].task) & PB_PIXEL_HALO_BIT) && __ldg(&a.edge[pix]) == 0u) {
+            reinterpret_cast<float4*>(a.hits)[idx] = make_float4(__uint_as_float(PBRTB200_MISS), 0.f, 0.f, 0.f);
+            continue;
+          }
+        }
         const float2 im = __ldg(a.img + idx);
         float2 ln = make_float2(0.f, 0.f);
         if (a.lens) ln = __ldg(a.lens + idx);
