@@ -416,7 +416,9 @@ def test_image_textures_ewa_and_trilinear(orc, tri, wrap, aniso):
     the oracle on the same scene.  Hit ids bit-exact; image within the float-edge tolerance
     (CUDA vs glibc expf/log2f/powf differ by ULPs inside the EWA weights and the level choice):
     RMSE <= 1e-5 linear RGB and <= 1e-4 relative error on >= 99.9 % of the pixels."""
-    cfg = scenes.textured(xres=200, yres=128, xs=2, ys=2, do_trilinear=tri, wrap=wrap, max_aniso=aniso)
+    # (small frames: at grazing angles the reference's lod choice — log2 of the UNSCALED minor axis,
+    # mipmap.rs:335 — makes single EWA lookups visit 10^6..10^8 texels; DESIGN.md §9 row 2)
+    cfg = scenes.textured(xres=120, yres=72, xs=2, ys=2, do_trilinear=tri, wrap=wrap, max_aniso=aniso)
     r = _renderer(cfg)
     film = r.render(cfg["scene"])
     osc = orc.OracleScene(cfg["scene"])
