@@ -432,3 +432,125 @@ def test_image_textures_ewa_and_trilinear(orc, tri, wrap, aniso):
     assert (rel.max(axis=-1) <= 1e-4).mean() >= 0.999, (rel.max(axis=-1) <= 1e-4).mean()
     # the textures are really in the picture: the ground is not one flat colour
     assert rgb_ref.std() > 0.02
+
+
+# ---- edge cases: empty / ragged / degenerate inputs --------------------------------------------
+
+def _edge_rays(rng, n):
+    """Rays that stress the slab / triangle arithmetic: axis-parallel directions (1/d = inf, 0*inf
+    NaNs in the slab test), negative zero components, origins on box planes, tiny and huge
+    directions, empty and inverted [mint, maxt] ranges, NaN components."""
+    rays = _rays_from(rng, n, -12, 12, 6.0)
+    k = n // 10
+    rays[0 * k:1 * k, 4] = 0.0                       # d.x = +0
+    rays[1 * k:2 * k, 5] = -0.0                      # d.y = -0
+    rays[2 * k:3 * k, 4:6] = 0.0                     # parallel to z
+    rays[3 * k:4 * k, 0:3] = np.round(rays[3 * k:4 * k, 0:3])  # origins on integer planes
+    rays[4 * k:5 * k, 4:7] *= np.float32(1e-20)      # tiny directions (1/d ~ 1e19)
+    rays[5 * k:6 * k, 4:7] *= np.float32(1e18)       # huge directions
+    rays[6 * k:7 * k, 7] = 0.0                       # maxt = 0
+    rays[7 * k:8 * k, 3] = 5.0
+    rays[7 * k:8 * k, 7] = 1.0                       # mint > maxt
+    rays[8 * k:8 * k + 5, 4] = np.nan                # NaN direction component
+    rays[8 * k + 5:8 * k + 10, 0] = np.nan           # NaN origin component
+    rays[8 * k + 10:8 * k + 15, 4:7] = 0.0           # zero direction
+    rays[9 * k:, 3] = 0.25                           # mint inside the scene
+    rays[9 * k:, 7] = 0.75
+    return rays
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 33, 4097])
+def test_trace_ragged_batch_sizes(orc, n):
+    """Empty, single-ray and non-multiple-of-32 batches through both trace hooks."""
+    cfg = scenes.config2(n=3000, xres=32, yres=32)
+    r = _renderer(cfg)
+    osc = orc.OracleScene(cfg["scene"])
+    rays = _rays_from(np.random.default_rng(n + 1), n, -30, 30) if n else np.zeros((0, 8), np.float32)
+    hits = r.intersect(cfg["scene"], rays)
+    occ = r.intersect_p(cfg["scene"], rays)
+    assert hits.shape == (n,) and occ.shape == (n,)
+    if n:
+        prim, tbb, _ = osc.trace_closest(rays)
+        oc, _ = osc.trace_any(rays)
+        assert np.array_equal(hits["prim"], prim) and np.array_equal(hits["t"].view(np.uint32), tbb[:, 0].view(np.uint32))
+        assert np.array_equal(occ, oc)
+
+
+@pytest.mark.parametrize("kind", ["triangles", "mixed"])
+def test_trace_degenerate_rays_bit_exact(orc, kind):
+    """Axis-parallel / zero / NaN / tiny / huge directions, empty ranges: ids and t bit-exact."""
+    cfg = scenes.config2(n=8000, xres=32, yres=32) if kind == "triangles" else scenes.config4(
+        n_ground=(40, 20), n_spheres=300, xres=32, yres=32, xs=1, ys=1)
+    r = _renderer(cfg)
+    osc = orc.OracleScene(cfg["scene"])
+    rays = _edge_rays(np.random.default_rng(99), 20000)
+    hits = r.intersect(cfg["scene"], rays)
+    prim, tbb, _ = osc.trace_closest(rays)
+    assert np.array_equal(hits["prim"], prim)
+    m = prim != pb.MISS
+    # rays with a NaN component "hit" with t = NaN on both sides (every comparison of the
+    # triangle test is false); NaN payload bits are not specified, everything else is bit-exact
+    nan = np.isnan(tbb[:, 0])
+    assert np.array_equal(np.isnan(hits["t"]), nan)
+    ok = m & ~nan
+    assert np.array_equal(hits["t"][ok].view(np.uint32), tbb[ok, 0].view(np.uint32))
+    occ = r.intersect_p(cfg["scene"], rays)
+    oc, _ = osc.trace_any(rays)
+    assert np.array_equal(occ, oc)
+    assert m.sum() > 500
+
+
+def test_degenerate_geometry(orc):
+    """Single-triangle scene (the root is a leaf), zero-area and duplicated triangles (coincident
+    centroids -> one leaf with more than 15 primitives, the leaf_count lookup path), rays that
+    start on a triangle."""
+    rng = np.random.default_rng(5)
+    one = pb.Shape.triangle_mesh(pb.Transform.new(), pb.Transform.new(), False, [0, 1, 2],
+                                 [[-1, -1, 2], [1, -1, 2], [0, 1, 2]])
+    mat = pb.Material.matte(pb.Texture.constant(0.5), pb.Texture.constant(0.0))
+    rays = _rays_from(rng, 2000, -2, 2, 1.0)
+    rays[:500, 0:3] = [0.0, -0.2, 2.0]  # origin exactly on the triangle's plane (t = 0 with mint = 0)
+    for prims, method in (([pb.Primitive.geometric(one, mat)], "sah"),):
+        scene = pb.Scene.new_with(pb.Primitive.bvh(prims, 1, method), [])
+        cfg = scenes.config1(xres=16, yres=16)
+        r = _renderer(cfg)
+        hits = r.intersect(scene, rays)
+        prim, tbb, _ = orc.OracleScene(scene).trace_closest(rays)
+        assert np.array_equal(hits["prim"], prim) and np.array_equal(hits["t"].view(np.uint32), tbb[:, 0].view(np.uint32))
+        assert (prim != pb.MISS).sum() > 50
+    # 40 copies of one triangle + zero-area triangles: centroid bounds are a point -> one big leaf
+    P = np.array([[-1, -1, 3], [1, -1, 3], [0, 1, 3]], np.float32)
+    vi = np.tile(np.arange(3, dtype=np.uint32), 40)
+    big = pb.Shape.triangle_mesh(pb.Transform.new(), pb.Transform.new(), False, vi, P)
+    Pz = np.array([[0, 0, 1], [0, 0, 1], [0, 0, 1], [1, 1, 1], [2, 2, 1], [3, 3, 1]], np.float32)  # point + collinear
+    zero = pb.Shape.triangle_mesh(pb.Transform.new(), pb.Transform.new(), False, [0, 1, 2, 3, 4, 5], Pz)
+    scene = pb.Scene.new_with(pb.Primitive.bvh([pb.Primitive.geometric(big, mat), pb.Primitive.geometric(zero, mat),
+                                                pb.Primitive.geometric(one, mat)], 4, "sah"), [])
+    r = _renderer(scenes.config1(xres=16, yres=16))
+    hits = r.intersect(scene, rays)
+    prim, tbb, _ = orc.OracleScene(scene).trace_closest(rays)
+    assert np.array_equal(hits["prim"], prim) and np.array_equal(hits["t"].view(np.uint32), tbb[:, 0].view(np.uint32))
+    occ = r.intersect_p(scene, rays)
+    oc, _ = orc.OracleScene(scene).trace_any(rays)
+    assert np.array_equal(occ, oc)
+
+
+def test_tiny_films_crops_and_lightless_scene(orc):
+    """1x1 film, a crop window that leaves a 3x2 film, a filter wider than the film (sample extent
+    starts at negative coordinates), and a scene without lights (black film, weights intact)."""
+    for kw in (dict(xres=1, yres=1), dict(xres=40, yres=30, crop=(0.3, 0.37, 0.5, 0.56))):
+        cfg = scenes.config1(**kw)
+        film = _renderer(cfg).render(cfg["scene"])
+        ref = orc.render(orc.OracleScene(cfg["scene"]), orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0))
+        assert film.shape == ref["film"].shape and film.size > 0
+        assert np.abs(pb.film_to_rgb(film) - ref["rgb"]).max() <= 1e-5
+        assert np.array_equal(film[..., 3].view(np.uint32), ref["film"][..., 3].view(np.uint32))
+    cfg = scenes.config1(xres=6, yres=4, filt=pb.Filter.gaussian(4.0, 4.0, 0.5))
+    film = _renderer(cfg).render(cfg["scene"])
+    ref = orc.render(orc.OracleScene(cfg["scene"]), orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0))
+    assert cfg["sampler"].ext[0] < 0
+    assert np.abs(pb.film_to_rgb(film) - ref["rgb"]).max() <= 1e-5
+    cfg = scenes.config1(xres=24, yres=16)
+    dark = pb.Scene.new_with(cfg["scene"].aggregate, [])
+    film = _renderer(cfg).render(dark)
+    assert np.all(film[..., :3] == 0.0) and film[..., 3].min() > 0
