@@ -50,10 +50,43 @@ struct Mesh {
 };
 
 // shape/sphere.rs:16-44
+// (Also carries the crate's other two quadrics, so that the primitive plumbing stays one type:
+// shape 1 = Cylinder (shape/cylinder.rs:17-38), shape 2 = Disk (shape/disk.rs:15-35).)
 struct Sphere {
   ShapeBase base;
   float radius, phi_max, z_min, z_max, theta_min, theta_max;
   uint32_t material = 0;
+  int shape = 0;                           // 0 sphere, 1 cylinder, 2 disk
+  float height = 0.f, inner_radius = 0.f;  // disk
+  struct CylinderTag {};
+  struct DiskTag {};
+  // Cylinder::new (cylinder.rs:27-38)
+  Sphere(CylinderTag, const Transform& o2w, const Transform& w2o, bool ro, float rad, float z0, float z1, float pm)
+      : base(o2w, w2o, ro) {
+    shape = 1;
+    radius = rad;
+    z_min = rmin(z0, z1);
+    z_max = rmax(z0, z1);
+    theta_min = theta_max = 0.f;
+    phi_max = as_radians(rclamp(pm, 0.0f, 360.0f));
+  }
+  // Disk::new (disk.rs:24-35)
+  Sphere(DiskTag, const Transform& o2w, const Transform& w2o, bool ro, float ht, float r, float ri, float tmax)
+      : base(o2w, w2o, ro) {
+    shape = 2;
+    height = ht;
+    radius = r;
+    inner_radius = ri;
+    z_min = z_max = ht;
+    theta_min = theta_max = 0.f;
+    phi_max = as_radians(rclamp(tmax, 0.0f, 360.0f));
+  }
+  // cylinder.rs:110-113 / disk.rs:83-87 / sphere.rs:119-121
+  float area() const {
+    if (shape == 1) return (z_max - z_min) * phi_max * radius;
+    if (shape == 2) return 0.5f * phi_max * (radius * radius - inner_radius * inner_radius);
+    return phi_max * radius * (z_max - z_min);
+  }
   Sphere(const Transform& o2w, const Transform& w2o, bool ro, float rad, float z0, float z1,
          float pm)
       : base(o2w, w2o, ro) {
@@ -67,7 +100,7 @@ struct Sphere {
     phi_max = as_radians(rclamp(pm, 0.0f, 360.0f));
   }
   // sphere.rs:112-117
-  BBox object_bound() const {
+  BBox object_bound() const {  // also cylinder.rs:104-108; disk.rs:77-81 (z = height on both corners)
     return BBox(V3(-radius, -radius, z_min), V3(radius, radius, z_max));
   }
   // sphere.rs:124-128
@@ -75,6 +108,8 @@ struct Sphere {
 
   // sphere.rs:46-107; `ray` already in object space.
   bool intersection_point(const Ray& ray, float* t_out, float* phi_out) const {
+    if (shape == 1) return cylinder_point(ray, t_out, phi_out);
+    if (shape == 2) return disk_point(ray, t_out, phi_out);
     float a = length_squared(ray.d);
     float b = 2.0f * dot(ray.d, ray.o);
     float c = length_squared(ray.o) - radius * radius;
@@ -109,6 +144,57 @@ struct Sphere {
     }
     *t_out = t_hit;
     *phi_out = ang;
+    return true;
+  }
+  // cylinder.rs:40-100
+  bool cylinder_point(const Ray& r, float* t_out, float* phi_out) const {
+    float a = r.d.x * r.d.x + r.d.y * r.d.y;
+    float b = 2.0f * (r.d.x * r.o.x + r.d.y * r.o.y);
+    float c = r.o.x * r.o.x + r.o.y * r.o.y - radius * radius;
+    float t0, t1;
+    if (!quadratic(a, b, c, &t0, &t1)) return false;
+    if (t0 > r.maxt || t1 < r.mint) return false;
+    float t_hit = t0;
+    if (t0 < r.mint) {
+      t_hit = t1;
+      if (t_hit > r.maxt) return false;
+    }
+    auto get_hit = [&](float t, V3* hit, float* angle) {
+      V3 h = r.at(t);
+      if (h.x == 0.0f && h.y == 0.0f) h.x = 1e-5f * radius;
+      float ang = std::atan2(h.y, h.x);
+      if (ang < 0.0f) ang = ang + 2.0f * PI_F;
+      *hit = h;
+      *angle = ang;
+    };
+    auto invalid = [&](const V3& h, float ang) { return h.z < z_min || h.z > z_max || ang > phi_max; };
+    V3 h;
+    float ang;
+    get_hit(t_hit, &h, &ang);
+    if (invalid(h, ang)) {
+      if (t_hit == t1) return false;
+      if (t1 > r.maxt) return false;
+      t_hit = t1;
+      get_hit(t_hit, &h, &ang);
+      if (invalid(h, ang)) return false;
+    }
+    *t_out = t_hit;
+    *phi_out = ang;
+    return true;
+  }
+  // disk.rs:37-71
+  bool disk_point(const Ray& r, float* t_out, float* phi_out) const {
+    if (std::fabs(r.d.z) < 1e-6f) return false;
+    float t_hit = (height - r.o.z) / r.d.z;
+    if (t_hit < r.mint || t_hit > r.maxt) return false;
+    V3 p_hit = r.at(t_hit);
+    float dist2 = p_hit.x * p_hit.x + p_hit.y * p_hit.y;
+    if (dist2 > (radius * radius) || dist2 < (inner_radius * inner_radius)) return false;
+    float a = std::atan2(p_hit.y, p_hit.x);
+    float phi = a < 0.0f ? a + 2.0f * PI_F : a;
+    if (phi > phi_max) return false;
+    *t_out = t_hit;
+    *phi_out = phi;
     return true;
   }
 };

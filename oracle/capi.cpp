@@ -95,6 +95,26 @@ int orc_add_sphere(OrcScene* s, const float* o2w, const float* o2w_inv, int ro, 
     s->sc.geom.add_sphere(std::move(sp));
   });
 }
+// Primitive::geometric(Shape::cylinder(o2w, w2o, ro, rad, z0, z1, phi_max), material) and
+// Shape::disk(o2w, w2o, ro, height, radius, inner_radius, phi_max)   (shape/mod.rs)
+int orc_add_cylinder(OrcScene* s, const float* o2w, const float* o2w_inv, int ro, float rad, float z0, float z1,
+                     float pm, uint32_t material) {
+  return guarded([&] {
+    Transform t = xf_from(o2w, o2w_inv);
+    auto sp = std::make_unique<Sphere>(Sphere::CylinderTag{}, t, t.inverse(), ro != 0, rad, z0, z1, pm);
+    sp->material = material;
+    s->sc.geom.add_sphere(std::move(sp));
+  });
+}
+int orc_add_disk(OrcScene* s, const float* o2w, const float* o2w_inv, int ro, float ht, float r, float ri,
+                 float pm, uint32_t material) {
+  return guarded([&] {
+    Transform t = xf_from(o2w, o2w_inv);
+    auto sp = std::make_unique<Sphere>(Sphere::DiskTag{}, t, t.inverse(), ro != 0, ht, r, ri, pm);
+    sp->material = material;
+    s->sc.geom.add_sphere(std::move(sp));
+  });
+}
 int orc_add_texture(OrcScene* s, int kind, const float* value, int map_kind, const float* map8,
                     int tex1, int tex2, int aa) {
   Texture t;
@@ -481,6 +501,37 @@ int orc_sphere_intersect(const float* o2w, const float* o2w_inv, int ro, float r
                          float z1, float pm, const float* r, float* out3, float* dg14) {
   Transform t = xf_from(o2w, o2w_inv);
   Sphere s(t, t.inverse(), ro != 0, rad, z0, z1, pm);
+  Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3]);
+  ray.maxt = r[7];
+  Ray oray = xf_ray(s.base.w2o, ray);
+  float th, phi;
+  if (!s.intersection_point(oray, &th, &phi)) return 0;
+  out3[0] = th;
+  out3[1] = th * 5e-4f;
+  out3[2] = phi;
+  if (dg14) {
+    DiffGeom dg = sphere_dg(s, ray, th, phi);
+    float v[14] = {dg.p.x, dg.p.y, dg.p.z, dg.nn.x, dg.nn.y, dg.nn.z, dg.u, dg.v,
+                   dg.dpdu.x, dg.dpdu.y, dg.dpdu.z, dg.dpdv.x, dg.dpdv.y, dg.dpdv.z};
+    std::memcpy(dg14, v, sizeof v);
+  }
+  return 1;
+}
+// Known-answer hook for Cylinder (shape 1: a, b, c = rad, z0, z1) and Disk (shape 2: a, b, c =
+// height, radius, inner_radius): out3 = t_hit, ray_epsilon, phi; dg14 as orc_sphere_intersect;
+// props13 = radius, z_min, z_max, phi_max, height, inner_radius, area, object bound min xyz, max xyz.
+int orc_quadric_intersect(int shape, const float* o2w, const float* o2w_inv, int ro, float a, float b, float c,
+                          float pm, const float* r, float* out3, float* dg14, float* props13) {
+  Transform t = xf_from(o2w, o2w_inv);
+  Sphere s = shape == 1 ? Sphere(Sphere::CylinderTag{}, t, t.inverse(), ro != 0, a, b, c, pm)
+                        : Sphere(Sphere::DiskTag{}, t, t.inverse(), ro != 0, a, b, c, pm);
+  if (props13) {
+    BBox ob = s.object_bound();
+    float v[13] = {s.radius, s.z_min, s.z_max, s.phi_max, s.height, s.inner_radius, s.area(),
+                   ob.p_min.x, ob.p_min.y, ob.p_min.z, ob.p_max.x, ob.p_max.y, ob.p_max.z};
+    std::memcpy(props13, v, sizeof v);
+  }
+  if (!r) return 0;
   Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3]);
   ray.maxt = r[7];
   Ray oray = xf_ray(s.base.w2o, ray);

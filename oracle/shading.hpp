@@ -390,7 +390,50 @@ inline DiffGeom tri_dg(const Prim& pr, const Ray& r, float t, float b1, float b2
   return DiffGeom(r.at(t), dpdu, dpdv, V3(), V3(), tu, tv, &m.base);
 }
 
+// helpers.rs:17-43
+inline DiffGeom compute_dg(const ShapeBase& base, float u, float v, const V3& p_hit, const V3& dpdu, const V3& dpdv,
+                           const V3& d2pduu, const V3& d2pduv, const V3& d2pdvv) {
+  float ee = dot(dpdu, dpdu), ff = dot(dpdu, dpdv), gg = dot(dpdv, dpdv);
+  V3 nn = normalize(cross(dpdu, dpdv));
+  float e = dot(nn, d2pduu), f = dot(nn, d2pduv), g = dot(nn, d2pdvv);
+  float inveeggff2 = 1.0f / (ee * gg - ff * ff);
+  V3 dndu = (f * ff - e * gg) * inveeggff2 * dpdu + (e * ff - f * ee) * inveeggff2 * dpdv;
+  V3 dndv = (g * ff - f * gg) * inveeggff2 * dpdu + (f * ff - g * ee) * inveeggff2 * dpdv;
+  const Transform& o2w = base.o2w;
+  return DiffGeom(o2w.pt(p_hit), o2w.vec(dpdu), o2w.vec(dpdv), o2w.nrm(dndu), o2w.nrm(dndv), u, v, &base);
+}
+
+// Cylinder::intersect dg part (cylinder.rs:127-154)
+inline DiffGeom cylinder_dg(const Sphere& s, const Ray& world_ray, float t_hit, float phi) {
+  Ray ray = xf_ray(s.base.w2o, world_ray);
+  V3 p_hit = ray.at(t_hit);
+  float u = phi / s.phi_max;
+  float v = (p_hit.z - s.z_min) / (s.z_max - s.z_min);
+  V3 dpdu = s.phi_max * V3(-p_hit.y, p_hit.x, 0.0f);
+  V3 dpdv(0.0f, 0.0f, s.z_max - s.z_min);
+  V3 d2pduu = -s.phi_max * s.phi_max * V3(p_hit.x, p_hit.y, 0.0f);
+  return compute_dg(s.base, u, v, p_hit, dpdu, dpdv, d2pduu, V3(), V3());
+}
+
+// Disk::intersect dg part (disk.rs:107-133); nn is overwritten from the OBJECT-space ray origin's
+// z against 0 (not against the disk height), exactly as written.
+inline DiffGeom disk_dg(const Sphere& s, const Ray& world_ray, float t_hit, float phi) {
+  Ray ray = xf_ray(s.base.w2o, world_ray);
+  V3 p_hit = ray.at(t_hit);
+  float u = phi / s.phi_max;
+  float dist = std::sqrt(p_hit.x * p_hit.x + p_hit.y * p_hit.y);
+  float v = 1.0f - (dist - s.inner_radius) / (s.radius - s.inner_radius);
+  V3 dpdu = (s.phi_max / (2.0f * PI_F)) * V3(-s.phi_max * p_hit.y, s.phi_max * p_hit.x, 0.0f);
+  V3 dpdv = ((s.inner_radius - s.radius) / dist) * V3(p_hit.x, p_hit.y, 0.0f);
+  const Transform& o2w = s.base.o2w;
+  DiffGeom dg(o2w.pt(p_hit), o2w.vec(dpdu), o2w.vec(dpdv), o2w.nrm(V3()), o2w.nrm(V3()), u, v, &s.base);
+  dg.nn = ray.o.z > 0.0f ? o2w.nrm(V3(0.0f, 0.0f, 1.0f)) : o2w.nrm(V3(0.0f, 0.0f, -1.0f));
+  return dg;
+}
+
 inline DiffGeom sphere_dg(const Sphere& s, const Ray& world_ray, float t_hit, float phi) {
+  if (s.shape == 1) return cylinder_dg(s, world_ray, t_hit, phi);
+  if (s.shape == 2) return disk_dg(s, world_ray, t_hit, phi);
   Ray ray = xf_ray(s.base.w2o, world_ray);
   V3 p_hit = ray.at(t_hit);
   float u = phi / s.phi_max;

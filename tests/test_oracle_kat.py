@@ -667,3 +667,125 @@ def test_mipmap_structure_and_unreadable_file(orc):
     L = orc.lib()
     assert [L.orc_modulo(a, 4) for a in (-5, -4, -1, 0, 3, 4, 9)] == [3, 0, 3, 0, 3, 0, 1]  # utils/mod.rs:219-223
     assert L.orc_sinc_1d(0.0, 2.0) == 1.0 and L.orc_sinc_1d(1.0, 2.0) == 0.0
+
+
+# ---- Disk and Cylinder ("next" row 4): shape/disk.rs:139-305, shape/cylinder.rs:156-352 ---------
+
+def _quadric(orc, shape, o2w, o2w_inv, a, b, c, pm, ray=None):
+    """shape 1 = Cylinder(rad, z0, z1), 2 = Disk(height, radius, inner_radius).  Returns
+    (hit, out3, dg14, props13)."""
+    L = orc.lib()
+    L.orc_quadric_intersect.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    out3, dg, props = np.zeros(3, np.float32), np.zeros(14, np.float32), np.zeros(13, np.float32)
+    ok = L.orc_quadric_intersect(shape, _p(o2w), _p(o2w_inv), 0, a, b, c, pm, None if ray is None else _p(ray),
+                                 _p(out3), _p(dg), _p(props))
+    return bool(ok), out3, dg, props
+
+
+def _xf(orc, kind, a3):
+    m, mi = np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32)
+    orc.lib().orc_transform(kind, _p(np.array(a3, np.float32)), _p(m), _p(mi))
+    return m, mi
+
+
+def test_disk_creation_bounds_area(orc):
+    """disk.rs:152-188 (creation, object bounds), :285-304 (areas)"""
+    I = _ident()
+    _, _, _, p = _quadric(orc, 2, I, I, 0.0, 1.0, 0.5, 360.0)
+    assert p[4] == 0.0 and p[0] == 1.0 and p[5] == 0.5 and p[3] == f32(2.0) * f32(math.pi)
+    assert p[7:13].tolist() == [-1.0, -1.0, 0.0, 1.0, 1.0, 0.0]
+    m, mi = _xf(orc, 1, [1.0, 2.0, 3.0])
+    _, _, _, p = _quadric(orc, 2, m, mi, 2.0, 0.0, 1.0, 90.0)
+    assert p[4] == 2.0 and p[0] == 0.0 and p[5] == 1.0 and p[3] == f32(0.5) * f32(math.pi)
+    assert p[7:13].tolist() == [0.0, 0.0, 2.0, 0.0, 0.0, 2.0]
+    area = lambda ht, r, ri, pm: _quadric(orc, 2, I, I, ht, r, ri, pm)[3][6]
+    assert area(0.0, 1.0, 0.0, 360.0) == f32(math.pi) and area(2381.0, 1.0, 0.0, 360.0) == f32(math.pi)
+    assert area(0.0, 1.0, 0.0, 180.0) == f32(0.5) * f32(math.pi)
+    assert area(0.0, 1.0, float(np.sqrt(f32(0.5))), 360.0) == f32(0.5) * f32(math.pi)
+
+
+def test_disk_can_be_intersected(orc):
+    """disk.rs:190-246"""
+    I = _ident()
+    down = lambda o: _ray(o, [0.0, 0.0, -1.0])
+    hit = lambda *a, **k: _quadric(orc, 2, *a, **k)[0]
+    assert hit(I, I, 0.0, 1.0, 0.0, 360.0, ray=down([0, 0, 1]))
+    assert not hit(I, I, 0.0, 1.0, 0.0, 360.0, ray=down([2, 2, 1]))
+    assert not hit(I, I, 0.0, 1.0, 0.5, 360.0, ray=down([0, 0, 1]))     # through the hole
+    assert not hit(I, I, 2.0, 1.0, 0.0, 360.0, ray=down([0, 0, 1]))     # starts behind the disk
+    assert hit(I, I, 0.0, 0.75, 0.25, 180.0, ray=down([0, 0.5, 1]))     # half pipe: top half
+    assert not hit(I, I, 0.0, 0.75, 0.25, 180.0, ray=down([0, -0.5, 1]))
+    m, mi = _xf(orc, 4, [180.0, 0, 0])                                  # rotate_z(180)
+    assert not hit(m, mi, 0.0, 0.75, 0.25, 180.0, ray=down([0, 0.5, 1]))
+    assert hit(m, mi, 0.0, 0.75, 0.25, 180.0, ray=down([0, -0.5, 1]))
+    assert not hit(m, mi, 0.0, 0.75, 0.25, 180.0, ray=_ray([1.0, 10.5, 140.0], [-1.0, -10.5, -140.0]))
+
+
+def test_disk_intersection_info(orc):
+    """disk.rs:248-283"""
+    I = _ident()
+    ok, o3, dg, _ = _quadric(orc, 2, I, I, 0.0, 1.0, 0.0, 360.0, ray=_ray([0, 0, 1], [0, 0, -1]))
+    assert ok and o3[0] == 1.0 and o3[1] == f32(5e-4)
+    assert dg[0:3].tolist() == [0.0, 0.0, 0.0] and dg[3:6].tolist() == [0.0, 0.0, 1.0]
+    ok, o3, dg, _ = _quadric(orc, 2, I, I, 0.0, 0.75, 0.25, 180.0, ray=_ray([0, 0.5, 1], [0, 0, -1]))
+    assert ok and o3[0] == 1.0 and o3[1] == f32(5e-4)
+    assert dg[0:3].tolist() == [0.0, 0.5, 0.0] and dg[3:6].tolist() == [0.0, 0.0, 1.0]
+    assert dg[6] == 0.5 and dg[7] == 0.5
+
+
+def test_cylinder_creation_bounds_area(orc):
+    """cylinder.rs:171-205 (creation, bounds ignore transform and phi_max), :335-351 (areas)"""
+    m, mi = _translate([1.0, 2.0, 3.0])
+    _, _, _, p = _quadric(orc, 1, m, mi, 3.2, 14.0, -3.0, 16.0)
+    assert p[0] == f32(3.2) and p[1] == -3.0 and p[2] == 14.0 and p[3] == f32(np.deg2rad(np.float64(16.0)))
+    I = _ident()
+    for o2w, pm in ((_ident(), 360.0), (_xf(orc, 1, [2.0, 3.0, 0.2])[0], 360.0), (_ident(), 180.0)):
+        oi = np.zeros((4, 4), np.float32)
+        assert orc.lib().orc_invert(_p(o2w), _p(oi)) == 0
+        _, _, _, p = _quadric(orc, 1, o2w, oi, 0.5, -2.0, -1.0, pm)
+        assert p[7:13].tolist() == [-0.5, -0.5, -2.0, 0.5, 0.5, -1.0]
+    inv_pi = float(f32(1.0) / f32(math.pi))
+    area = lambda o2w, oi, r, z0, z1, pm: _quadric(orc, 1, o2w, oi, r, z0, z1, pm)[3][6]
+    assert area(I, I, inv_pi, 0.0, 1.0, 360.0) == 2.0 and area(I, I, inv_pi, 0.0, 1.0, 180.0) == 1.0
+    s, si = _xf(orc, 1, [1.0, 2.0, 0.5])
+    assert area(s, si, inv_pi, 0.0, 1.0, 360.0) == 2.0
+    assert area(s, si, 0.0, 0.0, 1.0, 360.0) == 0.0 and area(s, si, 1.0, 0.0, 0.0, 360.0) == 0.0
+
+
+def test_cylinder_can_be_intersected(orc):
+    """cylinder.rs:207-303"""
+    I = _ident()
+    hit = lambda *a, **k: _quadric(orc, 1, *a, **k)[0]
+    simple = lambda o, d: hit(I, I, 0.5, -1.0, 1.0, 360.0, ray=_ray(o, d))
+    assert simple([1, 1, 1], [-1, -1, -1])
+    assert not simple([1, 1, 1], [0, 0, -1])
+    assert not simple([1, 1, 2], [-1, -1, 0])
+    assert not simple([-1, 1, -2], [1, -1, 0])
+    assert not simple([0.1, 0.1, -2], [0, 0, 1])            # down the middle
+    assert simple([0.1, 0.1, -2], [-0.4, -0.4, 1.5])        # from the inside
+    m, mi = _translate([1.0, 2.0, 3.0])
+    partial = lambda o, d: hit(m, mi, 1.0, -3.0, 0.0, 90.0, ray=_ray(o, d))
+    assert partial([2.0, 4.0, 1.5], [-1, -1, 0])
+    assert not partial([1.0, 2.0, 1.5], [-1, -1, 0])
+    assert partial([1.0, 2.0, 1.5], [1, 1, 0])
+    assert not partial([2.5, 2.5, 10.0], [-1, -1, -10])     # barely misses
+    for pm in (360.0, 0.1, 0.0, -1.0):                      # zero radius, tiny / zero / negative phi_max
+        assert hit(I, I, 0.0, -1.0, 1.0, pm, ray=_ray([1, 1, -0.5], [-1, -1, 0]))
+    assert hit(I, I, 0.0, 0.0, 0.0, 360.0, ray=_ray([1, 1, 1], [-1, -1, -1]))
+    assert not hit(I, I, 0.0, -1.0, -1.0, 360.0, ray=_ray([1, 1, 1], [-1, -1, -1]))
+
+
+def test_cylinder_intersection_information(orc):
+    """cylinder.rs:305-333"""
+    m, mi = _xf(orc, 3, [90.0, 0, 0])  # rotate_y(90)
+    d = np.array([0.0, -1.0, -1.0], np.float32)
+    d = d * (f32(1.0) / np.sqrt(f32(2.0)))
+    ok, o3, dg, _ = _quadric(orc, 1, m, mi, 1.0, -1.0, 1.0, 180.0, ray=_ray([0, 1, 1], d.tolist()))
+    s2 = math.sqrt(2.0)
+    assert ok and abs(o3[0] - (s2 - 1.0)) < 1e-6 and abs(o3[1] - (s2 - 1.0) * 5e-4) < 1e-6
+    assert np.sum((dg[0:3] - np.array([0.0, s2 / 2, s2 / 2])) ** 2) < 1e-6
+    assert np.sum((dg[3:6] - np.array([0.0, 1.0, 1.0]) / s2) ** 2) < 1e-6
+    assert dg[6] == 0.75 and abs(dg[7] - 0.5) < 1e-6
+    assert np.sum((dg[8:11] - np.array([0.0, -math.pi * s2 / 2, math.pi * s2 / 2])) ** 2) < 1e-6
+    assert np.sum((dg[11:14] - np.array([2.0, 0.0, 0.0])) ** 2) < 1e-6
