@@ -63,12 +63,20 @@ typedef struct {
   uint32_t user;   /* caller's id for this triangle (e.g. Rust prim_id); echoed, never read */
 } pbrtb200_tri48;
 
-/* One Sphere (src/shape/sphere.rs:17-25): world-to-object rows 0..2 of the 4x4 (affine) + params */
+/* One quadric: Sphere (src/shape/sphere.rs:17-25), Cylinder (src/shape/cylinder.rs:17-24) or Disk
+ * (src/shape/disk.rs:15-22): world-to-object rows 0..2 of the 4x4 (affine) + params.
+ *   sphere   : radius, z_min, z_max, phi_max, theta_min, theta_max
+ *   cylinder : radius, z_min, z_max, phi_max                       (theta_* unused)
+ *   disk     : radius, z_min = z_max = height, phi_max, theta_min = inner_radius              */
+#define PBRTB200_QUADRIC_SPHERE 0u
+#define PBRTB200_QUADRIC_CYLINDER 1u
+#define PBRTB200_QUADRIC_DISK 2u
+#define PBRTB200_QUADRIC_KIND_SHIFT 8 /* kind lives in bits 8..9 of `flip` */
 typedef struct {
   float w2o[12];
   float radius, z_min, z_max, phi_max, theta_min, theta_max;
   uint32_t material;
-  uint32_t flip;   /* reverse_orientation ^ transform_swaps_handedness */
+  uint32_t flip;   /* bit 0: reverse_orientation ^ transform_swaps_handedness; bits 8..9: kind */
 } pbrtb200_sphere80;
 
 /* Per-mesh shading data (ShapeBase of the mesh, src/shape/mod.rs:33-54) */

@@ -66,6 +66,13 @@ int pbh_add_triangle_mesh(pbh_scene* s, const float o2w[16], const float o2w_inv
                           const uint32_t* vi, uint64_t n_vi, const float* P, uint64_t n_p,
                           const float* N, const float* S, const float* UV, int material,
                           int area_light);
+/* Primitive::geometric(Shape::cylinder(o2w, w2o, ro, rad, z0, z1, phi_max_deg), material)
+ * (src/shape/cylinder.rs:27-38) and Shape::disk(o2w, w2o, ro, height, radius, inner_radius,
+ * phi_max_deg) (src/shape/disk.rs:24-35).  Return the object ordinal.                          */
+int pbh_add_cylinder(pbh_scene* s, const float o2w[16], const float o2w_inv[16], int ro, float rad,
+                     float z0, float z1, float phi_max_deg, int material);
+int pbh_add_disk(pbh_scene* s, const float o2w[16], const float o2w_inv[16], int ro, float height,
+                 float radius, float inner_radius, float phi_max_deg, int material);
 /* Primitive::geometric(Shape::sphere(o2w, w2o, ro, rad, z0, z1, phi_max_deg), material) */
 int pbh_add_sphere(pbh_scene* s, const float o2w[16], const float o2w_inv[16], int ro, float rad,
                    float z0, float z1, float phi_max_deg, int material);

@@ -70,6 +70,8 @@ def lib():
         L.orc_sphere_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, f32, f32, f32, f32, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
         L.orc_add_sphere.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, f32, f32, f32, f32, u32]
+        L.orc_add_cylinder.argtypes = L.orc_add_sphere.argtypes
+        L.orc_add_disk.argtypes = L.orc_add_sphere.argtypes
         L.orc_add_spot_light.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, f32, f32]
         L.orc_get_crop_window.argtypes = [u64, u64, f32, C.c_void_p]
         L.orc_film_extents.argtypes = [C.c_int, C.c_int, f32, f32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -207,6 +209,12 @@ class OracleScene:
             if s.kind == "sphere":
                 _ck(L.orc_add_sphere(self.h, _p(_f(s.o2w.m)), _p(_f(s.o2w.m_inv)), int(s.ro), s.rad, s.z0,
                                      s.z1, s.pm, m))
+            elif s.kind == "cylinder":
+                _ck(L.orc_add_cylinder(self.h, _p(_f(s.o2w.m)), _p(_f(s.o2w.m_inv)), int(s.ro), s.rad, s.z0,
+                                       s.z1, s.pm, m))
+            elif s.kind == "disk":
+                _ck(L.orc_add_disk(self.h, _p(_f(s.o2w.m)), _p(_f(s.o2w.m_inv)), int(s.ro), s.height, s.rad,
+                                   s.ri, s.pm, m))
             else:
                 al = -1 if p.area_light is None else light_ids[id(p.area_light)]
                 _ck(L.orc_add_mesh(self.h, _p(_f(s.o2w.m)), _p(_f(s.o2w.m_inv)), int(s.ro), _p(s.vi),

@@ -141,6 +141,8 @@ SYMBOLS = [
     ("pbh_add_triangle_mesh", i32, [_vp, _fp, _fp, C.c_int, P(u32), u64, _fp, u64, _fp, _fp, _fp,
                                     C.c_int, C.c_int]),
     ("pbh_add_sphere", i32, [_vp, _fp, _fp, C.c_int, f32, f32, f32, f32, C.c_int]),
+    ("pbh_add_cylinder", i32, [_vp, _fp, _fp, C.c_int, f32, f32, f32, f32, C.c_int]),
+    ("pbh_add_disk", i32, [_vp, _fp, _fp, C.c_int, f32, f32, f32, f32, C.c_int]),
     ("pbh_build_bvh", i32, [_vp, u32, C.c_char_p]),
     ("pbh_flat_scene", P(Scene), [_vp]),
     ("pbh_prim_order", None, [_vp, P(u32)]),

@@ -165,6 +165,16 @@ class Shape:
         return Shape("sphere", o2w, w2o, ro, rad=rad, z0=z0, z1=z1, pm=pm)
 
     @staticmethod
+    def cylinder(o2w, w2o, ro, rad, z0, z1, pm):
+        """Shape::cylinder (src/shape/cylinder.rs:27-38)"""
+        return Shape("cylinder", o2w, w2o, ro, rad=rad, z0=z0, z1=z1, pm=pm)
+
+    @staticmethod
+    def disk(o2w, w2o, ro, height, radius, inner_radius, pm):
+        """Shape::disk (src/shape/disk.rs:24-35)"""
+        return Shape("disk", o2w, w2o, ro, height=height, rad=radius, ri=inner_radius, pm=pm)
+
+    @staticmethod
     def triangle_mesh(o2w, w2o, ro, vi, P, N=None, S=None, uv=None):
         vi = np.ascontiguousarray(vi, dtype=np.uint32).reshape(-1)
         P = _f(P).reshape(-1, 3)
@@ -395,6 +405,10 @@ class HostScene:
             m = mat(p.material) if p.material is not None else 0
             if s.kind == "sphere":
                 rc = L.pbh_add_sphere(self.h, _fp(_f(s.o2w.m)), _fp(_f(s.o2w.m_inv)), int(s.ro), s.rad, s.z0, s.z1, s.pm, m)
+            elif s.kind == "cylinder":
+                rc = L.pbh_add_cylinder(self.h, _fp(_f(s.o2w.m)), _fp(_f(s.o2w.m_inv)), int(s.ro), s.rad, s.z0, s.z1, s.pm, m)
+            elif s.kind == "disk":
+                rc = L.pbh_add_disk(self.h, _fp(_f(s.o2w.m)), _fp(_f(s.o2w.m_inv)), int(s.ro), s.height, s.rad, s.ri, s.pm, m)
             else:
                 al = -1 if p.area_light is None else self.light_ids[id(p.area_light)]
                 npn = lambda a: None if a is None else _fp(a)

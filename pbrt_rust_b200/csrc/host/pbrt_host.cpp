@@ -160,11 +160,12 @@ struct MeshRec {
   std::vector<float> n, s, uv;
   int material, area_light;
 };
-struct SphereRec {
+struct SphereRec {  // a quadric: sphere, cylinder or disk (include/pbrtb200.h)
   Mat o2w, o2w_inv;
   bool ro;
   float radius, z_min, z_max, phi_max, theta_min, theta_max;
   int material;
+  uint32_t kind = PBRTB200_QUADRIC_SPHERE;
 };
 struct Object {
   int kind;  // 0 mesh, 1 sphere
@@ -871,6 +872,46 @@ int pbh_add_sphere(pbh_scene* s, const float o2w[16], const float o2w_inv[16], i
   return (int)s->objects.size() - 1;
 }
 
+int pbh_add_cylinder(pbh_scene* s, const float o2w[16], const float o2w_inv[16], int ro, float rad,
+                     float z0, float z1, float pm, int material) {
+  auto clampf = [](float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); };
+  SphereRec r;
+  std::memcpy(r.o2w, o2w, 64);
+  std::memcpy(r.o2w_inv, o2w_inv, 64);
+  r.ro = ro != 0;
+  r.kind = PBRTB200_QUADRIC_CYLINDER;  // cylinder.rs:27-38
+  r.radius = rad;
+  r.z_min = std::fmin(z0, z1);
+  r.z_max = std::fmax(z0, z1);
+  r.theta_min = r.theta_max = 0.0f;
+  r.phi_max = radians(clampf(pm, 0.0f, 360.0f));
+  r.material = material;
+  s->objects.push_back({1, (uint32_t)s->spheres.size()});
+  s->spheres.push_back(r);
+  s->built = false;
+  return (int)s->objects.size() - 1;
+}
+
+int pbh_add_disk(pbh_scene* s, const float o2w[16], const float o2w_inv[16], int ro, float height,
+                 float radius, float inner_radius, float pm, int material) {
+  auto clampf = [](float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); };
+  SphereRec r;
+  std::memcpy(r.o2w, o2w, 64);
+  std::memcpy(r.o2w_inv, o2w_inv, 64);
+  r.ro = ro != 0;
+  r.kind = PBRTB200_QUADRIC_DISK;  // disk.rs:24-35
+  r.radius = radius;
+  r.z_min = r.z_max = height;  // object bound (-r, -r, h)..(r, r, h), disk.rs:77-81
+  r.theta_min = inner_radius;
+  r.theta_max = 0.0f;
+  r.phi_max = radians(clampf(pm, 0.0f, 360.0f));
+  r.material = material;
+  s->objects.push_back({1, (uint32_t)s->spheres.size()});
+  s->spheres.push_back(r);
+  s->built = false;
+  return (int)s->objects.size() - 1;
+}
+
 int pbh_build_bvh(pbh_scene* s, uint32_t max_prims, const char* split_method) {
   s->built = false;
   s->err.clear();
@@ -970,7 +1011,7 @@ int pbh_build_bvh(pbh_scene* s, uint32_t max_prims, const char* split_method) {
     f.theta_min = r.theta_min;
     f.theta_max = r.theta_max;
     f.material = (uint32_t)std::max(r.material, 0);
-    f.flip = (r.ro ^ swaps_handedness(r.o2w)) ? 1u : 0u;
+    f.flip = ((r.ro ^ swaps_handedness(r.o2w)) ? 1u : 0u) | (r.kind << PBRTB200_QUADRIC_KIND_SHIFT);
     sphere_slot[o] = (uint32_t)s->fspheres.size();
     s->fspheres.push_back(f);
     float rows[12];

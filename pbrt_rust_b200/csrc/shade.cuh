@@ -195,6 +195,36 @@ PB_DEV DG sphere_dg(const pbrtb200_sphere80& s, const float* o2w, f3 ow, f3 dw, 
   const f3 o = xf_pt(s.w2o, ow), d = xf_vec(s.w2o, dw);
   const f3 p_hit = o + (d * t_hit);
   const float u = phi / s.phi_max;
+  const bool flip = (s.flip & 1u) != 0;
+  const uint32_t kind = (s.flip >> PBRTB200_QUADRIC_KIND_SHIFT) & 3u;
+  if (kind == PBRTB200_QUADRIC_DISK) {  // disk.rs:107-133 (z_min = height, theta_min = inner radius)
+    const float inner = s.theta_min;
+    const float dist = sqrtf(p_hit.x * p_hit.x + p_hit.y * p_hit.y);
+    const float v = 1.0f - (dist - inner) / (s.radius - inner);
+    const f3 dpdu = (s.phi_max / (2.0f * PB_PI)) * mk3(-s.phi_max * p_hit.y, s.phi_max * p_hit.x, 0.0f);
+    const f3 dpdv = ((inner - s.radius) / dist) * mk3(p_hit.x, p_hit.y, 0.0f);
+    const f3 zero = mk3(0.f, 0.f, 0.f);
+    DG g = dg_new(xf_pt(o2w, p_hit), xf_vec(o2w, dpdu), xf_vec(o2w, dpdv), xf_nrm(s.w2o, zero),
+                  xf_nrm(s.w2o, zero), u, v, flip);
+    // nn is overwritten from the object-space ray origin's z against 0, as written (disk.rs:127-131)
+    g.nn = xf_nrm(s.w2o, mk3(0.0f, 0.0f, o.z > 0.0f ? 1.0f : -1.0f));
+    return g;
+  }
+  if (kind == PBRTB200_QUADRIC_CYLINDER) {  // cylinder.rs:127-154 + helpers.rs:17-43
+    const float v = (p_hit.z - s.z_min) / (s.z_max - s.z_min);
+    const f3 dpdu = s.phi_max * mk3(-p_hit.y, p_hit.x, 0.0f);
+    const f3 dpdv = mk3(0.0f, 0.0f, s.z_max - s.z_min);
+    const f3 d2pduu = -s.phi_max * s.phi_max * mk3(p_hit.x, p_hit.y, 0.0f);
+    const f3 zero = mk3(0.f, 0.f, 0.f);
+    const float ee = dot3(dpdu, dpdu), ff = dot3(dpdu, dpdv), gg = dot3(dpdv, dpdv);
+    const f3 nn = normalize3(cross3(dpdu, dpdv));
+    const float e = dot3(nn, d2pduu), f = dot3(nn, zero), g = dot3(nn, zero);
+    const float inveeggff2 = 1.0f / (ee * gg - ff * ff);
+    const f3 dndu = (f * ff - e * gg) * inveeggff2 * dpdu + (e * ff - f * ee) * inveeggff2 * dpdv;
+    const f3 dndv = (g * ff - f * gg) * inveeggff2 * dpdu + (f * ff - g * ee) * inveeggff2 * dpdv;
+    return dg_new(xf_pt(o2w, p_hit), xf_vec(o2w, dpdu), xf_vec(o2w, dpdv), xf_nrm(s.w2o, dndu),
+                  xf_nrm(s.w2o, dndv), u, v, flip);
+  }
   const float theta = acosf(rclampf(p_hit.z / s.radius, -1.0f, 1.0f));
   const float v = (theta - s.theta_min) / (s.theta_max - s.theta_min);
   const float zradius = sqrtf(p_hit.x * p_hit.x + p_hit.y * p_hit.y);
@@ -215,7 +245,7 @@ PB_DEV DG sphere_dg(const pbrtb200_sphere80& s, const float* o2w, f3 ow, f3 dw, 
   const f3 dndv = (g * ff - f * gg) * inveeggff2 * dpdu + (f * ff - g * ee) * inveeggff2 * dpdv;
   // Normal transform uses (o2w).m_inv == w2o
   return dg_new(xf_pt(o2w, p_hit), xf_vec(o2w, dpdu), xf_vec(o2w, dpdv), xf_nrm(s.w2o, dndu),
-                xf_nrm(s.w2o, dndv), u, v, s.flip != 0);
+                xf_nrm(s.w2o, dndv), u, v, flip);
 }
 
 // ---- textures ---------------------------------------------------------------------------------

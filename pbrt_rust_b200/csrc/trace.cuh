@@ -77,10 +77,27 @@ PB_DEV bool sphere_hit(const pbrtb200_sphere80* __restrict__ sp, f3 ow, f3 dw, f
   for (int i = 0; i < 12; ++i) m[i] = __ldg(&sp->w2o[i]);
   const float radius = __ldg(&sp->radius), z_min = __ldg(&sp->z_min), z_max = __ldg(&sp->z_max),
               phi_max = __ldg(&sp->phi_max);
+  const uint32_t kind = (__ldg(&sp->flip) >> PBRTB200_QUADRIC_KIND_SHIFT) & 3u;
   f3 o = xf_pt(m, ow), d = xf_vec(m, dw);
-  float a = len2(d);
-  float b = 2.0f * dot3(d, o);
-  float c = len2(o) - radius * radius;
+  if (kind == PBRTB200_QUADRIC_DISK) {  // disk.rs:37-71 (z_min = height, theta_min = inner radius)
+    if (fabsf(d.z) < 1e-6f) return false;
+    const float t_hit = (z_min - o.z) / d.z;
+    if (t_hit < mint || t_hit > maxt) return false;
+    const f3 p_hit = o + (d * t_hit);
+    const float dist2 = p_hit.x * p_hit.x + p_hit.y * p_hit.y;
+    const float inner = __ldg(&sp->theta_min);
+    if (dist2 > (radius * radius) || dist2 < (inner * inner)) return false;
+    const float a = atan2f(p_hit.y, p_hit.x);
+    const float phi = a < 0.0f ? a + 2.0f * PB_PI : a;
+    if (phi > phi_max) return false;
+    *t_out = t_hit;
+    *phi_out = phi;
+    return true;
+  }
+  const bool cyl = kind == PBRTB200_QUADRIC_CYLINDER;  // cylinder.rs:40-100 shares sphere.rs's flow
+  float a = cyl ? d.x * d.x + d.y * d.y : len2(d);
+  float b = cyl ? 2.0f * (d.x * o.x + d.y * o.y) : 2.0f * dot3(d, o);
+  float c = (cyl ? o.x * o.x + o.y * o.y : len2(o)) - radius * radius;
   float t0, t1;
   if (!quadratic_(a, b, c, &t0, &t1)) return false;
   if (t0 > maxt || t1 < mint) return false;
@@ -93,8 +110,11 @@ PB_DEV bool sphere_hit(const pbrtb200_sphere80* __restrict__ sp, f3 ow, f3 dw, f
   if (h.x == 0.0f && h.y == 0.0f) h.x = 1e-5f * radius;
   float ang = atan2f(h.y, h.x);
   if (ang < 0.0f) ang += 2.0f * PB_PI;
-  bool invalid = (h.z > -radius && h.z < z_min) || (h.z < radius && h.z > z_max) || (ang > phi_max);
-  if (invalid) {
+  auto clipped = [&](f3 hp, float an) {  // sphere.rs:84-88 / cylinder.rs:78-80
+    return cyl ? (hp.z < z_min || hp.z > z_max || an > phi_max)
+               : ((hp.z > -radius && hp.z < z_min) || (hp.z < radius && hp.z > z_max) || (an > phi_max));
+  };
+  if (clipped(h, ang)) {
     if (t_hit == t1) return false;
     if (t1 > maxt) return false;
     t_hit = t1;
@@ -102,8 +122,7 @@ PB_DEV bool sphere_hit(const pbrtb200_sphere80* __restrict__ sp, f3 ow, f3 dw, f
     if (h.x == 0.0f && h.y == 0.0f) h.x = 1e-5f * radius;
     ang = atan2f(h.y, h.x);
     if (ang < 0.0f) ang += 2.0f * PB_PI;
-    invalid = (h.z > -radius && h.z < z_min) || (h.z < radius && h.z > z_max) || (ang > phi_max);
-    if (invalid) return false;
+    if (clipped(h, ang)) return false;
   }
   *t_out = t_hit;
   *phi_out = ang;

