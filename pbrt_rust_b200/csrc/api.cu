@@ -424,7 +424,11 @@ struct StageTimer {
 };
 
 // Samples per wavefront chunk: bounds the chunk-local buffers (hits, Le, contrib, shadow queue).
-constexpr int kChunkLog2Default = 23;  // measured best of 2^21..2^26 (profiles/r01_notes.md)
+// 2^25: measured best of 2^21..2^26 once the shade stage stopped being atomic-bound (every launch
+// of a persistent trace kernel costs ~40 us of ramp and tail; profiles/r01_notes.md).  render()
+// halves it until the chunk-local buffers fit kChunkBudgetBytes (many light slots).
+constexpr int kChunkLog2Default = 25;
+constexpr uint64_t kChunkBudgetBytes = 8ull << 30;
 uint64_t chunk_samples() {
   static const int lg = [] {
     const char* v = std::getenv("PBRTB200_CHUNK_LOG2");
@@ -1004,7 +1008,11 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   if (ns * (uint64_t)std::max(1u, rad_slots) >= 0xFFFFFFFFull)
     FAIL(PBRTB200_EINVAL, "frame has more than 2^32 radiance terms; render it in tiles");
 
-  uint64_t chunk_pix = std::max<uint64_t>(1, chunk_samples() / (uint64_t)ds.spp);
+  uint64_t chunk_cap = chunk_samples();
+  while (chunk_cap > (1ull << 20) &&
+         chunk_cap * (sizeof(pbrtb200_hit16) + (uint64_t)slots * (sizeof(pbrtb200_ray32) + sizeof(uint32_t))) > kChunkBudgetBytes)
+    chunk_cap >>= 1;
+  uint64_t chunk_pix = std::max<uint64_t>(1, chunk_cap / (uint64_t)ds.spp);
   chunk_pix = std::min(chunk_pix, npix);
   const uint64_t chunk_ns = chunk_pix * (uint64_t)ds.spp;
 

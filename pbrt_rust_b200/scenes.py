@@ -168,13 +168,16 @@ def procedural_image(w=200, h=120, seed=11):
 
 
 def textured(image=None, xres=256, yres=160, xs=2, ys=2, do_trilinear=False, max_aniso=8.0, wrap="repeat",
-             gamma=2.2, nx=40, nz=20, n_spheres=24, seed=5):
+             gamma=2.2, nx=40, nz=20, n_spheres=24, seed=5, eye=(0, 9, -26), look=(0, 0, 0), flat=False):
     """"Next" row 2 test scene: heightfield ground with an ImageTexture Kd (UV mapping, tiled 3x2)
     and a float ImageTexture sigma, plastic spheres whose Kd is a planar-mapped image and whose
     roughness is a float image; one point light + the quad area light."""
     if image is None:
         image = procedural_image()
     vi, P = heightfield(nx, nz)
+    if flat:  # no self-silhouettes: ray differentials (and with them the EWA footprints) stay sane
+        P = P.copy()
+        P[:, 1] = 0.0
     uv = np.stack([(P[:, 0] + 20.0) / 40.0, (P[:, 2] + 10.0) / 20.0], -1).astype(np.float32)
     kw = dict(do_trilinear=do_trilinear, max_aniso=max_aniso, wrap=wrap)
     kd_ground = Texture.image(UVMapping2D(3.0, 2.0, 0.1, 0.2), image, spectrum=True, scale=1.0, gamma=gamma, **kw)
@@ -195,7 +198,7 @@ def textured(image=None, xres=256, yres=160, xs=2, ys=2, do_trilinear=False, max
         Shape.triangle_mesh(Transform.new(), Transform.new(), False, lvi, lP), _matte(), AreaLight(10.0, 1)))
     scene = Scene.new_with(Primitive.bvh(prims, 4, "sah"),
                            [Light.point(Transform.translate((-8.0, 10.0, -12.0)), 120.0)])
-    c2w = Transform.look_at((0, 9, -26), (0, 0, 0), (0, 1, 0)).inverse()
+    c2w = Transform.look_at(eye, look, (0, 1, 0)).inverse()
     return _setup(scene, c2w, 45.0, xres, yres, xs, ys, True)
 
 

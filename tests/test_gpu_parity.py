@@ -416,9 +416,12 @@ def test_image_textures_ewa_and_trilinear(orc, tri, wrap, aniso):
     the oracle on the same scene.  Hit ids bit-exact; image within the float-edge tolerance
     (CUDA vs glibc expf/log2f/powf differ by ULPs inside the EWA weights and the level choice):
     RMSE <= 1e-5 linear RGB and <= 1e-4 relative error on >= 99.9 % of the pixels."""
-    # (small frames: at grazing angles the reference's lod choice — log2 of the UNSCALED minor axis,
-    # mipmap.rs:335 — makes single EWA lookups visit 10^6..10^8 texels; DESIGN.md §9 row 2)
-    cfg = scenes.textured(xres=120, yres=72, xs=2, ys=2, do_trilinear=tri, wrap=wrap, max_aniso=aniso)
+    # EWA variants render a flat ground: where a ray differential misses its tangent plane (bumps'
+    # self-silhouettes) du/dx reaches hundreds of texture periods, and the reference's lod choice —
+    # log2 of the UNSCALED minor axis, mipmap.rs:335 — then makes ONE lookup walk 10^7 texels
+    # (DESIGN.md §9 row 2).  The walk is reproduced faithfully, it is just slow to test.
+    cfg = scenes.textured(xres=160, yres=100, xs=2, ys=2, do_trilinear=tri, wrap=wrap, max_aniso=aniso,
+                          flat=not tri, n_spheres=24 if tri else 8)
     r = _renderer(cfg)
     film = r.render(cfg["scene"])
     osc = orc.OracleScene(cfg["scene"])
@@ -582,3 +585,16 @@ def test_cylinders_and_disks(orc):
     ref = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, primary_only=True), want_hits=True)
     assert np.mean(hitsr["prim"] == ref["hit_ids"]) >= 0.9999
     _image_check(cfg, orc, rel_tol=1e-3, frac=0.995, rmse_tol=1e-4)
+
+
+def test_image_textures_ewa_on_silhouettes_small(orc):
+    """The same EWA path on the bumpy ground + planar-mapped spheres (degenerate ray differentials
+    at silhouettes, very large ellipses), at a frame small enough to stay quick."""
+    cfg = scenes.textured(xres=48, yres=30, xs=2, ys=2, do_trilinear=False, wrap="repeat", max_aniso=8.0)
+    r = _renderer(cfg)
+    film = r.render(cfg["scene"])
+    ref = orc.render(orc.OracleScene(cfg["scene"]), orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0))
+    rgb, rgb_ref = pb.film_to_rgb(film), ref["rgb"]
+    assert float(np.sqrt(np.mean((rgb - rgb_ref) ** 2))) <= 1e-5
+    rel = np.abs(rgb - rgb_ref) / np.maximum(np.abs(rgb_ref), 1e-3)
+    assert (rel.max(axis=-1) <= 1e-4).mean() >= 0.995
