@@ -195,16 +195,11 @@ def main():
     gather = os.environ.get("PBRTB200_GATHER", "p2p") if world > 1 else "none"
     peers, frame_no = [], [0]
     if gather == "p2p":
-        try:
-            peers = [multigpu.PeerFilm(r.ctx, h * w, dist, torch.device("cuda", local)) for _ in range(2)]
-        except Exception as e:  # no peer access between these GPUs
+        peers = [multigpu.PeerFilm(r.ctx, h * w, dist, torch.device("cuda", local)) for _ in range(2)]
+        if not all(p.ok for p in peers):  # no CUDA IPC / peer access between these GPUs (same on every rank)
             if rank == 0:
-                print(f"bench: CUDA IPC film sharing unavailable ({e}); using the NCCL gather", file=sys.stderr)
-            gather = "nccl"
-        ok = torch.tensor([1 if gather == "p2p" else 0], device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok) == 0:
-            gather = "nccl"
+                print("bench: CUDA IPC film sharing unavailable; using the NCCL gather", file=sys.stderr)
+            gather, peers = "nccl", []
     peer_views = [p.tensor() for p in peers] if (gather == "p2p" and rank == 0) else []
     fence = torch.zeros(1, dtype=torch.int32, device="cuda")
 

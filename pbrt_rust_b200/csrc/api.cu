@@ -81,7 +81,8 @@ struct pbrtb200_ctx {
   DScene sc{};
   std::vector<pbrtb200_light> h_lights;
   DevBuf d_nodes, d_tris, d_leaf_prim, d_leaf_count, d_spheres, d_sphere_o2w, d_meshes, d_tri_uv,
-      d_tri_n, d_tri_s, d_materials, d_mat_flags, d_textures, d_lights, d_area_tris, d_mipmaps, d_texels, d_peer_film;
+      d_tri_n, d_tri_s, d_materials, d_mat_flags, d_textures, d_lights, d_area_tris, d_mipmaps, d_texels;
+  std::vector<void*> peer_films;  // pbrtb200_peer_film_create allocations (freed at destroy)
   // per-frame work buffers (grow-only)
   DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_lightu, d_edge, d_rad, d_hits,
       d_sq_rays, d_sq_slots, d_film, d_rects, d_rect_prefix, d_ctrl, d_rays_in, d_occ, d_out_a,
@@ -489,6 +490,7 @@ void pbrtb200_destroy(pbrtb200_ctx* ctx) {
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (void* p : ctx->peer_films) cudaFree(p);
   for (cudaEvent_t ev : ctx->band_events) cudaEventDestroy(ev);
   delete ctx;
 }
@@ -1289,14 +1291,16 @@ int pbrtb200_peer_film_create(pbrtb200_ctx* ctx, uint64_t n_pixels, void** dev_p
   if (!ctx || !dev_ptr || !handle64 || n_pixels == 0) return PBRTB200_EINVAL;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   CK(cudaSetDevice(ctx->device));
-  // a dedicated cudaMalloc allocation: IPC handles name whole allocations
-  CK(ctx->d_peer_film.ensure(n_pixels * sizeof(float4)));
-  CK(cudaMemsetAsync(ctx->d_peer_film.p, 0, n_pixels * sizeof(float4), ctx->stream));
+  // a dedicated cudaMalloc allocation per call: IPC handles name whole allocations
+  void* p = nullptr;
+  CK(cudaMalloc(&p, n_pixels * sizeof(float4)));
+  ctx->peer_films.push_back(p);
+  CK(cudaMemsetAsync(p, 0, n_pixels * sizeof(float4), ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   cudaIpcMemHandle_t h;
-  CK(cudaIpcGetMemHandle(&h, ctx->d_peer_film.p));
+  CK(cudaIpcGetMemHandle(&h, p));
   std::memcpy(handle64, &h, 64);
-  *dev_ptr = ctx->d_peer_film.p;
+  *dev_ptr = p;
   return PBRTB200_OK;
 }
 

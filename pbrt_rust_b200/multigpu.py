@@ -50,25 +50,34 @@ class PeerFilm:
     stores from k_film; include/pbrtb200.h pbrtb200_peer_film_*).  One process per GPU."""
 
     def __init__(self, ctx, n_pixels, dist, device):
+        """Collective: every rank must call it.  Never raises between the collectives it issues;
+        `self.ok` is False on every rank if any rank could not create or map the buffer."""
         import torch
         from ._ffi import lib
         from .api import DevicePtr
         self.ctx, self.dist = ctx, dist
         self.rank = dist.get_rank()
-        handle = torch.zeros(64, dtype=torch.uint8, device=device)
+        self.n_pixels = n_pixels
+        self.opened = False
+        msg = torch.zeros(65, dtype=torch.uint8, device=device)  # 64 handle bytes + "created" flag
         p = C.c_void_p()
         if self.rank == 0:
             buf = C.create_string_buffer(64)
-            ctx.check(lib().pbrtb200_peer_film_create(ctx.h, n_pixels, C.byref(p), buf))
-            handle.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
-        dist.broadcast(handle, src=0)
-        self.opened = False
-        if self.rank != 0:
-            raw = bytes(handle.cpu().numpy().tobytes())
-            ctx.check(lib().pbrtb200_peer_film_open(ctx.h, raw, C.byref(p)))
-            self.opened = True
-        self.ptr = DevicePtr(p.value)
-        self.n_pixels = n_pixels
+            if lib().pbrtb200_peer_film_create(ctx.h, n_pixels, C.byref(p), buf) == 0:
+                msg[:64].copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+                msg[64] = 1
+        dist.broadcast(msg, src=0)
+        host = msg.cpu().numpy()
+        good = int(host[64]) == 1
+        if good and self.rank != 0:
+            good = lib().pbrtb200_peer_film_open(ctx.h, bytes(host[:64].tobytes()), C.byref(p)) == 0
+            self.opened = good
+        flag = torch.tensor([1 if good else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self.ok = int(flag.item()) == 1
+        self.ptr = DevicePtr(p.value or 0)
+        if not self.ok:
+            self.close()
 
     def tensor(self):
         """Rank 0: the gathered film as a CUDA tensor view (n_pixels * 4 floats)."""

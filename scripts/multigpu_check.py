@@ -15,6 +15,7 @@ film = cfg["film"]; h, w = film.shape
 r = pb.GpuRenderer(cfg["sampler"], cfg["camera"], cfg["integrator"], num_cpus=8, device=local)
 tiles = multigpu.partition_tiles(film.get_pixel_extent(), rank, world)
 peer = multigpu.PeerFilm(r.ctx, h * w, dist, torch.device("cuda", local))
+assert peer.ok, "CUDA IPC film sharing unavailable"
 for _ in range(3):  # repeated frames: ownership is disjoint, so re-writing is idempotent
     r.render(cfg["scene"], tiles=tiles, out=peer.ptr, keep_others=True)
     dist.barrier()
