@@ -233,6 +233,108 @@ def quadrics(xres=160, yres=112, xs=2, ys=2, n=18, seed=9):
     return _setup(scene, c2w, 45.0, xres, yres, xs, ys, True)
 
 
+def random_scene(seed):
+    """A seeded random small scene + camera + sampler + film, drawn from everything the back end
+    supports: meshes with optional normals / tangents / uvs, spheres, cylinders, disks under random
+    (also handedness-flipping) transforms, matte / plastic materials over constant, checkerboard
+    (nested, antialiased or not), uv and trilinear image textures, point / spot / area lights,
+    every BVH split method, every filter, stratified and LD samplers, crop windows, depth of field.
+    Used by the differential (GPU vs oracle) fuzz test."""
+    rng = np.random.default_rng(seed)
+    U = lambda a=0.0, b=1.0: float(rng.uniform(a, b))
+    img = procedural_image(48, 40, seed=seed + 1)
+
+    def mapping():
+        if rng.integers(2):
+            return UVMapping2D(U(0.5, 6), U(0.5, 6), U(), U())
+        return PlanarMapping2D((U(-1, 1), U(-1, 1), U(-1, 1)), (U(-1, 1), U(-1, 1), U(-1, 1)), U(), U())
+
+    def spectrum_tex(depth=0):
+        k = int(rng.integers(5 if depth < 2 else 3))
+        if k == 0:
+            return Texture.constant((U(0.05, 0.9), U(0.05, 0.9), U(0.05, 0.9)))
+        if k == 1:
+            return Texture.uv(mapping())
+        if k == 2:
+            return Texture.image(mapping(), img, spectrum=True, do_trilinear=True, wrap=["repeat", "black", "clamp"][int(rng.integers(3))],
+                                 scale=U(0.6, 1.0), gamma=U(1.0, 2.2))
+        return Texture.checkerboard(mapping(), spectrum_tex(depth + 1), spectrum_tex(depth + 1), bool(rng.integers(2)))
+
+    def float_tex(lo, hi):
+        if rng.integers(3) == 0:
+            return Texture.image(mapping(), img, spectrum=False, do_trilinear=True, scale=hi, gamma=1.0)
+        return Texture.constant(U(lo, hi))
+
+    def material():
+        if rng.integers(2):
+            return Material.matte(spectrum_tex(), float_tex(0.0, 40.0) if rng.integers(2) else Texture.constant(0.0))
+        return Material.plastic(spectrum_tex(), Texture.constant(U(0.05, 0.5)), float_tex(0.02, 0.4))
+
+    def xform(spread=3.0):
+        t = Transform.translate((U(-spread, spread), U(0.2, 2.5), U(-spread, spread))) * Transform.rotate_x(U(0, 360)) \
+            * Transform.rotate_y(U(0, 360)) * Transform.scale(U(0.5, 1.4), U(0.5, 1.4), U(0.5, 1.4) * (-1.0 if rng.integers(4) == 0 else 1.0))
+        return t
+
+    prims = []
+    # ground mesh (sometimes with shading normals / tangents / uvs)
+    n = int(rng.integers(4, 14))
+    xs_ = np.linspace(-5, 5, n + 1)
+    X, Z = np.meshgrid(xs_, xs_, indexing="ij")
+    Y = U(0.0, 0.5) * np.sin(1.1 * X) * np.cos(0.8 * Z)
+    P = np.stack([X, Y, Z], -1).reshape(-1, 3).astype(np.float32)
+    a = (np.arange(n)[:, None] * (n + 1) + np.arange(n)[None, :]).astype(np.uint32)
+    b, c, d = a + (n + 1), a + 1, a + (n + 1) + 1
+    vi = np.stack([np.stack([a, c, b], -1), np.stack([b, c, d], -1)], axis=2).reshape(-1)
+    N = S = UV = None
+    if rng.integers(2):
+        N = np.stack([rng.uniform(-0.3, 0.3, X.shape), np.ones_like(X), rng.uniform(-0.3, 0.3, X.shape)], -1).reshape(-1, 3).astype(np.float32)
+    if rng.integers(2):
+        S = np.stack([np.ones_like(X), rng.uniform(-0.2, 0.2, X.shape), np.zeros_like(X)], -1).reshape(-1, 3).astype(np.float32)
+    if rng.integers(2):
+        UV = np.stack([(X + 5) / 10, (Z + 5) / 10], -1).reshape(-1, 2).astype(np.float32)
+    prims.append(Primitive.geometric(Shape.triangle_mesh(Transform.new(), Transform.new(), bool(rng.integers(2)), vi, P, N, S, UV), material()))
+    for _ in range(int(rng.integers(2, 9))):
+        t = xform()
+        kind = int(rng.integers(4))
+        ro = bool(rng.integers(2))
+        pm = 360.0 if rng.integers(2) else U(60, 350)
+        if kind == 0:
+            shape = Shape.sphere(t, t.inverse(), ro, U(0.3, 0.9), U(-0.9, -0.2), U(0.2, 0.9), pm)
+        elif kind == 1:
+            shape = Shape.cylinder(t, t.inverse(), ro, U(0.2, 0.7), U(-0.8, 0.0), U(0.1, 0.9), pm)
+        elif kind == 2:
+            shape = Shape.disk(t, t.inverse(), ro, U(-0.3, 0.3), U(0.5, 1.0), U(0.0, 0.3), pm)
+        else:
+            m = int(rng.integers(1, 20))
+            Pt = rng.uniform(-0.8, 0.8, (3 * m, 3)).astype(np.float32)
+            shape = Shape.triangle_mesh(t, t.inverse(), ro, np.arange(3 * m, dtype=np.uint32), Pt)
+        prims.append(Primitive.geometric(shape, material()))
+    lights = []
+    for _ in range(int(rng.integers(1, 4))):
+        k = int(rng.integers(3))
+        pos = (U(-5, 5), U(4, 9), U(-5, 5))
+        if k == 0:
+            lights.append(Light.point(Transform.translate(pos), (U(20, 90), U(20, 90), U(20, 90))))
+        elif k == 1:
+            l2w = Transform.look_at(pos, (U(-1, 1), 0.0, U(-1, 1)), (0, 1, 0)).inverse()
+            lights.append(Light.spot(l2w, U(60, 200), U(20, 60), U(2, 15)))
+        else:
+            lvi, lP = _quad_light(y=U(5, 9), half=U(0.5, 2.0), cx=U(-3, 3), cz=U(-3, 3))
+            prims.append(Primitive.geometric_area_light(
+                Shape.triangle_mesh(Transform.new(), Transform.new(), False, lvi, lP), _matte(), AreaLight(U(4, 15), int(rng.integers(1, 4)))))
+    scene = Scene.new_with(Primitive.bvh(prims, int(rng.integers(1, 5)), ["sah", "middle", "equal"][int(rng.integers(3))]), lights)
+    c2w = Transform.look_at((U(-4, 4), U(3, 8), U(-10, -6)), (U(-1, 1), U(0, 1), U(-1, 1)), (0, 1, 0)).inverse()
+    filt = [Filter.mean(0.5, 0.5), Filter.mean(U(0.5, 1.5), U(0.5, 1.5)), Filter.triangle(U(1, 2), U(1, 2)),
+            Filter.gaussian(U(1, 2.5), U(1, 2.5), U(0.5, 2)), Filter.mitchell(2.0, 2.0, 1 / 3, 1 / 3),
+            Filter.lanczos(U(1.5, 3), U(1.5, 3), 3.0)][int(rng.integers(6))]
+    crop = (0, 1, 0, 1) if rng.integers(3) else tuple(sorted([U(0, 0.5), U(0.5, 1)]) + sorted([U(0, 0.5), U(0.5, 1)]))
+    xres, yres = int(rng.integers(20, 72)), int(rng.integers(16, 56))
+    use_ld = bool(rng.integers(3) == 0)
+    lensr = U(0.02, 0.2) if rng.integers(4) == 0 else 0.0
+    return _setup(scene, c2w, U(35, 65), xres, yres, int(rng.integers(1, 4)), int(rng.integers(1, 4)), bool(rng.integers(4) != 0),
+                  sampler="ld" if use_ld else "stratified", crop=crop, filt=filt, lensr=lensr, focald=U(6, 12))
+
+
 def config5(nx=5000, nz=5000, xres=1920, yres=1080, xs=16, ys=16, crop=(0, 1, 0, 1)):
     """50 M-triangle heightfield, 4 area lights, 256 spp."""
     return config3(nx, nz, xres, yres, xs, ys, crop=crop, n_lights=4)
