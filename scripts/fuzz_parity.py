@@ -24,11 +24,21 @@ def check(seed, verbose=True):
     rel = np.abs(rgb - rgb_ref) / np.maximum(np.abs(rgb_ref), 1e-3)
     frac = float((rel.max(axis=-1) <= 1e-3).mean())
     wexact = bool(np.array_equal(film[..., 3].view(np.uint32), ref["film"][..., 3].view(np.uint32)))
-    ok = agree >= 0.9999 and rmse <= 1e-4 and frac >= 0.99 and wexact and np.isfinite(rgb).all()
+    # tile partition (what each GPU of a multi-GPU frame does): the owned tiles of 3 "ranks",
+    # rendered separately with halo pixels, must add up to the whole-film render bit for bit
+    from pbrt_rust_b200 import multigpu
+    ext = cfg["film"].get_pixel_extent()
+    acc = np.zeros_like(film)
+    for k in range(3):
+        tiles = multigpu.partition_tiles(ext, k, 3, tile=8 + 4 * (seed % 3))
+        if tiles:
+            acc += r.render(cfg["scene"], tiles=tiles)
+    tiles_ok = bool(np.array_equal(acc.view(np.uint32), film.view(np.uint32)))
+    ok = agree >= 0.9999 and rmse <= 1e-4 and frac >= 0.99 and wexact and np.isfinite(rgb).all() and tiles_ok
     if verbose or not ok:
         s = cfg["sampler"]
-        print("seed %4d %s  film %s  spp %d  ids %.6f  rmse %.2e  frac(rel<=1e-3) %.4f  weights %s  max rgb %.3f" % (
-            seed, "ok  " if ok else "FAIL", film.shape[:2], s.samples_per_pixel(), agree, rmse, frac, "exact" if wexact else "DIFF", float(rgb_ref.max())))
+        print("seed %4d %s  film %s  spp %d  ids %.6f  rmse %.2e  frac(rel<=1e-3) %.4f  weights %s  tiles %s  max rgb %.3f" % (
+            seed, "ok  " if ok else "FAIL", film.shape[:2], s.samples_per_pixel(), agree, rmse, frac, "exact" if wexact else "DIFF", "exact" if tiles_ok else "DIFF", float(rgb_ref.max())))
     return ok
 
 
