@@ -178,7 +178,14 @@ def main():
     t_scene = time.perf_counter() - t0
     h, w = film.shape
     from pbrt_rust_b200 import multigpu
-    tiles = multigpu.partition_tiles(film.get_pixel_extent(), rank, world) if world > 1 else None
+    # N > 1 partition.  "bands" (default): contiguous row bands whose boundaries follow the ranks'
+    # measured frame times during the warm-up frames (multigpu.BandBalancer) and are frozen for the
+    # timed frames; PBRTB200_PARTITION=cyclic: 64x64 tiles, tile -> rank = id mod N.
+    partition = os.environ.get("PBRTB200_PARTITION", "bands") if world > 1 else "whole"
+    balancer = multigpu.BandBalancer(film.get_pixel_extent(), world) if partition == "bands" else None
+    tiles = None
+    if world > 1:
+        tiles = balancer.tiles_for(rank) if balancer else multigpu.partition_tiles(film.get_pixel_extent(), rank, world)
     d_film = torch.zeros(h * w * 4, dtype=torch.float32, device="cuda")
     h_film_t = torch.zeros(h * w * 4, dtype=torch.float32).pin_memory()
     h_film = h_film_t.numpy().reshape(h, w, 4)
@@ -227,7 +234,24 @@ def main():
             torch.cuda.synchronize()
         return r.last_stats
 
+    def rank_times(ms):
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = ms
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.cpu()]
+
+    def rebalance(frames=12):
+        """Warm-up only: move the band boundaries until the slowest rank is within 2 % of the mean."""
+        nonlocal tiles
+        for _ in range(frames):
+            times = rank_times(frame(True)["ms_total"])
+            if balancer.imbalance(times) < 1.02 or not balancer.update(times):
+                break
+            tiles = balancer.tiles_for(rank)
+
     def timed(resident, steps, warmup):
+        if balancer and resident:
+            rebalance()
         for _ in range(warmup):
             frame(resident)
         acc = {"ms_trace": 0.0, "ms_shadow": 0.0, "ms_total": 0.0, "ms_raygen": 0.0, "ms_shade": 0.0,
@@ -267,6 +291,7 @@ def main():
         time.sleep(0.02)  # nvidia-smi needs a moment before its first sample
     ms, rays_per_frame, acc = timed(True, args.steps, args.warmup)
     clocks = clk.stop()
+    per_rank = rank_times(acc["ms_total"] / args.steps) if world > 1 else None
     ms_e2e, rays_e2e, _ = timed(False, args.steps, 1)
 
     # full-frame sanity: the last e2e film must be a plausible image
@@ -328,9 +353,13 @@ def main():
         "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_frame": rays_per_frame, "tiles": "64x64 cyclic" if world > 1 else "whole film",
+        "config": {"workload": WORKLOAD, "rays_per_frame": rays_per_frame, "tiles": partition,
                    "l2": "per-frame working set (112 MB scene + >2 GB wavefront buffers) exceeds the 126 MB L2; no explicit flush",
                    "scene_build_upload_s": t_scene,
+                   "partition": {"whole": "whole film", "cyclic": "64x64 tiles, cyclic",
+                                 "bands": "row bands balanced on measured rank times during warm-up"}[partition],
+                   "band_rows": balancer.b if balancer else None,
+                   "per_rank_device_ms": per_rank,
                    "film_gather": {"none": "single GPU", "p2p": "film kernels store owned tiles into rank 0's HBM over NVLink (CUDA IPC) + barrier",
                                    "nccl": "reduce(SUM) of zero-padded films (NCCL)"}[gather]},
         "clocks": clocks,

@@ -96,3 +96,62 @@ class PeerFilm:
         if self.opened:
             lib().pbrtb200_peer_film_close(self.ctx.h, C.c_void_p(self.ptr.addr))
             self.opened = False
+
+
+class BandBalancer:
+    """Cost-balanced contiguous partition: rank k owns the film rows [b[k], b[k+1]).  Contiguous
+    bands keep each GPU's rays in one part of the scene (the cyclic tiles make every GPU touch the
+    whole BVH with 1/G of the rays, which costs the closest-hit kernel ~20 %), and the boundaries
+    follow the measured per-rank frame time of the previous frame(s), so sky / horizon / dense
+    regions end up with equal work.  Any partition gives the same film (ownership is disjoint and
+    the per-pixel summation order does not depend on it), so rebalancing between frames is free of
+    side effects; only the pixel work list is rebuilt when the boundaries move."""
+
+    def __init__(self, pixel_extent, world, quantum=4):
+        self.x0, self.x1, self.y0, self.y1 = pixel_extent
+        self.world, self.q = world, quantum
+        h = self.y1 - self.y0
+        self.b = [self.y0 + self._snap(round(k * h / world)) for k in range(world)] + [self.y1]
+        self._fix()
+
+    def _snap(self, v):
+        return int(round(v / self.q)) * self.q
+
+    def _fix(self):  # strictly increasing, at least one quantum per rank when the film allows it
+        for k in range(1, self.world):
+            self.b[k] = max(self.b[k], self.b[k - 1] + self.q)
+        for k in range(self.world - 1, 0, -1):
+            self.b[k] = min(self.b[k], self.b[k + 1] - 1)
+        self.b[0], self.b[-1] = self.y0, self.y1
+
+    def tiles_for(self, rank):
+        a, c = self.b[rank], self.b[rank + 1]
+        return [(self.x0, a, self.x1, c)] if c > a else []
+
+    def imbalance(self, times):
+        return max(times) / (sum(times) / len(times))
+
+    def update(self, times, damping=0.8):
+        """times[k] = last frame time of rank k.  Moves the boundaries assuming a piecewise-constant
+        cost density per band; returns True if they changed."""
+        dens = [t / max(1, self.b[k + 1] - self.b[k]) for k, t in enumerate(times)]
+        total = sum(times)
+        target = total / self.world
+        new_b, k, acc, y = [self.y0], 0, 0.0, float(self.y0)
+        for r in range(1, self.world):
+            need = target * r
+            while k < self.world and acc + dens[k] * (self.b[k + 1] - y) < need:
+                acc += dens[k] * (self.b[k + 1] - y)
+                y = float(self.b[k + 1])
+                k += 1
+            if k >= self.world:
+                new_b.append(self.y1)
+                continue
+            yy = y + (need - acc) / max(dens[k], 1e-12)
+            new_b.append(yy)
+        new_b.append(self.y1)
+        old = list(self.b)
+        self.b = [self.y0] + [self.y0 + self._snap(old[i] + damping * (new_b[i] - old[i]) - self.y0)
+                              for i in range(1, self.world)] + [self.y1]
+        self._fix()
+        return self.b != old
