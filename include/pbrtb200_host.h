@@ -37,7 +37,7 @@ pbh_scene* pbh_scene_new(void);
 void pbh_scene_free(pbh_scene* s);
 const char* pbh_last_error(const pbh_scene* s);
 
-/* texture constructors (src/texture/*): return the texture id */
+/* texture constructors (src/texture/ *.rs): return the texture id */
 int pbh_texture_constant(pbh_scene* s, const float rgb[3]);
 int pbh_texture_checkerboard(pbh_scene* s, int map_kind, const float map[8], int tex1, int tex2,
                              int antialiased);

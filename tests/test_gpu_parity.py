@@ -614,3 +614,27 @@ def test_differential_fuzz_random_scenes(orc):
     spec.loader.exec_module(fz)
     bad = [s for s in range(80) if not fz.check(s, verbose=False)]
     assert not bad, bad
+
+
+def test_c_abi_from_plain_c(orc, tmp_path):
+    """examples/render_c_abi.c drives the whole path from C (host mirror + C ABI, no Python in the
+    process): its film must equal the Python binding's film bit for bit, its PNG must decode to
+    the developed bytes, and both agree with the oracle."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "render_c_abi")
+    assert os.path.exists(exe), "examples/render_c_abi is built by __graft_entry__.build()"
+    prefix = str(tmp_path / "c1")
+    out = subprocess.run([exe, "160", "120", prefix], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "kernel launches" in out.stdout
+    film_c = np.fromfile(prefix + ".film", np.float32).reshape(120, 160, 4)
+    cfg = scenes.config1(xres=160, yres=120)
+    r = _renderer(cfg)
+    film_py = r.render(cfg["scene"])
+    assert np.array_equal(film_c.view(np.uint32), film_py.view(np.uint32))
+    from pbrt_rust_b200.imageio import read_png_rgb8
+    assert np.array_equal(read_png_rgb8(prefix + ".png"), r.develop(film_py))
+    ref = orc.render(orc.OracleScene(cfg["scene"]), orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0))
+    assert float(np.sqrt(np.mean((pb.film_to_rgb(film_c) - ref["rgb"]) ** 2))) <= 1e-5
