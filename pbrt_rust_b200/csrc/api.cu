@@ -128,10 +128,6 @@ int upload(pbrtb200_ctx* ctx, DevBuf& buf, const T* src, size_t n) {
   return 0;
 }
 
-bool affine_ok(const float* m16) {
-  return m16[12] == 0.f && m16[13] == 0.f && m16[14] == 0.f && m16[15] == 1.f;
-}
-
 int tex_depth(const pbrtb200_scene* s, int id, int depth) {
   if (id < 0 || (uint32_t)id >= s->n_textures) return -1;
   const pbrtb200_texture& t = s->textures[id];
