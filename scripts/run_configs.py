@@ -38,8 +38,21 @@ f = r.host_scene.flat.contents
 info = dict(config=args.config, n_gpus=world, n_prims=int(f.n_prims), n_nodes=int(f.n_nodes), n_tris=int(f.n_tris),
             n_spheres=int(f.n_spheres), scene_gen_s=t_gen, bvh_build_flatten_upload_s=t_build)
 film = cfg["film"]; h, w = film.shape
-tiles = multigpu.partition_tiles(film.get_pixel_extent(), rank, world) if world > 1 else None
 d_film = torch.zeros(h * w * 4, dtype=torch.float32, device="cuda")
+tiles = None
+if world > 1 and args.config != "c2":
+    # time-balanced row bands (multigpu.BandBalancer), settled on a few untimed frames
+    bal = multigpu.BandBalancer(film.get_pixel_extent(), world)
+    tiles = bal.tiles_for(rank)
+    for _ in range(8):
+        r.render(cfg["scene"], tiles=tiles, out=d_film)
+        t = torch.zeros(world, dtype=torch.float64, device="cuda"); t[rank] = r.last_stats["ms_total"]
+        dist.all_reduce(t)
+        tl = [float(x) for x in t.cpu()]
+        if bal.imbalance(tl) < 1.02 or not bal.update(tl):
+            break
+        tiles = bal.tiles_for(rank)
+    info["band_rows"] = bal.b
 times, stats = [], None
 if args.config == "c2":
     for i in range(args.frames + 1):
