@@ -755,4 +755,38 @@ void orc_image_texture_eval_planar(void* m, const float* pd9, uint64_t n, float*
 }
 float orc_sinc_1d(float x, float tau) { return sinc_1d(x, tau); }
 int32_t orc_modulo(int32_t a, int32_t b) { return modulo(a, b); }
+// Texture::evaluate / TextureMapping2D::map at a hand-built DifferentialGeometry (the texture tests
+// of texture/{mod,checkerboard,uv,mapping2d}.rs).  dg15 = p, dpdx, dpdy, u, v, dudx, dudy, dvdx, dvdy.
+static DiffGeom dg_from15(const float* q) {
+  DiffGeom dg;
+  dg.p = V3(q[0], q[1], q[2]);
+  dg.dpdx = V3(q[3], q[4], q[5]);
+  dg.dpdy = V3(q[6], q[7], q[8]);
+  dg.u = q[9];
+  dg.v = q[10];
+  dg.dudx = q[11];
+  dg.dudy = q[12];
+  dg.dvdx = q[13];
+  dg.dvdy = q[14];
+  return dg;
+}
+void orc_texture_eval(OrcScene* s, int tex_id, const float* dg15, float* out3) {
+  RGB r = s->sc.textures.eval(tex_id, dg_from15(dg15));
+  out3[0] = r.c[0];
+  out3[1] = r.c[1];
+  out3[2] = r.c[2];
+}
+void orc_mapping_map(int map_kind, const float* map8, const float* dg15, float* out6) {
+  Mapping2D m;
+  m.kind = map_kind;
+  if (map_kind == 0) {
+    m.su = map8[0]; m.sv = map8[1]; m.du = map8[2]; m.dv = map8[3];
+  } else {
+    m.vs = V3(map8[0], map8[1], map8[2]);
+    m.vt = V3(map8[3], map8[4], map8[5]);
+    m.du = map8[6];
+    m.dv = map8[7];
+  }
+  m.map(dg_from15(dg15), out6);
+}
 }  // extern "C"

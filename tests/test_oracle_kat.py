@@ -789,3 +789,95 @@ def test_cylinder_intersection_information(orc):
     assert dg[6] == 0.75 and abs(dg[7] - 0.5) < 1e-6
     assert np.sum((dg[8:11] - np.array([0.0, -math.pi * s2 / 2, math.pi * s2 / 2])) ** 2) < 1e-6
     assert np.sum((dg[11:14] - np.array([2.0, 0.0, 0.0])) ** 2) < 1e-6
+
+
+# ---- textures and mappings: texture/{mod,checkerboard,uv,mapping2d}.rs tests ---------------------
+
+def _dg15(p=(0, 0, 0), dpdx=(0, 0, 0), dpdy=(0, 0, 0), u=0.0, v=0.0, dudx=0.0, dudy=0.0, dvdx=0.0, dvdy=0.0):
+    return np.array([*p, *dpdx, *dpdy, u, v, dudx, dudy, dvdx, dvdy], np.float32)
+
+
+def _map(orc, kind, params, dg):
+    out = np.zeros(6, np.float32)
+    orc.lib().orc_mapping_map(kind, _p(np.array(params, np.float32)), _p(dg), _p(out))
+    return out
+
+
+class _TexScene:
+    """An oracle scene used only as a texture table (orc_add_texture / orc_texture_eval)."""
+
+    def __init__(self, orc):
+        self.L = orc.lib()
+        self.L.orc_scene_new.restype = C.c_void_p
+        self.h = C.c_void_p(self.L.orc_scene_new())
+
+    def add(self, kind, value=(0, 0, 0), map_kind=1, params=(1, 0, 0, 0, 1, 0, 0, 0), t1=0, t2=0, aa=0):
+        return self.L.orc_add_texture(self.h, kind, _p(np.array(value, np.float32)), map_kind,
+                                      _p(np.array(params, np.float32)), t1, t2, aa)
+
+    def eval(self, tex, dg):
+        out = np.zeros(3, np.float32)
+        self.L.orc_texture_eval(self.h, tex, _p(dg), _p(out))
+        return out
+
+
+_PLANAR_NEW = (1, 0, 0, 0, 1, 0, 0, 0)  # PlanarMapping2D::new(): vs = x, vt = y, ds = dt = 0
+
+
+def test_constant_and_uv_textures(orc):
+    """texture/mod.rs:93-97 const_texture_works, texture/uv.rs:37-49 uv_texture_works"""
+    ts = _TexScene(orc)
+    c = ts.add(0, value=(2.5, 2.5, 2.5))
+    assert ts.eval(c, _dg15(p=(3, -1, 2), u=0.3)).tolist() == [2.5, 2.5, 2.5]
+    uv = ts.add(2, map_kind=1, params=_PLANAR_NEW)
+    assert ts.eval(uv, _dg15(p=(0.25, 0.25, 0.0))).tolist() == [0.25, 0.25, 0.0]
+    assert ts.eval(uv, _dg15(p=(1.25, -2.5, 0.0))).tolist() == [0.25, 0.5, 0.0]
+
+
+def test_checkerboard_texture(orc):
+    """texture/checkerboard.rs:131-147 (point sampled) and :170-189 (closed-form antialiasing)"""
+    ts = _TexScene(orc)
+    one, zero = ts.add(0, value=(1, 1, 1)), ts.add(0, value=(0, 0, 0))
+    chk = ts.add(1, map_kind=1, params=_PLANAR_NEW, t1=one, t2=zero, aa=0)
+    assert ts.eval(chk, _dg15(p=(0.5, 0.5, 0)))[0] == 1.0
+    assert ts.eval(chk, _dg15(p=(1.5, 0.5, 0)))[0] == 0.0
+    assert ts.eval(chk, _dg15(p=(1.5, 1.5, 0)))[0] == 1.0
+    aa = ts.add(1, map_kind=1, params=_PLANAR_NEW, t1=one, t2=zero, aa=1)
+    assert abs(ts.eval(aa, _dg15(p=(1.1, 0.5, 0), dpdx=(0.2, 0, 0)))[0] - 0.25) < 1e-3
+    assert abs(ts.eval(aa, _dg15(p=(1.1, 0.5, 0), dpdx=(0.2, 0.2, 0)))[0] - 0.25) < 1e-3
+    v = ts.eval(aa, _dg15(p=(1.1, 0.9, 0), dpdx=(0.2, 0, 0), dpdy=(0, 0.2, 0)))[0]
+    assert abs(v - 2.0 * (0.25 * 0.75)) < 1e-3
+
+
+def test_uv_mapping(orc):
+    """texture/mapping2d.rs:293-333 uv_mapping_can_map_coords / can_scale_coords (+ :216-246)"""
+    new = (1, 1, 0, 0)
+    assert _map(orc, 0, new, _dg15()).tolist() == [0, 0, 0, 0, 0, 0]
+    assert _map(orc, 0, new, _dg15(u=0.5, v=0.2)).tolist() == [0.5, f32(0.2), 0, 0, 0, 0]
+    assert _map(orc, 0, new, _dg15(u=0.5, v=0.2, dudx=10, dudy=12, dvdx=-1, dvdy=0)).tolist() == [0.5, f32(0.2), 10, -1, 12, 0]
+    sc = (2.0, 0.5, 1.0, -0.3)
+    assert _map(orc, 0, sc, _dg15()).tolist() == [1.0, f32(-0.3), 0, 0, 0, 0]
+    assert _map(orc, 0, sc, _dg15(p=(0.1, 10.0, -13.0))).tolist() == [1.0, f32(-0.3), 0, 0, 0, 0]
+    et = f32(0.2) * f32(0.5) - f32(0.3)
+    assert _map(orc, 0, sc, _dg15(u=0.5, v=0.2)).tolist() == [2.0, et, 0, 0, 0, 0]
+    assert _map(orc, 0, sc, _dg15(u=0.5, v=0.2, dudx=10, dudy=12, dvdx=-1, dvdy=0)).tolist() == [2.0, et, 20.0, -0.5, 24.0, 0.0]
+    for params in (new, sc):  # test_uv_mapping_deriv
+        a = _map(orc, 0, params, _dg15(u=0.5, v=0.1, dudx=10, dudy=12, dvdx=-1, dvdy=0))
+        dx, dy = f32(1.0), f32(-0.4)
+        b = _map(orc, 0, params, _dg15(u=f32(0.5) + dx * f32(10) + dy * f32(12), v=f32(0.1) + dx * f32(-1) + dy * f32(0),
+                                      dudx=10, dudy=12, dvdx=-1, dvdy=0))
+        assert a[2:].tolist() == b[2:].tolist()
+        assert abs(a[0] + dx * a[2] + dy * a[4] - b[0]) < 1e-3 and abs(a[1] + dx * a[3] + dy * a[5] - b[1]) < 1e-3
+
+
+def test_planar_mapping_differentials(orc):
+    """texture/mapping2d.rs:449-463 via test_positional_differentials (:248-284)"""
+    for params in (_PLANAR_NEW, (1.0, 2.0, 3.0, -3.0, 0.0, -1.2, 3.2, -1000.0)):
+        base = _map(orc, 1, params, _dg15())
+        assert _map(orc, 1, params, _dg15(u=0.5, v=0.1, dudx=10, dudy=12, dvdx=-1, dvdy=0)).tolist() == base.tolist()
+        p, dpdx, dpdy = np.array([0.3, 1.2, -4.0], np.float32), np.array([0.2, 0.0, -0.3], np.float32), np.array([-0.5, 0.1, 1.3], np.float32)
+        a = _map(orc, 1, params, _dg15(p=p, dpdx=dpdx, dpdy=dpdy))
+        dx, dy = f32(0.1), f32(-0.1)
+        b = _map(orc, 1, params, _dg15(p=p + dx * dpdx + dy * dpdy, dpdx=dpdx, dpdy=dpdy))
+        assert np.abs(a[2:] - b[2:]).max() < 0.01
+        assert abs(a[0] + dx * a[2] + dy * a[4] - b[0]) < 1e-3 and abs(a[1] + dx * a[3] + dy * a[5] - b[1]) < 1e-3
