@@ -29,7 +29,7 @@ int main(int argc, char** argv) {
   /* scene: Primitive::bvh(8 x Primitive::geometric(Shape::sphere(translate(v), ..), matte), 1, "sah") */
   pbh_scene* hs = pbh_scene_new();
   const float kd[3] = {0.5f, 0.5f, 0.5f}, sigma[3] = {0.f, 0.f, 0.f};
-  const int mat = pbh_material_matte(hs, pbh_texture_constant(hs, kd), pbh_texture_constant(hs, sigma));
+  const int mat = pbh_material_matte(hs, pbh_texture_constant(hs, kd), pbh_texture_constant(hs, sigma), -1);
   for (int i = 0; i < 8; ++i) {
     const float v[3] = {(i & 1) ? 2.f : 0.f, (i & 2) ? 2.f : 0.f, (i & 4) ? 2.f : 0.f};
     float m[16], minv[16];

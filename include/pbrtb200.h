@@ -93,15 +93,32 @@ typedef struct {
 #define PBRTB200_TEX_CHECKER2D 1
 #define PBRTB200_TEX_UV 2
 #define PBRTB200_TEX_IMAGE 3   /* ImageTexture (texture/imagemap.rs:70-73): tex1 = mipmap index */
+#define PBRTB200_TEX_SCALE 4   /* ScaleTexture (texture/mod.rs:68-86): tex1 * tex2                */
+#define PBRTB200_TEX_MIX 5     /* MixTexture (texture/mix.rs:9-28): tex1.lerp(tex2, tex3)          */
+#define PBRTB200_TEX_BILERP 6  /* BilerpTexture (texture/bilerp.rs:10-37): value = v00,v01,v10,v11 */
+#define PBRTB200_TEX_DOTS 7    /* DotsTexture (texture/dots.rs:10-47): tex1 inside, tex2 outside   */
+#define PBRTB200_TEX_FBM 8     /* FBmTexture (texture/fbm.rs:8-27): value[0] = omega, aa = octaves */
+#define PBRTB200_TEX_WRINKLED 9 /* WrinkledTexture (texture/fbm.rs:29-48): same fields             */
+#define PBRTB200_TEX_KIND_MAX 9
 #define PBRTB200_MAP_UV 0      /* UVMapping2D(su,sv,du,dv): map[0..3]                      */
 #define PBRTB200_MAP_PLANAR 1  /* PlanarMapping2D(vs,vt,ds,dt): map[0..2],map[3..5],map[6..7] */
+/* SphericalMapping2D / CylindricalMapping2D (texture/mapping2d.rs:106-173) and IdentityMapping3D
+ * (texture/mapping3d.rs:43-66, the mapping of FBm / Wrinkled): map[0..11] = rows 0..2 of
+ * world_to_texture.m (affine transforms only: the w row must be 0 0 0 1).                       */
+#define PBRTB200_MAP_SPHERICAL 2
+#define PBRTB200_MAP_CYLINDRICAL 3
+#define PBRTB200_MAP_IDENTITY3D 4
+#define PBRTB200_MAP_KIND_MAX 4
+#define PBRTB200_TEX_MAX_DEPTH 3 /* textures nest (checkerboard, scale, mix, dots) to this depth */
 typedef struct {
   int32_t kind;
-  float value[3];  /* Constant (float textures use value[0]) */
+  float value[12]; /* Constant: value[0..2] (float textures use value[0]); Bilerp: 4 x RGB;
+                      FBm / Wrinkled: value[0] = omega                                         */
   int32_t map_kind;
-  float map[8];
-  int32_t tex1, tex2;  /* Checkerboard children */
-  int32_t aa;          /* 0 NONE, 1 CLOSEDFORM (texture/checkerboard.rs:10-14) */
+  float map[12];
+  int32_t tex1, tex2, tex3; /* children: Checkerboard (tex1, tex2), Scale, Mix (tex3 = amount), Dots */
+  int32_t aa;      /* Checkerboard: 0 NONE, 1 CLOSEDFORM (texture/checkerboard.rs:10-14);
+                      FBm / Wrinkled: octaves                                                  */
 } pbrtb200_texture;
 
 /* MIPMap (src/texture/mipmap.rs:143-151).  The pyramid (mipmap.rs:159-204: level 0 is the image
@@ -128,6 +145,8 @@ typedef struct {
 typedef struct {
   int32_t kind;
   int32_t kd, sigma, ks, roughness;  /* texture indices */
+  int32_t bump;  /* bump_map: Option<ScalarTextureReference> (material/matte.rs:15, plastic.rs:18):
+                    texture index of the displacement map, or -1 for None                      */
 } pbrtb200_material;
 
 #define PBRTB200_LIGHT_POINT 0

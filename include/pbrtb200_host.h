@@ -39,9 +39,25 @@ const char* pbh_last_error(const pbh_scene* s);
 
 /* texture constructors (src/texture/ *.rs): return the texture id */
 int pbh_texture_constant(pbh_scene* s, const float rgb[3]);
-int pbh_texture_checkerboard(pbh_scene* s, int map_kind, const float map[8], int tex1, int tex2,
+int pbh_texture_checkerboard(pbh_scene* s, int map_kind, const float map[12], int tex1, int tex2,
                              int antialiased);
-int pbh_texture_uv(pbh_scene* s, int map_kind, const float map[8]);
+int pbh_texture_uv(pbh_scene* s, int map_kind, const float map[12]);
+/* SphericalMapping2D::new_with(xf) / CylindricalMapping2D::new_with(xf) (texture/mapping2d.rs:111-118,
+ * 146-153) and IdentityMapping3D::new_with(xf) (texture/mapping3d.rs:47-55): rows 0..2 of
+ * world_to_texture.m -> map[12].  PBRTB200_EINVAL when the transform is not affine.              */
+int pbh_mapping_from_transform(const float m[16], float map[12]);
+/* ScaleTexture::new(t1, t2) (texture/mod.rs:74-78), MixTexture::new(t1, t2, amount)
+ * (texture/mix.rs:16-19), BilerpTexture::new(map, t00, t01, t10, t11) (texture/bilerp.rs:19-26; float
+ * textures pass three equal channels), DotsTexture::new(mapping, inside, outside)
+ * (texture/dots.rs:17-20), FBmTexture::new / WrinkledTexture::new(octaves, roughness,
+ * IdentityMapping3D(world_to_texture)) (texture/fbm.rs:15-19, 36-40)                             */
+int pbh_texture_scale(pbh_scene* s, int tex1, int tex2);
+int pbh_texture_mix(pbh_scene* s, int tex1, int tex2, int amount);
+int pbh_texture_bilerp(pbh_scene* s, int map_kind, const float map[12], const float v00[3],
+                       const float v01[3], const float v10[3], const float v11[3]);
+int pbh_texture_dots(pbh_scene* s, int map_kind, const float map[12], int inside, int outside);
+int pbh_texture_fbm(pbh_scene* s, int octaves, float roughness, const float w2t[12]);
+int pbh_texture_wrinkled(pbh_scene* s, int octaves, float roughness, const float w2t[12]);
 /* TextureCache::new_texture (src/texture/imagemap.rs:128-138 / 183-193) + MIPMap::new
  * (src/texture/mipmap.rs:159-204).  rgb = what read_image returns (imagemap.rs:75-89): w*h RGB
  * texels = byte / 255, row-major from the top-left; NULL = the file could not be read, which the
@@ -49,12 +65,13 @@ int pbh_texture_uv(pbh_scene* s, int map_kind, const float map[8]);
  * ((s * scale).powf(gamma) per channel); 0: TextureCache<f32> ((s.y() * scale).powf(gamma)).
  * wrap = PBRTB200_WRAP_*.  Every call builds its own MIPMap (the reference's per-file cache is a
  * memory optimisation of its loader, not part of the evaluated function).                        */
-int pbh_texture_image(pbh_scene* s, int map_kind, const float map[8], const float* rgb, uint32_t w,
+int pbh_texture_image(pbh_scene* s, int map_kind, const float map[12], const float* rgb, uint32_t w,
                       uint32_t h, int spectrum, int do_trilinear, float max_aniso, int wrap,
                       float scale, float gamma);
-/* Material::matte(kd, sigma) / Material::plastic(kd, ks, roughness) (src/material/mod.rs:88-99) */
-int pbh_material_matte(pbh_scene* s, int kd, int sigma);
-int pbh_material_plastic(pbh_scene* s, int kd, int ks, int roughness);
+/* Material::matte(kd, sigma, bump_map) / Material::plastic(kd, ks, roughness, bump_map)
+ * (src/material/mod.rs:88-99); bump_map = texture id of the displacement map or -1 for None      */
+int pbh_material_matte(pbh_scene* s, int kd, int sigma, int bump_map);
+int pbh_material_plastic(pbh_scene* s, int kd, int ks, int roughness, int bump_map);
 /* PointLight::new / SpotLight::new (src/light/point.rs:21-25, spot.rs:24-35); area = extension */
 int pbh_light_point(pbh_scene* s, const float l2w[16], const float l2w_inv[16], const float I[3]);
 int pbh_light_spot(pbh_scene* s, const float l2w[16], const float l2w_inv[16], const float I[3],

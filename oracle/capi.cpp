@@ -115,43 +115,56 @@ int orc_add_disk(OrcScene* s, const float* o2w, const float* o2w_inv, int ro, fl
     s->sc.geom.add_sphere(std::move(sp));
   });
 }
-int orc_add_texture(OrcScene* s, int kind, const float* value, int map_kind, const float* map8,
-                    int tex1, int tex2, int aa) {
+// map12: UV (su,sv,du,dv) | Planar (vs, vt, ds, dt) | Spherical / Cylindrical / Identity3D: rows
+// 0..2 of world_to_texture.m (row 3 = 0 0 0 1, the affine case the device supports)
+static Mapping2D mapping_from(int map_kind, const float* m) {
+  Mapping2D mp;
+  mp.kind = map_kind;
+  if (map_kind == 0) {
+    mp.su = m[0];
+    mp.sv = m[1];
+    mp.du = m[2];
+    mp.dv = m[3];
+  } else if (map_kind == 1) {
+    mp.vs = V3(m[0], m[1], m[2]);
+    mp.vt = V3(m[3], m[4], m[5]);
+    mp.du = m[6];
+    mp.dv = m[7];
+  } else {
+    M44 a = M44::rows(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], 0, 0, 0, 1);
+    mp.w2t = Transform(a, a);  // only m is read by the mappings
+  }
+  return mp;
+}
+int orc_add_texture(OrcScene* s, int kind, const float* value12, int map_kind, const float* map12,
+                    int tex1, int tex2, int tex3, int aa) {
   Texture t;
   t.kind = kind;
-  t.value = RGB(value[0], value[1], value[2]);
-  t.mapping.kind = map_kind;
-  if (map_kind == 0) {
-    t.mapping.su = map8[0];
-    t.mapping.sv = map8[1];
-    t.mapping.du = map8[2];
-    t.mapping.dv = map8[3];
-  } else {
-    t.mapping.vs = V3(map8[0], map8[1], map8[2]);
-    t.mapping.vt = V3(map8[3], map8[4], map8[5]);
-    t.mapping.du = map8[6];
-    t.mapping.dv = map8[7];
-  }
+  t.value = RGB(value12[0], value12[1], value12[2]);
+  for (int k = 0; k < 4; ++k) t.bil[k] = RGB(value12[3 * k], value12[3 * k + 1], value12[3 * k + 2]);
+  t.mapping = mapping_from(map_kind, map12);
   t.tex1 = tex1;
   t.tex2 = tex2;
+  t.tex3 = tex3;
   t.aa = aa;
   s->sc.textures.t.push_back(t);
   return (int)s->sc.textures.t.size() - 1;
 }
 // TextureCache::new_texture (texture/imagemap.rs:128-138 / 183-193).  rgb = read_image's texels
 // (byte / 255, row-major) or NULL for an unreadable file (1x1 scale^gamma map, :116-120).
-int orc_add_image_texture(OrcScene* s, int map_kind, const float* map8, const float* rgb, uint32_t w,
+int orc_add_image_texture(OrcScene* s, int map_kind, const float* map12, const float* rgb, uint32_t w,
                           uint32_t h, int spectrum, int do_trilinear, float max_aniso, int wrap,
                           float scale, float gamma) {
-  const float zero[3] = {0.f, 0.f, 0.f};
-  int id = orc_add_texture(s, 3, zero, map_kind, map8, 0, 0, 0);
+  const float zero[12] = {0.f};
+  int id = orc_add_texture(s, 3, zero, map_kind, map12, 0, 0, 0, 0);
   s->sc.textures.mips.push_back(
       make_image_mipmap(rgb, w, h, spectrum != 0, do_trilinear != 0, max_aniso, wrap, scale, gamma));
   s->sc.textures.t[(size_t)id].tex1 = (int)s->sc.textures.mips.size() - 1;
   return id;
 }
-int orc_add_material(OrcScene* s, int kind, int kd, int sigma, int ks, int roughness) {
+int orc_add_material(OrcScene* s, int kind, int kd, int sigma, int ks, int roughness, int bump) {
   Material m;
+  m.bump = bump;
   m.kind = kind;
   m.kd = kd;
   m.sigma = sigma;
@@ -776,17 +789,42 @@ void orc_texture_eval(OrcScene* s, int tex_id, const float* dg15, float* out3) {
   out3[1] = r.c[1];
   out3[2] = r.c[2];
 }
-void orc_mapping_map(int map_kind, const float* map8, const float* dg15, float* out6) {
-  Mapping2D m;
-  m.kind = map_kind;
-  if (map_kind == 0) {
-    m.su = map8[0]; m.sv = map8[1]; m.du = map8[2]; m.dv = map8[3];
-  } else {
-    m.vs = V3(map8[0], map8[1], map8[2]);
-    m.vt = V3(map8[3], map8[4], map8[5]);
-    m.du = map8[6];
-    m.dv = map8[7];
-  }
-  m.map(dg_from15(dg15), out6);
+void orc_mapping_map(int map_kind, const float* map12, const float* dg15, float* out6) {
+  mapping_from(map_kind, map12).map(dg_from15(dg15), out6);
+}
+// IdentityMapping3D::map (mapping3d.rs:57-63): out9 = p, dpdx, dpdy
+void orc_mapping3d_map(const float* map12, const float* dg15, float* out9) {
+  V3 p, dx, dy;
+  mapping_from(4, map12).map3(dg_from15(dg15), &p, &dx, &dy);
+  out9[0] = p.x; out9[1] = p.y; out9[2] = p.z;
+  out9[3] = dx.x; out9[4] = dx.y; out9[5] = dx.z;
+  out9[6] = dy.x; out9[7] = dy.y; out9[8] = dy.z;
+}
+// texture/noise.rs: noise (:70-103), fbm (:112-127), turbulence (:129-145)
+float orc_noise(float x, float y, float z) { return noise(x, y, z); }
+float orc_fbm(int turbulence, const float* p3, const float* dpdx3, const float* dpdy3, float omega, int octaves) {
+  return fbm_or_turbulence(turbulence != 0, V3(p3[0], p3[1], p3[2]), V3(dpdx3[0], dpdx3[1], dpdx3[2]),
+                           V3(dpdy3[0], dpdy3[1], dpdy3[2]), omega, octaves);
+}
+// material::bump (material/mod.rs:23-77) at a hand-built shading geometry.
+// dgs27 = p, dpdu, dpdv, dndu, dndv, nn, (u, v, dudx, dudy, dvdx, dvdy), (flip, 0, 0); ng3 = geometric normal.
+// out9 = bumped dpdu, dpdv, nn.
+void orc_bump(OrcScene* s, int tex_id, const float* dgs27, const float* ng3, float* out9) {
+  DiffGeom g;
+  const float* q = dgs27;
+  g.p = V3(q[0], q[1], q[2]);
+  g.dpdu = V3(q[3], q[4], q[5]);
+  g.dpdv = V3(q[6], q[7], q[8]);
+  g.dndu = V3(q[9], q[10], q[11]);
+  g.dndv = V3(q[12], q[13], q[14]);
+  g.nn = V3(q[15], q[16], q[17]);
+  g.u = q[18]; g.v = q[19]; g.dudx = q[20]; g.dudy = q[21]; g.dvdx = q[22]; g.dvdy = q[23];
+  g.flip = q[24] != 0.0f;
+  DiffGeom gg;
+  gg.nn = V3(ng3[0], ng3[1], ng3[2]);
+  DiffGeom b = bump_dg(s->sc.textures, tex_id, gg, g);
+  out9[0] = b.dpdu.x; out9[1] = b.dpdu.y; out9[2] = b.dpdu.z;
+  out9[3] = b.dpdv.x; out9[4] = b.dpdv.y; out9[5] = b.dpdv.z;
+  out9[6] = b.nn.x; out9[7] = b.nn.y; out9[8] = b.nn.z;
 }
 }  // extern "C"

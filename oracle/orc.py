@@ -87,6 +87,12 @@ def lib():
         L.orc_mipmap_level.argtypes = [C.c_void_p, u32, C.c_void_p]
         L.orc_mipmap_lookup.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_void_p]
         L.orc_image_texture_eval_planar.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_void_p]
+        L.orc_noise.restype = f32
+        L.orc_noise.argtypes = [f32, f32, f32]
+        L.orc_fbm.restype = f32
+        L.orc_fbm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, f32, C.c_int]
+        L.orc_mapping3d_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_bump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_sinc_1d.restype = f32
         L.orc_sinc_1d.argtypes = [f32, f32]
         L.orc_modulo.restype = i32
@@ -144,7 +150,8 @@ def _f(a):
 
 
 def _p(a):
-    return None if a is None else C.c_void_p(a.ctypes.data)
+    # data_as keeps a reference to the array, so a temporary stays alive until the call returns
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
 class OracleError(RuntimeError):
@@ -169,10 +176,10 @@ class OracleScene:
                 return 0
             if id(t) in tex_ids:
                 return tex_ids[id(t)]
-            a = tex(t.tex1) if t.kind == 1 else 0
-            b = tex(t.tex2) if t.kind == 1 else 0
+            kids = [tex(c) for c in t.children()] + [0, 0, 0]
+            a, b, c3 = kids[0], kids[1], kids[2]
             mk = t.mapping.kind if t.mapping is not None else 0
-            mp = _f(t.mapping.params if t.mapping is not None else [0] * 8)
+            mp = _f(t.mapping.params if t.mapping is not None else [0] * 12)
             if t.kind == 3:
                 im = t.image
                 tx = None if im["texels"] is None else _f(im["texels"])
@@ -182,14 +189,15 @@ class OracleScene:
                                             im["gamma"])
                 tex_ids[id(t)] = i
                 return i
-            i = L.orc_add_texture(self.h, t.kind, _p(_f(t.value)), mk, _p(mp), a, b, t.aa)
+            i = L.orc_add_texture(self.h, t.kind, _p(_f(t.value12())), mk, _p(mp), a, b, c3, t.aa)
             tex_ids[id(t)] = i
             return i
 
         def mat(m):
             if id(m) in mat_ids:
                 return mat_ids[id(m)]
-            i = L.orc_add_material(self.h, m.kind, tex(m.kd), tex(m.sigma), tex(m.ks), tex(m.roughness))
+            bm = -1 if getattr(m, "bump_map", None) is None else tex(m.bump_map)
+            i = L.orc_add_material(self.h, m.kind, tex(m.kd), tex(m.sigma), tex(m.ks), tex(m.roughness), bm)
             mat_ids[id(m)] = i
             return i
 

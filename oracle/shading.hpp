@@ -44,9 +44,33 @@ inline RGB operator/(const RGB& a, float s) { return RGB(a.c[0] / s, a.c[1] / s,
 // ---------------------------------------------------------------------------------------------
 // Textures (texture/mod.rs:52-66, checkerboard.rs:24-95, uv.rs:20-26, mapping2d.rs:49-77,175-210)
 struct Mapping2D {
-  int kind = 0;  // 0 = UVMapping2D(su,sv,du,dv) ; 1 = PlanarMapping2D(vs,vt,ds,dt)
+  // 0 = UVMapping2D(su,sv,du,dv) ; 1 = PlanarMapping2D(vs,vt,ds,dt) ;
+  // 2 = SphericalMapping2D(world_to_texture) ; 3 = CylindricalMapping2D(world_to_texture) ;
+  // 4 = IdentityMapping3D(world_to_texture) (mapping3d.rs:43-66; used through map3)
+  int kind = 0;
   float su = 1.f, sv = 1.f, du = 0.f, dv = 0.f;
   V3 vs{1, 0, 0}, vt{0, 1, 0};
+  Transform w2t = Transform::translate(V3(0.f, 0.f, 0.f));
+  // mapping2d.rs:120-133 / 155-166: the point as a unit vector ((1,0,0) at the origin)
+  V3 unit_vec(const V3& p) const {
+    V3 v = w2t.pt(p);
+    if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f) return V3(1.0f, 0.0f, 0.0f);
+    return normalize(v);
+  }
+  void circular(const V3& p, float* s, float* t) const {
+    V3 vec = unit_vec(p);
+    if (kind == 2) {  // sphere(): spherical_theta / spherical_phi (vector.rs:210-217)
+      const float FRAC_1_PI = 0.318309886183790671537767526745028724f;
+      float theta = std::acos(rclamp(vec.z, -1.0f, 1.0f));
+      float phi = std::atan2(vec.y, vec.x);
+      if (phi < 0.0f) phi = phi + 2.0f * PI_F;
+      *s = theta * FRAC_1_PI;
+      *t = phi * FRAC_1_PI * 0.5f;
+    } else {  // cylinder()
+      *s = (PI_F + std::atan2(vec.y, vec.x)) / (2.0f * PI_F);
+      *t = vec.z;
+    }
+  }
   void map(const DiffGeom& dg, float o[6]) const {  // (s, t, dsdx, dtdx, dsdy, dtdy)
     if (kind == 0) {
       o[0] = su * dg.u + du;
@@ -55,7 +79,7 @@ struct Mapping2D {
       o[3] = sv * dg.dvdx;
       o[4] = su * dg.dudy;
       o[5] = sv * dg.dvdy;
-    } else {
+    } else if (kind == 1) {
       V3 vec = dg.p;
       o[0] = du + dot(vec, vs);
       o[1] = dv + dot(vec, vt);
@@ -63,18 +87,123 @@ struct Mapping2D {
       o[3] = dot(vt, dg.dpdx);
       o[4] = dot(vs, dg.dpdy);
       o[5] = dot(vt, dg.dpdy);
+    } else {  // get_circular_differentials (mapping2d.rs:78-104)
+      float s, t;
+      circular(dg.p, &s, &t);
+      const float delta = 0.1f;
+      auto deal_with_singularity = [](float res) {
+        if (res > 0.5f) return 1.0f - res;
+        if (res < -0.5f) return -(res + 1.0f);
+        return res;
+      };
+      float sx, tx, sy, ty;
+      circular(dg.p + delta * dg.dpdx, &sx, &tx);
+      circular(dg.p + delta * dg.dpdy, &sy, &ty);
+      o[0] = s;
+      o[1] = t;
+      o[2] = (sx - s) / delta;
+      o[3] = deal_with_singularity((tx - t) / delta);
+      o[4] = (sy - s) / delta;
+      o[5] = deal_with_singularity((ty - t) / delta);
     }
   }
+  // IdentityMapping3D::map_dg (mapping3d.rs:57-63)
+  void map3(const DiffGeom& dg, V3* p, V3* dpdx, V3* dpdy) const {
+    *dpdx = w2t.vec(dg.dpdx);
+    *dpdy = w2t.vec(dg.dpdy);
+    *p = w2t.pt(dg.p);
+  }
 };
+
+// texture/noise.rs ---------------------------------------------------------------------------
+namespace noise_detail {
+static const uint8_t PERM[256] = {  // NOISE_PERM (noise.rs:6-55; the table is stored twice there)
+    151, 160, 137, 91,  90,  15,  131, 13,  201, 95,  96,  53,  194, 233, 7,   225, 140, 36,  103, 30,
+    69,  142, 8,   99,  37,  240, 21,  10,  23,  190, 6,   148, 247, 120, 234, 75,  0,   26,  197, 62,
+    94,  252, 219, 203, 117, 35,  11,  32,  57,  177, 33,  88,  237, 149, 56,  87,  174, 20,  125, 136,
+    171, 168, 68,  175, 74,  165, 71,  134, 139, 48,  27,  166, 77,  146, 158, 231, 83,  111, 229, 122,
+    60,  211, 133, 230, 220, 105, 92,  41,  55,  46,  245, 40,  244, 102, 143, 54,  65,  25,  63,  161,
+    1,   216, 80,  73,  209, 76,  132, 187, 208, 89,  18,  169, 200, 196, 135, 130, 116, 188, 159, 86,
+    164, 100, 109, 198, 173, 186, 3,   64,  52,  217, 226, 250, 124, 123, 5,   202, 38,  147, 118, 126,
+    255, 82,  85,  212, 207, 206, 59,  227, 47,  16,  58,  17,  182, 189, 28,  42,  223, 183, 170, 213,
+    119, 248, 152, 2,   44,  154, 163, 70,  221, 153, 101, 155, 167, 43,  172, 9,   129, 22,  39,  253,
+    19,  98,  108, 110, 79,  113, 224, 232, 178, 185, 112, 104, 218, 246, 97,  228, 251, 34,  242, 193,
+    238, 210, 144, 12,  191, 179, 162, 241, 81,  51,  145, 235, 249, 14,  239, 107, 49,  192, 214, 31,
+    181, 199, 106, 157, 184, 84,  204, 176, 115, 121, 50,  45,  127, 4,   150, 254, 138, 236, 205, 93,
+    222, 114, 67,  29,  24,  72,  243, 141, 128, 195, 78,  66,  215, 61,  156, 180};
+inline uint32_t perm(uint32_t i) { return PERM[i & 255u]; }  // index < 512 into the doubled table
+inline float grad(uint32_t x, uint32_t y, uint32_t z, float dx, float dy, float dz) {  // :57-62
+  uint32_t h = perm(perm(perm(x) + y) + z) & 15u;
+  float u = (h < 8 || h == 12 || h == 13) ? dx : dy;
+  float v = (h < 4 || h == 12 || h == 13) ? dy : dz;
+  return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+}
+inline float noise_weight(float t) {  // :64-68
+  float t3 = t * t * t;
+  float t4 = t3 * t;
+  return 6.0f * t4 * t - 15.0f * t4 + 10.0f * t3;
+}
+inline float lerp_with(float a, float b, float t) { return a * (1.0f - t) + b * t; }  // utils/mod.rs:20
+}  // namespace noise_detail
+inline float noise(float x, float y, float z) {  // noise.rs:70-103
+  using namespace noise_detail;
+  uint32_t ix = (uint32_t)(f2i(std::floor(x)) & 255);
+  uint32_t iy = (uint32_t)(f2i(std::floor(y)) & 255);
+  uint32_t iz = (uint32_t)(f2i(std::floor(z)) & 255);
+  float dx = x - std::floor(x), dy = y - std::floor(y), dz = z - std::floor(z);
+  float w000 = grad(ix, iy, iz, dx, dy, dz);
+  float w100 = grad(ix + 1, iy, iz, dx - 1.0f, dy, dz);
+  float w010 = grad(ix, iy + 1, iz, dx, dy - 1.0f, dz);
+  float w110 = grad(ix + 1, iy + 1, iz, dx - 1.0f, dy - 1.0f, dz);
+  float w001 = grad(ix, iy, iz + 1, dx, dy, dz - 1.0f);
+  float w101 = grad(ix + 1, iy, iz + 1, dx - 1.0f, dy, dz - 1.0f);
+  float w011 = grad(ix, iy + 1, iz + 1, dx, dy - 1.0f, dz - 1.0f);
+  float w111 = grad(ix + 1, iy + 1, iz + 1, dx - 1.0f, dy - 1.0f, dz - 1.0f);
+  float wx = noise_weight(dx), wy = noise_weight(dy), wz = noise_weight(dz);
+  float x00 = lerp_with(w000, w100, wx);
+  float x10 = lerp_with(w010, w110, wx);
+  float x01 = lerp_with(w001, w101, wx);
+  float x11 = lerp_with(w011, w111, wx);
+  float y0 = lerp_with(x00, x10, wy);
+  float y1 = lerp_with(x01, x11, wy);
+  return lerp_with(y0, y1, wz);
+}
+inline float smoothstep(float mn, float mx, float value) {  // noise.rs:107-110
+  float v = rclamp((value - mn) / (mx - mn), 0.0f, 1.0f);
+  return v * v * (-2.0f * v + 3.0f);
+}
+// fbm (noise.rs:112-127) and turbulence (:129-145).  As written, turbulence takes |noise| only
+// for the partial octave (pbrt-v2 takes it in the loop as well).
+inline float fbm_or_turbulence(bool turb, const V3& p, const V3& dpdx, const V3& dpdy, float omega,
+                               int max_octaves) {
+  float s2 = rmax(length_squared(dpdx), length_squared(dpdy));
+  float foctaves = rclamp(-1.0f - 0.5f * std::log2(s2), 0.0f, (float)max_octaves);
+  int32_t octaves = f2i(std::floor(foctaves));
+  float sum = 0.0f, lambda = 1.0f, o = 1.0f;
+  for (int32_t i = 0; i < octaves; ++i) {
+    float v = noise(lambda * p.x, lambda * p.y, lambda * p.z);
+    sum = sum + o * v;
+    lambda = lambda * 1.99f;
+    o = o * omega;
+  }
+  float partial_octave = foctaves - std::floor(foctaves);
+  float n = noise(lambda * p.x, lambda * p.y, lambda * p.z);
+  if (turb) n = std::fabs(n);
+  return sum + o * smoothstep(0.3f, 0.7f, partial_octave) * n;
+}
 }  // namespace orc
 #include "mipmap.hpp"  // MIPMap over RGB texels (needs RGB above)
 namespace orc {
 struct Texture {
-  int kind = 0;  // 0 = Constant, 1 = Checkerboard2D, 2 = UV, 3 = ImageTexture (tex1 = mipmap index)
+  // 0 = Constant, 1 = Checkerboard2D, 2 = UV, 3 = ImageTexture (tex1 = mipmap index),
+  // 4 = Scale (tex1 * tex2), 5 = Mix (tex1.lerp(tex2, tex3)), 6 = Bilerp (v00, v01, v10, v11),
+  // 7 = Dots (tex1 inside, tex2 outside), 8 = FBm, 9 = Wrinkled (value.c[0] = omega, aa = octaves)
+  int kind = 0;
   RGB value;     // Constant (float textures use c[0])
+  RGB bil[4];    // Bilerp corner values v00, v01, v10, v11
   Mapping2D mapping;
-  int tex1 = 0, tex2 = 0;  // Checkerboard children (indices)
-  int aa = 0;              // 0 = NONE, 1 = CLOSEDFORM
+  int tex1 = 0, tex2 = 0, tex3 = 0;  // children (indices)
+  int aa = 0;                         // Checkerboard: 0 = NONE, 1 = CLOSEDFORM ; FBm/Wrinkled: octaves
 };
 struct TextureTable {
   std::vector<Texture> t;
@@ -93,6 +222,42 @@ struct TextureTable {
         float m[6];
         tx.mapping.map(dg, m);
         return RGB(m[0] - std::floor(m[0]), m[1] - std::floor(m[1]), 0.0f);
+      }
+      case 4:  // ScaleTexture (texture/mod.rs:81-85)
+        return eval(tx.tex1, dg) * eval(tx.tex2, dg);
+      case 5: {  // MixTexture (mix.rs:22-27): tex1.lerp(tex2, amount)
+        RGB a = eval(tx.tex1, dg), b = eval(tx.tex2, dg);
+        float amt = eval(tx.tex3, dg).c[0];
+        return a * (1.0f - amt) + b * amt;
+      }
+      case 6: {  // BilerpTexture (bilerp.rs:28-35)
+        float m[6];
+        tx.mapping.map(dg, m);
+        RGB tmp1 = tx.bil[0] * (1.0f - m[0]) + tx.bil[2] * m[0];
+        RGB tmp2 = tx.bil[1] * (1.0f - m[0]) + tx.bil[3] * m[0];
+        return tmp1 * (1.0f - m[1]) + tmp2 * m[1];
+      }
+      case 7: {  // DotsTexture (dots.rs:23-46)
+        float m[6];
+        tx.mapping.map(dg, m);
+        float s = m[0], t_ = m[1];
+        float s_cell = std::floor(s + 0.5f), t_cell = std::floor(t_ + 0.5f);
+        if (noise(s_cell + 0.5f, t_cell + 0.5f, 0.5f) > 0.0f) {
+          const float radius = 0.35f;
+          const float max_shift = 0.5f - radius;
+          float s_center = s_cell + max_shift * noise(s_cell + 1.5f, t_cell + 2.8f, 0.5f);
+          float t_center = t_cell + max_shift * noise(s_cell + 4.5f, t_cell + 9.8f, 0.5f);
+          float ds = s - s_center, dt = t_ - t_center;
+          if (ds * ds + dt * dt < radius * radius) return eval(tx.tex1, dg);
+          return eval(tx.tex2, dg);
+        }
+        return eval(tx.tex2, dg);
+      }
+      case 8:
+      case 9: {  // FBmTexture / WrinkledTexture (fbm.rs:21-26, 42-47)
+        V3 p, dpdx, dpdy;
+        tx.mapping.map3(dg, &p, &dpdx, &dpdy);
+        return RGB(fbm_or_turbulence(tx.kind == 9, p, dpdx, dpdy, tx.value.c[0], tx.aa));
       }
       default: {
         float m[6];
@@ -126,7 +291,34 @@ struct TextureTable {
 struct Material {
   int kind = 0;  // 0 = Matte(kd, sigma), 1 = Plastic(kd, ks, roughness)
   int kd = 0, sigma = 0, ks = 0, roughness = 0;  // texture ids
+  int bump = -1;  // bump_map: Option<..> (matte.rs:15, plastic.rs:18): displacement texture or -1
 };
+
+// material::bump (material/mod.rs:23-77)
+inline DiffGeom bump_dg(const TextureTable& tt, int d, const DiffGeom& dg_geom, const DiffGeom& dg_shading) {
+  DiffGeom dg_eval = dg_shading;
+  float du = 0.5f * (std::fabs(dg_shading.dudx) + std::fabs(dg_shading.dudy));
+  if (du == 0.0f) du = 0.1f;
+  dg_eval.p = dg_shading.p + du * dg_shading.dpdu;
+  dg_eval.u = dg_shading.u + du;
+  dg_eval.nn = normalize(cross(dg_shading.dpdu, dg_shading.dpdv) + du * dg_shading.dndu);
+  float u_displace = tt.eval(d, dg_eval).c[0];
+  float dv = 0.5f * (std::fabs(dg_shading.dvdx) + std::fabs(dg_shading.dvdy));
+  if (dv == 0.0f) dv = 0.1f;
+  dg_eval.p = dg_shading.p + dv * dg_shading.dpdv;
+  dg_eval.u = dg_shading.u;
+  dg_eval.v = dg_shading.v + dv;
+  dg_eval.nn = normalize(cross(dg_shading.dpdu, dg_shading.dpdv) + dv * dg_shading.dndv);
+  float v_displace = tt.eval(d, dg_eval).c[0];
+  float displace = tt.eval(d, dg_shading).c[0];
+  DiffGeom dg_bump = dg_shading;
+  dg_bump.dpdu = dg_shading.dpdu + (u_displace - displace) / du * dg_shading.nn + displace * dg_shading.dndu;
+  dg_bump.dpdv = dg_shading.dpdv + (v_displace - displace) / dv * dg_shading.nn + displace * dg_shading.dndv;
+  dg_bump.nn = normalize(cross(dg_bump.dpdu, dg_bump.dpdv));
+  if (dg_shading.flip) dg_bump.nn = V3(-dg_bump.nn.x, -dg_bump.nn.y, -dg_bump.nn.z);
+  if (dot(dg_bump.nn, dg_geom.nn) < 0.0f) dg_bump.nn = -dg_bump.nn;  // face_forward (normal.rs:22-24)
+  return dg_bump;
+}
 
 // ---------------------------------------------------------------------------------------------
 // bsdf/*
@@ -537,6 +729,7 @@ inline RGB whitted_li(const Scene& sc, const RayDifferential& rayd, const Hit& h
   dg.compute_differentials(rayd);
   DiffGeom dgs = pr.kind == Prim::TRI ? tri_shading_geometry(pr, dg) : dg;
   const Material& mat = sc.materials[pr.material()];
+  if (mat.bump >= 0) dgs = bump_dg(sc.textures, mat.bump, dg, dgs);  // matte.rs:33-37, plastic.rs:35-39
   BSDF bsdf(dgs, dg.nn);
   if (mat.kind == 0) {  // matte.rs:30-51
     RGB r = sc.textures.eval(mat.kd, dgs).clamp(0.0f, F32_MAX);

@@ -38,12 +38,13 @@ class Mesh(C.Structure):
 
 
 class Texture(C.Structure):
-    _fields_ = [("kind", i32), ("value", f32 * 3), ("map_kind", i32), ("map", f32 * 8),
-                ("tex1", i32), ("tex2", i32), ("aa", i32)]
+    _fields_ = [("kind", i32), ("value", f32 * 12), ("map_kind", i32), ("map", f32 * 12),
+                ("tex1", i32), ("tex2", i32), ("tex3", i32), ("aa", i32)]
 
 
 class Material(C.Structure):
-    _fields_ = [("kind", i32), ("kd", i32), ("sigma", i32), ("ks", i32), ("roughness", i32)]
+    _fields_ = [("kind", i32), ("kd", i32), ("sigma", i32), ("ks", i32), ("roughness", i32),
+                ("bump", i32)]
 
 
 class Light(C.Structure):
@@ -133,8 +134,15 @@ SYMBOLS = [
     ("pbh_texture_checkerboard", i32, [_vp, C.c_int, _fp, C.c_int, C.c_int, C.c_int]),
     ("pbh_texture_uv", i32, [_vp, C.c_int, _fp]),
     ("pbh_texture_image", i32, [_vp, C.c_int, _fp, _fp, u32, u32, C.c_int, C.c_int, f32, C.c_int, f32, f32]),
-    ("pbh_material_matte", i32, [_vp, C.c_int, C.c_int]),
-    ("pbh_material_plastic", i32, [_vp, C.c_int, C.c_int, C.c_int]),
+    ("pbh_mapping_from_transform", i32, [_fp, _fp]),
+    ("pbh_texture_scale", i32, [_vp, C.c_int, C.c_int]),
+    ("pbh_texture_mix", i32, [_vp, C.c_int, C.c_int, C.c_int]),
+    ("pbh_texture_bilerp", i32, [_vp, C.c_int, _fp, _fp, _fp, _fp, _fp]),
+    ("pbh_texture_dots", i32, [_vp, C.c_int, _fp, C.c_int, C.c_int]),
+    ("pbh_texture_fbm", i32, [_vp, C.c_int, f32, _fp]),
+    ("pbh_texture_wrinkled", i32, [_vp, C.c_int, f32, _fp]),
+    ("pbh_material_matte", i32, [_vp, C.c_int, C.c_int, C.c_int]),
+    ("pbh_material_plastic", i32, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("pbh_light_point", i32, [_vp, _fp, _fp, _fp]),
     ("pbh_light_spot", i32, [_vp, _fp, _fp, _fp, f32, f32]),
     ("pbh_light_area", i32, [_vp, _fp, C.c_int]),

@@ -87,7 +87,7 @@ class UVMapping2D:
     kind = 0
 
     def __init__(self, su=1.0, sv=1.0, du=0.0, dv=0.0):
-        self.params = [su, sv, du, dv, 0, 0, 0, 0]
+        self.params = [su, sv, du, dv] + [0] * 8
 
 
 class PlanarMapping2D:
@@ -95,14 +95,58 @@ class PlanarMapping2D:
     kind = 1
 
     def __init__(self, vs=(1, 0, 0), vt=(0, 1, 0), ds=0.0, dt=0.0):
-        self.params = [*vs, *vt, ds, dt]
+        self.params = [*vs, *vt, ds, dt, 0, 0, 0, 0]
+
+
+def _w2t_params(xf):
+    """rows 0..2 of world_to_texture.m; only affine transforms are supported on the device."""
+    xf = Transform.new() if xf is None else xf
+    out = np.zeros(12, np.float32)
+    rc = lib().pbh_mapping_from_transform(_fp(_f(xf.m)), _fp(out))
+    if rc:
+        raise PbrtError(rc, "world_to_texture must be an affine transform (w row 0 0 0 1)")
+    return out.tolist()
+
+
+class SphericalMapping2D:
+    """src/texture/mapping2d.rs:106-143: SphericalMapping2D::new() / new_with(world_to_texture)"""
+    kind = 2
+
+    def __init__(self, world_to_texture=None):
+        self.params = _w2t_params(world_to_texture)
+
+
+class CylindricalMapping2D:
+    """src/texture/mapping2d.rs:145-173: CylindricalMapping2D::new() / new_with(world_to_texture)"""
+    kind = 3
+
+    def __init__(self, world_to_texture=None):
+        self.params = _w2t_params(world_to_texture)
+
+
+class IdentityMapping3D:
+    """src/texture/mapping3d.rs:43-66: IdentityMapping3D::new() / new_with(world_to_texture)"""
+    kind = 4
+
+    def __init__(self, world_to_texture=None):
+        self.params = _w2t_params(world_to_texture)
 
 
 class Texture:
-    """src/texture/mod.rs:52-66 (Constant), checkerboard.rs:24-95, uv.rs:20-26"""
+    """src/texture/mod.rs:52-86 (Constant, Scale), checkerboard.rs:24-95, uv.rs:20-26, mix.rs, bilerp.rs,
+    dots.rs, fbm.rs.  Float textures are RGB textures with three equal channels."""
 
-    def __init__(self, kind, value=(0, 0, 0), mapping=None, tex1=None, tex2=None, aa=0):
+    def __init__(self, kind, value=(0, 0, 0), mapping=None, tex1=None, tex2=None, aa=0, tex3=None):
         self.kind, self.value, self.mapping, self.tex1, self.tex2, self.aa = kind, value, mapping, tex1, tex2, aa
+        self.tex3 = tex3
+
+    def children(self):
+        return {1: (self.tex1, self.tex2), 4: (self.tex1, self.tex2), 5: (self.tex1, self.tex2, self.tex3),
+                7: (self.tex1, self.tex2)}.get(self.kind, ())
+
+    def value12(self):
+        v = [float(x) for x in np.ravel(self.value)]
+        return v + [0.0] * (12 - len(v))
 
     @staticmethod
     def constant(v):
@@ -116,6 +160,37 @@ class Texture:
     @staticmethod
     def uv(mapping):
         return Texture(2, mapping=mapping)
+
+    @staticmethod
+    def scale(t1, t2):
+        """ScaleTexture::new (texture/mod.rs:74-78): t1 * t2"""
+        return Texture(4, tex1=t1, tex2=t2)
+
+    @staticmethod
+    def mix(t1, t2, amount):
+        """MixTexture::new (texture/mix.rs:16-19): t1.lerp(t2, amount)"""
+        return Texture(5, tex1=t1, tex2=t2, tex3=amount)
+
+    @staticmethod
+    def bilerp(mapping, v00, v01, v10, v11):
+        """BilerpTexture::new (texture/bilerp.rs:19-26)"""
+        c = [(v, v, v) if np.isscalar(v) else tuple(v) for v in (v00, v01, v10, v11)]
+        return Texture(6, value=[x for q in c for x in q], mapping=mapping)
+
+    @staticmethod
+    def dots(mapping, inside, outside):
+        """DotsTexture::new (texture/dots.rs:17-20)"""
+        return Texture(7, mapping=mapping, tex1=inside, tex2=outside)
+
+    @staticmethod
+    def fbm(octaves, roughness, mapping=None):
+        """FBmTexture::new(oct, roughness, map) (texture/fbm.rs:15-19)"""
+        return Texture(8, value=(roughness, 0, 0), mapping=mapping or IdentityMapping3D(), aa=int(octaves))
+
+    @staticmethod
+    def wrinkled(octaves, roughness, mapping=None):
+        """WrinkledTexture::new(oct, roughness, map) (texture/fbm.rs:36-40)"""
+        return Texture(9, value=(roughness, 0, 0), mapping=mapping or IdentityMapping3D(), aa=int(octaves))
 
     WRAP = {"repeat": 0, "black": 1, "clamp": 2}  # ImageWrap (texture/imagewrap.rs)
 
@@ -139,18 +214,19 @@ class Texture:
 
 
 class Material:
-    """src/material/mod.rs:79-99"""
+    """src/material/mod.rs:79-99; bump_map: Option<ScalarTextureReference> (material::bump, mod.rs:23-77)"""
 
-    def __init__(self, kind, kd, sigma=None, ks=None, roughness=None):
+    def __init__(self, kind, kd, sigma=None, ks=None, roughness=None, bump_map=None):
         self.kind, self.kd, self.sigma, self.ks, self.roughness = kind, kd, sigma, ks, roughness
+        self.bump_map = bump_map
 
     @staticmethod
-    def matte(kd, sigma):
-        return Material(0, kd, sigma=sigma)
+    def matte(kd, sigma, bump_map=None):
+        return Material(0, kd, sigma=sigma, bump_map=bump_map)
 
     @staticmethod
-    def plastic(kd, ks, roughness):
-        return Material(1, kd, ks=ks, roughness=roughness)
+    def plastic(kd, ks, roughness, bump_map=None):
+        return Material(1, kd, ks=ks, roughness=roughness, bump_map=bump_map)
 
 
 class Shape:
@@ -376,18 +452,39 @@ class HostScene:
                                         int(im["do_trilinear"]), im["max_aniso"], im["wrap"], im["scale"], im["gamma"])
                 if i < 0:
                     raise PbrtError(L.pbh_last_error(self.h).decode())
-            else:
+            elif t.kind == 2:
                 i = L.pbh_texture_uv(self.h, t.mapping.kind, _fp(_f(t.mapping.params)))
+            elif t.kind == 4:
+                a, b = tex(t.tex1), tex(t.tex2)
+                i = L.pbh_texture_scale(self.h, a, b)
+            elif t.kind == 5:
+                a, b, c = tex(t.tex1), tex(t.tex2), tex(t.tex3)
+                i = L.pbh_texture_mix(self.h, a, b, c)
+            elif t.kind == 6:
+                v = _f(t.value12())
+                i = L.pbh_texture_bilerp(self.h, t.mapping.kind, _fp(_f(t.mapping.params)), _fp(v[0:3].copy()),
+                                         _fp(v[3:6].copy()), _fp(v[6:9].copy()), _fp(v[9:12].copy()))
+            elif t.kind == 7:
+                a, b = tex(t.tex1), tex(t.tex2)
+                i = L.pbh_texture_dots(self.h, t.mapping.kind, _fp(_f(t.mapping.params)), a, b)
+            elif t.kind in (8, 9):
+                fn = L.pbh_texture_fbm if t.kind == 8 else L.pbh_texture_wrinkled
+                i = fn(self.h, t.aa, float(t.value[0]), _fp(_f(t.mapping.params)))
+                if i < 0:
+                    raise PbrtError(i, L.pbh_last_error(self.h).decode())
+            else:
+                raise PbrtError(_ffi.EINVAL, f"unknown texture kind {t.kind}")
             tex_ids[id(t)] = i
             return i
 
         def mat(m):
             if id(m) in mat_ids:
                 return mat_ids[id(m)]
+            bm = -1 if m.bump_map is None else tex(m.bump_map)
             if m.kind == 0:
-                i = L.pbh_material_matte(self.h, tex(m.kd), tex(m.sigma))
+                i = L.pbh_material_matte(self.h, tex(m.kd), tex(m.sigma), bm)
             else:
-                i = L.pbh_material_plastic(self.h, tex(m.kd), tex(m.ks), tex(m.roughness))
+                i = L.pbh_material_plastic(self.h, tex(m.kd), tex(m.ks), tex(m.roughness), bm)
             mat_ids[id(m)] = i
             return i
 

@@ -78,6 +78,7 @@ struct pbrtb200_ctx {
   std::string err;
   // scene
   bool has_scene = false, has_spheres = false, multi_leaf = false;
+  bool shade_ext = false;  // the scene needs k_shade's general texture evaluator / bump mapping
   DScene sc{};
   std::vector<pbrtb200_light> h_lights;
   DevBuf d_nodes, d_tris, d_leaf_prim, d_leaf_count, d_spheres, d_sphere_o2w, d_meshes, d_tri_uv,
@@ -128,16 +129,38 @@ int upload(pbrtb200_ctx* ctx, DevBuf& buf, const T* src, size_t n) {
   return 0;
 }
 
+// Validates texture `id` and everything below it; returns its nesting depth or -1.  A texture with
+// children (checkerboard, scale, mix, dots) may sit at levels 0 .. PBRTB200_TEX_MAX_DEPTH-1.
 int tex_depth(const pbrtb200_scene* s, int id, int depth) {
   if (id < 0 || (uint32_t)id >= s->n_textures) return -1;
   const pbrtb200_texture& t = s->textures[id];
+  if (t.kind < 0 || t.kind > PBRTB200_TEX_KIND_MAX) return -1;
+  if (t.kind == PBRTB200_TEX_CONSTANT) return 0;
+  if (t.kind == PBRTB200_TEX_FBM || t.kind == PBRTB200_TEX_WRINKLED)
+    return (t.map_kind == PBRTB200_MAP_IDENTITY3D && t.aa >= 0) ? 0 : -1;
+  const bool mapped = t.kind != PBRTB200_TEX_SCALE && t.kind != PBRTB200_TEX_MIX;
+  if (mapped && (t.map_kind < 0 || t.map_kind > PBRTB200_MAP_CYLINDRICAL)) return -1;
   if (t.kind == PBRTB200_TEX_IMAGE) return (t.tex1 >= 0 && (uint32_t)t.tex1 < s->n_mipmaps) ? 0 : -1;
-  if (t.kind < 0 || t.kind > PBRTB200_TEX_IMAGE) return -1;
-  if (t.kind != PBRTB200_TEX_CHECKER2D) return 0;
-  if (depth > 3) return -1;
-  int a = tex_depth(s, t.tex1, depth + 1), b = tex_depth(s, t.tex2, depth + 1);
-  if (a < 0 || b < 0) return -1;
-  return 1 + std::max(a, b);
+  if (t.kind == PBRTB200_TEX_UV || t.kind == PBRTB200_TEX_BILERP) return 0;
+  if (depth >= PBRTB200_TEX_MAX_DEPTH) return -1;
+  int d = 0;
+  const int kids[3] = {t.tex1, t.tex2, t.kind == PBRTB200_TEX_MIX ? t.tex3 : t.tex2};
+  for (int k : kids) {
+    const int c = tex_depth(s, k, depth + 1);
+    if (c < 0) return -1;
+    d = std::max(d, c);
+  }
+  return 1 + d;
+}
+// Does the scene need the general texture evaluator (k_shade<.., EXT = true>)?
+bool scene_needs_ext(const pbrtb200_scene* s) {
+  for (uint32_t i = 0; i < s->n_textures; ++i)
+    if (s->textures[i].kind > PBRTB200_TEX_IMAGE ||
+        (s->textures[i].kind != PBRTB200_TEX_CONSTANT && s->textures[i].map_kind > PBRTB200_MAP_PLANAR))
+      return true;
+  for (uint32_t i = 0; i < s->n_materials; ++i)
+    if (s->materials[i].bump >= 0) return true;
+  return false;
 }
 
 int trace_grid(pbrtb200_ctx* ctx, const void* kernel) {
@@ -576,6 +599,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
       FAIL(PBRTB200_EINVAL, "material sigma texture invalid");
     if (m.kind == PBRTB200_MAT_PLASTIC && (tex_depth(s, m.ks, 0) < 0 || tex_depth(s, m.roughness, 0) < 0))
       FAIL(PBRTB200_EINVAL, "material ks/roughness texture invalid");
+    if (m.bump >= 0 && tex_depth(s, m.bump, 0) < 0) FAIL(PBRTB200_EINVAL, "material bump texture invalid");
   }
   for (uint32_t i = 0; i < s->n_mipmaps; ++i) {  // every level must lie inside the texel pool
     const pbrtb200_mipmap& m = s->mipmaps[i];
@@ -632,6 +656,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
     bool v = varying(m.kd);
     if (m.kind == PBRTB200_MAT_MATTE) v = v || varying(m.sigma);
     if (m.kind == PBRTB200_MAT_PLASTIC) v = v || varying(m.ks) || varying(m.roughness);
+    if (m.bump >= 0) v = true;  // material::bump reads dudx .. dvdy (material/mod.rs:30-32, 45-47)
     mat_flags[i] = v ? 1 : 0;
   }
   if (upload(ctx, ctx->d_mat_flags, mat_flags.data(), mat_flags.size())) return PBRTB200_ENODEV;
@@ -654,6 +679,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   sc.textures = ctx->d_textures.as<pbrtb200_texture>();
   sc.mipmaps = s->n_mipmaps ? ctx->d_mipmaps.as<pbrtb200_mipmap>() : nullptr;
   sc.texels = s->n_mipmaps ? ctx->d_texels.as<float4>() : nullptr;
+  ctx->shade_ext = scene_needs_ext(s);
   sc.n_prims = s->n_prims;
   sc.n_lights = s->n_lights;
   {
@@ -1173,7 +1199,9 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       sa.rad_slots = rad_slots;
       sa.le_slot = le_slot;
       sa.strict_flags = integ->strict_flags;
-      if (ctx->sc.mipmaps)
+      if (ctx->shade_ext)
+        k_shade<PB_SHADE_EXT_MIN_BLOCKS, true, true><<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
+      else if (ctx->sc.mipmaps)
         k_shade<PB_SHADE_MIN_BLOCKS, true><<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
       else
         k_shade<PB_SHADE_MIN_BLOCKS, false><<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);

@@ -4,10 +4,29 @@
 // neither contracts a*b+c into an FMA nor substitutes approximate div/sqrt — Rust does neither,
 // and primary-hit primitive ids are required to match bit-exactly.
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
-
+#ifdef PB_HOST_CHECK
+// Host compilation of the device arithmetic for the CPU test-suite (tests/devsrc/): the few CUDA
+// intrinsics used below get plain C++ equivalents.  Never part of the product build.
+#include <cmath>
+#define PB_DEV inline
+struct float4 {
+  float x, y, z, w;
+};
+inline int __float2int_rz(float x) {  // cvt.rzi.s32.f32: saturating, NaN -> 0
+  if (std::isnan(x)) return 0;
+  if (x >= 2147483648.0f) return INT32_MAX;
+  if (x <= -2147483648.0f) return INT32_MIN;
+  return (int)x;
+}
+inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, int c) {
+  c &= 31;
+  return c ? (hi << c) | (lo >> (32 - c)) : hi;
+}
+#else
+#include <cuda_runtime.h>
 #define PB_DEV __device__ __forceinline__
+#endif
 #define PB_F32_MAX 3.402823466e+38f
 #define PB_PI 3.14159265358979323846f
 

@@ -588,25 +588,90 @@ int pbh_texture_constant(pbh_scene* s, const float rgb[3]) {
   s->textures.push_back(t);
   return (int)s->textures.size() - 1;
 }
-int pbh_texture_checkerboard(pbh_scene* s, int map_kind, const float map[8], int tex1, int tex2,
+int pbh_texture_checkerboard(pbh_scene* s, int map_kind, const float map[12], int tex1, int tex2,
                              int antialiased) {
   pbrtb200_texture t{};
   t.kind = PBRTB200_TEX_CHECKER2D;
   t.map_kind = map_kind;
-  std::memcpy(t.map, map, 32);
+  std::memcpy(t.map, map, 48);
   t.tex1 = tex1;
   t.tex2 = tex2;
   t.aa = antialiased ? 1 : 0;
   s->textures.push_back(t);
   return (int)s->textures.size() - 1;
 }
-int pbh_texture_uv(pbh_scene* s, int map_kind, const float map[8]) {
+int pbh_texture_uv(pbh_scene* s, int map_kind, const float map[12]) {
   pbrtb200_texture t{};
   t.kind = PBRTB200_TEX_UV;
   t.map_kind = map_kind;
-  std::memcpy(t.map, map, 32);
+  std::memcpy(t.map, map, 48);
   s->textures.push_back(t);
   return (int)s->textures.size() - 1;
+}
+int pbh_mapping_from_transform(const float m[16], float map[12]) {
+  if (m[12] != 0.f || m[13] != 0.f || m[14] != 0.f || m[15] != 1.f) return PBRTB200_EINVAL;
+  std::memcpy(map, m, 48);
+  return PBRTB200_OK;
+}
+int pbh_texture_scale(pbh_scene* s, int tex1, int tex2) {
+  pbrtb200_texture t{};
+  t.kind = PBRTB200_TEX_SCALE;
+  t.tex1 = tex1;
+  t.tex2 = tex2;
+  s->textures.push_back(t);
+  return (int)s->textures.size() - 1;
+}
+int pbh_texture_mix(pbh_scene* s, int tex1, int tex2, int amount) {
+  pbrtb200_texture t{};
+  t.kind = PBRTB200_TEX_MIX;
+  t.tex1 = tex1;
+  t.tex2 = tex2;
+  t.tex3 = amount;
+  s->textures.push_back(t);
+  return (int)s->textures.size() - 1;
+}
+int pbh_texture_bilerp(pbh_scene* s, int map_kind, const float map[12], const float v00[3],
+                       const float v01[3], const float v10[3], const float v11[3]) {
+  pbrtb200_texture t{};
+  t.kind = PBRTB200_TEX_BILERP;
+  t.map_kind = map_kind;
+  std::memcpy(t.map, map, 48);
+  std::memcpy(t.value + 0, v00, 12);
+  std::memcpy(t.value + 3, v01, 12);
+  std::memcpy(t.value + 6, v10, 12);
+  std::memcpy(t.value + 9, v11, 12);
+  s->textures.push_back(t);
+  return (int)s->textures.size() - 1;
+}
+int pbh_texture_dots(pbh_scene* s, int map_kind, const float map[12], int inside, int outside) {
+  pbrtb200_texture t{};
+  t.kind = PBRTB200_TEX_DOTS;
+  t.map_kind = map_kind;
+  std::memcpy(t.map, map, 48);
+  t.tex1 = inside;
+  t.tex2 = outside;
+  s->textures.push_back(t);
+  return (int)s->textures.size() - 1;
+}
+static int noise_texture(pbh_scene* s, int kind, int octaves, float roughness, const float w2t[12]) {
+  if (octaves < 0) {  // f32::clamp(0.0, max) panics when max < min (noise.rs:116)
+    s->err = "fbm/wrinkled texture: octaves must be >= 0";
+    return PBRTB200_EINVAL;
+  }
+  pbrtb200_texture t{};
+  t.kind = kind;
+  t.map_kind = PBRTB200_MAP_IDENTITY3D;
+  std::memcpy(t.map, w2t, 48);
+  t.value[0] = roughness;
+  t.aa = octaves;
+  s->textures.push_back(t);
+  return (int)s->textures.size() - 1;
+}
+int pbh_texture_fbm(pbh_scene* s, int octaves, float roughness, const float w2t[12]) {
+  return noise_texture(s, PBRTB200_TEX_FBM, octaves, roughness, w2t);
+}
+int pbh_texture_wrinkled(pbh_scene* s, int octaves, float roughness, const float w2t[12]) {
+  return noise_texture(s, PBRTB200_TEX_WRINKLED, octaves, roughness, w2t);
 }
 
 // ---- ImageTexture / MIPMap construction (texture/mipmap.rs, texture/imagemap.rs) ----------------
@@ -692,7 +757,7 @@ void mip_resize_pot(size_t w, size_t h, const std::vector<Tex3>& px, int wrap, s
 }
 }  // namespace
 
-int pbh_texture_image(pbh_scene* s, int map_kind, const float map[8], const float* rgb, uint32_t w,
+int pbh_texture_image(pbh_scene* s, int map_kind, const float map[12], const float* rgb, uint32_t w,
                       uint32_t h, int spectrum, int do_trilinear, float max_aniso, int wrap,
                       float scale, float gamma) {
   if (wrap < 0 || wrap > 2) {
@@ -767,22 +832,24 @@ int pbh_texture_image(pbh_scene* s, int map_kind, const float map[8], const floa
   pbrtb200_texture t{};
   t.kind = PBRTB200_TEX_IMAGE;
   t.map_kind = map_kind;
-  std::memcpy(t.map, map, 32);
+  std::memcpy(t.map, map, 48);
   t.tex1 = (int32_t)s->mipmaps.size() - 1;
   s->textures.push_back(t);
   return (int)s->textures.size() - 1;
 }
 
-int pbh_material_matte(pbh_scene* s, int kd, int sigma) {
+int pbh_material_matte(pbh_scene* s, int kd, int sigma, int bump_map) {
   pbrtb200_material m{};
+  m.bump = bump_map < 0 ? -1 : bump_map;
   m.kind = PBRTB200_MAT_MATTE;
   m.kd = kd;
   m.sigma = sigma;
   s->materials.push_back(m);
   return (int)s->materials.size() - 1;
 }
-int pbh_material_plastic(pbh_scene* s, int kd, int ks, int roughness) {
+int pbh_material_plastic(pbh_scene* s, int kd, int ks, int roughness, int bump_map) {
   pbrtb200_material m{};
+  m.bump = bump_map < 0 ? -1 : bump_map;
   m.kind = PBRTB200_MAT_PLASTIC;
   m.kd = kd;
   m.ks = ks;

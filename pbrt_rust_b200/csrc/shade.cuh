@@ -16,13 +16,7 @@
 #pragma once
 #include "scene.cuh"
 #include "trace.cuh"
-
-struct DG {
-  f3 p, nn;
-  float u, v;
-  f3 dpdu, dpdv, dndu, dndv, dpdx, dpdy;
-  float dudx, dudy, dvdx, dvdy;
-};
+#include "shade_tex.cuh"  // DG, texture mappings, procedural textures, bump
 
 // diff_geom.rs:52-79
 PB_DEV DG dg_new(f3 p, f3 dpdu, f3 dpdv, f3 dndu, f3 dndv, float u, float v, bool flip) {
@@ -249,28 +243,6 @@ PB_DEV DG sphere_dg(const pbrtb200_sphere80& s, const float* o2w, f3 ow, f3 dw, 
 }
 
 // ---- textures ---------------------------------------------------------------------------------
-PB_DEV void tex_map(const pbrtb200_texture& tx, const DG& dg, float m[6]) {
-  if (tx.map_kind == PBRTB200_MAP_UV) {  // mapping2d.rs:66-76
-    m[0] = tx.map[0] * dg.u + tx.map[2];
-    m[1] = tx.map[1] * dg.v + tx.map[3];
-    m[2] = tx.map[0] * dg.dudx;
-    m[3] = tx.map[1] * dg.dvdx;
-    m[4] = tx.map[0] * dg.dudy;
-    m[5] = tx.map[1] * dg.dvdy;
-  } else {  // mapping2d.rs:199-210
-    const f3 vs = mk3(tx.map[0], tx.map[1], tx.map[2]), vt = mk3(tx.map[3], tx.map[4], tx.map[5]);
-    m[0] = tx.map[6] + dot3(dg.p, vs);
-    m[1] = tx.map[7] + dot3(dg.p, vt);
-    m[2] = dot3(vs, dg.dpdx);
-    m[3] = dot3(vt, dg.dpdx);
-    m[4] = dot3(vs, dg.dpdy);
-    m[5] = dot3(vt, dg.dpdy);
-  }
-}
-PB_DEV float bump_int_(float x) {  // checkerboard.rs:62-66
-  const float half_x = x / 2.0f;
-  return floorf(half_x) + 2.0f * fmaxf(half_x - floorf(half_x) - 0.5f, 0.0f);
-}
 // ---- ImageTexture: MIPMap::lookup (texture/mipmap.rs:206-341) -----------------------------------
 // Level l of a map starts where level l-1 ends (row-major RGB float4 texels, include/pbrtb200.h).
 struct DMipLevel {
@@ -571,6 +543,20 @@ PB_DEV uint32_t warp_agg_inc(uint32_t* ctr) {
 #define PB_SHADE_MIN_BLOCKS 8  // 64 registers: the stage is latency-bound, occupancy wins (profiles/r01_notes.md)
 #endif
 
+// Texture lookup of the shading kernel: the inlined evaluator of the common kinds, or the general
+// out-of-line one (EXT).
+template <bool IMG, bool EXT>
+PB_DEV f3 shade_tex(const DScene& sc, const TexEnv& env, int id, const DG& dg) {
+  if constexpr (EXT)
+    return tex_eval_ext<PBRTB200_TEX_MAX_DEPTH>(env, id, dg);
+  else
+    return tex_eval<3, IMG>(sc, id, dg);
+}
+
+#ifndef PB_SHADE_EXT_MIN_BLOCKS
+#define PB_SHADE_EXT_MIN_BLOCKS 4  // general texture evaluator + bump: 128 registers
+#endif
+
 struct ShadeArgs {
   const float2* __restrict__ img;
   const float2* __restrict__ lens;    // may be NULL
@@ -594,7 +580,10 @@ struct ShadeArgs {
 
 // IMG: the scene has image textures (a separate instantiation keeps the MIPMap code, its
 // registers and its call-site spills out of the kernel every other scene runs).
-template <int MIN_BLOCKS, bool IMG>
+// EXT: the scene uses spherical / cylindrical mappings, scale / mix / bilerp / dots / fbm /
+// wrinkled textures or bump maps: every texture goes through the out-of-line general evaluator
+// (shade_tex.cuh) and material::bump runs before the BSDF frame is built.
+template <int MIN_BLOCKS, bool IMG, bool EXT = false>
 __global__ void __launch_bounds__(128, MIN_BLOCKS)
 k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -670,10 +659,12 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   DG dg, dgs;
   uint32_t material;
   int32_t area_light = -1;
+  [[maybe_unused]] bool shape_flip = false;  // reverse_orientation ^ transform_swaps_handedness (bump)
   if (pr & PB_LEAF_BIT) {
     const uint32_t si = pr & ~PB_LEAF_BIT;
     const pbrtb200_sphere80 sp = sc.spheres[si];
     material = sp.material;
+    if constexpr (EXT) shape_flip = (sp.flip & 1u) != 0;
     dg = sphere_dg(sp, sc.sphere_o2w + 12ull * si, o, d, t_hit, hb1);
     if (__ldg(&sc.mat_flags[material]) & 1u) differentials(dg);
     dgs = dg;
@@ -682,6 +673,7 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
     const pbrtb200_mesh m = sc.meshes[td.mesh];
     material = m.material;
     area_light = m.area_light;
+    if constexpr (EXT) shape_flip = m.flip != 0;
     dg = tri_dg(td, o, d, t_hit, hb1, hb2, m.flip != 0);
     if (__ldg(&sc.mat_flags[material]) & 1u) differentials(dg);
     dgs = tri_shading_geometry(sc, td, m, dg);
@@ -689,19 +681,27 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   ray_epsilon = t_hit * 5e-4f;  // mesh.rs:262, sphere.rs:180
 
   // Material::get_bsdf
+  const pbrtb200_material mat = sc.materials[material];
+  [[maybe_unused]] TexEnv env;
+  if constexpr (EXT) {
+    env.textures = sc.textures;
+    env.mipmaps = sc.mipmaps;
+    env.texels = sc.texels;
+    // matte.rs:33-37 / plastic.rs:35-39: bump(tex, &dg_geom, &dg_shading)
+    if (mat.bump >= 0) dgs = bump_dg_(env, mat.bump, dgs, dg.nn, shape_flip);
+  }
   bs.nn = dgs.nn;                      // bsdf/mod.rs:70-86
   bs.tn = bs.sn = mk3(0.f, 0.f, 0.f);  // filled below for BxDFs that read the local frame
   bs.ng = dg.nn;
   bs.ks = mk3(0.f, 0.f, 0.f);
   bs.a = bs.b = 0.f;
-  const pbrtb200_material mat = sc.materials[material];
   {
-    f3 kd = tex_eval<3, IMG>(sc, mat.kd, dgs);
+    f3 kd = shade_tex<IMG, EXT>(sc, env, mat.kd, dgs);
     bs.kd = mk3(rclampf(kd.x, 0.0f, PB_F32_MAX), rclampf(kd.y, 0.0f, PB_F32_MAX),
                 rclampf(kd.z, 0.0f, PB_F32_MAX));
   }
   if (mat.kind == PBRTB200_MAT_MATTE) {  // matte.rs:30-51
-    const float sig = rclampf(tex_eval<3, IMG>(sc, mat.sigma, dgs).x, 0.0f, 90.0f);
+    const float sig = rclampf(shade_tex<IMG, EXT>(sc, env, mat.sigma, dgs).x, 0.0f, 90.0f);
     if (sig == 0.0f) {
       bs.kind = 0;
     } else {  // orennayar.rs:16-29
@@ -713,10 +713,10 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
     }
   } else {  // plastic.rs:32-55
     bs.kind = 2;
-    const f3 ks = tex_eval<3, IMG>(sc, mat.ks, dgs);
+    const f3 ks = shade_tex<IMG, EXT>(sc, env, mat.ks, dgs);
     bs.ks = mk3(rclampf(ks.x, 0.0f, PB_F32_MAX), rclampf(ks.y, 0.0f, PB_F32_MAX),
                 rclampf(ks.z, 0.0f, PB_F32_MAX));
-    const float rough = tex_eval<3, IMG>(sc, mat.roughness, dgs).x;
+    const float rough = shade_tex<IMG, EXT>(sc, env, mat.roughness, dgs).x;
     float e = 1.0f / rough;
     if (e > 1000.0f || isnan(e)) e = 1000.0f;  // microfacet.rs:18-24
     bs.a = e;

@@ -11,7 +11,7 @@ f32 = np.float32
 
 
 def _p(a):
-    return C.c_void_p(a.ctypes.data)
+    return a.ctypes.data_as(C.c_void_p)  # keeps the array alive for the duration of the call
 
 
 def _ray(o, d, mint=0.0, maxt=F32_MAX):
@@ -797,9 +797,14 @@ def _dg15(p=(0, 0, 0), dpdx=(0, 0, 0), dpdy=(0, 0, 0), u=0.0, v=0.0, dudx=0.0, d
     return np.array([*p, *dpdx, *dpdy, u, v, dudx, dudy, dvdx, dvdy], np.float32)
 
 
+def _pad12(v):
+    v = [float(x) for x in np.ravel(v)]
+    return np.array(v + [0.0] * (12 - len(v)), np.float32)
+
+
 def _map(orc, kind, params, dg):
-    out = np.zeros(6, np.float32)
-    orc.lib().orc_mapping_map(kind, _p(np.array(params, np.float32)), _p(dg), _p(out))
+    out, m = np.zeros(6, np.float32), _pad12(params)
+    orc.lib().orc_mapping_map(kind, _p(m), _p(dg), _p(out))
     return out
 
 
@@ -811,9 +816,9 @@ class _TexScene:
         self.L.orc_scene_new.restype = C.c_void_p
         self.h = C.c_void_p(self.L.orc_scene_new())
 
-    def add(self, kind, value=(0, 0, 0), map_kind=1, params=(1, 0, 0, 0, 1, 0, 0, 0), t1=0, t2=0, aa=0):
-        return self.L.orc_add_texture(self.h, kind, _p(np.array(value, np.float32)), map_kind,
-                                      _p(np.array(params, np.float32)), t1, t2, aa)
+    def add(self, kind, value=(0, 0, 0), map_kind=1, params=(1, 0, 0, 0, 1, 0, 0, 0), t1=0, t2=0, aa=0, t3=0):
+        v, m = _pad12(value), _pad12(params)  # keep both arrays alive across the call
+        return self.L.orc_add_texture(self.h, kind, _p(v), map_kind, _p(m), t1, t2, t3, aa)
 
     def eval(self, tex, dg):
         out = np.zeros(3, np.float32)
@@ -881,3 +886,171 @@ def test_planar_mapping_differentials(orc):
         b = _map(orc, 1, params, _dg15(p=p + dx * dpdx + dy * dpdy, dpdx=dpdx, dpdy=dpdy))
         assert np.abs(a[2:] - b[2:]).max() < 0.01
         assert abs(a[0] + dx * a[2] + dy * a[4] - b[0]) < 1e-3 and abs(a[1] + dx * a[3] + dy * a[5] - b[1]) < 1e-3
+
+
+# ---- spherical / cylindrical / 3D mappings, scale / mix / bilerp textures, noise ------------------
+
+def _w2t(orc, *ops):
+    """rows 0..2 of a product of transforms: ops = (kind, args) as for _xf"""
+    m = np.eye(4, dtype=np.float32)
+    for kind, a in ops:
+        mm, _ = _xf(orc, kind, a)
+        m = (m.astype(np.float32) @ np.asarray(mm, np.float32).reshape(4, 4)).astype(np.float32)
+    return m.reshape(-1)[:12]
+
+
+_IDENT12 = (1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0)
+
+
+def _positional_differentials(orc, kind, params):
+    """texture/mapping2d.rs:248-284 test_positional_differentials"""
+    base = _map(orc, kind, params, _dg15())
+    assert _map(orc, kind, params, _dg15(u=0.5, v=0.1, dudx=10, dudy=12, dvdx=-1, dvdy=0)).tolist() == base.tolist()
+    p, dpdx, dpdy = np.array([0.3, 1.2, -4.0], np.float32), np.array([0.2, 0.0, -0.3], np.float32), np.array([-0.5, 0.1, 1.3], np.float32)
+    a = _map(orc, kind, params, _dg15(p=p, dpdx=dpdx, dpdy=dpdy))
+    dx, dy = f32(0.1), f32(-0.1)
+    b = _map(orc, kind, params, _dg15(p=p + dx * dpdx + dy * dpdy, dpdx=dpdx, dpdy=dpdy))
+    assert np.abs(a[2:] - b[2:]).max() < 0.01
+    assert abs(a[0] + dx * a[2] + dy * a[4] - b[0]) < 1e-3 and abs(a[1] + dx * a[3] + dy * a[5] - b[1]) < 1e-3
+
+
+@pytest.mark.parametrize("kind", [2, 3])
+def test_spherical_and_cylindrical_mapping_can_map_coords(orc, kind):
+    """texture/mapping2d.rs:335-375 (spherical) and :392-432 (cylindrical)"""
+    assert _map(orc, kind, _IDENT12, _dg15()).tolist() == [0.5, 0.0, 0.0, 0.0, 0.0, 0.0]
+    assert _map(orc, kind, _IDENT12, _dg15(u=0.5, v=0.2)).tolist() == [0.5, 0.0, 0.0, 0.0, 0.0, 0.0]
+    s, t = _map(orc, kind, _IDENT12, _dg15(p=(0.1, 0.2, 0.6)))[:2]
+    assert s != 0.0 and t != 0.0
+    for i in range(1, 9):
+        di = f32(i) / f32(10.0)
+        ns, nt = _map(orc, kind, _IDENT12, _dg15(p=(f32(0.1) * di, f32(0.2) * di, f32(0.6) * di)))[:2]
+        assert abs(s - ns) < 1e-5 and abs(t - nt) < 1e-5
+    # transformed_*_mapping_can_map_coords: translate(1,2,3) at the origin == identity at (1,2,3)
+    tr = _w2t(orc, (0, [1.0, 2.0, 3.0]))
+    assert _map(orc, kind, tr, _dg15()).tolist() == _map(orc, kind, _IDENT12, _dg15(p=(1.0, 2.0, 3.0))).tolist()
+
+
+@pytest.mark.parametrize("kind", [2, 3])
+def test_spherical_and_cylindrical_mapping_differentials(orc, kind):
+    """texture/mapping2d.rs:377-390, 434-447: identity and translate(1,2,3) * rotate_x(45)"""
+    _positional_differentials(orc, kind, _IDENT12)
+    _positional_differentials(orc, kind, _w2t(orc, (0, [1.0, 2.0, 3.0]), (2, [45.0, 0, 0])))
+
+
+def test_identity_mapping_3d(orc):
+    """texture/mapping3d.rs:70-116 test_positional_differentials for IdentityMapping3D"""
+    L = orc.lib()
+
+    def m3(params, dg):
+        out, m = np.zeros(9, np.float32), _pad12(params)
+        L.orc_mapping3d_map(_p(m), _p(dg), _p(out))
+        return out
+
+    for params in (_IDENT12, _w2t(orc, (0, [1.0, 2.0, 3.0]), (2, [45.0, 0, 0]))):
+        base = m3(params, _dg15())
+        assert m3(params, _dg15(u=0.5, v=0.1, dudx=10, dudy=12, dvdx=-1, dvdy=0)).tolist() == base.tolist()
+        p, dpdx, dpdy = np.array([0.3, 1.2, -4.0], np.float32), np.array([0.2, 0.0, -0.3], np.float32), np.array([-0.5, 0.1, 1.3], np.float32)
+        a = m3(params, _dg15(p=p, dpdx=dpdx, dpdy=dpdy))
+        dx, dy = f32(0.1), f32(-0.1)
+        b = m3(params, _dg15(p=p + dx * dpdx + dy * dpdy, dpdx=dpdx, dpdy=dpdy))
+        assert a[3:].tolist() == b[3:].tolist()
+        ep = a[0:3] + dx * a[3:6] + dy * a[6:9]
+        assert float(np.sum((ep - b[0:3]) ** 2)) < 1e-3
+
+
+def test_scale_mix_and_bilerp_textures(orc):
+    """texture/mod.rs:99-105 scale_texture_works, mix.rs:35-45 mix_texture_works,
+    bilerp.rs:45-61 bilerp_texture_works"""
+    ts = _TexScene(orc)
+    two, vec = ts.add(0, value=(2, 2, 2)), ts.add(0, value=(1, 2, 3))
+    assert ts.eval(ts.add(4, t1=two, t2=vec), _dg15()).tolist() == [2.0, 4.0, 6.0]
+    a, b, amt = ts.add(0, value=(1, -2, 15)), ts.add(0, value=(1, 2, 3)), ts.add(0, value=(0.75, 0.75, 0.75))
+    assert ts.eval(ts.add(5, t1=a, t2=b, t3=amt), _dg15()).tolist() == [1.0, 1.0, 6.0]
+    bil = ts.add(6, value=(2, 2, 2, 3, 3, 3, 1, 1, 1, 4, 4, 4), map_kind=0, params=(1, 1, 0, 0))
+    assert ts.eval(bil, _dg15())[0] == 2.0
+    assert ts.eval(bil, _dg15(u=0.5, v=0.5))[0] == 2.5
+    assert ts.eval(bil, _dg15(u=1.0, v=0.5))[0] == 2.5
+    assert ts.eval(bil, _dg15(u=1.0, v=1.0))[0] == 4.0
+
+
+def test_noise(orc):
+    """texture/noise.rs:151-175 noise_is_zero_at_integers / noise_is_nonzero_at_nonintegers"""
+    L = orc.lib()
+    for i in range(-10, 10):
+        for j in range(-10, 10):
+            for k in range(-10, 10):
+                assert L.orc_noise(float(i), float(j), float(k)) == 0.0
+                v = abs(L.orc_noise(f32(i) + f32(0.3), f32(j) + f32(0.2), f32(k) + f32(0.1)))
+                assert 0.0 < v <= 1.0
+
+
+@pytest.mark.parametrize("turb,p", [(0, (0.3, -0.4, 10.2)), (1, (0.3, -0.3, 10.2))])
+def test_fbm_and_turbulence_are_more_or_less_continuous(orc, turb, p):
+    """texture/noise.rs:177-213"""
+    L = orc.lib()
+    dpdx, dpdy = np.array([0.1, 0, 0], np.float32), np.array([0, 0.1, 0], np.float32)
+    p = np.array(p, np.float32)
+    v = L.orc_fbm(turb, _p(p), _p(dpdx), _p(dpdy), 1.0, 10)
+    q = p + np.array([0.01, -0.01, 0.005], np.float32)
+    v2 = L.orc_fbm(turb, _p(q), _p(dpdx), _p(dpdy), 1.0, 10)
+    assert abs(v) > 0.0 and abs(v2) > 0.0 and v != v2 and abs(v - v2) < 0.06
+
+
+def test_dots_and_noise_textures_through_the_table(orc):
+    """DotsTexture (dots.rs:23-46) picks inside/outside by the noise lattice; FBm / Wrinkled
+    textures (fbm.rs) equal fbm / turbulence at the mapped point."""
+    ts = _TexScene(orc)
+    one, zero = ts.add(0, value=(1, 1, 1)), ts.add(0, value=(0, 0, 0))
+    dots = ts.add(7, map_kind=1, params=_PLANAR_NEW, t1=one, t2=zero)
+    L = orc.lib()
+    seen = set()
+    for ix in range(-6, 7):
+        for iy in range(-6, 7):
+            cell_has_dot = L.orc_noise(f32(ix) + f32(0.5), f32(iy) + f32(0.5), 0.5) > 0.0
+            centre = ts.eval(dots, _dg15(p=(ix, iy, 0)))[0]
+            corner = ts.eval(dots, _dg15(p=(ix + 0.49, iy + 0.49, 0)))[0]
+            assert corner == 0.0  # |offset| >= 0.49 - 0.15 per axis: always outside the 0.35 radius
+            if not cell_has_dot:
+                assert centre == 0.0
+            else:
+                assert centre == 1.0  # the centre shifts by at most 0.15 * sqrt(2) < 0.35
+            seen.add(bool(cell_has_dot))
+    assert seen == {True, False}
+    p, dpdx, dpdy = np.array([0.3, -0.4, 10.2], np.float32), np.array([0.1, 0, 0], np.float32), np.array([0, 0.1, 0], np.float32)
+    for kind, turb in ((8, 0), (9, 1)):
+        t = ts.add(kind, value=(0.5, 0, 0), map_kind=4, params=_IDENT12, aa=6)
+        want = L.orc_fbm(turb, _p(p), _p(dpdx), _p(dpdy), 0.5, 6)
+        got = ts.eval(t, _dg15(p=p, dpdx=dpdx, dpdy=dpdy))
+        assert got.tolist() == [want, want, want]
+
+
+def _bump(orc, ts, tex, dgs, ng):
+    out, g, n = np.zeros(9, np.float32), np.array(dgs, np.float32), np.array(ng, np.float32)
+    orc.lib().orc_bump(ts.h, tex, _p(g), _p(n), _p(out))
+    return out
+
+
+def test_bump_mapping(orc):
+    """material::bump (material/mod.rs:23-77).  The reference's own test is an `unimplemented!()` stub
+    (:146-155), so these are properties of the function as written: a constant displacement d leaves
+    dpdu + d * dndu, a displacement linear in u tilts dpdu along the normal by its slope, and the
+    result is flipped to the side of the geometric normal."""
+    ts = _TexScene(orc)
+    #        p        dpdu     dpdv     dndu         dndv         nn       u    v    dudx dudy dvdx dvdy  flip
+    dgs = [0, 0, 0, 1, 0, 0, 0, 1, 0, 0.5, 0, 0, 0, 0.25, 0, 0, 0, 1, 0.3, 0.6, 0.2, 0.0, 0.0, 0.4, 0, 0, 0]
+    const = ts.add(0, value=(0.5, 0.5, 0.5))
+    b = _bump(orc, ts, const, dgs, (0, 0, 1))
+    assert b[0:3].tolist() == [1.25, 0, 0] and b[3:6].tolist() == [0, 1.125, 0] and b[6:9].tolist() == [0, 0, 1]
+    assert _bump(orc, ts, const, dgs, (0, 0, -1))[6:9].tolist() == [0, 0, -1]  # face_forward
+    dgs_flip = list(dgs)
+    dgs_flip[24] = 1.0
+    assert _bump(orc, ts, const, dgs_flip, (0, 0, -1))[6:9].tolist() == [0, 0, -1]
+    # displacement = 2 * u (bilerp over UV: v00 = v01 = 0, v10 = v11 = 2)
+    lin = ts.add(6, value=(0, 0, 0, 0, 0, 0, 2, 2, 2, 2, 2, 2), map_kind=0, params=(1, 1, 0, 0))
+    dgs0 = list(dgs)
+    dgs0[9:15] = [0] * 6  # no dndu / dndv
+    b = _bump(orc, ts, lin, dgs0, (0, 0, 1))
+    assert abs(b[0] - 1.0) < 1e-6 and abs(b[2] - 2.0) < 1e-5 and b[1] == 0.0      # dpdu = (1, 0, slope)
+    assert np.abs(b[3:6] - np.array([0, 1, 0])).max() < 1e-6                       # no v dependence
+    n = np.array([-2.0, 0.0, 1.0]) / math.sqrt(5.0)
+    assert np.abs(b[6:9] - n).max() < 1e-6
