@@ -146,7 +146,8 @@ typedef struct {
   int32_t kind;
   int32_t kd, sigma, ks, roughness;  /* texture indices */
   int32_t bump;  /* bump_map: Option<ScalarTextureReference> (material/matte.rs:15, plastic.rs:18):
-                    texture index of the displacement map, or -1 for None                      */
+                    0 = None (so a zero-initialised struct has no bump map), otherwise the texture
+                    index of the displacement map + 1                                          */
 } pbrtb200_material;
 
 #define PBRTB200_LIGHT_POINT 0

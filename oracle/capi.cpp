@@ -807,11 +807,12 @@ float orc_fbm(int turbulence, const float* p3, const float* dpdx3, const float* 
                            V3(dpdy3[0], dpdy3[1], dpdy3[2]), omega, octaves);
 }
 // material::bump (material/mod.rs:23-77) at a hand-built shading geometry.
-// dgs27 = p, dpdu, dpdv, dndu, dndv, nn, (u, v, dudx, dudy, dvdx, dvdy), (flip, 0, 0); ng3 = geometric normal.
+// dgs33 = p, dpdu, dpdv, dndu, dndv, nn, (u, v, dudx, dudy, dvdx, dvdy), (flip, 0, 0), dpdx, dpdy;
+// ng3 = geometric normal.
 // out9 = bumped dpdu, dpdv, nn.
-void orc_bump(OrcScene* s, int tex_id, const float* dgs27, const float* ng3, float* out9) {
+void orc_bump(OrcScene* s, int tex_id, const float* dgs33, const float* ng3, float* out9) {
   DiffGeom g;
-  const float* q = dgs27;
+  const float* q = dgs33;
   g.p = V3(q[0], q[1], q[2]);
   g.dpdu = V3(q[3], q[4], q[5]);
   g.dpdv = V3(q[6], q[7], q[8]);
@@ -820,6 +821,8 @@ void orc_bump(OrcScene* s, int tex_id, const float* dgs27, const float* ng3, flo
   g.nn = V3(q[15], q[16], q[17]);
   g.u = q[18]; g.v = q[19]; g.dudx = q[20]; g.dudy = q[21]; g.dvdx = q[22]; g.dvdy = q[23];
   g.flip = q[24] != 0.0f;
+  g.dpdx = V3(q[27], q[28], q[29]);
+  g.dpdy = V3(q[30], q[31], q[32]);
   DiffGeom gg;
   gg.nn = V3(ng3[0], ng3[1], ng3[2]);
   DiffGeom b = bump_dg(s->sc.textures, tex_id, gg, g);

@@ -170,6 +170,7 @@ class OracleScene:
         L = lib()
         self.h = C.c_void_p(L.orc_scene_new())
         tex_ids, mat_ids, light_ids = {}, {}, {}
+        self.tex_ids = tex_ids  # id(api.Texture) -> oracle texture index
 
         def tex(t):
             if t is None:

@@ -432,6 +432,7 @@ class HostScene:
         self.h = L.pbh_scene_new()
         self.scene = scene
         tex_ids, mat_ids, self.light_ids = {}, {}, {}
+        self.tex_ids = tex_ids  # id(api.Texture) -> index into the flat texture table
 
         def tex(t):
             if t is None:

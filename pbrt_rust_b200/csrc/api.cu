@@ -159,7 +159,7 @@ bool scene_needs_ext(const pbrtb200_scene* s) {
         (s->textures[i].kind != PBRTB200_TEX_CONSTANT && s->textures[i].map_kind > PBRTB200_MAP_PLANAR))
       return true;
   for (uint32_t i = 0; i < s->n_materials; ++i)
-    if (s->materials[i].bump >= 0) return true;
+    if (s->materials[i].bump != 0) return true;
   return false;
 }
 
@@ -599,7 +599,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
       FAIL(PBRTB200_EINVAL, "material sigma texture invalid");
     if (m.kind == PBRTB200_MAT_PLASTIC && (tex_depth(s, m.ks, 0) < 0 || tex_depth(s, m.roughness, 0) < 0))
       FAIL(PBRTB200_EINVAL, "material ks/roughness texture invalid");
-    if (m.bump >= 0 && tex_depth(s, m.bump, 0) < 0) FAIL(PBRTB200_EINVAL, "material bump texture invalid");
+    if (m.bump != 0 && tex_depth(s, m.bump - 1, 0) < 0) FAIL(PBRTB200_EINVAL, "material bump texture invalid");
   }
   for (uint32_t i = 0; i < s->n_mipmaps; ++i) {  // every level must lie inside the texel pool
     const pbrtb200_mipmap& m = s->mipmaps[i];
@@ -656,7 +656,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
     bool v = varying(m.kd);
     if (m.kind == PBRTB200_MAT_MATTE) v = v || varying(m.sigma);
     if (m.kind == PBRTB200_MAT_PLASTIC) v = v || varying(m.ks) || varying(m.roughness);
-    if (m.bump >= 0) v = true;  // material::bump reads dudx .. dvdy (material/mod.rs:30-32, 45-47)
+    if (m.bump != 0) v = true;  // material::bump reads dudx .. dvdy (material/mod.rs:30-32, 45-47)
     mat_flags[i] = v ? 1 : 0;
   }
   if (upload(ctx, ctx->d_mat_flags, mat_flags.data(), mat_flags.size())) return PBRTB200_ENODEV;

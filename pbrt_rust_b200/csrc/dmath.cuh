@@ -9,6 +9,7 @@
 // Host compilation of the device arithmetic for the CPU test-suite (tests/devsrc/): the few CUDA
 // intrinsics used below get plain C++ equivalents.  Never part of the product build.
 #include <cmath>
+using std::isnan;
 #define PB_DEV inline
 struct float4 {
   float x, y, z, w;

@@ -840,7 +840,7 @@ int pbh_texture_image(pbh_scene* s, int map_kind, const float map[12], const flo
 
 int pbh_material_matte(pbh_scene* s, int kd, int sigma, int bump_map) {
   pbrtb200_material m{};
-  m.bump = bump_map < 0 ? -1 : bump_map;
+  m.bump = bump_map < 0 ? 0 : bump_map + 1;
   m.kind = PBRTB200_MAT_MATTE;
   m.kd = kd;
   m.sigma = sigma;
@@ -849,7 +849,7 @@ int pbh_material_matte(pbh_scene* s, int kd, int sigma, int bump_map) {
 }
 int pbh_material_plastic(pbh_scene* s, int kd, int ks, int roughness, int bump_map) {
   pbrtb200_material m{};
-  m.bump = bump_map < 0 ? -1 : bump_map;
+  m.bump = bump_map < 0 ? 0 : bump_map + 1;
   m.kind = PBRTB200_MAT_PLASTIC;
   m.kd = kd;
   m.ks = ks;

@@ -688,7 +688,7 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
     env.mipmaps = sc.mipmaps;
     env.texels = sc.texels;
     // matte.rs:33-37 / plastic.rs:35-39: bump(tex, &dg_geom, &dg_shading)
-    if (mat.bump >= 0) dgs = bump_dg_(env, mat.bump, dgs, dg.nn, shape_flip);
+    if (mat.bump > 0) dgs = bump_dg_(env, mat.bump - 1, dgs, dg.nn, shape_flip);
   }
   bs.nn = dgs.nn;                      // bsdf/mod.rs:70-86
   bs.tn = bs.sn = mk3(0.f, 0.f, 0.f);  // filled below for BxDFs that read the local frame

@@ -5,7 +5,8 @@ oracle are fed from these same descriptions.  The generator PRNG is SplitMix64 (
 the renderer's StdRng)."""
 import numpy as np
 
-from .api import (AreaLight, Camera, Film, Filter, Light, Material, PlanarMapping2D, Primitive,
+from .api import (AreaLight, Camera, CylindricalMapping2D, Film, Filter, IdentityMapping3D, Light, Material,
+                  PlanarMapping2D, Primitive, SphericalMapping2D,
                   Sampler, Scene, Shape, SurfaceIntegrator, Texture, Transform, UVMapping2D)
 
 
@@ -233,42 +234,120 @@ def quadrics(xres=160, yres=112, xs=2, ys=2, n=18, seed=9):
     return _setup(scene, c2w, 45.0, xres, yres, xs, ys, True)
 
 
-def random_scene(seed):
+class TexGen:
+    """Random textures / materials for the differential fuzzers.  ext=False draws exactly what the
+    round-1 fuzzer drew (constant, uv, image, nested checkerboards over UV / planar mappings);
+    ext=True adds spherical / cylindrical mappings, scale / mix / bilerp / dots / fbm / wrinkled
+    textures and bump maps.  images=False leaves image textures out (host check of the device source)."""
+
+    def __init__(self, rng, img, ext=False, images=True):
+        self.rng, self.img, self.ext, self.images = rng, img, ext, images
+
+    def U(self, a=0.0, b=1.0):
+        return float(self.rng.uniform(a, b))
+
+    def w2t(self):
+        U = self.U
+        return Transform.translate((U(-2, 2), U(-2, 2), U(-2, 2))) * Transform.rotate_x(U(0, 360)) * Transform.rotate_y(U(0, 360)) \
+            * Transform.scale(U(0.3, 2.0), U(0.3, 2.0), U(0.3, 2.0))
+
+    def mapping(self):
+        rng, U = self.rng, self.U
+        k = int(rng.integers(4 if self.ext else 2))
+        if k == 1:
+            return UVMapping2D(U(0.5, 6), U(0.5, 6), U(), U())
+        if k == 0:
+            return PlanarMapping2D((U(-1, 1), U(-1, 1), U(-1, 1)), (U(-1, 1), U(-1, 1), U(-1, 1)), U(), U())
+        return (SphericalMapping2D if k == 2 else CylindricalMapping2D)(self.w2t() if rng.integers(3) else None)
+
+    def image(self, spectrum, mapping, **kw):
+        if not self.images:
+            return Texture.constant((self.U(0.1, 0.9),) * 3 if not spectrum else (self.U(0.1, 0.9), self.U(0.1, 0.9), self.U(0.1, 0.9)))
+        return Texture.image(mapping, self.img, spectrum=spectrum, do_trilinear=True, **kw)
+
+    def noise_tex(self):
+        rng, U = self.rng, self.U
+        mk = Texture.fbm if rng.integers(2) else Texture.wrinkled
+        return mk(int(rng.integers(0, 7)), U(0.3, 0.8), IdentityMapping3D(self.w2t() if rng.integers(3) else None))
+
+    def spectrum_tex(self, depth=0):
+        rng, U = self.rng, self.U
+        if self.ext and rng.integers(2):
+            k = int(rng.integers(5 if depth < 2 else 1))
+            if k == 0:
+                return Texture.bilerp(self.mapping(), *[(U(0, 1), U(0, 1), U(0, 1)) for _ in range(4)])
+            if k == 1:
+                return Texture.scale(self.spectrum_tex(depth + 1), self.unit_tex(depth + 1))
+            if k == 2:
+                return Texture.mix(self.spectrum_tex(depth + 1), self.spectrum_tex(depth + 1), self.unit_tex(depth + 1))
+            if k == 3:
+                return Texture.dots(self.mapping(), self.spectrum_tex(depth + 1), self.spectrum_tex(depth + 1))
+            return Texture.scale(Texture.constant((U(0.2, 0.9), U(0.2, 0.9), U(0.2, 0.9))), self.unit_tex(depth + 1))
+        k = int(rng.integers(5 if depth < 2 else 3))
+        if k == 0:
+            return Texture.constant((U(0.05, 0.9), U(0.05, 0.9), U(0.05, 0.9)))
+        if k == 1:
+            return Texture.uv(self.mapping())
+        if k == 2:
+            return self.image(True, self.mapping(), wrap=["repeat", "black", "clamp"][int(rng.integers(3))], scale=U(0.6, 1.0), gamma=U(1.0, 2.2))
+        return Texture.checkerboard(self.mapping(), self.spectrum_tex(depth + 1), self.spectrum_tex(depth + 1), bool(rng.integers(2)))
+
+    def unit_tex(self, depth=0):
+        """a float texture with values in [0, 1] wherever u, v are in [0, 1] (every shape's are)"""
+        rng, U = self.rng, self.U
+        k = int(rng.integers(4 if depth < 3 else 2))
+        if k == 0:
+            return Texture.constant(U(0, 1))
+        if k == 1:
+            return Texture.bilerp(UVMapping2D(), U(0, 1), U(0, 1), U(0, 1), U(0, 1))
+        if k == 2:
+            return Texture.dots(self.mapping(), Texture.constant(U(0, 1)), Texture.constant(U(0, 1)))
+        return Texture.checkerboard(self.mapping(), Texture.constant(U(0, 1)), Texture.constant(U(0, 1)), bool(rng.integers(2)))
+
+    def float_tex(self, lo, hi):
+        rng, U = self.rng, self.U
+        if self.ext and rng.integers(2):  # lo + (hi - lo) * unit, as a mix of two constants
+            return Texture.mix(Texture.constant(lo), Texture.constant(hi), self.unit_tex(1))
+        if rng.integers(3) == 0:
+            return self.image(False, self.mapping(), scale=hi, gamma=1.0)
+        return Texture.constant(U(lo, hi))
+
+    def bump_tex(self):
+        """a displacement map of small amplitude (None half of the time)"""
+        rng, U = self.rng, self.U
+        k = int(rng.integers(6))
+        if k >= 3:
+            return None
+        amp = Texture.constant(U(0.01, 0.08))
+        if k == 0:
+            return Texture.scale(amp, self.noise_tex())
+        if k == 1:
+            return Texture.scale(amp, self.unit_tex(1))
+        return Texture.scale(amp, Texture.checkerboard(self.mapping(), Texture.constant(1.0), self.noise_tex(), True))
+
+    def material(self):
+        rng, U = self.rng, self.U
+        if rng.integers(2):
+            m = Material.matte(self.spectrum_tex(), self.float_tex(0.0, 40.0) if rng.integers(2) else Texture.constant(0.0))
+        else:
+            m = Material.plastic(self.spectrum_tex(), Texture.constant(U(0.05, 0.5)), self.float_tex(0.02, 0.4))
+        if self.ext:
+            m.bump_map = self.bump_tex()
+        return m
+
+
+def random_scene(seed, ext=False):
     """A seeded random small scene + camera + sampler + film, drawn from everything the back end
     supports: meshes with optional normals / tangents / uvs, spheres, cylinders, disks under random
     (also handedness-flipping) transforms, matte / plastic materials over constant, checkerboard
     (nested, antialiased or not), uv and trilinear image textures, point / spot / area lights,
     every BVH split method, every filter, stratified and LD samplers, crop windows, depth of field.
-    Used by the differential (GPU vs oracle) fuzz test."""
+    ext=True also draws the spherical / cylindrical mappings, the scale / mix / bilerp / dots / fbm /
+    wrinkled textures and bump maps (TexGen).  Used by the differential (GPU vs oracle) fuzz tests."""
     rng = np.random.default_rng(seed)
     U = lambda a=0.0, b=1.0: float(rng.uniform(a, b))
     img = procedural_image(48, 40, seed=seed + 1)
-
-    def mapping():
-        if rng.integers(2):
-            return UVMapping2D(U(0.5, 6), U(0.5, 6), U(), U())
-        return PlanarMapping2D((U(-1, 1), U(-1, 1), U(-1, 1)), (U(-1, 1), U(-1, 1), U(-1, 1)), U(), U())
-
-    def spectrum_tex(depth=0):
-        k = int(rng.integers(5 if depth < 2 else 3))
-        if k == 0:
-            return Texture.constant((U(0.05, 0.9), U(0.05, 0.9), U(0.05, 0.9)))
-        if k == 1:
-            return Texture.uv(mapping())
-        if k == 2:
-            return Texture.image(mapping(), img, spectrum=True, do_trilinear=True, wrap=["repeat", "black", "clamp"][int(rng.integers(3))],
-                                 scale=U(0.6, 1.0), gamma=U(1.0, 2.2))
-        return Texture.checkerboard(mapping(), spectrum_tex(depth + 1), spectrum_tex(depth + 1), bool(rng.integers(2)))
-
-    def float_tex(lo, hi):
-        if rng.integers(3) == 0:
-            return Texture.image(mapping(), img, spectrum=False, do_trilinear=True, scale=hi, gamma=1.0)
-        return Texture.constant(U(lo, hi))
-
-    def material():
-        if rng.integers(2):
-            return Material.matte(spectrum_tex(), float_tex(0.0, 40.0) if rng.integers(2) else Texture.constant(0.0))
-        return Material.plastic(spectrum_tex(), Texture.constant(U(0.05, 0.5)), float_tex(0.02, 0.4))
+    material = TexGen(rng, img, ext=ext).material
 
     def xform(spread=3.0):
         t = Transform.translate((U(-spread, spread), U(0.2, 2.5), U(-spread, spread))) * Transform.rotate_x(U(0, 360)) \

@@ -1,5 +1,10 @@
 """Differential fuzzing: seeded random scenes (scenes.random_scene) rendered by the CUDA back end and
-by the CPU oracle.  usage: python scripts/fuzz_parity.py [first_seed] [count]
+by the CPU oracle.  usage: python scripts/fuzz_parity.py [first_seed] [count] [ext]
+`ext` draws the extended texture set (spherical / cylindrical mappings, scale / mix / bilerp / dots /
+fbm / wrinkled, bump maps).  Those mappings go through acosf / atan2f / log2f, where CUDA and glibc
+differ by ULPs, and feed discontinuous textures (checker cells, dots, uv fractions): a sample on a
+cell border may land on the other side, so for `ext` the image RMSE is taken over the best 99 % of
+the pixels and 98 % of the pixels must agree to 1e-3 relative.
 Prints one line per seed; exits non-zero if any seed breaks the stated tolerance (hit ids >= 99.99 %
 equal — quadric phi clipping edges are the documented float-edge case — image RMSE <= 1e-4 and
 relative error <= 1e-3 on >= 99 % of the pixels; weight sums bit-exact)."""
@@ -11,8 +16,8 @@ from pbrt_rust_b200 import scenes
 from oracle import orc
 
 
-def check(seed, verbose=True):
-    cfg = scenes.random_scene(seed)
+def check(seed, verbose=True, ext=False):
+    cfg = scenes.random_scene(seed, ext=ext)
     r = pb.GpuRenderer(cfg["sampler"], cfg["camera"], cfg["integrator"], num_cpus=8)
     film = r.render(cfg["scene"])
     hits, _, _ = r.primary_hits(cfg["scene"])
@@ -20,7 +25,10 @@ def check(seed, verbose=True):
     ref = orc.render(osc, orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0), want_hits=True)
     agree = float(np.mean(hits["prim"] == ref["hit_ids"]))
     rgb, rgb_ref = pb.film_to_rgb(film), ref["rgb"]
-    rmse = float(np.sqrt(np.mean((rgb - rgb_ref) ** 2)))
+    err2 = ((rgb - rgb_ref) ** 2).sum(axis=-1).reshape(-1)
+    if ext:  # drop the worst 1 % of the pixels (cell-border flips, see the module docstring)
+        err2 = np.sort(err2)[:max(1, int(np.ceil(0.99 * err2.size)))]
+    rmse = float(np.sqrt(err2.sum() / (3 * err2.size)))
     rel = np.abs(rgb - rgb_ref) / np.maximum(np.abs(rgb_ref), 1e-3)
     frac = float((rel.max(axis=-1) <= 1e-3).mean())
     wexact = bool(np.array_equal(film[..., 3].view(np.uint32), ref["film"][..., 3].view(np.uint32)))
@@ -34,7 +42,7 @@ def check(seed, verbose=True):
         if tiles:
             acc += r.render(cfg["scene"], tiles=tiles)
     tiles_ok = bool(np.array_equal(acc.view(np.uint32), film.view(np.uint32)))
-    ok = agree >= 0.9999 and rmse <= 1e-4 and frac >= 0.99 and wexact and np.isfinite(rgb).all() and tiles_ok
+    ok = agree >= 0.9999 and rmse <= 1e-4 and frac >= (0.98 if ext else 0.99) and wexact and np.isfinite(rgb).all() and tiles_ok
     if verbose or not ok:
         s = cfg["sampler"]
         print("seed %4d %s  film %s  spp %d  ids %.6f  rmse %.2e  frac(rel<=1e-3) %.4f  weights %s  tiles %s  max rgb %.3f" % (
@@ -45,6 +53,7 @@ def check(seed, verbose=True):
 if __name__ == "__main__":
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     count = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-    bad = [s for s in range(first, first + count) if not check(s)]
+    ext = len(sys.argv) > 3 and sys.argv[3] == "ext"
+    bad = [s for s in range(first, first + count) if not check(s, ext=ext)]
     print("fuzz: %d seeds, %d failures %s" % (count, len(bad), bad))
     sys.exit(1 if bad else 0)

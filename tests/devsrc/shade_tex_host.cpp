@@ -1,0 +1,44 @@
+// TEST INFRASTRUCTURE ONLY.  Compiles the device source pbrt_rust_b200/csrc/shade_tex.cuh as host
+// code (PB_HOST_CHECK: no CUDA, intrinsics replaced by plain C++) so the CPU test-suite can run the
+// very arithmetic the GPU kernel executes against the oracle where no GPU exists.  The product
+// never loads this library; image textures (MIPMap lookups) stay device-only and are not covered.
+#define PB_HOST_CHECK 1
+#include "../../pbrt_rust_b200/csrc/shade_tex.cuh"
+
+#include <cstring>
+
+static_assert(sizeof(DG) == 30 * sizeof(float), "DG is 30 packed floats");
+
+extern "C" {
+// dg30 = struct DG: p, nn, u, v, dpdu, dpdv, dndu, dndv, dpdx, dpdy, dudx, dudy, dvdx, dvdy
+void devsrc_tex_eval(const pbrtb200_texture* table, int id, const float* dg30, float* out3) {
+  DG dg;
+  std::memcpy(&dg, dg30, sizeof dg);
+  TexEnv env{table, nullptr, nullptr};
+  const f3 r = tex_eval_ext<PBRTB200_TEX_MAX_DEPTH>(env, id, dg);
+  out3[0] = r.x;
+  out3[1] = r.y;
+  out3[2] = r.z;
+}
+void devsrc_tex_map(const pbrtb200_texture* tx, const float* dg30, float* out6) {
+  DG dg;
+  std::memcpy(&dg, dg30, sizeof dg);
+  tex_map_ext(*tx, dg, out6);
+}
+// out9 = bumped dpdu, dpdv, nn
+void devsrc_bump(const pbrtb200_texture* table, int id, const float* dg30, const float* ng3, int flip,
+                 float* out9) {
+  DG dg;
+  std::memcpy(&dg, dg30, sizeof dg);
+  TexEnv env{table, nullptr, nullptr};
+  const DG b = bump_dg_(env, id, dg, mk3(ng3[0], ng3[1], ng3[2]), flip != 0);
+  out9[0] = b.dpdu.x; out9[1] = b.dpdu.y; out9[2] = b.dpdu.z;
+  out9[3] = b.dpdv.x; out9[4] = b.dpdv.y; out9[5] = b.dpdv.z;
+  out9[6] = b.nn.x;   out9[7] = b.nn.y;   out9[8] = b.nn.z;
+}
+float devsrc_noise(float x, float y, float z) { return noise_(x, y, z); }
+float devsrc_fbm(int turb, const float* p, const float* dpdx, const float* dpdy, float omega, int octaves) {
+  return fbm_(turb != 0, mk3(p[0], p[1], p[2]), mk3(dpdx[0], dpdx[1], dpdx[2]), mk3(dpdy[0], dpdy[1], dpdy[2]),
+              omega, octaves);
+}
+}

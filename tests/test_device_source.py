@@ -1,0 +1,190 @@
+"""The device source of the texture stage, compiled for the host, against the oracle (CPU only).
+
+pbrt_rust_b200/csrc/shade_tex.cuh (mappings, noise, every texture kind except image lookups, bump
+mapping) is plain arithmetic; tests/devsrc/shade_tex_host.cpp compiles that very source with g++
+(PB_HOST_CHECK) so its logic is checked here, where no GPU exists.  Texture tables come from the
+product's host mirror (the flatten shim), descriptions from scenes.TexGen; the oracle gets the same
+descriptions.  The `-m gpu` suite repeats the comparison on the device through whole renders.
+This is a checker only: nothing in the product loads libdevsrc.so.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import pbrt_rust_b200 as pb
+from pbrt_rust_b200 import _ffi, scenes
+from pbrt_rust_b200.api import HostScene, Material, Primitive, Scene, Shape, Texture, Transform
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "devsrc", "shade_tex_host.cpp")
+LIB = os.path.join(HERE, "devsrc", "libdevsrc.so")
+DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "dmath.cuh")] + \
+    [os.path.join(HERE, "..", "include", "pbrtb200.h")]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+                               "-Wno-unknown-pragmas", "-o", LIB, SRC])
+    L = C.CDLL(LIB)
+    L.devsrc_noise.restype = C.c_float
+    L.devsrc_noise.argtypes = [C.c_float] * 3
+    L.devsrc_fbm.restype = C.c_float
+    L.devsrc_fbm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
+    L.devsrc_tex_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.devsrc_bump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _scene_of(materials):
+    """one tiny triangle per material: enough for the host mirror / oracle to register every texture"""
+    prims = []
+    for i, m in enumerate(materials):
+        P = np.array([[i, 0, 0], [i + 0.5, 0, 0], [i, 0.5, 0]], np.float32)
+        prims.append(Primitive.geometric(Shape.triangle_mesh(Transform.new(), Transform.new(), False,
+                                                             np.arange(3, dtype=np.uint32), P), m))
+    return Scene.new_with(Primitive.bvh(prims, 1, "sah"), [])
+
+
+def _random_dg(rng):
+    """struct DG as 30 floats: p, nn, u, v, dpdu, dpdv, dndu, dndv, dpdx, dpdy, dudx, dudy, dvdx, dvdy"""
+    g = np.zeros(30, np.float32)
+    g[0:3] = rng.uniform(-4, 4, 3)
+    dpdu, dpdv = rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3)
+    nn = np.cross(dpdu, dpdv)
+    g[3:6] = nn / np.linalg.norm(nn)
+    g[6:8] = rng.uniform(0, 1, 2)
+    g[8:11], g[11:14] = dpdu, dpdv
+    g[14:17], g[17:20] = rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.3, 0.3, 3)
+    scale = 10.0 ** rng.uniform(-3, 0)
+    g[20:23], g[23:26] = rng.uniform(-1, 1, 3) * scale, rng.uniform(-1, 1, 3) * scale
+    g[26:30] = rng.uniform(-1, 1, 4) * scale
+    if rng.integers(6) == 0:
+        g[20:30] = 0.0  # no differentials
+    return g
+
+
+def _dg15(g):
+    return np.concatenate([g[0:3], g[20:23], g[23:26], g[6:8], g[26:30]]).astype(np.float32)
+
+
+def _dgs33(g, flip):
+    return np.concatenate([g[0:3], g[8:11], g[11:14], g[14:17], g[17:20], g[3:6], g[6:8], g[26:30],
+                           [1.0 if flip else 0.0, 0, 0], g[20:23], g[23:26]]).astype(np.float32)
+
+
+def test_noise_and_fbm_match_the_oracle_bit_for_bit(dev, orc):
+    """noise is +,-,* only: the device source must agree with the oracle exactly; fbm / turbulence
+    add one log2f, the same glibc call on both sides here."""
+    L = orc.lib()
+    rng = np.random.default_rng(7)
+    for _ in range(4000):
+        x, y, z = (np.float32(v) for v in rng.uniform(-300, 300, 3))
+        assert dev.devsrc_noise(x, y, z) == L.orc_noise(x, y, z)
+    for _ in range(1500):
+        p = rng.uniform(-20, 20, 3).astype(np.float32)
+        dx = (rng.uniform(-1, 1, 3) * 10.0 ** rng.uniform(-4, 0)).astype(np.float32)
+        dy = (rng.uniform(-1, 1, 3) * 10.0 ** rng.uniform(-4, 0)).astype(np.float32)
+        om, octs, turb = np.float32(rng.uniform(0.2, 0.9)), int(rng.integers(0, 9)), int(rng.integers(2))
+        assert dev.devsrc_fbm(turb, _p(p), _p(dx), _p(dy), om, octs) == L.orc_fbm(turb, _p(p), _p(dx), _p(dy), om, octs)
+    zero = np.zeros(3, np.float32)  # s2 = 0: log2(0) = -inf -> all octaves
+    assert dev.devsrc_fbm(0, _p(p), _p(zero), _p(zero), 0.5, 5) == L.orc_fbm(0, _p(p), _p(zero), _p(zero), 0.5, 5)
+
+
+def test_device_texture_evaluator_matches_the_oracle(dev, orc):
+    """Random texture trees over every mapping and kind (no images), random shading geometry:
+    tex_eval_ext of the device source == the oracle's Texture::evaluate restatement, bit for bit
+    (both sides call the same libm here; the GPU run allows the CUDA-libm tolerance)."""
+    from oracle import orc as O
+    rng = np.random.default_rng(2024)
+    gen = scenes.TexGen(rng, None, ext=True, images=False)
+    texs = [gen.spectrum_tex() for _ in range(150)] + [gen.unit_tex() for _ in range(40)] + \
+        [gen.float_tex(0.02, 0.4) for _ in range(30)] + [gen.noise_tex() for _ in range(30)]
+    kinds = set()
+
+    def walk(t):
+        kinds.add((t.kind, t.mapping.kind if t.mapping is not None else -1))
+        for c in t.children():
+            walk(c)
+
+    for t in texs:
+        walk(t)
+    assert {k for k, _ in kinds} == {0, 1, 2, 4, 5, 6, 7, 8, 9}, kinds
+    assert {m for _, m in kinds} >= {0, 1, 2, 3, 4}
+    scene = _scene_of([Material.matte(t, Texture.constant(0.0)) for t in texs])
+    hs, osc = HostScene(scene), O.OracleScene(scene)
+    flat = hs.flat.contents
+    table = C.cast(flat.textures, C.c_void_p)
+    n = 0
+    for t in texs:
+        hid, oid = hs.tex_ids[id(t)], osc.tex_ids[id(t)]
+        for _ in range(40):
+            g = _random_dg(rng)
+            got, want, q = np.zeros(3, np.float32), np.zeros(3, np.float32), _dg15(g)
+            dev.devsrc_tex_eval(table, hid, _p(g), _p(got))
+            O.lib().orc_texture_eval(osc.h, oid, _p(q), _p(want))
+            assert got.tolist() == want.tolist(), (t.kind, got, want)
+            n += 1
+    assert n == 40 * len(texs)
+
+
+def test_device_bump_matches_the_oracle(dev, orc):
+    """material::bump of the device source == the oracle's, over random displacement maps"""
+    from oracle import orc as O
+    rng = np.random.default_rng(99)
+    gen = scenes.TexGen(rng, None, ext=True, images=False)
+    bumps = []
+    while len(bumps) < 60:
+        b = gen.bump_tex()
+        if b is not None:
+            bumps.append(b)
+    scene = _scene_of([Material.matte(Texture.constant(0.5), Texture.constant(0.0), bump_map=b) for b in bumps])
+    hs, osc = HostScene(scene), O.OracleScene(scene)
+    flat = hs.flat.contents
+    assert all(flat.materials[i].bump > 0 for i in range(flat.n_materials))
+    table = C.cast(flat.textures, C.c_void_p)
+    for b in bumps:
+        hid, oid = hs.tex_ids[id(b)], osc.tex_ids[id(b)]
+        for _ in range(25):
+            g = _random_dg(rng)
+            flip = bool(rng.integers(2))
+            ng = g[3:6] * np.float32(-1.0 if rng.integers(2) else 1.0)
+            got, want, q = np.zeros(9, np.float32), np.zeros(9, np.float32), _dgs33(g, flip)
+            dev.devsrc_bump(table, hid, _p(g), _p(ng), int(flip), _p(got))
+            O.lib().orc_bump(osc.h, oid, _p(q), _p(ng), _p(want))
+            assert got.tolist() == want.tolist()
+
+
+def test_flat_texture_table_layout():
+    """the host mirror fills the fields the device evaluator reads (include/pbrtb200.h)"""
+    a, b = Texture.constant((1, 2, 3)), Texture.constant(0.25)
+    mix = Texture.mix(a, Texture.scale(a, b), b)
+    bil = Texture.bilerp(pb.api.UVMapping2D(2, 3, 0.5, 0.25), 1.0, 2.0, 3.0, (4, 5, 6))
+    fbm = Texture.fbm(5, 0.5, pb.api.IdentityMapping3D(Transform.translate((1, 2, 3))))
+    dots = Texture.dots(pb.api.SphericalMapping2D(), a, b)
+    scene = _scene_of([Material.matte(mix, b, bump_map=fbm), Material.plastic(bil, a, b), Material.matte(dots, b)])
+    hs = HostScene(scene)
+    f = hs.flat.contents
+    t = lambda x: f.textures[hs.tex_ids[id(x)]]
+    assert t(mix).kind == 5 and (t(mix).tex1, t(mix).tex3) == (hs.tex_ids[id(a)], hs.tex_ids[id(b)])
+    assert f.textures[t(mix).tex2].kind == 4
+    assert t(bil).kind == 6 and list(t(bil).value) == [1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 5, 6]
+    assert list(t(bil).map)[:4] == [2, 3, 0.5, 0.25] and t(bil).map_kind == 0
+    assert t(fbm).kind == 8 and t(fbm).aa == 5 and t(fbm).value[0] == 0.5 and t(fbm).map_kind == 4
+    assert list(t(fbm).map) == [1, 0, 0, 1, 0, 1, 0, 2, 0, 0, 1, 3]
+    assert t(dots).kind == 7 and t(dots).map_kind == 2 and list(t(dots).map) == [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]
+    assert [f.materials[i].bump for i in range(3)] == [hs.tex_ids[id(fbm)] + 1, 0, 0]
+    with pytest.raises(pb.api.PbrtError):  # projective world_to_texture: not representable in map[12]
+        m = np.eye(4, dtype=np.float32)
+        m[3, 0] = 0.5
+        pb.api.SphericalMapping2D(Transform(m, m))
+    with pytest.raises(pb.api.PbrtError):  # f32::clamp(0.0, max) panics for max < 0 (noise.rs:116)
+        HostScene(_scene_of([Material.matte(Texture.fbm(-1, 0.5), b)]))

@@ -616,6 +616,42 @@ def test_differential_fuzz_random_scenes(orc):
     assert not bad, bad
 
 
+def test_differential_fuzz_extended_textures_and_bump(orc):
+    """scenes.random_scene(ext=True): spherical / cylindrical mappings, scale / mix / bilerp / dots /
+    fbm / wrinkled textures and bump maps (k_shade's EXT variant) — GPU against oracle.  Hit ids and
+    weight sums as above; image RMSE <= 1e-4 over the best 99 % of the pixels and relative error
+    <= 1e-3 on >= 98 % (CUDA vs glibc acosf / atan2f / log2f can move a sample across a checker /
+    dots cell border; scripts/fuzz_parity.py)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "fuzz_parity", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "fuzz_parity.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    bad = [s for s in range(40) if not fz.check(s, verbose=False, ext=True)]
+    assert not bad, bad
+
+
+def test_bump_mapped_sphere_changes_the_shading_only(orc):
+    """A bump map moves no geometry: hit ids and t equal the un-bumped render bit for bit, the image
+    differs from it, and matches the oracle's bump-mapped render."""
+    def build(bump):
+        cfg = scenes.config1(xres=96, yres=72)
+        for p in cfg["scene"].aggregate.prims:
+            p.material.bump_map = bump
+        return cfg
+    disp = pb.api.Texture.scale(pb.api.Texture.constant(0.05), pb.api.Texture.fbm(4, 0.6))
+    plain, bumped = build(None), build(disp)
+    rp, rb = _renderer(plain), _renderer(bumped)
+    fp, fb = rp.render(plain["scene"]), rb.render(bumped["scene"])
+    hp, _, _ = rp.primary_hits(plain["scene"])
+    hb, _, _ = rb.primary_hits(bumped["scene"])
+    assert np.array_equal(hp["prim"], hb["prim"]) and np.array_equal(hp["t"].view(np.uint32), hb["t"].view(np.uint32))
+    assert float(np.abs(pb.film_to_rgb(fp) - pb.film_to_rgb(fb)).max()) > 1e-3
+    ref = orc.render(orc.OracleScene(bumped["scene"]), orc.render_config(bumped["camera"], bumped["sampler"], num_cpus=8, mode=0))
+    assert float(np.sqrt(np.mean((pb.film_to_rgb(fb) - ref["rgb"]) ** 2))) <= 2e-5
+
+
 def test_c_abi_from_plain_c(orc, tmp_path):
     """examples/render_c_abi.c drives the whole path from C (host mirror + C ABI, no Python in the
     process): its film must equal the Python binding's film bit for bit, its PNG must decode to

@@ -1036,8 +1036,8 @@ def test_bump_mapping(orc):
     dpdu + d * dndu, a displacement linear in u tilts dpdu along the normal by its slope, and the
     result is flipped to the side of the geometric normal."""
     ts = _TexScene(orc)
-    #        p        dpdu     dpdv     dndu         dndv         nn       u    v    dudx dudy dvdx dvdy  flip
-    dgs = [0, 0, 0, 1, 0, 0, 0, 1, 0, 0.5, 0, 0, 0, 0.25, 0, 0, 0, 1, 0.3, 0.6, 0.2, 0.0, 0.0, 0.4, 0, 0, 0]
+    #        p        dpdu     dpdv     dndu         dndv         nn       u    v    dudx dudy dvdx dvdy  flip      dpdx, dpdy
+    dgs = [0, 0, 0, 1, 0, 0, 0, 1, 0, 0.5, 0, 0, 0, 0.25, 0, 0, 0, 1, 0.3, 0.6, 0.2, 0.0, 0.0, 0.4, 0, 0, 0] + [0] * 6
     const = ts.add(0, value=(0.5, 0.5, 0.5))
     b = _bump(orc, ts, const, dgs, (0, 0, 1))
     assert b[0:3].tolist() == [1.25, 0, 0] and b[3:6].tolist() == [0, 1.125, 0] and b[6:9].tolist() == [0, 0, 1]
