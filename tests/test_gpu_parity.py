@@ -640,7 +640,10 @@ def test_bump_mapped_sphere_changes_the_shading_only(orc):
         for p in cfg["scene"].aggregate.prims:
             p.material.bump_map = bump
         return cfg
-    disp = pb.api.Texture.scale(pb.api.Texture.constant(0.05), pb.api.Texture.fbm(4, 0.6))
+    # (fbm / wrinkled would be a poor probe here: with the reference's camera-space ray differentials,
+    # SURVEY D15, their footprint estimate is so large that zero octaves are summed)
+    disp = pb.api.Texture.scale(pb.api.Texture.constant(0.5),
+                                pb.api.Texture.bilerp(pb.api.UVMapping2D(4.0, 4.0, 0.0, 0.0), 0.0, 0.2, 0.2, 0.0))
     plain, bumped = build(None), build(disp)
     rp, rb = _renderer(plain), _renderer(bumped)
     fp, fb = rp.render(plain["scene"]), rb.render(bumped["scene"])
