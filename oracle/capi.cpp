@@ -703,6 +703,41 @@ void orc_transform(int kind, const float* a3, float* m16, float* minv16) {
   std::memcpy(m16, t.m.m, 64);
   std::memcpy(minv16, t.m_inv.m, 64);
 }
+// Matrix4x4 / Transform algebra hooks for the reference's own unit tests
+// (transform/matrix4x4.rs:208-353, transform/transform.rs:300-590).
+void orc_mat_mul(const float* a16, const float* b16, float* out16) {
+  M44 a, b;
+  std::memcpy(a.m, a16, 64);
+  std::memcpy(b.m, b16, 64);
+  M44 r = a * b;
+  std::memcpy(out16, r.m, 64);
+}
+void orc_mat_transpose(const float* a16, float* out16) {
+  M44 a;
+  std::memcpy(a.m, a16, 64);
+  M44 r = a.transpose();
+  std::memcpy(out16, r.m, 64);
+}
+void orc_xf_mul(const float* am, const float* aminv, const float* bm, const float* bminv, float* m16,
+                float* minv16) {
+  Transform t = xf_from(am, aminv) * xf_from(bm, bminv);
+  std::memcpy(m16, t.m.m, 64);
+  std::memcpy(minv16, t.m_inv.m, 64);
+}
+int orc_xf_swaps_handedness(const float* m, const float* minv) { return xf_from(m, minv).swaps_handedness() ? 1 : 0; }
+void orc_xf_bbox(const float* m, const float* minv, const float* box6, float* out6) {
+  BBox b = xf_bbox(xf_from(m, minv), BBox(V3(box6[0], box6[1], box6[2]), V3(box6[3], box6[4], box6[5])));
+  out6[0] = b.p_min.x; out6[1] = b.p_min.y; out6[2] = b.p_min.z;
+  out6[3] = b.p_max.x; out6[4] = b.p_max.y; out6[5] = b.p_max.z;
+}
+// Transform::xf(Ray): ray8 = o, mint, d, maxt
+void orc_xf_ray(const float* m, const float* minv, const float* ray8, float* out8) {
+  Ray r(V3(ray8[0], ray8[1], ray8[2]), V3(ray8[4], ray8[5], ray8[6]), ray8[3]);
+  r.maxt = ray8[7];
+  Ray t = xf_ray(xf_from(m, minv), r);
+  out8[0] = t.o.x; out8[1] = t.o.y; out8[2] = t.o.z; out8[3] = t.mint;
+  out8[4] = t.d.x; out8[5] = t.d.y; out8[6] = t.d.z; out8[7] = t.maxt;
+}
 void orc_task_windows(const int32_t* ext4, uint32_t num_tasks, int32_t* windows, uint32_t* keys) {
   SamplerDesc sd;
   for (int i = 0; i < 4; ++i) sd.ext[i] = ext4[i];

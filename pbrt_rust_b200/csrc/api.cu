@@ -174,11 +174,11 @@ int trace_grid(pbrtb200_ctx* ctx, const void* kernel) {
 
 // Dispatch on (ANY, SPH, MULTI, SRC, MODE).  MODE = SIMT loop shape (trace.cuh); the defaults were
 // chosen from measurements (profiles/), PBRTB200_TRACE_MODE / PBRTB200_SHADOW_MODE override them.
-int env_mode(const char* name, int dflt) {
+int env_mode(const char* name, int dflt, int max_mode) {
   const char* v = std::getenv(name);
   if (!v || !*v) return dflt;
   const int m = std::atoi(v);
-  return (m >= 0 && m <= 1) ? m : dflt;
+  return (m >= 0 && m <= max_mode) ? m : dflt;
 }
 
 template <bool ANY, int SRC>
@@ -192,8 +192,8 @@ int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a_in)
   }();
   TraceArgs a = a_in;
   a.batch = (uint32_t)batch;
-  static const int mode_closest = env_mode("PBRTB200_TRACE_MODE", 1);
-  static const int mode_any = env_mode("PBRTB200_SHADOW_MODE", 0);
+  static const int mode_closest = env_mode("PBRTB200_TRACE_MODE", 1, 1);
+  static const int mode_any = env_mode("PBRTB200_SHADOW_MODE", 0, 3);  // 2, 3: unordered (trace.cuh)
   const int mode = ANY ? mode_any : mode_closest;
 #define PB_LAUNCH(SPH, MULTI, MODE)                                                        \
   {                                                                                        \
@@ -203,7 +203,10 @@ int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a_in)
   }
 #define PB_LAUNCH_M(SPH, MULTI)                                                            \
   {                                                                                        \
-    if (mode == 0) PB_LAUNCH(SPH, MULTI, 0) else PB_LAUNCH(SPH, MULTI, 1)              \
+    if (mode == 0) PB_LAUNCH(SPH, MULTI, 0) else if (mode == 1) PB_LAUNCH(SPH, MULTI, 1)   \
+    else if constexpr (ANY) {                                                              \
+      if (mode == 2) PB_LAUNCH(SPH, MULTI, 2) else PB_LAUNCH(SPH, MULTI, 3)            \
+    }                                                                                      \
   }
   if (ctx->has_spheres) {
     if (ctx->multi_leaf) PB_LAUNCH_M(true, true) else PB_LAUNCH_M(true, false)
@@ -679,7 +682,13 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   sc.textures = ctx->d_textures.as<pbrtb200_texture>();
   sc.mipmaps = s->n_mipmaps ? ctx->d_mipmaps.as<pbrtb200_mipmap>() : nullptr;
   sc.texels = s->n_mipmaps ? ctx->d_texels.as<float4>() : nullptr;
-  ctx->shade_ext = scene_needs_ext(s);
+  // PBRTB200_FORCE_EXT=1 runs every scene through the general evaluator (measurement knob: what the
+  // out-of-line texture path costs on a scene that does not need it)
+  static const bool force_ext = [] {
+    const char* v = std::getenv("PBRTB200_FORCE_EXT");
+    return v && *v && std::atoi(v) != 0;
+  }();
+  ctx->shade_ext = force_ext || scene_needs_ext(s);
   sc.n_prims = s->n_prims;
   sc.n_lights = s->n_lights;
   {

@@ -157,6 +157,10 @@ PB_DEV bool slab_test_finite(float bminx, float bminy, float bminz, float bmaxx,
 // MODE selects the SIMT loop shape (both visit the same leaves in the same order):
 //   0  if-if        : each iteration a lane does one node step OR one leaf        (best for any-hit)
 //   1  while-while  : lanes run node steps until every lane of the warp holds a leaf (best closest)
+//   2, 3 (ANY only) : shapes 0 / 1 without the near/far child ordering.  An any-hit query is a
+//                     boolean over the set of leaves whose boxes pass; no accepted hit shrinks maxt
+//                     before it returns, so that set does not depend on the visiting order and the
+//                     axis decode + selects of bvh.rs:409-415 buy nothing for unoccluded rays.
 // Measured and dropped (profiles/r01_notes.md): speculative postponed-leaf traversal (no gain) and a
 // persistent kernel with per-lane ray refill (-30..-70 %: refilled lanes lose ray coherence), and a
 // warp-cooperative any-hit kernel with subtree stealing between lanes (-18 %).
@@ -164,6 +168,8 @@ template <bool ANY, bool SPH, bool MULTI, bool FINITE, int MODE>
 PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, float maxt,
                             uint32_t* s_ref, float* s_t0) {
   constexpr int stride = PB_TRACE_THREADS;
+  constexpr bool UNORDERED = ANY && MODE >= 2;
+  constexpr int SHAPE = MODE & 1;
   TraceResult res;
   res.prim = PBRTB200_MISS;
   res.t = 0.f;
@@ -207,9 +213,12 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
     const bool h1 = box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &T01);
     const uint32_t r0 = __float_as_uint(q3.x), r1 = __float_as_uint(q3.y);
     if (h0 & h1) {
-      const uint32_t axis = __float_as_uint(q3.w);
       // bvh.rs:409-415: dir_is_neg[axis] -> the second child is visited first
-      const bool neg = axis == 0 ? neg0 : (axis == 1 ? neg1 : neg2);
+      bool neg = false;
+      if (!UNORDERED) {
+        const uint32_t axis = __float_as_uint(q3.w);
+        neg = axis == 0 ? neg0 : (axis == 1 ? neg1 : neg2);
+      }
       const uint32_t far_ref = neg ? r0 : r1;
       const float far_t0 = neg ? T00 : T01;
       if (sp < PB_SM_STACK) {
@@ -267,7 +276,7 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
            sc.root_bmax[2], &T0root))
     return res;
   uint32_t cur = sc.root_ref;
-  if (MODE == 0) {
+  if (SHAPE == 0) {
     while (cur != PB_DONE) {
       if (!(cur & PB_LEAF_BIT)) {
         cur = node_step(cur);
@@ -276,7 +285,7 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
         cur = pop();
       }
     }
-  } else if (MODE == 1) {
+  } else {
     for (;;) {
       while (!(cur & PB_LEAF_BIT)) cur = node_step(cur);
       if (cur == PB_DONE) break;

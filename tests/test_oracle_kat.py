@@ -1054,3 +1054,199 @@ def test_bump_mapping(orc):
     assert np.abs(b[3:6] - np.array([0, 1, 0])).max() < 1e-6                       # no v dependence
     n = np.array([-2.0, 0.0, 1.0]) / math.sqrt(5.0)
     assert np.abs(b[6:9] - n).max() < 1e-6
+
+
+# ---- Matrix4x4 / Transform: transform/matrix4x4.rs and transform/transform.rs tests ---------------
+
+def _m(rows):
+    return np.array(rows, np.float32).reshape(4, 4)
+
+
+def _mat_mul(orc, a, b):
+    out = np.zeros((4, 4), np.float32)
+    orc.lib().orc_mat_mul(_p(_m(a)), _p(_m(b)), _p(out))
+    return out
+
+
+def _invert(orc, a):
+    out = np.zeros((4, 4), np.float32)
+    rc = orc.lib().orc_invert(_p(_m(a)), _p(out))
+    return rc, out
+
+
+class _X:
+    """Transform = (m, m_inv) with the oracle's algebra"""
+
+    def __init__(self, orc, m, mi):
+        self.orc, self.m, self.mi = orc, np.ascontiguousarray(m, np.float32), np.ascontiguousarray(mi, np.float32)
+
+    @staticmethod
+    def mk(orc, kind, a3):
+        return _X(orc, *_xf(orc, kind, a3))
+
+    @staticmethod
+    def from_matrix(orc, m):
+        rc, mi = _invert(orc, m)
+        assert rc == 0
+        return _X(orc, _m(m), mi)
+
+    def __mul__(self, o):
+        m, mi = np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32)
+        self.orc.lib().orc_xf_mul(_p(self.m), _p(self.mi), _p(o.m), _p(o.mi), _p(m), _p(mi))
+        return _X(self.orc, m, mi)
+
+    def inverse(self):
+        return _X(self.orc, self.mi, self.m)
+
+    def apply(self, kind, v):
+        out, v = np.zeros(3, np.float32), np.array(v, np.float32)
+        self.orc.lib().orc_xf_apply(_p(self.m), _p(self.mi), kind, _p(v), _p(out))
+        return out
+
+    pt = lambda self, v: self.apply(0, v)
+    vec = lambda self, v: self.apply(1, v)
+    nrm = lambda self, v: self.apply(2, v)
+
+    def swaps(self):
+        return bool(self.orc.lib().orc_xf_swaps_handedness(_p(self.m), _p(self.mi)))
+
+
+def _nrm3(v):
+    v = np.array(v, np.float32)
+    return v * (f32(1.0) / np.sqrt(np.sum(v * v, dtype=np.float32)))
+
+
+def test_matrix4x4_transpose_and_product(orc):
+    """transform/matrix4x4.rs:277-330 it_can_be_transposed / they_can_be_multiplied"""
+    a = [[1, 2, 3, 4], [4, 3, 2, 1], [-1, 2, -3, 4], [0, 0, 0, 0]]
+    out = np.zeros((4, 4), np.float32)
+    orc.lib().orc_mat_transpose(_p(_m(a)), _p(out))
+    assert out.tolist() == [[1, 4, -1, 0], [2, 3, 2, 0], [3, 2, -3, 0], [4, 1, 4, 0]]
+    ident = np.eye(4, dtype=np.float32)
+    m1 = [[1, 4, -1, 0], [2, 3, 2, 0], [3, 2, -3, 0], [4, 1, 4, 0]]
+    m2 = [[3, -2, -1, 0], [0, 0.1, -2, 3], [2, 6, 3, 0], [6, 6, 1, 1]]
+    assert np.array_equal(_mat_mul(orc, ident, ident), ident)
+    assert np.array_equal(_mat_mul(orc, m1, ident), _m(m1)) and np.array_equal(_mat_mul(orc, ident, m2), _m(m2))
+    want = _m([[1, -7.6, -12, 12], [10, 8.3, -2, 9], [3, -23.8, -16, 6], [20, 16.1, 6, 3]])
+    assert np.array_equal(_mat_mul(orc, m1, m2), want)
+    assert not np.array_equal(_mat_mul(orc, m2, m1), want)
+
+
+def test_matrix4x4_inverse(orc):
+    """transform/matrix4x4.rs:332-375 it_can_be_inverted (check_mat!: |diff| < 5e-5) and
+    it_cant_invert_singular_matrices (panic -> error)"""
+    rc, inv = _invert(orc, np.eye(4))
+    assert rc == 0 and np.abs(inv - np.eye(4)).max() < 5e-5
+    m = [[1, -2, 3, 0], [2, -5, 12, 0], [0, 2, -10, 0], [0, 0, 0, 1]]
+    rc, inv = _invert(orc, m)
+    assert rc == 0
+    assert np.abs(_mat_mul(orc, m, inv) - np.eye(4)).max() < 5e-5 and np.abs(_mat_mul(orc, inv, m) - np.eye(4)).max() < 5e-5
+    n = [[2, 3, 1, 5], [1, 0, 3, 1], [0, 2, -3, 2], [0, 2, 3, 1]]
+    rc, inv = _invert(orc, n)
+    assert rc == 0 and np.abs(inv - _m([[18, -35, -28, 1], [9, -18, -14, 1], [-2, 4, 3, 0], [-12, 24, 19, -1]])).max() < 5e-5
+    m2 = [[-0.70710677, -0.40824828, -0.57735026, 1.0], [0.0, 0.81649655, -0.57735026, 1.0],
+          [0.70710677, -0.40824828, -0.57735026, 1.0], [0, 0, 0, 1]]
+    rc, inv = _invert(orc, m2)
+    want = _m([[-0.70710677, 0.0, 0.70710677, 0.0], [-0.40824828, 0.81649655, -0.40824828, 0.0],
+               [-0.57735026, -0.57735026, -0.57735026, 1.73205], [0, 0, 0, 1]])
+    assert rc == 0 and np.abs(inv - want).max() < 5e-5
+    rc, _ = _invert(orc, [[32, 8, 11, 17], [8, 20, 17, 23], [11, 17, 14, 26], [17, 23, 26, 2]])
+    assert rc != 0 and b"ingular" in orc.lib().orc_last_error()
+
+
+def test_transform_vectors_points_normals(orc):
+    """transform/transform.rs: it_can_transform_vectors, it_cannot_translate_vectors,
+    it_can_transform_points, it_can_transform_normals, it_can_translate_points, it_can_scale_vectors"""
+    s2 = f32(np.sqrt(f32(2.0)))
+    rx45 = _X.mk(orc, 2, [45.0, 0, 0])
+    v = _nrm3([1, 1, 0])
+    vt = np.array([s2 / f32(2), 0.5, 0.5], np.float32)
+    assert float(np.sum((rx45.vec(v) - vt) ** 2)) < 1e-6
+    ident = _X(orc, np.eye(4), np.eye(4))
+    assert ident.vec(vt).tolist() == vt.tolist()
+    x2 = _X.mk(orc, 0, [1, 2, 3]) * _X.mk(orc, 3, [90.0, 0, 0])
+    assert float(np.sum((x2.vec([1, 1, 1]) - np.array([1, 1, -1])) ** 2)) < 1e-6
+    assert x2.vec([0, 0, 0]).tolist() == [0, 0, 0] and ident.vec([1, 5, -13]).tolist() == [1, 5, -13]
+    assert _X.mk(orc, 0, [1, 4, -300]).vec([1, 1, 1]).tolist() == [1, 1, 1]
+    assert x2.pt([1, 1, 1]).tolist() == [2, 3, 2] and x2.pt([0, 0, 0]).tolist() == [1, 2, 3]
+    assert ident.pt([1, 5, -13]).tolist() == [1, 5, -13]
+    assert x2.nrm(_nrm3([1, 1, 1])).tolist() == _nrm3([1, 1, -1]).tolist()
+    assert _nrm3(_X.mk(orc, 1, [2, 2, 2]).nrm([1, 0, 0])).tolist() == [1, 0, 0]
+    got = _nrm3(_X.mk(orc, 3, [45.0, 0, 0]).nrm(_nrm3([1, 1, 1])))
+    assert got.tolist() == [f32(0.8164967), f32(0.5773503), 0.0]
+    assert _X.mk(orc, 0, [1, 2, 3]).pt([1, 1, 1]).tolist() == [2, 3, 4]
+    sc = _X.mk(orc, 1, [2.0, 0.5, 100.0])
+    assert sc.vec([1, 2, 0]).tolist() == [2, 1, 0] and sc.vec([-1, 0, -0.01]).tolist() == [-2, 0, -1]
+
+
+def test_transform_inverse_and_rotations(orc):
+    """transform/transform.rs: it_can_be_inverted, it_can_rotate_about_x / y / z"""
+    x = _X.from_matrix(orc, [[2, 3, 1, 5], [1, 0, 3, 1], [0, 2, -3, 2], [0, 2, 3, 1]])
+    p = np.array([1, 2, 3], np.float32)
+    assert float(np.sum((x.inverse().pt(x.pt(p)) - p) ** 2)) < 1e-6
+    s2 = f32(np.sqrt(f32(2.0)))
+    for kind, axis, src, want in ((2, [1, 0, 0], [1, 1, 0], [s2 / 2, 0.5, 0.5]),
+                                  (3, [0, 1, 0], [1, 1, 0], [0.5, s2 / 2, -0.5]),
+                                  (4, [0, 0, 1], [0, 1, 1], [-0.5, 0.5, s2 / 2])):
+        r = _X.mk(orc, kind, [45.0, 0, 0])
+        assert r.vec(axis).tolist() == axis and r.vec([0, 0, 0]).tolist() == [0, 0, 0]
+        assert float(np.sum((r.vec(_nrm3(src)) - np.array(want, np.float32)) ** 2)) < 1e-6
+
+
+def test_transform_look_at(orc):
+    """transform/transform.rs it_can_look_at_a_point"""
+    def look(pos, at, up):
+        m, mi = np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32)
+        a, b, c = (np.array(v, np.float32) for v in (pos, at, up))
+        orc.lib().orc_look_at(_p(a), _p(b), _p(c), _p(m), _p(mi))
+        return _X(orc, m, mi)
+    x = look([1, 1, 1], [0, 0, 0], [0, 1, 0])
+    o = x.pt([0, 0, 0])
+    assert abs(o[0]) < 1e-6 and abs(o[1]) < 1e-6 and o[2] > 1.0
+    q = x.pt([-1, -1, -1])
+    assert abs(q[0]) < 1e-6 and abs(q[1]) < 1e-6 and q[2] > 2.0
+    x2 = look([1, 2, 3], [-1, 0, 4], [0, 1, 0])
+    z = x2.pt([0, 0, -3])
+    assert z[2] == 0.0 and abs(z[0]) > 0.1 and abs(z[1]) > 0.1
+    mid = x2.pt([0, 1, 3.5])
+    assert mid[2] > 1.0 and abs(mid[0]) < 1e-6 and abs(mid[1]) < 1e-6
+
+
+def test_transform_handedness_rays_and_bboxes(orc):
+    """transform/transform.rs: it_can_detect_handedness_swap, it_can_transform_rays,
+    it_can_transform_bboxes"""
+    ident = _X(orc, np.eye(4), np.eye(4))
+    assert not ident.swaps()
+    flips = []
+    for k in range(3):
+        m = np.eye(4, dtype=np.float32)
+        m[k, k] = -1.0
+        flips.append(_X.from_matrix(orc, m))
+        assert flips[-1].swaps()
+    m2 = flips[2]
+    x1 = m2 * _X.mk(orc, 2, [34.0, 0, 0])
+    x2 = x1 * _X.mk(orc, 0, [1, -2, 4])
+    la_m, la_mi = np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32)
+    a, b, c = (np.array(v, np.float32) for v in ([1, 0, -3], [15, 12, -0.0], [0, 1, 0]))
+    orc.lib().orc_look_at(_p(a), _p(b), _p(c), _p(la_m), _p(la_mi))
+    x3 = x2 * _X(orc, la_m, la_mi)
+    assert x1.swaps() and x2.swaps() and x3.swaps() and not (x3 * m2).swaps()
+    # rays: only o and d move
+    ray = np.array([0, 0, 0, 0.0, 1, 0, 0, 3.4028235e38], np.float32)
+    out = np.zeros(8, np.float32)
+    orc.lib().orc_xf_ray(_p(ident.m), _p(ident.mi), _p(ray), _p(out))
+    assert out.tolist() == ray.tolist()
+    x = _X.mk(orc, 0, [1, 1, 1]) * _X.mk(orc, 3, [90.0, 0, 0])
+    orc.lib().orc_xf_ray(_p(x.m), _p(x.mi), _p(ray), _p(out))
+    assert out[0:3].tolist() == [1, 1, 1] and float(np.sum((out[4:7] - np.array([0, 0, -1])) ** 2)) < 1e-6
+    assert out[3] == 0.0 and out[7] == ray[7]
+    # bboxes
+    box = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    got = np.zeros(6, np.float32)
+    orc.lib().orc_xf_bbox(_p(ident.m), _p(ident.mi), _p(box), _p(got))
+    assert got.tolist() == box.tolist()
+    x = _X.mk(orc, 0, [-3, 0, 1]) * _X.mk(orc, 2, [45.0, 0, 0])
+    orc.lib().orc_xf_bbox(_p(x.m), _p(x.mi), _p(box), _p(got))
+    s2 = f32(np.sqrt(f32(2.0)))
+    want = np.array([-4.0, -s2, -s2 + f32(1.0), -2.0, s2, s2 + f32(1.0)], np.float32)
+    assert got.tolist() == want.tolist()  # assert_eq! in the reference: exact
