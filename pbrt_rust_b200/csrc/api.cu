@@ -193,7 +193,7 @@ int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a_in)
   TraceArgs a = a_in;
   a.batch = (uint32_t)batch;
   static const int mode_closest = env_mode("PBRTB200_TRACE_MODE", 1, 1);
-  static const int mode_any = env_mode("PBRTB200_SHADOW_MODE", 0, 3);  // 2, 3: unordered (trace.cuh)
+  static const int mode_any = env_mode("PBRTB200_SHADOW_MODE", 2, 3);  // 2, 3: unordered (trace.cuh)
   const int mode = ANY ? mode_any : mode_closest;
 #define PB_LAUNCH(SPH, MULTI, MODE)                                                        \
   {                                                                                        \

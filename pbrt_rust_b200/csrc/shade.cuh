@@ -547,14 +547,21 @@ PB_DEV uint32_t warp_agg_inc(uint32_t* ctr) {
 // out-of-line one (EXT).
 template <bool IMG, bool EXT>
 PB_DEV f3 shade_tex(const DScene& sc, const TexEnv& env, int id, const DG& dg) {
-  if constexpr (EXT)
-    return tex_eval_ext<PBRTB200_TEX_MAX_DEPTH>(env, id, dg);
-  else
+  if constexpr (EXT) {
+    const pbrtb200_texture* tx = env.textures + id;  // constants (most sigma / ks / roughness maps) stay inline
+    if (__ldg(&tx->kind) == PBRTB200_TEX_CONSTANT) return mk3(__ldg(&tx->value[0]), __ldg(&tx->value[1]), __ldg(&tx->value[2]));
+    // The out-of-line evaluator takes the geometry by address; a private copy made only on this
+    // path keeps the caller's `dg` in registers (an unconditional copy cost config 3 0.2 ms/frame
+    // of local-memory stores although all of its textures are constants).
+    const DG tmp = dg;
+    return tex_eval_ext<PBRTB200_TEX_MAX_DEPTH>(env, id, tmp);
+  } else {
     return tex_eval<3, IMG>(sc, id, dg);
+  }
 }
 
 #ifndef PB_SHADE_EXT_MIN_BLOCKS
-#define PB_SHADE_EXT_MIN_BLOCKS 4  // general texture evaluator + bump: 128 registers
+#define PB_SHADE_EXT_MIN_BLOCKS 6  // general texture evaluator + bump: 80 registers (4 / 6 / 8 measured, profiles/r01_notes.md)
 #endif
 
 struct ShadeArgs {

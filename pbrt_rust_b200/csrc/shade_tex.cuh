@@ -278,7 +278,12 @@ PB_DEV DG bump_dg_(const TexEnv& env, int d, const DG& dgs, f3 ng, bool flip) {
   ev.v = dgs.v + dv;
   ev.nn = normalize3(cross3(dgs.dpdu, dgs.dpdv) + dv * dgs.dndv);
   const float v_displace = tex_eval_ext<PBRTB200_TEX_MAX_DEPTH>(env, d, ev).x;
-  const float displace = tex_eval_ext<PBRTB200_TEX_MAX_DEPTH>(env, d, dgs).x;
+  // d.evaluate(dg_shading): through `ev` again, so that only this one copy has its address taken
+  // (the caller's dgs stays in registers)
+  ev.p = dgs.p;
+  ev.v = dgs.v;
+  ev.nn = dgs.nn;
+  const float displace = tex_eval_ext<PBRTB200_TEX_MAX_DEPTH>(env, d, ev).x;
   DG b = dgs;
   b.dpdu = dgs.dpdu + (u_displace - displace) / du * dgs.nn + displace * dgs.dndu;
   b.dpdv = dgs.dpdv + (v_displace - displace) / dv * dgs.nn + displace * dgs.dndv;
