@@ -184,6 +184,54 @@ def test_error_codes():
     assert e.value.code == -1
 
 
+def test_upload_validates_texture_tables():
+    """pbrtb200_upload_scene rejects what the device evaluator cannot run (PBRTB200_EINVAL, never a
+    wrong image): parents nested deeper than PBRTB200_TEX_MAX_DEPTH, a noise texture without its 3D
+    mapping, a child index out of range, an unknown kind; the deepest legal nesting is accepted."""
+    import ctypes as C
+    T = pb.api.Texture
+    leaf = T.constant(0.5)
+
+    def nest(levels):
+        t = leaf
+        for _ in range(levels):
+            t = T.scale(t, T.constant(0.9))
+        return t
+
+    def cfg_with(kd):
+        cfg = scenes.config1(xres=32, yres=24)
+        for p in cfg["scene"].aggregate.prims:
+            p.material.kd = kd
+        return cfg
+
+    ok = cfg_with(nest(3))
+    film = _renderer(ok).render(ok["scene"])
+    assert np.isfinite(film).all() and film[..., :3].max() > 0
+    bad = cfg_with(nest(4))
+    with pytest.raises(pb.PbrtError) as e:
+        _renderer(bad).render(bad["scene"])
+    assert e.value.code == -1
+
+    def corrupt(mutate):
+        cfg = cfg_with(T.mix(T.fbm(3, 0.5), T.uv(pb.api.UVMapping2D()), T.constant(0.25)))
+        r = _renderer(cfg)
+        hs = pb.api.HostScene(cfg["scene"])
+        f = hs.flat.contents
+        mutate(f, hs)
+        with pytest.raises(pb.PbrtError) as e:
+            r.ctx.upload(hs)
+        assert e.value.code == -1
+
+    def kind_of(f, k):
+        return next(i for i in range(f.n_textures) if f.textures[i].kind == k)
+
+    corrupt(lambda f, hs: setattr(f.textures[kind_of(f, 8)], "map_kind", 0))     # fbm needs IdentityMapping3D
+    corrupt(lambda f, hs: setattr(f.textures[kind_of(f, 5)], "tex3", 10 ** 6))   # amount index out of range
+    corrupt(lambda f, hs: setattr(f.textures[kind_of(f, 2)], "kind", 42))        # unknown kind
+    corrupt(lambda f, hs: setattr(f.textures[kind_of(f, 2)], "map_kind", 9))     # unknown mapping
+    corrupt(lambda f, hs: setattr(f.materials[0], "bump", 10 ** 6))              # bump index out of range
+
+
 # ---- BASELINE.json's full sizes ---------------------------------------------------------------
 def test_config2_full_size_hit_ids_bit_exact(orc):
     """Config 2 as named: BVH (sah/4) over 100 K random triangles, 1920x1080, pixel-centre samples.
