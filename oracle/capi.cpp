@@ -738,6 +738,29 @@ void orc_xf_ray(const float* m, const float* minv, const float* ray8, float* out
   out8[0] = t.o.x; out8[1] = t.o.y; out8[2] = t.o.z; out8[3] = t.mint;
   out8[4] = t.d.x; out8[5] = t.d.y; out8[6] = t.d.z; out8[7] = t.maxt;
 }
+// geometry/{vector,point,normal}.rs primitives used all over the path.  op: 0 cross -> out3,
+// 1 dot -> out[0], 2 length(a) -> out[0], 3 normalize(a) -> out3, 4 coordinate_system(a) -> out6,
+// 5 distance(a, b) -> out[0], 6 face_forward(a, b) -> out3, 7 length_squared(a), 8 distance_squared
+void orc_vec_op(int op, const float* a3, const float* b3, float* out) {
+  V3 a(a3[0], a3[1], a3[2]), b(b3[0], b3[1], b3[2]), r;
+  switch (op) {
+    case 0: r = cross(a, b); break;
+    case 1: out[0] = dot(a, b); return;
+    case 2: out[0] = length(a); return;
+    case 3: r = normalize(a); break;
+    case 4: {
+      V3 x, y;
+      coordinate_system(a, &x, &y);
+      out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = y.x; out[4] = y.y; out[5] = y.z;
+      return;
+    }
+    case 5: out[0] = distance(a, b); return;
+    case 6: r = face_forward(a, b); break;
+    case 7: out[0] = length_squared(a); return;
+    default: out[0] = length_squared(a - b); return;
+  }
+  out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
 void orc_task_windows(const int32_t* ext4, uint32_t num_tasks, int32_t* windows, uint32_t* keys) {
   SamplerDesc sd;
   for (int i = 0; i < 4; ++i) sd.ext[i] = ext4[i];

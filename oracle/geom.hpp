@@ -89,6 +89,8 @@ inline float distance(const V3& a, const V3& b) { return length(a - b); }
 
 // vector.rs:184-195 (as written: the first branch uses v1.x for BOTH components where pbrt uses
 // -v1.z and v1.x; returns (v3 x v1, v3))
+// normal.rs:22-24 (a NaN dot product is not < 0: the normal is kept)
+inline V3 face_forward(const V3& n, const V3& v) { return dot(n, v) < 0.0f ? -n : n; }
 inline void coordinate_system(const V3& v1, V3* o1, V3* o2) {
   V3 v2;
   if (std::fabs(v1.x) > std::fabs(v1.y)) {

@@ -316,7 +316,7 @@ inline DiffGeom bump_dg(const TextureTable& tt, int d, const DiffGeom& dg_geom, 
   dg_bump.dpdv = dg_shading.dpdv + (v_displace - displace) / dv * dg_shading.nn + displace * dg_shading.dndv;
   dg_bump.nn = normalize(cross(dg_bump.dpdu, dg_bump.dpdv));
   if (dg_shading.flip) dg_bump.nn = V3(-dg_bump.nn.x, -dg_bump.nn.y, -dg_bump.nn.z);
-  if (dot(dg_bump.nn, dg_geom.nn) < 0.0f) dg_bump.nn = -dg_bump.nn;  // face_forward (normal.rs:22-24)
+  dg_bump.nn = face_forward(dg_bump.nn, dg_geom.nn);
   return dg_bump;
 }
 

@@ -1250,3 +1250,66 @@ def test_transform_handedness_rays_and_bboxes(orc):
     s2 = f32(np.sqrt(f32(2.0)))
     want = np.array([-4.0, -s2, -s2 + f32(1.0), -2.0, s2, s2 + f32(1.0)], np.float32)
     assert got.tolist() == want.tolist()  # assert_eq! in the reference: exact
+
+
+# ---- geometry/{vector,point,normal}.rs ------------------------------------------------------------
+
+def _vop(orc, op, a, b=(0, 0, 0), n=3):
+    out, a, b = np.zeros(6, np.float32), np.array(a, np.float32), np.array(b, np.float32)
+    orc.lib().orc_vec_op(op, _p(a), _p(b), _p(out))
+    return out[:n] if n > 1 else out[0]
+
+
+def test_vector_length_cross_dot_coordinate_system(orc):
+    """geometry/vector.rs:243-292 (lengths, cross), :431-466 (dot), :482-490 (coordinate_system)"""
+    inf, nan = float("inf"), float("nan")
+    for v, want in (((0, 0, 0), 0.0), ((1, 0, 0), 1.0), ((-1, 0, 0), 1.0), ((1, 1, 1), 3.0), ((0, 2, 0), 4.0),
+                    ((0, 0, 2), 4.0), ((inf, 0, 0), inf), ((0, inf, 0), inf), ((0, 0, inf), inf)):
+        assert _vop(orc, 7, v, n=1) == want and _vop(orc, 2, v, n=1) == np.sqrt(f32(want))
+    for k in range(3):
+        v = [0.0, 0.0, 0.0]
+        v[k] = nan
+        assert np.isnan(_vop(orc, 7, v, n=1)) and np.isnan(_vop(orc, 2, v, n=1))
+    x, y, z = (1, 0, 0), (0, 1, 0), (0, 0, 1)
+    neg = lambda v: [-c for c in v]
+    assert _vop(orc, 0, x, y).tolist() == list(z) and _vop(orc, 0, y, x).tolist() == neg(z)
+    assert _vop(orc, 0, y, z).tolist() == list(x) and _vop(orc, 0, z, y).tolist() == neg(x)
+    assert _vop(orc, 0, z, x).tolist() == list(y) and _vop(orc, 0, x, z).tolist() == neg(y)
+    assert _vop(orc, 0, (1, 1, 0), x).tolist() == neg(z) and _vop(orc, 0, x, (1, 1, 0)).tolist() == list(z)
+    assert _vop(orc, 1, x, y, 1) == 0 and _vop(orc, 1, y, z, 1) == 0 and _vop(orc, 1, z, x, 1) == 0
+    assert _vop(orc, 1, x, x, 1) == 1 and _vop(orc, 1, y, y, 1) == 1 and _vop(orc, 1, z, z, 1) == 1
+    v = (2, 3, 4)
+    assert [_vop(orc, 1, e, v, 1) for e in (x, y, z)] == [2, 3, 4]
+    s = np.sqrt(f32(113.0))
+    u = np.array([f32(3) / s, f32(10) / s, f32(2) / s], np.float32)
+    rem = np.array(v, np.float32) - _vop(orc, 1, u, v, 1) * u
+    assert abs(_vop(orc, 1, rem, u, 1)) < 1e-6
+    for k in range(3):
+        w = [0.0, 0.0, 0.0]
+        w[k] = nan
+        assert np.isnan(_vop(orc, 1, u, w, 1))
+        w[k] = inf
+        assert _vop(orc, 1, u, w, 1) == inf
+    v = (3.0, -1.0, 0.0003)
+    cs = _vop(orc, 4, v, n=6)
+    a, b = cs[:3], cs[3:]
+    assert abs(_vop(orc, 1, v, a, 1)) < 1e-6 and abs(_vop(orc, 1, v, b, 1)) < 1e-6 and abs(_vop(orc, 1, a, b, 1)) < 1e-6
+
+
+def test_point_distances_and_face_forward(orc):
+    """geometry/point.rs:196-226 (distance, distance_squared), geometry/normal.rs:415-430 (face_forward)"""
+    inf, nan = float("inf"), float("nan")
+    o = (0, 0, 0)
+    for v, want in (((0, 0, 0), 0.0), ((1, 0, 0), 1.0), ((-1, 0, 0), 1.0), ((1, 1, 1), 3.0), ((0, 2, 0), 4.0),
+                    ((0, 0, 2), 4.0), ((inf, 0, 0), inf), ((0, inf, 0), inf), ((0, 0, inf), inf)):
+        assert _vop(orc, 8, v, o, 1) == want and _vop(orc, 5, v, o, 1) == np.sqrt(f32(want))
+    for k in range(3):
+        v = [0.0, 0.0, 0.0]
+        v[k] = nan
+        assert np.isnan(_vop(orc, 8, v, o, 1)) and np.isnan(_vop(orc, 5, v, o, 1))
+    n, minus = [1.0, 0.0, 0.0], [-1.0, -0.0, -0.0]
+    ff = lambda v: _vop(orc, 6, n, v).tolist()
+    assert ff((-1, -1, -1)) == minus and ff((1, 1, 1)) == n
+    for v in ((nan, 1, 1), (1, nan, 1), (1, 1, nan), (inf, 1, 1), (1, inf, 1), (1, 1, inf), (1, -inf, 1), (1, 1, -inf)):
+        assert ff(v) == n
+    assert ff((-inf, 1, 1)) == minus
