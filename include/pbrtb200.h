@@ -212,6 +212,7 @@ typedef struct {
 
 #define PBRTB200_SAMPLER_STRATIFIED 0
 #define PBRTB200_SAMPLER_LD 1
+#define PBRTB200_SAMPLER_HALTON 2 /* Sampler::halton (src/sampler/halton.rs): xs = samples per pixel */
 /* Sampler::stratified / low_discrepancy (src/sampler/mod.rs:30-50) over the full sample extent,
  * plus SamplerRenderer.num_tasks (sampler_renderer.rs:41-44), which fixes the per-task sub-windows
  * (sampler/base.rs:29-48) and RNG seeds (sampler_renderer.rs:74).                               */
@@ -317,6 +318,14 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam,
                           const pbrtb200_sampler* smp, pbrtb200_hit16* out_hits,
                           float* out_samples, pbrtb200_ray32* out_rays, int is_device,
                           pbrtb200_stats* stats);
+
+/* HaltonSampler frames have a variable number of samples per pixel.  Per-sample outputs of
+ * pbrtb200_primary_hits then use a padded layout: *cap slots per pixel of the sampler extent
+ * ([((y - y_start) * width + (x - x_start)) * cap + slot]), a pixel's samples in generation order,
+ * unused slots with prim = PBRTB200_MISS and NaN image coordinates.  This call returns cap (the
+ * largest per-pixel count) and the number of real samples so that the caller can size them.     */
+int pbrtb200_halton_layout(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t* cap,
+                           uint64_t* n_samples);
 
 /* Film::write_image's pixel pipeline as intended (src/camera/film.rs:316-354 + write_img :15-33;
  * the code as written allocates n_pix instead of 3*n_pix floats and overwrites rgb

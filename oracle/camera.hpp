@@ -345,6 +345,7 @@ struct SamplerDesc {
 
   size_t spp() const {
     if (kind == 0) return (size_t)xs * (size_t)ys;
+    if (kind == 2) return (size_t)xs;  // HaltonSampler: samples_per_pixel as given (halton.rs:18-29)
     size_t p = 1;
     while (p < (size_t)xs) p <<= 1;  // lds.rs:18 next_power_of_two
     return p;
@@ -356,6 +357,74 @@ struct SamplerDesc {
     return cam + 2 * n * (size_t)light_samples;
   }
 };
+
+// ---------------------------------------------------------------------------------------------
+// HaltonSampler (sampler/halton.rs), sampler kind 2.
+// montecarlo.rs:7-20 (f64 arithmetic, as written)
+inline double radical_inverse(uint64_t n, uint64_t b) {
+  double v = 0.0;
+  uint64_t num = n;
+  const double inv_base = 1.0 / (double)b;
+  double aib = 1.0;
+  while (num > 0) {
+    double d = (double)(num % b);
+    num /= b;
+    aib *= inv_base;
+    v += d * aib;
+  }
+  return v;
+}
+static const uint32_t HALTON_PRIMES[40] = {2,  3,  5,  7,  11, 13, 17, 19, 23, 29,  31,  37,  41,  43,
+                                           47, 53, 59, 61, 67, 71, 73, 79, 83, 89,  97,  101, 103, 107,
+                                           109, 113, 127, 131, 137, 139, 149, 151, 157, 163, 167, 173};
+#define ORC_HALTON_MAX_LIGHT_PAIRS 16
+// One (sub-)sampler: HaltonSampler::new over a window (halton.rs:18-29)
+struct HaltonWindow {
+  int ext[4];
+  float delta;      // lerp_delta = dy.max(dx) (halton.rs:62-66)
+  uint64_t wanted;  // max(dx, dy)^2 * samples_per_pixel
+};
+inline HaltonWindow halton_window(const int ext[4], size_t spp) {
+  HaltonWindow w;
+  for (int i = 0; i < 4; ++i) w.ext[i] = ext[i];
+  const int dx = ext[1] - ext[0], dy = ext[3] - ext[2];
+  const int m = dx > dy ? dx : dy;
+  w.wanted = (uint64_t)((int64_t)m * (int64_t)m) * (uint64_t)spp;
+  w.delta = rmax((float)dy, (float)dx);
+  return w;
+}
+// get_more_samples for candidate index i = current_sample (halton.rs:49-108).  Returns false when
+// the candidate falls outside the window and is skipped.  The lens / time dimensions use the index
+// AFTER the increment (`self.current_sample += 1` precedes them, :72), as written.
+// Light-sample floats: ORACLE-DEFINED (as written the 1D/2D sample arrays panic —
+// `split_at_mut(off)` hands latin_hypercube the slice before the offset, :96-107): pair q of the
+// camera sample = radical inverses of the incremented index in bases prime[5 + 2q], prime[6 + 2q].
+inline bool halton_candidate(const SamplerDesc& sd, const HaltonWindow& w, uint64_t i, CameraSample* cs,
+                             float* light_u) {
+  const float u = (float)radical_inverse(i, 3);
+  const float v = (float)radical_inverse(i, 2);
+  const float xs = (float)w.ext[0], ys = (float)w.ext[2];
+  const float image_x = lerpf(xs, xs + w.delta, u);
+  const float image_y = lerpf(ys, ys + w.delta, v);
+  const uint64_t cur = i + 1;
+  if (image_x >= (float)w.ext[1] || image_y >= (float)w.ext[3]) return false;
+  cs->image_x = image_x;
+  cs->image_y = image_y;
+  cs->lens_u = (float)radical_inverse(cur, 5);
+  cs->lens_v = (float)radical_inverse(cur, 7);
+  cs->time = lerpf(sd.sopen, sd.sclose, (float)radical_inverse(cur, 11));
+  for (int q = 0; q < sd.light_samples; ++q) {
+    light_u[2 * q] = (float)radical_inverse(cur, HALTON_PRIMES[5 + 2 * q]);
+    light_u[2 * q + 1] = (float)radical_inverse(cur, HALTON_PRIMES[6 + 2 * q]);
+  }
+  return true;
+}
+// Home pixel of an accepted sample inside its window (binning only: add_sample decides coverage).
+inline void halton_home_pixel(const HaltonWindow& w, const CameraSample& cs, int* px, int* py) {
+  int x = f2i(std::floor(cs.image_x)), y = f2i(std::floor(cs.image_y));
+  *px = x < w.ext[0] ? w.ext[0] : (x > w.ext[1] - 1 ? w.ext[1] - 1 : x);
+  *py = y < w.ext[2] ? w.ext[2] : (y > w.ext[3] - 1 ? w.ext[3] - 1 : y);
+}
 
 // Generates the `spp` camera samples (and light-sample floats) of ONE pixel, advancing `rng`
 // exactly as the reference's get_more_samples does (stratified.rs:60-127 / lds.rs:50-70 +

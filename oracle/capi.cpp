@@ -3,6 +3,7 @@
 // extern "C" surface of the CPU oracle, loaded with ctypes by tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs (nothing else may load it).
 #include <chrono>
+#include <limits>
 #include <cstdio>
 #include <string>
 
@@ -464,6 +465,46 @@ int orc_camera_samples(const OrcRenderConfig* c, int light_pairs, int x0, int x1
       }
   });
 }
+
+// HaltonSampler: slots per pixel of the padded per-sample layout (the largest per-pixel count)
+// and, optionally, the per-pixel counts over the full sampler extent.
+int orc_halton_cap(const OrcRenderConfig* c, int light_pairs, uint32_t* out_cap, uint32_t* out_counts) {
+  return guarded([&] {
+    RenderConfig cfg = make_config(nullptr, c);
+    cfg.sampler.light_samples = light_pairs;
+    HaltonLayout L = halton_layout(cfg.sampler, cfg.num_tasks, std::max(1, cfg.n_threads));
+    *out_cap = L.cap;
+    if (out_counts) std::memcpy(out_counts, L.counts.data(), L.counts.size() * sizeof(uint32_t));
+  });
+}
+// HaltonSampler camera samples in the padded layout [pixel raster over the full extent][cap]:
+// out_cs 5 floats (NaN image coordinates mark unused slots), out_light_u 2 * light_pairs floats.
+int orc_halton_samples(const OrcRenderConfig* c, int light_pairs, uint32_t cap, float* out_cs, float* out_light_u) {
+  return guarded([&] {
+    RenderConfig cfg = make_config(nullptr, c);
+    cfg.sampler.light_samples = light_pairs;
+    HaltonLayout L = halton_layout(cfg.sampler, cfg.num_tasks, std::max(1, cfg.n_threads));
+    if (cap != L.cap) throw std::runtime_error("halton: cap mismatch");
+    const size_t total = L.counts.size() * (size_t)cap, lf = 2 * (size_t)light_pairs;
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    for (size_t k = 0; k < total; ++k) {
+      out_cs[5 * k] = out_cs[5 * k + 1] = nan;
+      out_cs[5 * k + 2] = out_cs[5 * k + 3] = out_cs[5 * k + 4] = 0.f;
+    }
+    for (size_t k = 0; k < L.entries.size(); ++k) {
+      const HaltonEntry& e = L.entries[k];
+      const size_t o = (size_t)e.pixel * cap + e.slot;
+      out_cs[5 * o] = e.cs.image_x;
+      out_cs[5 * o + 1] = e.cs.image_y;
+      out_cs[5 * o + 2] = e.cs.lens_u;
+      out_cs[5 * o + 3] = e.cs.lens_v;
+      out_cs[5 * o + 4] = e.cs.time;
+      if (out_light_u)
+        for (size_t q = 0; q < lf; ++q) out_light_u[lf * o + q] = L.light_u[lf * k + q];
+    }
+  });
+}
+double orc_radical_inverse(uint64_t n, uint64_t b) { return radical_inverse(n, b); }
 
 // ---- small known-answer hooks (each mirrors one reference function) ----
 int orc_quadratic(float a, float b, float c, float* t0, float* t1) {

@@ -87,6 +87,10 @@ def lib():
         L.orc_mipmap_level.argtypes = [C.c_void_p, u32, C.c_void_p]
         L.orc_mipmap_lookup.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_void_p]
         L.orc_image_texture_eval_planar.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_void_p]
+        L.orc_radical_inverse.restype = C.c_double
+        L.orc_radical_inverse.argtypes = [u64, u64]
+        L.orc_halton_cap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_halton_samples.argtypes = [C.c_void_p, C.c_int, u32, C.c_void_p, C.c_void_p]
         L.orc_noise.restype = f32
         L.orc_noise.argtypes = [f32, f32, f32]
         L.orc_fbm.restype = f32
@@ -308,6 +312,8 @@ def render(oscene, cfg, want_hits=False, strict_flags=False):
     film = np.zeros((h, w, 4), np.float32)
     rgb = np.zeros((h, w, 3), np.float32)
     spp = cfg.xs * cfg.ys if cfg.sampler_kind == 0 else 1 << max(0, (cfg.xs - 1).bit_length())
+    if cfg.sampler_kind == 2:  # HaltonSampler: padded layout, cap slots per pixel
+        spp = halton_cap(cfg)[0]
     ns = (se[1] - se[0]) * (se[3] - se[2]) * spp
     hit_ids = np.zeros(ns, np.uint32) if want_hits else None
     hit_ts = np.zeros(ns, np.float32) if want_hits else None
@@ -320,6 +326,27 @@ def render(oscene, cfg, want_hits=False, strict_flags=False):
     rc = L.orc_render(oscene.h, C.byref(cfg), _p(film), _p(rgb), _p(hit_ids), _p(hit_ts), C.byref(st))
     _ck(rc)
     return dict(film=film, rgb=rgb, stats=st.as_dict(), hit_ids=hit_ids, hit_ts=hit_ts)
+
+
+def halton_cap(cfg):
+    """(cap, per-pixel counts over the full sampler extent) of a HaltonSampler frame."""
+    lay = layout(cfg)
+    se = lay["sample_ext"]
+    counts = np.zeros((se[3] - se[2], se[1] - se[0]), np.uint32)
+    cap = C.c_uint32(0)
+    _ck(lib().orc_halton_cap(C.byref(cfg), 0, C.byref(cap), _p(counts)))
+    return int(cap.value), counts
+
+
+def halton_samples(cfg, light_pairs=0):
+    """Camera samples of a HaltonSampler frame in the padded layout: (H, W, cap, 5) with NaN image
+    coordinates in unused slots, and the light-sample floats (H, W, cap, 2 * light_pairs)."""
+    cap, counts = halton_cap(cfg)
+    h, w = counts.shape
+    cs = np.zeros((h, w, cap, 5), np.float32)
+    lu = np.zeros((h, w, cap, max(1, 2 * light_pairs)), np.float32)
+    _ck(lib().orc_halton_samples(C.byref(cfg), light_pairs, cap, _p(cs), _p(lu) if light_pairs else None))
+    return cs, lu, counts
 
 
 def camera_samples(cfg, light_pairs, x0, x1, y0, y1, spp):

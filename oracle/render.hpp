@@ -98,11 +98,122 @@ inline RGB sample_radiance(const Scene& sc, const RenderConfig& cfg, const Camer
   return L;
 }
 
+// ---- HaltonSampler renders (sampler kind 2) -------------------------------------------------------
+// The accepted candidates of every task, binned by home pixel.  Layout of everything per-sample
+// (hit ids, the GPU's wavefront buffers): [pixel raster over the full extent][slot], `cap` slots per
+// pixel (cap = the largest count), a pixel's samples in (task, index) order — one task per pixel.
+struct HaltonEntry {
+  uint32_t pixel;  // raster index over the full sampler extent
+  uint32_t slot;
+  uint32_t task;
+  CameraSample cs;
+};
+struct HaltonLayout {
+  std::vector<HaltonEntry> entries;  // task-major, index order within a task
+  std::vector<float> light_u;        // 2 * light_samples floats per entry
+  std::vector<uint32_t> counts;      // per pixel
+  uint32_t cap = 0;
+};
+inline HaltonLayout halton_layout(const SamplerDesc& sd, uint32_t num_tasks, int n_threads) {
+  if (sd.light_samples > ORC_HALTON_MAX_LIGHT_PAIRS) throw std::runtime_error("halton: too many light samples");
+  std::vector<TaskWindow> tw = task_windows(sd, num_tasks);
+  const int full_w = sd.ext[1] - sd.ext[0];
+  const size_t lf = 2 * (size_t)sd.light_samples;
+  std::vector<std::vector<HaltonEntry>> per(num_tasks);
+  std::vector<std::vector<float>> per_lu(num_tasks);
+  std::atomic<uint32_t> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      uint32_t t = next.fetch_add(1);
+      if (t >= num_tasks) break;
+      if (tw[t].empty) continue;
+      HaltonWindow w = halton_window(tw[t].ext, sd.spp());
+      std::vector<float> lu(lf + 1);
+      for (uint64_t i = 0; i < w.wanted; ++i) {
+        HaltonEntry e;
+        if (!halton_candidate(sd, w, i, &e.cs, lu.data())) continue;
+        int px, py;
+        halton_home_pixel(w, e.cs, &px, &py);
+        e.pixel = (uint32_t)((size_t)(py - sd.ext[2]) * (size_t)full_w + (size_t)(px - sd.ext[0]));
+        e.slot = 0;
+        e.task = t;
+        per[t].push_back(e);
+        per_lu[t].insert(per_lu[t].end(), lu.begin(), lu.begin() + lf);
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 0; i < std::max(1, n_threads); ++i) th.emplace_back(worker);
+  for (auto& t : th) t.join();
+  HaltonLayout L;
+  L.counts.assign((size_t)full_w * (size_t)(sd.ext[3] - sd.ext[2]), 0u);
+  for (uint32_t t = 0; t < num_tasks; ++t) {
+    for (HaltonEntry& e : per[t]) {
+      e.slot = L.counts[e.pixel]++;
+      L.cap = std::max(L.cap, e.slot + 1);
+      L.entries.push_back(e);
+    }
+    L.light_u.insert(L.light_u.end(), per_lu[t].begin(), per_lu[t].end());
+  }
+  return L;
+}
+
+inline void render_halton(const Scene& sc, RenderConfig& cfg, RenderStats* stats, uint32_t* hit_ids, float* hit_ts) {
+  const SamplerDesc& sd = cfg.sampler;
+  const int nthreads = std::max(1, cfg.n_threads);
+  HaltonLayout L = halton_layout(sd, cfg.num_tasks, nthreads);
+  const size_t n = L.entries.size(), lf = 2 * (size_t)sd.light_samples;
+  if (hit_ids)
+    for (size_t k = 0; k < L.counts.size() * (size_t)L.cap; ++k) {
+      hit_ids[k] = 0xFFFFFFFFu;
+      if (hit_ts) hit_ts[k] = 0.f;
+    }
+  std::vector<RGB> rad(n);
+  std::vector<RenderStats> tstats((size_t)nthreads);
+  std::atomic<size_t> next{0};
+  auto worker = [&](int tid) {
+    for (;;) {
+      size_t b = next.fetch_add(256);
+      if (b >= n) break;
+      for (size_t k = b; k < std::min(n, b + 256); ++k) {
+        const HaltonEntry& e = L.entries[k];
+        size_t o = (size_t)e.pixel * (size_t)L.cap + e.slot;
+        rad[k] = sample_radiance(sc, cfg, e.cs, L.light_u.data() + lf * k, &tstats[(size_t)tid],
+                                 hit_ids ? hit_ids + o : nullptr, hit_ts ? hit_ts + o : nullptr);
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 0; i < nthreads; ++i) th.emplace_back(worker, i);
+  for (auto& t : th) t.join();
+  for (auto& s : tstats) stats->add(s);
+  if (cfg.mode == 1) {
+    // strict: per-task sub-films, samples in generation order (sampler_renderer.rs:61-144)
+    size_t k = 0;
+    for (uint32_t t = 0; t < cfg.num_tasks; ++t) {
+      if (k >= n || L.entries[k].task != t) continue;
+      Film tf = cfg.film.sub_film(t, cfg.num_tasks);
+      for (; k < n && L.entries[k].task == t; ++k) tf.add_sample(L.entries[k].cs, rad[k].c);
+      cfg.film.add_sub_film(tf);
+    }
+    return;
+  }
+  // default: pixel raster order, a pixel's samples in slot order (the GPU path's contract)
+  std::vector<size_t> order(L.counts.size() * (size_t)L.cap, (size_t)-1);
+  for (size_t k = 0; k < n; ++k) order[(size_t)L.entries[k].pixel * L.cap + L.entries[k].slot] = k;
+  for (size_t o = 0; o < order.size(); ++o)
+    if (order[o] != (size_t)-1) cfg.film.add_sample(L.entries[order[o]].cs, rad[order[o]].c);
+}
+
 // hit_ids / hit_ts (optional): one entry per camera sample, laid out
 // [(y - ext.y0) * width + (x - ext.x0)] * spp + i over the FULL sampler extent.
 inline void render(const Scene& sc, RenderConfig& cfg, RenderStats* stats, uint32_t* hit_ids,
                    float* hit_ts) {
   const SamplerDesc& sd = cfg.sampler;
+  if (sd.kind == 2) {
+    render_halton(sc, cfg, stats, hit_ids, hit_ts);
+    return;
+  }
   const size_t spp = sd.spp();
   const size_t W = sd.words_per_pixel();
   std::vector<TaskWindow> tw = task_windows(sd, cfg.num_tasks);

@@ -118,6 +118,7 @@ SYMBOLS = [
                               C.c_int, P(Stats)]),
     ("pbrtb200_trace_closest", i32, [_vp, _vp, u64, _vp, C.c_int, P(Stats)]),
     ("pbrtb200_trace_any", i32, [_vp, _vp, u64, _vp, C.c_int, P(Stats)]),
+    ("pbrtb200_halton_layout", i32, [_vp, P(Sampler), P(u32), P(u64)]),
     ("pbrtb200_primary_hits", i32, [_vp, P(Camera), P(Sampler), _vp, _vp, _vp, C.c_int, P(Stats)]),
     ("pbh_translate", None, [_fp, _fp, _fp]),
     ("pbh_scale", None, [f32, f32, f32, _fp, _fp]),

@@ -403,9 +403,16 @@ class Sampler:
     def low_discrepancy(x_start, x_end, y_start, y_end, spp, sopen, sclose):
         return Sampler(1, (x_start, x_end, y_start, y_end), spp, 1, True, sopen, sclose)
 
+    @staticmethod
+    def halton(x_start, x_end, y_start, y_end, spp, sopen, sclose):
+        """Sampler::halton (src/sampler/mod.rs:36-40): a variable number of samples per pixel."""
+        return Sampler(2, (x_start, x_end, y_start, y_end), spp, 1, True, sopen, sclose)
+
     def samples_per_pixel(self):
         if self.kind == 0:
             return self.xs * self.ys
+        if self.kind == 2:
+            return self.xs
         p = 1
         while p < self.xs:
             p <<= 1
@@ -619,6 +626,13 @@ class GpuRenderer:
         return _ffi.Sampler(s.kind, s.ext[0], s.ext[1], s.ext[2], s.ext[3], s.xs, s.ys, int(s.jitter),
                             s.sopen, s.sclose, self.num_tasks)
 
+    def halton_layout(self):
+        """(slots per pixel, real samples) of a HaltonSampler frame over the whole sampler extent."""
+        cap, n = C.c_uint32(0), C.c_uint64(0)
+        smp = self.sampler_desc()
+        self.ctx.check(lib().pbrtb200_halton_layout(self.ctx.h, C.byref(smp), C.byref(cap), C.byref(n)))
+        return int(cap.value), int(n.value)
+
     def preprocess(self, scene):
         """Builds/flattens/uploads the scene once (the reference builds its BVH at scene creation)."""
         if self._scene_key is not scene:
@@ -654,7 +668,10 @@ class GpuRenderer:
         """Config-2 hook: per camera sample (raster order over the sampler extent) the closest hit."""
         self.preprocess(scene)
         s = self.sampler
-        n = (s.ext[1] - s.ext[0]) * (s.ext[3] - s.ext[2]) * s.samples_per_pixel()
+        per_pixel = s.samples_per_pixel()
+        if s.kind == 2:  # HaltonSampler: padded layout, `cap` slots per pixel (pbrtb200_halton_layout)
+            per_pixel = self.halton_layout()[0]
+        n = (s.ext[1] - s.ext[0]) * (s.ext[3] - s.ext[2]) * per_pixel
         hits = np.zeros(n, dtype=HIT_DTYPE)
         smp_out = np.zeros((n, 5), np.float32) if want_samples else None
         rays = np.zeros((n, 8), np.float32) if want_rays else None

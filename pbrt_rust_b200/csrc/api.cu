@@ -12,6 +12,7 @@
 #include "film.cuh"
 #include "host_logic.hpp"
 #include "raygen.cuh"
+#include "halton.cuh"
 #include "shade.cuh"
 #include "trace.cuh"
 
@@ -85,6 +86,9 @@ struct pbrtb200_ctx {
       d_tri_n, d_tri_s, d_materials, d_mat_flags, d_textures, d_lights, d_area_tris, d_mipmaps, d_texels;
   std::vector<void*> peer_films;  // pbrtb200_peer_film_create allocations (freed at destroy)
   // per-frame work buffers (grow-only)
+  DevBuf d_halton_tasks, d_hcounts, d_hidx;  // HaltonSampler: task windows, per-pixel counts, slots
+  unsigned long long halton_candidates = 0;
+  uint32_t halton_n_tasks = 0;
   DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_lightu, d_edge, d_rad, d_hits,
       d_sq_rays, d_sq_slots, d_film, d_rects, d_rect_prefix, d_ctrl, d_rays_in, d_occ, d_out_a,
       d_out_b, d_out_c;
@@ -237,6 +241,7 @@ void fill_camera(const pbrtb200_camera* c, int spp, DCamera* out) {
 
 int sampler_spp(const pbrtb200_sampler* s) {
   if (s->kind == PBRTB200_SAMPLER_STRATIFIED) return s->xs * s->ys;
+  if (s->kind == PBRTB200_SAMPLER_HALTON) return s->xs;  // samples_per_pixel as given (halton.rs:18-29)
   int p = 1;
   while (p < s->xs) p <<= 1;  // lds.rs:18 next_power_of_two
   return p;
@@ -244,8 +249,10 @@ int sampler_spp(const pbrtb200_sampler* s) {
 
 int check_sampler(pbrtb200_ctx* ctx, const pbrtb200_sampler* s) {
   if (!s) FAIL(PBRTB200_EINVAL, "sampler is NULL");
-  if (s->kind != PBRTB200_SAMPLER_STRATIFIED && s->kind != PBRTB200_SAMPLER_LD)
+  if (s->kind != PBRTB200_SAMPLER_STRATIFIED && s->kind != PBRTB200_SAMPLER_LD && s->kind != PBRTB200_SAMPLER_HALTON)
     FAIL(PBRTB200_EINVAL, "unsupported sampler kind");
+  if (s->kind == PBRTB200_SAMPLER_HALTON && ctx->sc.area_sample_pairs > PB_HALTON_MAX_LIGHT_PAIRS)
+    FAIL(PBRTB200_EINVAL, "HaltonSampler: more than 16 area-light samples per camera sample");
   if (s->xs < 1 || (s->kind == PBRTB200_SAMPLER_STRATIFIED && s->ys < 1))
     FAIL(PBRTB200_EINVAL, "sampler needs >= 1 sample per pixel");
   if (s->x_end <= s->x_start || s->y_end <= s->y_start)
@@ -385,6 +392,28 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
   if (upload(ctx, ctx->d_pixels, list.data(), list.size())) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_pix_index, index.data(), index.size())) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_task_keys, keys.data(), keys.size())) return PBRTB200_ENODEV;
+  std::vector<DHaltonTask> htasks;
+  if (smp->kind == PBRTB200_SAMPLER_HALTON) {  // HaltonSampler::new per sub-window (halton.rs:18-29, 36-47)
+    unsigned long long first = 0;
+    for (int t = 0; t < smp->num_tasks; ++t) {
+      int32_t w[4];
+      pbh::sampler_sub_window(ext, (uint64_t)t, (uint64_t)smp->num_tasks, w);
+      DHaltonTask ht{};
+      ht.x0 = w[0]; ht.x1 = w[1]; ht.y0 = w[2]; ht.y1 = w[3];
+      ht.first = first;
+      if (w[0] != w[1] && w[2] != w[3]) {
+        const int dx = w[1] - w[0], dy = w[3] - w[2], m = dx > dy ? dx : dy;
+        ht.wanted = (unsigned long long)((long long)m * (long long)m) * (unsigned long long)smp->xs;
+        ht.delta = std::fmax((float)dy, (float)dx);
+        if (ht.wanted > 0xFFFFFFFFull) FAIL(PBRTB200_EINVAL, "HaltonSampler: a task has more than 2^32 candidates");
+      }
+      first += ht.wanted;
+      htasks.push_back(ht);
+    }
+    ctx->halton_candidates = first;
+    ctx->halton_n_tasks = (uint32_t)htasks.size();
+    if (upload(ctx, ctx->d_halton_tasks, htasks.data(), htasks.size())) return PBRTB200_ENODEV;
+  }
   std::vector<uint32_t> prefix(rects.size() / 4 + 1, 0);
   for (size_t r = 0; r < rects.size() / 4; ++r)
     prefix[r + 1] = prefix[r] + (uint32_t)((rects[4 * r + 2] - rects[4 * r]) * (rects[4 * r + 3] - rects[4 * r + 1]));
@@ -922,6 +951,89 @@ static int run_raygen(pbrtb200_ctx* ctx, const DSampler& ds, bool full, uint64_t
   return 0;
 }
 
+// ---- HaltonSampler (halton.cuh): the padded per-sample layout of the current pixel list ----------
+static HaltonArgs halton_args(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t cap) {
+  HaltonArgs a{};
+  a.tasks = ctx->d_halton_tasks.as<DHaltonTask>();
+  a.n_tasks = ctx->halton_n_tasks;
+  a.n_candidates = ctx->halton_candidates;
+  a.pix_index = ctx->d_pix_index.as<int32_t>();
+  a.sx0 = smp->x_start;
+  a.sy0 = smp->y_start;
+  a.sw = smp->x_end - smp->x_start;
+  a.counts = ctx->d_hcounts.as<uint32_t>();
+  a.fill = ctx->d_hcounts.as<uint32_t>() + ctx->n_list_pixels;
+  a.idx = ctx->d_hidx.as<uint32_t>();
+  a.cap = cap;
+  return a;
+}
+// Pass 0: accepted candidates per list pixel -> *cap (the largest count, >= 1) and *total.
+// Synchronises (the caller sizes its buffers from cap).
+static int halton_count(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t* cap, uint64_t* total) {
+  const uint64_t npix = ctx->n_list_pixels;
+  CK(ctx->d_hcounts.ensure((2 * npix + 4) * sizeof(uint32_t)));  // counts, fill, {max, pad, sum64}
+  CK(cudaMemsetAsync(ctx->d_hcounts.p, 0, (2 * npix + 4) * sizeof(uint32_t), ctx->stream));
+  const unsigned long long nc = ctx->halton_candidates;
+  if (nc >= (1ull << 31) * 256ull) FAIL(PBRTB200_EINVAL, "HaltonSampler: too many candidates for one launch");
+  if (nc) {
+    k_halton_bin<0><<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(halton_args(ctx, smp, 0));
+    CK(cudaGetLastError());
+  }
+  uint32_t* st = ctx->d_hcounts.as<uint32_t>() + 2 * npix;
+  k_halton_stats<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(
+      ctx->d_hcounts.as<uint32_t>(), npix, st, reinterpret_cast<unsigned long long*>(st + 2));
+  CK(cudaGetLastError());
+  uint32_t h[4];
+  CK(cudaMemcpyAsync(h, st, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *cap = std::max(1u, h[0]);
+  unsigned long long sum;
+  std::memcpy(&sum, &h[2], 8);
+  *total = sum;
+  return 0;
+}
+// Passes 1 + 2: scatter the candidate indices, sort per pixel, evaluate the camera samples into
+// d_img / d_lens / d_time / d_lightu (npix * cap slots each, sized by the caller).
+static int halton_fill(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t cap, bool full, bool with_film) {
+  const uint64_t npix = ctx->n_list_pixels;
+  CK(ctx->d_hidx.ensure(npix * cap * sizeof(uint32_t)));
+  const unsigned long long nc = ctx->halton_candidates;
+  if (nc) {
+    k_halton_bin<1><<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(halton_args(ctx, smp, cap));
+    CK(cudaGetLastError());
+  }
+  HaltonSampleArgs sa{};
+  sa.tasks = ctx->d_halton_tasks.as<DHaltonTask>();
+  sa.pixels = ctx->d_pixels.as<DPixel>();
+  sa.n_pixels = npix;
+  sa.counts = ctx->d_hcounts.as<uint32_t>();
+  sa.idx = ctx->d_hidx.as<uint32_t>();
+  sa.cap = cap;
+  sa.img = ctx->d_img.as<float2>();
+  sa.lens = full ? ctx->d_lens.as<float2>() : nullptr;
+  sa.time = full ? ctx->d_time.as<float>() : nullptr;
+  sa.light_pairs = with_film ? ctx->sc.area_sample_pairs : 0u;
+  sa.lightu = sa.light_pairs ? ctx->d_lightu.as<float2>() : nullptr;
+  sa.edge = with_film ? ctx->d_edge.as<uint32_t>() : nullptr;
+  sa.sopen = smp->shutter_open;
+  sa.sclose = smp->shutter_close;
+  k_halton_samples<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(sa);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int pbrtb200_halton_layout(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t* cap, uint64_t* n_samples) {
+  if (!ctx) return PBRTB200_EINVAL;
+  if (int rc = check_sampler(ctx, smp)) return rc;
+  if (smp->kind != PBRTB200_SAMPLER_HALTON || !cap) FAIL(PBRTB200_EINVAL, "not a HaltonSampler");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = build_pixel_list(ctx, smp, nullptr, nullptr)) return rc;
+  uint64_t total = 0;
+  if (int rc = halton_count(ctx, smp, cap, &total)) return rc;
+  if (n_samples) *n_samples = total;
+  return PBRTB200_OK;
+}
+
 int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb200_sampler* smp,
                           pbrtb200_hit16* out_hits, float* out_samples, pbrtb200_ray32* out_rays,
                           int is_device, pbrtb200_stats* stats) {
@@ -936,8 +1048,14 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const p
   fill_sampler(ctx, smp, &ds);
   DCamera dc;
   fill_camera(cam, ds.spp, &dc);
-  const uint64_t npix = ctx->n_list_pixels, ns = npix * (uint64_t)ds.spp;
-  const bool full = out_samples != nullptr || cam->lens_radius > 0.0f || smp->kind != PBRTB200_SAMPLER_STRATIFIED;
+  const bool halton = smp->kind == PBRTB200_SAMPLER_HALTON;
+  uint32_t hcap = 0;
+  uint64_t hvalid = 0;
+  if (halton)
+    if (int rc = halton_count(ctx, smp, &hcap, &hvalid)) return rc;
+  const int lay = halton ? (int)hcap : ds.spp;  // slots per list pixel in every per-sample buffer
+  const uint64_t npix = ctx->n_list_pixels, ns = npix * (uint64_t)lay;
+  const bool full = out_samples != nullptr || cam->lens_radius > 0.0f || smp->kind == PBRTB200_SAMPLER_LD;
   CK(ctx->d_img.ensure(ns * sizeof(float2)));
   if (full) {
     CK(ctx->d_lens.ensure(ns * sizeof(float2)));
@@ -946,10 +1064,15 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const p
   CK(ctx->d_hits.ensure(ns * sizeof(pbrtb200_hit16)));
   StageTimer tm{ctx, stats != nullptr};
   size_t e0 = tm.mark();
-  if (int rc = run_raygen(ctx, ds, full, 0, npix, 0, nullptr)) return rc;
+  if (halton) {
+    if (int rc = halton_fill(ctx, smp, hcap, full, false)) return rc;
+  } else if (int rc = run_raygen(ctx, ds, full, 0, npix, 0, nullptr)) {
+    return rc;
+  }
   size_t e1 = tm.mark();
   CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
   TraceArgs a{};
+  a.padded = halton ? 1u : 0u;
   a.img = ctx->d_img.as<float2>();
   a.lens = (full && cam->lens_radius > 0.0f) ? ctx->d_lens.as<float2>() : nullptr;
   a.hits = ctx->d_hits.as<pbrtb200_hit16>();
@@ -982,7 +1105,7 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const p
   }
   if (d_oh || d_os || d_or) {
     k_scatter_raster<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->d_pixels.as<DPixel>(), ns, ds.spp, smp->x_start, smp->y_start, smp->x_end - smp->x_start,
+        ctx->d_pixels.as<DPixel>(), ns, lay, smp->x_start, smp->y_start, smp->x_end - smp->x_start,
         ctx->d_img.as<float2>(), full ? ctx->d_lens.as<float2>() : nullptr,
         full ? ctx->d_time.as<float>() : nullptr, ctx->d_hits.as<pbrtb200_hit16>(), dc, d_oh, d_os, d_or);
     CK(cudaGetLastError());
@@ -1002,7 +1125,7 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const p
   if (stats) {
     float ms[6];
     tm.collect(ms);
-    stats->camera_rays = ns;
+    stats->camera_rays = halton ? hvalid : ns;
     stats->ms_raygen = ms[0];
     stats->ms_trace = ms[1];
     stats->ms_film = ms[4];
@@ -1032,8 +1155,15 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   fill_sampler(ctx, smp, &ds);
   DCamera dc;
   fill_camera(cam, ds.spp, &dc);
-  const uint64_t npix = ctx->n_list_pixels, ns = npix * (uint64_t)ds.spp;
-  const bool full = cam->lens_radius > 0.0f || smp->kind != PBRTB200_SAMPLER_STRATIFIED;
+  // HaltonSampler: a variable number of samples per pixel -> `hcap` padded slots per list pixel
+  const bool halton = smp->kind == PBRTB200_SAMPLER_HALTON;
+  uint32_t hcap = 0;
+  uint64_t hvalid = 0;
+  if (halton)
+    if (int rc = halton_count(ctx, smp, &hcap, &hvalid)) return rc;
+  const int lay = halton ? (int)hcap : ds.spp;  // slots per list pixel in every per-sample buffer
+  const uint64_t npix = ctx->n_list_pixels, ns = npix * (uint64_t)lay;
+  const bool full = cam->lens_radius > 0.0f || smp->kind == PBRTB200_SAMPLER_LD;
   const uint32_t slots = std::max(1u, ctx->sc.light_slots);
   const uint32_t le_slot = ctx->sc.area_sample_pairs ? 1u : 0u;
   const uint32_t rad_slots = ctx->sc.n_lights ? ctx->sc.light_slots + le_slot : 0u;
@@ -1045,9 +1175,9 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   while (chunk_cap > (1ull << 20) &&
          chunk_cap * (sizeof(pbrtb200_hit16) + (uint64_t)slots * (sizeof(pbrtb200_ray32) + sizeof(uint32_t))) > kChunkBudgetBytes)
     chunk_cap >>= 1;
-  uint64_t chunk_pix = std::max<uint64_t>(1, chunk_cap / (uint64_t)ds.spp);
+  uint64_t chunk_pix = std::max<uint64_t>(1, chunk_cap / (uint64_t)lay);
   chunk_pix = std::min(chunk_pix, npix);
-  const uint64_t chunk_ns = chunk_pix * (uint64_t)ds.spp;
+  const uint64_t chunk_ns = chunk_pix * (uint64_t)lay;
 
   CK(ctx->d_img.ensure(ns * sizeof(float2)));
   if (full) {
@@ -1093,7 +1223,8 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   df.sx1 = smp->x_end;
   df.sy0 = smp->y_start;
   df.sy1 = smp->y_end;
-  df.spp = ds.spp;
+  df.spp = lay;
+  df.padded = halton ? 1 : 0;
   DFold fd{};
   fd.rad_slots = rad_slots;
   fd.le_slot = le_slot;
@@ -1166,11 +1297,18 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     return r;
   };
 
+  if (halton) {  // candidates land anywhere: every sample of the frame is generated up front
+    size_t h0 = tm.mark();
+    if (int rc = halton_fill(ctx, smp, hcap, full, true)) return rc;
+    tm.span(h0, tm.mark(), 0);
+    launches += 4;  // k_halton_bin<0>, k_halton_stats (halton_count above), k_halton_bin<1>, k_halton_samples
+  }
   for (uint64_t p0 = 0; p0 < npix; p0 += chunk_pix) {
     const uint64_t cp = std::min(chunk_pix, npix - p0);
-    const uint64_t s0 = p0 * (uint64_t)ds.spp, cn = cp * (uint64_t)ds.spp;
+    const uint64_t s0 = p0 * (uint64_t)lay, cn = cp * (uint64_t)lay;
     size_t e0 = tm.mark();
-    if (int rc = run_raygen(ctx, ds, full, p0, cp, s0, film)) return rc;
+    if (!halton)
+      if (int rc = run_raygen(ctx, ds, full, p0, cp, s0, film)) return rc;
     size_t e1 = tm.mark();
     CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(&ctrl(ctx)->sq_count, 0, sizeof(uint32_t), ctx->stream));
@@ -1181,10 +1319,11 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     ta.n = cn;
     ta.counter = &ctrl(ctx)->counter;
     ta.flags = &ctrl(ctx)->flags;
+    ta.padded = halton ? 1u : 0u;
     if (tiles && tiles->n_rects) {  // halo pixels that cannot reach an owned pixel are not traced
       ta.pixels = ctx->d_pixels.as<DPixel>() + p0;
       ta.edge = ctx->d_edge.as<uint32_t>() + p0;
-      ta.spp = (uint32_t)ds.spp;
+      ta.spp = (uint32_t)lay;
     }
     if (int rc = launch_trace_t<false, 1>(ctx, dc, ta)) return rc;
     size_t e2 = tm.mark();
@@ -1268,7 +1407,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   if (stats) {
     float ms[6];
     tm.collect(ms);
-    stats->camera_rays = ns;
+    stats->camera_rays = halton ? hvalid : ns;
     stats->camera_hits = h.hit_total;
     stats->shadow_rays = h.shadow_total;
     stats->ms_raygen = ms[0];

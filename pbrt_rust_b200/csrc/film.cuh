@@ -20,7 +20,8 @@ struct DFilm {
   int x_start, y_start, x_count, y_count;  // film pixel extent
   float xw, yw, inv_xw, inv_yw;
   int sx0, sx1, sy0, sy1;  // sampler extent
-  int spp;
+  int spp;     // slots per list pixel
+  int padded;  // HaltonSampler: a pixel's unused trailing slots carry a NaN image coordinate
 };
 
 #define PB_MAX_FOLD_LIGHTS 64
@@ -121,6 +122,7 @@ k_film(const DFilm f, const DFold fd, const FilmArgs a) {
       const uint64_t base = (uint64_t)li * (uint64_t)f.spp;
       for (int i = 0; i < f.spp; ++i) {
         const float2 im = __ldg(a.img + base + i);
+        if (f.padded && im.x != im.x) break;  // the rest of this pixel's slots are unused
         // film.rs:198-210
         const float dimage_x = im.x - 0.5f, dimage_y = im.y - 0.5f;
         const int x0 = max(f.x_start, f2i_sat(ceilf(dimage_x - f.xw)));

@@ -35,6 +35,8 @@ def _setup(scene, cam2world, fov, xres, yres, xs, ys, jitter, sampler="stratifie
     e = film.get_sample_extent()
     if sampler == "stratified":
         smp = Sampler.stratified(e[0], e[1], e[2], e[3], xs, ys, jitter, 0.0, 0.0)
+    elif sampler == "halton":
+        smp = Sampler.halton(e[0], e[1], e[2], e[3], xs * ys, 0.0, 0.0)
     else:
         smp = Sampler.low_discrepancy(e[0], e[1], e[2], e[3], xs * ys, 0.0, 0.0)
     return dict(scene=scene, camera=cam, film=film, sampler=smp, integrator=SurfaceIntegrator.whitted(max_depth))
