@@ -89,6 +89,11 @@ struct pbrtb200_ctx {
   DevBuf d_halton_tasks, d_hcounts, d_hidx;  // HaltonSampler: task windows, per-pixel counts, slots
   unsigned long long halton_candidates = 0;
   uint32_t halton_n_tasks = 0;
+  // The binning of a HaltonSampler frame is a pure function of the pixel list (no RNG): it is kept
+  // until the list is rebuilt, like the list itself.
+  bool halton_valid = false;   // d_hcounts / d_hidx hold the binned candidate indices of the list
+  uint32_t halton_cap = 0;
+  uint64_t halton_total = 0;
   DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_lightu, d_edge, d_rad, d_hits,
       d_sq_rays, d_sq_slots, d_film, d_rects, d_rect_prefix, d_ctrl, d_rays_in, d_occ, d_out_a,
       d_out_b, d_out_c;
@@ -305,6 +310,7 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
       key.film_ext[1] == fy0 && key.film_ext[2] == fx1 && key.film_ext[3] == fy1)
     return 0;
   key.valid = false;
+  ctx->halton_valid = false;
 
   const int32_t ext[4] = {smp->x_start, smp->x_end, smp->y_start, smp->y_end};
   const int sw = ext[1] - ext[0], sh = ext[3] - ext[2];
@@ -970,6 +976,11 @@ static HaltonArgs halton_args(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, ui
 // Pass 0: accepted candidates per list pixel -> *cap (the largest count, >= 1) and *total.
 // Synchronises (the caller sizes its buffers from cap).
 static int halton_count(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t* cap, uint64_t* total) {
+  if (ctx->halton_valid) {  // same pixel list as the last frame: the binning is still there
+    *cap = ctx->halton_cap;
+    *total = ctx->halton_total;
+    return 0;
+  }
   const uint64_t npix = ctx->n_list_pixels;
   CK(ctx->d_hcounts.ensure((2 * npix + 4) * sizeof(uint32_t)));  // counts, fill, {max, pad, sum64}
   CK(cudaMemsetAsync(ctx->d_hcounts.p, 0, (2 * npix + 4) * sizeof(uint32_t), ctx->stream));
@@ -990,6 +1001,8 @@ static int halton_count(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t
   unsigned long long sum;
   std::memcpy(&sum, &h[2], 8);
   *total = sum;
+  ctx->halton_cap = *cap;
+  ctx->halton_total = sum;
   return 0;
 }
 // Passes 1 + 2: scatter the candidate indices, sort per pixel, evaluate the camera samples into
@@ -998,10 +1011,11 @@ static int halton_fill(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t 
   const uint64_t npix = ctx->n_list_pixels;
   CK(ctx->d_hidx.ensure(npix * cap * sizeof(uint32_t)));
   const unsigned long long nc = ctx->halton_candidates;
-  if (nc) {
+  if (nc && !ctx->halton_valid) {
     k_halton_bin<1><<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(halton_args(ctx, smp, cap));
     CK(cudaGetLastError());
   }
+  ctx->halton_valid = true;  // (k_halton_samples sorts each pixel's slots in place: idempotent)
   HaltonSampleArgs sa{};
   sa.tasks = ctx->d_halton_tasks.as<DHaltonTask>();
   sa.pixels = ctx->d_pixels.as<DPixel>();
@@ -1155,12 +1169,19 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   fill_sampler(ctx, smp, &ds);
   DCamera dc;
   fill_camera(cam, ds.spp, &dc);
+  StageTimer tm{ctx, stats != nullptr};
+  uint32_t launches = 0;
+  size_t eA = tm.mark();
   // HaltonSampler: a variable number of samples per pixel -> `hcap` padded slots per list pixel
   const bool halton = smp->kind == PBRTB200_SAMPLER_HALTON;
   uint32_t hcap = 0;
   uint64_t hvalid = 0;
-  if (halton)
+  if (halton) {
+    const bool cached = ctx->halton_valid;
     if (int rc = halton_count(ctx, smp, &hcap, &hvalid)) return rc;
+    tm.span(eA, tm.mark(), 0);
+    launches += cached ? 0 : 2;  // k_halton_bin<0>, k_halton_stats
+  }
   const int lay = halton ? (int)hcap : ds.spp;  // slots per list pixel in every per-sample buffer
   const uint64_t npix = ctx->n_list_pixels, ns = npix * (uint64_t)lay;
   const bool full = cam->lens_radius > 0.0f || smp->kind == PBRTB200_SAMPLER_LD;
@@ -1201,9 +1222,6 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   CK(cudaMemcpyToSymbolAsync(c_filter_table, film->filter_table, sizeof(float) * 256, 0,
                              cudaMemcpyHostToDevice, ctx->stream));
 
-  StageTimer tm{ctx, stats != nullptr};
-  uint32_t launches = 0;
-  size_t eA = tm.mark();
   CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
   CK(cudaMemsetAsync(ctx->d_edge.p, 0, npix * sizeof(uint32_t), ctx->stream));
   if (tiles && tiles->n_rects && !(tiles->flags & PBRTB200_TILES_KEEP_OTHERS))
@@ -1299,9 +1317,10 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
 
   if (halton) {  // candidates land anywhere: every sample of the frame is generated up front
     size_t h0 = tm.mark();
+    const bool cached = ctx->halton_valid;
     if (int rc = halton_fill(ctx, smp, hcap, full, true)) return rc;
     tm.span(h0, tm.mark(), 0);
-    launches += 4;  // k_halton_bin<0>, k_halton_stats (halton_count above), k_halton_bin<1>, k_halton_samples
+    launches += cached ? 1 : 2;  // (k_halton_bin<1>,) k_halton_samples
   }
   for (uint64_t p0 = 0; p0 < npix; p0 += chunk_pix) {
     const uint64_t cp = std::min(chunk_pix, npix - p0);

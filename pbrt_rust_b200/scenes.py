@@ -412,8 +412,11 @@ def random_scene(seed, ext=False):
     xres, yres = int(rng.integers(20, 72)), int(rng.integers(16, 56))
     use_ld = bool(rng.integers(3) == 0)
     lensr = U(0.02, 0.2) if rng.integers(4) == 0 else 0.0
+    sampler = "ld" if use_ld else "stratified"
+    if ext and rng.integers(3) == 0:  # (drawn in ext mode only: ext=False keeps the round-1 draws)
+        sampler = "halton"
     return _setup(scene, c2w, U(35, 65), xres, yres, int(rng.integers(1, 4)), int(rng.integers(1, 4)), bool(rng.integers(4) != 0),
-                  sampler="ld" if use_ld else "stratified", crop=crop, filt=filt, lensr=lensr, focald=U(6, 12))
+                  sampler=sampler, crop=crop, filt=filt, lensr=lensr, focald=U(6, 12))
 
 
 def config5(nx=5000, nz=5000, xres=1920, yres=1080, xs=16, ys=16, crop=(0, 1, 0, 1)):
