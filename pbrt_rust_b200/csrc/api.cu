@@ -86,7 +86,8 @@ struct pbrtb200_ctx {
       d_tri_n, d_tri_s, d_materials, d_mat_flags, d_textures, d_lights, d_area_tris, d_mipmaps, d_texels;
   std::vector<void*> peer_films;  // pbrtb200_peer_film_create allocations (freed at destroy)
   // per-frame work buffers (grow-only)
-  DevBuf d_halton_tasks, d_hcounts, d_hidx;  // HaltonSampler: task windows, per-pixel counts, slots
+  DevBuf d_halton_tasks, d_hcounts, d_hidx, d_hoffsets;  // HaltonSampler: task windows, per-pixel counts, candidate indices, sample offsets
+  std::vector<uint32_t> h_hoffsets;                      // host copy of the offsets (n_list_pixels + 1)
   unsigned long long halton_candidates = 0;
   uint32_t halton_n_tasks = 0;
   // The binning of a HaltonSampler frame is a pure function of the pixel list (no RNG): it is kept
@@ -969,8 +970,9 @@ static HaltonArgs halton_args(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, ui
   a.sw = smp->x_end - smp->x_start;
   a.counts = ctx->d_hcounts.as<uint32_t>();
   a.fill = ctx->d_hcounts.as<uint32_t>() + ctx->n_list_pixels;
+  a.offsets = ctx->d_hoffsets.as<uint32_t>();
   a.idx = ctx->d_hidx.as<uint32_t>();
-  a.cap = cap;
+  (void)cap;
   return a;
 }
 // Pass 0: accepted candidates per list pixel -> *cap (the largest count, >= 1) and *total.
@@ -982,34 +984,42 @@ static int halton_count(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t
     return 0;
   }
   const uint64_t npix = ctx->n_list_pixels;
-  CK(ctx->d_hcounts.ensure((2 * npix + 4) * sizeof(uint32_t)));  // counts, fill, {max, pad, sum64}
-  CK(cudaMemsetAsync(ctx->d_hcounts.p, 0, (2 * npix + 4) * sizeof(uint32_t), ctx->stream));
+  CK(ctx->d_hcounts.ensure(2 * npix * sizeof(uint32_t)));  // counts, fill
+  CK(cudaMemsetAsync(ctx->d_hcounts.p, 0, 2 * npix * sizeof(uint32_t), ctx->stream));
   const unsigned long long nc = ctx->halton_candidates;
   if (nc >= (1ull << 31) * 256ull) FAIL(PBRTB200_EINVAL, "HaltonSampler: too many candidates for one launch");
   if (nc) {
     k_halton_bin<0><<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(halton_args(ctx, smp, 0));
     CK(cudaGetLastError());
   }
-  uint32_t* st = ctx->d_hcounts.as<uint32_t>() + 2 * npix;
-  k_halton_stats<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(
-      ctx->d_hcounts.as<uint32_t>(), npix, st, reinterpret_cast<unsigned long long*>(st + 2));
-  CK(cudaGetLastError());
-  uint32_t h[4];
-  CK(cudaMemcpyAsync(h, st, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  // exclusive scan of the counts on the host: once per pixel list, like the list itself
+  std::vector<uint32_t> counts(npix);
+  CK(cudaMemcpyAsync(counts.data(), ctx->d_hcounts.p, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  *cap = std::max(1u, h[0]);
-  unsigned long long sum;
-  std::memcpy(&sum, &h[2], 8);
+  ctx->h_hoffsets.assign(npix + 1, 0u);
+  uint32_t mx = 0;
+  uint64_t sum = 0;
+  for (uint64_t i = 0; i < npix; ++i) {
+    ctx->h_hoffsets[i] = (uint32_t)sum;
+    sum += counts[i];
+    mx = std::max(mx, counts[i]);
+  }
+  if (sum >= 0xFFFFFFFFull) FAIL(PBRTB200_EINVAL, "HaltonSampler: more than 2^32 samples; render in tiles");
+  ctx->h_hoffsets[npix] = (uint32_t)sum;
+  if (upload(ctx, ctx->d_hoffsets, ctx->h_hoffsets.data(), ctx->h_hoffsets.size())) return PBRTB200_ENODEV;
+  CK(cudaStreamSynchronize(ctx->stream));
+  *cap = std::max(1u, mx);
   *total = sum;
   ctx->halton_cap = *cap;
   ctx->halton_total = sum;
   return 0;
 }
 // Passes 1 + 2: scatter the candidate indices, sort per pixel, evaluate the camera samples into
-// d_img / d_lens / d_time / d_lightu (npix * cap slots each, sized by the caller).
-static int halton_fill(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t cap, bool full, bool with_film) {
+// d_img / d_lens / d_time / d_lightu (halton_total samples each, sized by the caller).
+static int halton_fill(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t cap, bool full, const pbrtb200_film* film) {
+  const bool with_film = film != nullptr;
   const uint64_t npix = ctx->n_list_pixels;
-  CK(ctx->d_hidx.ensure(npix * cap * sizeof(uint32_t)));
+  CK(ctx->d_hidx.ensure(std::max<uint64_t>(1, ctx->halton_total) * sizeof(uint32_t)));
   const unsigned long long nc = ctx->halton_candidates;
   if (nc && !ctx->halton_valid) {
     k_halton_bin<1><<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(halton_args(ctx, smp, cap));
@@ -1020,15 +1030,16 @@ static int halton_fill(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t 
   sa.tasks = ctx->d_halton_tasks.as<DHaltonTask>();
   sa.pixels = ctx->d_pixels.as<DPixel>();
   sa.n_pixels = npix;
-  sa.counts = ctx->d_hcounts.as<uint32_t>();
+  sa.offsets = ctx->d_hoffsets.as<uint32_t>();
   sa.idx = ctx->d_hidx.as<uint32_t>();
-  sa.cap = cap;
   sa.img = ctx->d_img.as<float2>();
   sa.lens = full ? ctx->d_lens.as<float2>() : nullptr;
   sa.time = full ? ctx->d_time.as<float>() : nullptr;
   sa.light_pairs = with_film ? ctx->sc.area_sample_pairs : 0u;
   sa.lightu = sa.light_pairs ? ctx->d_lightu.as<float2>() : nullptr;
   sa.edge = with_film ? ctx->d_edge.as<uint32_t>() : nullptr;
+  sa.xw = with_film ? film->filter_xw : 0.f;
+  sa.yw = with_film ? film->filter_yw : 0.f;
   sa.sopen = smp->shutter_open;
   sa.sclose = smp->shutter_close;
   k_halton_samples<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(sa);
@@ -1067,26 +1078,26 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const p
   uint64_t hvalid = 0;
   if (halton)
     if (int rc = halton_count(ctx, smp, &hcap, &hvalid)) return rc;
-  const int lay = halton ? (int)hcap : ds.spp;  // slots per list pixel in every per-sample buffer
-  const uint64_t npix = ctx->n_list_pixels, ns = npix * (uint64_t)lay;
+  // HaltonSampler: compact per-sample buffers (hvalid samples), padded raster layout on output
+  const uint64_t npix = ctx->n_list_pixels, ns = halton ? hvalid : npix * (uint64_t)ds.spp;
+  const uint64_t n_out = halton ? npix * (uint64_t)hcap : ns;
   const bool full = out_samples != nullptr || cam->lens_radius > 0.0f || smp->kind == PBRTB200_SAMPLER_LD;
-  CK(ctx->d_img.ensure(ns * sizeof(float2)));
+  CK(ctx->d_img.ensure(std::max<uint64_t>(1, ns) * sizeof(float2)));
   if (full) {
-    CK(ctx->d_lens.ensure(ns * sizeof(float2)));
-    CK(ctx->d_time.ensure(ns * sizeof(float)));
+    CK(ctx->d_lens.ensure(std::max<uint64_t>(1, ns) * sizeof(float2)));
+    CK(ctx->d_time.ensure(std::max<uint64_t>(1, ns) * sizeof(float)));
   }
-  CK(ctx->d_hits.ensure(ns * sizeof(pbrtb200_hit16)));
+  CK(ctx->d_hits.ensure(std::max<uint64_t>(1, ns) * sizeof(pbrtb200_hit16)));
   StageTimer tm{ctx, stats != nullptr};
   size_t e0 = tm.mark();
   if (halton) {
-    if (int rc = halton_fill(ctx, smp, hcap, full, false)) return rc;
+    if (int rc = halton_fill(ctx, smp, hcap, full, nullptr)) return rc;
   } else if (int rc = run_raygen(ctx, ds, full, 0, npix, 0, nullptr)) {
     return rc;
   }
   size_t e1 = tm.mark();
   CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
   TraceArgs a{};
-  a.padded = halton ? 1u : 0u;
   a.img = ctx->d_img.as<float2>();
   a.lens = (full && cam->lens_radius > 0.0f) ? ctx->d_lens.as<float2>() : nullptr;
   a.hits = ctx->d_hits.as<pbrtb200_hit16>();
@@ -1105,21 +1116,27 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const p
     d_or = out_rays;
   } else {
     if (out_hits) {
-      CK(ctx->d_out_a.ensure(ns * sizeof(pbrtb200_hit16)));
+      CK(ctx->d_out_a.ensure(n_out * sizeof(pbrtb200_hit16)));
       d_oh = ctx->d_out_a.as<pbrtb200_hit16>();
     }
     if (out_samples) {
-      CK(ctx->d_out_b.ensure(ns * 5 * sizeof(float)));
+      CK(ctx->d_out_b.ensure(n_out * 5 * sizeof(float)));
       d_os = ctx->d_out_b.as<float>();
     }
     if (out_rays) {
-      CK(ctx->d_out_c.ensure(ns * sizeof(pbrtb200_ray32)));
+      CK(ctx->d_out_c.ensure(n_out * sizeof(pbrtb200_ray32)));
       d_or = ctx->d_out_c.as<pbrtb200_ray32>();
     }
   }
-  if (d_oh || d_os || d_or) {
+  if (halton && (d_oh || d_os || d_or)) {
+    k_scatter_halton<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->d_pixels.as<DPixel>(), npix, hcap, ctx->d_hoffsets.as<uint32_t>(), smp->x_start, smp->y_start,
+        smp->x_end - smp->x_start, ctx->d_img.as<float2>(), full ? ctx->d_lens.as<float2>() : nullptr,
+        full ? ctx->d_time.as<float>() : nullptr, ctx->d_hits.as<pbrtb200_hit16>(), dc, d_oh, d_os, d_or);
+    CK(cudaGetLastError());
+  } else if (d_oh || d_os || d_or) {
     k_scatter_raster<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->d_pixels.as<DPixel>(), ns, lay, smp->x_start, smp->y_start, smp->x_end - smp->x_start,
+        ctx->d_pixels.as<DPixel>(), ns, ds.spp, smp->x_start, smp->y_start, smp->x_end - smp->x_start,
         ctx->d_img.as<float2>(), full ? ctx->d_lens.as<float2>() : nullptr,
         full ? ctx->d_time.as<float>() : nullptr, ctx->d_hits.as<pbrtb200_hit16>(), dc, d_oh, d_os, d_or);
     CK(cudaGetLastError());
@@ -1130,16 +1147,16 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const p
   tm.span(e2, e3, 4);
   tm.span(e0, e3, 5);
   if (!is_device) {
-    if (out_hits) CK(cudaMemcpyAsync(out_hits, d_oh, ns * sizeof(pbrtb200_hit16), cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_samples) CK(cudaMemcpyAsync(out_samples, d_os, ns * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_rays) CK(cudaMemcpyAsync(out_rays, d_or, ns * sizeof(pbrtb200_ray32), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_hits) CK(cudaMemcpyAsync(out_hits, d_oh, n_out * sizeof(pbrtb200_hit16), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_samples) CK(cudaMemcpyAsync(out_samples, d_os, n_out * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_rays) CK(cudaMemcpyAsync(out_rays, d_or, n_out * sizeof(pbrtb200_ray32), cudaMemcpyDeviceToHost, ctx->stream));
   }
   CtrlBlock h;
   if (int rc = finish_flags(ctx, &h)) return rc;
   if (stats) {
     float ms[6];
     tm.collect(ms);
-    stats->camera_rays = halton ? hvalid : ns;
+    stats->camera_rays = ns;
     stats->ms_raygen = ms[0];
     stats->ms_trace = ms[1];
     stats->ms_film = ms[4];
@@ -1172,7 +1189,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   StageTimer tm{ctx, stats != nullptr};
   uint32_t launches = 0;
   size_t eA = tm.mark();
-  // HaltonSampler: a variable number of samples per pixel -> `hcap` padded slots per list pixel
+  // HaltonSampler: a variable number of samples per pixel, addressed through per-pixel offsets
   const bool halton = smp->kind == PBRTB200_SAMPLER_HALTON;
   uint32_t hcap = 0;
   uint64_t hvalid = 0;
@@ -1180,10 +1197,14 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     const bool cached = ctx->halton_valid;
     if (int rc = halton_count(ctx, smp, &hcap, &hvalid)) return rc;
     tm.span(eA, tm.mark(), 0);
-    launches += cached ? 0 : 2;  // k_halton_bin<0>, k_halton_stats
+    launches += cached ? 0 : 1;  // k_halton_bin<0>
   }
-  const int lay = halton ? (int)hcap : ds.spp;  // slots per list pixel in every per-sample buffer
-  const uint64_t npix = ctx->n_list_pixels, ns = npix * (uint64_t)lay;
+  const int lay = halton ? (int)hcap : ds.spp;  // upper bound of the samples of one list pixel
+  const uint64_t npix = ctx->n_list_pixels, ns = halton ? std::max<uint64_t>(1, hvalid) : npix * (uint64_t)ds.spp;
+  // first sample of list pixel p (HaltonSampler: host copy of the offsets; else p * spp)
+  auto first_sample = [&](uint64_t p) -> uint64_t {
+    return halton ? (uint64_t)ctx->h_hoffsets[p] : p * (uint64_t)ds.spp;
+  };
   const bool full = cam->lens_radius > 0.0f || smp->kind == PBRTB200_SAMPLER_LD;
   const uint32_t slots = std::max(1u, ctx->sc.light_slots);
   const uint32_t le_slot = ctx->sc.area_sample_pairs ? 1u : 0u;
@@ -1198,7 +1219,11 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     chunk_cap >>= 1;
   uint64_t chunk_pix = std::max<uint64_t>(1, chunk_cap / (uint64_t)lay);
   chunk_pix = std::min(chunk_pix, npix);
-  const uint64_t chunk_ns = chunk_pix * (uint64_t)lay;
+  uint64_t chunk_ns = chunk_pix * (uint64_t)lay;
+  if (halton && ns <= chunk_cap) {  // the whole frame fits one chunk (lay is only an upper bound per pixel)
+    chunk_pix = npix;
+    chunk_ns = ns;
+  }
 
   CK(ctx->d_img.ensure(ns * sizeof(float2)));
   if (full) {
@@ -1241,8 +1266,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   df.sx1 = smp->x_end;
   df.sy0 = smp->y_start;
   df.sy1 = smp->y_end;
-  df.spp = lay;
-  df.padded = halton ? 1 : 0;
+  df.spp = ds.spp;
   DFold fd{};
   fd.rad_slots = rad_slots;
   fd.le_slot = le_slot;
@@ -1272,6 +1296,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     fa.img = ctx->d_img.as<float2>();
     fa.rad = ctx->d_rad.as<float4>();
     fa.edge = ctx->d_edge.as<uint32_t>();
+    fa.offsets = halton ? ctx->d_hoffsets.as<uint32_t>() : nullptr;
     fa.pix_index = ctx->d_pix_index.as<int32_t>();
     fa.rects = ctx->d_rects.as<int32_t>();
     fa.rect_prefix = ctx->d_rect_prefix.as<uint32_t>();
@@ -1318,13 +1343,21 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   if (halton) {  // candidates land anywhere: every sample of the frame is generated up front
     size_t h0 = tm.mark();
     const bool cached = ctx->halton_valid;
-    if (int rc = halton_fill(ctx, smp, hcap, full, true)) return rc;
+    if (int rc = halton_fill(ctx, smp, hcap, full, film)) return rc;
     tm.span(h0, tm.mark(), 0);
     launches += cached ? 1 : 2;  // (k_halton_bin<1>,) k_halton_samples
   }
   for (uint64_t p0 = 0; p0 < npix; p0 += chunk_pix) {
     const uint64_t cp = std::min(chunk_pix, npix - p0);
-    const uint64_t s0 = p0 * (uint64_t)lay, cn = cp * (uint64_t)lay;
+    const uint64_t s0 = first_sample(p0), cn = first_sample(p0 + cp) - s0;
+    if (cn == 0) {  // (HaltonSampler: a run of pixels without a single sample)
+      if (banded && p0 + cp < npix) {
+        const uint32_t r = rows_final(p0 + cp);
+        if (r > film_done)
+          if (int rc = film_rows(film_done, r)) return rc;
+      }
+      continue;
+    }
     size_t e0 = tm.mark();
     if (!halton)
       if (int rc = run_raygen(ctx, ds, full, p0, cp, s0, film)) return rc;
@@ -1338,11 +1371,10 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     ta.n = cn;
     ta.counter = &ctrl(ctx)->counter;
     ta.flags = &ctrl(ctx)->flags;
-    ta.padded = halton ? 1u : 0u;
-    if (tiles && tiles->n_rects) {  // halo pixels that cannot reach an owned pixel are not traced
+    if (tiles && tiles->n_rects && !halton) {  // halo pixels that cannot reach an owned pixel are not traced
       ta.pixels = ctx->d_pixels.as<DPixel>() + p0;
       ta.edge = ctx->d_edge.as<uint32_t>() + p0;
-      ta.spp = (uint32_t)lay;
+      ta.spp = (uint32_t)ds.spp;
     }
     if (int rc = launch_trace_t<false, 1>(ctx, dc, ta)) return rc;
     size_t e2 = tm.mark();

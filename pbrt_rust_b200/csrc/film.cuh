@@ -20,8 +20,7 @@ struct DFilm {
   int x_start, y_start, x_count, y_count;  // film pixel extent
   float xw, yw, inv_xw, inv_yw;
   int sx0, sx1, sy0, sy1;  // sampler extent
-  int spp;     // slots per list pixel
-  int padded;  // HaltonSampler: a pixel's unused trailing slots carry a NaN image coordinate
+  int spp;
 };
 
 #define PB_MAX_FOLD_LIGHTS 64
@@ -36,6 +35,7 @@ __constant__ float c_filter_table[256];
 struct FilmArgs {
   const float2* __restrict__ img;         // per sample, list order
   const float4* __restrict__ rad;         // per sample x rad_slots radiance terms (rgb)
+  const uint32_t* __restrict__ offsets;   // HaltonSampler: list pixel li owns samples [offsets[li], offsets[li+1]); else NULL (li * spp)
   const uint32_t* __restrict__ edge;      // per list pixel
   const int32_t* __restrict__ pix_index;  // sampler-extent raster -> list position or -1
   const int32_t* __restrict__ rects;      // film pixel rects to fill
@@ -119,10 +119,14 @@ k_film(const DFilm f, const DFold fd, const FilmArgs a) {
       if (li < 0) continue;
       const bool own = (qx == x) && (qy == y);
       if (!own && __ldg(&a.edge[li]) == 0u) continue;  // cannot reach any pixel but its own
-      const uint64_t base = (uint64_t)li * (uint64_t)f.spp;
-      for (int i = 0; i < f.spp; ++i) {
+      uint64_t base = (uint64_t)li * (uint64_t)f.spp;
+      int cnt = f.spp;
+      if (a.offsets) {  // variable samples per pixel (halton.cuh)
+        base = __ldg(&a.offsets[li]);
+        cnt = (int)(__ldg(&a.offsets[li + 1]) - (uint32_t)base);
+      }
+      for (int i = 0; i < cnt; ++i) {
         const float2 im = __ldg(a.img + base + i);
-        if (f.padded && im.x != im.x) break;  // the rest of this pixel's slots are unused
         // film.rs:198-210
         const float dimage_x = im.x - 0.5f, dimage_y = im.y - 0.5f;
         const int x0 = max(f.x_start, f2i_sat(ceilf(dimage_x - f.xw)));

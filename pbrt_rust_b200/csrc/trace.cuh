@@ -349,9 +349,6 @@ struct TraceArgs {
   const DPixel* __restrict__ pixels;   // may be NULL: trace everything
   const uint32_t* __restrict__ edge;
   uint32_t spp;
-  // SRC 1, HaltonSampler frames: per-pixel slots are padded; a NaN image coordinate marks an unused
-  // slot (halton.cuh), which is answered with MISS without tracing.
-  uint32_t padded;
 };
 
 template <bool ANY, bool SPH, bool MULTI, int SRC, int MODE>
@@ -391,10 +388,6 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
           }
         }
         const float2 im = __ldg(a.img + idx);
-        if (a.padded && im.x != im.x) {
-          reinterpret_cast<float4*>(a.hits)[idx] = make_float4(__uint_as_float(PBRTB200_MISS), 0.f, 0.f, 0.f);
-          continue;
-        }
         float2 ln = make_float2(0.f, 0.f);
         if (a.lens) ln = __ldg(a.lens + idx);
         camera_ray(cam, im.x, im.y, ln.x, ln.y, &o, &d, nullptr);
