@@ -117,6 +117,8 @@ keep = {"k_raygen_groups": "k_raygen_groups", "k_raygen_full": "k_raygen_full",
         "_Z7k_shadeILi8ELb0ELb0EE": "k_shade", "_Z7k_shadeILi8ELb1ELb0EE": "k_shade_image_textures",
         "_Z7k_shadeILi6ELb1ELb1EE": "k_shade_ext", "_Z12tex_eval_extILi3EE": "k_shade_ext_tex_eval_level3",
         "_Z12tex_eval_extILi0EE": "k_shade_ext_tex_eval_level0", "_Z6noise_fff": "k_shade_ext_noise",
+        "k_halton_binILi0": "k_halton_bin_count", "k_halton_binILi1": "k_halton_bin_scatter",
+        "k_halton_samples": "k_halton_samples",
         "_Z6k_film5DFilm": "k_film", "k_film_develop": "k_film_develop", "k_area_tri_setup": "k_area_tri_setup", "k_scatter_raster": "k_scatter_raster",
         "_Z7k_traceILb0ELb0ELb1ELi1ELi1EE": "k_trace_closest_tri_multi_camera_whilewhile",
         "_Z7k_traceILb1ELb0ELb1ELi0ELi2EE": "k_trace_any_tri_multi_queue_ifif_unordered",
