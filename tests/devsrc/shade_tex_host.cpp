@@ -42,3 +42,17 @@ float devsrc_fbm(int turb, const float* p, const float* dpdx, const float* dpdy,
               omega, octaves);
 }
 }
+
+// ---- HaltonSampler arithmetic (pbrt_rust_b200/csrc/halton_math.cuh) -------------------------------
+#include "../../pbrt_rust_b200/csrc/halton_math.cuh"
+extern "C" {
+double devsrc_radical_inverse(unsigned long long n, unsigned int b) { return radical_inverse_(n, b); }
+// win4 = x0, x1, y0, y1 of the task window; returns 1 and the image position when the candidate is kept
+int devsrc_halton_image(const int* win4, float delta, unsigned long long i, float* out2) {
+  DHaltonTask t{};
+  t.x0 = win4[0]; t.x1 = win4[1]; t.y0 = win4[2]; t.y1 = win4[3];
+  t.delta = delta;
+  return halton_image(t, i, &out2[0], &out2[1]) ? 1 : 0;
+}
+unsigned int devsrc_halton_prime(int k) { return pb_halton_primes[k]; }
+}

@@ -21,7 +21,7 @@ from pbrt_rust_b200.api import HostScene, Material, Primitive, Scene, Shape, Tex
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "devsrc", "shade_tex_host.cpp")
 LIB = os.path.join(HERE, "devsrc", "libdevsrc.so")
-DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "dmath.cuh")] + \
+DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "dmath.cuh", "halton_math.cuh")] + \
     [os.path.join(HERE, "..", "include", "pbrtb200.h")]
 
 
@@ -37,6 +37,10 @@ def dev():
     L.devsrc_fbm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
     L.devsrc_tex_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.devsrc_bump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.devsrc_radical_inverse.restype = C.c_double
+    L.devsrc_radical_inverse.argtypes = [C.c_uint64, C.c_uint32]
+    L.devsrc_halton_image.argtypes = [C.c_void_p, C.c_float, C.c_uint64, C.c_void_p]
+    L.devsrc_halton_prime.restype = C.c_uint32
     return L
 
 
@@ -188,3 +192,42 @@ def test_flat_texture_table_layout():
         pb.api.SphericalMapping2D(Transform(m, m))
     with pytest.raises(pb.api.PbrtError):  # f32::clamp(0.0, max) panics for max < 0 (noise.rs:116)
         HostScene(_scene_of([Material.matte(Texture.fbm(-1, 0.5), b)]))
+
+
+def test_device_halton_arithmetic_matches_the_oracle(dev, orc):
+    """radical_inverse_ and halton_image of csrc/halton_math.cuh against the oracle's HaltonSampler
+    (sampler/halton.rs:57-76, montecarlo.rs:7-20): f64 radical inverses bit for bit, and for whole
+    task windows the same accepted candidates with the same image positions."""
+    L = orc.lib()
+    rng = np.random.default_rng(5)
+    primes = [dev.devsrc_halton_prime(k) for k in range(40)]
+    assert primes[:8] == [2, 3, 5, 7, 11, 13, 17, 19] and all(all(p % q for q in range(2, int(p ** 0.5) + 1)) for p in primes)
+    for _ in range(20000):
+        n, b = int(rng.integers(0, 2 ** 40)), primes[int(rng.integers(0, 40))]
+        assert dev.devsrc_radical_inverse(n, b) == L.orc_radical_inverse(n, b)
+    from pbrt_rust_b200 import scenes
+    cfg = scenes.config1(xres=37, yres=23, sampler="halton")
+    c = orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0)
+    cs, _, counts = orc.halton_samples(c)
+    lay = orc.layout(c)
+    se, nt = lay["sample_ext"], lay["num_tasks"]
+    ext = np.array(se, np.int32)
+    seen = np.zeros_like(counts)
+    out = np.zeros(2, np.float32)
+    for t in range(nt):
+        win = np.zeros(4, np.int32)
+        L.orc_compute_sub_window(_p(ext), t, nt, _p(win))
+        x0, x1, y0, y1 = (int(v) for v in win)
+        if x0 == x1 or y0 == y1:
+            continue
+        dx, dy = x1 - x0, y1 - y0
+        delta = np.float32(max(float(dy), float(dx)))
+        for i in range(max(dx, dy) ** 2 * 4):
+            if not dev.devsrc_halton_image(_p(win), delta, i, _p(out)):
+                continue
+            px = min(max(int(np.floor(out[0])), x0), x1 - 1) - se[0]
+            py = min(max(int(np.floor(out[1])), y0), y1 - 1) - se[2]
+            k = seen[py, px]
+            assert k < counts[py, px] and cs[py, px, k, 0] == out[0] and cs[py, px, k, 1] == out[1]
+            seen[py, px] += 1
+    assert np.array_equal(seen, counts)
