@@ -56,3 +56,30 @@ int devsrc_halton_image(const int* win4, float delta, unsigned long long i, floa
 }
 unsigned int devsrc_halton_prime(int k) { return pb_halton_primes[k]; }
 }
+
+// ---- traversal arithmetic (csrc/trace_math.cuh) and dmath.cuh helpers ------------------------------
+#include "../../pbrt_rust_b200/csrc/trace_math.cuh"
+extern "C" {
+// box6 = bmin, bmax; ray8 = o, mint, d, maxt.  finite != 0: the min/max variant for finite 1/d.
+int devsrc_slab(const float* box6, const float* ray8, int finite, float* t0_out) {
+  const f3 o = mk3(ray8[0], ray8[1], ray8[2]);
+  const f3 inv = mk3(1.f / ray8[4], 1.f / ray8[5], 1.f / ray8[6]);
+  return (finite ? slab_test_finite(box6[0], box6[1], box6[2], box6[3], box6[4], box6[5], o, inv, ray8[3], ray8[7], t0_out)
+                 : slab_test(box6[0], box6[1], box6[2], box6[3], box6[4], box6[5], o, inv, ray8[3], ray8[7], t0_out))
+             ? 1 : 0;
+}
+int devsrc_tri_hit(const float* p9, const float* ray8, float* tbb) {
+  return tri_hit(mk3(p9[0], p9[1], p9[2]), mk3(p9[3], p9[4], p9[5]), mk3(p9[6], p9[7], p9[8]), mk3(ray8[0], ray8[1], ray8[2]),
+                 mk3(ray8[4], ray8[5], ray8[6]), ray8[3], ray8[7], &tbb[0], &tbb[1], &tbb[2]) ? 1 : 0;
+}
+int devsrc_quadratic(float a, float b, float c, float* t01) { return quadratic_(a, b, c, &t01[0], &t01[1]) ? 1 : 0; }
+int devsrc_solve2x2(const float* a4, const float* b2, float* x2) {
+  return solve2x2_(a4[0], a4[1], a4[2], a4[3], b2[0], b2[1], &x2[0], &x2[1]) ? 1 : 0;
+}
+void devsrc_coordinate_system(const float* v3, float* out6) {
+  f3 a, b;
+  coordinate_system_(mk3(v3[0], v3[1], v3[2]), &a, &b);
+  out6[0] = a.x; out6[1] = a.y; out6[2] = a.z; out6[3] = b.x; out6[4] = b.y; out6[5] = b.z;
+}
+void devsrc_chacha12_block(const uint32_t* key8, unsigned long long blk, uint32_t* out16) { chacha12_block(key8, blk, out16); }
+}

@@ -21,7 +21,7 @@ from pbrt_rust_b200.api import HostScene, Material, Primitive, Scene, Shape, Tex
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "devsrc", "shade_tex_host.cpp")
 LIB = os.path.join(HERE, "devsrc", "libdevsrc.so")
-DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "dmath.cuh", "halton_math.cuh")] + \
+DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh")] + \
     [os.path.join(HERE, "..", "include", "pbrtb200.h")]
 
 
@@ -41,6 +41,12 @@ def dev():
     L.devsrc_radical_inverse.argtypes = [C.c_uint64, C.c_uint32]
     L.devsrc_halton_image.argtypes = [C.c_void_p, C.c_float, C.c_uint64, C.c_void_p]
     L.devsrc_halton_prime.restype = C.c_uint32
+    L.devsrc_slab.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.devsrc_tri_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.devsrc_quadratic.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
+    L.devsrc_solve2x2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.devsrc_coordinate_system.argtypes = [C.c_void_p, C.c_void_p]
+    L.devsrc_chacha12_block.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
     return L
 
 
@@ -231,3 +237,106 @@ def test_device_halton_arithmetic_matches_the_oracle(dev, orc):
             assert k < counts[py, px] and cs[py, px, k, 0] == out[0] and cs[py, px, k, 1] == out[1]
             seen[py, px] += 1
     assert np.array_equal(seen, counts)
+
+
+def _edge_rays(rng, n):
+    """rays with zero / tiny / huge / NaN direction components, origins on box planes, empty ranges"""
+    o = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    d = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    k = rng.integers(0, 8, n)
+    for a in range(3):
+        d[(k == 1 + a) | (k == 6), a] = 0.0
+    d[k == 4] *= np.float32(1e-30)
+    d[k == 5] *= np.float32(1e30)
+    d[k == 7, rng.integers(0, 3)] = np.nan
+    m = rng.integers(0, 4, n) == 0
+    o[m] = np.round(o[m])  # on integer planes
+    mint = np.where(rng.integers(0, 4, n) == 0, rng.uniform(0, 4, n), 0.0).astype(np.float32)
+    maxt = np.where(rng.integers(0, 3, n) == 0, rng.uniform(0, 8, n), 3.4028235e38).astype(np.float32)
+    return np.concatenate([o, mint[:, None], d, maxt[:, None]], axis=1).astype(np.float32)
+
+
+def test_device_slab_and_triangle_tests_match_the_oracle(dev, orc):
+    """slab_test / slab_test_finite (bbox.rs:185-209) and tri_hit (mesh.rs:41-72) of
+    csrc/trace_math.cuh against the oracle on random and degenerate inputs: decisions equal, entry
+    distance equal, (t, b1, b2) bit for bit.  The min/max variant is only used when 1/d is finite on every
+    axis (trace_ray), which is where it must equal the reference's swap form."""
+    L = orc.lib()
+    rng = np.random.default_rng(11)
+    rays = np.concatenate([_edge_rays(rng, 6000), _edge_rays(np.random.default_rng(12), 6000)])
+    n_fin = n_hit = n_tri = 0
+    for r in rays:
+        lo = np.round(rng.uniform(-3, 2, 3)) if rng.integers(3) == 0 else rng.uniform(-3, 2, 3)
+        box = np.concatenate([lo, lo + rng.uniform(0, 3, 3) * (rng.integers(0, 5, 3) > 0)]).astype(np.float32)
+        r = r.copy()
+        if rng.integers(2) and np.isfinite(r[4:7]).all() and (r[4:7] != 0).all():  # aim half of the plain rays at the box
+            r[4:7] = ((box[:3] + box[3:]) * 0.5 + rng.uniform(-0.6, 0.6, 3) - r[0:3]).astype(np.float32)
+        t01, t0 = np.zeros(2, np.float32), np.zeros(1, np.float32)
+        want = L.orc_bbox_intersect(_p(box), _p(r), _p(t01))
+        got = dev.devsrc_slab(_p(box), _p(r), 0, _p(t0))
+        assert got == want
+        if want:
+            # (the entry distance only feeds comparisons; max(-0.0, +0.0) may come out with either
+            # sign depending on how fmax is lowered, so compare the value, not the bits)
+            assert t0[0] == t01[0]
+            n_hit += 1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = np.float32(1.0) / r[4:7]
+        if np.isfinite(inv).all():
+            n_fin += 1
+            got = dev.devsrc_slab(_p(box), _p(r), 1, _p(t0))
+            assert got == want
+            if want:
+                assert t0[0] == t01[0]
+        centre = (r[0:3] + r[4:7] * np.float32(rng.uniform(0.2, 2.0))) if rng.integers(2) and np.isfinite(r[4:7]).all() else rng.uniform(-3, 3, 3)
+        p9 = (np.asarray(centre, np.float64)[None, :] + rng.uniform(-1.5, 1.5, (3, 3))).astype(np.float32).reshape(-1)
+        if rng.integers(8) == 0:
+            p9[6:9] = p9[0:3]  # degenerate triangle
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        want = L.orc_tri_intersect(_p(p9), _p(r), _p(a))
+        got = dev.devsrc_tri_hit(_p(p9), _p(r), _p(b))
+        assert got == want
+        if want:
+            n_tri += 1
+            nan = np.isnan(a)
+            assert np.array_equal(np.isnan(b), nan) and np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32))
+    assert n_fin > 3000 and n_hit > 1000 and n_tri > 1000, (n_fin, n_hit, n_tri)
+
+
+def test_device_math_helpers_match_the_oracle(dev, orc):
+    """quadratic_ (utils/mod.rs:56-92), solve2x2_ (:94-110), coordinate_system_ (vector.rs:184-195 as
+    written) and chacha12_block (rand_chacha 0.3 ChaCha12) of csrc/dmath.cuh against the oracle."""
+    L = orc.lib()
+    rng = np.random.default_rng(21)
+    for _ in range(5000):
+        a, b, c = (np.float32(v) for v in rng.uniform(-4, 4, 3))
+        if rng.integers(6) == 0:
+            a = np.float32(0.0)
+        if rng.integers(6) == 0:
+            c = np.float32(b * b / (4 * a)) if a != 0 else c  # discriminant near zero
+        w0, w1, g = np.zeros(1, np.float32), np.zeros(1, np.float32), np.zeros(2, np.float32)
+        want = L.orc_quadratic(a, b, c, _p(w0), _p(w1))
+        got = dev.devsrc_quadratic(a, b, c, _p(g))
+        assert got == want
+        if want:
+            assert g.view(np.uint32).tolist() == [w0.view(np.uint32)[0], w1.view(np.uint32)[0]]
+        a4, b2 = rng.uniform(-2, 2, 4).astype(np.float32), rng.uniform(-2, 2, 2).astype(np.float32)
+        if rng.integers(5) == 0:
+            a4[2:] = a4[:2] * np.float32(2.0)  # singular
+        xw, xg = np.zeros(2, np.float32), np.zeros(2, np.float32)
+        want = L.orc_solve_2x2(_p(a4), _p(b2), _p(xw))
+        got = dev.devsrc_solve2x2(_p(a4), _p(b2), _p(xg))
+        assert got == want and (not want or np.array_equal(xw.view(np.uint32), xg.view(np.uint32)))
+        v = rng.uniform(-2, 2, 3).astype(np.float32)
+        cw, cg, zero = np.zeros(6, np.float32), np.zeros(6, np.float32), np.zeros(3, np.float32)
+        L.orc_vec_op(4, _p(v), _p(zero), _p(cw))
+        dev.devsrc_coordinate_system(_p(v), _p(cg))
+        assert np.array_equal(cw.view(np.uint32), cg.view(np.uint32))
+    for seed in (0, 1, 12, 255):
+        key = np.zeros(8, np.uint32)
+        L.orc_seed_from_u64(C.c_uint64(seed), _p(key))
+        for blk in (0, 1, 7, 2 ** 32 + 5):
+            want, got = np.zeros(16, np.uint32), np.zeros(16, np.uint32)
+            L.orc_stream_words(_p(key), C.c_uint64(16 * blk), C.c_uint64(16), _p(want))
+            dev.devsrc_chacha12_block(_p(key), blk, _p(got))
+            assert np.array_equal(want, got)
