@@ -506,6 +506,67 @@ int orc_halton_samples(const OrcRenderConfig* c, int light_pairs, uint32_t cap, 
 }
 double orc_radical_inverse(uint64_t n, uint64_t b) { return radical_inverse(n, b); }
 
+// ---- shading-stage hooks (used by the device-source checks, tests/test_device_source.py) --------
+// BSDF::f (bsdf/mod.rs:132-149) for one material evaluated to constants.
+// kind: 0 matte/Lambertian, 1 matte/OrenNayar (sigma in degrees), 2 plastic (Lambertian + Blinn, roughness).
+// frame9 = shading nn, geometric ng, dpdu (BSDF::new_with_eta builds sn, tn from nn and dpdu).
+void orc_bsdf_f(int kind, const float* kd3, const float* ks3, float sigma_or_rough, const float* frame9,
+                const float* wo3, const float* wi3, int strict_flags, float* out3) {
+  DiffGeom dgs;
+  dgs.nn = V3(frame9[0], frame9[1], frame9[2]);
+  dgs.dpdu = V3(frame9[6], frame9[7], frame9[8]);
+  BSDF bsdf(dgs, V3(frame9[3], frame9[4], frame9[5]));
+  BxDF d;
+  d.r = RGB(kd3[0], kd3[1], kd3[2]);
+  if (kind == 1) {  // orennayar.rs:16-29
+    d.kind = 1;
+    float sigma = as_radians(sigma_or_rough);
+    float sigma2 = sigma * sigma;
+    d.a = 1.0f - (sigma2 / (2.0f * (sigma + 0.33f)));
+    d.b = 0.45f * sigma2 / (sigma2 + 0.09f);
+  } else {
+    d.kind = 0;
+  }
+  bsdf.bxdfs[bsdf.n_bxdfs++] = d;
+  if (kind == 2) {
+    BxDF sp;
+    sp.kind = 2;
+    sp.r = RGB(ks3[0], ks3[1], ks3[2]);
+    float e = 1.0f / sigma_or_rough;
+    if (e > 1000.0f || std::isnan(e)) e = 1000.0f;  // microfacet.rs:18-24
+    sp.a = e;
+    bsdf.bxdfs[bsdf.n_bxdfs++] = sp;
+  }
+  RGB f = bsdf.f(V3(wo3[0], wo3[1], wo3[2]), V3(wi3[0], wi3[1], wi3[2]), strict_flags != 0);
+  out3[0] = f.c[0]; out3[1] = f.c[1]; out3[2] = f.c[2];
+}
+float orc_fresnel_dielectric(float cosi, float eta_i, float eta_t) { return BxDF::fresnel_dielectric(cosi, eta_i, eta_t); }
+// DifferentialGeometry::compute_differentials (diff_geom.rs:81-152).  g12 = p, nn, dpdu, dpdv;
+// rd12 = rx_origin, ry_origin, rx_dir, ry_dir; out10 = dpdx, dpdy, dudx, dvdx, dudy, dvdy.
+void orc_compute_differentials(const float* g12, const float* rd12, float* out10) {
+  DiffGeom dg;
+  dg.p = V3(g12[0], g12[1], g12[2]);
+  dg.nn = V3(g12[3], g12[4], g12[5]);
+  dg.dpdu = V3(g12[6], g12[7], g12[8]);
+  dg.dpdv = V3(g12[9], g12[10], g12[11]);
+  RayDifferential rd;
+  rd.has_differentials = true;
+  rd.rx_origin = V3(rd12[0], rd12[1], rd12[2]);
+  rd.ry_origin = V3(rd12[3], rd12[4], rd12[5]);
+  rd.rx_dir = V3(rd12[6], rd12[7], rd12[8]);
+  rd.ry_dir = V3(rd12[9], rd12[10], rd12[11]);
+  dg.compute_differentials(rd);
+  out10[0] = dg.dpdx.x; out10[1] = dg.dpdx.y; out10[2] = dg.dpdx.z;
+  out10[3] = dg.dpdy.x; out10[4] = dg.dpdy.y; out10[5] = dg.dpdy.z;
+  out10[6] = dg.dudx; out10[7] = dg.dvdx; out10[8] = dg.dudy; out10[9] = dg.dvdy;
+}
+// VisibilityTester::segment (visibility_tester.rs:16-24): ray8 = o, mint, d, maxt
+void orc_vis_segment(const float* p1, float eps1, const float* p2, float eps2, float* ray8) {
+  Ray r = vis_segment(V3(p1[0], p1[1], p1[2]), eps1, V3(p2[0], p2[1], p2[2]), eps2, 0.f);
+  ray8[0] = r.o.x; ray8[1] = r.o.y; ray8[2] = r.o.z; ray8[3] = r.mint;
+  ray8[4] = r.d.x; ray8[5] = r.d.y; ray8[6] = r.d.z; ray8[7] = r.maxt;
+}
+
 // ---- small known-answer hooks (each mirrors one reference function) ----
 int orc_quadratic(float a, float b, float c, float* t0, float* t1) {
   return quadratic(a, b, c, t0, t1) ? 1 : 0;

@@ -83,3 +83,65 @@ void devsrc_coordinate_system(const float* v3, float* out6) {
 }
 void devsrc_chacha12_block(const uint32_t* key8, unsigned long long blk, uint32_t* out16) { chacha12_block(key8, blk, out16); }
 }
+
+// ---- shading arithmetic (csrc/shade_math.cuh) ------------------------------------------------------
+#include "../../pbrt_rust_b200/csrc/shade_math.cuh"
+extern "C" {
+// the material -> DBSDF step of k_shade (matte.rs:30-51, plastic.rs:32-55) for constant textures,
+// then BSDF::f.  frame9 = shading nn, geometric ng, dpdu.
+void devsrc_bsdf_f(int kind, const float* kd3, const float* ks3, float sigma_or_rough, const float* frame9,
+                   const float* wo3, const float* wi3, int strict_flags, float* out3) {
+  DBSDF bs;
+  bs.nn = mk3(frame9[0], frame9[1], frame9[2]);
+  bs.ng = mk3(frame9[3], frame9[4], frame9[5]);
+  bs.tn = bs.sn = mk3(0.f, 0.f, 0.f);
+  bs.kd = mk3(kd3[0], kd3[1], kd3[2]);
+  bs.ks = mk3(0.f, 0.f, 0.f);
+  bs.a = bs.b = 0.f;
+  bs.kind = kind;
+  if (kind == 1) {
+    const float sigma = sigma_or_rough * PB_PI / 180.0f;
+    const float sigma2 = sigma * sigma;
+    bs.a = 1.0f - (sigma2 / (2.0f * (sigma + 0.33f)));
+    bs.b = 0.45f * sigma2 / (sigma2 + 0.09f);
+  } else if (kind == 2) {
+    bs.ks = mk3(ks3[0], ks3[1], ks3[2]);
+    float e = 1.0f / sigma_or_rough;
+    if (e > 1000.0f || isnan(e)) e = 1000.0f;
+    bs.a = e;
+  }
+  if (bs.kind != 0) {
+    bs.tn = normalize3(mk3(frame9[6], frame9[7], frame9[8]));
+    bs.sn = cross3(bs.nn, bs.tn);
+  }
+  const f3 f = bsdf_f(bs, mk3(wo3[0], wo3[1], wo3[2]), mk3(wi3[0], wi3[1], wi3[2]), strict_flags != 0);
+  out3[0] = f.x; out3[1] = f.y; out3[2] = f.z;
+}
+float devsrc_fresnel_dielectric(float cosi, float ei, float et) { return fresnel_dielectric_(cosi, ei, et); }
+void devsrc_compute_differentials(const float* g12, const float* rd12, float* out10) {
+  DG g{};
+  g.p = mk3(g12[0], g12[1], g12[2]);
+  g.nn = mk3(g12[3], g12[4], g12[5]);
+  g.dpdu = mk3(g12[6], g12[7], g12[8]);
+  g.dpdv = mk3(g12[9], g12[10], g12[11]);
+  dg_compute_differentials(g, mk3(rd12[0], rd12[1], rd12[2]), mk3(rd12[3], rd12[4], rd12[5]),
+                           mk3(rd12[6], rd12[7], rd12[8]), mk3(rd12[9], rd12[10], rd12[11]));
+  out10[0] = g.dpdx.x; out10[1] = g.dpdx.y; out10[2] = g.dpdx.z;
+  out10[3] = g.dpdy.x; out10[4] = g.dpdy.y; out10[5] = g.dpdy.z;
+  out10[6] = g.dudx; out10[7] = g.dvdx; out10[8] = g.dudy; out10[9] = g.dvdy;
+}
+void devsrc_vis_segment(const float* p1, float eps1, const float* p2, float eps2, float* ray8) {
+  pbrtb200_ray32 r;
+  vis_segment(mk3(p1[0], p1[1], p1[2]), eps1, mk3(p2[0], p2[1], p2[2]), eps2, &r);
+  ray8[0] = r.o[0]; ray8[1] = r.o[1]; ray8[2] = r.o[2]; ray8[3] = r.mint;
+  ray8[4] = r.d[0]; ray8[5] = r.d[1]; ray8[6] = r.d[2]; ray8[7] = r.maxt;
+}
+// dg of a quadric hit: rec = the flattened record, o2w12 = object-to-world rows; out14 = p, nn, u, v, dpdu, dpdv
+void devsrc_quadric_dg(const pbrtb200_sphere80* rec, const float* o2w12, const float* o3, const float* d3, float t_hit,
+                       float phi, float* out14) {
+  const DG g = sphere_dg(*rec, o2w12, mk3(o3[0], o3[1], o3[2]), mk3(d3[0], d3[1], d3[2]), t_hit, phi);
+  const float v[14] = {g.p.x, g.p.y, g.p.z, g.nn.x, g.nn.y, g.nn.z, g.u, g.v, g.dpdu.x, g.dpdu.y, g.dpdu.z,
+                       g.dpdv.x, g.dpdv.y, g.dpdv.z};
+  std::memcpy(out14, v, sizeof v);
+}
+}

@@ -21,7 +21,7 @@ from pbrt_rust_b200.api import HostScene, Material, Primitive, Scene, Shape, Tex
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "devsrc", "shade_tex_host.cpp")
 LIB = os.path.join(HERE, "devsrc", "libdevsrc.so")
-DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh")] + \
+DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "shade_math.cuh")] + \
     [os.path.join(HERE, "..", "include", "pbrtb200.h")]
 
 
@@ -47,6 +47,12 @@ def dev():
     L.devsrc_solve2x2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.devsrc_coordinate_system.argtypes = [C.c_void_p, C.c_void_p]
     L.devsrc_chacha12_block.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.devsrc_bsdf_f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.devsrc_fresnel_dielectric.restype = C.c_float
+    L.devsrc_fresnel_dielectric.argtypes = [C.c_float] * 3
+    L.devsrc_compute_differentials.argtypes = [C.c_void_p] * 3
+    L.devsrc_vis_segment.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
+    L.devsrc_quadric_dg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
     return L
 
 
@@ -340,3 +346,111 @@ def test_device_math_helpers_match_the_oracle(dev, orc):
             L.orc_stream_words(_p(key), C.c_uint64(16 * blk), C.c_uint64(16), _p(want))
             dev.devsrc_chacha12_block(_p(key), blk, _p(got))
             assert np.array_equal(want, got)
+
+
+def _unit(rng):
+    v = rng.normal(size=3)
+    return (v / np.linalg.norm(v)).astype(np.float32)
+
+
+def test_device_bsdf_differentials_and_segments_match_the_oracle(dev, orc):
+    """BSDF::f over Lambertian / Oren-Nayar / plastic (bsdf/*.rs), Fresnel::Dielectric, DifferentialGeometry::
+    compute_differentials (diff_geom.rs:81-152) and VisibilityTester::segment of csrc/shade_math.cuh
+    against the oracle, bit for bit (both sides call the same libm here)."""
+    L = orc.lib()
+    L.orc_fresnel_dielectric.restype = C.c_float
+    L.orc_fresnel_dielectric.argtypes = [C.c_float] * 3
+    L.orc_bsdf_f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_vis_segment.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
+    rng = np.random.default_rng(31)
+    nonblack = 0
+    for _ in range(6000):
+        kind = int(rng.integers(0, 3))
+        kd, ks = rng.uniform(0, 1, 3).astype(np.float32), rng.uniform(0, 1, 3).astype(np.float32)
+        par = np.float32(rng.uniform(0.5, 60.0) if kind == 1 else rng.uniform(0.0005, 0.6))
+        nn = _unit(rng)
+        ng = nn if rng.integers(3) else _unit(rng)
+        dpdu = (np.cross(nn, _unit(rng)) * rng.uniform(0.2, 3.0)).astype(np.float32)
+        frame = np.concatenate([nn, ng, dpdu]).astype(np.float32)
+        wo = _unit(rng)
+        wi = (_unit(rng) * np.float32(rng.uniform(0.5, 8.0) if rng.integers(2) else 1.0)).astype(np.float32)  # point.rs: wi un-normalised
+        if rng.integers(10) == 0:
+            wi = (nn * np.float32(2.0)).astype(np.float32)   # along the normal: sin_theta = 0 paths
+        want, got = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        strict = int(rng.integers(8) == 0)
+        L.orc_bsdf_f(kind, _p(kd), _p(ks), par, _p(frame), _p(wo), _p(wi), strict, _p(want))
+        dev.devsrc_bsdf_f(kind, _p(kd), _p(ks), par, _p(frame), _p(wo), _p(wi), strict, _p(got))
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan) and np.array_equal(want[~nan].view(np.uint32), got[~nan].view(np.uint32)), (kind, want, got)
+        nonblack += bool((want != 0).any())
+        c, ei, et = np.float32(rng.uniform(-1.2, 1.2)), np.float32(rng.uniform(1.0, 2.0)), np.float32(rng.uniform(1.0, 2.0))
+        assert dev.devsrc_fresnel_dielectric(c, ei, et) == L.orc_fresnel_dielectric(c, ei, et)
+        g12 = np.concatenate([rng.uniform(-3, 3, 3), nn, dpdu, np.cross(nn, dpdu) * rng.uniform(0.3, 2.0)]).astype(np.float32)
+        rd12 = np.concatenate([rng.uniform(-5, 5, 6), _unit(rng), _unit(rng)]).astype(np.float32)
+        if rng.integers(10) == 0:
+            rd12[6:9] = np.cross(nn, _unit(rng))   # differential ray parallel to the tangent plane
+        dw, dg_ = np.zeros(10, np.float32), np.zeros(10, np.float32)
+        L.orc_compute_differentials(_p(g12), _p(rd12), _p(dw))
+        dev.devsrc_compute_differentials(_p(g12), _p(rd12), _p(dg_))
+        nan = np.isnan(dw)
+        assert np.array_equal(np.isnan(dg_), nan) and np.array_equal(dw[~nan].view(np.uint32), dg_[~nan].view(np.uint32))
+        p1, p2 = rng.uniform(-5, 5, 3).astype(np.float32), rng.uniform(-5, 5, 3).astype(np.float32)
+        e1, e2 = np.float32(rng.uniform(0, 1e-2)), np.float32(rng.choice([0.0, 1e-3]))
+        rw, rg = np.zeros(8, np.float32), np.zeros(8, np.float32)
+        L.orc_vis_segment(_p(p1), e1, _p(p2), e2, _p(rw))
+        dev.devsrc_vis_segment(_p(p1), e1, _p(p2), e2, _p(rg))
+        assert np.array_equal(rw.view(np.uint32), rg.view(np.uint32))
+    assert nonblack > 2000
+
+
+def test_device_quadric_dg_matches_the_oracle(dev, orc):
+    """The dg of Sphere / Cylinder / Disk hits (sphere.rs:143-180, cylinder.rs:127-154, disk.rs:107-133,
+    helpers.rs:17-43) of csrc/shade_math.cuh, fed with the host mirror's flattened records, against
+    the oracle's Shape::intersect: p, nn, (u, v), dpdu, dpdv bit for bit."""
+    from pbrt_rust_b200.api import Light
+    L = orc.lib()
+    L.orc_quadric_intersect.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(41)
+    U = lambda a, b: float(rng.uniform(a, b))
+    hits = {0: 0, 1: 0, 2: 0}
+    for _ in range(300):
+        t = Transform.translate((U(-2, 2), U(-2, 2), U(-2, 2))) * Transform.rotate_x(U(0, 360)) * Transform.rotate_y(U(0, 360)) \
+            * Transform.scale(U(0.5, 1.5), U(0.5, 1.5), U(0.5, 1.5) * (-1.0 if rng.integers(4) == 0 else 1.0))
+        ro, pm = bool(rng.integers(2)), 360.0 if rng.integers(2) else U(90, 350)
+        shape = int(rng.integers(3))
+        if shape == 0:
+            prm = (U(0.4, 1.2), U(-0.9, -0.2), U(0.2, 0.9))
+            prm = (prm[0], prm[1] * prm[0], prm[2] * prm[0])
+            sh = Shape.sphere(t, t.inverse(), ro, prm[0], prm[1], prm[2], pm)
+        elif shape == 1:
+            prm = (U(0.3, 1.0), U(-1.0, 0.0), U(0.1, 1.0))
+            sh = Shape.cylinder(t, t.inverse(), ro, prm[0], prm[1], prm[2], pm)
+        else:
+            prm = (U(-0.3, 0.3), U(0.6, 1.2), U(0.0, 0.3))
+            sh = Shape.disk(t, t.inverse(), ro, prm[0], prm[1], prm[2], pm)
+        m = Material.matte(Texture.constant(0.5), Texture.constant(0.0))
+        hs = HostScene(Scene.new_with(Primitive.bvh([Primitive.geometric(sh, m)], 1, "sah"), []))
+        f = hs.flat.contents
+        rec = C.cast(f.spheres, C.c_void_p)
+        o2w = C.cast(f.sphere_o2w, C.c_void_p)
+        centre = np.asarray(t.m, np.float32).reshape(4, 4)[:3, 3]
+        for _ in range(12):
+            o = (centre + _unit(rng) * np.float32(U(2.5, 5.0))).astype(np.float32)
+            d = (centre + rng.uniform(-0.5, 0.5, 3) - o).astype(np.float32)
+            ray = np.concatenate([o, [0.0], d, [3.4028235e38]]).astype(np.float32)
+            o3, want, props = np.zeros(3, np.float32), np.zeros(14, np.float32), np.zeros(13, np.float32)
+            m_, mi_ = np.asarray(t.m, np.float32), np.asarray(t.m_inv, np.float32)
+            if shape == 0:
+                ok = L.orc_sphere_intersect(_p(m_), _p(mi_), int(ro), C.c_float(prm[0]), C.c_float(prm[1]), C.c_float(prm[2]),
+                                            C.c_float(pm), _p(ray), _p(o3), _p(want))
+            else:
+                ok = L.orc_quadric_intersect(shape, _p(m_), _p(mi_), int(ro), prm[0], prm[1], prm[2], pm, _p(ray), _p(o3),
+                                             _p(want), _p(props))
+            if not ok:
+                continue
+            got = np.zeros(14, np.float32)
+            dev.devsrc_quadric_dg(rec, o2w, _p(o), _p(d), o3[0], o3[2], _p(got))
+            assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (shape, want, got)
+            hits[shape] += 1
+    assert min(hits.values()) > 100, hits
