@@ -110,45 +110,6 @@ k_raygen_groups(const DSampler smp, const RaygenArgs a) {
   }
 }
 
-// sampler/utils.rs:6-20 (as written: the last bit-reversal step shifts by 2)
-PB_DEV float van_der_corput_(uint32_t n, uint32_t scramble) {
-  n = (n << 16) | (n >> 16);
-  n = ((n & 0x00ff00ffu) << 8) | ((n & 0xff00ff00u) >> 8);
-  n = ((n & 0x0f0f0f0fu) << 4) | ((n & 0xf0f0f0f0u) >> 4);
-  n = ((n & 0x33333333u) << 2) | ((n & 0xCCCCCCCCu) >> 2);
-  n = ((n & 0x55555555u) << 2) | ((n & 0xAAAAAAAAu) >> 2);
-  n ^= scramble;
-  return (float)((double)((n >> 8) & 0xffffffu) / 16777216.0);
-}
-// sampler/utils.rs:22-35
-PB_DEV float sobol2_(uint32_t n, uint32_t scramble) {
-  uint32_t s = scramble, v = 1u << 31;
-  while (n != 0) {
-    if ((n & 1u) == 0) s ^= v;
-    v ^= v >> 1;
-    n >>= 1;
-  }
-  return (float)((double)((s >> 8) & 0xFFFFFFu) / 16777216.0);
-}
-
-// rng.rs:23-33 over `count` groups of DIMS floats stored as float / float2 in global memory
-PB_DEV void shuffle2(WordStream& ws, float2* v, uint32_t count) {
-  for (uint32_t i = 0; i < count; ++i) {
-    const uint32_t other = i + (uint32_t)(ws.random_uint() % (uint64_t)(count - i));
-    const float2 t = v[i];
-    v[i] = v[other];
-    v[other] = t;
-  }
-}
-PB_DEV void shuffle1(WordStream& ws, float* v, uint32_t count) {
-  for (uint32_t i = 0; i < count; ++i) {
-    const uint32_t other = i + (uint32_t)(ws.random_uint() % (uint64_t)(count - i));
-    const float t = v[i];
-    v[i] = v[other];
-    v[other] = t;
-  }
-}
-
 // General path: one thread per pixel runs the pixel's whole sample block, including the lens /
 // time shuffles and the LD sampler; results are built in place in the thread's own slice of the
 // output arrays.  `time` receives lerp(shutter_open, shutter_close, t) (stratified.rs:92-93).

@@ -145,3 +145,21 @@ void devsrc_quadric_dg(const pbrtb200_sphere80* rec, const float* o2w12, const f
   std::memcpy(out14, v, sizeof v);
 }
 }
+
+// ---- sampler helpers of csrc/dmath.cuh: LD radical inverses, the StdRng word stream, RNG::shuffle ----
+extern "C" {
+float devsrc_van_der_corput(uint32_t n, uint32_t scramble) { return van_der_corput_(n, scramble); }
+float devsrc_sobol2(uint32_t n, uint32_t scramble) { return sobol2_(n, scramble); }
+// n floats of RNG::random_float() from the stream keyed by key8, starting at word `start`
+void devsrc_stream_floats(const uint32_t* key8, unsigned long long start, unsigned long long n, float* out) {
+  WordStream ws;
+  ws.init(key8, start);
+  for (unsigned long long i = 0; i < n; ++i) out[i] = ws.random_float();
+}
+// RNG::shuffle (rng.rs:23-33) of `count` groups of dims (1 or 2) floats
+void devsrc_shuffle(const uint32_t* key8, unsigned long long start, float* v, uint32_t count, int dims) {
+  WordStream ws;
+  ws.init(key8, start);
+  if (dims == 2) shuffle2(ws, reinterpret_cast<float2*>(v), count); else shuffle1(ws, v, count);
+}
+}

@@ -53,6 +53,12 @@ def dev():
     L.devsrc_compute_differentials.argtypes = [C.c_void_p] * 3
     L.devsrc_vis_segment.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
     L.devsrc_quadric_dg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    L.devsrc_van_der_corput.restype = C.c_float
+    L.devsrc_van_der_corput.argtypes = [C.c_uint32, C.c_uint32]
+    L.devsrc_sobol2.restype = C.c_float
+    L.devsrc_sobol2.argtypes = [C.c_uint32, C.c_uint32]
+    L.devsrc_stream_floats.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+    L.devsrc_shuffle.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int]
     return L
 
 
@@ -454,3 +460,29 @@ def test_device_quadric_dg_matches_the_oracle(dev, orc):
             assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (shape, want, got)
             hits[shape] += 1
     assert min(hits.values()) > 100, hits
+
+
+def test_device_sampler_helpers_match_the_oracle(dev, orc):
+    """van_der_corput / sobol2 (sampler/utils.rs:6-35, as written), RNG::random_float and RNG::shuffle
+    (rng.rs:15-33) over the ChaCha12 word stream of csrc/dmath.cuh against the oracle."""
+    L = orc.lib()
+    L.orc_van_der_corput.argtypes = [C.c_uint32, C.c_uint32]
+    L.orc_sobol2.argtypes = [C.c_uint32, C.c_uint32]
+    rng = np.random.default_rng(51)
+    for _ in range(20000):
+        n, sc = int(rng.integers(0, 2 ** 32)), int(rng.integers(0, 2 ** 32))
+        assert dev.devsrc_van_der_corput(n, sc) == L.orc_van_der_corput(n, sc)
+        assert dev.devsrc_sobol2(n, sc) == L.orc_sobol2(n, sc)
+    for seed in (0, 3, 12, 4095):
+        key = np.zeros(8, np.uint32)
+        L.orc_seed_from_u64(C.c_uint64(seed), _p(key))
+        want, got = np.zeros(1000, np.float32), np.zeros(1000, np.float32)
+        L.orc_rng_floats(C.c_uint64(seed), C.c_uint64(1000), _p(want))
+        dev.devsrc_stream_floats(_p(key), 0, 1000, _p(got))
+        assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+        for dims, count in ((1, 1), (1, 17), (2, 16), (2, 63)):
+            v = rng.uniform(0, 1, count * dims).astype(np.float32)
+            a, b = v.copy(), v.copy()
+            L.orc_rng_shuffle(C.c_uint64(seed), _p(a), C.c_uint64(count * dims), C.c_uint64(dims))
+            dev.devsrc_shuffle(_p(key), 0, _p(b), count, dims)
+            assert np.array_equal(a, b) and sorted(a.tolist()) == sorted(v.tolist())
