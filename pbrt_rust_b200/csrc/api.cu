@@ -959,7 +959,7 @@ static int run_raygen(pbrtb200_ctx* ctx, const DSampler& ds, bool full, uint64_t
 }
 
 // ---- HaltonSampler (halton.cuh): the padded per-sample layout of the current pixel list ----------
-static HaltonArgs halton_args(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t cap) {
+static HaltonArgs halton_args(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp) {
   HaltonArgs a{};
   a.tasks = ctx->d_halton_tasks.as<DHaltonTask>();
   a.n_tasks = ctx->halton_n_tasks;
@@ -972,7 +972,6 @@ static HaltonArgs halton_args(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, ui
   a.fill = ctx->d_hcounts.as<uint32_t>() + ctx->n_list_pixels;
   a.offsets = ctx->d_hoffsets.as<uint32_t>();
   a.idx = ctx->d_hidx.as<uint32_t>();
-  (void)cap;
   return a;
 }
 // Pass 0: accepted candidates per list pixel -> *cap (the largest count, >= 1) and *total.
@@ -989,7 +988,7 @@ static int halton_count(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t
   const unsigned long long nc = ctx->halton_candidates;
   if (nc >= (1ull << 31) * 256ull) FAIL(PBRTB200_EINVAL, "HaltonSampler: too many candidates for one launch");
   if (nc) {
-    k_halton_bin<0><<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(halton_args(ctx, smp, 0));
+    k_halton_bin<0><<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(halton_args(ctx, smp));
     CK(cudaGetLastError());
   }
   // exclusive scan of the counts on the host: once per pixel list, like the list itself
@@ -1016,13 +1015,13 @@ static int halton_count(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t
 }
 // Passes 1 + 2: scatter the candidate indices, sort per pixel, evaluate the camera samples into
 // d_img / d_lens / d_time / d_lightu (halton_total samples each, sized by the caller).
-static int halton_fill(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, uint32_t cap, bool full, const pbrtb200_film* film) {
+static int halton_fill(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, bool full, const pbrtb200_film* film) {
   const bool with_film = film != nullptr;
   const uint64_t npix = ctx->n_list_pixels;
   CK(ctx->d_hidx.ensure(std::max<uint64_t>(1, ctx->halton_total) * sizeof(uint32_t)));
   const unsigned long long nc = ctx->halton_candidates;
   if (nc && !ctx->halton_valid) {
-    k_halton_bin<1><<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(halton_args(ctx, smp, cap));
+    k_halton_bin<1><<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(halton_args(ctx, smp));
     CK(cudaGetLastError());
   }
   ctx->halton_valid = true;  // (k_halton_samples sorts each pixel's slots in place: idempotent)
@@ -1091,7 +1090,7 @@ int pbrtb200_primary_hits(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const p
   StageTimer tm{ctx, stats != nullptr};
   size_t e0 = tm.mark();
   if (halton) {
-    if (int rc = halton_fill(ctx, smp, hcap, full, nullptr)) return rc;
+    if (int rc = halton_fill(ctx, smp, full, nullptr)) return rc;
   } else if (int rc = run_raygen(ctx, ds, full, 0, npix, 0, nullptr)) {
     return rc;
   }
@@ -1343,7 +1342,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   if (halton) {  // candidates land anywhere: every sample of the frame is generated up front
     size_t h0 = tm.mark();
     const bool cached = ctx->halton_valid;
-    if (int rc = halton_fill(ctx, smp, hcap, full, film)) return rc;
+    if (int rc = halton_fill(ctx, smp, full, film)) return rc;
     tm.span(h0, tm.mark(), 0);
     launches += cached ? 1 : 2;  // (k_halton_bin<1>,) k_halton_samples
   }
