@@ -567,6 +567,20 @@ void orc_vis_segment(const float* p1, float eps1, const float* p2, float eps2, f
   ray8[4] = r.d.x; ray8[5] = r.d.y; ray8[6] = r.d.z; ray8[7] = r.maxt;
 }
 
+// Film::add_sample (film.rs:192-249) of ONE sample with L = (1, 1, 1) into an empty film:
+// out_w = weight_sum per film pixel (pixel extent, row-major).
+int orc_film_add_sample(const OrcRenderConfig* c, float image_x, float image_y, float* out_w) {
+  return guarded([&] {
+    RenderConfig cfg = make_config(nullptr, c);
+    CameraSample cs;
+    cs.image_x = image_x;
+    cs.image_y = image_y;
+    const float rgb[3] = {1.f, 1.f, 1.f};
+    cfg.film.add_sample(cs, rgb);
+    for (size_t i = 0; i < cfg.film.pixels.size(); ++i) out_w[i] = cfg.film.pixels[i].weight_sum;
+  });
+}
+
 // ---- small known-answer hooks (each mirrors one reference function) ----
 int orc_quadratic(float a, float b, float c, float* t0, float* t1) {
   return quadratic(a, b, c, t0, t1) ? 1 : 0;

@@ -8,8 +8,11 @@
 #ifdef PB_HOST_CHECK
 // Host compilation of the device arithmetic for the CPU test-suite (tests/devsrc/): the few CUDA
 // intrinsics used below get plain C++ equivalents.  Never part of the product build.
+#include <algorithm>
 #include <cmath>
 using std::isnan;
+using std::max;
+using std::min;
 #define PB_DEV inline
 struct float4 {
   float x, y, z, w;

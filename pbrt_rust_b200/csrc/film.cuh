@@ -16,19 +16,14 @@
 #pragma once
 #include "scene.cuh"
 
-struct DFilm {
-  int x_start, y_start, x_count, y_count;  // film pixel extent
-  float xw, yw, inv_xw, inv_yw;
-  int sx0, sx1, sy0, sy1;  // sampler extent
-  int spp;
-};
-
 #define PB_MAX_FOLD_LIGHTS 64
 struct DFold {  // how the per-sample radiance terms fold into L (light order)
   uint32_t rad_slots, le_slot, n_lights;
   uint16_t ns[PB_MAX_FOLD_LIGHTS];   // samples of light i (1 for point/spot)
   uint8_t area[PB_MAX_FOLD_LIGHTS];  // 1 = area light (averaged over its samples)
 };
+
+#include "film_math.cuh"  // DFilm, film_sample_index
 
 __constant__ float c_filter_table[256];
 
@@ -127,20 +122,9 @@ k_film(const DFilm f, const DFold fd, const FilmArgs a) {
       }
       for (int i = 0; i < cnt; ++i) {
         const float2 im = __ldg(a.img + base + i);
-        // film.rs:198-210
-        const float dimage_x = im.x - 0.5f, dimage_y = im.y - 0.5f;
-        const int x0 = max(f.x_start, f2i_sat(ceilf(dimage_x - f.xw)));
-        const int x1 = min(f.x_start + f.x_count - 1, f2i_sat(floorf(dimage_x + f.xw)));
-        const int y0 = max(f.y_start, f2i_sat(ceilf(dimage_y - f.yw)));
-        const int y1 = min(f.y_start + f.y_count - 1, f2i_sat(floorf(dimage_y + f.yw)));
-        if ((x1 - x0) < 0 || (y1 - y0) < 0) continue;
-        if (x < x0 || x > x1 || y < y0 || y > y1) continue;
-        // film.rs:216-224
-        const float fx = ((float)x - dimage_x) * f.inv_xw * 16.0f;
-        const float fy = ((float)y - dimage_y) * f.inv_yw * 16.0f;
-        const int ix = min(f2i_sat(floorf(fabsf(fx))), 15);
-        const int iy = min(f2i_sat(floorf(fabsf(fy))), 15);
-        const float wt = c_filter_table[iy * 16 + ix];
+        int ti;
+        if (!film_sample_index(f, im.x, im.y, x, y, &ti)) continue;
+        const float wt = c_filter_table[ti];
         float cx, cy, cz;
         const bool bad = fold_radiance(fd, a.rad + (base + i) * fd.rad_slots, &cx, &cy, &cz);
         if (bad && own) ++nans;

@@ -163,3 +163,26 @@ void devsrc_shuffle(const uint32_t* key8, unsigned long long start, float* v, ui
   if (dims == 2) shuffle2(ws, reinterpret_cast<float2*>(v), count); else shuffle1(ws, v, count);
 }
 }
+
+// ---- Film::add_sample arithmetic (csrc/film_math.cuh) ------------------------------------------------
+#include "../../pbrt_rust_b200/csrc/film_math.cuh"
+extern "C" {
+// weight the sample at (sx, sy) adds to every film pixel (0 where it does not reach): out_w row-major
+void devsrc_film_weights(const pbrtb200_film* film, float sx, float sy, float* out_w) {
+  DFilm f{};
+  f.x_start = film->x_pixel_start;
+  f.y_start = film->y_pixel_start;
+  f.x_count = film->x_pixel_count;
+  f.y_count = film->y_pixel_count;
+  f.xw = film->filter_xw;
+  f.yw = film->filter_yw;
+  f.inv_xw = 1.0f / film->filter_xw;  // filter.rs:12-19
+  f.inv_yw = 1.0f / film->filter_yw;
+  for (int y = 0; y < f.y_count; ++y)
+    for (int x = 0; x < f.x_count; ++x) {
+      int ti;
+      out_w[(size_t)y * f.x_count + x] =
+          film_sample_index(f, sx, sy, f.x_start + x, f.y_start + y, &ti) ? film->filter_table[ti] : 0.0f;
+    }
+}
+}

@@ -21,7 +21,7 @@ from pbrt_rust_b200.api import HostScene, Material, Primitive, Scene, Shape, Tex
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "devsrc", "shade_tex_host.cpp")
 LIB = os.path.join(HERE, "devsrc", "libdevsrc.so")
-DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "shade_math.cuh")] + \
+DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "shade_math.cuh", "film_math.cuh")] + \
     [os.path.join(HERE, "..", "include", "pbrtb200.h")]
 
 
@@ -59,6 +59,7 @@ def dev():
     L.devsrc_sobol2.argtypes = [C.c_uint32, C.c_uint32]
     L.devsrc_stream_floats.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
     L.devsrc_shuffle.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int]
+    L.devsrc_film_weights.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
     return L
 
 
@@ -486,3 +487,38 @@ def test_device_sampler_helpers_match_the_oracle(dev, orc):
             L.orc_rng_shuffle(C.c_uint64(seed), _p(a), C.c_uint64(count * dims), C.c_uint64(dims))
             dev.devsrc_shuffle(_p(key), 0, _p(b), count, dims)
             assert np.array_equal(a, b) and sorted(a.tolist()) == sorted(v.tolist())
+
+
+def test_device_film_arithmetic_matches_the_oracle(dev, orc):
+    """Film::add_sample's extent and filter-table arithmetic (film.rs:192-249) of csrc/film_math.cuh,
+    with the host mirror's film record and table, against the oracle's Film for every filter, crop
+    windows and samples on / outside the film border: the weight every pixel receives, bit for bit."""
+    from pbrt_rust_b200.api import Camera, Film, Filter, Sampler
+    L = orc.lib()
+    L.orc_film_add_sample.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    rng = np.random.default_rng(61)
+    U = lambda a, b: float(rng.uniform(a, b))
+    touched = 0
+    for trial in range(60):
+        filt = [Filter.mean(0.5, 0.5), Filter.mean(U(0.5, 2.5), U(0.5, 2.5)), Filter.triangle(U(1, 2.5), U(1, 2.5)),
+                Filter.gaussian(U(1, 2.5), U(1, 2.5), U(0.5, 2)), Filter.mitchell(2.0, 2.0, 1 / 3, 1 / 3),
+                Filter.lanczos(U(1.5, 3), U(1.5, 3), 3.0)][trial % 6]
+        crop = (0, 1, 0, 1) if trial % 3 else tuple(sorted([U(0, 0.5), U(0.5, 1)]) + sorted([U(0, 0.5), U(0.5, 1)]))
+        xres, yres = int(rng.integers(6, 30)), int(rng.integers(5, 24))
+        film = Film.image(xres, yres, filt, crop)
+        cam = Camera.perspective(Transform.new(), (-1.0, 1.0, -1.0, 1.0), 0.0, 0.0, 0.0, 1e6, 50.0, film)
+        e = film.get_sample_extent()
+        cfg = orc.render_config(cam, Sampler.stratified(e[0], e[1], e[2], e[3], 1, 1, False, 0.0, 0.0), num_cpus=8, mode=0)
+        h, w = film.shape
+        px = film.get_pixel_extent()
+        for _ in range(40):
+            k = int(rng.integers(4))
+            sx = U(e[0] - 1.0, e[1] + 1.0) if k else float(rng.integers(px[0], px[1] + 1)) + (0.5 if rng.integers(2) else 0.0)
+            sy = U(e[2] - 1.0, e[3] + 1.0) if k else float(rng.integers(px[2], px[3] + 1)) + (0.5 if rng.integers(2) else 0.0)
+            want, got = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+            rc = L.orc_film_add_sample(C.byref(cfg), sx, sy, _p(want))
+            assert rc == 0
+            dev.devsrc_film_weights(C.byref(film.desc), sx, sy, _p(got))
+            assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (trial, sx, sy)
+            touched += int((want != 0).sum())
+    assert touched > 5000
