@@ -14,7 +14,7 @@
 // "equal t replaces" tie rule (mesh.rs:71, bvh.rs:401-404) — is identical.
 #pragma once
 #include "scene.cuh"
-#include "trace_math.cuh"  // slab_test, slab_test_finite, tri_hit
+#include "trace_math.cuh"  // slab_test, slab_test_finite, tri_hit, camera_ray
 
 PB_DEV float4 ldg4(const float4* p) { return __ldg(p); }
 
@@ -240,24 +240,6 @@ PB_DEV TraceResult trace_ray(const DScene& sc, f3 o, f3 d, float mint, float max
   if (big < __int_as_float(0x7f800000) && inv.x == inv.x && inv.y == inv.y && inv.z == inv.z)
     return traverse<ANY, SPH, MULTI, true, MODE>(sc, o, d, inv, mint, maxt, s_ref, s_t0);
   return traverse<ANY, SPH, MULTI, false, 0>(sc, o, d, inv, mint, maxt, s_ref, s_t0);
-}
-
-// camera/mod.rs:168-195, 212-271 (Perspective arm), projective.rs:79-97, animated.rs:275-284
-PB_DEV void camera_ray(const DCamera& cam, float ix, float iy, float lu, float lv, f3* o, f3* d,
-                       f3* p_camera_out) {
-  f3 p_camera = xf_pt44(cam.r2c, mk3(ix, iy, 0.0f));
-  f3 ro = mk3(0.f, 0.f, 0.f);
-  f3 rd = normalize3(p_camera);
-  if (cam.lens_radius > 0.0f) {  // handle_dof (concentric_sample_disk is the identity)
-    float u = lu * cam.lens_radius, v = lv * cam.lens_radius;
-    float ft = cam.focal_distance / rd.z;
-    f3 p_focus = ro + (rd * ft);
-    ro = mk3(u, v, 0.0f);
-    rd = normalize3(p_focus - ro);
-  }
-  *o = xf_pt44(cam.c2w, ro);
-  *d = xf_vec(cam.c2w, rd);
-  if (p_camera_out) *p_camera_out = p_camera;
 }
 
 // ---- kernels ---------------------------------------------------------------------------------

@@ -1,9 +1,9 @@
 // Ray / box and ray / triangle arithmetic of the traversal kernels (sm_100a): BBox::intersect
-// (src/bbox.rs:185-209) and Triangle::get_intersection_point (src/shape/mesh.rs:41-72), operation
-// order as written.  Plain arithmetic: the same source compiles as host code (PB_HOST_CHECK,
+// (src/bbox.rs:185-209), Triangle::get_intersection_point (src/shape/mesh.rs:41-72) and the
+// perspective camera ray (src/camera/mod.rs:168-271), operation order as written.  Plain arithmetic: the same source compiles as host code (PB_HOST_CHECK,
 // tests/devsrc/) so the CPU test-suite can run it against the oracle; the product runs it on the GPU.
 #pragma once
-#include "dmath.cuh"
+#include "scene.cuh"  // DCamera (includes dmath.cuh)
 
 // bbox.rs:185-209.  Returns pass/fail and T0 (the entry distance after all three axes).
 PB_DEV bool slab_test(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
@@ -71,3 +71,20 @@ PB_DEV bool slab_test_finite(float bminx, float bminy, float bminz, float bmaxx,
   return !(t0 > t1);
 }
 
+// camera/mod.rs:168-195, 212-271 (Perspective arm), projective.rs:79-97, animated.rs:275-284
+PB_DEV void camera_ray(const DCamera& cam, float ix, float iy, float lu, float lv, f3* o, f3* d,
+                       f3* p_camera_out) {
+  f3 p_camera = xf_pt44(cam.r2c, mk3(ix, iy, 0.0f));
+  f3 ro = mk3(0.f, 0.f, 0.f);
+  f3 rd = normalize3(p_camera);
+  if (cam.lens_radius > 0.0f) {  // handle_dof (concentric_sample_disk is the identity)
+    float u = lu * cam.lens_radius, v = lv * cam.lens_radius;
+    float ft = cam.focal_distance / rd.z;
+    f3 p_focus = ro + (rd * ft);
+    ro = mk3(u, v, 0.0f);
+    rd = normalize3(p_focus - ro);
+  }
+  *o = xf_pt44(cam.c2w, ro);
+  *d = xf_vec(cam.c2w, rd);
+  if (p_camera_out) *p_camera_out = p_camera;
+}

@@ -186,3 +186,26 @@ void devsrc_film_weights(const pbrtb200_film* film, float sx, float sy, float* o
     }
 }
 }
+
+// ---- perspective camera ray (camera_ray, csrc/trace_math.cuh) ----------------------------------------
+extern "C" {
+// cs5 = image_x, image_y, lens_u, lens_v, time -> ray6 = o, d (world space).  The DCamera is filled
+// exactly as api.cu's fill_camera does.
+void devsrc_camera_ray(const pbrtb200_camera* c, int spp, const float* cs5, float* ray6) {
+  DCamera dc;
+  std::memcpy(dc.r2c, c->raster_to_camera, 64);
+  std::memcpy(dc.c2w, c->camera_to_world, 64);
+  for (int i = 0; i < 3; ++i) {
+    dc.dx[i] = c->dx_camera[i];
+    dc.dy[i] = c->dy_camera[i];
+  }
+  dc.sopen = c->shutter_open;
+  dc.sclose = c->shutter_close;
+  dc.lens_radius = c->lens_radius;
+  dc.focal_distance = c->focal_distance;
+  dc.diff_scale = 1.0f / std::sqrt((float)spp);
+  f3 o, d;
+  camera_ray(dc, cs5[0], cs5[1], cs5[2], cs5[3], &o, &d, nullptr);
+  ray6[0] = o.x; ray6[1] = o.y; ray6[2] = o.z; ray6[3] = d.x; ray6[4] = d.y; ray6[5] = d.z;
+}
+}

@@ -60,6 +60,7 @@ def dev():
     L.devsrc_stream_floats.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
     L.devsrc_shuffle.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int]
     L.devsrc_film_weights.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    L.devsrc_camera_ray.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -522,3 +523,27 @@ def test_device_film_arithmetic_matches_the_oracle(dev, orc):
             assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (trial, sx, sy)
             touched += int((want != 0).sum())
     assert touched > 5000
+
+
+@pytest.mark.parametrize("sampler,lensr", [("stratified", 0.0), ("stratified", 0.15), ("ld", 0.05)])
+def test_device_camera_ray_matches_the_oracle(dev, orc, sampler, lensr):
+    """camera_ray of csrc/trace_math.cuh (camera/mod.rs:168-271 incl. depth of field, projective.rs:79-97)
+    fed with the host mirror's camera record, against Camera::generate_ray of the oracle for every
+    camera sample of a small frame: origin and direction bit for bit."""
+    cfg = scenes.config1(xres=24, yres=18, sampler=sampler)
+    cam = cfg["camera"]
+    if lensr:
+        from pbrt_rust_b200.api import Camera
+        cam = Camera.perspective(cam.cam2world, cam.screen_window, 0.0, 0.0, lensr, 7.5, cam.fov, cam.film)
+    ocfg = orc.render_config(cam, cfg["sampler"], num_cpus=8, mode=0)
+    se = orc.layout(ocfg)["sample_ext"]
+    spp = cfg["sampler"].samples_per_pixel()
+    cs, rays, _, _ = orc.camera_samples(ocfg, 0, se[0], se[1], se[2], se[3], spp)
+    assert cs.shape[0] == (se[1] - se[0]) * (se[3] - se[2]) * spp
+    if lensr:
+        assert np.abs(rays[:, 0:3] - rays[0, 0:3]).max() > 1e-3   # origins move over the lens
+    out = np.zeros(6, np.float32)
+    for k in range(cs.shape[0]):
+        dev.devsrc_camera_ray(C.byref(cam.desc), spp, _p(cs[k]), _p(out))
+        assert np.array_equal(out[0:3].view(np.uint32), rays[k, 0:3].view(np.uint32))
+        assert np.array_equal(out[3:6].view(np.uint32), rays[k, 4:7].view(np.uint32))
