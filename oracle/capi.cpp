@@ -567,6 +567,33 @@ void orc_vis_segment(const float* p1, float eps1, const float* p2, float eps2, f
   ray8[4] = r.d.x; ray8[5] = r.d.y; ray8[6] = r.d.z; ray8[7] = r.maxt;
 }
 
+// Triangle::intersect's dg part + get_shading_geometry (mesh.rs:105-193, 220-262) for ONE triangle.
+// P9 = object-space p1, p2, p3 in the order the Triangle holds them (refine-reversed); N9 / S9 / UV6
+// per-vertex normals / tangents / uvs or NULL.  out_dg14 = p, nn, u, v, dpdu, dpdv (geometric);
+// out_dgs17 = nn, dpdu, dpdv, dndu, dndv, u, v (shading).
+int orc_tri_surface(const float* o2w, const float* o2w_inv, int ro, const float* P9, const float* N9,
+                    const float* S9, const float* UV6, const float* ray8, float t, float b1, float b2,
+                    float* out_dg14, float* out_dgs17) {
+  return guarded([&] {
+    Transform xf = xf_from(o2w, o2w_inv);
+    const uint32_t idx[3] = {0, 1, 2};
+    Mesh m(xf, xf.inverse(), ro != 0, idx, 3, P9, 3, N9, S9, UV6);
+    Prim pr;
+    pr.kind = Prim::TRI;
+    pr.mesh = &m;
+    pr.v[0] = 0; pr.v[1] = 1; pr.v[2] = 2;
+    Ray ray(V3(ray8[0], ray8[1], ray8[2]), V3(ray8[4], ray8[5], ray8[6]), ray8[3]);
+    ray.maxt = ray8[7];
+    DiffGeom dg = tri_dg(pr, ray, t, b1, b2);
+    DiffGeom dgs = tri_shading_geometry(pr, dg);
+    const float a[14] = {dg.p.x, dg.p.y, dg.p.z, dg.nn.x, dg.nn.y, dg.nn.z, dg.u, dg.v,
+                         dg.dpdu.x, dg.dpdu.y, dg.dpdu.z, dg.dpdv.x, dg.dpdv.y, dg.dpdv.z};
+    std::memcpy(out_dg14, a, sizeof a);
+    const float b[17] = {dgs.nn.x, dgs.nn.y, dgs.nn.z, dgs.dpdu.x, dgs.dpdu.y, dgs.dpdu.z, dgs.dpdv.x, dgs.dpdv.y, dgs.dpdv.z,
+                         dgs.dndu.x, dgs.dndu.y, dgs.dndu.z, dgs.dndv.x, dgs.dndv.y, dgs.dndv.z, dgs.u, dgs.v};
+    std::memcpy(out_dgs17, b, sizeof b);
+  });
+}
 // Film::add_sample (film.rs:192-249) of ONE sample with L = (1, 1, 1) into an empty film:
 // out_w = weight_sum per film pixel (pixel extent, row-major).
 int orc_film_add_sample(const OrcRenderConfig* c, float image_x, float image_y, float* out_w) {

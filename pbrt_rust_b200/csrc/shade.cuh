@@ -19,11 +19,6 @@
 #include "shade_tex.cuh"  // DG, texture mappings, procedural textures, bump
 #include "shade_math.cuh"  // dg construction + differentials, quadric dg, BxDFs, BSDF::f, shadow segments
 
-struct TriData {
-  f3 p1, p2, p3;
-  uint32_t mesh, attr;
-  float uv[3][2];
-};
 PB_DEV TriData load_tri(const DScene& sc, uint32_t tri) {
   TriData t;
   const float4* tp = sc.tris + 3ull * tri;
@@ -46,85 +41,6 @@ PB_DEV TriData load_tri(const DScene& sc, uint32_t tri) {
     t.uv[2][0] = 1.f; t.uv[2][1] = 1.f;
   }
   return t;
-}
-
-// mesh.rs:220-262
-PB_DEV DG tri_dg(const TriData& t, f3 o, f3 d, float th, float b1, float b2, bool flip) {
-  const float du1 = t.uv[0][0] - t.uv[2][0];
-  const float du2 = t.uv[1][0] - t.uv[2][0];
-  const float dv1 = t.uv[0][1] - t.uv[2][1];
-  const float dv2 = t.uv[1][1] - t.uv[2][1];
-  const f3 dp1 = t.p1 - t.p3, dp2 = t.p2 - t.p3;
-  f3 dpdu, dpdv;
-  const float determinant = du1 * dv2 - dv1 * du2;
-  if (determinant == 0.0f) {
-    coordinate_system_(normalize3(cross3(t.p3 - t.p1, t.p2 - t.p1)), &dpdu, &dpdv);
-  } else {
-    const float inv_det = 1.0f / determinant;
-    dpdu = (dv2 * dp1 - dv1 * dp2) * inv_det;
-    dpdv = (-du2 * dp1 + du1 * dp2) * inv_det;
-  }
-  const float b0 = 1.0f - b1 - b2;
-  const float tu = b0 * t.uv[0][0] + b1 * t.uv[1][0] + b2 * t.uv[2][0];
-  const float tv = b0 * t.uv[0][1] + b1 * t.uv[1][1] + b2 * t.uv[2][1];
-  return dg_new(o + (d * th), dpdu, dpdv, mk3(0, 0, 0), mk3(0, 0, 0), tu, tv, flip);
-}
-
-// mesh.rs:105-193 (as written, including the (ss, ts) tuple binding and the zeroed differentials)
-PB_DEV DG tri_shading_geometry(const DScene& sc, const TriData& t, const pbrtb200_mesh& m,
-                               const DG& dg) {
-  const bool has_n = sc.tri_n && m.has_n, has_s = sc.tri_s && m.has_s;
-  if (!has_n && !has_s) return dg;
-  float b[3];
-  {
-    float x0, x1;
-    if (solve2x2_(t.uv[1][0] - t.uv[0][0], t.uv[2][0] - t.uv[0][0], t.uv[1][1] - t.uv[0][1],
-                  t.uv[2][1] - t.uv[0][1], dg.u - t.uv[0][0], dg.v - t.uv[0][1], &x0, &x1)) {
-      b[0] = 1.0f - x0 - x1;
-      b[1] = x0;
-      b[2] = x1;
-    } else {
-      const float third = 1.f / 3.f;
-      b[0] = b[1] = b[2] = third;
-    }
-  }
-  f3 n0, n1, n2;
-  if (has_n) {
-    const float* q = sc.tri_n + 9ull * t.attr;
-    n0 = mk3(q[0], q[1], q[2]);
-    n1 = mk3(q[3], q[4], q[5]);
-    n2 = mk3(q[6], q[7], q[8]);
-  }
-  f3 ns = has_n ? normalize3(xf_vec(m.o2w, b[0] * n0 + b[1] * n1 + b[2] * n2)) : dg.nn;
-  f3 ss;
-  if (has_s) {
-    const float* q = sc.tri_s + 9ull * t.attr;
-    ss = normalize3(xf_vec(
-        m.o2w, b[0] * mk3(q[0], q[1], q[2]) + b[1] * mk3(q[3], q[4], q[5]) + b[2] * mk3(q[6], q[7], q[8])));
-  } else {
-    ss = normalize3(dg.dpdu);
-  }
-  f3 ts = cross3(ss, ns);
-  if (len2(ts) > 0.f) {
-    ss = normalize3(ts);
-    ts = cross3(ns, ts);
-  } else {
-    coordinate_system_(ns, &ss, &ts);
-  }
-  f3 dndu = mk3(0, 0, 0), dndv = mk3(0, 0, 0);
-  if (has_n) {
-    const float du1 = t.uv[0][0] - t.uv[2][0], du2 = t.uv[1][0] - t.uv[2][0];
-    const float dv1 = t.uv[0][1] - t.uv[2][1], dv2 = t.uv[1][1] - t.uv[2][1];
-    const f3 dn1 = n0 - n2, dn2 = n1 - n2;
-    const float determinant = du1 * dv2 - dv1 * du2;
-    if (determinant != 0.0f) {
-      const float inv_det = 1.0f / determinant;
-      dndu = (dv2 * dn1 - dv1 * dn2) * inv_det;
-      dndv = (-du2 * dn1 + du1 * dn2) * inv_det;
-    }
-  }
-  return dg_new(dg.p, ss, ts, xf_nrm(m.o2w_inv, dndu), xf_nrm(m.o2w_inv, dndv), dg.u, dg.v,
-                m.flip != 0);
 }
 
 // ---- textures ---------------------------------------------------------------------------------

@@ -209,3 +209,34 @@ void devsrc_camera_ray(const pbrtb200_camera* c, int spp, const float* cs5, floa
   ray6[0] = o.x; ray6[1] = o.y; ray6[2] = o.z; ray6[3] = d.x; ray6[4] = d.y; ray6[5] = d.z;
 }
 }
+
+// ---- triangle dg + shading geometry (tri_dg, tri_shading_geometry, csrc/shade_math.cuh) -------------
+extern "C" {
+// pw9 = WORLD-space p1, p2, p3; mesh = the flattened per-mesh record; n9 / s9 / uv6 = the triangle's
+// attribute record (object-space normals / tangents, uvs) or NULL.
+void devsrc_tri_surface(const pbrtb200_mesh* mesh, const float* pw9, const float* n9, const float* s9, const float* uv6,
+                        const float* o3, const float* d3, float t, float b1, float b2, float* out_dg14, float* out_dgs17) {
+  TriData td;
+  td.p1 = mk3(pw9[0], pw9[1], pw9[2]);
+  td.p2 = mk3(pw9[3], pw9[4], pw9[5]);
+  td.p3 = mk3(pw9[6], pw9[7], pw9[8]);
+  td.mesh = 0;
+  td.attr = 0;
+  if (uv6) {
+    for (int k = 0; k < 3; ++k) { td.uv[k][0] = uv6[2 * k]; td.uv[k][1] = uv6[2 * k + 1]; }
+  } else {  // mesh.rs:74-87 default uvs
+    td.uv[0][0] = 0.f; td.uv[0][1] = 0.f; td.uv[1][0] = 1.f; td.uv[1][1] = 0.f; td.uv[2][0] = 1.f; td.uv[2][1] = 1.f;
+  }
+  DScene sc{};
+  sc.tri_n = n9;
+  sc.tri_s = s9;
+  const DG dg = tri_dg(td, mk3(o3[0], o3[1], o3[2]), mk3(d3[0], d3[1], d3[2]), t, b1, b2, mesh->flip != 0);
+  const DG gs = tri_shading_geometry(sc, td, *mesh, dg);
+  const float a[14] = {dg.p.x, dg.p.y, dg.p.z, dg.nn.x, dg.nn.y, dg.nn.z, dg.u, dg.v,
+                       dg.dpdu.x, dg.dpdu.y, dg.dpdu.z, dg.dpdv.x, dg.dpdv.y, dg.dpdv.z};
+  std::memcpy(out_dg14, a, sizeof a);
+  const float b[17] = {gs.nn.x, gs.nn.y, gs.nn.z, gs.dpdu.x, gs.dpdu.y, gs.dpdu.z, gs.dpdv.x, gs.dpdv.y, gs.dpdv.z,
+                       gs.dndu.x, gs.dndu.y, gs.dndu.z, gs.dndv.x, gs.dndv.y, gs.dndv.z, gs.u, gs.v};
+  std::memcpy(out_dgs17, b, sizeof b);
+}
+}

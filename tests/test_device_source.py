@@ -61,6 +61,7 @@ def dev():
     L.devsrc_shuffle.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int]
     L.devsrc_film_weights.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
     L.devsrc_camera_ray.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.devsrc_tri_surface.argtypes = [C.c_void_p] * 7 + [C.c_float] * 3 + [C.c_void_p] * 2
     return L
 
 
@@ -547,3 +548,66 @@ def test_device_camera_ray_matches_the_oracle(dev, orc, sampler, lensr):
         dev.devsrc_camera_ray(C.byref(cam.desc), spp, _p(cs[k]), _p(out))
         assert np.array_equal(out[0:3].view(np.uint32), rays[k, 0:3].view(np.uint32))
         assert np.array_equal(out[3:6].view(np.uint32), rays[k, 4:7].view(np.uint32))
+
+
+def test_device_triangle_surface_matches_the_oracle(dev, orc):
+    """tri_dg and tri_shading_geometry of csrc/shade_math.cuh (mesh.rs:105-193 as written — the (ss, ts)
+    tuple binding, zeroed differentials —, :220-262), fed with the host mirror's flattened triangle,
+    mesh and attribute records, against the oracle's Triangle for meshes with / without normals,
+    tangents and uvs under random (also mirroring) transforms: geometric and shading dg bit for bit."""
+    L = orc.lib()
+    L.orc_tri_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_float] * 3 + [C.c_void_p] * 2
+    rng = np.random.default_rng(71)
+    U = lambda a, b: float(rng.uniform(a, b))
+    done = set()
+    for trial in range(400):
+        t = Transform.translate((U(-2, 2), U(-2, 2), U(-2, 2))) * Transform.rotate_x(U(0, 360)) * Transform.rotate_z(U(0, 360)) \
+            * Transform.scale(U(0.5, 1.5), U(0.5, 1.5), U(0.5, 1.5) * (-1.0 if rng.integers(3) == 0 else 1.0))
+        if rng.integers(4) == 0:
+            t = Transform.new()
+        ro = bool(rng.integers(2))
+        P = rng.uniform(-1, 1, (3, 3)).astype(np.float32)
+        has_n, has_s, has_uv = bool(rng.integers(2)), bool(rng.integers(2)), bool(rng.integers(2))
+        N = (np.cross(P[1] - P[0], P[2] - P[0])[None, :] + rng.uniform(-0.3, 0.3, (3, 3))).astype(np.float32) if has_n else None
+        S = ((P[1] - P[0])[None, :] + rng.uniform(-0.2, 0.2, (3, 3))).astype(np.float32) if has_s else None
+        UV = rng.uniform(0, 1, (3, 2)).astype(np.float32) if has_uv else None
+        if has_uv and rng.integers(6) == 0:
+            UV[2] = UV[0]  # degenerate uv parameterisation -> coordinate_system branch
+        mat = Material.matte(Texture.constant(0.5), Texture.constant(0.0))
+        sh = Shape.triangle_mesh(t, t.inverse(), ro, np.arange(3, dtype=np.uint32), P, N, S, UV)
+        hs = HostScene(Scene.new_with(Primitive.bvh([Primitive.geometric(sh, mat)], 1, "sah"), []))
+        f = hs.flat.contents
+        tri = f.tris[0]
+        pw = np.array([*tri.p1, *tri.p2, *tri.p3], np.float32)
+        attr = int(tri.attr)
+        n9 = np.ctypeslib.as_array(f.tri_n, shape=(f.n_attr * 9,))[9 * attr:9 * attr + 9].copy() if has_n else None
+        s9 = np.ctypeslib.as_array(f.tri_s, shape=(f.n_attr * 9,))[9 * attr:9 * attr + 9].copy() if has_s else None
+        uv6 = np.ctypeslib.as_array(f.tri_uv, shape=(f.n_attr * 6,))[6 * attr:6 * attr + 6].copy() if has_uv else None
+        rev = [2, 1, 0]  # the Triangle holds (P[vi[2]], P[vi[1]], P[vi[0]]) (mesh.rs:329-331)
+        oP = np.ascontiguousarray(P[rev]).reshape(-1)
+        oN = np.ascontiguousarray(N[rev]).reshape(-1) if has_n else None
+        oS = np.ascontiguousarray(S[rev]).reshape(-1) if has_s else None
+        oUV = np.ascontiguousarray(UV[rev]).reshape(-1) if has_uv else None
+        m_, mi_ = np.asarray(t.m, np.float32), np.asarray(t.m_inv, np.float32)
+        mesh_rec = C.byref(f.meshes[0])
+        for _ in range(4):
+            bb = rng.dirichlet([1, 1, 1])
+            hit = bb[0] * pw[0:3] + bb[1] * pw[3:6] + bb[2] * pw[6:9]
+            o = (hit + _unit(rng) * U(1.0, 4.0)).astype(np.float32)
+            d = (hit - o).astype(np.float32) * np.float32(U(0.5, 2.0))
+            ray = np.concatenate([o, [0.0], d, [3.4028235e38]]).astype(np.float32)
+            tbb = np.zeros(3, np.float32)
+            if not L.orc_tri_intersect(_p(pw), _p(ray), _p(tbb)):
+                continue
+            wa, wb, ga, gb = np.zeros(14, np.float32), np.zeros(17, np.float32), np.zeros(14, np.float32), np.zeros(17, np.float32)
+            pn = lambda a: None if a is None else _p(a)
+            rc = L.orc_tri_surface(_p(m_), _p(mi_), int(ro), _p(oP), pn(oN), pn(oS), pn(oUV), _p(ray), tbb[0], tbb[1], tbb[2],
+                                   _p(wa), _p(wb))
+            assert rc == 0
+            dev.devsrc_tri_surface(mesh_rec, _p(pw), pn(n9), pn(s9), pn(uv6), _p(o), _p(d), tbb[0], tbb[1], tbb[2], _p(ga), _p(gb))
+            for want, got in ((wa, ga), (wb, gb)):
+                nan = np.isnan(want)
+                assert np.array_equal(np.isnan(got), nan) and np.array_equal(want[~nan].view(np.uint32), got[~nan].view(np.uint32)), \
+                    (has_n, has_s, has_uv, want, got)
+            done.add((has_n, has_s, has_uv))
+    assert len(done) == 8
