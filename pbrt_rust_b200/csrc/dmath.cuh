@@ -26,6 +26,10 @@ inline int __float2int_rz(float x) {  // cvt.rzi.s32.f32: saturating, NaN -> 0
   if (x <= -2147483648.0f) return INT32_MIN;
   return (int)x;
 }
+template <class T>
+inline T __ldg(const T* p) {  // ld.global.nc
+  return *p;
+}
 inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, int c) {
   c &= 31;
   return c ? (hi << c) | (lo >> (32 - c)) : hi;

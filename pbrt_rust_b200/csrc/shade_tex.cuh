@@ -171,13 +171,11 @@ PB_DEV float fbm_(bool turb, f3 p, f3 dpdx, f3 dpdy, float omega, int max_octave
 // ---- general texture evaluation -----------------------------------------------------------------
 struct TexEnv {
   const pbrtb200_texture* textures;
-  const pbrtb200_mipmap* mipmaps;  // image textures: headers and texel pool (device only)
+  const pbrtb200_mipmap* mipmaps;  // image textures: headers and texel pool
   const float4* texels;
 };
-#ifndef PB_HOST_CHECK
-__device__ __noinline__ f3 mip_lookup(const float4* __restrict__ texels, const pbrtb200_mipmap* __restrict__ mmp,
-                                      float s, float t, float dsdx, float dtdx, float dsdy, float dtdy);
-#endif
+PB_NOINLINE f3 mip_lookup(const float4* __restrict__ texels, const pbrtb200_mipmap* __restrict__ mmp,
+                          float s, float t, float dsdx, float dtdx, float dsdy, float dtdy);  // shade_mip.cuh
 
 // Every texture kind; parents (checkerboard, scale, mix, dots) nest PBRTB200_TEX_MAX_DEPTH deep
 // (validated at upload).  One out-of-line function per level keeps the code size linear in the
@@ -215,10 +213,8 @@ PB_NOINLINE f3 tex_eval_ext(const TexEnv& env, int id, const DG& dg) {
     const f3 tmp2 = v01 * (1.0f - m[0]) + v11 * m[0];
     return tmp1 * (1.0f - m[1]) + tmp2 * m[1];
   }
-#ifndef PB_HOST_CHECK
   if (kind == PBRTB200_TEX_IMAGE)  // imagemap.rs:200-206
     return mip_lookup(env.texels, env.mipmaps + tx.tex1, m[0], m[1], m[2], m[3], m[4], m[5]);
-#endif
   if constexpr (DEPTH > 0) {
     const float s = m[0], t = m[1];
     if (kind == PBRTB200_TEX_DOTS) {  // dots.rs:23-46

@@ -1,9 +1,10 @@
 // TEST INFRASTRUCTURE ONLY.  Compiles the device source pbrt_rust_b200/csrc/shade_tex.cuh as host
 // code (PB_HOST_CHECK: no CUDA, intrinsics replaced by plain C++) so the CPU test-suite can run the
 // very arithmetic the GPU kernel executes against the oracle where no GPU exists.  The product
-// never loads this library; image textures (MIPMap lookups) stay device-only and are not covered.
+// never loads this library.
 #define PB_HOST_CHECK 1
 #include "../../pbrt_rust_b200/csrc/shade_tex.cuh"
+#include "../../pbrt_rust_b200/csrc/shade_mip.cuh"
 
 #include <cstring>
 
@@ -11,6 +12,16 @@ static_assert(sizeof(DG) == 30 * sizeof(float), "DG is 30 packed floats");
 
 extern "C" {
 // dg30 = struct DG: p, nn, u, v, dpdu, dpdv, dndu, dndv, dpdx, dpdy, dudx, dudy, dvdx, dvdy
+void devsrc_tex_eval_img(const pbrtb200_texture* table, const pbrtb200_mipmap* mipmaps, const float* texels, int id,
+                         const float* dg30, float* out3) {
+  DG dg;
+  std::memcpy(&dg, dg30, sizeof dg);
+  TexEnv env{table, mipmaps, reinterpret_cast<const float4*>(texels)};
+  const f3 r = tex_eval_ext<PBRTB200_TEX_MAX_DEPTH>(env, id, dg);
+  out3[0] = r.x;
+  out3[1] = r.y;
+  out3[2] = r.z;
+}
 void devsrc_tex_eval(const pbrtb200_texture* table, int id, const float* dg30, float* out3) {
   DG dg;
   std::memcpy(&dg, dg30, sizeof dg);

@@ -21,7 +21,7 @@ from pbrt_rust_b200.api import HostScene, Material, Primitive, Scene, Shape, Tex
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "devsrc", "shade_tex_host.cpp")
 LIB = os.path.join(HERE, "devsrc", "libdevsrc.so")
-DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "shade_math.cuh", "film_math.cuh")] + \
+DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "shade_mip.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "shade_math.cuh", "film_math.cuh")] + \
     [os.path.join(HERE, "..", "include", "pbrtb200.h")]
 
 
@@ -36,6 +36,7 @@ def dev():
     L.devsrc_fbm.restype = C.c_float
     L.devsrc_fbm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
     L.devsrc_tex_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.devsrc_tex_eval_img.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.devsrc_bump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.devsrc_radical_inverse.restype = C.c_double
     L.devsrc_radical_inverse.argtypes = [C.c_uint64, C.c_uint32]
@@ -611,3 +612,45 @@ def test_device_triangle_surface_matches_the_oracle(dev, orc):
                     (has_n, has_s, has_uv, want, got)
             done.add((has_n, has_s, has_uv))
     assert len(done) == 8
+
+
+def test_device_image_textures_match_the_oracle(dev, orc):
+    """MIPMap::lookup (trilinear and EWA, all three wrap modes, spectrum and float maps; mipmap.rs:
+    112-341) of csrc/shade_mip.cuh over the host mirror's pyramids (MIPMap::new, texel pool layout),
+    reached through the general evaluator, against the oracle's ImageTexture — bit for bit — alone and
+    nested inside checkerboard / mix / scale trees (scenes.TexGen with images)."""
+    from oracle import orc as O
+    from pbrt_rust_b200.api import PlanarMapping2D, UVMapping2D
+    rng = np.random.default_rng(81)
+    img = scenes.procedural_image(37, 23, seed=5)   # not a power of two: resized by MIPMap::new
+    texs = []
+    for tri in (True, False):
+        for wrap in ("repeat", "black", "clamp"):
+            for spectrum in (True, False):
+                mp = UVMapping2D(float(rng.uniform(0.5, 3)), float(rng.uniform(0.5, 3)), float(rng.uniform(0, 1)), float(rng.uniform(0, 1))) \
+                    if rng.integers(2) else PlanarMapping2D(tuple(rng.uniform(-0.5, 0.5, 3)), tuple(rng.uniform(-0.5, 0.5, 3)), 0.1, 0.2)
+                texs.append(Texture.image(mp, img, spectrum=spectrum, do_trilinear=tri, max_aniso=float(rng.choice([2.0, 8.0])),
+                                          wrap=wrap, scale=float(rng.uniform(0.6, 1.0)), gamma=float(rng.uniform(1.0, 2.2))))
+    gen = scenes.TexGen(np.random.default_rng(82), img, ext=True, images=True)
+    nested = [gen.spectrum_tex() for _ in range(80)]
+    texs += nested
+
+    def has_image(t):
+        return t.kind == 3 or any(has_image(c) for c in t.children())
+
+    assert sum(has_image(t) for t in nested) >= 15
+    scene = _scene_of([Material.matte(t, Texture.constant(0.0)) for t in texs])
+    hs, osc = HostScene(scene), O.OracleScene(scene)
+    f = hs.flat.contents
+    assert f.n_mipmaps >= 12
+    table, mips, texels = C.cast(f.textures, C.c_void_p), C.cast(f.mipmaps, C.c_void_p), C.cast(f.texels, C.c_void_p)
+    for t in texs:
+        hid, oid = hs.tex_ids[id(t)], osc.tex_ids[id(t)]
+        for _ in range(30):
+            g = _random_dg(rng)
+            g[20:30] *= np.float32(0.05)   # modest footprints: the EWA ellipse stays a few texels wide
+            got, want, q = np.zeros(3, np.float32), np.zeros(3, np.float32), _dg15(g)
+            dev.devsrc_tex_eval_img(table, mips, texels, hid, _p(g), _p(got))
+            O.lib().orc_texture_eval(osc.h, oid, _p(q), _p(want))
+            nan = np.isnan(want)
+            assert np.array_equal(np.isnan(got), nan) and np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32)), (t.kind, got, want)
