@@ -577,56 +577,13 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   if (s->n_tris && !s->tris) FAIL(PBRTB200_EINVAL, "tris is NULL");
   if (s->n_tris && (!s->meshes || !s->n_meshes)) FAIL(PBRTB200_EINVAL, "triangles need meshes");
 
-  // ---- BVH: reference linear nodes -> 64-byte pair nodes ----
-  const uint32_t nn = s->n_nodes;
-  std::vector<uint32_t> pair_index(nn, 0xFFFFFFFFu);
-  uint32_t n_inner = 0;
-  for (uint32_t i = 0; i < nn; ++i)
-    if (!s->nodes[i].is_leaf) pair_index[i] = n_inner++;
-  std::vector<uint16_t> leaf_count(s->n_prims, 0);
-  bool multi = false, big_leaf = false;
-  uint64_t covered = 0;
-  auto child_ref = [&](uint32_t c, uint32_t* ref) -> bool {
-    if (c >= nn) return false;
-    const pbrtb200_node32& nd = s->nodes[c];
-    if (nd.is_leaf) {
-      if (nd.count == 0 || (uint64_t)nd.offset + nd.count > s->n_prims) return false;
-      *ref = PB_LEAF_BIT | ((std::min<uint32_t>(nd.count, 16u) - 1u) << PB_LEAF_CNT_SHIFT) | nd.offset;
-    } else {
-      *ref = pair_index[c];
-    }
-    return true;
-  };
-  std::vector<float4> pairs(4ull * n_inner);
-  for (uint32_t i = 0; i < nn; ++i) {
-    const pbrtb200_node32& nd = s->nodes[i];
-    if (nd.is_leaf) {
-      if (nd.count == 0 || (uint64_t)nd.offset + nd.count > s->n_prims)
-        FAIL(PBRTB200_EINVAL, "leaf node range outside the primitive list");
-      leaf_count[nd.offset] = nd.count;
-      if (nd.count > 1) multi = true;
-      if (nd.count >= 16) big_leaf = true;
-      covered += nd.count;
-      continue;
-    }
-    if (nd.axis > 2) FAIL(PBRTB200_EINVAL, "inner node axis > 2");
-    uint32_t r0, r1;
-    if (i + 1 >= nn || nd.offset <= i + 1 || !child_ref(i + 1, &r0) || !child_ref(nd.offset, &r1))
-      FAIL(PBRTB200_EINVAL, "inner node child index invalid");
-    const pbrtb200_node32 &c0 = s->nodes[i + 1], &c1 = s->nodes[nd.offset];
-    float4* q = &pairs[4ull * pair_index[i]];
-    q[0] = make_float4(c0.bmin[0], c0.bmin[1], c0.bmin[2], c0.bmax[0]);
-    q[1] = make_float4(c0.bmax[1], c0.bmax[2], c1.bmin[0], c1.bmin[1]);
-    q[2] = make_float4(c1.bmin[2], c1.bmax[0], c1.bmax[1], c1.bmax[2]);
-    float4 m;
-    std::memcpy(&m.x, &r0, 4);
-    std::memcpy(&m.y, &r1, 4);
-    m.z = 0.f;
-    uint32_t ax = nd.axis;
-    std::memcpy(&m.w, &ax, 4);
-    q[3] = m;
-  }
-  if (covered != s->n_prims) FAIL(PBRTB200_EINVAL, "leaves do not cover the primitive list exactly once");
+  // ---- BVH: reference linear nodes -> 64-byte pair nodes (host_logic.hpp) ----
+  pbh::PairNodes pn;
+  if (const char* why = pbh::build_pair_nodes(s->nodes, s->n_nodes, s->n_prims, &pn)) FAIL(PBRTB200_EINVAL, why);
+  static_assert(sizeof(pbh::F4) == sizeof(float4), "pair-node quads are float4");
+  const std::vector<pbh::F4>& pairs = pn.pairs;
+  const std::vector<uint16_t>& leaf_count = pn.leaf_count;
+  const bool multi = pn.multi, big_leaf = pn.big_leaf;
 
   // ---- validation of the shading tables ----
   for (uint32_t i = 0; i < s->n_materials; ++i) {
@@ -727,13 +684,10 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   ctx->shade_ext = force_ext || scene_needs_ext(s);
   sc.n_prims = s->n_prims;
   sc.n_lights = s->n_lights;
-  {
-    const pbrtb200_node32& root = s->nodes[0];
-    sc.root_ref = root.is_leaf ? (PB_LEAF_BIT | ((std::min<uint32_t>(root.count, 16u) - 1u) << PB_LEAF_CNT_SHIFT) | root.offset) : 0u;
-    for (int i = 0; i < 3; ++i) {
-      sc.root_bmin[i] = root.bmin[i];
-      sc.root_bmax[i] = root.bmax[i];
-    }
+  sc.root_ref = pn.root_ref;
+  for (int i = 0; i < 3; ++i) {
+    sc.root_bmin[i] = pn.root_bmin[i];
+    sc.root_bmax[i] = pn.root_bmax[i];
   }
   ctx->has_spheres = need_leaf_prim;
   ctx->multi_leaf = multi;

@@ -10,6 +10,7 @@
 // intrinsics used below get plain C++ equivalents.  Never part of the product build.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 using std::isnan;
 using std::max;
 using std::min;
@@ -26,6 +27,17 @@ inline int __float2int_rz(float x) {  // cvt.rzi.s32.f32: saturating, NaN -> 0
   if (x <= -2147483648.0f) return INT32_MIN;
   return (int)x;
 }
+inline uint32_t __float_as_uint(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
+inline float __uint_as_float(uint32_t u) {
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+inline float __int_as_float(int i) { return __uint_as_float((uint32_t)i); }
 template <class T>
 inline T __ldg(const T* p) {  // ld.global.nc
   return *p;

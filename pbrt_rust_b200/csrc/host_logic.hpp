@@ -4,7 +4,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <vector>
+
+#include "../../include/pbrtb200.h"
+#include "leaf_ref.h"
 
 namespace pbh {
 
@@ -72,6 +76,80 @@ inline void sampler_sub_window(const int32_t ext[4], uint64_t num, uint64_t coun
   out[1] = sat_i32(lerp(psx, pex, t[1]));
   out[2] = sat_i32(lerp(psy, pey, t[2]));
   out[3] = sat_i32(lerp(psy, pey, t[3]));
+}
+
+// ---- BVH: the reference's linear PackedBVHNode array -> 64-byte pair nodes (layout: scene.cuh) ----
+struct F4 {  // layout of CUDA's float4
+  alignas(16) float x;
+  float y, z, w;
+};
+struct PairNodes {
+  std::vector<F4> pairs;             // 4 per inner node
+  std::vector<uint16_t> leaf_count;  // per primitive offset: primitives of the leaf starting there
+  bool multi = false;                // some leaf holds more than one primitive
+  bool big_leaf = false;             // some leaf holds >= 16 (count does not fit the inline field)
+  uint32_t root_ref = 0;
+  float root_bmin[3] = {0.f, 0.f, 0.f}, root_bmax[3] = {0.f, 0.f, 0.f};
+};
+// Returns nullptr on success, else what is wrong with the node array.
+inline const char* build_pair_nodes(const pbrtb200_node32* nodes, uint32_t nn, uint32_t n_prims, PairNodes* out) {
+  std::vector<uint32_t> pair_index(nn, 0xFFFFFFFFu);
+  uint32_t n_inner = 0;
+  for (uint32_t i = 0; i < nn; ++i)
+    if (!nodes[i].is_leaf) pair_index[i] = n_inner++;
+  out->leaf_count.assign(n_prims, 0);
+  out->multi = out->big_leaf = false;
+  uint64_t covered = 0;
+  auto leaf_ref = [](const pbrtb200_node32& nd) {
+    return PB_LEAF_BIT | ((std::min<uint32_t>(nd.count, 16u) - 1u) << PB_LEAF_CNT_SHIFT) | nd.offset;
+  };
+  auto child_ref = [&](uint32_t c, uint32_t* ref) -> bool {
+    if (c >= nn) return false;
+    const pbrtb200_node32& nd = nodes[c];
+    if (nd.is_leaf) {
+      if (nd.count == 0 || (uint64_t)nd.offset + nd.count > n_prims) return false;
+      *ref = leaf_ref(nd);
+    } else {
+      *ref = pair_index[c];
+    }
+    return true;
+  };
+  out->pairs.assign(4ull * n_inner, F4{0.f, 0.f, 0.f, 0.f});
+  for (uint32_t i = 0; i < nn; ++i) {
+    const pbrtb200_node32& nd = nodes[i];
+    if (nd.is_leaf) {
+      if (nd.count == 0 || (uint64_t)nd.offset + nd.count > n_prims)
+        return "leaf node range outside the primitive list";
+      out->leaf_count[nd.offset] = nd.count;
+      if (nd.count > 1) out->multi = true;
+      if (nd.count >= 16) out->big_leaf = true;
+      covered += nd.count;
+      continue;
+    }
+    if (nd.axis > 2) return "inner node axis > 2";
+    uint32_t r0, r1;
+    if (i + 1 >= nn || nd.offset <= i + 1 || !child_ref(i + 1, &r0) || !child_ref(nd.offset, &r1))
+      return "inner node child index invalid";
+    const pbrtb200_node32 &c0 = nodes[i + 1], &c1 = nodes[nd.offset];
+    F4* q = &out->pairs[4ull * pair_index[i]];
+    q[0] = F4{c0.bmin[0], c0.bmin[1], c0.bmin[2], c0.bmax[0]};
+    q[1] = F4{c0.bmax[1], c0.bmax[2], c1.bmin[0], c1.bmin[1]};
+    q[2] = F4{c1.bmin[2], c1.bmax[0], c1.bmax[1], c1.bmax[2]};
+    F4 m{0.f, 0.f, 0.f, 0.f};
+    std::memcpy(&m.x, &r0, 4);
+    std::memcpy(&m.y, &r1, 4);
+    const uint32_t ax = nd.axis;
+    std::memcpy(&m.w, &ax, 4);
+    q[3] = m;
+  }
+  if (covered != n_prims) return "leaves do not cover the primitive list exactly once";
+  const pbrtb200_node32& root = nodes[0];
+  out->root_ref = root.is_leaf ? leaf_ref(root) : 0u;
+  for (int i = 0; i < 3; ++i) {
+    out->root_bmin[i] = root.bmin[i];
+    out->root_bmax[i] = root.bmax[i];
+  }
+  return nullptr;
 }
 
 }  // namespace pbh

@@ -3,11 +3,7 @@
 #include "../../include/pbrtb200.h"
 #include "dmath.cuh"
 
-#define PB_LEAF_BIT 0x80000000u
-// Leaf ref = bit31 | (min(count,16)-1) << 27 | prim_offset (27 bits: up to 134 M primitives).
-// A count field of 15 means "16 or more: read leaf_count[prim_offset]".
-#define PB_LEAF_CNT_SHIFT 27
-#define PB_LEAF_OFF_MASK 0x07FFFFFFu
+#include "leaf_ref.h"  // PB_LEAF_BIT, PB_LEAF_CNT_SHIFT, PB_LEAF_OFF_MASK
 #define PB_SM_STACK 24                                   // traversal-stack entries kept in smem
 #define PB_LM_STACK (PBRTB200_STACK_DEPTH - PB_SM_STACK) // deeper entries spill to local memory
 #define PB_TRACE_THREADS 128

@@ -251,3 +251,62 @@ void devsrc_tri_surface(const pbrtb200_mesh* mesh, const float* pw9, const float
   std::memcpy(out_dgs17, b, sizeof b);
 }
 }
+
+// ---- the traversal itself (csrc/trace_core.cuh) over a flattened scene --------------------------------
+#include <vector>
+
+#include "../../pbrt_rust_b200/csrc/host_logic.hpp"
+#include "../../pbrt_rust_b200/csrc/trace_core.cuh"
+extern "C" {
+// Scene::intersect / intersect_p for n rays (ray8 = o, mint, d, maxt) through the device traversal source,
+// with the pair nodes packed by the product's own build_pair_nodes and the kernel variant the library
+// would launch.  any_mode: -1 closest hit (hit4 = prim, t, b1, b2 per ray), else the any-hit SIMT mode
+// 0..3 (hit4[0] = prim or MISS).  Returns 0, or -1 with a bad scene / -2 on a stack overflow.
+int devsrc_trace(const pbrtb200_scene* s, const float* rays8, unsigned long long n, int any_mode, float* hit4) {
+  pbh::PairNodes pn;
+  if (pbh::build_pair_nodes(s->nodes, s->n_nodes, s->n_prims, &pn)) return -1;
+  DScene sc{};
+  sc.nodes = reinterpret_cast<const float4*>(pn.pairs.data());
+  sc.tris = reinterpret_cast<const float4*>(s->tris);
+  const bool sph = s->n_spheres > 0 || s->leaf_prim != nullptr;
+  sc.leaf_prim = sph ? s->leaf_prim : nullptr;
+  sc.leaf_count = pn.big_leaf ? pn.leaf_count.data() : nullptr;
+  sc.spheres = s->spheres;
+  sc.sphere_o2w = s->sphere_o2w;
+  sc.n_prims = s->n_prims;
+  sc.root_ref = pn.root_ref;
+  for (int i = 0; i < 3; ++i) {
+    sc.root_bmin[i] = pn.root_bmin[i];
+    sc.root_bmax[i] = pn.root_bmax[i];
+  }
+  std::vector<uint32_t> s_ref((size_t)PB_SM_STACK * PB_TRACE_THREADS);
+  std::vector<float> s_t0((size_t)PB_SM_STACK * PB_TRACE_THREADS);
+  int rc = 0;
+  for (unsigned long long i = 0; i < n; ++i) {
+    const float* r = rays8 + 8 * i;
+    const f3 o = mk3(r[0], r[1], r[2]), d = mk3(r[4], r[5], r[6]);
+    uint32_t* sr = s_ref.data() + (i % PB_TRACE_THREADS);  // this "thread's" stack column
+    float* st = s_t0.data() + (i % PB_TRACE_THREADS);
+    TraceResult t;
+#define PB_T(ANY, MODE)                                                                      \
+  t = sph ? (pn.multi ? trace_ray<ANY, true, true, MODE>(sc, o, d, r[3], r[7], sr, st)        \
+                      : trace_ray<ANY, true, false, MODE>(sc, o, d, r[3], r[7], sr, st))      \
+          : (pn.multi ? trace_ray<ANY, false, true, MODE>(sc, o, d, r[3], r[7], sr, st)       \
+                      : trace_ray<ANY, false, false, MODE>(sc, o, d, r[3], r[7], sr, st))
+    switch (any_mode) {
+      case -1: PB_T(false, 1); break;
+      case 0: PB_T(true, 0); break;
+      case 1: PB_T(true, 1); break;
+      case 2: PB_T(true, 2); break;
+      default: PB_T(true, 3); break;
+    }
+#undef PB_T
+    if (t.overflow) rc = -2;
+    hit4[4 * i] = __uint_as_float(t.prim);
+    hit4[4 * i + 1] = t.t;
+    hit4[4 * i + 2] = t.b1;
+    hit4[4 * i + 3] = t.b2;
+  }
+  return rc;
+}
+}

@@ -21,7 +21,7 @@ from pbrt_rust_b200.api import HostScene, Material, Primitive, Scene, Shape, Tex
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "devsrc", "shade_tex_host.cpp")
 LIB = os.path.join(HERE, "devsrc", "libdevsrc.so")
-DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "shade_mip.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "shade_math.cuh", "film_math.cuh")] + \
+DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "shade_mip.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "trace_core.cuh", "host_logic.hpp", "leaf_ref.h", "scene.cuh", "shade_math.cuh", "film_math.cuh")] + \
     [os.path.join(HERE, "..", "include", "pbrtb200.h")]
 
 
@@ -63,6 +63,7 @@ def dev():
     L.devsrc_film_weights.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
     L.devsrc_camera_ray.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.devsrc_tri_surface.argtypes = [C.c_void_p] * 7 + [C.c_float] * 3 + [C.c_void_p] * 2
+    L.devsrc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     return L
 
 
@@ -654,3 +655,64 @@ def test_device_image_textures_match_the_oracle(dev, orc):
             O.lib().orc_texture_eval(osc.h, oid, _p(q), _p(want))
             nan = np.isnan(want)
             assert np.array_equal(np.isnan(got), nan) and np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32)), (t.kind, got, want)
+
+
+def _scene_rays(rng, n, lo, hi, spread):
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    tgt = rng.uniform(-spread, spread, (n, 3)).astype(np.float32)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3], rays[:, 4:7], rays[:, 7] = o, tgt - o, 3.4028235e38
+    k = rng.integers(0, 6, n)
+    rays[k == 0, 7] = rng.uniform(0.2, 1.5, int((k == 0).sum()))      # short segments (shadow-ray like)
+    rays[k == 1, 3] = rng.uniform(0.0, 0.8, int((k == 1).sum()))      # mint > 0
+    return rays
+
+
+@pytest.mark.parametrize("kind", ["triangles_single", "triangles_multi", "mixed_quadrics", "random_scenes"])
+def test_device_traversal_matches_the_oracle(dev, orc, kind):
+    """The kernels' traversal source (csrc/trace_core.cuh: pair-node steps, shared-memory-style stack,
+    leaf decoding, triangle / sphere / cylinder / disk tests, the finite and the NaN-faithful slab
+    paths) run on the CPU over the host mirror's flattened scene with the product's own pair-node
+    packing, against BVHAccelerator::intersect / intersect_p of the oracle: hit ids, t and the
+    barycentrics bit for bit (phi of quadrics within the libm-free tolerance 0 here: same libm), the
+    occlusion bit for all four any-hit loop shapes, ordered and unordered."""
+    from oracle import orc as O
+    rng = np.random.default_rng({"triangles_single": 1, "triangles_multi": 2, "mixed_quadrics": 3, "random_scenes": 4}[kind])
+    if kind == "triangles_single":
+        cfgs = [scenes.config3(nx=40, nz=20, xres=16, yres=16, xs=1, ys=1)]
+    elif kind == "triangles_multi":
+        cfgs = [scenes.config2(n=4000, xres=16, yres=16)]
+    elif kind == "mixed_quadrics":
+        cfgs = [scenes.config4(n_ground=(30, 15), n_spheres=200, xres=16, yres=16, xs=1, ys=1)]
+    else:
+        cfgs = [scenes.random_scene(seed) for seed in (3, 11, 29, 42)]
+    for cfg in cfgs:
+        hs, osc = HostScene(cfg["scene"]), O.OracleScene(cfg["scene"])
+        f = hs.flat.contents
+        lo = np.array([f.nodes[0].bmin[i] for i in range(3)]) - 3.0
+        hi = np.array([f.nodes[0].bmax[i] for i in range(3)]) + 3.0
+        rays = np.concatenate([_scene_rays(rng, 3000, lo, hi, float(max(abs(lo).max(), abs(hi).max())) * 0.7),
+                               _edge_rays(rng, 600) * np.float32([4, 4, 4, 1, 1, 1, 1, 1])]).astype(np.float32)
+        prim, tbb, _ = osc.trace_closest(rays)
+        got = np.zeros((rays.shape[0], 4), np.float32)
+        assert dev.devsrc_trace(C.byref(f), _p(rays), rays.shape[0], -1, _p(got)) == 0
+        gprim = got[:, 0].copy().view(np.uint32)
+        hit = prim != 0xFFFFFFFF
+        assert hit.mean() > 0.1
+        # A ray with a NaN direction component "hits" every triangle it tests with t = NaN (all of the
+        # test's comparisons are false), and a NaN maxt no longer bounds later box tests, so the
+        # reference may go on to subtrees the device pruned while maxt was still finite: both sides
+        # report a NaN hit, possibly at different primitives (DESIGN.md, float-edge cases).
+        nan_dir = np.isnan(rays[:, 4:7]).any(axis=1)
+        assert np.array_equal(gprim[~nan_dir], prim[~nan_dir])
+        assert np.array_equal(gprim[nan_dir] != 0xFFFFFFFF, hit[nan_dir])
+        nan = np.isnan(tbb[:, 0])
+        assert np.array_equal(np.isnan(got[hit, 1]), nan[hit])
+        ok = hit & ~nan
+        assert np.array_equal(got[ok, 1].view(np.uint32), tbb[ok, 0].view(np.uint32))
+        assert np.array_equal(got[ok, 2:4].view(np.uint32), tbb[ok, 1:3].view(np.uint32))
+        occ, _ = osc.trace_any(rays)
+        for mode in range(4):
+            g = np.zeros((rays.shape[0], 4), np.float32)
+            assert dev.devsrc_trace(C.byref(f), _p(rays), rays.shape[0], mode, _p(g)) == 0
+            assert np.array_equal((g[:, 0].copy().view(np.uint32) != 0xFFFFFFFF).astype(np.uint8), occ), mode
