@@ -36,6 +36,36 @@ def test_struct_sizes_match_the_abi():
     assert C.sizeof(_ffi.Film) == 4 * 8 + 256 * 4
 
 
+def test_ctypes_layouts_match_the_c_header(tmp_path):
+    """Every struct of include/pbrtb200.h: size and the offset of every field as the C compiler lays
+    them out == the ctypes mirror in _ffi.py (what a Rust #[repr(C)] binding must reproduce too)."""
+    import subprocess
+    pairs = {"pbrtb200_node32": _ffi.Node32, "pbrtb200_tri48": _ffi.Tri48, "pbrtb200_sphere80": _ffi.Sphere80,
+             "pbrtb200_mesh": _ffi.Mesh, "pbrtb200_texture": _ffi.Texture, "pbrtb200_mipmap": _ffi.MipMap,
+             "pbrtb200_material": _ffi.Material, "pbrtb200_light": _ffi.Light, "pbrtb200_scene": _ffi.Scene,
+             "pbrtb200_camera": _ffi.Camera, "pbrtb200_sampler": _ffi.Sampler, "pbrtb200_film": _ffi.Film,
+             "pbrtb200_integrator": _ffi.Integrator, "pbrtb200_tileset": _ffi.TileSet, "pbrtb200_stats": _ffi.Stats}
+    header = open(os.path.join(ROOT, "include", "pbrtb200.h")).read()
+    declared = set(re.findall(r"}\s*(pbrtb200_[a-z0-9_]+);", header)) - {"pbrtb200_ray32", "pbrtb200_hit16"}
+    assert declared == set(pairs), declared ^ set(pairs)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pbrtb200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    assert C.sizeof(_ffi.Texture) == 120 and C.sizeof(_ffi.Material) == 24
+
+
 def test_no_cpu_fallback_without_a_device():
     """On a box without CUDA the product must fail loudly, not fall back."""
     import torch
