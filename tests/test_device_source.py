@@ -685,7 +685,7 @@ def test_device_traversal_matches_the_oracle(dev, orc, kind):
     elif kind == "mixed_quadrics":
         cfgs = [scenes.config4(n_ground=(30, 15), n_spheres=200, xres=16, yres=16, xs=1, ys=1)]
     else:
-        cfgs = [scenes.random_scene(seed) for seed in (3, 11, 29, 42)]
+        cfgs = [scenes.random_scene(seed) for seed in (3, 11, 29, 42, 57, 64, 71, 88, 93, 105, 117, 123)]
     for cfg in cfgs:
         hs, osc = HostScene(cfg["scene"]), O.OracleScene(cfg["scene"])
         f = hs.flat.contents
