@@ -594,6 +594,25 @@ int orc_tri_surface(const float* o2w, const float* o2w_inv, int ro, const float*
     std::memcpy(out_dgs17, b, sizeof b);
   });
 }
+// Film::add_sample over n samples in the given order: cs2 = image (x, y) pairs, rgb3 = radiance.
+// out_xyzw = xyz sums + weight_sum per film pixel (pixel extent, row-major).
+int orc_film_accumulate(const OrcRenderConfig* c, const float* cs2, const float* rgb3, uint64_t n, float* out_xyzw) {
+  return guarded([&] {
+    RenderConfig cfg = make_config(nullptr, c);
+    for (uint64_t i = 0; i < n; ++i) {
+      CameraSample cs;
+      cs.image_x = cs2[2 * i];
+      cs.image_y = cs2[2 * i + 1];
+      cfg.film.add_sample(cs, rgb3 + 3 * i);
+    }
+    for (size_t i = 0; i < cfg.film.pixels.size(); ++i) {
+      out_xyzw[4 * i + 0] = cfg.film.pixels[i].xyz[0];
+      out_xyzw[4 * i + 1] = cfg.film.pixels[i].xyz[1];
+      out_xyzw[4 * i + 2] = cfg.film.pixels[i].xyz[2];
+      out_xyzw[4 * i + 3] = cfg.film.pixels[i].weight_sum;
+    }
+  });
+}
 // Film::add_sample (film.rs:192-249) of ONE sample with L = (1, 1, 1) into an empty film:
 // out_w = weight_sum per film pixel (pixel extent, row-major).
 int orc_film_add_sample(const OrcRenderConfig* c, float image_x, float image_y, float* out_w) {

@@ -38,6 +38,14 @@ inline float __uint_as_float(uint32_t u) {
   return f;
 }
 inline float __int_as_float(int i) { return __uint_as_float((uint32_t)i); }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+template <class T, class U>
+inline T atomicAdd(T* p, U v) {  // one host thread: a plain read-modify-write
+  const T old = *p;
+  *p = (T)(old + (T)v);
+  return old;
+}
 template <class T>
 inline T __ldg(const T* p) {  // ld.global.nc
   return *p;

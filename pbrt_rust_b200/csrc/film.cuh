@@ -25,7 +25,11 @@ struct DFold {  // how the per-sample radiance terms fold into L (light order)
 
 #include "film_math.cuh"  // DFilm, film_sample_index
 
+#ifdef PB_HOST_CHECK
+static float c_filter_table[256];  // host check: a plain array the harness fills
+#else
 __constant__ float c_filter_table[256];
+#endif
 
 struct FilmArgs {
   const float2* __restrict__ img;         // per sample, list order
@@ -73,11 +77,9 @@ PB_DEV bool fold_radiance(const DFold& fd, const float4* __restrict__ r, float* 
   return isnan(L.x) || isnan(L.y) || isnan(L.z);
 }
 
-__global__ void __launch_bounds__(128)
-k_film(const DFilm f, const DFold fd, const FilmArgs a) {
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= a.count) return;
-  const uint32_t gid = a.first + tid;
+// One film pixel (ordinal `gid` over the rects of this call): the whole gather.  Written as a
+// function of the ordinal so that the host check (tests/devsrc/) can run it pixel by pixel.
+PB_DEV void film_pixel(const DFilm& f, const DFold& fd, const FilmArgs& a, uint32_t gid) {
   // locate the rect (few rects per GPU; binary search over the prefix sums)
   uint32_t lo = 0, hi = a.n_rects;
   while (hi - lo > 1) {
@@ -140,6 +142,14 @@ k_film(const DFilm f, const DFold fd, const FilmArgs a) {
       make_float4(X, Y, Z, Wt);
 }
 
+#ifndef PB_HOST_CHECK
+__global__ void __launch_bounds__(128)
+k_film(const DFilm f, const DFold fd, const FilmArgs a) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= a.count) return;
+  film_pixel(f, fd, a, a.first + tid);
+}
+
 // Film::write_image pixel pipeline (film.rs:331-340 as intended, write_img film.rs:21-23).
 __global__ void __launch_bounds__(256)
 k_film_develop(const float4* __restrict__ film, uint64_t n, float* __restrict__ out_rgb,
@@ -172,3 +182,4 @@ k_film_develop(const float4* __restrict__ film, uint64_t n, float* __restrict__ 
     out_rgb8[3 * i + 2] = to_byte(b);
   }
 }
+#endif  // PB_HOST_CHECK

@@ -310,3 +310,56 @@ int devsrc_trace(const pbrtb200_scene* s, const float* rays8, unsigned long long
   return rc;
 }
 }
+
+// ---- the film gather itself (film_pixel, csrc/film.cuh) over a whole frame -----------------------------
+#include "../../pbrt_rust_b200/csrc/film.cuh"
+extern "C" {
+// Whole-film gather of a frame whose sampler pixels are listed in raster order over the sampler extent
+// ext4 = (x0, x1, y0, y1), spp samples each: img2 = image (x, y) per sample, rgb3 = its radiance (one
+// non-area light term, no Le slot).  out_xyzw = the film, row-major over the film pixel extent.
+void devsrc_film_gather(const pbrtb200_film* film, const int* ext4, int spp, const float* img2, const float* rgb3,
+                        float* out_xyzw) {
+  std::memcpy(c_filter_table, film->filter_table, sizeof c_filter_table);
+  DFilm f{};
+  f.x_start = film->x_pixel_start;
+  f.y_start = film->y_pixel_start;
+  f.x_count = film->x_pixel_count;
+  f.y_count = film->y_pixel_count;
+  f.xw = film->filter_xw;
+  f.yw = film->filter_yw;
+  f.inv_xw = 1.0f / film->filter_xw;
+  f.inv_yw = 1.0f / film->filter_yw;
+  f.sx0 = ext4[0]; f.sx1 = ext4[1]; f.sy0 = ext4[2]; f.sy1 = ext4[3];
+  f.spp = spp;
+  DFold fd{};
+  fd.rad_slots = 1;
+  fd.le_slot = 0;
+  fd.n_lights = 1;
+  fd.ns[0] = 1;
+  fd.area[0] = 0;
+  const size_t npx = (size_t)(ext4[1] - ext4[0]) * (size_t)(ext4[3] - ext4[2]), ns = npx * (size_t)spp;
+  std::vector<float4> rad(ns);
+  for (size_t i = 0; i < ns; ++i) rad[i] = make_float4(rgb3[3 * i], rgb3[3 * i + 1], rgb3[3 * i + 2], 0.f);
+  std::vector<uint32_t> edge(npx, 1u);
+  std::vector<int32_t> index(npx);
+  for (size_t i = 0; i < npx; ++i) index[i] = (int32_t)i;
+  const int32_t rect[4] = {f.x_start, f.y_start, f.x_start + f.x_count, f.y_start + f.y_count};
+  const uint32_t prefix[2] = {0u, (uint32_t)(f.x_count * f.y_count)};
+  uint32_t nan_count = 0;
+  FilmArgs a{};
+  a.img = reinterpret_cast<const float2*>(img2);
+  a.rad = rad.data();
+  a.offsets = nullptr;
+  a.edge = edge.data();
+  a.pix_index = index.data();
+  a.rects = rect;
+  a.rect_prefix = prefix;
+  a.n_rects = 1;
+  a.n_pixels = prefix[1];
+  a.first = 0;
+  a.count = prefix[1];
+  a.out = reinterpret_cast<float4*>(out_xyzw);
+  a.nan_count = &nan_count;
+  for (uint32_t gid = 0; gid < a.n_pixels; ++gid) film_pixel(f, fd, a, gid);
+}
+}

@@ -21,7 +21,7 @@ from pbrt_rust_b200.api import HostScene, Material, Primitive, Scene, Shape, Tex
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "devsrc", "shade_tex_host.cpp")
 LIB = os.path.join(HERE, "devsrc", "libdevsrc.so")
-DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "shade_mip.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "trace_core.cuh", "host_logic.hpp", "leaf_ref.h", "scene.cuh", "shade_math.cuh", "film_math.cuh")] + \
+DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "shade_mip.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "trace_core.cuh", "host_logic.hpp", "leaf_ref.h", "scene.cuh", "shade_math.cuh", "film_math.cuh", "film.cuh")] + \
     [os.path.join(HERE, "..", "include", "pbrtb200.h")]
 
 
@@ -64,6 +64,7 @@ def dev():
     L.devsrc_camera_ray.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.devsrc_tri_surface.argtypes = [C.c_void_p] * 7 + [C.c_float] * 3 + [C.c_void_p] * 2
     L.devsrc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    L.devsrc_film_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -716,3 +717,38 @@ def test_device_traversal_matches_the_oracle(dev, orc, kind):
             g = np.zeros((rays.shape[0], 4), np.float32)
             assert dev.devsrc_trace(C.byref(f), _p(rays), rays.shape[0], mode, _p(g)) == 0
             assert np.array_equal((g[:, 0].copy().view(np.uint32) != 0xFFFFFFFF).astype(np.uint8), occ), mode
+
+
+@pytest.mark.parametrize("sampler", ["stratified", "ld"])
+def test_device_film_gather_matches_the_oracle(dev, orc, sampler):
+    """film_pixel (csrc/film.cuh: the per-pixel gather over neighbouring sampler pixels in raster
+    order, add_sample's arithmetic, the radiance fold and to_xyz) run for every film pixel of a frame
+    on the oracle's own camera samples and random radiance, against a sequential Film::add_sample
+    sweep of the oracle in raster order: xyz sums and weight sums bit for bit, for every filter and
+    for crop windows (the deterministic-accumulation contract of DESIGN.md §4)."""
+    from pbrt_rust_b200.api import Camera, Film, Filter, Sampler
+    L = orc.lib()
+    L.orc_film_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    rng = np.random.default_rng(91)
+    U = lambda a, b: float(rng.uniform(a, b))
+    for trial in range(12):
+        filt = [Filter.mean(0.5, 0.5), Filter.mean(U(0.5, 2.0), U(0.5, 2.0)), Filter.triangle(U(1, 2), U(1, 2)),
+                Filter.gaussian(U(1, 2.5), U(1, 2.5), U(0.5, 2)), Filter.mitchell(2.0, 2.0, 1 / 3, 1 / 3),
+                Filter.lanczos(U(1.5, 3), U(1.5, 3), 3.0)][trial % 6]
+        crop = (0, 1, 0, 1) if trial < 6 else tuple(sorted([U(0, 0.4), U(0.6, 1)]) + sorted([U(0, 0.4), U(0.6, 1)]))
+        film = Film.image(int(rng.integers(12, 28)), int(rng.integers(10, 22)), filt, crop)
+        cam = Camera.perspective(Transform.new(), (-1.0, 1.0, -1.0, 1.0), 0.0, 0.0, 0.0, 1e6, 50.0, film)
+        e = film.get_sample_extent()
+        smp = Sampler.stratified(e[0], e[1], e[2], e[3], 2, 2, True, 0.0, 0.0) if sampler == "stratified" \
+            else Sampler.low_discrepancy(e[0], e[1], e[2], e[3], 4, 0.0, 0.0)
+        cfg = orc.render_config(cam, smp, num_cpus=8, mode=0)
+        cs, _, _, _ = orc.camera_samples(cfg, 0, e[0], e[1], e[2], e[3], 4)   # raster order, 4 per pixel
+        img = np.ascontiguousarray(cs[:, 0:2])
+        rgb = rng.uniform(0, 3, (cs.shape[0], 3)).astype(np.float32)
+        h, w = film.shape
+        want, got = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+        assert L.orc_film_accumulate(C.byref(cfg), _p(img), _p(rgb), cs.shape[0], _p(want)) == 0
+        ext = np.array(e, np.int32)
+        dev.devsrc_film_gather(C.byref(film.desc), _p(ext), 4, _p(img), _p(rgb), _p(got))
+        assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (trial, float(np.abs(want - got).max()))
+        assert (want[..., 3] != 0).mean() > 0.9  # (negative lobes of mitchell / lanczos are fine)
