@@ -752,3 +752,35 @@ def test_device_film_gather_matches_the_oracle(dev, orc, sampler):
         dev.devsrc_film_gather(C.byref(film.desc), _p(ext), 4, _p(img), _p(rgb), _p(got))
         assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (trial, float(np.abs(want - got).max()))
         assert (want[..., 3] != 0).mean() > 0.9  # (negative lobes of mitchell / lanczos are fine)
+
+
+@pytest.mark.parametrize("which", ["config1", "config2", "config4"])
+def test_device_primary_hits_of_a_frame_match_the_oracle(dev, orc, which):
+    """The config-2 check on the CPU: every camera sample of a small frame through the device source's
+    camera_ray and traversal (host mirror's flattened scene, product pair-node packing) against the
+    oracle's render — primary-hit ids 100 % equal, t bit for bit."""
+    from oracle import orc as O
+    cfg = {"config1": lambda: scenes.config1(xres=40, yres=30),
+           "config2": lambda: scenes.config2(n=5000, xres=48, yres=32),
+           "config4": lambda: scenes.config4(n_ground=(30, 15), n_spheres=150, xres=40, yres=24, xs=2, ys=1)}[which]()
+    hs, osc = HostScene(cfg["scene"]), O.OracleScene(cfg["scene"])
+    ocfg = O.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0, primary_only=True)
+    ref = O.render(osc, ocfg, want_hits=True)
+    se = O.layout(ocfg)["sample_ext"]
+    spp = cfg["sampler"].samples_per_pixel()
+    # (the light-sample floats of area lights sit in the same per-pixel stream: same pair count as the render)
+    pairs = sum(l.num_samples for l in cfg["scene"].all_lights() if l.kind == "area")
+    cs, _, _, _ = O.camera_samples(ocfg, pairs, se[0], se[1], se[2], se[3], spp)
+    rays = np.zeros((cs.shape[0], 8), np.float32)
+    out = np.zeros(6, np.float32)
+    for k in range(cs.shape[0]):
+        dev.devsrc_camera_ray(C.byref(cfg["camera"].desc), spp, _p(cs[k]), _p(out))
+        rays[k, 0:3], rays[k, 4:7] = out[0:3], out[3:6]
+    rays[:, 7] = 3.4028235e38
+    got = np.zeros((rays.shape[0], 4), np.float32)
+    assert dev.devsrc_trace(C.byref(hs.flat.contents), _p(rays), rays.shape[0], -1, _p(got)) == 0
+    prim = got[:, 0].copy().view(np.uint32)
+    assert np.array_equal(prim, ref["hit_ids"])
+    hit = prim != 0xFFFFFFFF
+    assert 0.1 < hit.mean()
+    assert np.array_equal(got[hit, 1].view(np.uint32), ref["hit_ts"][hit].view(np.uint32))
