@@ -66,6 +66,24 @@ def test_ctypes_layouts_match_the_c_header(tmp_path):
     assert C.sizeof(_ffi.Texture) == 120 and C.sizeof(_ffi.Material) == 24
 
 
+def test_rust_ffi_is_generated_from_the_header():
+    """integration/rust/src/gpu/ffi.rs (the binding a maintainer adds to the crate) is exactly what
+    scripts/gen_rust_ffi.py produces from the current header, declares every pbrtb200_* entry point
+    and mirrors every public struct with its size."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "scripts", "gen_rust_ffi.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    text, fns = g.generate()
+    assert open(g.OUT).read() == text, "run python scripts/gen_rust_ffi.py"
+    header = open(os.path.join(ROOT, "include", "pbrtb200.h")).read()
+    declared = set(re.findall(r"\b(pbrtb200_[a-z_0-9]+)\s*\(", header)) - {"pbrtb200_ctx"}
+    assert declared == set(fns), declared ^ set(fns)
+    for cname in re.findall(r"}\s*(pbrtb200_[a-z0-9_]+);", header):
+        assert f"pub struct {cname} " in text, cname
+    assert "size_of::<pbrtb200_texture>() == 120" in text and "size_of::<pbrtb200_scene>()" in text
+
+
 def test_no_cpu_fallback_without_a_device():
     """On a box without CUDA the product must fail loudly, not fall back."""
     import torch
