@@ -2,6 +2,16 @@
 // It lives inside the crate because the fields it reads are private.
 use super::ffi::*;
 
+// short names used in the sketch
+pub type Node32 = pbrtb200_node32;
+pub type Tri48 = pbrtb200_tri48;
+pub type Sphere80 = pbrtb200_sphere80;
+pub type MeshRec = pbrtb200_mesh;
+pub type TextureRec = pbrtb200_texture;
+pub type MaterialRec = pbrtb200_material;
+pub type LightRec = pbrtb200_light;
+pub type SceneDesc = pbrtb200_scene;
+
 pub struct FlatScene { nodes: Vec<Node32>, leaf_prim: Vec<u32>, tris: Vec<Tri48>,
                        spheres: Vec<Sphere80>, sphere_o2w: Vec<f32>, meshes: Vec<MeshRec>, /* … */ }
 
