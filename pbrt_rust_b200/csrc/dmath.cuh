@@ -38,6 +38,31 @@ inline float __uint_as_float(uint32_t u) {
   return f;
 }
 inline float __int_as_float(int i) { return __uint_as_float((uint32_t)i); }
+// Kernels under the host check: one emulated thread per block (blockDim = 1), which is what the
+// block-level bookkeeping of k_shade degenerates to with a single lane; the harness sets blockIdx.
+struct PbDim3 {
+  unsigned x, y, z;
+};
+static PbDim3 blockIdx{0, 0, 0}, threadIdx{0, 0, 0};
+static const PbDim3 blockDim{1, 1, 1};
+#define __global__
+#define __shared__ static
+#define __launch_bounds__(...)
+inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline void __syncthreads() {}
+inline unsigned __activemask() { return 1u; }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+template <class T>
+inline T __shfl_sync(unsigned, T v, int) {
+  return v;
+}
+template <class T, class U>
+inline T atomicOr(T* p, U v) {
+  const T old = *p;
+  *p = (T)(old | (T)v);
+  return old;
+}
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 template <class T, class U>
@@ -57,6 +82,13 @@ inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, int c) {
 #else
 #include <cuda_runtime.h>
 #define PB_DEV __device__ __forceinline__
+#endif
+#ifdef PB_HOST_CHECK
+#define PB_PREFETCH_L1(p) ((void)(p))
+#define PB_PREFETCH_L2(p) ((void)(p))
+#else
+#define PB_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#define PB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
 #define PB_F32_MAX 3.402823466e+38f
 #define PB_PI 3.14159265358979323846f

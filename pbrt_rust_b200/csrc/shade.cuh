@@ -160,8 +160,8 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   if (in_range) {
     hraw = __ldg(reinterpret_cast<const float4*>(a.hits) + idx);
     // independent streams this thread will need later: start them now (no register cost)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.img + idx));
-    if (a.lightu) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.lightu + (a.sample0 + idx) * sc.area_sample_pairs));
+    PB_PREFETCH_L2(a.img + idx);
+    if (a.lightu) PB_PREFETCH_L2(a.lightu + (a.sample0 + idx) * sc.area_sample_pairs);
   }
   const uint32_t prim = __float_as_uint(hraw.x);
   // Block-level bookkeeping. A same-address global atomic retires at ~0.66 ns on B200 (measured,
@@ -196,8 +196,8 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   // material -> texture); start fetching it now so it overlaps the camera-ray arithmetic below.
   if (!sc.leaf_prim) {
     const char* tp = reinterpret_cast<const char*>(sc.tris + 3ull * prim);
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(tp));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + 32));
+    PB_PREFETCH_L1(tp);
+    PB_PREFETCH_L1(tp + 32);
   }
 
   // Regenerate the camera ray and its differentials (camera/mod.rs:212-271, ray.rs:107-112;

@@ -363,3 +363,222 @@ void devsrc_film_gather(const pbrtb200_film* film, const int* ext4, int spp, con
   for (uint32_t gid = 0; gid < a.n_pixels; ++gid) film_pixel(f, fd, a, gid);
 }
 }
+
+// ---- a whole frame through the device source: camera rays, closest hit, k_shade, any-hit, film ----------
+#include "../../pbrt_rust_b200/csrc/shade.cuh"
+namespace {
+template <bool ANY, int MODE>
+TraceResult trace_any_variant(const DScene& sc, bool sph, bool multi, f3 o, f3 d, float mint, float maxt, uint32_t* sr, float* st) {
+  return sph ? (multi ? trace_ray<ANY, true, true, MODE>(sc, o, d, mint, maxt, sr, st)
+                      : trace_ray<ANY, true, false, MODE>(sc, o, d, mint, maxt, sr, st))
+             : (multi ? trace_ray<ANY, false, true, MODE>(sc, o, d, mint, maxt, sr, st)
+                      : trace_ray<ANY, false, false, MODE>(sc, o, d, mint, maxt, sr, st));
+}
+}  // namespace
+extern "C" {
+// One frame.  The camera samples come from the caller (raster pixel order over the sampler extent
+// ext4, spp per pixel): img2 image positions, lens2 lens positions or NULL, lightu = area_sample_pairs
+// float pairs per sample or NULL.  Everything else is the device source: camera_ray, the traversal,
+// the k_shade kernel (one emulated thread per block), the any-hit pass over its shadow queue and
+// film_pixel; the scene set-up mirrors pbrtb200_upload_scene.  out_xyzw = the film; stats3 = camera
+// hits, shadow rays, occluded shadow rays.  Returns 0 or a negative code.
+int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb200_film* film, const int* ext4, int spp,
+                  const float* img2, const float* lens2, const float* lightu, int strict_flags, float* out_xyzw,
+                  unsigned long long* stats3) {
+  pbh::PairNodes pn;
+  if (pbh::build_pair_nodes(s->nodes, s->n_nodes, s->n_prims, &pn)) return -1;
+  DScene sc{};
+  sc.nodes = reinterpret_cast<const float4*>(pn.pairs.data());
+  sc.tris = reinterpret_cast<const float4*>(s->tris);
+  const bool sph = s->n_spheres > 0 || s->leaf_prim != nullptr;
+  sc.leaf_prim = sph ? s->leaf_prim : nullptr;
+  sc.leaf_count = pn.big_leaf ? pn.leaf_count.data() : nullptr;
+  sc.spheres = s->spheres;
+  sc.sphere_o2w = s->sphere_o2w;
+  sc.meshes = s->meshes;
+  sc.tri_uv = s->tri_uv;
+  sc.tri_n = s->tri_n;
+  sc.tri_s = s->tri_s;
+  sc.materials = s->materials;
+  sc.textures = s->textures;
+  sc.mipmaps = s->n_mipmaps ? s->mipmaps : nullptr;
+  sc.texels = s->n_mipmaps ? reinterpret_cast<const float4*>(s->texels) : nullptr;
+  sc.n_prims = s->n_prims;
+  sc.n_lights = s->n_lights;
+  sc.root_ref = pn.root_ref;
+  for (int i = 0; i < 3; ++i) {
+    sc.root_bmin[i] = pn.root_bmin[i];
+    sc.root_bmax[i] = pn.root_bmax[i];
+  }
+  // mat_flags, the EXT decision, light slots, area-light records: as pbrtb200_upload_scene does
+  std::vector<uint8_t> mat_flags(std::max<uint32_t>(1u, s->n_materials), 0);
+  bool ext = false;
+  for (uint32_t i = 0; i < s->n_textures; ++i)
+    if (s->textures[i].kind > PBRTB200_TEX_IMAGE ||
+        (s->textures[i].kind != PBRTB200_TEX_CONSTANT && s->textures[i].map_kind > PBRTB200_MAP_PLANAR))
+      ext = true;
+  for (uint32_t i = 0; i < s->n_materials; ++i) {
+    const pbrtb200_material& m = s->materials[i];
+    auto varying = [&](int id) { return s->textures[id].kind != PBRTB200_TEX_CONSTANT; };
+    bool v = varying(m.kd);
+    if (m.kind == PBRTB200_MAT_MATTE) v = v || varying(m.sigma);
+    if (m.kind == PBRTB200_MAT_PLASTIC) v = v || varying(m.ks) || varying(m.roughness);
+    if (m.bump != 0) v = ext = true;
+    mat_flags[i] = v ? 1 : 0;
+  }
+  sc.mat_flags = mat_flags.data();
+  std::vector<pbrtb200_light> lights(s->lights, s->lights + s->n_lights);
+  for (const pbrtb200_light& l : lights) {
+    if (l.kind == PBRTB200_LIGHT_AREA) {
+      sc.light_slots += (uint32_t)l.num_samples;
+      sc.area_sample_pairs += (uint32_t)l.num_samples;
+    } else {
+      sc.light_slots += 1;
+    }
+  }
+  std::vector<DAreaTri> at(std::max<uint32_t>(1u, s->n_area_prims));
+  for (uint32_t i = 0; i < s->n_area_prims; ++i) {  // k_area_tri_setup, one emulated thread per block
+    blockIdx.x = i;
+    k_area_tri_setup(sc, s->area_prims, s->n_area_prims, at.data());
+  }
+  for (pbrtb200_light& l : lights) {
+    if (l.kind != PBRTB200_LIGHT_AREA) continue;
+    float total = 0.f;
+    for (uint32_t k = 0; k < l.n_tris; ++k) total += at[l.first_tri + k].area;
+    l.total_area = total;
+    float acc = 0.f, lo = 0.f;
+    for (uint32_t k = 0; k < l.n_tris; ++k) {
+      acc += at[l.first_tri + k].area;
+      float hi = acc / total;
+      if (k + 1 == l.n_tris) hi = 1.0f;
+      at[l.first_tri + k].cdf_lo = lo;
+      at[l.first_tri + k].cdf_hi = hi;
+      lo = hi;
+    }
+  }
+  sc.lights = lights.data();
+  DCamera dc;
+  std::memcpy(dc.r2c, c->raster_to_camera, 64);
+  std::memcpy(dc.c2w, c->camera_to_world, 64);
+  for (int i = 0; i < 3; ++i) {
+    dc.dx[i] = c->dx_camera[i];
+    dc.dy[i] = c->dy_camera[i];
+  }
+  dc.sopen = c->shutter_open;
+  dc.sclose = c->shutter_close;
+  dc.lens_radius = c->lens_radius;
+  dc.focal_distance = c->focal_distance;
+  dc.diff_scale = 1.0f / std::sqrt((float)spp);
+
+  const size_t npx = (size_t)(ext4[1] - ext4[0]) * (size_t)(ext4[3] - ext4[2]), n = npx * (size_t)spp;
+  const float2* img = reinterpret_cast<const float2*>(img2);
+  const float2* lens = (lens2 && c->lens_radius > 0.0f) ? reinterpret_cast<const float2*>(lens2) : nullptr;
+  std::vector<uint32_t> s_ref((size_t)PB_SM_STACK * PB_TRACE_THREADS);
+  std::vector<float> s_t0((size_t)PB_SM_STACK * PB_TRACE_THREADS);
+  // closest hit per camera sample (the SRC = 1 path of k_trace: camera_ray, mint 0, maxt f32::MAX)
+  std::vector<pbrtb200_hit16> hits(std::max<size_t>(1, n));
+  int rc = 0;
+  for (size_t i = 0; i < n; ++i) {
+    f3 o, d;
+    camera_ray(dc, img[i].x, img[i].y, lens ? lens[i].x : 0.f, lens ? lens[i].y : 0.f, &o, &d, nullptr);
+    const TraceResult t = trace_any_variant<false, 1>(sc, sph, pn.multi, o, d, 0.0f, PB_F32_MAX, s_ref.data(), s_t0.data());
+    if (t.overflow) rc = -2;
+    hits[i].prim = t.prim;
+    hits[i].t = t.t;
+    hits[i].b1 = t.b1;
+    hits[i].b2 = t.b2;
+  }
+  // k_shade
+  const uint32_t slots = std::max(1u, sc.light_slots);
+  const uint32_t le_slot = sc.area_sample_pairs ? 1u : 0u;
+  const uint32_t rad_slots = sc.n_lights ? sc.light_slots + le_slot : 0u;
+  std::vector<float4> rad(std::max<size_t>(1, n * std::max(1u, rad_slots)));
+  std::vector<pbrtb200_ray32> sq_rays(std::max<size_t>(1, n * slots));
+  std::vector<uint32_t> sq_slots(std::max<size_t>(1, n * slots));
+  uint32_t sq_count = 0;
+  unsigned long long hit_total = 0, occluded = 0;
+  if (sc.n_lights) {
+    ShadeArgs sa{};
+    sa.img = img;
+    sa.lens = lens;
+    sa.lightu = sc.area_sample_pairs ? reinterpret_cast<const float2*>(lightu) : nullptr;
+    sa.hits = hits.data();
+    sa.area_tris = at.data();
+    sa.rad = rad.data();
+    sa.sq_rays = sq_rays.data();
+    sa.sq_slots = sq_slots.data();
+    sa.sq_count = &sq_count;
+    sa.hit_total = &hit_total;
+    sa.n = n;
+    sa.sample0 = 0;
+    sa.rad_slots = rad_slots;
+    sa.le_slot = le_slot;
+    sa.strict_flags = strict_flags;
+    for (size_t i = 0; i < n; ++i) {
+      blockIdx.x = (unsigned)i;
+      if (ext)
+        k_shade<PB_SHADE_EXT_MIN_BLOCKS, true, true>(sc, dc, sa);
+      else if (sc.mipmaps)
+        k_shade<PB_SHADE_MIN_BLOCKS, true>(sc, dc, sa);
+      else
+        k_shade<PB_SHADE_MIN_BLOCKS, false>(sc, dc, sa);
+    }
+    // the any-hit pass over the shadow queue (k_trace<ANY>, default loop shape 2)
+    for (uint32_t q = 0; q < sq_count; ++q) {
+      const pbrtb200_ray32& r = sq_rays[q];
+      const TraceResult t = trace_any_variant<true, 2>(sc, sph, pn.multi, mk3(r.o[0], r.o[1], r.o[2]), mk3(r.d[0], r.d[1], r.d[2]),
+                                                       r.mint, r.maxt, s_ref.data(), s_t0.data());
+      if (t.overflow) rc = -2;
+      if (t.prim != PBRTB200_MISS) {
+        rad[sq_slots[q]] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ++occluded;
+      }
+    }
+  }
+  // film
+  std::memcpy(c_filter_table, film->filter_table, sizeof c_filter_table);
+  DFilm f{};
+  f.x_start = film->x_pixel_start;
+  f.y_start = film->y_pixel_start;
+  f.x_count = film->x_pixel_count;
+  f.y_count = film->y_pixel_count;
+  f.xw = film->filter_xw;
+  f.yw = film->filter_yw;
+  f.inv_xw = 1.0f / film->filter_xw;
+  f.inv_yw = 1.0f / film->filter_yw;
+  f.sx0 = ext4[0]; f.sx1 = ext4[1]; f.sy0 = ext4[2]; f.sy1 = ext4[3];
+  f.spp = spp;
+  DFold fd{};
+  fd.rad_slots = rad_slots;
+  fd.le_slot = le_slot;
+  fd.n_lights = sc.n_lights;
+  for (uint32_t i = 0; i < sc.n_lights; ++i) {
+    fd.area[i] = lights[i].kind == PBRTB200_LIGHT_AREA ? 1 : 0;
+    fd.ns[i] = (uint16_t)(fd.area[i] ? lights[i].num_samples : 1);
+  }
+  std::vector<uint32_t> edge(npx, 1u);
+  std::vector<int32_t> index(npx);
+  for (size_t i = 0; i < npx; ++i) index[i] = (int32_t)i;
+  const int32_t rect[4] = {f.x_start, f.y_start, f.x_start + f.x_count, f.y_start + f.y_count};
+  const uint32_t prefix[2] = {0u, (uint32_t)(f.x_count * f.y_count)};
+  uint32_t nan_count = 0;
+  FilmArgs a{};
+  a.img = img;
+  a.rad = rad.data();
+  a.edge = edge.data();
+  a.pix_index = index.data();
+  a.rects = rect;
+  a.rect_prefix = prefix;
+  a.n_rects = 1;
+  a.n_pixels = prefix[1];
+  a.first = 0;
+  a.count = prefix[1];
+  a.out = reinterpret_cast<float4*>(out_xyzw);
+  a.nan_count = &nan_count;
+  for (uint32_t gid = 0; gid < a.n_pixels; ++gid) film_pixel(f, fd, a, gid);
+  stats3[0] = hit_total;
+  stats3[1] = sq_count;
+  stats3[2] = occluded;
+  return nan_count ? -3 : rc;
+}
+}
