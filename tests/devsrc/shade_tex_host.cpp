@@ -582,3 +582,178 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
   return nan_count ? -3 : rc;
 }
 }
+
+// ---- the sample-generation kernels (k_raygen_groups / k_raygen_full, k_halton_*), emulated thread by thread ----
+#include "../../pbrt_rust_b200/csrc/raygen.cuh"
+#include "../../pbrt_rust_b200/csrc/halton.cuh"
+namespace {
+// the raster-order pixel list of a whole sampler extent with each pixel's task and in-window index
+// (what build_pixel_list derives from sampler/base.rs:29-48), plus the task keys
+void raster_pixel_list(const pbrtb200_sampler* smp, std::vector<DPixel>* list, std::vector<uint32_t>* keys,
+                       std::vector<DHaltonTask>* htasks) {
+  const int32_t ext[4] = {smp->x_start, smp->x_end, smp->y_start, smp->y_end};
+  const int sw = ext[1] - ext[0], sh = ext[3] - ext[2];
+  list->assign((size_t)sw * sh, DPixel{0, 0, 0xFFFFu});
+  keys->assign(8 * (size_t)smp->num_tasks, 0u);
+  unsigned long long first = 0;
+  for (int t = 0; t < smp->num_tasks; ++t) {
+    pbh::task_key((uint64_t)t, &(*keys)[8 * (size_t)t]);
+    int32_t w[4];
+    pbh::sampler_sub_window(ext, (uint64_t)t, (uint64_t)smp->num_tasks, w);
+    DHaltonTask ht{};
+    ht.x0 = w[0]; ht.x1 = w[1]; ht.y0 = w[2]; ht.y1 = w[3];
+    ht.first = first;
+    if (w[0] != w[1] && w[2] != w[3]) {
+      const int dx = w[1] - w[0], dy = w[3] - w[2], m = dx > dy ? dx : dy;
+      ht.wanted = (unsigned long long)((long long)m * (long long)m) * (unsigned long long)smp->xs;
+      ht.delta = std::fmax((float)dy, (float)dx);
+      const uint32_t tw = (uint32_t)(w[1] - w[0]);
+      for (int y = w[2]; y < w[3]; ++y)
+        for (int x = w[0]; x < w[1]; ++x) {
+          DPixel& p = (*list)[(size_t)(y - ext[2]) * sw + (size_t)(x - ext[0])];
+          p.xy = (int32_t)(((uint32_t)(uint16_t)(int16_t)x) | ((uint32_t)(uint16_t)(int16_t)y << 16));
+          p.k = (uint32_t)(y - w[2]) * tw + (uint32_t)(x - w[0]);
+          p.task = (uint32_t)t;
+        }
+    }
+    first += ht.wanted;
+    htasks->push_back(ht);
+  }
+}
+}  // namespace
+extern "C" {
+// Stratified / LD sample generation for the whole sampler extent (raster pixel order, spp per pixel).
+// full != 0 runs k_raygen_full (lens / time shuffles, LD), else k_raygen_groups (stratified, image
+// samples + light floats only).  out_cs5: image_x, image_y, lens_u, lens_v, time; out_lightu: light_pairs
+// float pairs per sample; out_edge: per pixel.  Film geometry for the edge flags comes from `film`.
+void devsrc_raygen(const pbrtb200_sampler* smp, int light_pairs, const pbrtb200_film* film, int full, float* out_cs5,
+                   float* out_lightu, uint32_t* out_edge) {
+  std::vector<DPixel> list;
+  std::vector<uint32_t> keys;
+  std::vector<DHaltonTask> unused;
+  raster_pixel_list(smp, &list, &keys, &unused);
+  DSampler ds{};  // as fill_sampler does
+  ds.kind = smp->kind;
+  ds.xs = smp->xs;
+  ds.ys = smp->kind == PBRTB200_SAMPLER_STRATIFIED ? smp->ys : 1;
+  ds.jitter = smp->jitter;
+  int spp = smp->xs * smp->ys;
+  if (smp->kind != PBRTB200_SAMPLER_STRATIFIED) {
+    spp = 1;
+    while (spp < smp->xs) spp <<= 1;
+  }
+  ds.spp = spp;
+  const uint32_t n = (uint32_t)spp;
+  ds.cam_words = smp->kind == PBRTB200_SAMPLER_STRATIFIED ? (smp->jitter ? 9u * n : 4u * n) : 2u * (5u + 6u * n);
+  ds.words_per_pixel = ds.cam_words + 2u * n * (uint32_t)light_pairs;
+  ds.sopen = smp->shutter_open;
+  ds.sclose = smp->shutter_close;
+  ds.task_keys = keys.data();
+  const size_t npx = list.size(), ns = npx * (size_t)spp;
+  std::vector<float2> img(ns), lens(ns, float2{0.f, 0.f}), lu(std::max<size_t>(1, ns * (size_t)light_pairs));
+  std::vector<float> tm(ns, 0.f);
+  std::vector<uint32_t> edge(npx, 0u);
+  RaygenArgs ra{};
+  ra.pixels = list.data();
+  ra.n_pixels = npx;
+  ra.img = img.data();
+  ra.lens = full ? lens.data() : nullptr;
+  ra.time = full ? tm.data() : nullptr;
+  ra.light_pairs = (uint32_t)light_pairs;
+  ra.lightu = light_pairs ? lu.data() : nullptr;
+  ra.edge = edge.data();
+  ra.fx_start = film->x_pixel_start;
+  ra.fy_start = film->y_pixel_start;
+  ra.fx_count = film->x_pixel_count;
+  ra.fy_count = film->y_pixel_count;
+  ra.xw = film->filter_xw;
+  ra.yw = film->filter_yw;
+  const size_t threads = full ? npx : npx * (size_t)((spp + 7) / 8);
+  for (size_t t = 0; t < threads; ++t) {
+    blockIdx.x = (unsigned)t;
+    if (full) k_raygen_full(ds, ra); else k_raygen_groups(ds, ra);
+  }
+  for (size_t i = 0; i < ns; ++i) {
+    out_cs5[5 * i] = img[i].x;
+    out_cs5[5 * i + 1] = img[i].y;
+    out_cs5[5 * i + 2] = lens[i].x;
+    out_cs5[5 * i + 3] = lens[i].y;
+    out_cs5[5 * i + 4] = tm[i];
+  }
+  if (light_pairs) std::memcpy(out_lightu, lu.data(), ns * (size_t)light_pairs * sizeof(float2));
+  std::memcpy(out_edge, edge.data(), npx * sizeof(uint32_t));
+}
+
+// The Halton kernels over the whole sampler extent: k_halton_bin<0>, the host scan, k_halton_bin<1>,
+// k_halton_samples.  out_counts per pixel (raster); samples written compactly in pixel order: out_cs5
+// (sum of counts entries), out_lightu (light_pairs float pairs each).  Returns the number of samples.
+unsigned long long devsrc_halton(const pbrtb200_sampler* smp, int light_pairs, uint32_t* out_counts, float* out_cs5,
+                                 float* out_lightu, unsigned long long capacity) {
+  std::vector<DPixel> list;
+  std::vector<uint32_t> keys;
+  std::vector<DHaltonTask> tasks;
+  raster_pixel_list(smp, &list, &keys, &tasks);
+  const size_t npx = list.size();
+  std::vector<int32_t> index(npx);
+  for (size_t i = 0; i < npx; ++i) index[i] = (int32_t)i;
+  std::vector<uint32_t> counts(npx, 0u), fill(npx, 0u), offsets(npx + 1, 0u);
+  HaltonArgs a{};
+  a.tasks = tasks.data();
+  a.n_tasks = (uint32_t)tasks.size();
+  a.n_candidates = tasks.empty() ? 0 : tasks.back().first + tasks.back().wanted;
+  a.pix_index = index.data();
+  a.sx0 = smp->x_start;
+  a.sy0 = smp->y_start;
+  a.sw = smp->x_end - smp->x_start;
+  a.counts = counts.data();
+  a.fill = fill.data();
+  a.offsets = offsets.data();
+  for (unsigned long long g = 0; g < a.n_candidates; ++g) {
+    blockIdx.x = (unsigned)g;
+    k_halton_bin<0>(a);
+  }
+  unsigned long long total = 0;
+  for (size_t i = 0; i < npx; ++i) {
+    offsets[i] = (uint32_t)total;
+    total += counts[i];
+  }
+  offsets[npx] = (uint32_t)total;
+  std::memcpy(out_counts, counts.data(), npx * sizeof(uint32_t));
+  if (total > capacity) return total;
+  std::vector<uint32_t> idx(std::max<unsigned long long>(1, total));
+  a.idx = idx.data();
+  for (unsigned long long g = a.n_candidates; g-- > 0;) {  // reverse order: the per-pixel sort must restore index order
+    blockIdx.x = (unsigned)g;
+    k_halton_bin<1>(a);
+  }
+  std::vector<float2> img(std::max<unsigned long long>(1, total)), lens(img.size()), lu(std::max<size_t>(1, img.size() * (size_t)light_pairs));
+  std::vector<float> tm(img.size());
+  HaltonSampleArgs sa{};
+  sa.tasks = tasks.data();
+  sa.pixels = list.data();
+  sa.n_pixels = npx;
+  sa.offsets = offsets.data();
+  sa.idx = idx.data();
+  sa.img = img.data();
+  sa.lens = lens.data();
+  sa.time = tm.data();
+  sa.lightu = light_pairs ? lu.data() : nullptr;
+  sa.light_pairs = (uint32_t)light_pairs;
+  sa.edge = nullptr;
+  sa.sopen = smp->shutter_open;
+  sa.sclose = smp->shutter_close;
+  for (size_t li = 0; li < npx; ++li) {
+    blockIdx.x = (unsigned)li;
+    k_halton_samples(sa);
+  }
+  for (unsigned long long i = 0; i < total; ++i) {
+    out_cs5[5 * i] = img[i].x;
+    out_cs5[5 * i + 1] = img[i].y;
+    out_cs5[5 * i + 2] = lens[i].x;
+    out_cs5[5 * i + 3] = lens[i].y;
+    out_cs5[5 * i + 4] = tm[i];
+  }
+  if (light_pairs) std::memcpy(out_lightu, lu.data(), total * (size_t)light_pairs * sizeof(float2));
+  return total;
+}
+}

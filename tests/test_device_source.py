@@ -21,7 +21,7 @@ from pbrt_rust_b200.api import HostScene, Material, Primitive, Scene, Shape, Tex
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "devsrc", "shade_tex_host.cpp")
 LIB = os.path.join(HERE, "devsrc", "libdevsrc.so")
-DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "shade_mip.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "trace_core.cuh", "host_logic.hpp", "leaf_ref.h", "scene.cuh", "shade_math.cuh", "film_math.cuh", "film.cuh", "shade.cuh", "trace.cuh")] + \
+DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "shade_mip.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "trace_core.cuh", "host_logic.hpp", "leaf_ref.h", "scene.cuh", "shade_math.cuh", "film_math.cuh", "film.cuh", "shade.cuh", "trace.cuh", "raygen.cuh", "halton.cuh")] + \
     [os.path.join(HERE, "..", "include", "pbrtb200.h")]
 
 
@@ -65,6 +65,9 @@ def dev():
     L.devsrc_tri_surface.argtypes = [C.c_void_p] * 7 + [C.c_float] * 3 + [C.c_void_p] * 2
     L.devsrc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     L.devsrc_film_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.devsrc_raygen.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.devsrc_halton.restype = C.c_uint64
+    L.devsrc_halton.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.devsrc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p, C.c_void_p]
     return L
@@ -853,3 +856,67 @@ def test_device_source_renders_random_scenes_like_the_oracle(dev, orc):
             assert int(stats[0]) == ref["stats"]["camera_hits"] and int(stats[1]) == ref["stats"]["shadow_rays"]
             n += 1
     assert n >= 20
+
+
+def _sampler_desc(smp, num_tasks):
+    return _ffi.Sampler(smp.kind, smp.ext[0], smp.ext[1], smp.ext[2], smp.ext[3], smp.xs, smp.ys, int(smp.jitter),
+                        smp.sopen, smp.sclose, num_tasks)
+
+
+@pytest.mark.parametrize("kind,xs,ys,jitter,pairs", [("stratified", 2, 2, True, 0), ("stratified", 3, 2, True, 2),
+                                                     ("stratified", 4, 4, True, 1), ("stratified", 2, 1, False, 0),
+                                                     ("ld", 4, 1, True, 0), ("ld", 6, 1, True, 3)])
+def test_device_raygen_kernels_match_the_oracle(dev, orc, kind, xs, ys, jitter, pairs):
+    """k_raygen_groups and k_raygen_full, emulated thread by thread over a whole sampler extent with
+    the reference's task windows and per-task StdRng keys, against the oracle's get_more_samples:
+    image / lens / time samples and the light-sample floats bit for bit (stratified incl. the
+    lens / time shuffles, unjittered, LD with its scrambles and shuffles)."""
+    from pbrt_rust_b200.api import Sampler
+    cfg = scenes.config1(xres=37, yres=22)
+    e = cfg["sampler"].ext
+    smp = Sampler.stratified(e[0], e[1], e[2], e[3], xs, ys, jitter, 0.25, 0.75) if kind == "stratified" \
+        else Sampler.low_discrepancy(e[0], e[1], e[2], e[3], xs, 0.25, 0.75)
+    ocfg = orc.render_config(cfg["camera"], smp, num_cpus=8, mode=0)
+    ocfg.sopen, ocfg.sclose = 0.25, 0.75
+    lay = orc.layout(ocfg)
+    spp = smp.samples_per_pixel()
+    cs, _, _, lu = orc.camera_samples(ocfg, pairs, e[0], e[1], e[2], e[3], spp)
+    desc = _sampler_desc(smp, lay["num_tasks"])
+    npx = (e[1] - e[0]) * (e[3] - e[2])
+    for full in ([1] if kind == "ld" else [0, 1]):
+        got = np.zeros((npx * spp, 5), np.float32)
+        glu = np.zeros((npx * spp, max(1, 2 * pairs)), np.float32)
+        edge = np.zeros(npx, np.uint32)
+        dev.devsrc_raygen(C.byref(desc), pairs, C.byref(cfg["film"].desc), full, _p(got), _p(glu), _p(edge))
+        cols = slice(0, 5) if full else slice(0, 2)
+        assert np.array_equal(got[:, cols].view(np.uint32), cs[:, cols].view(np.uint32)), (full,)
+        if pairs:
+            assert np.array_equal(glu.view(np.uint32), lu.view(np.uint32))
+        # box filter of half a pixel: a sample leaves its own pixel only on exact pixel borders
+        assert edge.mean() < 0.2
+
+
+@pytest.mark.parametrize("spp,pairs,res", [(4, 0, (33, 21)), (7, 2, (28, 19))])
+def test_device_halton_kernels_match_the_oracle(dev, orc, spp, pairs, res):
+    """k_halton_bin<0>, the host scan, k_halton_bin<1> (run in REVERSE candidate order here, so that
+    only the per-pixel sort can put the samples back into generation order) and k_halton_samples,
+    emulated thread by thread, against the oracle's HaltonSampler: per-pixel counts, every camera
+    sample and the light-sample floats bit for bit."""
+    from pbrt_rust_b200.api import Sampler
+    cfg = scenes.config1(xres=res[0], yres=res[1])
+    e = cfg["sampler"].ext
+    smp = Sampler.halton(e[0], e[1], e[2], e[3], spp, 0.1, 0.9)
+    ocfg = orc.render_config(cfg["camera"], smp, num_cpus=8, mode=0)
+    ocfg.sopen, ocfg.sclose = 0.1, 0.9
+    cs, lu, counts = orc.halton_samples(ocfg, pairs)
+    desc = _sampler_desc(smp, orc.layout(ocfg)["num_tasks"])
+    total = int(counts.sum())
+    gc = np.zeros(counts.size, np.uint32)
+    got = np.zeros((total, 5), np.float32)
+    glu = np.zeros((total, max(1, 2 * pairs)), np.float32)
+    assert dev.devsrc_halton(C.byref(desc), pairs, _p(gc), _p(got), _p(glu), total) == total
+    assert np.array_equal(gc.reshape(counts.shape), counts)
+    valid = ~np.isnan(cs[..., 0])
+    assert np.array_equal(got.view(np.uint32), cs[valid].view(np.uint32))     # compact, pixel raster then generation order
+    if pairs:
+        assert np.array_equal(glu.view(np.uint32), lu[valid].view(np.uint32))
