@@ -1,7 +1,9 @@
-// TEST INFRASTRUCTURE ONLY.  Compiles the device source pbrt_rust_b200/csrc/shade_tex.cuh as host
-// code (PB_HOST_CHECK: no CUDA, intrinsics replaced by plain C++) so the CPU test-suite can run the
-// very arithmetic the GPU kernel executes against the oracle where no GPU exists.  The product
-// never loads this library.
+// TEST INFRASTRUCTURE ONLY.  Compiles the device source of pbrt_rust_b200/csrc/ (the *_math.cuh /
+// trace_core.cuh / shade*.cuh / film.cuh / raygen.cuh / halton.cuh headers, kernels included) as
+// host code: PB_HOST_CHECK replaces the few CUDA intrinsics and launch keywords by plain C++ and
+// runs a kernel as one emulated thread per block.  The CPU test-suite drives it against the oracle
+// where no GPU exists — single functions, whole kernels and whole frames.  The product never loads
+// this library.
 #define PB_HOST_CHECK 1
 #include "../../pbrt_rust_b200/csrc/shade_tex.cuh"
 #include "../../pbrt_rust_b200/csrc/shade_mip.cuh"

@@ -1,7 +1,7 @@
 """The device source of the texture stage, compiled for the host, against the oracle (CPU only).
 
 pbrt_rust_b200/csrc/shade_tex.cuh (mappings, noise, every texture kind except image lookups, bump
-mapping) is plain arithmetic; tests/devsrc/shade_tex_host.cpp compiles that very source with g++
+mapping) is plain arithmetic; tests/devsrc/device_source_host.cpp compiles that very source with g++
 (PB_HOST_CHECK) so its logic is checked here, where no GPU exists.  Texture tables come from the
 product's host mirror (the flatten shim), descriptions from scenes.TexGen; the oracle gets the same
 descriptions.  The `-m gpu` suite repeats the comparison on the device through whole renders.
@@ -19,7 +19,7 @@ from pbrt_rust_b200 import _ffi, scenes
 from pbrt_rust_b200.api import HostScene, Material, Primitive, Scene, Shape, Texture, Transform
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "devsrc", "shade_tex_host.cpp")
+SRC = os.path.join(HERE, "devsrc", "device_source_host.cpp")
 LIB = os.path.join(HERE, "devsrc", "libdevsrc.so")
 DEPS = [SRC] + [os.path.join(HERE, "..", "pbrt_rust_b200", "csrc", f) for f in ("shade_tex.cuh", "shade_mip.cuh", "dmath.cuh", "halton_math.cuh", "trace_math.cuh", "trace_core.cuh", "host_logic.hpp", "leaf_ref.h", "scene.cuh", "shade_math.cuh", "film_math.cuh", "film.cuh", "shade.cuh", "trace.cuh", "raygen.cuh", "halton.cuh")] + \
     [os.path.join(HERE, "..", "include", "pbrtb200.h")]
