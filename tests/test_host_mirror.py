@@ -84,6 +84,20 @@ def test_rust_ffi_is_generated_from_the_header():
     assert "size_of::<pbrtb200_texture>() == 120" in text and "size_of::<pbrtb200_scene>()" in text
 
 
+def test_host_check_mode_is_not_part_of_the_product():
+    """PB_HOST_CHECK (the host compilation of the device source used by tests/devsrc/) is never
+    defined by the product build, and libpbrtb200.so exports none of the harness's entry points."""
+    import subprocess
+    import __graft_entry__ as g
+    assert not any("PB_HOST_CHECK" in f for f in g.NVCC_FLAGS)
+    for root_, _, files in os.walk(os.path.join(ROOT, "pbrt_rust_b200")):
+        for f in files:
+            if f.endswith((".cu", ".cpp", ".py")):
+                assert "define PB_HOST_CHECK" not in open(os.path.join(root_, f), errors="ignore").read(), f
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", pb.LIB_PATH], text=True)
+    assert "devsrc_" not in syms and "orc_" not in syms
+
+
 def test_no_cpu_fallback_without_a_device():
     """On a box without CUDA the product must fail loudly, not fall back."""
     import torch
