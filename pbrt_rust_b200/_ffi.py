@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpbrtb200.so")
+# PBRTB200_LIB names an alternative build of the same library (A/B measurements of kernel variants
+# built by __graft_entry__.build_variant); the default is the product.
+LIB_PATH = os.environ.get("PBRTB200_LIB") or os.path.join(_HERE, "libpbrtb200.so")
 
 OK, EINVAL, ENODEV, ENAN, ESTACK, ESINGULAR, ENOMEM = 0, -1, -2, -3, -4, -5, -6
 MISS = 0xFFFFFFFF

@@ -15,6 +15,7 @@
 #include "halton.cuh"
 #include "shade.cuh"
 #include "trace.cuh"
+#include "trace_launch.h"
 
 static_assert(sizeof(pbrtb200_node32) == 32, "node32 layout");
 static_assert(sizeof(pbrtb200_tri48) == 48, "tri48 layout");
@@ -82,7 +83,7 @@ struct pbrtb200_ctx {
   bool shade_ext = false;  // the scene needs k_shade's general texture evaluator / bump mapping
   DScene sc{};
   std::vector<pbrtb200_light> h_lights;
-  DevBuf d_nodes, d_tris, d_leaf_prim, d_leaf_count, d_spheres, d_sphere_o2w, d_meshes, d_tri_uv,
+  DevBuf d_nodes, d_tris, d_leaf_prim, d_leaf_count, d_leaf_boxes, d_spheres, d_sphere_o2w, d_meshes, d_tri_uv,
       d_tri_n, d_tri_s, d_materials, d_mat_flags, d_textures, d_lights, d_area_tris, d_mipmaps, d_texels;
   std::vector<void*> peer_films;  // pbrtb200_peer_film_create allocations (freed at destroy)
   // per-frame work buffers (grow-only)
@@ -173,27 +174,21 @@ bool scene_needs_ext(const pbrtb200_scene* s) {
   return false;
 }
 
-int trace_grid(pbrtb200_ctx* ctx, const void* kernel) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PB_TRACE_THREADS, 0) !=
-          cudaSuccess ||
-      per_sm < 1)
-    per_sm = 4;
-  return ctx->sm_count * per_sm;
-}
-
-// Dispatch on (ANY, SPH, MULTI, SRC, MODE).  MODE = SIMT loop shape (trace.cuh); the defaults were
-// chosen from measurements (profiles/), PBRTB200_TRACE_MODE / PBRTB200_SHADOW_MODE override them.
-int env_mode(const char* name, int dflt, int max_mode) {
-  const char* v = std::getenv(name);
-  if (!v || !*v) return dflt;
-  const int m = std::atoi(v);
-  return (m >= 0 && m <= max_mode) ? m : dflt;
+// Box-test family of the traversal kernels (trace_core.cuh child_box): 3 = octant-specialised FFMA
+// tests for inner nodes + the reference's exact test in the leaf phase (default), 2 = exact tests
+// specialised per octant, 1 = exact min / max tests.  All three produce the same hits bit for bit;
+// PBRTB200_BOX selects one for A/B measurements.
+int trace_box_family() {
+  static const int box = [] {
+    const char* v = std::getenv("PBRTB200_BOX");
+    const int b = v && *v ? std::atoi(v) : 3;
+    return (b >= 1 && b <= 3) ? b : 3;
+  }();
+  return box;
 }
 
 template <bool ANY, int SRC>
 int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a_in) {
-  const DScene& sc = ctx->sc;
   // 32-ray packets a warp claims per work-counter atomic (same-address atomics retire at ~0.66 ns)
   static const int batch = [] {
     const char* v = std::getenv("PBRTB200_TRACE_BATCH");
@@ -202,30 +197,8 @@ int launch_trace_t(pbrtb200_ctx* ctx, const DCamera& cam, const TraceArgs& a_in)
   }();
   TraceArgs a = a_in;
   a.batch = (uint32_t)batch;
-  static const int mode_closest = env_mode("PBRTB200_TRACE_MODE", 1, 1);
-  static const int mode_any = env_mode("PBRTB200_SHADOW_MODE", 2, 3);  // 2, 3: unordered (trace.cuh)
-  const int mode = ANY ? mode_any : mode_closest;
-#define PB_LAUNCH(SPH, MULTI, MODE)                                                        \
-  {                                                                                        \
-    auto kfn = k_trace<ANY, SPH, MULTI, SRC, MODE>;                                        \
-    const int grid = trace_grid(ctx, (const void*)kfn);                                    \
-    kfn<<<grid, PB_TRACE_THREADS, 0, ctx->stream>>>(sc, cam, a);                           \
-  }
-#define PB_LAUNCH_M(SPH, MULTI)                                                            \
-  {                                                                                        \
-    if (mode == 0) PB_LAUNCH(SPH, MULTI, 0) else if (mode == 1) PB_LAUNCH(SPH, MULTI, 1)   \
-    else if constexpr (ANY) {                                                              \
-      if (mode == 2) PB_LAUNCH(SPH, MULTI, 2) else PB_LAUNCH(SPH, MULTI, 3)            \
-    }                                                                                      \
-  }
-  if (ctx->has_spheres) {
-    if (ctx->multi_leaf) PB_LAUNCH_M(true, true) else PB_LAUNCH_M(true, false)
-  } else {
-    if (ctx->multi_leaf) PB_LAUNCH_M(false, true) else PB_LAUNCH_M(false, false)
-  }
-#undef PB_LAUNCH_M
-#undef PB_LAUNCH
-  CK(cudaGetLastError());
+  TraceLaunchCfg cfg{ctx->stream, ctx->sm_count, ctx->has_spheres, ctx->multi_leaf};
+  CK(pb_launch_trace(ANY, SRC, trace_box_family(), cfg, ctx->sc, cam, a));
   return 0;
 }
 
@@ -569,7 +542,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   ctx->list_key.valid = false;
   if (s->n_nodes == 0 || !s->nodes) FAIL(PBRTB200_EINVAL, "scene has no BVH nodes");
   if (s->n_prims == 0) FAIL(PBRTB200_EINVAL, "scene has no primitives");
-  if (s->n_prims > PB_LEAF_OFF_MASK) FAIL(PBRTB200_EINVAL, "too many primitives (limit 134217727)");
+  if (s->n_prims > PB_LEAF_OFF_MASK - 16u) FAIL(PBRTB200_EINVAL, "too many primitives (limit 134217711)");
   if (s->n_spheres && (!s->leaf_prim || !s->spheres || !s->sphere_o2w))
     FAIL(PBRTB200_EINVAL, "spheres need leaf_prim, spheres and sphere_o2w");
   if (!s->n_spheres && s->n_tris != s->n_prims && !s->leaf_prim)
@@ -583,7 +556,24 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   static_assert(sizeof(pbh::F4) == sizeof(float4), "pair-node quads are float4");
   const std::vector<pbh::F4>& pairs = pn.pairs;
   const std::vector<uint16_t>& leaf_count = pn.leaf_count;
-  const bool multi = pn.multi, big_leaf = pn.big_leaf;
+  bool multi = pn.multi;
+  const bool big_leaf = pn.big_leaf;
+  // The FFMA kernels apply the reference's exact test of a leaf's box in the leaf phase.  For a leaf
+  // that is one triangle the box is recomputed from the vertices (mesh.rs:197-204) — if the caller's
+  // node array agrees (+0 == -0); otherwise, and for quadrics / multi-primitive leaves, the stored
+  // boxes are read from memory (the MULTI kernel variants).
+  if (!multi && !(s->n_spheres > 0 || s->leaf_prim) && s->tris) {
+    for (uint32_t i = 0; i < s->n_nodes && !multi; ++i) {
+      const pbrtb200_node32& nd = s->nodes[i];
+      if (!nd.is_leaf) continue;
+      const pbrtb200_tri48& t = s->tris[nd.offset];
+      const float* v[3] = {t.p1, t.p2, t.p3};
+      for (int a = 0; a < 3; ++a) {
+        const float lo = std::fmin(std::fmin(v[0][a], v[1][a]), v[2][a]), hi = std::fmax(std::fmax(v[0][a], v[1][a]), v[2][a]);
+        if (!(lo == nd.bmin[a]) || !(hi == nd.bmax[a])) multi = true;
+      }
+    }
+  }
 
   // ---- validation of the shading tables ----
   for (uint32_t i = 0; i < s->n_materials; ++i) {
@@ -633,6 +623,8 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   const bool need_leaf_prim = s->n_spheres > 0 || (s->leaf_prim != nullptr);
   if (need_leaf_prim && upload(ctx, ctx->d_leaf_prim, s->leaf_prim, s->n_prims)) return PBRTB200_ENODEV;
   if (big_leaf && upload(ctx, ctx->d_leaf_count, leaf_count.data(), leaf_count.size())) return PBRTB200_ENODEV;
+  const bool need_leaf_boxes = multi || need_leaf_prim;
+  if (need_leaf_boxes && upload(ctx, ctx->d_leaf_boxes, pn.leaf_boxes.data(), pn.leaf_boxes.size())) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_spheres, s->spheres, s->n_spheres)) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_sphere_o2w, s->sphere_o2w, 12ull * s->n_spheres)) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_meshes, s->meshes, s->n_meshes)) return PBRTB200_ENODEV;
@@ -664,6 +656,7 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   sc.tris = ctx->d_tris.as<float4>();
   sc.leaf_prim = need_leaf_prim ? ctx->d_leaf_prim.as<uint32_t>() : nullptr;
   sc.leaf_count = big_leaf ? ctx->d_leaf_count.as<uint16_t>() : nullptr;
+  sc.leaf_boxes = need_leaf_boxes ? ctx->d_leaf_boxes.as<float4>() : nullptr;
   sc.spheres = ctx->d_spheres.as<pbrtb200_sphere80>();
   sc.sphere_o2w = ctx->d_sphere_o2w.as<float>();
   sc.meshes = ctx->d_meshes.as<pbrtb200_mesh>();
@@ -688,7 +681,10 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* s) {
   for (int i = 0; i < 3; ++i) {
     sc.root_bmin[i] = pn.root_bmin[i];
     sc.root_bmax[i] = pn.root_bmax[i];
+    sc.babs[i] = pn.babs[i];
   }
+  sc.boxes_finite = pn.boxes_finite ? 1u : 0u;
+  sc.boxes_ordered = pn.boxes_ordered ? 1u : 0u;
   ctx->has_spheres = need_leaf_prim;
   ctx->multi_leaf = multi;
 

@@ -86,6 +86,10 @@ struct F4 {  // layout of CUDA's float4
 struct PairNodes {
   std::vector<F4> pairs;             // 4 per inner node
   std::vector<uint16_t> leaf_count;  // per primitive offset: primitives of the leaf starting there
+  std::vector<F4> leaf_boxes;        // 2 per primitive offset: box of the leaf starting there (min, max)
+  float babs[3] = {0.f, 0.f, 0.f};   // max |coordinate| over all node boxes
+  bool boxes_finite = true;          // no inf / NaN box coordinate
+  bool boxes_ordered = true;         // min <= max on every axis of every box
   bool multi = false;                // some leaf holds more than one primitive
   bool big_leaf = false;             // some leaf holds >= 16 (count does not fit the inline field)
   uint32_t root_ref = 0;
@@ -98,7 +102,17 @@ inline const char* build_pair_nodes(const pbrtb200_node32* nodes, uint32_t nn, u
   for (uint32_t i = 0; i < nn; ++i)
     if (!nodes[i].is_leaf) pair_index[i] = n_inner++;
   out->leaf_count.assign(n_prims, 0);
+  out->leaf_boxes.assign(2ull * n_prims, F4{0.f, 0.f, 0.f, 0.f});
   out->multi = out->big_leaf = false;
+  out->boxes_finite = out->boxes_ordered = true;
+  out->babs[0] = out->babs[1] = out->babs[2] = 0.f;
+  for (uint32_t i = 0; i < nn; ++i)
+    for (int a = 0; a < 3; ++a) {
+      const float lo = nodes[i].bmin[a], hi = nodes[i].bmax[a];
+      if (!std::isfinite(lo) || !std::isfinite(hi)) out->boxes_finite = false;
+      if (!(lo <= hi)) out->boxes_ordered = false;
+      out->babs[a] = std::max(out->babs[a], std::max(std::fabs(lo), std::fabs(hi)));
+    }
   uint64_t covered = 0;
   auto leaf_ref = [](const pbrtb200_node32& nd) {
     return PB_LEAF_BIT | ((std::min<uint32_t>(nd.count, 16u) - 1u) << PB_LEAF_CNT_SHIFT) | nd.offset;
@@ -121,6 +135,8 @@ inline const char* build_pair_nodes(const pbrtb200_node32* nodes, uint32_t nn, u
       if (nd.count == 0 || (uint64_t)nd.offset + nd.count > n_prims)
         return "leaf node range outside the primitive list";
       out->leaf_count[nd.offset] = nd.count;
+      out->leaf_boxes[2ull * nd.offset] = F4{nd.bmin[0], nd.bmin[1], nd.bmin[2], 0.f};
+      out->leaf_boxes[2ull * nd.offset + 1] = F4{nd.bmax[0], nd.bmax[1], nd.bmax[2], 0.f};
       if (nd.count > 1) out->multi = true;
       if (nd.count >= 16) out->big_leaf = true;
       covered += nd.count;
@@ -138,7 +154,8 @@ inline const char* build_pair_nodes(const pbrtb200_node32* nodes, uint32_t nn, u
     F4 m{0.f, 0.f, 0.f, 0.f};
     std::memcpy(&m.x, &r0, 4);
     std::memcpy(&m.y, &r1, 4);
-    const uint32_t ax = nd.axis;
+    const uint32_t ax = nd.axis, ax_bit = 1u << nd.axis;
+    std::memcpy(&m.z, &ax_bit, 4);
     std::memcpy(&m.w, &ax, 4);
     q[3] = m;
   }

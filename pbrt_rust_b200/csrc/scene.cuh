@@ -14,7 +14,7 @@
 //   q0 = (c0.min.x, c0.min.y, c0.min.z, c0.max.x)
 //   q1 = (c0.max.y, c0.max.z, c1.min.x, c1.min.y)
 //   q2 = (c1.min.z, c1.max.x, c1.max.y, c1.max.z)
-//   q3 = bits(ref0, ref1, unused, axis)
+//   q3 = bits(ref0, ref1, 1 << axis, axis)
 // c0 is the reference's first child (node i+1), c1 its second child (second_child_offset).
 // ref: bit31 = 0 -> index of another pair node; bit31 = 1 -> leaf, low 31 bits = prim_offset into
 // the ordered primitive list plus an inline primitive count (see PB_LEAF_CNT_SHIFT).
@@ -23,6 +23,10 @@ struct DScene {
   const float4* __restrict__ tris;            // 3 x float4 per triangle (pbrtb200_tri48)
   const uint32_t* __restrict__ leaf_prim;     // NULL when the scene has no spheres (prim i == tri i)
   const uint16_t* __restrict__ leaf_count;    // NULL when every leaf holds exactly one primitive
+  const float4* __restrict__ leaf_boxes;      // 2 x float4 per primitive offset: the box of the leaf that
+                                              // starts there, as the reference stores it (min.xyz, max.xyz);
+                                              // NULL when every leaf is one triangle whose box equals the
+                                              // bounds of its vertices (checked at upload)
   const pbrtb200_sphere80* __restrict__ spheres;
   const float* __restrict__ sphere_o2w;
   const pbrtb200_mesh* __restrict__ meshes;
@@ -41,6 +45,9 @@ struct DScene {
   uint32_t light_slots;        // sum over lights of (area ? num_samples : 1)
   uint32_t area_sample_pairs;  // sum over area lights of num_samples (RNG pairs per camera sample)
   float root_bmin[3], root_bmax[3];
+  float babs[3];           // max |coordinate| over every node box, per axis (BOX 3 error bound)
+  uint32_t boxes_finite;   // every node box coordinate is finite (else: compare-and-swap tests only)
+  uint32_t boxes_ordered;  // every node box has min <= max on every axis (octant-specialised tests)
 };
 
 struct DCamera {

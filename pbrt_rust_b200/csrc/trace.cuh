@@ -43,13 +43,16 @@ struct TraceArgs {
   uint32_t spp;
 };
 
-template <bool ANY, bool SPH, bool MULTI, int SRC, int MODE>
-__global__ void __launch_bounds__(PB_TRACE_THREADS)
+#ifndef PB_TRACE_MIN_BLOCKS
+#define PB_TRACE_MIN_BLOCKS(ANY) ((ANY) ? 10 : 9)
+#endif
+template <bool ANY, bool SPH, bool MULTI, int SRC, int MODE, int BOX>
+__global__ void __launch_bounds__(PB_TRACE_THREADS, PB_TRACE_MIN_BLOCKS(ANY))
 k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
-  __shared__ uint32_t sh_ref[PB_SM_STACK * PB_TRACE_THREADS];
-  __shared__ float sh_t0[ANY ? 1 : PB_SM_STACK * PB_TRACE_THREADS];  // any-hit keeps no T0
-  uint32_t* s_ref = sh_ref + threadIdx.x;
-  float* s_t0 = ANY ? sh_t0 : sh_t0 + threadIdx.x;
+  // child refs, then (closest hit only: any-hit keeps no T0) the entry distances
+  __shared__ uint32_t sh_stack[(ANY ? 1 : 2) * PB_SM_STACK * PB_TRACE_THREADS];
+  uint32_t* s_ref = sh_stack + threadIdx.x;
+  float* s_t0 = reinterpret_cast<float*>(s_ref + (ANY ? 0 : PB_SM_STACK * PB_TRACE_THREADS));
   const int lane = threadIdx.x & 31;
   const uint64_t n = a.n_dyn ? (uint64_t)(*a.n_dyn) : a.n;
   if (a.shadow_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.shadow_total, (unsigned long long)n);
@@ -86,8 +89,11 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
         mint = 0.0f;         // ray.rs:30-38 Ray::new_with(.., start = 0)
         maxt = PB_F32_MAX;
       }
-      TraceResult r = trace_ray<ANY, SPH, MULTI, MODE>(sc, o, d, mint, maxt, s_ref, s_t0);
-      if (r.overflow) atomicOr(a.flags, 1u);
+      TraceResult r = trace_ray<ANY, SPH, MULTI, MODE, BOX>(sc, o, d, mint, maxt, s_ref, s_t0);
+      if (r.prim == PB_OVERFLOW) {
+        atomicOr(a.flags, 1u);
+        r.prim = PBRTB200_MISS;
+      }
       if (ANY) {
         const bool occ = r.prim != PBRTB200_MISS;
         if (a.occluded) a.occluded[idx] = occ ? 1 : 0;

@@ -70,17 +70,131 @@ PB_DEV bool sphere_hit(const pbrtb200_sphere80* __restrict__ sp, f3 ow, f3 dw, f
 }
 
 struct TraceResult {
-  uint32_t prim;
+  uint32_t prim;  // PBRTB200_MISS, PB_OVERFLOW (the stack overflowed: result invalid) or the hit
   float t, b1, b2;
-  bool overflow;
 };
+#define PB_OVERFLOW 0xFFFFFFFEu
 
 #define PB_DONE 0xFFFFFFFFu  // traversal finished (has the leaf bit set, so it leaves the node loop)
+#define PB_DONE_OVF 0xFFFFFFFEu  // ... because the stack overflowed (no leaf ref: n_prims < 2^27 - 16)
+
+// Per-ray constants of the box tests.
+struct RayBox {
+  f3 o, inv;    // exact tests: (plane - o) * inv, bbox.rs:190-193
+  f3 ncn, ncf;  // BOX 3 only: t_near = fma(plane, inv, ncn), t_far = fma(plane, inv, ncf)
+};
+
+// The box test of one child, selected at compile time.
+//   BOX 0  bbox.rs:185-209 literally (compare + swap): reproduces the reference's NaN behaviour for
+//          rays with a zero direction component.
+//   BOX 1  the same values through min / max (every 1/d finite, box coordinates finite).
+//   BOX 2  BOX 1 specialised for the ray's octant OCT (bit a = 1/d[a] < 0): with bmin <= bmax the
+//          products (bmin - o) * inv and (bmax - o) * inv are ordered by the sign of inv alone
+//          (rounding is monotonic), so the swap of bbox.rs:194-196 is decided at compile time and the
+//          six per-axis min / max disappear.  Same values as BOX 1, bit for bit.
+//   BOX 3  CONSERVATIVE test for inner nodes: one FFMA per plane, t = plane * inv - (o * inv -/+ e),
+//          where e bounds the rounding difference to the reference's (plane - o) * inv for every
+//          plane inside the scene bounds (trace_ray computes it per ray).  It passes whenever the
+//          reference's test passes (T0c <= T0, Fc >= F), possibly more often.  By the containment
+//          lemma (DESIGN.md "Traversal") which leaves are visited, and in which order, is decided by
+//          each leaf's own exact test, which BOX 3 applies in the leaf phase to every primitive that
+//          reports a hit; inner tests may be any superset.
+template <int BOX, int OCT>
+PB_DEV bool child_box(const RayBox& rb, float ax, float ay, float az, float bx, float by, float bz,
+                      float mint, float maxt, float* T0) {
+  if (BOX == 0) return slab_test(ax, ay, az, bx, by, bz, rb.o, rb.inv, mint, maxt, T0);
+  if (BOX == 1) return slab_test_finite(ax, ay, az, bx, by, bz, rb.o, rb.inv, mint, maxt, T0);
+  const float nx = (OCT & 1) ? bx : ax, fx = (OCT & 1) ? ax : bx;
+  const float ny = (OCT & 2) ? by : ay, fy = (OCT & 2) ? ay : by;
+  const float nz = (OCT & 4) ? bz : az, fz = (OCT & 4) ? az : bz;
+  float tnx, tny, tnz, tfx, tfy, tfz;
+  if (BOX == 2) {
+    tnx = (nx - rb.o.x) * rb.inv.x;
+    tfx = (fx - rb.o.x) * rb.inv.x;
+    tny = (ny - rb.o.y) * rb.inv.y;
+    tfy = (fy - rb.o.y) * rb.inv.y;
+    tnz = (nz - rb.o.z) * rb.inv.z;
+    tfz = (fz - rb.o.z) * rb.inv.z;
+  } else {
+    tnx = fmaf(nx, rb.inv.x, rb.ncn.x);
+    tfx = fmaf(fx, rb.inv.x, rb.ncf.x);
+    tny = fmaf(ny, rb.inv.y, rb.ncn.y);
+    tfy = fmaf(fy, rb.inv.y, rb.ncf.y);
+    tnz = fmaf(nz, rb.inv.z, rb.ncn.z);
+    tfz = fmaf(fz, rb.inv.z, rb.ncf.z);
+  }
+  const float t0 = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, mint));
+  const float t1 = fminf(fminf(tfx, tfy), fminf(tfz, maxt));
+  *T0 = t0;
+  return !(t0 > t1);
+}
+
+// The traversal stack of one thread: PB_SM_STACK entries in shared memory (conflict-free
+// [depth][lane] layout: entry k of a thread lives PB_TRACE_THREADS words after entry k - 1), deeper
+// entries in local memory.  An entry is a child ref, plus (closest hit only) the child's entry
+// distance T0 for the re-check at pop.  On the device the stack pointer IS the shared-memory byte
+// address of the next free entry, so a push / pop is one add and one or two STS / LDS with an
+// immediate offset — no index arithmetic (the kernels are bound by instruction issue).
+template <bool ANY>
+struct TStack {
+#ifdef PB_HOST_CHECK
+  uint32_t* s_ref;
+  float* s_t0;
+  int sp;
+  PB_DEV void init(uint32_t* ref, float* t0) {
+    s_ref = ref;
+    s_t0 = t0;
+    sp = 0;
+  }
+  PB_DEV bool empty() const { return sp == 0; }
+  PB_DEV int depth() const { return sp; }
+  PB_DEV bool in_shared() const { return sp < PB_SM_STACK; }
+  PB_DEV void put(uint32_t r, float t0) {
+    s_ref[sp * PB_TRACE_THREADS] = r;
+    if (!ANY) s_t0[sp * PB_TRACE_THREADS] = t0;
+  }
+  PB_DEV void get(uint32_t* r, float* t0) const {
+    *r = s_ref[sp * PB_TRACE_THREADS];
+    if (!ANY) *t0 = s_t0[sp * PB_TRACE_THREADS];
+  }
+  PB_DEV void up() { ++sp; }
+  PB_DEV void down() { --sp; }
+#else
+  static constexpr uint32_t kStep = 4u * PB_TRACE_THREADS;           // bytes between entries
+  static constexpr uint32_t kT0 = 4u * PB_SM_STACK * PB_TRACE_THREADS;  // T0 array follows the refs
+  uint32_t top;  // shared-window byte address of the next free entry (while sp <= PB_SM_STACK)
+  int sp;        // entries on the stack (limit checks only; the address is never derived from it)
+  PB_DEV void init(uint32_t* ref, float*) {  // (s_t0 == s_ref + PB_SM_STACK * PB_TRACE_THREADS)
+    top = (uint32_t)__cvta_generic_to_shared(ref);
+    sp = 0;
+  }
+  PB_DEV bool empty() const { return sp == 0; }
+  PB_DEV int depth() const { return sp; }
+  PB_DEV bool in_shared() const { return sp < PB_SM_STACK; }
+  PB_DEV void put(uint32_t r, float t0) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(top), "r"(r) : "memory");
+    if (!ANY) asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(top), "f"(t0), "n"(kT0) : "memory");
+  }
+  PB_DEV void get(uint32_t* r, float* t0) const {
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(*r) : "r"(top) : "memory");
+    if (!ANY) asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(*t0) : "r"(top), "n"(kT0) : "memory");
+  }
+  PB_DEV void up() {
+    top += kStep;
+    ++sp;
+  }
+  PB_DEV void down() {
+    top -= kStep;
+    --sp;
+  }
+#endif
+};
 
 // One ray through the pair-node BVH.  s_ref / s_t0 point at this thread's column of the shared
-// stack (stride PB_TRACE_THREADS).  ANY: stop at the first accepted hit (VisibilityTester).
-// FINITE: every component of 1/d is finite (the common case; selects the cheaper slab test).
-// MODE selects the SIMT loop shape (both visit the same leaves in the same order):
+// stack (stride PB_TRACE_THREADS; s_t0 == s_ref + PB_SM_STACK * PB_TRACE_THREADS).  ANY: stop at
+// the first accepted hit (VisibilityTester).
+// BOX / OCT: the box test (child_box).  MODE selects the SIMT loop shape (all visit the same leaves
+// in the same order):
 //   0  if-if        : each iteration a lane does one node step OR one leaf        (best for any-hit)
 //   1  while-while  : lanes run node steps until every lane of the warp holds a leaf (best closest)
 //   2, 3 (ANY only) : shapes 0 / 1 without the near/far child ordering.  An any-hit query is a
@@ -90,41 +204,39 @@ struct TraceResult {
 // Measured and dropped (profiles/r01_notes.md): speculative postponed-leaf traversal (no gain) and a
 // persistent kernel with per-lane ray refill (-30..-70 %: refilled lanes lose ray coherence), and a
 // warp-cooperative any-hit kernel with subtree stealing between lanes (-18 %).
-template <bool ANY, bool SPH, bool MULTI, bool FINITE, int MODE>
-PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, float maxt,
+template <bool ANY, bool SPH, bool MULTI, int BOX, int MODE, int OCT>
+PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, float mint, float maxt,
                             uint32_t* s_ref, float* s_t0) {
-  constexpr int stride = PB_TRACE_THREADS;
   constexpr bool UNORDERED = ANY && MODE >= 2;
   constexpr int SHAPE = MODE & 1;
+  constexpr bool LEAF_EXACT = BOX == 3;  // inner tests are conservative: exact leaf test in the leaf phase
   TraceResult res;
   res.prim = PBRTB200_MISS;
   res.t = 0.f;
   res.b1 = 0.f;
   res.b2 = 0.f;
-  res.overflow = false;
-  // bvh.rs:382-383
-  const bool neg0 = inv.x < 0.0f, neg1 = inv.y < 0.0f, neg2 = inv.z < 0.0f;
   uint32_t l_ref[PB_LM_STACK];
   float l_t0[PB_LM_STACK];
-  int sp = 0;
+  TStack<ANY> st;
+  st.init(s_ref, s_t0);
   auto box = [&](float ax, float ay, float az, float bx, float by, float bz, float* T0) {
-    return FINITE ? slab_test_finite(ax, ay, az, bx, by, bz, o, inv, mint, maxt, T0)
-                  : slab_test(ax, ay, az, bx, by, bz, o, inv, mint, maxt, T0);
+    return child_box<BOX, OCT>(rb, ax, ay, az, bx, by, bz, mint, maxt, T0);
   };
   // pop the next stack entry that still passes the reference's box test at pop (live maxt).
   // ANY: an any-hit query returns at its first accepted hit, so maxt never shrinks while entries
   // are on the stack; every pushed entry passed with this very maxt and T0 need not be kept.
+  // (BOX 3: the kept T0 is the conservative one, T0c <= T0: the re-check stays a superset.)
   auto pop = [&]() -> uint32_t {
-    while (sp > 0) {
-      --sp;
+    while (!st.empty()) {
+      st.down();
       uint32_t r;
       float t0 = 0.f;
-      if (sp < PB_SM_STACK) {
-        r = s_ref[sp * stride];
-        if (!ANY) t0 = s_t0[sp * stride];
+      if (st.in_shared()) {
+        st.get(&r, &t0);
       } else {
-        r = l_ref[sp - PB_SM_STACK];
-        if (!ANY) t0 = l_t0[sp - PB_SM_STACK];
+        const int k = st.depth() - PB_SM_STACK;
+        r = l_ref[k];
+        if (!ANY) t0 = l_t0[k];
       }
       if (ANY || !(t0 > maxt)) return r;
     }
@@ -138,29 +250,34 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
     const bool h0 = box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &T00);
     const bool h1 = box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &T01);
     const uint32_t r0 = __float_as_uint(q3.x), r1 = __float_as_uint(q3.y);
-    if (h0 & h1) {
-      // bvh.rs:409-415: dir_is_neg[axis] -> the second child is visited first
+    if (h0) {
+      if (!h1) return r0;
+      // both pass.  bvh.rs:409-415: dir_is_neg[axis] -> the second child is visited first
       bool neg = false;
       if (!UNORDERED) {
-        const uint32_t axis = __float_as_uint(q3.w);
-        neg = axis == 0 ? neg0 : (axis == 1 ? neg1 : neg2);
+        if (BOX >= 2) {
+          neg = (__float_as_uint(q3.z) & (uint32_t)OCT) != 0u;  // q3.z = 1 << axis
+        } else {
+          const uint32_t axis = __float_as_uint(q3.w);
+          neg = axis == 0 ? rb.inv.x < 0.0f : (axis == 1 ? rb.inv.y < 0.0f : rb.inv.z < 0.0f);  // bvh.rs:382-383
+        }
       }
       const uint32_t far_ref = neg ? r0 : r1;
       const float far_t0 = neg ? T00 : T01;
-      if (sp < PB_SM_STACK) {
-        s_ref[sp * stride] = far_ref;
-        if (!ANY) s_t0[sp * stride] = far_t0;
-      } else if (sp < PBRTB200_STACK_DEPTH) {
-        l_ref[sp - PB_SM_STACK] = far_ref;
-        if (!ANY) l_t0[sp - PB_SM_STACK] = far_t0;
+      if (st.in_shared()) {
+        st.put(far_ref, far_t0);
       } else {
-        res.overflow = true;
-        return PB_DONE;
+        const int k = st.depth() - PB_SM_STACK;
+        if (k >= PB_LM_STACK) {
+          return PB_DONE_OVF;
+        }
+        l_ref[k] = far_ref;
+        if (!ANY) l_t0[k] = far_t0;
       }
-      ++sp;
+      st.up();
       return neg ? r1 : r0;
     }
-    if (h0 | h1) return h0 ? r0 : r1;
+    if (h1) return r1;
     return pop();
   };
   // bvh.rs:398-405: every primitive of the leaf in order; the last accepted hit wins.
@@ -172,19 +289,38 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
       cnt = ((ref >> PB_LEAF_CNT_SHIFT) & 0xFu) + 1u;  // 1..15 inline; 16 = look it up
       if (cnt == 16u) cnt = (uint32_t)__ldg(&sc.leaf_count[off]);
     }
+    int leaf_ok = -1;  // LEAF_EXACT: the reference's test of this leaf's box (bvh.rs:393), evaluated
+                       // lazily with the maxt the leaf was entered with — no hit, no test
     for (uint32_t i = 0; i < cnt; ++i) {
       const uint32_t pi = off + i;
       uint32_t pr = SPH ? __ldg(&sc.leaf_prim[pi]) : pi;
       bool hit;
       float t, b1, b2 = 0.f;
+      float4 a, b, c;
       if (SPH && (pr & PB_LEAF_BIT)) {
         hit = sphere_hit(sc.spheres + (pr & ~PB_LEAF_BIT), o, d, mint, maxt, &t, &b1);
       } else {
         const float4* tp = sc.tris + 3ull * pr;
-        const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+        a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
         hit = tri_hit(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), o, d, mint,
                       maxt, &t, &b1, &b2);
       }
+      if (LEAF_EXACT && hit && leaf_ok < 0) {
+        // maxt is still the value the leaf was entered with: this is the first hit inside it
+        float T0;
+        if (SPH || MULTI) {  // the leaf's own box as the reference stores it
+          const float4 lo = ldg4(sc.leaf_boxes + 2ull * off), hi = ldg4(sc.leaf_boxes + 2ull * off + 1);
+          leaf_ok = slab_test_finite(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, rb.o, rb.inv, mint, maxt, &T0) ? 1 : 0;
+        } else {  // single-triangle leaf: mesh.rs:197-204, the bounds of its three vertices
+          leaf_ok = slab_test_finite(fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y),
+                                     fminf(fminf(a.z, b.z), c.z), fmaxf(fmaxf(a.x, b.x), c.x),
+                                     fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z), rb.o,
+                                     rb.inv, mint, maxt, &T0)
+                        ? 1
+                        : 0;
+        }
+      }
+      if (LEAF_EXACT && leaf_ok == 0) return false;  // the reference never enters this leaf
       if (hit) {
         maxt = t;  // geometric.rs:64
         res.prim = pi;
@@ -203,7 +339,7 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
     return res;
   uint32_t cur = sc.root_ref;
   if (SHAPE == 0) {
-    while (cur != PB_DONE) {
+    while (cur < PB_DONE_OVF) {
       if (!(cur & PB_LEAF_BIT)) {
         cur = node_step(cur);
       } else {
@@ -214,22 +350,70 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, f3 inv, float mint, fl
   } else {
     for (;;) {
       while (!(cur & PB_LEAF_BIT)) cur = node_step(cur);
-      if (cur == PB_DONE) break;
+      if (cur >= PB_DONE_OVF) break;
       if (leaf(cur)) return res;
       cur = pop();
     }
   }
+  if (cur == PB_DONE_OVF) res.prim = PB_OVERFLOW;
   return res;
 }
 
-template <bool ANY, bool SPH, bool MULTI, int MODE>
-PB_DEV TraceResult trace_ray(const DScene& sc, f3 o, f3 d, float mint, float maxt, uint32_t* s_ref,
-                             float* s_t0) {
-  const f3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);  // bvh.rs:382
-  const float big = fmaxf(fmaxf(fabsf(inv.x), fabsf(inv.y)), fabsf(inv.z));
-  // (NaN-propagating test: a NaN or infinite component takes the exact-compare path)
-  if (big < __int_as_float(0x7f800000) && inv.x == inv.x && inv.y == inv.y && inv.z == inv.z)
-    return traverse<ANY, SPH, MULTI, true, MODE>(sc, o, d, inv, mint, maxt, s_ref, s_t0);
-  return traverse<ANY, SPH, MULTI, false, 0>(sc, o, d, inv, mint, maxt, s_ref, s_t0);
+// BOX 3 constants.  Reference value r = fl(fl(p - o) * inv); ours f = fl(p * inv - c), c = fl(o * inv).
+// With u = 2^-24 and every plane |p| <= B (the scene bound on that axis):
+//   |r - x| <= (2u + u^2) |x|,  |f - x| <= u |o inv| (1 + u) + u |x|,  x = (p - o) inv,  |x| <= (B + |o|) |inv|
+// so |f - r| < 4.1 u (B + |o|) |inv|.  e = 16 u (B + |o|) |inv| + FLT_MIN also covers the rounding of
+// c -/+ e itself and results in the subnormal range.  Returns false when the bound is not usable
+// (overflow); the caller then takes an exact path.
+PB_DEV bool ffma_constants(const DScene& sc, f3 o, f3 inv, RayBox* rb) {
+  const float k = 9.5367431640625e-07f;  // 2^-20
+  const float tiny = 1.17549435e-38f;
+  const float mx = (sc.babs[0] + fabsf(o.x)) * fabsf(inv.x), my = (sc.babs[1] + fabsf(o.y)) * fabsf(inv.y),
+              mz = (sc.babs[2] + fabsf(o.z)) * fabsf(inv.z);
+  if (!(fmaxf(fmaxf(mx, my), mz) < 1.2676506e30f)) return false;  // 2^100 (also rejects NaN)
+  const float ex = mx * k + tiny, ey = my * k + tiny, ez = mz * k + tiny;
+  const float cx = o.x * inv.x, cy = o.y * inv.y, cz = o.z * inv.z;
+  rb->ncn = mk3(-(cx + ex), -(cy + ey), -(cz + ez));
+  rb->ncf = mk3(-(cx - ex), -(cy - ey), -(cz - ez));
+  return true;
 }
 
+// BOX: the box test the kernel variant was built for (1, 2 or 3; see child_box).  Rays it cannot
+// serve take an exact fall-back inside the same kernel: a zero / NaN direction component -> BOX 0
+// (the reference's compare-and-swap, NaN-faithful); BOX 2 / 3 need the warp's rays in ONE octant
+// (the specialised loops are selected by a switch: lanes in different octants would run one after
+// the other), a warp that mixes octants runs BOX 1 together.
+template <bool ANY, bool SPH, bool MULTI, int MODE, int BOX = 1>
+PB_DEV TraceResult trace_ray(const DScene& sc, f3 o, f3 d, float mint, float maxt, uint32_t* s_ref,
+                             float* s_t0) {
+  RayBox rb;
+  rb.o = o;
+  rb.inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);  // bvh.rs:382
+  rb.ncn = rb.ncf = mk3(0.f, 0.f, 0.f);
+  const f3 inv = rb.inv;
+  const float big = fmaxf(fmaxf(fabsf(inv.x), fabsf(inv.y)), fabsf(inv.z));
+  // (NaN-propagating test: a NaN or infinite component takes the exact-compare path)
+  const bool finite = big < __int_as_float(0x7f800000) && inv.x == inv.x && inv.y == inv.y && inv.z == inv.z;
+  if (!finite || !sc.boxes_finite) return traverse<ANY, SPH, MULTI, 0, 0, 0>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
+  if (BOX >= 2 && sc.boxes_ordered) {
+    bool ok = true;
+    if (BOX == 3) ok = ffma_constants(sc, o, inv, &rb);
+    const uint32_t oct = (inv.x < 0.0f ? 1u : 0u) | (inv.y < 0.0f ? 2u : 0u) | (inv.z < 0.0f ? 4u : 0u);
+    int same = 0;
+    __match_all_sync(__activemask(), ok ? oct : 8u, &same);
+    if (same && ok) {
+#ifdef PB_OCT_ONLY
+      return traverse<ANY, SPH, MULTI, BOX, MODE, PB_OCT_ONLY>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
+#else
+      switch (oct) {
+#define PB_OCT(K) \
+  case K:         \
+    return traverse<ANY, SPH, MULTI, BOX, MODE, K>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
+        PB_OCT(0) PB_OCT(1) PB_OCT(2) PB_OCT(3) PB_OCT(4) PB_OCT(5) PB_OCT(6) default : PB_OCT(7)
+#undef PB_OCT
+      }
+#endif
+    }
+  }
+  return traverse<ANY, SPH, MULTI, 1, MODE, 0>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
+}

@@ -259,30 +259,75 @@ void devsrc_tri_surface(const pbrtb200_mesh* mesh, const float* pw9, const float
 
 #include "../../pbrt_rust_b200/csrc/host_logic.hpp"
 #include "../../pbrt_rust_b200/csrc/trace_core.cuh"
+namespace {
+int g_box = 3;  // box-test family of the traversal (trace_core.cuh child_box), devsrc_set_box
+// The traversal part of pbrtb200_upload_scene (csrc/api.cu): pair nodes, leaf boxes, box flags, and
+// the "a one-triangle leaf's box equals the bounds of its vertices" check that decides whether the
+// leaf boxes must be read from memory (MULTI variants).
+bool traversal_scene(const pbrtb200_scene* s, pbh::PairNodes* pn, DScene* sc, bool* sph, bool* multi) {
+  if (pbh::build_pair_nodes(s->nodes, s->n_nodes, s->n_prims, pn)) return false;
+  sc->nodes = reinterpret_cast<const float4*>(pn->pairs.data());
+  sc->tris = reinterpret_cast<const float4*>(s->tris);
+  *sph = s->n_spheres > 0 || s->leaf_prim != nullptr;
+  *multi = pn->multi;
+  if (!*multi && !*sph && s->tris)
+    for (uint32_t i = 0; i < s->n_nodes && !*multi; ++i) {
+      const pbrtb200_node32& nd = s->nodes[i];
+      if (!nd.is_leaf) continue;
+      const pbrtb200_tri48& t = s->tris[nd.offset];
+      const float* v[3] = {t.p1, t.p2, t.p3};
+      for (int a = 0; a < 3; ++a) {
+        const float lo = std::fmin(std::fmin(v[0][a], v[1][a]), v[2][a]), hi = std::fmax(std::fmax(v[0][a], v[1][a]), v[2][a]);
+        if (!(lo == nd.bmin[a]) || !(hi == nd.bmax[a])) *multi = true;
+      }
+    }
+  sc->leaf_prim = *sph ? s->leaf_prim : nullptr;
+  sc->leaf_count = pn->big_leaf ? pn->leaf_count.data() : nullptr;
+  sc->leaf_boxes = (*multi || *sph) ? reinterpret_cast<const float4*>(pn->leaf_boxes.data()) : nullptr;
+  sc->spheres = s->spheres;
+  sc->sphere_o2w = s->sphere_o2w;
+  sc->n_prims = s->n_prims;
+  sc->root_ref = pn->root_ref;
+  for (int i = 0; i < 3; ++i) {
+    sc->root_bmin[i] = pn->root_bmin[i];
+    sc->root_bmax[i] = pn->root_bmax[i];
+    sc->babs[i] = pn->babs[i];
+  }
+  sc->boxes_finite = pn->boxes_finite ? 1u : 0u;
+  sc->boxes_ordered = pn->boxes_ordered ? 1u : 0u;
+  return true;
+}
+template <bool ANY, int MODE, int BOX>
+TraceResult trace_variant_box(const DScene& sc, bool sph, bool multi, f3 o, f3 d, float mint, float maxt, uint32_t* sr, float* st) {
+  return sph ? (multi ? trace_ray<ANY, true, true, MODE, BOX>(sc, o, d, mint, maxt, sr, st)
+                      : trace_ray<ANY, true, false, MODE, BOX>(sc, o, d, mint, maxt, sr, st))
+             : (multi ? trace_ray<ANY, false, true, MODE, BOX>(sc, o, d, mint, maxt, sr, st)
+                      : trace_ray<ANY, false, false, MODE, BOX>(sc, o, d, mint, maxt, sr, st));
+}
+template <bool ANY, int MODE>
+TraceResult trace_any_variant(const DScene& sc, bool sph, bool multi, f3 o, f3 d, float mint, float maxt, uint32_t* sr, float* st) {
+  switch (g_box) {
+    case 1: return trace_variant_box<ANY, MODE, 1>(sc, sph, multi, o, d, mint, maxt, sr, st);
+    case 2: return trace_variant_box<ANY, MODE, 2>(sc, sph, multi, o, d, mint, maxt, sr, st);
+    default: return trace_variant_box<ANY, MODE, 3>(sc, sph, multi, o, d, mint, maxt, sr, st);
+  }
+}
+}  // namespace
 extern "C" {
+// Box-test family used by devsrc_trace / devsrc_render from now on (1, 2, 3; the product's
+// PBRTB200_BOX).
+void devsrc_set_box(int box) { g_box = box; }
 // Scene::intersect / intersect_p for n rays (ray8 = o, mint, d, maxt) through the device traversal source,
 // with the pair nodes packed by the product's own build_pair_nodes and the kernel variant the library
 // would launch.  any_mode: -1 closest hit (hit4 = prim, t, b1, b2 per ray), else the any-hit SIMT mode
 // 0..3 (hit4[0] = prim or MISS).  Returns 0, or -1 with a bad scene / -2 on a stack overflow.
 int devsrc_trace(const pbrtb200_scene* s, const float* rays8, unsigned long long n, int any_mode, float* hit4) {
   pbh::PairNodes pn;
-  if (pbh::build_pair_nodes(s->nodes, s->n_nodes, s->n_prims, &pn)) return -1;
   DScene sc{};
-  sc.nodes = reinterpret_cast<const float4*>(pn.pairs.data());
-  sc.tris = reinterpret_cast<const float4*>(s->tris);
-  const bool sph = s->n_spheres > 0 || s->leaf_prim != nullptr;
-  sc.leaf_prim = sph ? s->leaf_prim : nullptr;
-  sc.leaf_count = pn.big_leaf ? pn.leaf_count.data() : nullptr;
-  sc.spheres = s->spheres;
-  sc.sphere_o2w = s->sphere_o2w;
-  sc.n_prims = s->n_prims;
-  sc.root_ref = pn.root_ref;
-  for (int i = 0; i < 3; ++i) {
-    sc.root_bmin[i] = pn.root_bmin[i];
-    sc.root_bmax[i] = pn.root_bmax[i];
-  }
+  bool sph = false, multi = false;
+  if (!traversal_scene(s, &pn, &sc, &sph, &multi)) return -1;
   std::vector<uint32_t> s_ref((size_t)PB_SM_STACK * PB_TRACE_THREADS);
-  std::vector<float> s_t0((size_t)PB_SM_STACK * PB_TRACE_THREADS);
+  std::vector<float> s_t0((size_t)PB_SM_STACK * PB_TRACE_THREADS);  // (host stack: two arrays)
   int rc = 0;
   for (unsigned long long i = 0; i < n; ++i) {
     const float* r = rays8 + 8 * i;
@@ -290,11 +335,7 @@ int devsrc_trace(const pbrtb200_scene* s, const float* rays8, unsigned long long
     uint32_t* sr = s_ref.data() + (i % PB_TRACE_THREADS);  // this "thread's" stack column
     float* st = s_t0.data() + (i % PB_TRACE_THREADS);
     TraceResult t;
-#define PB_T(ANY, MODE)                                                                      \
-  t = sph ? (pn.multi ? trace_ray<ANY, true, true, MODE>(sc, o, d, r[3], r[7], sr, st)        \
-                      : trace_ray<ANY, true, false, MODE>(sc, o, d, r[3], r[7], sr, st))      \
-          : (pn.multi ? trace_ray<ANY, false, true, MODE>(sc, o, d, r[3], r[7], sr, st)       \
-                      : trace_ray<ANY, false, false, MODE>(sc, o, d, r[3], r[7], sr, st))
+#define PB_T(ANY, MODE) t = trace_any_variant<ANY, MODE>(sc, sph, multi, o, d, r[3], r[7], sr, st)
     switch (any_mode) {
       case -1: PB_T(false, 1); break;
       case 0: PB_T(true, 0); break;
@@ -303,7 +344,7 @@ int devsrc_trace(const pbrtb200_scene* s, const float* rays8, unsigned long long
       default: PB_T(true, 3); break;
     }
 #undef PB_T
-    if (t.overflow) rc = -2;
+    if (t.prim == PB_OVERFLOW) rc = -2;
     hit4[4 * i] = __uint_as_float(t.prim);
     hit4[4 * i + 1] = t.t;
     hit4[4 * i + 2] = t.b1;
@@ -368,15 +409,6 @@ void devsrc_film_gather(const pbrtb200_film* film, const int* ext4, int spp, con
 
 // ---- a whole frame through the device source: camera rays, closest hit, k_shade, any-hit, film ----------
 #include "../../pbrt_rust_b200/csrc/shade.cuh"
-namespace {
-template <bool ANY, int MODE>
-TraceResult trace_any_variant(const DScene& sc, bool sph, bool multi, f3 o, f3 d, float mint, float maxt, uint32_t* sr, float* st) {
-  return sph ? (multi ? trace_ray<ANY, true, true, MODE>(sc, o, d, mint, maxt, sr, st)
-                      : trace_ray<ANY, true, false, MODE>(sc, o, d, mint, maxt, sr, st))
-             : (multi ? trace_ray<ANY, false, true, MODE>(sc, o, d, mint, maxt, sr, st)
-                      : trace_ray<ANY, false, false, MODE>(sc, o, d, mint, maxt, sr, st));
-}
-}  // namespace
 extern "C" {
 // One frame.  The camera samples come from the caller (raster pixel order over the sampler extent
 // ext4, spp per pixel): img2 image positions, lens2 lens positions or NULL, lightu = area_sample_pairs
@@ -388,15 +420,9 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
                   const float* img2, const float* lens2, const float* lightu, int strict_flags, float* out_xyzw,
                   unsigned long long* stats3) {
   pbh::PairNodes pn;
-  if (pbh::build_pair_nodes(s->nodes, s->n_nodes, s->n_prims, &pn)) return -1;
   DScene sc{};
-  sc.nodes = reinterpret_cast<const float4*>(pn.pairs.data());
-  sc.tris = reinterpret_cast<const float4*>(s->tris);
-  const bool sph = s->n_spheres > 0 || s->leaf_prim != nullptr;
-  sc.leaf_prim = sph ? s->leaf_prim : nullptr;
-  sc.leaf_count = pn.big_leaf ? pn.leaf_count.data() : nullptr;
-  sc.spheres = s->spheres;
-  sc.sphere_o2w = s->sphere_o2w;
+  bool sph = false, multi = false;
+  if (!traversal_scene(s, &pn, &sc, &sph, &multi)) return -1;
   sc.meshes = s->meshes;
   sc.tri_uv = s->tri_uv;
   sc.tri_n = s->tri_n;
@@ -405,13 +431,7 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
   sc.textures = s->textures;
   sc.mipmaps = s->n_mipmaps ? s->mipmaps : nullptr;
   sc.texels = s->n_mipmaps ? reinterpret_cast<const float4*>(s->texels) : nullptr;
-  sc.n_prims = s->n_prims;
   sc.n_lights = s->n_lights;
-  sc.root_ref = pn.root_ref;
-  for (int i = 0; i < 3; ++i) {
-    sc.root_bmin[i] = pn.root_bmin[i];
-    sc.root_bmax[i] = pn.root_bmax[i];
-  }
   // mat_flags, the EXT decision, light slots, area-light records: as pbrtb200_upload_scene does
   std::vector<uint8_t> mat_flags(std::max<uint32_t>(1u, s->n_materials), 0);
   bool ext = false;
@@ -476,15 +496,15 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
   const float2* img = reinterpret_cast<const float2*>(img2);
   const float2* lens = (lens2 && c->lens_radius > 0.0f) ? reinterpret_cast<const float2*>(lens2) : nullptr;
   std::vector<uint32_t> s_ref((size_t)PB_SM_STACK * PB_TRACE_THREADS);
-  std::vector<float> s_t0((size_t)PB_SM_STACK * PB_TRACE_THREADS);
+  std::vector<float> s_t0((size_t)PB_SM_STACK * PB_TRACE_THREADS);  // (host stack: two arrays)
   // closest hit per camera sample (the SRC = 1 path of k_trace: camera_ray, mint 0, maxt f32::MAX)
   std::vector<pbrtb200_hit16> hits(std::max<size_t>(1, n));
   int rc = 0;
   for (size_t i = 0; i < n; ++i) {
     f3 o, d;
     camera_ray(dc, img[i].x, img[i].y, lens ? lens[i].x : 0.f, lens ? lens[i].y : 0.f, &o, &d, nullptr);
-    const TraceResult t = trace_any_variant<false, 1>(sc, sph, pn.multi, o, d, 0.0f, PB_F32_MAX, s_ref.data(), s_t0.data());
-    if (t.overflow) rc = -2;
+    const TraceResult t = trace_any_variant<false, 1>(sc, sph, multi, o, d, 0.0f, PB_F32_MAX, s_ref.data(), s_t0.data());
+    if (t.prim == PB_OVERFLOW) rc = -2;
     hits[i].prim = t.prim;
     hits[i].t = t.t;
     hits[i].b1 = t.b1;
@@ -528,9 +548,9 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
     // the any-hit pass over the shadow queue (k_trace<ANY>, default loop shape 2)
     for (uint32_t q = 0; q < sq_count; ++q) {
       const pbrtb200_ray32& r = sq_rays[q];
-      const TraceResult t = trace_any_variant<true, 2>(sc, sph, pn.multi, mk3(r.o[0], r.o[1], r.o[2]), mk3(r.d[0], r.d[1], r.d[2]),
+      const TraceResult t = trace_any_variant<true, 2>(sc, sph, multi, mk3(r.o[0], r.o[1], r.o[2]), mk3(r.d[0], r.d[1], r.d[2]),
                                                        r.mint, r.maxt, s_ref.data(), s_t0.data());
-      if (t.overflow) rc = -2;
+      if (t.prim == PB_OVERFLOW) rc = -2;
       if (t.prim != PBRTB200_MISS) {
         rad[sq_slots[q]] = make_float4(0.f, 0.f, 0.f, 0.f);
         ++occluded;
