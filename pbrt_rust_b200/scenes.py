@@ -120,6 +120,48 @@ def config3(nx=1000, nz=500, xres=1920, yres=1080, xs=4, ys=4, crop=(0, 1, 0, 1)
     return _setup(scene, c2w, 36.0, xres, yres, xs, ys, True, crop=crop)
 
 
+def irradiance_probe(target=(0.0, 0.0, 0.0), emit_down=True, light_samples=1, kd=0.5, radiance=15.0,
+                     res=16, spp=8, eye=None):
+    """A flat Lambertian receiver (y = 0, Kd = kd) under the 4x4 quad emitter of config 3 (y = 8), seen
+    through a very narrow camera aimed at `target`: every pixel sees (nearly) the same point, so the
+    mean pixel value is the direct-lighting estimate there, Lo = Kd / pi * E, with E given in closed
+    form by Lambert's polygon formula (`polygon_irradiance`).  emit_down=False flips the quad's
+    winding: it then faces away from the receiver and E = 0.  `eye` overrides the camera position
+    (e.g. below the emitter, looking up at it: the pixel value is then Le itself)."""
+    gP = np.array([[-40.0, 0.0, -40.0], [40.0, 0.0, -40.0], [40.0, 0.0, 40.0], [-40.0, 0.0, 40.0]], np.float32)
+    gvi = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    lvi, lP = _quad_light()
+    if not emit_down:
+        lvi = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    mat = _matte(kd, 0.0)
+    prims = [Primitive.geometric(Shape.triangle_mesh(Transform.new(), Transform.new(), False, gvi, gP), mat),
+             Primitive.geometric_area_light(Shape.triangle_mesh(Transform.new(), Transform.new(), False, lvi, lP),
+                                            mat, AreaLight(radiance, light_samples))]
+    scene = Scene.new_with(Primitive.bvh(prims, 4, "sah"), [])
+    t = np.asarray(target, np.float64)
+    e = np.asarray(eye, np.float64) if eye is not None else t + np.array([3.0, 5.0, -9.0])
+    up = (0, 1, 0) if abs(e[0] - t[0]) + abs(e[2] - t[2]) > 1e-6 else (0, 0, 1)
+    c2w = Transform.look_at(tuple(e), tuple(t), up).inverse()
+    cfg = _setup(scene, c2w, 0.25, res, res, spp, spp, True)
+    cfg["light_quad"] = lP.astype(np.float64)
+    return cfg
+
+
+def polygon_irradiance(p, n, verts, radiance):
+    """Irradiance at point p (unit normal n) from a planar polygon of uniform radiance that lies
+    entirely above p's horizon and is not occluded (Lambert 1760): E = L / 2 * |sum_i Gamma_i (n . g_i)|
+    with Gamma_i the angle subtended by edge i and g_i the unit normal of the plane through p and edge i."""
+    p, n = np.asarray(p, np.float64), np.asarray(n, np.float64)
+    v = [np.asarray(q, np.float64) - p for q in verts]
+    v = [q / np.linalg.norm(q) for q in v]
+    acc = 0.0
+    for i in range(len(v)):
+        a, b = v[i], v[(i + 1) % len(v)]
+        c = np.cross(a, b)
+        acc += np.arccos(np.clip(np.dot(a, b), -1.0, 1.0)) * np.dot(n, c / np.linalg.norm(c))
+    return radiance * abs(acc) / 2.0
+
+
 def config4(n_ground=(500, 200), n_spheres=20_000, xres=3840, yres=2160, xs=8, ys=8, crop=(0, 1, 0, 1),
             seed=4):
     """textured ground (checkerboard matte, Oren-Nayar sigma 20) + jittered

@@ -446,6 +446,23 @@ def test_multiple_area_lights_and_samples(orc):
     assert r.last_stats["shadow_rays"] > r.last_stats["camera_hits"]      # several rays per hit
 
 
+@pytest.mark.parametrize("target,light_samples", [((0.0, 0.0, 0.0), 1), ((7.0, 0.0, 3.0), 1), ((-11.0, 0.0, -6.5), 4)])
+def test_area_light_matches_the_closed_form_irradiance(orc, target, light_samples):
+    """A13 pinned to physics on the device: the direct-lighting estimate under the quad emitter
+    converges to Kd / pi * E with E from Lambert's polygon formula (1 % at 2^14 samples), and equals
+    the oracle's image within the usual tolerance.  The back-facing emitter gives exactly zero."""
+    from test_oracle_kat import _film_rgb_of_grey
+    cfg = scenes.irradiance_probe(target=target, light_samples=light_samples, res=16, spp=8)
+    r, film, ref = _image_check(cfg, orc)
+    got = pb.film_to_rgb(film).reshape(-1, 3).mean(axis=0)
+    want = _film_rgb_of_grey(0.5 / np.pi * scenes.polygon_irradiance(target, (0.0, 1.0, 0.0), cfg["light_quad"], 15.0))
+    assert np.allclose(got, want, rtol=1e-2), (got, want)
+    assert r.last_stats["shadow_rays"] == r.last_stats["camera_rays"] * light_samples
+    back = scenes.irradiance_probe(target=target, emit_down=False, res=8, spp=4)
+    rb = _renderer(back)
+    assert pb.film_to_rgb(rb.render(back["scene"])).max() == 0.0 and rb.last_stats["shadow_rays"] == 0
+
+
 def test_nan_radiance_is_an_error_not_a_silent_image(orc):
     """sampler_renderer.rs:105 (intent): a NaN radiance fails the render."""
     mat = pb.Material.matte(pb.Texture.constant(float("nan")), pb.Texture.constant(0.0))
