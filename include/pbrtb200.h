@@ -240,7 +240,9 @@ typedef struct {
   int32_t strict_flags; /* 1 = reproduce BSDF::f's as-written flag test (always black) */
 } pbrtb200_integrator;
 
-/* Film pixel rectangles this call renders (multi-GPU tile partition); NULL = whole film. */
+/* Film pixel rectangles this call renders (multi-GPU tile partition).  A NULL tile set = the whole
+ * film.  A tile set with n_rects == 0 owns NO pixel: the call renders nothing (and zeroes the film
+ * unless PBRTB200_TILES_KEEP_OTHERS is set) - it is never read as "whole film". */
 #define PBRTB200_TILES_KEEP_OTHERS 1u /* do not clear the film pixels outside the rects */
 typedef struct {
   const int32_t* rects; /* n_rects x (x0, y0, x1, y1), half-open, in film pixel coordinates */

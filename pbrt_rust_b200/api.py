@@ -564,6 +564,7 @@ class Context:
         if rc:
             raise PbrtError(rc, lib().pbrtb200_last_error(None).decode())
         self.device = device
+        self.scene_key, self.host_scene = None, None
 
     def check(self, rc):
         if rc:
@@ -573,8 +574,13 @@ class Context:
         """Issue this ctx's work on the given cudaStream_t (int handle), e.g. torch's current stream."""
         self.check(lib().pbrtb200_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
-    def upload(self, host_scene):
+    def upload(self, host_scene, scene_key=None):
+        """Uploads a flattened scene.  The ctx remembers WHICH scene it holds (`scene_key`,
+        `host_scene`): renderers that share a ctx compare against that, not against their own
+        last upload, so one renderer can never render another renderer's scene by accident."""
+        self.scene_key, self.host_scene = None, None
         self.check(lib().pbrtb200_upload_scene(self.h, host_scene.flat))
+        self.scene_key, self.host_scene = scene_key, host_scene
 
     def close(self):
         if self.h:
@@ -606,6 +612,12 @@ def _ptr(a):
     return C.c_void_p(a.data_ptr()), (1 if a.is_cuda else 0)
 
 
+def _like(dev_tensor, n, dtype):
+    """An uninitialised output buffer of n elements on the device `dev_tensor` lives on (torch)."""
+    import torch
+    return torch.empty(n, dtype={np.uint8: torch.uint8}[dtype], device=dev_tensor.device)
+
+
 class GpuRenderer:
     """Drop-in for SamplerRenderer (src/sampler_renderer.rs:26-54): same constructor arguments
     (sampler, camera, surface integrator; the volume integrator is a stub in the reference), and
@@ -617,9 +629,11 @@ class GpuRenderer:
         # sampler_renderer.rs:39-44 (num_cpus::get() is a property of the host running the crate)
         self.num_tasks = int(lib().pbh_num_tasks(num_cpus, film.x_res * film.y_res))
         self.ctx = ctx or Context(device)
-        self._scene_key = None
-        self.host_scene = None
         self.last_stats = None
+
+    @property
+    def host_scene(self):
+        return self.ctx.host_scene
 
     def sampler_desc(self):
         s = self.sampler
@@ -635,10 +649,8 @@ class GpuRenderer:
 
     def preprocess(self, scene):
         """Builds/flattens/uploads the scene once (the reference builds its BVH at scene creation)."""
-        if self._scene_key is not scene:
-            self.host_scene = HostScene(scene)
-            self.ctx.upload(self.host_scene)
-            self._scene_key = scene
+        if self.ctx.scene_key is not scene:
+            self.ctx.upload(HostScene(scene), scene_key=scene)
 
     def render(self, scene, tiles=None, out=None, keep_others=False):
         """Returns the film as an (H, W, 4) array: sum(w*XYZ), sum(w).  `out` may be a CUDA tensor
@@ -650,7 +662,7 @@ class GpuRenderer:
         if out is None:
             out = np.zeros((h, w, 4), np.float32)
         ts = None
-        if tiles is not None:
+        if tiles is not None:  # an EMPTY tile list is a tile set without pixels, not "the whole film"
             rects = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 4)
             ts = _ffi.TileSet(rects.ctypes.data_as(C.POINTER(C.c_int32)), rects.shape[0], 1 if keep_others else 0)
         integ = _ffi.Integrator(0, self.surf.max_depth, int(self.surf.strict_flags))
@@ -689,11 +701,13 @@ class GpuRenderer:
     def intersect(self, scene, rays, hits=None):
         self.preprocess(scene)
         n = rays.shape[0]
-        if hits is None:
-            hits = np.zeros(n, dtype=HIT_DTYPE)
-        st = _ffi.Stats()
         pr, dev = _ptr(rays)
-        ph, _ = _ptr(hits)
+        if hits is None:
+            hits = _like(rays, n * 16, np.uint8) if dev else np.zeros(n, dtype=HIT_DTYPE)
+        st = _ffi.Stats()
+        ph, hdev = _ptr(hits)
+        if hdev != dev:  # the C ABI takes ONE is_device flag for both buffers
+            raise PbrtError(_ffi.EINVAL, "intersect: rays and hits must both be host arrays or both be device tensors")
         rc = lib().pbrtb200_trace_closest(self.ctx.h, pr, n, ph, dev, C.byref(st))
         self.last_stats = st.as_dict()
         self.ctx.check(rc)
@@ -702,11 +716,13 @@ class GpuRenderer:
     def intersect_p(self, scene, rays, occluded=None):
         self.preprocess(scene)
         n = rays.shape[0]
-        if occluded is None:
-            occluded = np.zeros(n, np.uint8)
-        st = _ffi.Stats()
         pr, dev = _ptr(rays)
-        po, _ = _ptr(occluded)
+        if occluded is None:
+            occluded = _like(rays, n, np.uint8) if dev else np.zeros(n, np.uint8)
+        st = _ffi.Stats()
+        po, odev = _ptr(occluded)
+        if odev != dev:
+            raise PbrtError(_ffi.EINVAL, "intersect_p: rays and occluded must both be host arrays or both be device tensors")
         rc = lib().pbrtb200_trace_any(self.ctx.h, pr, n, po, dev, C.byref(st))
         self.last_stats = st.as_dict()
         self.ctx.check(rc)

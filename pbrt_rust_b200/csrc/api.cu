@@ -65,7 +65,7 @@ struct CtrlBlock {  // small device-side control words, zeroed per use
   uint32_t pad;
 };
 
-std::string g_create_err;
+thread_local std::string g_create_err;  // pbrtb200_create failures, per calling thread
 
 }  // namespace
 
@@ -263,7 +263,10 @@ void fill_sampler(pbrtb200_ctx* ctx, const pbrtb200_sampler* s, DSampler* out) {
 // pixels of `rects`, in 8x4-tile-major order, each with its task id and in-window index.
 int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb200_film* film,
                      const pbrtb200_tileset* tiles) {
-  const bool whole = !(tiles && tiles->n_rects > 0 && tiles->rects);
+  // tiles == NULL: the whole film.  (A tile set WITHOUT rects never gets here: pbrtb200_render
+  // answers it before building a list.)
+  if (tiles && (tiles->n_rects == 0 || !tiles->rects)) FAIL(PBRTB200_EINVAL, "tile set without rects");
+  const bool whole = tiles == nullptr;
   std::vector<int32_t> rects;
   const int32_t fx0 = film ? film->x_pixel_start : 0, fy0 = film ? film->y_pixel_start : 0;
   const int32_t fx1 = film ? fx0 + film->x_pixel_count : 0, fy1 = film ? fy0 + film->y_pixel_count : 0;
@@ -1129,6 +1132,21 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   if (ctx->sc.n_lights && !ctx->d_materials.p) FAIL(PBRTB200_EINVAL, "scene has no materials");
   CK(cudaSetDevice(ctx->device));
   if (stats) std::memset(stats, 0, sizeof *stats);
+  if (tiles && tiles->n_rects > 0 && !tiles->rects) FAIL(PBRTB200_EINVAL, "tiles->rects is NULL");
+  if (tiles && tiles->n_rects == 0) {
+    // An EMPTY tile set owns no pixel (a rank whose band is empty): nothing is rendered.  The film is
+    // zeroed unless the caller keeps the other owners' pixels — never treated as "the whole film".
+    if (!(tiles->flags & PBRTB200_TILES_KEEP_OTHERS)) {
+      const size_t bytes = (size_t)film->x_pixel_count * (size_t)film->y_pixel_count * sizeof(float4);
+      if (out_is_device) {
+        CK(cudaMemsetAsync(out_xyzw, 0, bytes, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+      } else {
+        std::memset(out_xyzw, 0, bytes);
+      }
+    }
+    return PBRTB200_OK;
+  }
   if (int rc = build_pixel_list(ctx, smp, film, tiles)) return rc;
 
   DSampler ds;
@@ -1198,7 +1216,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
 
   CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
   CK(cudaMemsetAsync(ctx->d_edge.p, 0, npix * sizeof(uint32_t), ctx->stream));
-  if (tiles && tiles->n_rects && !(tiles->flags & PBRTB200_TILES_KEEP_OTHERS))
+  if (tiles && !(tiles->flags & PBRTB200_TILES_KEEP_OTHERS))
     CK(cudaMemsetAsync(d_film, 0, film_px * sizeof(float4), ctx->stream));  // else k_film writes every pixel
 
   // ---- film stage (launched per band, see below) ---------------------------------------------
@@ -1232,7 +1250,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     const char* v = std::getenv("PBRTB200_FILM_BANDS");
     return v && *v ? std::atoi(v) : 2;
   }();
-  const bool banded = band_mode > 0 && !out_is_device && !(tiles && tiles->n_rects);
+  const bool banded = band_mode > 0 && !out_is_device && !tiles;
   struct Band {
     uint32_t y0, y1;
     size_t event;
@@ -1320,7 +1338,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     ta.n = cn;
     ta.counter = &ctrl(ctx)->counter;
     ta.flags = &ctrl(ctx)->flags;
-    if (tiles && tiles->n_rects && !halton) {  // halo pixels that cannot reach an owned pixel are not traced
+    if (tiles && !halton) {  // halo pixels that cannot reach an owned pixel are not traced
       ta.pixels = ctx->d_pixels.as<DPixel>() + p0;
       ta.edge = ctx->d_edge.as<uint32_t>() + p0;
       ta.spp = (uint32_t)ds.spp;

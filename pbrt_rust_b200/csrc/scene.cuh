@@ -4,7 +4,9 @@
 #include "dmath.cuh"
 
 #include "leaf_ref.h"  // PB_LEAF_BIT, PB_LEAF_CNT_SHIFT, PB_LEAF_OFF_MASK
+#ifndef PB_SM_STACK
 #define PB_SM_STACK 24                                   // traversal-stack entries kept in smem
+#endif
 #define PB_LM_STACK (PBRTB200_STACK_DEPTH - PB_SM_STACK) // deeper entries spill to local memory
 #define PB_TRACE_THREADS 128
 

@@ -117,12 +117,17 @@ class BandBalancer:
     def _snap(self, v):
         return int(round(v / self.q)) * self.q
 
-    def _fix(self):  # strictly increasing, at least one quantum per rank when the film allows it
+    def _fix(self):
+        """Boundaries non-decreasing inside [y0, y1]; at least one quantum per rank when the film has
+        that many rows (a film with fewer rows than ranks leaves the last ranks an EMPTY band: they
+        get an empty tile set and render nothing)."""
+        self.b[0], self.b[-1] = self.y0, self.y1
         for k in range(1, self.world):
             self.b[k] = max(self.b[k], self.b[k - 1] + self.q)
         for k in range(self.world - 1, 0, -1):
             self.b[k] = min(self.b[k], self.b[k + 1] - 1)
-        self.b[0], self.b[-1] = self.y0, self.y1
+        for k in range(1, self.world):  # short films: clamp instead of running past either end
+            self.b[k] = min(max(self.b[k], self.b[k - 1], self.y0), self.y1)
 
     def tiles_for(self, rank):
         a, c = self.b[rank], self.b[rank + 1]

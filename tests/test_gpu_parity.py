@@ -3,6 +3,7 @@ same seeded inputs.  Integer/index results (hit primitive ids, occlusion flags) 
 float results carry the tolerance stated next to each assert."""
 import numpy as np
 import pytest
+import torch
 
 import pbrt_rust_b200 as pb
 from pbrt_rust_b200 import scenes
@@ -227,6 +228,43 @@ def test_tiles_are_partition_independent(orc):
     b = r.render(cfg["scene"], tiles=[(64, 0, 128, 32)])
     merged = a + b
     assert np.array_equal(merged.view(np.uint32), whole.view(np.uint32))
+
+
+def test_empty_tile_set_renders_nothing(orc):
+    """a tile set with zero rects is "no pixel", not "the whole film": the film comes back
+    zeroed, or untouched with keep_others (a rank whose band is empty must not overwrite the gather)."""
+    cfg = scenes.config1(xres=64, yres=48)
+    r = _renderer(cfg)
+    whole = r.render(cfg["scene"]).copy()
+    assert whole[..., 3].min() > 0
+    out = np.full_like(whole, 7.0)
+    r.render(cfg["scene"], tiles=[], out=out)
+    assert not out.any()
+    out = np.full_like(whole, 7.0)
+    r.render(cfg["scene"], tiles=[], out=out, keep_others=True)
+    assert (out == 7.0).all()
+    dev = torch.full((whole.size,), 7.0, dtype=torch.float32, device="cuda")
+    r.render(cfg["scene"], tiles=[], out=dev, keep_others=True)
+    assert bool((dev == 7.0).all())
+    r.render(cfg["scene"], tiles=[], out=dev)
+    assert not bool(dev.any())
+
+
+def test_intersect_with_device_rays_allocates_device_outputs(orc):
+    """rays on the device + default outputs -> the outputs live on the device too (one
+    is_device flag covers both buffers of the C call); a host/device mix is refused."""
+    cfg = scenes.config2(n=2000, xres=32, yres=32)
+    r = _renderer(cfg)
+    rng = np.random.default_rng(5)
+    rays = _rays_from(rng, 4096, np.float32([-10, -10, -10]), np.float32([10, 10, 10]))
+    want = r.intersect(cfg["scene"], rays)
+    drays = torch.from_numpy(rays).cuda()
+    got = r.intersect(cfg["scene"], drays)
+    assert got.is_cuda and np.array_equal(got.cpu().numpy().view(pb.HIT_DTYPE), want)
+    occ = r.intersect_p(cfg["scene"], drays)
+    assert occ.is_cuda and np.array_equal(occ.cpu().numpy(), r.intersect_p(cfg["scene"], rays))
+    with pytest.raises(pb.PbrtError):
+        r.intersect(cfg["scene"], drays, hits=np.zeros(4096, pb.HIT_DTYPE))
 
 
 def test_strict_flags_reproduce_black_image():

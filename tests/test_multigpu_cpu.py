@@ -80,3 +80,23 @@ def test_band_balancer_covers_rows_and_converges(world):
     tiny = multigpu.BandBalancer((3, 9, 5, 5 + world + 1), world)
     rows = sorted(r for k in range(world) for (_, y0, _, y1) in tiny.tiles_for(k) for r in range(y0, y1))
     assert rows == list(range(5, 5 + world + 1))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("ext", [(0, 1920, 0, 1080), (0, 64, 0, 5), (3, 40, 7, 8), (0, 16, 0, 33)])
+def test_band_balancer_always_covers_the_film_exactly_once(world, ext):
+    """Row bands: boundaries stay inside the film and non-decreasing, whatever the measured times
+    do; a film with fewer rows than ranks leaves some ranks an EMPTY tile list (which the C ABI
+    renders as "nothing", never as "the whole film")."""
+    bal = multigpu.BandBalancer(ext, world)
+    rng = np.random.default_rng(world * 1000 + ext[3])
+    for step in range(12):
+        b = bal.b
+        assert b[0] == ext[2] and b[-1] == ext[3] and all(b[i] <= b[i + 1] for i in range(world))
+        cov = np.zeros((ext[3] - ext[2], ext[1] - ext[0]), np.int32)
+        for r in range(world):
+            for (a, y0, c, y1) in bal.tiles_for(r):
+                assert ext[0] <= a < c <= ext[1] and ext[2] <= y0 < y1 <= ext[3]
+                cov[y0 - ext[2]:y1 - ext[2], a - ext[0]:c - ext[0]] += 1
+        assert cov.min() == 1 and cov.max() == 1
+        bal.update(list(rng.random(world) * 3 + 0.01))
