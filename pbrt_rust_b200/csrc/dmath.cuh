@@ -52,10 +52,7 @@ inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline void __syncthreads() {}
 inline unsigned __activemask() { return 1u; }
-inline unsigned __match_all_sync(unsigned m, unsigned, int* pred) {  // a single lane always agrees
-  *pred = 1;
-  return m;
-}
+inline bool __all_sync(unsigned, bool p) { return p; }  // a single lane always agrees with itself
 inline int __ffs(int v) { return __builtin_ffs(v); }
 template <class T>
 inline T __shfl_sync(unsigned, T v, int) {

@@ -50,9 +50,14 @@ template <bool ANY, bool SPH, bool MULTI, int SRC, int MODE, int BOX>
 __global__ void __launch_bounds__(PB_TRACE_THREADS, PB_TRACE_MIN_BLOCKS(ANY))
 k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
   // child refs, then (closest hit only: any-hit keeps no T0) the entry distances
+#if PB_SM_STACK > 0
   __shared__ uint32_t sh_stack[(ANY ? 1 : 2) * PB_SM_STACK * PB_TRACE_THREADS];
   uint32_t* s_ref = sh_stack + threadIdx.x;
   float* s_t0 = reinterpret_cast<float*>(s_ref + (ANY ? 0 : PB_SM_STACK * PB_TRACE_THREADS));
+#else  // the whole stack in local memory (L1-resident, no shared-memory carve-out)
+  uint32_t* s_ref = nullptr;
+  float* s_t0 = nullptr;
+#endif
   const int lane = threadIdx.x & 31;
   const uint64_t n = a.n_dyn ? (uint64_t)(*a.n_dyn) : a.n;
   if (a.shadow_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.shadow_total, (unsigned long long)n);

@@ -88,7 +88,7 @@ struct RayBox {
 //   BOX 0  bbox.rs:185-209 literally (compare + swap): reproduces the reference's NaN behaviour for
 //          rays with a zero direction component.
 //   BOX 1  the same values through min / max (every 1/d finite, box coordinates finite).
-//   BOX 2  BOX 1 specialised for the ray's octant OCT (bit a = 1/d[a] < 0): with bmin <= bmax the
+//   BOX 2  BOX 1 specialised for the sign of 1/d per axis (AX, below): with bmin <= bmax the
 //          products (bmin - o) * inv and (bmax - o) * inv are ordered by the sign of inv alone
 //          (rounding is monotonic), so the swap of bbox.rs:194-196 is decided at compile time and the
 //          six per-axis min / max disappear.  Same values as BOX 1, bit for bit.
@@ -99,30 +99,40 @@ struct RayBox {
 //          lemma (DESIGN.md "Traversal") which leaves are visited, and in which order, is decided by
 //          each leaf's own exact test, which BOX 3 applies in the leaf phase to every primitive that
 //          reports a hit; inner tests may be any superset.
-template <int BOX, int OCT>
+// AX (BOX 2 / 3): per axis a = x, y, z two bits, (AX >> 2a) & 3 = 0: every ray of the warp has
+// 1/d[a] >= 0, 1: every ray has 1/d[a] < 0, 2: the warp mixes signs on this axis (that axis keeps
+// the min / max form; shadow rays towards a light overhead mix x and z in most warps).
+template <int BOX, int AX>
+PB_DEV void axis_t(float lo, float hi, float o, float inv, float ncn, float ncf, int a, float* tn, float* tf) {
+  const int s = (AX >> (2 * a)) & 3;
+  if (BOX == 2) {
+    if (s == 2) {
+      const float ta = (lo - o) * inv, tb = (hi - o) * inv;
+      *tn = fminf(ta, tb);
+      *tf = fmaxf(ta, tb);
+    } else {
+      *tn = ((s ? hi : lo) - o) * inv;
+      *tf = ((s ? lo : hi) - o) * inv;
+    }
+  } else {
+    if (s == 2) {
+      *tn = fminf(fmaf(lo, inv, ncn), fmaf(hi, inv, ncn));
+      *tf = fmaxf(fmaf(lo, inv, ncf), fmaf(hi, inv, ncf));
+    } else {
+      *tn = fmaf(s ? hi : lo, inv, ncn);
+      *tf = fmaf(s ? lo : hi, inv, ncf);
+    }
+  }
+}
+template <int BOX, int AX>
 PB_DEV bool child_box(const RayBox& rb, float ax, float ay, float az, float bx, float by, float bz,
                       float mint, float maxt, float* T0) {
   if (BOX == 0) return slab_test(ax, ay, az, bx, by, bz, rb.o, rb.inv, mint, maxt, T0);
   if (BOX == 1) return slab_test_finite(ax, ay, az, bx, by, bz, rb.o, rb.inv, mint, maxt, T0);
-  const float nx = (OCT & 1) ? bx : ax, fx = (OCT & 1) ? ax : bx;
-  const float ny = (OCT & 2) ? by : ay, fy = (OCT & 2) ? ay : by;
-  const float nz = (OCT & 4) ? bz : az, fz = (OCT & 4) ? az : bz;
   float tnx, tny, tnz, tfx, tfy, tfz;
-  if (BOX == 2) {
-    tnx = (nx - rb.o.x) * rb.inv.x;
-    tfx = (fx - rb.o.x) * rb.inv.x;
-    tny = (ny - rb.o.y) * rb.inv.y;
-    tfy = (fy - rb.o.y) * rb.inv.y;
-    tnz = (nz - rb.o.z) * rb.inv.z;
-    tfz = (fz - rb.o.z) * rb.inv.z;
-  } else {
-    tnx = fmaf(nx, rb.inv.x, rb.ncn.x);
-    tfx = fmaf(fx, rb.inv.x, rb.ncf.x);
-    tny = fmaf(ny, rb.inv.y, rb.ncn.y);
-    tfy = fmaf(fy, rb.inv.y, rb.ncf.y);
-    tnz = fmaf(nz, rb.inv.z, rb.ncn.z);
-    tfz = fmaf(fz, rb.inv.z, rb.ncf.z);
-  }
+  axis_t<BOX, AX>(ax, bx, rb.o.x, rb.inv.x, rb.ncn.x, rb.ncf.x, 0, &tnx, &tfx);
+  axis_t<BOX, AX>(ay, by, rb.o.y, rb.inv.y, rb.ncn.y, rb.ncf.y, 1, &tny, &tfy);
+  axis_t<BOX, AX>(az, bz, rb.o.z, rb.inv.z, rb.ncn.z, rb.ncf.z, 2, &tnz, &tfz);
   const float t0 = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, mint));
   const float t1 = fminf(fminf(tfx, tfy), fminf(tfz, maxt));
   *T0 = t0;
@@ -165,7 +175,7 @@ struct TStack {
   uint32_t top;  // shared-window byte address of the next free entry (while sp <= PB_SM_STACK)
   int sp;        // entries on the stack (limit checks only; the address is never derived from it)
   PB_DEV void init(uint32_t* ref, float*) {  // (s_t0 == s_ref + PB_SM_STACK * PB_TRACE_THREADS)
-    top = (uint32_t)__cvta_generic_to_shared(ref);
+    top = PB_SM_STACK > 0 ? (uint32_t)__cvta_generic_to_shared(ref) : 0u;
     sp = 0;
   }
   PB_DEV bool empty() const { return sp == 0; }
@@ -180,11 +190,11 @@ struct TStack {
     if (!ANY) asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(*t0) : "r"(top), "n"(kT0) : "memory");
   }
   PB_DEV void up() {
-    top += kStep;
+    if (PB_SM_STACK > 0) top += kStep;
     ++sp;
   }
   PB_DEV void down() {
-    top -= kStep;
+    if (PB_SM_STACK > 0) top -= kStep;
     --sp;
   }
 #endif
@@ -193,7 +203,7 @@ struct TStack {
 // One ray through the pair-node BVH.  s_ref / s_t0 point at this thread's column of the shared
 // stack (stride PB_TRACE_THREADS; s_t0 == s_ref + PB_SM_STACK * PB_TRACE_THREADS).  ANY: stop at
 // the first accepted hit (VisibilityTester).
-// BOX / OCT: the box test (child_box).  MODE selects the SIMT loop shape (all visit the same leaves
+// BOX / AX: the box test (child_box).  MODE selects the SIMT loop shape (all visit the same leaves
 // in the same order):
 //   0  if-if        : each iteration a lane does one node step OR one leaf        (best for any-hit)
 //   1  while-while  : lanes run node steps until every lane of the warp holds a leaf (best closest)
@@ -204,23 +214,26 @@ struct TStack {
 // Measured and dropped (profiles/r01_notes.md): speculative postponed-leaf traversal (no gain) and a
 // persistent kernel with per-lane ray refill (-30..-70 %: refilled lanes lose ray coherence), and a
 // warp-cooperative any-hit kernel with subtree stealing between lanes (-18 %).
-template <bool ANY, bool SPH, bool MULTI, int BOX, int MODE, int OCT>
+template <bool ANY, bool SPH, bool MULTI, int BOX, int MODE, int AX>
 PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, float mint, float maxt,
                             uint32_t* s_ref, float* s_t0) {
   constexpr bool UNORDERED = ANY && MODE >= 2;
   constexpr int SHAPE = MODE & 1;
   constexpr bool LEAF_EXACT = BOX == 3;  // inner tests are conservative: exact leaf test in the leaf phase
+  constexpr bool SM = PB_SM_STACK > 0;
   TraceResult res;
   res.prim = PBRTB200_MISS;
   res.t = 0.f;
   res.b1 = 0.f;
   res.b2 = 0.f;
+  // bvh.rs:382-383, as a mask over the q3.z axis bit of a node
+  const uint32_t oct = (rb.inv.x < 0.0f ? 1u : 0u) | (rb.inv.y < 0.0f ? 2u : 0u) | (rb.inv.z < 0.0f ? 4u : 0u);
   uint32_t l_ref[PB_LM_STACK];
   float l_t0[PB_LM_STACK];
   TStack<ANY> st;
   st.init(s_ref, s_t0);
   auto box = [&](float ax, float ay, float az, float bx, float by, float bz, float* T0) {
-    return child_box<BOX, OCT>(rb, ax, ay, az, bx, by, bz, mint, maxt, T0);
+    return child_box<BOX, AX>(rb, ax, ay, az, bx, by, bz, mint, maxt, T0);
   };
   // pop the next stack entry that still passes the reference's box test at pop (live maxt).
   // ANY: an any-hit query returns at its first accepted hit, so maxt never shrinks while entries
@@ -231,7 +244,7 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, floa
       st.down();
       uint32_t r;
       float t0 = 0.f;
-      if (st.in_shared()) {
+      if (SM && st.in_shared()) {
         st.get(&r, &t0);
       } else {
         const int k = st.depth() - PB_SM_STACK;
@@ -250,34 +263,24 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, floa
     const bool h0 = box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &T00);
     const bool h1 = box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &T01);
     const uint32_t r0 = __float_as_uint(q3.x), r1 = __float_as_uint(q3.y);
-    if (h0) {
-      if (!h1) return r0;
+    if (h0 & h1) {
       // both pass.  bvh.rs:409-415: dir_is_neg[axis] -> the second child is visited first
       bool neg = false;
-      if (!UNORDERED) {
-        if (BOX >= 2) {
-          neg = (__float_as_uint(q3.z) & (uint32_t)OCT) != 0u;  // q3.z = 1 << axis
-        } else {
-          const uint32_t axis = __float_as_uint(q3.w);
-          neg = axis == 0 ? rb.inv.x < 0.0f : (axis == 1 ? rb.inv.y < 0.0f : rb.inv.z < 0.0f);  // bvh.rs:382-383
-        }
-      }
+      if (!UNORDERED) neg = (__float_as_uint(q3.z) & oct) != 0u;  // q3.z = 1 << axis
       const uint32_t far_ref = neg ? r0 : r1;
       const float far_t0 = neg ? T00 : T01;
-      if (st.in_shared()) {
+      if (SM && st.in_shared()) {
         st.put(far_ref, far_t0);
       } else {
         const int k = st.depth() - PB_SM_STACK;
-        if (k >= PB_LM_STACK) {
-          return PB_DONE_OVF;
-        }
+        if (k >= PB_LM_STACK) return PB_DONE_OVF;
         l_ref[k] = far_ref;
         if (!ANY) l_t0[k] = far_t0;
       }
       st.up();
       return neg ? r1 : r0;
     }
-    if (h1) return r1;
+    if (h0 | h1) return h0 ? r0 : r1;
     return pop();
   };
   // bvh.rs:398-405: every primitive of the leaf in order; the last accepted hit wins.
@@ -378,11 +381,14 @@ PB_DEV bool ffma_constants(const DScene& sc, f3 o, f3 inv, RayBox* rb) {
   return true;
 }
 
+#ifdef PB_HOST_CHECK
+static int pb_host_force_mixed = 0;  // bit a: treat axis a as sign-mixed (tests/devsrc only)
+#endif
 // BOX: the box test the kernel variant was built for (1, 2 or 3; see child_box).  Rays it cannot
 // serve take an exact fall-back inside the same kernel: a zero / NaN direction component -> BOX 0
-// (the reference's compare-and-swap, NaN-faithful); BOX 2 / 3 need the warp's rays in ONE octant
-// (the specialised loops are selected by a switch: lanes in different octants would run one after
-// the other), a warp that mixes octants runs BOX 1 together.
+// (the reference's compare-and-swap, NaN-faithful).  BOX 2 / 3 are specialised per axis for the sign
+// of 1/d when the whole warp agrees on it (AX: 0 / 1), an axis on which the warp mixes signs keeps
+// the min / max form (AX: 2) — one of 27 loops, selected by a warp-uniform switch.
 template <bool ANY, bool SPH, bool MULTI, int MODE, int BOX = 1>
 PB_DEV TraceResult trace_ray(const DScene& sc, f3 o, f3 d, float mint, float maxt, uint32_t* s_ref,
                              float* s_t0) {
@@ -398,21 +404,29 @@ PB_DEV TraceResult trace_ray(const DScene& sc, f3 o, f3 d, float mint, float max
   if (BOX >= 2 && sc.boxes_ordered) {
     bool ok = true;
     if (BOX == 3) ok = ffma_constants(sc, o, inv, &rb);
-    const uint32_t oct = (inv.x < 0.0f ? 1u : 0u) | (inv.y < 0.0f ? 2u : 0u) | (inv.z < 0.0f ? 4u : 0u);
-    int same = 0;
-    __match_all_sync(__activemask(), ok ? oct : 8u, &same);
-    if (same && ok) {
-#ifdef PB_OCT_ONLY
-      return traverse<ANY, SPH, MULTI, BOX, MODE, PB_OCT_ONLY>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
-#else
-      switch (oct) {
-#define PB_OCT(K) \
-  case K:         \
-    return traverse<ANY, SPH, MULTI, BOX, MODE, K>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
-        PB_OCT(0) PB_OCT(1) PB_OCT(2) PB_OCT(3) PB_OCT(4) PB_OCT(5) PB_OCT(6) default : PB_OCT(7)
-#undef PB_OCT
-      }
+    const unsigned m = __activemask();
+    if (__all_sync(m, ok)) {
+      // per axis: 0 = every lane >= 0, 1 = every lane < 0, 2 = mixed
+      const unsigned bx = __ballot_sync(m, inv.x < 0.0f), by = __ballot_sync(m, inv.y < 0.0f),
+                     bz = __ballot_sync(m, inv.z < 0.0f);
+      int sx = bx == 0u ? 0 : (bx == m ? 1 : 2), sy = by == 0u ? 0 : (by == m ? 1 : 2),
+          sz = bz == 0u ? 0 : (bz == m ? 1 : 2);
+#ifdef PB_HOST_CHECK  // one emulated lane never mixes signs: the harness forces the mixed forms
+      if (pb_host_force_mixed & 1) sx = 2;
+      if (pb_host_force_mixed & 2) sy = 2;
+      if (pb_host_force_mixed & 4) sz = 2;
 #endif
+      switch (sx + 3 * sy + 9 * sz) {
+#define PB_AX(X, Y, Z) \
+  case X + 3 * Y + 9 * Z: \
+    return traverse<ANY, SPH, MULTI, BOX, MODE, X | (Y << 2) | (Z << 4)>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
+#define PB_AX3(Y, Z) PB_AX(0, Y, Z) PB_AX(1, Y, Z) PB_AX(2, Y, Z)
+#define PB_AX9(Z) PB_AX3(0, Z) PB_AX3(1, Z) PB_AX3(2, Z)
+        PB_AX9(0) PB_AX9(1) PB_AX9(2)
+#undef PB_AX9
+#undef PB_AX3
+#undef PB_AX
+      }
     }
   }
   return traverse<ANY, SPH, MULTI, 1, MODE, 0>(sc, o, d, rb, mint, maxt, s_ref, s_t0);

@@ -317,6 +317,8 @@ extern "C" {
 // Box-test family used by devsrc_trace / devsrc_render from now on (1, 2, 3; the product's
 // PBRTB200_BOX).
 void devsrc_set_box(int box) { g_box = box; }
+// Bit a set: the specialised loops treat axis a as "the warp mixes signs here" (min / max form).
+void devsrc_force_mixed_axes(int mask) { pb_host_force_mixed = mask; }
 // Scene::intersect / intersect_p for n rays (ray8 = o, mint, d, maxt) through the device traversal source,
 // with the pair nodes packed by the product's own build_pair_nodes and the kernel variant the library
 // would launch.  any_mode: -1 closest hit (hit4 = prim, t, b1, b2 per ray), else the any-hit SIMT mode

@@ -674,9 +674,9 @@ def _scene_rays(rng, n, lo, hi, spread):
     return rays
 
 
-@pytest.mark.parametrize("box", [1, 2, 3])
+@pytest.mark.parametrize("box,mixed", [(1, 0), (2, 0), (3, 0), (2, 5), (3, 7), (3, 2)])
 @pytest.mark.parametrize("kind", ["triangles_single", "triangles_multi", "mixed_quadrics", "random_scenes"])
-def test_device_traversal_matches_the_oracle(dev, orc, kind, box):
+def test_device_traversal_matches_the_oracle(dev, orc, kind, box, mixed):
     """The kernels' traversal source (csrc/trace_core.cuh: pair-node steps, shared-memory-style stack,
     leaf decoding, triangle / sphere / cylinder / disk tests, the finite and the NaN-faithful slab
     paths) run on the CPU over the host mirror's flattened scene with the product's own pair-node
@@ -684,9 +684,12 @@ def test_device_traversal_matches_the_oracle(dev, orc, kind, box):
     barycentrics bit for bit (phi of quadrics within the libm-free tolerance 0 here: same libm), the
     occlusion bit for all four any-hit loop shapes, ordered and unordered.  `box` = the box-test family
     (trace_core.cuh child_box): exact min / max, exact per octant, and conservative FFMA inner tests with
-    the reference's exact test applied in the leaf phase — all three must give the same bits."""
+    the reference's exact test applied in the leaf phase — all three must give the same bits.  `mixed`
+    forces the per-axis "the warp mixes signs" form of the specialised tests (a single emulated lane
+    never does by itself)."""
     from oracle import orc as O
     dev.devsrc_set_box(box)
+    dev.devsrc_force_mixed_axes(mixed)
     rng = np.random.default_rng({"triangles_single": 1, "triangles_multi": 2, "mixed_quadrics": 3, "random_scenes": 4}[kind])
     if kind == "triangles_single":
         cfgs = [scenes.config3(nx=40, nz=20, xres=16, yres=16, xs=1, ys=1)]
@@ -727,6 +730,7 @@ def test_device_traversal_matches_the_oracle(dev, orc, kind, box):
             assert dev.devsrc_trace(C.byref(f), _p(rays), rays.shape[0], mode, _p(g)) == 0
             assert np.array_equal((g[:, 0].copy().view(np.uint32) != 0xFFFFFFFF).astype(np.uint8), occ), mode
     dev.devsrc_set_box(3)
+    dev.devsrc_force_mixed_axes(0)
 
 
 @pytest.mark.parametrize("sampler", ["stratified", "ld"])
