@@ -1,20 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200 rendering back end (contract in the task prompt).
+"""bench.py — benchmark of the B200 rendering back end (contract in the task prompt).
 
-A "step" is one full frame of the hot path: BASELINE.json config 3 — a procedural 1 M-triangle
-heightfield + quad area light, Whitted/direct lighting, 1920x1080, Stratified 4x4 = 16 spp,
-box filter — i.e. 33.2 M camera rays + their shadow rays per frame.
+A "step" is one full frame of the hot path.  Default workload = BASELINE.json config 3: a procedural
+1 M-triangle heightfield + quad area light, Whitted / direct lighting, 1920x1080, Stratified 4x4 =
+16 spp, box filter — 33.2 M camera rays + their shadow rays per frame.  `--config c1|c2|c4|c5` runs
+the other BASELINE configs at their named sizes through the same code.
 
-  python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+  python bench.py --gpus N --steps K --warmup W [--config c3]   # our arm (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...        # CPU restatement of the reference
 
-metric  : Mrays/s (primary + shadow), whole job.  `value` = scene resident and film left in HBM;
-          `e2e` = same call through the C ABI with a pinned HOST film buffer (D2H inside the timed
-          region, descriptors H2D).  ms_per_step is the frame time.
-roofline: dominant kernel = k_trace (closest hit).  achieved = algorithmic bytes / device time of
-          its launches in the timed region; algorithmic bytes/ray = 32 N_nodes + 48 N_tri +
-          80 N_sph + 48 with N_* counted by the CPU oracle on a bounded sample
-          (same scene and camera at 1/16 of the pixels) and scaled by the ray count.
+metric   Mrays/s (primary + shadow), whole job.  `value`: scene resident, film left in HBM.  `e2e`:
+         the same frame through the C ABI into a pinned HOST film (D2H inside the timed region).
+N > 1    rank 0 drives all N GPUs through pbrtb200_group_render (one process, one host thread per
+         device; include/pbrtb200.h); the other ranks only join the barriers.  Every device renders a
+         row band and copies its own rows to the host film over its own PCIe link.
+roofline the traversal kernels are bound by instruction issue, not by HBM (the 112 MB scene lives in
+         L2 / L1): achieved = warp instructions per second of k_trace<closest> (instructions per ray
+         from the committed ncu capture profiles/r02_counters.json x rays of the timed frames / its
+         measured device time), peak = 148 SMs x 4 schedulers x the SM clock sampled during the run.
+         The measured DRAM traffic and the HBM fraction it implies are reported next to it.
 """
 import argparse
 import json
@@ -29,11 +33,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "config3: 1M-tri heightfield + quad area light, direct lighting, 1920x1080, 16 spp"
+WORKLOADS = {
+    "c1": "config1: 8 spheres + point light (aggregates/mod.rs:82-91 fixture), Whitted, 640x480, 4 spp",
+    "c2": "config2: BVH over 100K random triangles, primary closest hit only, 1920x1080, 1 spp",
+    "c3": "config3: 1M-tri heightfield + quad area light, direct lighting, 1920x1080, 16 spp",
+    "c4": "config4: 200K-tri ground + 20K spheres, textured matte/plastic, point + area light, 3840x2160, 64 spp",
+    "c5": "config5: 50M-tri heightfield, 4 area lights, 1920x1080, 256 spp",
+}
 
 
-def make_cfg(scale=1):
+def make_cfg(config="c3", scale=1):
     from pbrt_rust_b200 import scenes
+    if config == "c1":
+        return scenes.config1(xres=640 // scale, yres=480 // scale)
+    if config == "c2":
+        return scenes.config2(xres=1920 // scale, yres=1080 // scale)
+    if config == "c4":
+        return scenes.config4(xres=3840 // scale, yres=2160 // scale)
+    if config == "c5":
+        return scenes.config5(xres=1920 // scale, yres=1080 // scale)
     return scenes.config3(nx=1000, nz=500, xres=1920 // scale, yres=1080 // scale, xs=4, ys=4)
 
 
@@ -83,17 +101,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_sample(cfg_small, n_threads, mode, count):
-    """Oracle run on the bounded sample; returns (stats dict, seconds)."""
-    from oracle import orc
-    osc = orc.OracleScene(cfg_small["scene"])
-    oc = orc.render_config(cfg_small["camera"], cfg_small["sampler"], num_cpus=n_threads, mode=mode,
-                           n_threads=n_threads, count_traversal=count)
-    t0 = time.perf_counter()
-    res = orc.render(osc, oc)
-    return res["stats"], time.perf_counter() - t0, osc, oc
-
-
 def bytes_per_ray(st):
     """B_ray = 32 N_nodes + 48 N_tri + 80 N_sph + 48, averaged over the sample."""
     prim = (32 * st["nodes_visited"] + 48 * st["tris_tested"] + 80 * st["spheres_tested"]) / max(1, st["camera_rays"]) + 48
@@ -101,44 +108,99 @@ def bytes_per_ray(st):
     return prim, sh
 
 
+def cpu_scene(config, scale, cores, mode, count=False):
+    """(oracle scene, RenderConfig, shares_product_code).  Config 3 is built from oracle/refscene.py,
+    which needs liborc.so and numpy only; the other configs describe their scene through the api.py
+    data classes, whose constructors call the host mirror inside libpbrtb200.so (transforms, film and
+    camera descriptors — no rendering code)."""
+    from oracle import orc
+    if config == "c3":
+        from oracle import refscene
+        h, c = refscene.config3(nx=1000, nz=500, xres=1920 // scale, yres=1080 // scale, xs=4, ys=4, num_cpus=cores,
+                                mode=mode, n_threads=cores, count_traversal=count)
+        return h, c, False
+    cfg = make_cfg(config, scale)
+    c = orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=cores, mode=mode, n_threads=cores, count_traversal=count,
+                          primary_only=(config == "c2"))
+    return orc.OracleScene(cfg["scene"]), c, True
+
+
+# bounded CPU sample per config: (scale of the frame's resolution) so that one oracle frame stays in the
+# ~10-30 s range on 16 cores; c4 / c5 at full size would take minutes
+CPU_SCALE = {"c1": 1, "c2": 1, "c3": 1, "c4": 8, "c5": 8}
+
+
 def run_reference(args):
-    """CPU arm: the oracle in reference-faithful (strict) mode — the reference's own task split,
-    per-task StdRng and sub-films, one thread per host core — on a bounded sample per step."""
+    """CPU arm: the C++ restatement of the reference (oracle) in reference-faithful (strict) mode — the
+    reference's own task split, per-task StdRng and sub-films, num_tasks worker tasks on the host's
+    cores — one frame of the workload (or a bounded sample of it) per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import __graft_entry__ as g
-    g.build()
     from oracle import orc
+    orc.build()
     cores = os.cpu_count() or 1
-    cfg_s = make_cfg(scale=2)
-    osc = orc.OracleScene(cfg_s["scene"])
-    oc = orc.render_config(cfg_s["camera"], cfg_s["sampler"], num_cpus=cores, mode=1, n_threads=cores)
-    times, rays = [], 0
+    scale = CPU_SCALE[args.config] * (2 if (cores < 12 and args.config == "c3") else 1)
+    scene, rc, shares = cpu_scene(args.config, scale, cores, 1)
+    lay = orc.layout(rc)
+    times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        res = orc.render(osc, oc)
+        orc.render(scene, rc)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
-            # shadow rays are not counted in the plain timing run; count once below
-    oc_c = orc.render_config(cfg_s["camera"], cfg_s["sampler"], num_cpus=cores, mode=1, n_threads=cores,
-                             count_traversal=True)
-    st = orc.render(osc, oc_c)["stats"]
+    _, rc_c, _ = cpu_scene(args.config, scale, cores, 1, count=True) if False else (None, None, None)
+    rc.count_traversal = 1  # one counted frame: shadow rays are only counted with the traversal counters on
+    st = orc.render(scene, rc)["stats"]
     rays = st["camera_rays"] + st["shadow_rays"]
     ms = 1e3 * float(np.mean(times))
     v = rays / (ms * 1e-3) / 1e6
-    sample = "same scene+camera at 960x540x16spp (1/4 of the frame's pixels) per step, strict task mode"
+    sample = ("the full frame" if scale == 1 else f"same scene and camera at 1/{scale} of the resolution "
+              f"(1/{scale * scale} of the pixels)") + f" per step, strict task mode ({lay['num_tasks']} tasks)"
     line = {
         "impl": "reference", "metric": "Mrays/s (primary+shadow)", "value": v, "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": {"workload": WORKLOADS[args.config], "sample": sample, "same_config": scale == 1,
+                                        "shares_code_with_gpu_arm": shares},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "busy_threads": min(cores, lay["num_tasks"]),
+                         "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "C++ restatement of pbrt_rust's algorithm (oracle); the Rust crate cannot be built here",
+        "note": "C++ restatement of pbrt_rust's algorithm (oracle); the Rust crate cannot be built here. Strict mode keeps the "
+                "reference's task count (ceil(log2(..)), sampler_renderer.rs:41-44): only that many threads are ever busy.",
     }
     print(json.dumps(line))
+
+
+def cpu_baseline_leg(config, n_cam_per_frame):
+    """The CPU oracle timed on this box's host cores on a bounded sample of the workload: strict mode
+    (the reference's own task count) and an all-cores run (row bands over every core), plus the
+    traversal counts of SURVEY §8d."""
+    from oracle import orc
+    cores = os.cpu_count() or 1
+    scale = CPU_SCALE[config] * (2 if (cores < 12 and config == "c3") else 1)
+    scene, rc, _ = cpu_scene(config, scale, cores, 0, count=True)
+    t0 = time.perf_counter()
+    st_c = orc.render(scene, rc)["stats"]                 # counts, default mode (all cores)
+    b_prim, b_sh = bytes_per_ray(st_c)
+    rays = st_c["camera_rays"] + st_c["shadow_rays"]
+    rc.count_traversal = 0
+    rc.mode = 1
+    lay = orc.layout(rc)
+    t0 = time.perf_counter()
+    orc.render(scene, rc)
+    dt_strict = time.perf_counter() - t0
+    rc.mode = 0
+    t0 = time.perf_counter()
+    orc.render(scene, rc)
+    dt_all = time.perf_counter() - t0
+    sample = "the full frame" if scale == 1 else f"same scene and camera at 1/{scale} of the resolution (1/{scale * scale} of the pixels)"
+    return {"value": rays / dt_strict / 1e6, "unit": "Mrays/s", "cores": cores, "busy_threads": min(cores, lay["num_tasks"]),
+            "kind": "port", "sample": sample + f", strict task mode ({lay['num_tasks']} tasks as the reference computes them)",
+            "seconds": dt_strict,
+            "all_cores": {"value": rays / dt_all / 1e6, "unit": "Mrays/s", "busy_threads": cores, "seconds": dt_all,
+                          "mode": "same frame, row bands over every host core (not the reference's task split)"}}, b_prim, b_sh
 
 
 def main():
@@ -147,6 +209,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / oracle-count leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -166,211 +229,144 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
     torch.cuda.set_device(local)
-    import pbrt_rust_b200 as pb
-
-    cfg = make_cfg()
-    film = cfg["film"]
-    r = pb.GpuRenderer(cfg["sampler"], cfg["camera"], cfg["integrator"], num_cpus=8, device=local)
-    stream = torch.cuda.current_stream()
-    r.ctx.set_stream(stream.cuda_stream)
-    t0 = time.perf_counter()
-    r.preprocess(cfg["scene"])  # host BVH build + flatten + upload (once, like scene creation)
-    t_scene = time.perf_counter() - t0
-    h, w = film.shape
-    from pbrt_rust_b200 import multigpu
-    # N > 1 partition.  "bands" (default): contiguous row bands whose boundaries follow the ranks'
-    # measured frame times during the warm-up frames (multigpu.BandBalancer) and are frozen for the
-    # timed frames; PBRTB200_PARTITION=cyclic: 64x64 tiles, tile -> rank = id mod N.
-    partition = os.environ.get("PBRTB200_PARTITION", "bands") if world > 1 else "whole"
-    balancer = multigpu.BandBalancer(film.get_pixel_extent(), world) if partition == "bands" else None
-    tiles = None
-    if world > 1:
-        tiles = balancer.tiles_for(rank) if balancer else multigpu.partition_tiles(film.get_pixel_extent(), rank, world)
-    d_film = torch.zeros(h * w * 4, dtype=torch.float32, device="cuda")
-    h_film_t = torch.zeros(h * w * 4, dtype=torch.float32).pin_memory()
-    h_film = h_film_t.numpy().reshape(h, w, 4)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # N > 1 film gather.  Default "p2p": rank 0 shares its film buffer over CUDA IPC and every
-    # rank's film kernel stores its owned tiles straight into it over NVLink (two buffers,
-    # alternating, so rank 0 can still read frame k while frame k+1 is written); the only other
-    # per-frame communication is a barrier.  PBRTB200_GATHER=nccl: reduce(SUM) of zero-padded films.
-    gather = os.environ.get("PBRTB200_GATHER", "p2p") if world > 1 else "none"
-    peers, frame_no = [], [0]
-    if gather == "p2p":
-        peers = [multigpu.PeerFilm(r.ctx, h * w, dist, torch.device("cuda", local)) for _ in range(2)]
-        if not all(p.ok for p in peers):  # no CUDA IPC / peer access between these GPUs (same on every rank)
-            if rank == 0:
-                print("bench: CUDA IPC film sharing unavailable; using the NCCL gather", file=sys.stderr)
-            gather, peers = "nccl", []
-    peer_views = [p.tensor() for p in peers] if (gather == "p2p" and rank == 0) else []
-    fence = torch.zeros(1, dtype=torch.int32, device="cuda")
+    if rank != 0:
+        # Ranks 1..N-1 hold their GPU for the job and join the barriers around the timed regions; rank 0
+        # drives every GPU through the C ABI's group call (one process, one host thread per device).
+        for _ in range(4):
+            barrier()
+        dist.destroy_process_group()
+        return
+
+    import pbrt_rust_b200 as pb
+    cfg = make_cfg(args.config)
+    film = cfg["film"]
+    devices = list(range(world))
+    r = pb.GpuRenderer(cfg["sampler"], cfg["camera"], cfg["integrator"], num_cpus=8, devices=devices)
+    t0 = time.perf_counter()
+    r.preprocess(cfg["scene"])  # host BVH build + flatten + upload to every device (once, like scene creation)
+    t_scene = time.perf_counter() - t0
+    h, w = film.shape
+    primary_only = args.config == "c2"
+    d_film = torch.zeros(h * w * 4, dtype=torch.float32, device="cuda:0")
+    h_film_t = torch.zeros(h * w * 4, dtype=torch.float32).pin_memory()
+    h_film = h_film_t.numpy().reshape(h, w, 4)
+    spp = cfg["sampler"].samples_per_pixel()
+    e = cfg["sampler"].ext
+    n_samples = (e[1] - e[0]) * (e[3] - e[2]) * spp
+    hits_host = np.zeros(n_samples, dtype=pb.HIT_DTYPE) if primary_only else None
 
     def frame(resident):
-        if world == 1:
-            # resident: film left in HBM; e2e: C ABI with a host film buffer (D2H inside the call)
-            r.render(cfg["scene"], tiles=tiles, out=d_film if resident else h_film)
+        if primary_only:  # config 2: camera samples -> closest hits (hit records to the host in the e2e leg)
+            r.primary_hits(cfg["scene"])
             return r.last_stats
-        k = frame_no[0] & 1
-        frame_no[0] += 1
-        if gather == "p2p":
-            r.render(cfg["scene"], tiles=tiles, out=peers[k].ptr, keep_others=True)
-            # frame fence: a 4-byte all-reduce ordered on the stream after this rank's film kernel;
-            # when it completes, every rank's stores have landed in rank 0's HBM (no host block)
-            dist.all_reduce(fence, op=dist.ReduceOp.SUM)
-            src = peer_views[k] if rank == 0 else None
-        else:
-            r.render(cfg["scene"], tiles=tiles, out=d_film)
-            dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)
-            src = d_film
-        if not resident:
-            # what a user of N GPUs receives: the finished frame in (pinned) host memory on rank 0
-            if rank == 0:
-                h_film_t.copy_(src, non_blocking=True)
-            torch.cuda.synchronize()
+        r.render(cfg["scene"], out=d_film if resident else h_film)
         return r.last_stats
 
-    def rank_times(ms):
-        t = torch.zeros(world, dtype=torch.float64, device="cuda")
-        t[rank] = ms
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return [float(x) for x in t.cpu()]
-
-    def rebalance(frames=12):
-        """Warm-up only: move the band boundaries until the slowest rank is within 2 % of the mean."""
-        nonlocal tiles
-        for _ in range(frames):
-            times = rank_times(frame(True)["ms_total"])
-            if balancer.imbalance(times) < 1.02 or not balancer.update(times):
-                break
-            tiles = balancer.tiles_for(rank)
-
     def timed(resident, steps, warmup):
-        if balancer and resident:
-            rebalance()
         for _ in range(warmup):
             frame(resident)
         acc = {"ms_trace": 0.0, "ms_shadow": 0.0, "ms_total": 0.0, "ms_raygen": 0.0, "ms_shade": 0.0,
-               "ms_film": 0.0, "kernel_launches": 0, "rays": 0, "camera_rays": 0, "shadow_rays": 0}
+               "ms_film": 0.0, "kernel_launches": 0, "camera_rays": 0, "shadow_rays": 0}
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        t0 = time.perf_counter()
         for _ in range(steps):
             st = frame(resident)
-            for k in ("ms_trace", "ms_shadow", "ms_total", "ms_raygen", "ms_shade", "ms_film", "kernel_launches",
-                      "camera_rays", "shadow_rays"):
+            for k in acc:
                 acc[k] += st[k]
-        e1.record(stream)
+        torch.cuda.synchronize()   # (every frame call is synchronous: the film is complete when it returns)
+        ms = (time.perf_counter() - t0) * 1e3 / steps
         barrier()
-        ms = e0.elapsed_time(e1) / steps
-        t = torch.tensor([ms, float(acc["camera_rays"]), float(acc["shadow_rays"])], dtype=torch.float64,
-                         device="cuda")
-        if world > 1:
-            mx = t.clone()
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            sm = t.clone()
-            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-            ms, cam, sh = float(mx[0]), float(sm[1]), float(sm[2])
-        else:
-            cam, sh = float(t[1]), float(t[2])
-        # Tile halos make ranks re-evaluate a few boundary samples; count every ray of the frame once
+        # Band halos make devices re-evaluate a few boundary samples; count every ray of the frame once
         # (scale to the frame's own camera-sample count) so that N-GPU values stay comparable.
-        e = cfg["sampler"].ext
-        frame_cam = float((e[1] - e[0]) * (e[3] - e[2]) * cfg["sampler"].samples_per_pixel()) * steps
-        rays = (cam + sh) * (frame_cam / cam)
+        cam = float(acc["camera_rays"])
+        rays = (cam + float(acc["shadow_rays"])) * (float(n_samples) * steps / max(cam, 1.0))
         return ms, rays / steps, acc
 
-    clk = ClockSampler(local)
+    clk = ClockSampler(0)
     clk.start()
     t_wait = time.perf_counter()
     while clk.proc and not clk.rows and time.perf_counter() - t_wait < 3.0:
         time.sleep(0.02)  # nvidia-smi needs a moment before its first sample
-    ms, rays_per_frame, acc = timed(True, args.steps, args.warmup)
+    # warm-up frames also let the group settle its row bands on measured device times
+    ms, rays_per_frame, acc = timed(True, args.steps, max(args.warmup, 8) if world > 1 else args.warmup)
     clocks = clk.stop()
-    per_rank = rank_times(acc["ms_total"] / args.steps) if world > 1 else None
-    ms_e2e, rays_e2e, _ = timed(False, args.steps, 1)
+    bands = r.ctx.bands() if world > 1 else None
+    ms_e2e, rays_e2e, acc_e = timed(False, args.steps, 2)
 
-    # full-frame sanity: the last e2e film must be a plausible image
-    if rank == 0:
+    if not primary_only:  # full-frame sanity: the last e2e film must be a plausible image
         wsum = h_film[..., 3]
         assert np.isfinite(h_film).all() and wsum.min() > 0 and h_film[..., :3].max() > 0
 
     value = rays_per_frame / (ms * 1e-3) / 1e6
     e2e_v = rays_e2e / (ms_e2e * 1e-3) / 1e6
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    counters = {}
+    try:
+        counters = json.load(open(os.path.join(ROOT, "profiles", "r02_counters.json"))).get(args.config, {})
+    except Exception:
+        pass
 
-    roofline, cpu_baseline = None, None
+    n_cam = acc["camera_rays"] / args.steps
+    t_trace = acc["ms_trace"] / args.steps * 1e-3
+    sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9  # G warp-instructions / s
+    ipr = counters.get("closest_warp_inst_per_ray")
+    traffic = counters.get("closest_dram_bytes_per_launch")
+    achieved = (ipr * n_cam / t_trace / 1e9) if (ipr and t_trace > 0 and world == 1) else None
+    roofline = {
+        "bound": "issue", "kernel": "k_trace<closest> (all launches of one frame)",
+        "achieved": achieved, "peak": issue_peak, "unit": "G warp-inst/s",
+        "frac": (achieved / issue_peak) if achieved else None,
+        "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
+        "warp_inst_per_ray": ipr, "counters_source": "profiles/r02_counters.json (ncu smsp__inst_executed.sum of the same command)" if ipr else None,
+        "traffic": traffic,
+        "hbm": {"achieved": (traffic / t_trace / 1e9) if (traffic and t_trace > 0 and world == 1) else None, "peak": hbm_peak,
+                "unit": "GB/s", "peak_source": peak_src,
+                "frac": (traffic / t_trace / 1e9 / hbm_peak) if (traffic and t_trace > 0 and world == 1) else None},
+        "kernel_ms_per_frame": t_trace * 1e3, "shadow_kernel_ms_per_frame": acc["ms_shadow"] / args.steps,
+        "shadow_warp_inst_per_ray": counters.get("any_warp_inst_per_ray"),
+    }
+    cpu_baseline = None
     if not args.no_cpu and world == 1:
-        cores = os.cpu_count() or 1
-        # bounded sample: the full frame costs ~7 s on 16 host cores; halve the resolution on
-        # smaller hosts so the CPU leg stays within ~10-30 s
-        scale = 1 if cores >= 12 else 2
-        cfg_s = make_cfg(scale=scale)
-        st_c, _, osc, _ = oracle_sample(cfg_s, cores, 0, True)       # counts (default mode)
-        b_prim, b_sh = bytes_per_ray(st_c)
-        from oracle import orc
-        oc = orc.render_config(cfg_s["camera"], cfg_s["sampler"], num_cpus=cores, mode=1, n_threads=cores)
-        t0 = time.perf_counter()
-        orc.render(osc, oc)
-        dt = time.perf_counter() - t0
-        sample = ("the full 1920x1080x16spp frame, strict task mode" if scale == 1 else
-                  "same scene+camera at 960x540x16spp (1/4 of the frame's pixels), strict task mode")
-        cpu_baseline = {"value": (st_c["camera_rays"] + st_c["shadow_rays"]) / dt / 1e6, "unit": "Mrays/s",
-                        "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
-        n_cam = acc["camera_rays"] / args.steps
-        alg_bytes = b_prim * n_cam                                     # per frame, closest-hit kernel
-        t_trace = acc["ms_trace"] / args.steps * 1e-3
-        achieved = alg_bytes / t_trace / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_trace_closest_bytes_per_frame")
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": "k_trace<closest> (all launches of one frame)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src,
-                    "alg_bytes_per_primary_ray": b_prim, "alg_bytes_per_shadow_ray": b_sh,
-                    "kernel_ms_per_frame": t_trace * 1e3,
-                    "shadow_kernel_ms_per_frame": acc["ms_shadow"] / args.steps,
-                    "shadow_achieved": b_sh * (acc["shadow_rays"] / args.steps) / max(1e-9, acc["ms_shadow"] / args.steps * 1e-3) / 1e9}
+        cpu_baseline, b_prim, b_sh = cpu_baseline_leg(args.config, n_cam)
+        roofline["algorithmic_bytes_per_primary_ray"] = b_prim   # SURVEY §8d; far above the DRAM traffic because
+        roofline["algorithmic_bytes_per_shadow_ray"] = b_sh      # the scene is L2 / L1-resident
+        roofline["algorithmic_gbps"] = b_prim * n_cam / t_trace / 1e9 if t_trace > 0 else None
 
     line = {
         "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_frame": rays_per_frame, "tiles": partition,
-                   "l2": "per-frame working set (112 MB scene + >2 GB wavefront buffers) exceeds the 126 MB L2; no explicit flush",
+        "config": {"workload": WORKLOADS[args.config], "rays_per_frame": rays_per_frame,
+                   "l2": "per-frame working set (scene + >1 GB of wavefront buffers) exceeds the 126 MB L2; no explicit flush",
                    "scene_build_upload_s": t_scene,
-                   "partition": {"whole": "whole film", "cyclic": "64x64 tiles, cyclic",
-                                 "bands": "row bands balanced on measured rank times during warm-up"}[partition],
-                   "band_rows": balancer.b if balancer else None,
-                   "per_rank_device_ms": per_rank,
-                   "film_gather": {"none": "single GPU", "p2p": "film kernels store owned tiles into rank 0's HBM over NVLink (CUDA IPC) + barrier",
-                                   "nccl": "reduce(SUM) of zero-padded films (NCCL)"}[gather]},
+                   "partition": "whole film" if world == 1 else "row bands of equal cost (cost probe, then measured device times), one per GPU",
+                   "band_rows": bands[0] if bands else None, "per_device_ms": bands[1] if bands else None,
+                   "film_gather": "single GPU" if world == 1 else
+                                  "value: film kernels store their rows into GPU 0's film over NVLink (peer access); "
+                                  "e2e: every GPU copies its own rows into the host film over its own PCIe link",
+                   "driver": "one process drives all GPUs (pbrtb200_group_render); ranks > 0 only join the barriers" if world > 1 else "single context"},
         "clocks": clocks,
         "e2e": {"value": e2e_v, "unit": "Mrays/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": 1024 + 64 + 44 + 12 + 128 + (16 * len(tiles) if tiles else 0),
-                "d2h_bytes_per_step": h * w * 16},
+                "h2d_bytes_per_step": (1024 + 64 + 44 + 12 + 128) * world,
+                "d2h_bytes_per_step": int(n_samples * 16) if primary_only else h * w * 16},
         "gpu_launches": int(acc["kernel_launches"]),
         "stage_ms_per_frame": {k: acc[k] / args.steps for k in ("ms_raygen", "ms_trace", "ms_shade", "ms_shadow", "ms_film", "ms_total")},
+        "roofline": roofline,
     }
-    if roofline:
-        line["roofline"] = roofline
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line))

@@ -290,6 +290,15 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
                     const pbrtb200_tileset* tiles, float* out_xyzw, int out_is_device,
                     pbrtb200_stats* stats);
 
+/* Where does a frame's time go?  row_cost[y] (film->y_pixel_count floats, host memory) = traversal
+ * cost (BVH node steps + primitive tests of one camera ray and one shadow ray per light, plus a
+ * constant per sample) summed over the probe pixels of film row y, probing every stride-th pixel in
+ * x and y (rows in between repeat their probe row).  Relative numbers only.  It is what
+ * pbrtb200_group_render cuts row bands of equal cost with before a frame has ever been timed; the
+ * reference balances by work stealing over its task queue (src/sampler_renderer.rs:168-173). */
+int pbrtb200_cost_profile(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb200_film* film, int stride,
+                          float* row_cost);
+
 /* Multi-GPU film gather without a collective (ownership of film pixels is disjoint,
  * the reference merges sub-films by pixel ownership, film.rs:149-186).  One process per GPU: the
  * gathering rank creates a film buffer and exports a CUDA IPC handle; every other rank opens it
@@ -304,6 +313,37 @@ int pbrtb200_peer_film_create(pbrtb200_ctx* ctx, uint64_t n_pixels, void** dev_p
                               unsigned char handle64[64]);
 int pbrtb200_peer_film_open(pbrtb200_ctx* ctx, const unsigned char handle64[64], void** dev_ptr);
 int pbrtb200_peer_film_close(pbrtb200_ctx* ctx, void* dev_ptr);
+
+/* ---- all the GPUs of one box behind ONE call ---------------------------------------------------
+ * SamplerRenderer::render is one call that fans the frame out to every worker of the machine and
+ * returns the finished film (src/sampler_renderer.rs:147-182; the pool of num_cpus threads at
+ * :168-173; trait at src/renderer.rs:8-10).  A group is that for GPUs: one process, one context and
+ * one host thread per device, the scene replicated on every device.  A frame is cut into contiguous
+ * row bands of equal COST (first frame of a view: pbrtb200_cost_profile; later frames of the same
+ * view: the bands follow each device's measured time), every device renders its band with
+ * pbrtb200_render's own pipeline and
+ *   - out_is_device == 0: copies ITS OWN rows straight into the caller's host film over its own PCIe
+ *     link (N links in parallel, no gather, no collective);
+ *   - out_is_device != 0: out_xyzw is a buffer on the group's FIRST device; the other devices' film
+ *     kernels store their rows into it over NVLink (peer access).
+ * Every film pixel is produced by exactly one device with the summation order of a single-GPU
+ * render: the film is bit-identical to pbrtb200_render's for any number of devices.
+ * devices == NULL: devices 0 .. n_devices-1.  stats: rays / launches summed over the devices, the
+ * ms_* fields are the slowest device's.  Errors: as pbrtb200_render; pbrtb200_group_last_error names
+ * the failing device.  A group call is synchronous; one call at a time per group.                  */
+typedef struct pbrtb200_group pbrtb200_group;
+int pbrtb200_group_create(const int* devices, int n_devices, pbrtb200_group** out);
+void pbrtb200_group_destroy(pbrtb200_group* g);
+const char* pbrtb200_group_last_error(const pbrtb200_group* g); /* g may be NULL (create errors) */
+int pbrtb200_group_size(const pbrtb200_group* g);
+pbrtb200_ctx* pbrtb200_group_ctx(pbrtb200_group* g, int i); /* device i's context (borrowed) */
+int pbrtb200_group_upload_scene(pbrtb200_group* g, const pbrtb200_scene* scene);
+int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const pbrtb200_sampler* smp,
+                          const pbrtb200_film* film, const pbrtb200_integrator* integ, float* out_xyzw,
+                          int out_is_device, pbrtb200_stats* stats);
+/* Row bands of the last frame: bounds[0 .. n_devices] (film rows, bounds[i] .. bounds[i+1] on device i)
+ * and each device's device time in ms; either pointer may be NULL. */
+int pbrtb200_group_bands(const pbrtb200_group* g, int32_t* bounds, float* device_ms);
 
 /* Scene::intersect for a batch of rays (src/scene.rs:60-63).  *_is_device: pointers are device
  * memory on the ctx's device (used by bench.py's resident-input arm).                           */

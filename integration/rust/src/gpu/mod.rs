@@ -213,7 +213,7 @@ impl Renderer for GpuRenderer {
         let rc = unsafe {
             match &self.backend {
                 &Backend::Single(ctx) => pbrtb200_render(ctx, &cam, &smp, &fd, &integ, ::std::ptr::null(), xyzw.as_mut_ptr(), 0, &mut st),
-                &Backend::Group(g) => pbrtb200_group_render(g, &cam, &smp, &fd, &integ, xyzw.as_mut_ptr(), &mut st),
+                &Backend::Group(g) => pbrtb200_group_render(g, &cam, &smp, &fd, &integ, xyzw.as_mut_ptr(), 0, &mut st),
             }
         };
         self.last_stats = st;

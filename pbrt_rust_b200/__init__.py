@@ -4,7 +4,7 @@ include/pbrtb200.h); this package is the ctypes binding and a data-only mirror o
 scene/camera/sampler constructors.  There is no CPU fallback: the library must be built and a CUDA
 device must be present to render."""
 from ._ffi import LIB_PATH, MISS, lib
-from .api import (HIT_DTYPE, AreaLight, Camera, Context, DevicePtr, Film, Filter, GpuRenderer, HostScene, Light,
+from .api import (HIT_DTYPE, AreaLight, Camera, Context, DevicePtr, Film, Filter, GpuRenderer, Group, HostScene, Light,
                   Material, PbrtError, PlanarMapping2D, Primitive, Sampler, Scene, Shape,
                   SurfaceIntegrator, Texture, Transform, UVMapping2D, film_to_rgb, rgb_to_bytes, write_image)
 

@@ -170,6 +170,15 @@ SYMBOLS = [
     ("pbrtb200_peer_film_open", i32, [_vp, C.c_char_p, P(_vp)]),
     ("pbrtb200_peer_film_close", i32, [_vp, _vp]),
     ("pbrtb200_film_develop", i32, [_vp, _vp, C.c_int, u64, _vp, _vp, C.c_int]),
+    ("pbrtb200_cost_profile", i32, [_vp, P(Camera), P(Film), C.c_int, _fp]),
+    ("pbrtb200_group_create", i32, [P(C.c_int), C.c_int, P(_vp)]),
+    ("pbrtb200_group_destroy", None, [_vp]),
+    ("pbrtb200_group_last_error", C.c_char_p, [_vp]),
+    ("pbrtb200_group_size", i32, [_vp]),
+    ("pbrtb200_group_ctx", _vp, [_vp, C.c_int]),
+    ("pbrtb200_group_upload_scene", i32, [_vp, P(Scene)]),
+    ("pbrtb200_group_render", i32, [_vp, P(Camera), P(Sampler), P(Film), P(Integrator), _vp, C.c_int, P(Stats)]),
+    ("pbrtb200_group_bands", i32, [_vp, P(i32), _fp]),
 ]
 
 _lib = None

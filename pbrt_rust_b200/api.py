@@ -594,6 +594,48 @@ class Context:
             pass
 
 
+class Group:
+    """pbrtb200_group: every GPU in `devices` behind one render call (include/pbrtb200.h), the
+    counterpart of the reference's thread pool behind SamplerRenderer::render
+    (src/sampler_renderer.rs:168-173).  Duck-types Context for GpuRenderer."""
+
+    def __init__(self, devices):
+        self.devices = list(devices)
+        self.h = C.c_void_p()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        rc = lib().pbrtb200_group_create(arr, len(self.devices), C.byref(self.h))
+        if rc:
+            raise PbrtError(rc, lib().pbrtb200_group_last_error(None).decode())
+        self.scene_key, self.host_scene = None, None
+
+    def check(self, rc):
+        if rc:
+            raise PbrtError(rc, lib().pbrtb200_group_last_error(self.h).decode())
+
+    def upload(self, host_scene, scene_key=None):
+        self.scene_key, self.host_scene = None, None
+        self.check(lib().pbrtb200_group_upload_scene(self.h, host_scene.flat))
+        self.scene_key, self.host_scene = scene_key, host_scene
+
+    def bands(self):
+        """(row bounds of the last frame, per-device device ms)"""
+        n = len(self.devices)
+        b, t = (C.c_int32 * (n + 1))(), np.zeros(n, np.float32)
+        self.check(lib().pbrtb200_group_bands(self.h, b, _fp(t)))
+        return list(b), t.tolist()
+
+    def close(self):
+        if self.h:
+            lib().pbrtb200_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DevicePtr:
     """A raw device address (e.g. a peer GPU's film mapped with pbrtb200_peer_film_open)."""
 
@@ -623,12 +665,14 @@ class GpuRenderer:
     (sampler, camera, surface integrator; the volume integrator is a stub in the reference), and
     `render(scene)` replaces `Renderer::render` (src/renderer.rs:9)."""
 
-    def __init__(self, sampler, camera, surf, vol=None, num_cpus=8, device=0, ctx=None):
+    def __init__(self, sampler, camera, surf, vol=None, num_cpus=8, device=0, ctx=None, devices=None):
+        """devices: a list of CUDA device indices renders every frame on all of them (Group)."""
         self.sampler, self.camera, self.surf = sampler, camera, surf
         film = camera.film
         # sampler_renderer.rs:39-44 (num_cpus::get() is a property of the host running the crate)
         self.num_tasks = int(lib().pbh_num_tasks(num_cpus, film.x_res * film.y_res))
-        self.ctx = ctx or Context(device)
+        self.ctx = ctx or (Group(devices) if devices is not None and len(devices) > 1 else
+                           Context(devices[0] if devices else device))
         self.last_stats = None
 
     @property
@@ -669,9 +713,15 @@ class GpuRenderer:
         st = _ffi.Stats()
         smp = self.sampler_desc()
         p, is_dev = _ptr(out)
-        rc = lib().pbrtb200_render(self.ctx.h, C.byref(self.camera.desc), C.byref(smp), C.byref(film.desc),
-                                   C.byref(integ), C.byref(ts) if ts is not None else None, p, is_dev,
-                                   C.byref(st))
+        if isinstance(self.ctx, Group):
+            if ts is not None:
+                raise PbrtError(_ffi.EINVAL, "a Group partitions the film itself: tiles are not accepted")
+            rc = lib().pbrtb200_group_render(self.ctx.h, C.byref(self.camera.desc), C.byref(smp), C.byref(film.desc),
+                                             C.byref(integ), p, is_dev, C.byref(st))
+        else:
+            rc = lib().pbrtb200_render(self.ctx.h, C.byref(self.camera.desc), C.byref(smp), C.byref(film.desc),
+                                       C.byref(integ), C.byref(ts) if ts is not None else None, p, is_dev,
+                                       C.byref(st))
         self.last_stats = st.as_dict()
         self.ctx.check(rc)
         return out
@@ -728,6 +778,16 @@ class GpuRenderer:
         self.ctx.check(rc)
         return occluded
 
+
+    def cost_profile(self, scene, stride=4):
+        """pbrtb200_cost_profile: relative cost of each film row (what Group balances its bands with)."""
+        self.preprocess(scene)
+        film = self.camera.film
+        out = np.zeros(film.shape[0], np.float32)
+        h = lib().pbrtb200_group_ctx(self.ctx.h, 0) if isinstance(self.ctx, Group) else self.ctx.h
+        rc = lib().pbrtb200_cost_profile(h, C.byref(self.camera.desc), C.byref(film.desc), stride, _fp(out))
+        self.ctx.check(rc)
+        return out
 
     def develop(self, film, want_rgb=False):
         """Film::write_image's pixel pipeline on the device (film.rs:316-354 as intended, D6):

@@ -77,6 +77,7 @@ struct pbrtb200_ctx {
   cudaStream_t copy_stream = nullptr; // film bands travel to the host while later chunks render
   std::vector<cudaEvent_t> band_events;
   std::vector<uint32_t> rows_ready;   // per sampler row: list pixels that must be done (prefix max)
+  std::vector<uint32_t> row_first;    // per sampler row r: smallest list index of any pixel in rows >= r
   std::string err;
   // scene
   bool has_scene = false, has_spheres = false, multi_leaf = false;
@@ -96,7 +97,7 @@ struct pbrtb200_ctx {
   bool halton_valid = false;   // d_hcounts / d_hidx hold the binned candidate indices of the list
   uint32_t halton_cap = 0;
   uint64_t halton_total = 0;
-  DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_lightu, d_edge, d_rad, d_hits,
+  DevBuf d_pixels, d_pix_index, d_task_keys, d_img, d_lens, d_time, d_lightu, d_edge, d_rec, d_terms, d_hits,
       d_sq_rays, d_sq_slots, d_film, d_rects, d_rect_prefix, d_ctrl, d_rays_in, d_occ, d_out_a,
       d_out_b, d_out_c;
   // cached pixel work list
@@ -174,15 +175,15 @@ bool scene_needs_ext(const pbrtb200_scene* s) {
   return false;
 }
 
-// Box-test family of the traversal kernels (trace_core.cuh child_box): 3 = octant-specialised FFMA
-// tests for inner nodes + the reference's exact test in the leaf phase (default), 2 = exact tests
-// specialised per octant, 1 = exact min / max tests.  All three produce the same hits bit for bit;
-// PBRTB200_BOX selects one for A/B measurements.
+// Box-test family of the traversal kernels (trace_core.cuh child_box): 2 = exact tests specialised
+// per sign of 1/d (default), 3 = FFMA tests for inner nodes + the reference's exact test in the leaf
+// phase, 1 = exact min / max tests.  All three produce the same hits bit for bit; PBRTB200_BOX
+// selects one for A/B measurements.
 int trace_box_family() {
   static const int box = [] {
     const char* v = std::getenv("PBRTB200_BOX");
-    const int b = v && *v ? std::atoi(v) : 3;
-    return (b >= 1 && b <= 3) ? b : 3;
+    const int b = v && *v ? std::atoi(v) : 2;
+    return (b >= 1 && b <= 3) ? b : 2;
   }();
   return box;
 }
@@ -372,6 +373,16 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
     }
     ctx->rows_ready[(size_t)yy] = m;
   }
+  // row_first[r] = first list pixel still needed once everything above sampler row r is filtered
+  ctx->row_first.assign((size_t)sh + 1, (uint32_t)list.size());
+  for (int yy = sh - 1; yy >= 0; --yy) {
+    uint32_t m = ctx->row_first[(size_t)yy + 1];
+    for (int xx = 0; xx < sw; ++xx) {
+      const int32_t li = index[(size_t)yy * sw + (size_t)xx];
+      if (li >= 0) m = std::min(m, (uint32_t)li);
+    }
+    ctx->row_first[(size_t)yy] = m;
+  }
   if (upload(ctx, ctx->d_pixels, list.data(), list.size())) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_pix_index, index.data(), index.size())) return PBRTB200_ENODEV;
   if (upload(ctx, ctx->d_task_keys, keys.data(), keys.size())) return PBRTB200_ENODEV;
@@ -463,14 +474,18 @@ struct StageTimer {
 // of a persistent trace kernel costs ~40 us of ramp and tail; profiles/r01_notes.md).  render()
 // halves it until the chunk-local buffers fit kChunkBudgetBytes (many light slots).
 constexpr int kChunkLog2Default = 25;
-constexpr uint64_t kChunkBudgetBytes = 8ull << 30;
-uint64_t chunk_samples() {
-  static const int lg = [] {
-    const char* v = std::getenv("PBRTB200_CHUNK_LOG2");
-    const int x = v ? std::atoi(v) : kChunkLog2Default;
-    return (x >= 16 && x <= 30) ? x : kChunkLog2Default;
-  }();
-  return 1ull << lg;
+constexpr uint64_t kChunkBudgetBytes = 4ull << 30;   // chunk-local buffers (hits, shadow queue, terms)
+// Per-sample frame buffers larger than this go into the pixel ring (render()).  PBRTB200_FRAME_BUDGET_MB
+// overrides it (read per call: the tests force the ring on small frames with it).
+uint64_t frame_budget_bytes() {
+  const char* v = std::getenv("PBRTB200_FRAME_BUDGET_MB");
+  const long long mb = v && *v ? std::atoll(v) : 4096;
+  return (uint64_t)std::max(1ll, mb) << 20;
+}
+uint64_t chunk_samples() {  // (read per call: the tests shrink it to run several chunks on small frames)
+  const char* v = std::getenv("PBRTB200_CHUNK_LOG2");
+  const int x = v && *v ? std::atoi(v) : kChunkLog2Default;
+  return 1ull << ((x >= 10 && x <= 30) ? x : kChunkLog2Default);
 }
 
 }  // namespace
@@ -1174,35 +1189,62 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   };
   const bool full = cam->lens_radius > 0.0f || smp->kind == PBRTB200_SAMPLER_LD;
   const uint32_t slots = std::max(1u, ctx->sc.light_slots);
-  const uint32_t le_slot = ctx->sc.area_sample_pairs ? 1u : 0u;
-  const uint32_t rad_slots = ctx->sc.n_lights ? ctx->sc.light_slots + le_slot : 0u;
+  const bool lit = ctx->sc.n_lights > 0;
+  const bool multi_slot = lit && slots > 1;  // several radiance terms per sample: folded per chunk (k_fold)
+  const uint32_t pairs = ctx->sc.area_sample_pairs;
   if (ctx->sc.n_lights > PB_MAX_FOLD_LIGHTS) FAIL(PBRTB200_EINVAL, "more than 64 lights");
-  if (ns * (uint64_t)std::max(1u, rad_slots) >= 0xFFFFFFFFull)
-    FAIL(PBRTB200_EINVAL, "frame has more than 2^32 radiance terms; render it in tiles");
+  if (npix >= 0x7FFFFFFFull) FAIL(PBRTB200_EINVAL, "more than 2^31 sampler pixels");
 
+  // ---- wavefront sizing -------------------------------------------------------------------------
+  // Chunk-local buffers (hit records, shadow queue, radiance terms of multi-slot scenes) are bounded
+  // by kChunkBudgetBytes; shadow-queue slot words index terms with 30 bits.
+  const uint64_t chunk_bytes_per_sample = sizeof(pbrtb200_hit16) + (lit ? (uint64_t)slots * (sizeof(pbrtb200_ray32) + sizeof(uint32_t)) : 0) +
+                                          (multi_slot ? (uint64_t)slots * sizeof(float4) : 0);
   uint64_t chunk_cap = chunk_samples();
-  while (chunk_cap > (1ull << 20) &&
-         chunk_cap * (sizeof(pbrtb200_hit16) + (uint64_t)slots * (sizeof(pbrtb200_ray32) + sizeof(uint32_t))) > kChunkBudgetBytes)
+  while (chunk_cap > (1ull << 10) &&
+         (chunk_cap * chunk_bytes_per_sample > kChunkBudgetBytes || chunk_cap * slots > PB_SQ_INDEX))
     chunk_cap >>= 1;
   uint64_t chunk_pix = std::max<uint64_t>(1, chunk_cap / (uint64_t)lay);
   chunk_pix = std::min(chunk_pix, npix);
-  uint64_t chunk_ns = chunk_pix * (uint64_t)lay;
-  if (halton && ns <= chunk_cap) {  // the whole frame fits one chunk (lay is only an upper bound per pixel)
-    chunk_pix = npix;
-    chunk_ns = ns;
-  }
+  if (halton && ns <= chunk_cap) chunk_pix = npix;  // the whole frame fits one chunk (lay is only an upper bound per pixel)
 
-  CK(ctx->d_img.ensure(ns * sizeof(float2)));
+  // Per-sample buffers that outlive a chunk (image positions, radiance records, lens / time / light
+  // floats) are addressed per list pixel.  A whole-film frame whose buffers would exceed
+  // kFrameBudgetBytes keeps them in a RING over list pixels instead: chunks run in list order, after
+  // every chunk the film rows that are complete are filtered (k_film per band), and a pixel's slot is
+  // reused once no unfiltered film row can reach it.  Memory is then O(chunk), not O(frame).
+  const uint64_t frame_bytes_per_sample = sizeof(float2) + (lit ? sizeof(float4) : 0) + (full ? sizeof(float2) + sizeof(float) : 0) +
+                                          (uint64_t)pairs * sizeof(float2);
+  const bool whole_film = tiles == nullptr;
+  const int halo_rows = (int)std::ceil(film->filter_yw + 0.5f) + 2;
+  uint64_t ring_px = npix;  // no ring
+  if (whole_film && !halton && ns * frame_bytes_per_sample > frame_budget_bytes()) {
+    const uint64_t lag_px = (uint64_t)(2 * halo_rows + 8) * (uint64_t)(smp->x_end - smp->x_start);
+    uint64_t want = chunk_pix + lag_px, r = 1;
+    while (r < want) r <<= 1;
+    if (r < npix) ring_px = r;
+  }
+  const bool ring = ring_px < npix;
+  const uint32_t pixel_mask = ring ? (uint32_t)(ring_px - 1) : 0xFFFFFFFFu;
+  const uint64_t ring_ns = ring ? ring_px * (uint64_t)lay : ns;
+  auto phys = [&](uint64_t p) -> uint64_t { return first_sample(ring ? (p & (ring_px - 1)) : p); };
+
+  uint64_t chunk_ns = chunk_pix * (uint64_t)lay;
+  if (halton && chunk_pix == npix) chunk_ns = ns;
+  CK(ctx->d_img.ensure(ring_ns * sizeof(float2)));
   if (full) {
-    CK(ctx->d_lens.ensure(ns * sizeof(float2)));
-    CK(ctx->d_time.ensure(ns * sizeof(float)));
+    CK(ctx->d_lens.ensure(ring_ns * sizeof(float2)));
+    CK(ctx->d_time.ensure(ring_ns * sizeof(float)));
   }
   CK(ctx->d_edge.ensure(npix * sizeof(uint32_t)));
-  if (ctx->sc.area_sample_pairs) CK(ctx->d_lightu.ensure(ns * ctx->sc.area_sample_pairs * sizeof(float2)));
-  if (rad_slots) CK(ctx->d_rad.ensure(ns * rad_slots * sizeof(float4)));
+  if (pairs) CK(ctx->d_lightu.ensure(ring_ns * pairs * sizeof(float2)));
+  if (lit) CK(ctx->d_rec.ensure(ring_ns * sizeof(float4)));
+  if (multi_slot) CK(ctx->d_terms.ensure(chunk_ns * slots * sizeof(float4)));
   CK(ctx->d_hits.ensure(chunk_ns * sizeof(pbrtb200_hit16)));
-  CK(ctx->d_sq_rays.ensure(chunk_ns * slots * sizeof(pbrtb200_ray32)));
-  CK(ctx->d_sq_slots.ensure(chunk_ns * slots * sizeof(uint32_t)));
+  if (lit) {
+    CK(ctx->d_sq_rays.ensure(chunk_ns * slots * sizeof(pbrtb200_ray32)));
+    CK(ctx->d_sq_slots.ensure(chunk_ns * slots * sizeof(uint32_t)));
+  }
   const size_t film_px = (size_t)film->x_pixel_count * (size_t)film->y_pixel_count;
   float4* d_film = nullptr;
   if (out_is_device) {
@@ -1211,8 +1253,6 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     CK(ctx->d_film.ensure(film_px * sizeof(float4)));
     d_film = ctx->d_film.as<float4>();
   }
-  CK(cudaMemcpyToSymbolAsync(c_filter_table, film->filter_table, sizeof(float) * 256, 0,
-                             cudaMemcpyHostToDevice, ctx->stream));
 
   CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
   CK(cudaMemsetAsync(ctx->d_edge.p, 0, npix * sizeof(uint32_t), ctx->stream));
@@ -1235,42 +1275,44 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   df.sy1 = smp->y_end;
   df.spp = ds.spp;
   DFold fd{};
-  fd.rad_slots = rad_slots;
-  fd.le_slot = le_slot;
+  fd.slots = slots;
   fd.n_lights = ctx->sc.n_lights;
   for (uint32_t i = 0; i < ctx->sc.n_lights; ++i) {
     const pbrtb200_light& l = ctx->h_lights[i];
     fd.area[i] = l.kind == PBRTB200_LIGHT_AREA ? 1 : 0;
     fd.ns[i] = (uint16_t)(fd.area[i] ? l.num_samples : 1);
   }
-  // Whole-film renders into host memory run k_film in bands: after each chunk the film rows whose
-  // every contributing sample exists are filtered and start their device->host copy on a second
-  // stream, so the PCIe transfer hides behind the remaining chunks.
+  // k_film runs in BANDS of finished film rows: always with a ring (the samples are about to be
+  // overwritten), and for whole-film renders into host memory (each band's device->host copy travels
+  // on a second stream while later chunks render).
   static const int band_mode = [] {  // 0: one film launch + one copy; N > 0: N tail pieces
     const char* v = std::getenv("PBRTB200_FILM_BANDS");
     return v && *v ? std::atoi(v) : 2;
   }();
-  const bool banded = band_mode > 0 && !out_is_device && !tiles;
+  const bool banded = whole_film && !halton && (ring || (band_mode > 0 && !out_is_device));
+  const bool band_copies = banded && !out_is_device;
   struct Band {
     uint32_t y0, y1;
     size_t event;
   };
   std::vector<Band> bands;
   uint32_t film_done = 0;  // film rows [0, film_done) are filtered
+  FilmArgs fa{};  // (1 KB of filter table: filled once)
+  fa.img = ctx->d_img.as<float2>();
+  fa.rec = lit ? ctx->d_rec.as<float4>() : nullptr;
+  fa.lights = ctx->sc.lights;
+  fa.edge = ctx->d_edge.as<uint32_t>();
+  fa.offsets = halton ? ctx->d_hoffsets.as<uint32_t>() : nullptr;
+  fa.pix_index = ctx->d_pix_index.as<int32_t>();
+  fa.rects = ctx->d_rects.as<int32_t>();
+  fa.rect_prefix = ctx->d_rect_prefix.as<uint32_t>();
+  fa.n_rects = ctx->n_rects;
+  fa.n_pixels = ctx->n_film_pixels;
+  fa.pixel_mask = pixel_mask;
+  fa.out = d_film;
+  std::memcpy(fa.table, film->filter_table, sizeof fa.table);
   auto film_rows = [&](uint32_t y0, uint32_t y1) -> int {
     size_t eF0 = tm.mark();
-    FilmArgs fa{};
-    fa.img = ctx->d_img.as<float2>();
-    fa.rad = ctx->d_rad.as<float4>();
-    fa.edge = ctx->d_edge.as<uint32_t>();
-    fa.offsets = halton ? ctx->d_hoffsets.as<uint32_t>() : nullptr;
-    fa.pix_index = ctx->d_pix_index.as<int32_t>();
-    fa.rects = ctx->d_rects.as<int32_t>();
-    fa.rect_prefix = ctx->d_rect_prefix.as<uint32_t>();
-    fa.n_rects = ctx->n_rects;
-    fa.n_pixels = ctx->n_film_pixels;
-    fa.out = d_film;
-    fa.nan_count = &ctrl(ctx)->nan_count;
     if (banded) {  // one rect = the whole film, row-major
       fa.first = y0 * (uint32_t)film->x_pixel_count;
       fa.count = (y1 - y0) * (uint32_t)film->x_pixel_count;
@@ -1278,33 +1320,48 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       fa.first = 0;
       fa.count = fa.n_pixels;
     }
-    k_film<<<(fa.count + 127) / 128, 128, 0, ctx->stream>>>(df, fd, fa);
+    k_film<<<(fa.count + 127) / 128, 128, 0, ctx->stream>>>(df, fa);
     CK(cudaGetLastError());
     launches += 1;
     tm.span(eF0, tm.mark(), 4);
     if (banded) {
-      if (bands.size() == ctx->band_events.size()) {
-        cudaEvent_t ev;
-        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        ctx->band_events.push_back(ev);
+      if (band_copies) {
+        if (bands.size() == ctx->band_events.size()) {
+          cudaEvent_t ev;
+          CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+          ctx->band_events.push_back(ev);
+        }
+        CK(cudaEventRecord(ctx->band_events[bands.size()], ctx->stream));
+        bands.push_back({y0, y1, bands.size()});
       }
-      CK(cudaEventRecord(ctx->band_events[bands.size()], ctx->stream));
-      bands.push_back({y0, y1, bands.size()});
       film_done = y1;
     }
     return 0;
+  };
+  // k_film's gather extent of film row r, in sampler rows (clamped to the sampler extent)
+  auto gather_lo = [&](uint32_t r) -> int {
+    const int y = film->y_pixel_start + (int)r;
+    return std::max((int)std::ceil((float)y - 0.5f - film->filter_yw) - 1, smp->y_start);
+  };
+  auto gather_hi = [&](uint32_t r) -> int {
+    const int y = film->y_pixel_start + (int)r;
+    return std::min((int)std::floor((float)y + 0.5f + film->filter_yw) + 1, smp->y_end - 1);
   };
   // film rows [0, r) are final once `done` list pixels are finished
   auto rows_final = [&](uint64_t done) -> uint32_t {
     uint32_t r = film_done;
     while (r < (uint32_t)film->y_pixel_count) {
-      const int y = film->y_pixel_start + (int)r;
-      int qy1 = (int)std::floor((float)y + 0.5f + film->filter_yw) + 1;  // k_film's gather extent
-      qy1 = std::min(qy1, smp->y_end - 1);
+      const int qy1 = gather_hi(r);
       if (qy1 >= smp->y_start && (uint64_t)ctx->rows_ready[(size_t)(qy1 - smp->y_start)] > done) break;
       ++r;
     }
     return r;
+  };
+  // first list pixel an unfiltered film row can still reach (ring: everything before it is free)
+  auto live_start = [&]() -> uint64_t {
+    if (film_done >= (uint32_t)film->y_pixel_count) return npix;
+    const int qy0 = gather_lo(film_done);
+    return ctx->row_first[(size_t)std::min(std::max(qy0 - smp->y_start, 0), smp->y_end - smp->y_start)];
   };
 
   if (halton) {  // candidates land anywhere: every sample of the frame is generated up front
@@ -1314,15 +1371,19 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     tm.span(h0, tm.mark(), 0);
     launches += cached ? 1 : 2;  // (k_halton_bin<1>,) k_halton_samples
   }
-  for (uint64_t p0 = 0; p0 < npix; p0 += chunk_pix) {
-    const uint64_t cp = std::min(chunk_pix, npix - p0);
-    const uint64_t s0 = first_sample(p0), cn = first_sample(p0 + cp) - s0;
+  for (uint64_t p0 = 0; p0 < npix;) {
+    uint64_t cp = std::min(chunk_pix, npix - p0);
+    if (ring) {
+      cp = std::min(cp, ring_px - (p0 & (ring_px - 1)));  // a chunk is contiguous in the ring
+      const uint64_t room = ring_px - (p0 - live_start());
+      if (room == 0) FAIL(PBRTB200_ENOMEM, "sample ring too small for this filter width (PBRTB200_CHUNK_LOG2)");
+      cp = std::min(cp, room);
+    }
+    const uint64_t s0 = phys(p0);
+    const uint64_t cn = halton ? first_sample(p0 + cp) - first_sample(p0) : cp * (uint64_t)lay;
+    const uint64_t p1 = p0 + cp;
     if (cn == 0) {  // (HaltonSampler: a run of pixels without a single sample)
-      if (banded && p0 + cp < npix) {
-        const uint32_t r = rows_final(p0 + cp);
-        if (r > film_done)
-          if (int rc = film_rows(film_done, r)) return rc;
-      }
+      p0 = p1;
       continue;
     }
     size_t e0 = tm.mark();
@@ -1348,22 +1409,22 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     launches += 2;
     tm.span(e0, e1, 0);
     tm.span(e1, e2, 1);
-    if (ctx->sc.n_lights) {
+    if (lit) {
       ShadeArgs sa{};
       sa.img = ta.img;
       sa.lens = ta.lens;
-      sa.lightu = ctx->sc.area_sample_pairs ? ctx->d_lightu.as<float2>() : nullptr;
+      sa.lightu = pairs ? ctx->d_lightu.as<float2>() + s0 * pairs : nullptr;
       sa.hits = ta.hits;
       sa.area_tris = ctx->d_area_tris.as<DAreaTri>();
-      sa.rad = ctx->d_rad.as<float4>();
+      // one slot: the terms ARE the radiance records; several: chunk-local terms, folded below
+      sa.terms = multi_slot ? ctx->d_terms.as<float4>() : ctx->d_rec.as<float4>() + s0;
       sa.sq_rays = ctx->d_sq_rays.as<pbrtb200_ray32>();
       sa.sq_slots = ctx->d_sq_slots.as<uint32_t>();
       sa.sq_count = &ctrl(ctx)->sq_count;
       sa.hit_total = &ctrl(ctx)->hit_total;
+      sa.nan_count = &ctrl(ctx)->nan_count;
       sa.n = cn;
-      sa.sample0 = s0;
-      sa.rad_slots = rad_slots;
-      sa.le_slot = le_slot;
+      sa.slots = slots;
       sa.strict_flags = integ->strict_flags;
       if (ctx->shade_ext)
         k_shade<PB_SHADE_EXT_MIN_BLOCKS, true, true><<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
@@ -1376,8 +1437,9 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));
       TraceArgs sh{};
       sh.rays = sa.sq_rays;
-      sh.contrib = sa.rad;
+      sh.contrib = sa.terms;
       sh.slots = sa.sq_slots;
+      sh.nan_count = &ctrl(ctx)->nan_count;
       sh.n_dyn = &ctrl(ctx)->sq_count;
       sh.shadow_total = &ctrl(ctx)->shadow_total;
       sh.counter = &ctrl(ctx)->counter;
@@ -1387,12 +1449,25 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       tm.span(e2, e3, 2);
       tm.span(e3, e4, 3);
       launches += 2;
+      if (multi_slot) {
+        FoldArgs fo{};
+        fo.terms = sa.terms;
+        fo.lights = ctx->sc.lights;
+        fo.rec = ctx->d_rec.as<float4>() + s0;
+        fo.n = cn;
+        fo.nan_count = &ctrl(ctx)->nan_count;
+        k_fold<<<(unsigned)((cn + 255) / 256), 256, 0, ctx->stream>>>(fd, fo);
+        CK(cudaGetLastError());
+        tm.span(e4, tm.mark(), 2);
+        launches += 1;
+      }
     }
-    if (banded && p0 + cp < npix) {
-      const uint32_t r = rows_final(p0 + cp);
+    if (banded && p1 < npix) {
+      const uint32_t r = rows_final(p1);
       if (r > film_done)
         if (int rc = film_rows(film_done, r)) return rc;
     }
+    p0 = p1;
   }
   if (!banded) {
     if (int rc = film_rows(0u, (uint32_t)film->y_pixel_count)) return rc;
@@ -1400,13 +1475,14 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     // the rows left after the last chunk go out in a few pieces so that the copy of one piece
     // overlaps the filtering of the next
     const uint32_t H = (uint32_t)film->y_pixel_count;
-    const uint32_t step = std::max(16u, (H - film_done + (uint32_t)band_mode - 1u) / (uint32_t)band_mode);
+    const uint32_t pieces = (uint32_t)std::max(1, band_copies ? band_mode : 1);
+    const uint32_t step = std::max(16u, (H - film_done + pieces - 1u) / pieces);
     while (film_done < H)
       if (int rc = film_rows(film_done, std::min(H, film_done + step))) return rc;
   }
   tm.span(eA, tm.mark(), 5);
   if (!out_is_device) {
-    if (banded) {
+    if (band_copies) {
       // every band: wait for its film launch on the copy stream, then move its rows to the host
       for (const Band& b : bands) {
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->band_events[b.event], 0));
@@ -1441,6 +1517,32 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   return PBRTB200_OK;
 }
 
+
+int pbrtb200_cost_profile(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb200_film* film, int stride,
+                          float* row_cost) {
+  if (!ctx) return PBRTB200_EINVAL;
+  if (!ctx->has_scene) FAIL(PBRTB200_EINVAL, "no scene uploaded");
+  if (!cam || !film || !row_cost || stride < 1) FAIL(PBRTB200_EINVAL, "bad argument");
+  if (film->x_pixel_count < 1 || film->y_pixel_count < 1) FAIL(PBRTB200_EINVAL, "empty film");
+  CK(cudaSetDevice(ctx->device));
+  const int h = film->y_pixel_count;
+  CK(ctx->d_out_b.ensure((size_t)h * sizeof(float)));
+  CK(cudaMemsetAsync(ctx->d_out_b.p, 0, (size_t)h * sizeof(float), ctx->stream));
+  DCamera dc;
+  fill_camera(cam, 1, &dc);
+  dc.lens_radius = 0.0f;  // (probe rays are pinhole rays)
+  TraceLaunchCfg cfg{ctx->stream, ctx->sm_count, ctx->has_spheres, ctx->multi_leaf};
+  // constant part of a camera sample (raygen, shading, film) in units of traversal steps: on
+  // config 3 those stages take about a third of the time of its ~55 steps per sample
+  const float base_cost = 20.0f;
+  CK(pb_launch_cost_probe(cfg, ctx->sc, dc, film->x_pixel_start, film->y_pixel_start, film->x_pixel_count, h, stride,
+                          base_cost, ctx->d_area_tris.p, ctx->d_out_b.as<float>()));
+  CK(cudaMemcpyAsync(row_cost, ctx->d_out_b.p, (size_t)h * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int y = 0; y < h; ++y)  // a probe row stands for the `stride` rows it starts
+    if (y % stride) row_cost[y] = row_cost[y - y % stride];
+  return PBRTB200_OK;
+}
 
 int pbrtb200_film_develop(pbrtb200_ctx* ctx, const float* film_xyzw, int film_is_device,
                           uint64_t n_pixels, float* out_rgb, uint8_t* out_rgb8, int out_is_device) {

@@ -1,4 +1,4 @@
-// Film accumulation kernel (sm_100a): deterministic per-pixel gather, fused with the radiance fold.
+// Film accumulation kernel (sm_100a): deterministic per-pixel gather over per-sample radiance records.
 //
 // Replaces Film::add_sample (src/camera/film.rs:192-249) over all samples of a frame, the light
 // sum of WhittedIntegrator::li (src/integrator/whitted.rs:49-66) and Spectrum::to_xyz
@@ -17,23 +17,25 @@
 #include "scene.cuh"
 
 #define PB_MAX_FOLD_LIGHTS 64
-struct DFold {  // how the per-sample radiance terms fold into L (light order)
-  uint32_t rad_slots, le_slot, n_lights;
+struct DFold {  // how the per-sample radiance terms of a multi-light scene fold into L (light order)
+  uint32_t slots, n_lights;
   uint16_t ns[PB_MAX_FOLD_LIGHTS];   // samples of light i (1 for point/spot)
   uint8_t area[PB_MAX_FOLD_LIGHTS];  // 1 = area light (averaged over its samples)
 };
 
 #include "film_math.cuh"  // DFilm, film_sample_index
 
-#ifdef PB_HOST_CHECK
-static float c_filter_table[256];  // host check: a plain array the harness fills
-#else
-__constant__ float c_filter_table[256];
-#endif
-
+// Per camera sample the frame keeps ONE float4 "radiance record" (list order; a ring over list pixels
+// when the frame is larger than the wavefront budget, DESIGN.md "Radiance path"):
+//   xyz = v, w = bits(e): L = (e ? Le(light e - 1) : 0) + v
+// With a single light slot v is that slot's term f * Li * |wi.n| / pdf, written by k_shade and
+// zeroed by the any-hit kernel when the shadow ray is occluded, so L = Le + v is exactly
+// whitted.rs:49-66 for one light.  With several slots k_fold has already folded everything
+// (Le included, in light order) and e = 0.
 struct FilmArgs {
-  const float2* __restrict__ img;         // per sample, list order
-  const float4* __restrict__ rad;         // per sample x rad_slots radiance terms (rgb)
+  const float2* __restrict__ img;         // per sample, list order (ring-addressed like `rec`)
+  const float4* __restrict__ rec;         // radiance records; NULL: the scene has no light (L = 0)
+  const pbrtb200_light* __restrict__ lights;  // Le lookup for e != 0
   const uint32_t* __restrict__ offsets;   // HaltonSampler: list pixel li owns samples [offsets[li], offsets[li+1]); else NULL (li * spp)
   const uint32_t* __restrict__ edge;      // per list pixel
   const int32_t* __restrict__ pix_index;  // sampler-extent raster -> list position or -1
@@ -42,44 +44,56 @@ struct FilmArgs {
   uint32_t n_rects;
   uint32_t n_pixels;  // total pixels over all rects
   uint32_t first, count;  // this launch covers pixel ordinals [first, first + count)
+  uint32_t pixel_mask;    // ring over list pixels: list pixel li lives at slot li & pixel_mask (all ones: no ring)
   float4* __restrict__ out;  // film, row-major over the film pixel extent
-  uint32_t* nan_count;
+  float table[256];          // the film's 16 x 16 filter table (film.rs:99-110), per launch: two
+                             // contexts with different filters may render concurrently
 };
 
-// L = Le + sum over lights; to_xyz.  Returns true if L has a NaN (sampler_renderer.rs:105 intent).
-PB_DEV bool fold_radiance(const DFold& fd, const float4* __restrict__ r, float* X, float* Y,
-                          float* Z) {
-  f3 L = mk3(0.f, 0.f, 0.f);
-  uint32_t slot = 0;
-  if (fd.le_slot) {
-    const float4 le = __ldg(r);
-    L = mk3(le.x, le.y, le.z);
-    slot = 1;
+// XYZ of a radiance record (spectrum.rs:37-41 for RGB spectra).
+PB_DEV void record_xyz(const FilmArgs& a, float4 r, float* X, float* Y, float* Z) {
+  f3 L = mk3(r.x, r.y, r.z);
+  const uint32_t e = __float_as_uint(r.w);
+  if (e) {  // the sample hit an emitter: L = Le + v, Le first as in whitted.rs:46-66
+    const pbrtb200_light* lt = a.lights + (e - 1u);
+    L = mk3(__ldg(&lt->intensity[0]), __ldg(&lt->intensity[1]), __ldg(&lt->intensity[2])) + L;
   }
+  *X = 0.412453f * L.x + 0.357580f * L.y + 0.180423f * L.z;
+  *Y = 0.212671f * L.x + 0.715160f * L.y + 0.072169f * L.z;
+  *Z = 0.019334f * L.x + 0.119193f * L.y + 0.950227f * L.z;
+}
+
+// L = Le + sum over lights (multi-slot scenes), whitted.rs:46-66 with D10's per-light average.
+// terms: `slots` float4 per sample, term j = (c_j, j == 0 ? bits(e) : 0).  Returns true if L has a NaN
+// (sampler_renderer.rs:105 intent).
+PB_DEV bool fold_terms(const DFold& fd, const pbrtb200_light* __restrict__ lights, const float4* __restrict__ r, float4* out) {
+  const float4 first = r[0];
+  f3 L = mk3(0.f, 0.f, 0.f);
+  const uint32_t e = __float_as_uint(first.w);
+  if (e) L = mk3(lights[e - 1u].intensity[0], lights[e - 1u].intensity[1], lights[e - 1u].intensity[2]);
+  uint32_t slot = 0;
   for (uint32_t li = 0; li < fd.n_lights; ++li) {
     if (fd.area[li]) {
       const uint32_t ns = fd.ns[li];
       f3 Ld = mk3(0.f, 0.f, 0.f);
       for (uint32_t s = 0; s < ns; ++s) {
-        const float4 c = __ldg(r + slot++);
+        const float4 c = r[slot++];
         Ld = Ld + mk3(c.x, c.y, c.z);
       }
       const float fns = (float)ns;
       L = L + mk3(Ld.x / fns, Ld.y / fns, Ld.z / fns);
     } else {
-      const float4 c = __ldg(r + slot++);
+      const float4 c = r[slot++];
       L = L + mk3(c.x, c.y, c.z);
     }
   }
-  *X = 0.412453f * L.x + 0.357580f * L.y + 0.180423f * L.z;
-  *Y = 0.212671f * L.x + 0.715160f * L.y + 0.072169f * L.z;
-  *Z = 0.019334f * L.x + 0.119193f * L.y + 0.950227f * L.z;
+  *out = make_float4(L.x, L.y, L.z, 0.f);
   return isnan(L.x) || isnan(L.y) || isnan(L.z);
 }
 
 // One film pixel (ordinal `gid` over the rects of this call): the whole gather.  Written as a
 // function of the ordinal so that the host check (tests/devsrc/) can run it pixel by pixel.
-PB_DEV void film_pixel(const DFilm& f, const DFold& fd, const FilmArgs& a, uint32_t gid) {
+PB_DEV void film_pixel(const DFilm& f, const FilmArgs& a, uint32_t gid) {
   // locate the rect (few rects per GPU; binary search over the prefix sums)
   uint32_t lo = 0, hi = a.n_rects;
   while (hi - lo > 1) {
@@ -101,7 +115,6 @@ PB_DEV void film_pixel(const DFilm& f, const DFold& fd, const FilmArgs& a, uint3
   qy1 = min(qy1, f.sy1 - 1);
   const int sw = f.sx1 - f.sx0;
   float X = 0.f, Y = 0.f, Z = 0.f, Wt = 0.f;
-  uint32_t nans = 0;
   for (int qy = qy0; qy <= qy1; ++qy) {
     // A sample of sampler pixel q has image coordinate in [q, q+1]; all of add_sample's float ops
     // are monotonic, so its pixel extent lies inside [ceil((q-0.5)-w), floor((q+0.5)+w)].
@@ -116,7 +129,7 @@ PB_DEV void film_pixel(const DFilm& f, const DFold& fd, const FilmArgs& a, uint3
       if (li < 0) continue;
       const bool own = (qx == x) && (qy == y);
       if (!own && __ldg(&a.edge[li]) == 0u) continue;  // cannot reach any pixel but its own
-      uint64_t base = (uint64_t)li * (uint64_t)f.spp;
+      uint64_t base = (uint64_t)((uint32_t)li & a.pixel_mask) * (uint64_t)f.spp;
       int cnt = f.spp;
       if (a.offsets) {  // variable samples per pixel (halton.cuh)
         base = __ldg(&a.offsets[li]);
@@ -126,10 +139,9 @@ PB_DEV void film_pixel(const DFilm& f, const DFold& fd, const FilmArgs& a, uint3
         const float2 im = __ldg(a.img + base + i);
         int ti;
         if (!film_sample_index(f, im.x, im.y, x, y, &ti)) continue;
-        const float wt = c_filter_table[ti];
-        float cx, cy, cz;
-        const bool bad = fold_radiance(fd, a.rad + (base + i) * fd.rad_slots, &cx, &cy, &cz);
-        if (bad && own) ++nans;
+        const float wt = a.table[ti];
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        if (a.rec) record_xyz(a, __ldg(a.rec + base + i), &cx, &cy, &cz);
         X += wt * cx;  // film.rs:241-244
         Y += wt * cy;
         Z += wt * cz;
@@ -137,17 +149,34 @@ PB_DEV void film_pixel(const DFilm& f, const DFold& fd, const FilmArgs& a, uint3
       }
     }
   }
-  if (nans) atomicAdd(a.nan_count, nans);
   a.out[(size_t)(y - f.y_start) * (size_t)f.x_count + (size_t)(x - f.x_start)] =
       make_float4(X, Y, Z, Wt);
 }
 
 #ifndef PB_HOST_CHECK
 __global__ void __launch_bounds__(128)
-k_film(const DFilm f, const DFold fd, const FilmArgs a) {
+k_film(const DFilm f, const FilmArgs a) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= a.count) return;
-  film_pixel(f, fd, a, a.first + tid);
+  film_pixel(f, a, a.first + tid);
+}
+
+// Multi-slot scenes: folds the `slots` radiance terms of each sample of a chunk into its radiance
+// record (one thread per sample) and counts NaN radiances once per sample.
+struct FoldArgs {
+  const float4* __restrict__ terms;  // chunk-local: slots per sample
+  const pbrtb200_light* __restrict__ lights;
+  float4* __restrict__ rec;          // the chunk's slice of the record buffer
+  uint64_t n;
+  uint32_t* nan_count;
+};
+__global__ void __launch_bounds__(256)
+k_fold(const DFold fd, const FoldArgs a) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  float4 r;
+  if (fold_terms(fd, a.lights, a.terms + i * fd.slots, &r)) atomicAdd(a.nan_count, 1u);
+  a.rec[i] = r;
 }
 
 // Film::write_image pixel pipeline (film.rs:331-340 as intended, write_img film.rs:21-23).

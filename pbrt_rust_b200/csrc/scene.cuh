@@ -4,11 +4,21 @@
 #include "dmath.cuh"
 
 #include "leaf_ref.h"  // PB_LEAF_BIT, PB_LEAF_CNT_SHIFT, PB_LEAF_OFF_MASK
-#ifndef PB_SM_STACK
-#define PB_SM_STACK 24                                   // traversal-stack entries kept in smem
+// Traversal-stack entries kept in shared memory, per kernel kind; deeper entries (all of them for a
+// depth of 0) live in local memory, i.e. in L1.  Shared memory and L1 share one 256 KB array per SM:
+// the closest-hit kernel keeps a short shared stack (24 entries cost it ~150 KB of L1 and 8 % of its
+// speed), the any-hit kernel none at all (measured, profiles/r02_notes.md).
+#ifndef PB_SM_STACK_CLOSEST
+#define PB_SM_STACK_CLOSEST 8
 #endif
-#define PB_LM_STACK (PBRTB200_STACK_DEPTH - PB_SM_STACK) // deeper entries spill to local memory
+#ifndef PB_SM_STACK_ANY
+#define PB_SM_STACK_ANY 0
+#endif
+#define PB_SM_STACK_OF(ANY) ((ANY) ? PB_SM_STACK_ANY : PB_SM_STACK_CLOSEST)
+#define PB_SM_STACK_MAX (PB_SM_STACK_CLOSEST > PB_SM_STACK_ANY ? PB_SM_STACK_CLOSEST : PB_SM_STACK_ANY)
+#ifndef PB_TRACE_THREADS
 #define PB_TRACE_THREADS 128
+#endif
 
 // BVH "pair node", 64 B = 4 x float4, built at upload from the reference's linear PackedBVHNode
 // array (pbrtb200_node32).  An inner node stores BOTH children's boxes so one 64-byte fetch
@@ -50,6 +60,12 @@ struct DScene {
   float babs[3];           // max |coordinate| over every node box, per axis (BOX 3 error bound)
   uint32_t boxes_finite;   // every node box coordinate is finite (else: compare-and-swap tests only)
   uint32_t boxes_ordered;  // every node box has min <= max on every axis (octant-specialised tests)
+};
+
+// Internal record of one emissive triangle (built on device at upload from scene.area_prims).
+struct DAreaTri {
+  float p1[3], p2[3], p3[3], nn[3];
+  float area, cdf_lo, cdf_hi, pad;
 };
 
 struct DCamera {

@@ -83,11 +83,6 @@ PB_DEV f3 tex_eval(const DScene& sc, int id, const DG& dg) {
   }
 }
 
-// Internal record of one emissive triangle (built on device at upload from scene.area_prims).
-struct DAreaTri {
-  float p1[3], p2[3], p3[3], nn[3];
-  float area, cdf_lo, cdf_hi, pad;
-};
 
 // Warp-aggregated queue push: one atomicAdd per warp for all lanes that call it together.
 PB_DEV uint32_t warp_agg_inc(uint32_t* ctr) {
@@ -131,18 +126,19 @@ struct ShadeArgs {
   const float2* __restrict__ lightu;  // light-sample float pairs (raygen), NULL without area lights
   const pbrtb200_hit16* __restrict__ hits;
   const DAreaTri* __restrict__ area_tris;
-  // Per camera sample `rad_slots` float4 radiance terms, frame-global index (sample0 + idx):
-  //   [0]                 Le            (only when the scene has area lights: le_slot == 1)
-  //   [le_slot + j]       f*Li*|wi.n|/pdf of light slot j (0 when nothing is reflected)
-  // The any-hit kernel zeroes a term whose shadow ray is occluded; the film kernel folds them.
-  float4* __restrict__ rad;
+  // Per camera sample of the chunk `slots` float4 radiance terms (index idx * slots + j):
+  //   term j = (f * Li * |wi.n| / pdf of light slot j, 0 when nothing is reflected ; w)
+  //   w of term 0 = bits(e): e - 1 = the area light whose emitter was hit facing the camera, 0 = none
+  // The any-hit kernel zeroes the xyz of a term whose shadow ray is occluded.  With ONE slot the terms
+  // ARE the frame's radiance records (film.cuh: L = Le(e) + v); with several, k_fold folds them.
+  float4* __restrict__ terms;
   pbrtb200_ray32* __restrict__ sq_rays;  // shadow-ray queue (chunk-local)
-  uint32_t* __restrict__ sq_slots;       // rad term each shadow ray guards (frame-global index)
+  uint32_t* __restrict__ sq_slots;       // term each shadow ray guards (chunk-local index) | PB_SQ_* flags
   uint32_t* sq_count;
   unsigned long long* hit_total;
+  uint32_t* nan_count;                   // NaN emitted radiance (the terms are checked where they become final)
   uint64_t n;
-  uint64_t sample0;  // frame-global index of this chunk's first sample
-  uint32_t rad_slots, le_slot;
+  uint32_t slots;
   int strict_flags;
 };
 
@@ -161,7 +157,7 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
     hraw = __ldg(reinterpret_cast<const float4*>(a.hits) + idx);
     // independent streams this thread will need later: start them now (no register cost)
     PB_PREFETCH_L2(a.img + idx);
-    if (a.lightu) PB_PREFETCH_L2(a.lightu + (a.sample0 + idx) * sc.area_sample_pairs);
+    if (a.lightu) PB_PREFETCH_L2(a.lightu + idx * sc.area_sample_pairs);
   }
   const uint32_t prim = __float_as_uint(hraw.x);
   // Block-level bookkeeping. A same-address global atomic retires at ~0.66 ns on B200 (measured,
@@ -184,10 +180,11 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   // Every thread of the block walks the light loop below (its trip counts depend on the scene
   // only) so the queue push can use block barriers; `alive` threads are the ones with a hit.
   const bool alive = in_range && prim != PBRTB200_MISS;
-  float4* rad = a.rad + (a.sample0 + (in_range ? idx : 0)) * a.rad_slots;
+  float4* terms = a.terms + (in_range ? idx : 0) * a.slots;
   if (in_range && !alive)  // miss: sum of light.le(ray) = 0 (light/mod.rs:50-52)
-    for (uint32_t q = 0; q < a.rad_slots; ++q) rad[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t q = 0; q < a.slots; ++q) terms[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   DBSDF bs;
+  uint32_t le_bits = 0u;
   f3 p = mk3(0.f, 0.f, 0.f), n = p, wo = p;
   float ray_epsilon = 0.f;
   if (alive) {
@@ -298,27 +295,27 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   n = dgs.nn;
   wo = -d;
 
-  // Emitted radiance at an emissive triangle (extension): L if n.w > 0.
-  f3 le = mk3(0.f, 0.f, 0.f);
-  if (area_light >= 0) {
-    const pbrtb200_light al = sc.lights[area_light];
-    if (dot3(dg.nn, wo) > 0.0f) le = mk3(al.intensity[0], al.intensity[1], al.intensity[2]);
+  // Emitted radiance at an emissive triangle (extension): L if n.w > 0.  Only the light's
+  // index travels with the sample; the film / fold kernels add its radiance first (whitted.rs:46).
+  if (area_light >= 0 && dot3(dg.nn, wo) > 0.0f) {
+    le_bits = (uint32_t)area_light + 1u;
+    const pbrtb200_light* al = sc.lights + area_light;
+    if (isnan(al->intensity[0]) || isnan(al->intensity[1]) || isnan(al->intensity[2])) atomicAdd(a.nan_count, 1u);
   }
-  if (a.le_slot) rad[0] = make_float4(le.x, le.y, le.z, 0.f);
   }  // alive
 
   // Light-sample floats: 2 per area-light sample, drawn by raygen from the pixel's
   // stream after its camera-sample block, in (camera sample, light, light sample) order.
-  const float2* lu = a.lightu ? a.lightu + (a.sample0 + idx) * sc.area_sample_pairs : nullptr;
+  const float2* lu = a.lightu ? a.lightu + idx * sc.area_sample_pairs : nullptr;
 
-  uint32_t slot = a.le_slot;
-  const uint32_t gslot0 = (uint32_t)((a.sample0 + idx) * a.rad_slots);
+  uint32_t slot = 0;
+  const uint32_t gslot0 = (uint32_t)(idx * a.slots);
   for (uint32_t li = 0; li < sc.n_lights; ++li) {
     const pbrtb200_light lt = sc.lights[li];
     const int ns = lt.kind == PBRTB200_LIGHT_AREA ? lt.num_samples : 1;
     for (int sidx = 0; sidx < ns; ++sidx, ++slot) {
       pbrtb200_ray32 vis;
-      bool shadow = false;
+      bool shadow = false, term_nan = false;
       if (alive) {
       f3 Li, wi;
       float pdf;
@@ -380,7 +377,8 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
           shadow = true;
         }
       }
-      rad[slot] = make_float4(c.x, c.y, c.z, 0.f);
+      term_nan = isnan(c.x) || isnan(c.y) || isnan(c.z);
+      terms[slot] = make_float4(c.x, c.y, c.z, slot == 0u ? __uint_as_float(le_bits) : 0.f);
       }  // alive
       // block-aggregated push: ballot per warp, one global atomic per block and slot
       const unsigned sm = __ballot_sync(0xffffffffu, shadow);
@@ -398,7 +396,7 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
         float4* rq = reinterpret_cast<float4*>(a.sq_rays + q);
         rq[0] = make_float4(vis.o[0], vis.o[1], vis.o[2], vis.mint);
         rq[1] = make_float4(vis.d[0], vis.d[1], vis.d[2], vis.maxt);
-        a.sq_slots[q] = gslot0 + slot;
+        a.sq_slots[q] = (gslot0 + slot) | (term_nan ? PB_SQ_NAN : 0u) | ((slot == 0u && le_bits) ? PB_SQ_KEEPW : 0u);
       }
     }
   }

@@ -17,6 +17,11 @@
 #include "trace_math.cuh"  // slab_test, slab_test_finite, tri_hit, camera_ray
 #include "trace_core.cuh"  // sphere_hit, traverse, trace_ray (one ray through the pair-node BVH)
 
+// Flags in the upper bits of a shadow-queue slot word (chunk-local term index in the low 30 bits).
+#define PB_SQ_NAN 0x80000000u    // the guarded term holds a NaN: an unoccluded ray makes the sample's radiance NaN
+#define PB_SQ_KEEPW 0x40000000u  // the term's w carries an emitter index: zero xyz only
+#define PB_SQ_INDEX 0x3FFFFFFFu
+
 // ---- kernels ---------------------------------------------------------------------------------
 // Persistent grid: each warp pulls 32-ray packets from a global counter (warp-aggregated: one
 // atomic per warp), so slow packets do not stall a whole block's worth of queued work.
@@ -28,7 +33,8 @@ struct TraceArgs {
   pbrtb200_hit16* __restrict__ hits;        // closest-hit output (may be NULL for ANY)
   uint8_t* __restrict__ occluded;           // ANY output (API hook), may be NULL
   float4* __restrict__ contrib;             // ANY in the render pipeline: zero slot if occluded
-  const uint32_t* __restrict__ slots;       // ANY in the render pipeline: slot index per ray
+  const uint32_t* __restrict__ slots;       // ANY in the render pipeline: term index | flags per ray
+  uint32_t* nan_count;                      // ANY in the render pipeline: unoccluded rays guarding a NaN term
   const uint32_t* __restrict__ n_dyn;       // if non-NULL the ray count is read from device memory
   unsigned long long* shadow_total;         // if non-NULL: += ray count (stats)
   uint64_t n;
@@ -44,20 +50,16 @@ struct TraceArgs {
 };
 
 #ifndef PB_TRACE_MIN_BLOCKS
-#define PB_TRACE_MIN_BLOCKS(ANY) ((ANY) ? 10 : 9)
+#define PB_TRACE_MIN_BLOCKS(ANY) 12  // 40 registers: occupancy pays (profiles/r02_notes.md)
 #endif
 template <bool ANY, bool SPH, bool MULTI, int SRC, int MODE, int BOX>
 __global__ void __launch_bounds__(PB_TRACE_THREADS, PB_TRACE_MIN_BLOCKS(ANY))
 k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
   // child refs, then (closest hit only: any-hit keeps no T0) the entry distances
-#if PB_SM_STACK > 0
-  __shared__ uint32_t sh_stack[(ANY ? 1 : 2) * PB_SM_STACK * PB_TRACE_THREADS];
-  uint32_t* s_ref = sh_stack + threadIdx.x;
-  float* s_t0 = reinterpret_cast<float*>(s_ref + (ANY ? 0 : PB_SM_STACK * PB_TRACE_THREADS));
-#else  // the whole stack in local memory (L1-resident, no shared-memory carve-out)
-  uint32_t* s_ref = nullptr;
-  float* s_t0 = nullptr;
-#endif
+  constexpr int SMD = PB_SM_STACK_OF(ANY);
+  __shared__ uint32_t sh_stack[(ANY ? 1 : 2) * (SMD > 0 ? SMD : 1) * (SMD > 0 ? PB_TRACE_THREADS : 1)];
+  uint32_t* s_ref = sh_stack + (SMD > 0 ? threadIdx.x : 0);
+  float* s_t0 = reinterpret_cast<float*>(s_ref + (ANY ? 0 : SMD * PB_TRACE_THREADS));
   const int lane = threadIdx.x & 31;
   const uint64_t n = a.n_dyn ? (uint64_t)(*a.n_dyn) : a.n;
   if (a.shadow_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.shadow_total, (unsigned long long)n);
@@ -102,7 +104,21 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
       if (ANY) {
         const bool occ = r.prim != PBRTB200_MISS;
         if (a.occluded) a.occluded[idx] = occ ? 1 : 0;
-        if (a.contrib && occ) a.contrib[__ldg(a.slots + idx)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.contrib) {  // render pipeline: the guarded radiance term (shade.cuh PB_SQ_*)
+          const uint32_t sl = __ldg(a.slots + idx);
+          float4* term = a.contrib + (sl & PB_SQ_INDEX);
+          if (occ) {
+            if (sl & PB_SQ_KEEPW) {  // w carries an emitter index
+              term->x = 0.f;
+              term->y = 0.f;
+              term->z = 0.f;
+            } else {
+              *term = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          } else if (sl & PB_SQ_NAN) {
+            atomicAdd(a.nan_count, 1u);  // sampler_renderer.rs:105 intent: counted once, where it becomes final
+          }
+        }
       } else {
         const uint64_t oi = idx;
         float4 h;

@@ -72,6 +72,7 @@ PB_DEV bool sphere_hit(const pbrtb200_sphere80* __restrict__ sp, f3 ow, f3 dw, f
 struct TraceResult {
   uint32_t prim;  // PBRTB200_MISS, PB_OVERFLOW (the stack overflowed: result invalid) or the hit
   float t, b1, b2;
+  uint32_t steps;  // COUNT instantiations only: node steps + primitive tests (cost probe, api.cu)
 };
 #define PB_OVERFLOW 0xFFFFFFFEu
 
@@ -147,6 +148,8 @@ PB_DEV bool child_box(const RayBox& rb, float ax, float ay, float az, float bx, 
 // immediate offset — no index arithmetic (the kernels are bound by instruction issue).
 template <bool ANY>
 struct TStack {
+  static constexpr int SMD = PB_SM_STACK_OF(ANY);                 // entries in shared memory
+  static constexpr int LMD = PBRTB200_STACK_DEPTH - SMD;          // entries in local memory
 #ifdef PB_HOST_CHECK
   uint32_t* s_ref;
   float* s_t0;
@@ -158,7 +161,7 @@ struct TStack {
   }
   PB_DEV bool empty() const { return sp == 0; }
   PB_DEV int depth() const { return sp; }
-  PB_DEV bool in_shared() const { return sp < PB_SM_STACK; }
+  PB_DEV bool in_shared() const { return sp < SMD; }
   PB_DEV void put(uint32_t r, float t0) {
     s_ref[sp * PB_TRACE_THREADS] = r;
     if (!ANY) s_t0[sp * PB_TRACE_THREADS] = t0;
@@ -171,16 +174,16 @@ struct TStack {
   PB_DEV void down() { --sp; }
 #else
   static constexpr uint32_t kStep = 4u * PB_TRACE_THREADS;           // bytes between entries
-  static constexpr uint32_t kT0 = 4u * PB_SM_STACK * PB_TRACE_THREADS;  // T0 array follows the refs
+  static constexpr uint32_t kT0 = 4u * (SMD > 0 ? SMD : 1) * PB_TRACE_THREADS;  // T0 array follows the refs
   uint32_t top;  // shared-window byte address of the next free entry (while sp <= PB_SM_STACK)
   int sp;        // entries on the stack (limit checks only; the address is never derived from it)
-  PB_DEV void init(uint32_t* ref, float*) {  // (s_t0 == s_ref + PB_SM_STACK * PB_TRACE_THREADS)
-    top = PB_SM_STACK > 0 ? (uint32_t)__cvta_generic_to_shared(ref) : 0u;
+  PB_DEV void init(uint32_t* ref, float*) {  // (s_t0 == s_ref + SMD * PB_TRACE_THREADS)
+    top = SMD > 0 ? (uint32_t)__cvta_generic_to_shared(ref) : 0u;
     sp = 0;
   }
   PB_DEV bool empty() const { return sp == 0; }
   PB_DEV int depth() const { return sp; }
-  PB_DEV bool in_shared() const { return sp < PB_SM_STACK; }
+  PB_DEV bool in_shared() const { return sp < SMD; }
   PB_DEV void put(uint32_t r, float t0) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(top), "r"(r) : "memory");
     if (!ANY) asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(top), "f"(t0), "n"(kT0) : "memory");
@@ -190,18 +193,18 @@ struct TStack {
     if (!ANY) asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(*t0) : "r"(top), "n"(kT0) : "memory");
   }
   PB_DEV void up() {
-    if (PB_SM_STACK > 0) top += kStep;
+    if (SMD > 0) top += kStep;
     ++sp;
   }
   PB_DEV void down() {
-    if (PB_SM_STACK > 0) top -= kStep;
+    if (SMD > 0) top -= kStep;
     --sp;
   }
 #endif
 };
 
 // One ray through the pair-node BVH.  s_ref / s_t0 point at this thread's column of the shared
-// stack (stride PB_TRACE_THREADS; s_t0 == s_ref + PB_SM_STACK * PB_TRACE_THREADS).  ANY: stop at
+// stack (stride PB_TRACE_THREADS; s_t0 == s_ref + PB_SM_STACK_OF(ANY) * PB_TRACE_THREADS).  ANY: stop at
 // the first accepted hit (VisibilityTester).
 // BOX / AX: the box test (child_box).  MODE selects the SIMT loop shape (all visit the same leaves
 // in the same order):
@@ -214,22 +217,24 @@ struct TStack {
 // Measured and dropped (profiles/r01_notes.md): speculative postponed-leaf traversal (no gain) and a
 // persistent kernel with per-lane ray refill (-30..-70 %: refilled lanes lose ray coherence), and a
 // warp-cooperative any-hit kernel with subtree stealing between lanes (-18 %).
-template <bool ANY, bool SPH, bool MULTI, int BOX, int MODE, int AX>
+template <bool ANY, bool SPH, bool MULTI, int BOX, int MODE, int AX, bool COUNT = false>
 PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, float mint, float maxt,
                             uint32_t* s_ref, float* s_t0) {
   constexpr bool UNORDERED = ANY && MODE >= 2;
   constexpr int SHAPE = MODE & 1;
   constexpr bool LEAF_EXACT = BOX == 3;  // inner tests are conservative: exact leaf test in the leaf phase
-  constexpr bool SM = PB_SM_STACK > 0;
+  constexpr int SMD = TStack<ANY>::SMD, LMD = TStack<ANY>::LMD;
+  constexpr bool SM = SMD > 0;
   TraceResult res;
   res.prim = PBRTB200_MISS;
   res.t = 0.f;
   res.b1 = 0.f;
   res.b2 = 0.f;
+  res.steps = 0u;
   // bvh.rs:382-383, as a mask over the q3.z axis bit of a node
   const uint32_t oct = (rb.inv.x < 0.0f ? 1u : 0u) | (rb.inv.y < 0.0f ? 2u : 0u) | (rb.inv.z < 0.0f ? 4u : 0u);
-  uint32_t l_ref[PB_LM_STACK];
-  float l_t0[PB_LM_STACK];
+  uint32_t l_ref[LMD];
+  float l_t0[ANY ? 1 : LMD];
   TStack<ANY> st;
   st.init(s_ref, s_t0);
   auto box = [&](float ax, float ay, float az, float bx, float by, float bz, float* T0) {
@@ -247,7 +252,7 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, floa
       if (SM && st.in_shared()) {
         st.get(&r, &t0);
       } else {
-        const int k = st.depth() - PB_SM_STACK;
+        const int k = st.depth() - SMD;
         r = l_ref[k];
         if (!ANY) t0 = l_t0[k];
       }
@@ -257,13 +262,15 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, floa
   };
   // one inner-node step: both children's boxes, descend near / push far / pop
   auto node_step = [&](uint32_t cur) -> uint32_t {
+    if (COUNT) ++res.steps;
     const float4* n = sc.nodes + 4ull * cur;
     const float4 q0 = ldg4(n), q1 = ldg4(n + 1), q2 = ldg4(n + 2), q3 = ldg4(n + 3);
     float T00, T01;
     const bool h0 = box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &T00);
     const bool h1 = box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &T01);
     const uint32_t r0 = __float_as_uint(q3.x), r1 = __float_as_uint(q3.y);
-    if (h0 & h1) {
+    if (h0) {
+      if (!h1) return r0;
       // both pass.  bvh.rs:409-415: dir_is_neg[axis] -> the second child is visited first
       bool neg = false;
       if (!UNORDERED) neg = (__float_as_uint(q3.z) & oct) != 0u;  // q3.z = 1 << axis
@@ -272,15 +279,15 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, floa
       if (SM && st.in_shared()) {
         st.put(far_ref, far_t0);
       } else {
-        const int k = st.depth() - PB_SM_STACK;
-        if (k >= PB_LM_STACK) return PB_DONE_OVF;
+        const int k = st.depth() - SMD;
+        if (k >= LMD) return PB_DONE_OVF;
         l_ref[k] = far_ref;
         if (!ANY) l_t0[k] = far_t0;
       }
       st.up();
       return neg ? r1 : r0;
     }
-    if (h0 | h1) return h0 ? r0 : r1;
+    if (h1) return r1;
     return pop();
   };
   // bvh.rs:398-405: every primitive of the leaf in order; the last accepted hit wins.
@@ -295,6 +302,7 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, floa
     int leaf_ok = -1;  // LEAF_EXACT: the reference's test of this leaf's box (bvh.rs:393), evaluated
                        // lazily with the maxt the leaf was entered with — no hit, no test
     for (uint32_t i = 0; i < cnt; ++i) {
+      if (COUNT) res.steps += 2u;  // a primitive test costs about two node steps
       const uint32_t pi = off + i;
       uint32_t pr = SPH ? __ldg(&sc.leaf_prim[pi]) : pi;
       bool hit;
@@ -381,6 +389,12 @@ PB_DEV bool ffma_constants(const DScene& sc, f3 o, f3 inv, RayBox* rb) {
   return true;
 }
 
+// Which kernels get the 27-loop per-axis dispatch (else 8 octant loops + the generic one for warps
+// that mix signs): measured, the any-hit kernel gains from it, the closest-hit kernel loses
+// (instruction-cache pressure, profiles/r02_notes.md).
+#ifndef PB_TRI_STATE
+#define PB_TRI_STATE(ANY) (ANY)
+#endif
 #ifdef PB_HOST_CHECK
 static int pb_host_force_mixed = 0;  // bit a: treat axis a as sign-mixed (tests/devsrc only)
 #endif
@@ -389,7 +403,7 @@ static int pb_host_force_mixed = 0;  // bit a: treat axis a as sign-mixed (tests
 // (the reference's compare-and-swap, NaN-faithful).  BOX 2 / 3 are specialised per axis for the sign
 // of 1/d when the whole warp agrees on it (AX: 0 / 1), an axis on which the warp mixes signs keeps
 // the min / max form (AX: 2) — one of 27 loops, selected by a warp-uniform switch.
-template <bool ANY, bool SPH, bool MULTI, int MODE, int BOX = 1>
+template <bool ANY, bool SPH, bool MULTI, int MODE, int BOX = 1, bool COUNT = false>
 PB_DEV TraceResult trace_ray(const DScene& sc, f3 o, f3 d, float mint, float maxt, uint32_t* s_ref,
                              float* s_t0) {
   RayBox rb;
@@ -400,7 +414,7 @@ PB_DEV TraceResult trace_ray(const DScene& sc, f3 o, f3 d, float mint, float max
   const float big = fmaxf(fmaxf(fabsf(inv.x), fabsf(inv.y)), fabsf(inv.z));
   // (NaN-propagating test: a NaN or infinite component takes the exact-compare path)
   const bool finite = big < __int_as_float(0x7f800000) && inv.x == inv.x && inv.y == inv.y && inv.z == inv.z;
-  if (!finite || !sc.boxes_finite) return traverse<ANY, SPH, MULTI, 0, 0, 0>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
+  if (!finite || !sc.boxes_finite) return traverse<ANY, SPH, MULTI, 0, 0, 0, COUNT>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
   if (BOX >= 2 && sc.boxes_ordered) {
     bool ok = true;
     if (BOX == 3) ok = ffma_constants(sc, o, inv, &rb);
@@ -416,18 +430,24 @@ PB_DEV TraceResult trace_ray(const DScene& sc, f3 o, f3 d, float mint, float max
       if (pb_host_force_mixed & 2) sy = 2;
       if (pb_host_force_mixed & 4) sz = 2;
 #endif
-      switch (sx + 3 * sy + 9 * sz) {
 #define PB_AX(X, Y, Z) \
   case X + 3 * Y + 9 * Z: \
     return traverse<ANY, SPH, MULTI, BOX, MODE, X | (Y << 2) | (Z << 4)>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
+      if (PB_TRI_STATE(ANY)) {  // 27 loops: shadow rays towards a light overhead mix signs in most warps
+        switch (sx + 3 * sy + 9 * sz) {
 #define PB_AX3(Y, Z) PB_AX(0, Y, Z) PB_AX(1, Y, Z) PB_AX(2, Y, Z)
 #define PB_AX9(Z) PB_AX3(0, Z) PB_AX3(1, Z) PB_AX3(2, Z)
-        PB_AX9(0) PB_AX9(1) PB_AX9(2)
+          PB_AX9(0) PB_AX9(1) PB_AX9(2)
 #undef PB_AX9
 #undef PB_AX3
-#undef PB_AX
+        }
+      } else if (sx != 2 && sy != 2 && sz != 2) {  // 8 loops: camera rays share their octant
+        switch (sx + 3 * sy + 9 * sz) {
+          PB_AX(0, 0, 0) PB_AX(1, 0, 0) PB_AX(0, 1, 0) PB_AX(1, 1, 0) PB_AX(0, 0, 1) PB_AX(1, 0, 1) PB_AX(0, 1, 1) PB_AX(1, 1, 1)
+        }
       }
+#undef PB_AX
     }
   }
-  return traverse<ANY, SPH, MULTI, 1, MODE, 0>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
+  return traverse<ANY, SPH, MULTI, 1, MODE, 0, COUNT>(sc, o, d, rb, mint, maxt, s_ref, s_t0);
 }

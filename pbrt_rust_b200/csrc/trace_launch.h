@@ -23,3 +23,8 @@ cudaError_t pb_launch_trace(bool any, int src, int box, const TraceLaunchCfg& cf
 cudaError_t pb_launch_trace_box1(bool any, int src, const TraceLaunchCfg& cfg, const DScene& sc, const DCamera& cam, const TraceArgs& a);
 cudaError_t pb_launch_trace_box2(bool any, int src, const TraceLaunchCfg& cfg, const DScene& sc, const DCamera& cam, const TraceArgs& a);
 cudaError_t pb_launch_trace_box3(bool any, int src, const TraceLaunchCfg& cfg, const DScene& sc, const DCamera& cam, const TraceArgs& a);
+
+// Cost probe (trace_probe.cu): per film row, the summed traversal cost (node steps + primitive tests,
+// camera ray + one shadow ray per light) of one probe ray per stride x stride pixels.
+cudaError_t pb_launch_cost_probe(const TraceLaunchCfg& cfg, const DScene& sc, const DCamera& cam, int x0, int y0,
+                                 int w, int h, int stride, float base_cost, const void* area_tris, float* d_row_cost);

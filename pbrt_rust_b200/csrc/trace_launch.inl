@@ -3,6 +3,13 @@
 
 #include "trace_launch.h"
 
+// SIMT loop shapes (trace_core.cuh traverse): measured best per kernel kind
+#ifndef PB_MODE_ANY
+#define PB_MODE_ANY 2
+#endif
+#ifndef PB_MODE_CLOSEST
+#define PB_MODE_CLOSEST 1
+#endif
 namespace {
 template <class K>
 int grid_for(K kfn, int sm_count) {
@@ -19,7 +26,7 @@ int grid_for(K kfn, int sm_count) {
 }
 template <bool ANY, int SRC>
 cudaError_t launch(const TraceLaunchCfg& cfg, const DScene& sc, const DCamera& cam, const TraceArgs& a) {
-  constexpr int MODE = ANY ? 2 : 1;
+  constexpr int MODE = ANY ? PB_MODE_ANY : PB_MODE_CLOSEST;
 #define PB_LAUNCH(SPH, MULTI)                                                      \
   {                                                                                \
     auto kfn = k_trace<ANY, SPH, MULTI, SRC, MODE, PB_TRACE_BOX>;                  \

@@ -5,20 +5,10 @@ oracle are fed from these same descriptions.  The generator PRNG is SplitMix64 (
 the renderer's StdRng)."""
 import numpy as np
 
+from .procgen import heightfield, quad_light as _quad_light, random_triangles, splitmix64  # noqa: F401
 from .api import (AreaLight, Camera, CylindricalMapping2D, Film, Filter, IdentityMapping3D, Light, Material,
                   PlanarMapping2D, Primitive, SphericalMapping2D,
                   Sampler, Scene, Shape, SurfaceIntegrator, Texture, Transform, UVMapping2D)
-
-
-def splitmix64(seed, n):
-    """n uniform floats in [0,1) from SplitMix64(seed), vectorised."""
-    with np.errstate(over="ignore"):
-        i = np.arange(1, n + 1, dtype=np.uint64)
-        z = np.uint64(seed) + i * np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
 
 
 def _matte(kd=0.5, sigma=0.0):
@@ -56,15 +46,6 @@ def config1(xres=640, yres=480, sampler="stratified", crop=(0, 1, 0, 1), filt=No
     return _setup(scene, c2w, 60.0, xres, yres, 2, 2, True, sampler=sampler, crop=crop, filt=filt)
 
 
-def random_triangles(n=100_000, seed=1):
-    u = splitmix64(seed, n * 12).reshape(n, 12)
-    c = u[:, 0:3] * 20.0 - 10.0
-    off = (u[:, 3:12] * 0.6 - 0.3).reshape(n, 3, 3)
-    P = (c[:, None, :] + off).astype(np.float32).reshape(-1, 3)
-    vi = np.arange(3 * n, dtype=np.uint32)
-    return vi, P
-
-
 def config2(n=100_000, xres=1920, yres=1080, seed=1, crop=(0, 1, 0, 1)):
     """BVH (sah/4) over n random triangles, pixel-centre samples, 1 spp."""
     vi, P = random_triangles(n, seed)
@@ -72,33 +53,6 @@ def config2(n=100_000, xres=1920, yres=1080, seed=1, crop=(0, 1, 0, 1)):
     scene = Scene.new_with(Primitive.bvh([Primitive.geometric(mesh, _matte())], 4, "sah"), [])
     c2w = Transform.look_at((0, 0, -35), (0, 0, 0), (0, 1, 0)).inverse()
     return _setup(scene, c2w, 40.0, xres, yres, 1, 1, False, crop=crop)
-
-
-def heightfield(nx, nz, x0=-20.0, x1=20.0, z0=-10.0, z1=10.0):
-    """(nx x nz) cells, 2 triangles per cell: y = 0.6 sin(0.9x) cos(1.1z) + 0.15 hash(i,j)."""
-    i = np.arange(nx + 1, dtype=np.float64)
-    j = np.arange(nz + 1, dtype=np.float64)
-    X, Z = np.meshgrid(x0 + (x1 - x0) * i / nx, z0 + (z1 - z0) * j / nz, indexing="ij")
-    ii, jj = np.meshgrid(np.arange(nx + 1, dtype=np.uint64), np.arange(nz + 1, dtype=np.uint64), indexing="ij")
-    with np.errstate(over="ignore"):
-        h = (ii * np.uint64(73856093)) ^ (jj * np.uint64(19349663))
-        h = (h ^ (h >> np.uint64(13))) * np.uint64(0x9E3779B97F4A7C15)
-        hv = (h >> np.uint64(40)).astype(np.float64) / float(1 << 24)
-    Y = 0.6 * np.sin(0.9 * X) * np.cos(1.1 * Z) + 0.15 * hv * (40.0 / nx)
-    P = np.stack([X, Y, Z], axis=-1).astype(np.float32).reshape(-1, 3)
-    a = (np.arange(nx)[:, None] * (nz + 1) + np.arange(nz)[None, :]).astype(np.uint32)
-    b, c, d = a + (nz + 1), a + 1, a + (nz + 1) + 1
-    vi = np.stack([np.stack([a, c, b], -1), np.stack([b, c, d], -1)], axis=2).reshape(-1).astype(np.uint32)
-    return vi, P
-
-
-def _quad_light(y=8.0, half=2.0, cx=0.0, cz=0.0):
-    P = np.array([[cx - half, y, cz - half], [cx + half, y, cz - half], [cx + half, y, cz + half],
-                  [cx - half, y, cz + half]], np.float32)
-    # winding chosen so that dg.nn (= normalize((p2-p1) x (p3-p2)) after the refine reversal,
-    # mesh.rs:220-262 with default uvs) points down (-y): the quad emits towards the ground.
-    vi = np.array([0, 2, 1, 0, 3, 2], np.uint32)
-    return vi, P
 
 
 def config3(nx=1000, nz=500, xres=1920, yres=1080, xs=4, ys=4, crop=(0, 1, 0, 1), n_lights=1,

@@ -328,8 +328,8 @@ int devsrc_trace(const pbrtb200_scene* s, const float* rays8, unsigned long long
   DScene sc{};
   bool sph = false, multi = false;
   if (!traversal_scene(s, &pn, &sc, &sph, &multi)) return -1;
-  std::vector<uint32_t> s_ref((size_t)PB_SM_STACK * PB_TRACE_THREADS);
-  std::vector<float> s_t0((size_t)PB_SM_STACK * PB_TRACE_THREADS);  // (host stack: two arrays)
+  std::vector<uint32_t> s_ref((size_t)(PB_SM_STACK_MAX + 1) * PB_TRACE_THREADS);
+  std::vector<float> s_t0((size_t)(PB_SM_STACK_MAX + 1) * PB_TRACE_THREADS);  // (host stack: two arrays)
   int rc = 0;
   for (unsigned long long i = 0; i < n; ++i) {
     const float* r = rays8 + 8 * i;
@@ -364,7 +364,6 @@ extern "C" {
 // non-area light term, no Le slot).  out_xyzw = the film, row-major over the film pixel extent.
 void devsrc_film_gather(const pbrtb200_film* film, const int* ext4, int spp, const float* img2, const float* rgb3,
                         float* out_xyzw) {
-  std::memcpy(c_filter_table, film->filter_table, sizeof c_filter_table);
   DFilm f{};
   f.x_start = film->x_pixel_start;
   f.y_start = film->y_pixel_start;
@@ -376,24 +375,17 @@ void devsrc_film_gather(const pbrtb200_film* film, const int* ext4, int spp, con
   f.inv_yw = 1.0f / film->filter_yw;
   f.sx0 = ext4[0]; f.sx1 = ext4[1]; f.sy0 = ext4[2]; f.sy1 = ext4[3];
   f.spp = spp;
-  DFold fd{};
-  fd.rad_slots = 1;
-  fd.le_slot = 0;
-  fd.n_lights = 1;
-  fd.ns[0] = 1;
-  fd.area[0] = 0;
   const size_t npx = (size_t)(ext4[1] - ext4[0]) * (size_t)(ext4[3] - ext4[2]), ns = npx * (size_t)spp;
-  std::vector<float4> rad(ns);
-  for (size_t i = 0; i < ns; ++i) rad[i] = make_float4(rgb3[3 * i], rgb3[3 * i + 1], rgb3[3 * i + 2], 0.f);
+  std::vector<float4> rec(ns);  // radiance records: one light term, no emitter
+  for (size_t i = 0; i < ns; ++i) rec[i] = make_float4(rgb3[3 * i], rgb3[3 * i + 1], rgb3[3 * i + 2], 0.f);
   std::vector<uint32_t> edge(npx, 1u);
   std::vector<int32_t> index(npx);
   for (size_t i = 0; i < npx; ++i) index[i] = (int32_t)i;
   const int32_t rect[4] = {f.x_start, f.y_start, f.x_start + f.x_count, f.y_start + f.y_count};
   const uint32_t prefix[2] = {0u, (uint32_t)(f.x_count * f.y_count)};
-  uint32_t nan_count = 0;
   FilmArgs a{};
   a.img = reinterpret_cast<const float2*>(img2);
-  a.rad = rad.data();
+  a.rec = rec.data();
   a.offsets = nullptr;
   a.edge = edge.data();
   a.pix_index = index.data();
@@ -403,9 +395,10 @@ void devsrc_film_gather(const pbrtb200_film* film, const int* ext4, int spp, con
   a.n_pixels = prefix[1];
   a.first = 0;
   a.count = prefix[1];
+  a.pixel_mask = 0xFFFFFFFFu;
   a.out = reinterpret_cast<float4*>(out_xyzw);
-  a.nan_count = &nan_count;
-  for (uint32_t gid = 0; gid < a.n_pixels; ++gid) film_pixel(f, fd, a, gid);
+  std::memcpy(a.table, film->filter_table, sizeof a.table);
+  for (uint32_t gid = 0; gid < a.n_pixels; ++gid) film_pixel(f, a, gid);
 }
 }
 
@@ -497,8 +490,8 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
   const size_t npx = (size_t)(ext4[1] - ext4[0]) * (size_t)(ext4[3] - ext4[2]), n = npx * (size_t)spp;
   const float2* img = reinterpret_cast<const float2*>(img2);
   const float2* lens = (lens2 && c->lens_radius > 0.0f) ? reinterpret_cast<const float2*>(lens2) : nullptr;
-  std::vector<uint32_t> s_ref((size_t)PB_SM_STACK * PB_TRACE_THREADS);
-  std::vector<float> s_t0((size_t)PB_SM_STACK * PB_TRACE_THREADS);  // (host stack: two arrays)
+  std::vector<uint32_t> s_ref((size_t)(PB_SM_STACK_MAX + 1) * PB_TRACE_THREADS);
+  std::vector<float> s_t0((size_t)(PB_SM_STACK_MAX + 1) * PB_TRACE_THREADS);  // (host stack: two arrays)
   // closest hit per camera sample (the SRC = 1 path of k_trace: camera_ray, mint 0, maxt f32::MAX)
   std::vector<pbrtb200_hit16> hits(std::max<size_t>(1, n));
   int rc = 0;
@@ -512,14 +505,13 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
     hits[i].b1 = t.b1;
     hits[i].b2 = t.b2;
   }
-  // k_shade
+  // k_shade: `slots` radiance terms per sample (one slot: they are the radiance records themselves)
   const uint32_t slots = std::max(1u, sc.light_slots);
-  const uint32_t le_slot = sc.area_sample_pairs ? 1u : 0u;
-  const uint32_t rad_slots = sc.n_lights ? sc.light_slots + le_slot : 0u;
-  std::vector<float4> rad(std::max<size_t>(1, n * std::max(1u, rad_slots)));
+  std::vector<float4> terms(std::max<size_t>(1, n * slots));
+  std::vector<float4> rec(std::max<size_t>(1, n));
   std::vector<pbrtb200_ray32> sq_rays(std::max<size_t>(1, n * slots));
   std::vector<uint32_t> sq_slots(std::max<size_t>(1, n * slots));
-  uint32_t sq_count = 0;
+  uint32_t sq_count = 0, nan_count = 0;
   unsigned long long hit_total = 0, occluded = 0;
   if (sc.n_lights) {
     ShadeArgs sa{};
@@ -528,15 +520,14 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
     sa.lightu = sc.area_sample_pairs ? reinterpret_cast<const float2*>(lightu) : nullptr;
     sa.hits = hits.data();
     sa.area_tris = at.data();
-    sa.rad = rad.data();
+    sa.terms = terms.data();
     sa.sq_rays = sq_rays.data();
     sa.sq_slots = sq_slots.data();
     sa.sq_count = &sq_count;
     sa.hit_total = &hit_total;
+    sa.nan_count = &nan_count;
     sa.n = n;
-    sa.sample0 = 0;
-    sa.rad_slots = rad_slots;
-    sa.le_slot = le_slot;
+    sa.slots = slots;
     sa.strict_flags = strict_flags;
     for (size_t i = 0; i < n; ++i) {
       blockIdx.x = (unsigned)i;
@@ -553,14 +544,31 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
       const TraceResult t = trace_any_variant<true, 2>(sc, sph, multi, mk3(r.o[0], r.o[1], r.o[2]), mk3(r.d[0], r.d[1], r.d[2]),
                                                        r.mint, r.maxt, s_ref.data(), s_t0.data());
       if (t.prim == PB_OVERFLOW) rc = -2;
+      float4& term = terms[sq_slots[q] & PB_SQ_INDEX];  // what k_trace<ANY> does with the guarded term
       if (t.prim != PBRTB200_MISS) {
-        rad[sq_slots[q]] = make_float4(0.f, 0.f, 0.f, 0.f);
+        term = make_float4(0.f, 0.f, 0.f, (sq_slots[q] & PB_SQ_KEEPW) ? term.w : 0.f);
         ++occluded;
+      } else if (sq_slots[q] & PB_SQ_NAN) {
+        ++nan_count;
       }
     }
   }
+  DFold fd{};
+  fd.slots = slots;
+  fd.n_lights = sc.n_lights;
+  for (uint32_t i = 0; i < sc.n_lights; ++i) {
+    fd.area[i] = lights[i].kind == PBRTB200_LIGHT_AREA ? 1 : 0;
+    fd.ns[i] = (uint16_t)(fd.area[i] ? lights[i].num_samples : 1);
+  }
+  if (sc.n_lights) {
+    if (slots > 1) {  // k_fold
+      for (size_t i = 0; i < n; ++i)
+        if (fold_terms(fd, sc.lights, terms.data() + i * slots, &rec[i])) ++nan_count;
+    } else {
+      rec = terms;
+    }
+  }
   // film
-  std::memcpy(c_filter_table, film->filter_table, sizeof c_filter_table);
   DFilm f{};
   f.x_start = film->x_pixel_start;
   f.y_start = film->y_pixel_start;
@@ -572,23 +580,15 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
   f.inv_yw = 1.0f / film->filter_yw;
   f.sx0 = ext4[0]; f.sx1 = ext4[1]; f.sy0 = ext4[2]; f.sy1 = ext4[3];
   f.spp = spp;
-  DFold fd{};
-  fd.rad_slots = rad_slots;
-  fd.le_slot = le_slot;
-  fd.n_lights = sc.n_lights;
-  for (uint32_t i = 0; i < sc.n_lights; ++i) {
-    fd.area[i] = lights[i].kind == PBRTB200_LIGHT_AREA ? 1 : 0;
-    fd.ns[i] = (uint16_t)(fd.area[i] ? lights[i].num_samples : 1);
-  }
   std::vector<uint32_t> edge(npx, 1u);
   std::vector<int32_t> index(npx);
   for (size_t i = 0; i < npx; ++i) index[i] = (int32_t)i;
   const int32_t rect[4] = {f.x_start, f.y_start, f.x_start + f.x_count, f.y_start + f.y_count};
   const uint32_t prefix[2] = {0u, (uint32_t)(f.x_count * f.y_count)};
-  uint32_t nan_count = 0;
   FilmArgs a{};
   a.img = img;
-  a.rad = rad.data();
+  a.rec = sc.n_lights ? rec.data() : nullptr;
+  a.lights = sc.lights;
   a.edge = edge.data();
   a.pix_index = index.data();
   a.rects = rect;
@@ -597,9 +597,10 @@ int devsrc_render(const pbrtb200_scene* s, const pbrtb200_camera* c, const pbrtb
   a.n_pixels = prefix[1];
   a.first = 0;
   a.count = prefix[1];
+  a.pixel_mask = 0xFFFFFFFFu;
   a.out = reinterpret_cast<float4*>(out_xyzw);
-  a.nan_count = &nan_count;
-  for (uint32_t gid = 0; gid < a.n_pixels; ++gid) film_pixel(f, fd, a, gid);
+  std::memcpy(a.table, film->filter_table, sizeof a.table);
+  for (uint32_t gid = 0; gid < a.n_pixels; ++gid) film_pixel(f, a, gid);
   stats3[0] = hit_total;
   stats3[1] = sq_count;
   stats3[2] = occluded;

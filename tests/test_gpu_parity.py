@@ -230,6 +230,72 @@ def test_tiles_are_partition_independent(orc):
     assert np.array_equal(merged.view(np.uint32), whole.view(np.uint32))
 
 
+@pytest.mark.parametrize("filt", [None, "gaussian"])
+@pytest.mark.parametrize("lights", [(1, 1), (3, 2)])
+def test_sample_ring_and_small_chunks_give_the_same_film(orc, monkeypatch, filt, lights):
+    """The wavefront buffers are O(chunk): with a tiny frame budget the per-sample buffers become a ring
+    over list pixels, chunks run in list order and finished film rows are filtered band by band.  The
+    film must equal the single-chunk, whole-frame render bit for bit (host and device output), for one
+    light slot (records written by k_shade) and several (k_fold), box and wide filters."""
+    f = pb.Filter.gaussian(2.0, 2.0, 2.0) if filt else None
+    cfg = scenes.config3(nx=80, nz=40, xres=128, yres=96, xs=2, ys=2, n_lights=lights[0], light_samples=lights[1])
+    if f is not None:
+        cfg = scenes._setup(cfg["scene"], cfg["camera"].cam2world, 36.0, 128, 96, 2, 2, True, filt=f)
+    r = _renderer(cfg)
+    want = r.render(cfg["scene"]).copy()
+    assert want[..., 3].min() > 0 and r.last_stats["shadow_rays"] > 0
+    monkeypatch.setenv("PBRTB200_FRAME_BUDGET_MB", "1")
+    for lg in (12, 14):
+        monkeypatch.setenv("PBRTB200_CHUNK_LOG2", str(lg))
+        got = r.render(cfg["scene"])
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), lg
+        assert r.last_stats["kernel_launches"] >= 15         # really ran in several chunks and bands
+        dev = torch.zeros(want.size, dtype=torch.float32, device="cuda")
+        r.render(cfg["scene"], out=dev)
+        assert np.array_equal(dev.cpu().numpy().reshape(want.shape).view(np.uint32), want.view(np.uint32)), lg
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+def test_group_render_is_bit_identical_to_one_gpu(orc, n_dev):
+    """pbrtb200_group_render: the frame cut into row bands over n_dev GPUs, every device copying its
+    own rows into the caller's host film (or storing them into the first device's film over peer
+    access), equals the single-context render bit for bit — first frame (bands from the cost probe)
+    and later frames of the same view (bands rebalanced on measured times)."""
+    if torch.cuda.device_count() < n_dev:
+        pytest.skip(f"needs {n_dev} CUDA devices")
+    cfg = scenes.config3(nx=120, nz=60, xres=200, yres=150, xs=2, ys=2, n_lights=2, light_samples=2)
+    want = _renderer(cfg).render(cfg["scene"]).copy()
+    grp = pb.Group(list(range(n_dev)))
+    r = _renderer(cfg, ctx=grp)
+    for frame in range(4):
+        got = r.render(cfg["scene"])
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), frame
+        bounds, ms = grp.bands()
+        assert bounds[0] == 0 and bounds[-1] == 150 and all(a <= b for a, b in zip(bounds, bounds[1:]))
+    assert r.last_stats["camera_rays"] >= cfg["sampler"].samples_per_pixel() * 200 * 150
+    dev = torch.zeros(want.size, dtype=torch.float32, device="cuda:0")
+    r.render(cfg["scene"], out=dev)
+    assert np.array_equal(dev.cpu().numpy().reshape(want.shape).view(np.uint32), want.view(np.uint32))
+    wide = scenes.config1(xres=96, yres=64, filt=pb.Filter.gaussian(2.0, 2.0, 2.0))
+    want = _renderer(wide).render(wide["scene"]).copy()
+    got = _renderer(wide, ctx=pb.Group(list(range(n_dev)))).render(wide["scene"])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_cost_profile_follows_the_scene(orc):
+    """pbrtb200_cost_profile: rows that see geometry cost more than rows that see nothing, and the
+    probe rows repeat over their stride."""
+    cfg = scenes.config1(xres=64, yres=96)
+    r = _renderer(cfg)
+    c = r.cost_profile(cfg["scene"], stride=4)
+    assert c.shape == (96,) and np.isfinite(c).all() and (c > 0).all()
+    assert np.array_equal(c[0::4], c[1::4]) and np.array_equal(c[0::4], c[3::4])
+    hits, _, _ = r.primary_hits(cfg["scene"])
+    e = cfg["sampler"].ext
+    per_row = (hits["prim"].reshape(e[3] - e[2], -1) != 0xFFFFFFFF).mean(axis=1)
+    assert c[per_row[:96] > 0.3].mean() > 1.2 * c[per_row[:96] == 0].mean()
+
+
 def test_empty_tile_set_renders_nothing(orc):
     """a tile set with zero rects is "no pixel", not "the whole film": the film comes back
     zeroed, or untouched with keep_others (a rank whose band is empty must not overwrite the gather)."""
