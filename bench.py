@@ -150,7 +150,6 @@ def run_reference(args):
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
-    _, rc_c, _ = cpu_scene(args.config, scale, cores, 1, count=True) if False else (None, None, None)
     rc.count_traversal = 1  # one counted frame: shadow rays are only counted with the traversal counters on
     st = orc.render(scene, rc)["stats"]
     rays = st["camera_rays"] + st["shadow_rays"]
@@ -224,16 +223,23 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank == 0:
         g.build()
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+        # one NCCL collective proves the N ranks see each other over NVLink; after that the ranks meet
+        # on a gloo (CPU) group: an NCCL barrier is a kernel that SPINS on its GPU until every rank
+        # arrives, and ranks 1..N-1 would spin on the very GPUs rank 0 is rendering on
+        t = torch.ones(1, device=torch.device("cuda", local))
+        dist.all_reduce(t)
+        assert int(t.item()) == world
+        cpu_group = dist.new_group(backend="gloo")
     torch.cuda.set_device(local)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     if rank != 0:
         # Ranks 1..N-1 hold their GPU for the job and join the barriers around the timed regions; rank 0

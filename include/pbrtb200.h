@@ -341,6 +341,12 @@ int pbrtb200_group_upload_scene(pbrtb200_group* g, const pbrtb200_scene* scene);
 int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const pbrtb200_sampler* smp,
                           const pbrtb200_film* film, const pbrtb200_integrator* integ, float* out_xyzw,
                           int out_is_device, pbrtb200_stats* stats);
+/* Device i's own stats of the last frame (rays it traced, its stage times). */
+int pbrtb200_group_device_stats(const pbrtb200_group* g, int i, pbrtb200_stats* out);
+/* The band cut itself (pure host arithmetic, no device needed): n_bands contiguous row bands of equal
+ * summed cost over film rows y0 .. y0 + n_rows, boundaries snapped to 4 rows (sampler pixels are
+ * listed in 8 x 4 tiles), non-decreasing, bounds[0] = y0, bounds[n_bands] = y0 + n_rows. */
+int pbrtb200_cut_bands(const float* row_cost, int n_rows, int y0, int n_bands, int32_t* bounds);
 /* Row bands of the last frame: bounds[0 .. n_devices] (film rows, bounds[i] .. bounds[i+1] on device i)
  * and each device's device time in ms; either pointer may be NULL. */
 int pbrtb200_group_bands(const pbrtb200_group* g, int32_t* bounds, float* device_ms);

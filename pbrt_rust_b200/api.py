@@ -624,6 +624,15 @@ class Group:
         self.check(lib().pbrtb200_group_bands(self.h, b, _fp(t)))
         return list(b), t.tolist()
 
+    def device_stats(self):
+        """Per-device stats dicts of the last frame."""
+        out = []
+        for i in range(len(self.devices)):
+            st = _ffi.Stats()
+            self.check(lib().pbrtb200_group_device_stats(self.h, i, C.byref(st)))
+            out.append(st.as_dict())
+        return out
+
     def close(self):
         if self.h:
             lib().pbrtb200_group_destroy(self.h)

@@ -129,6 +129,15 @@ pbrtb200_ctx* pbrtb200_group_ctx(pbrtb200_group* g, int i) {
   return (g && i >= 0 && i < (int)g->w.size()) ? g->w[(size_t)i].ctx : nullptr;
 }
 
+int pbrtb200_cut_bands(const float* row_cost, int n_rows, int y0, int n_bands, int32_t* bounds) {
+  if (!row_cost || !bounds || n_rows < 1 || n_bands < 1) return PBRTB200_EINVAL;
+  std::vector<double> c(row_cost, row_cost + n_rows);
+  std::vector<int> b;
+  cut_bands(c, y0, n_bands, 4, &b);
+  for (int i = 0; i <= n_bands; ++i) bounds[i] = b[(size_t)i];
+  return PBRTB200_OK;
+}
+
 int pbrtb200_group_create(const int* devices, int n_devices, pbrtb200_group** out) {
   if (!out) return PBRTB200_EINVAL;
   *out = nullptr;
@@ -216,6 +225,12 @@ int pbrtb200_group_upload_scene(pbrtb200_group* g, const pbrtb200_scene* scene) 
   g->view.valid = false;
   g->run([&](int i) { g->w[(size_t)i].rc = pbrtb200_upload_scene(g->w[(size_t)i].ctx, scene); });
   return g->collect("upload_scene");
+}
+
+int pbrtb200_group_device_stats(const pbrtb200_group* g, int i, pbrtb200_stats* out) {
+  if (!g || !out || i < 0 || i >= (int)g->w.size()) return PBRTB200_EINVAL;
+  *out = g->w[(size_t)i].st;
+  return PBRTB200_OK;
 }
 
 int pbrtb200_group_bands(const pbrtb200_group* g, int32_t* bounds, float* device_ms) {

@@ -100,3 +100,27 @@ def test_band_balancer_always_covers_the_film_exactly_once(world, ext):
                 cov[y0 - ext[2]:y1 - ext[2], a - ext[0]:c - ext[0]] += 1
         assert cov.min() == 1 and cov.max() == 1
         bal.update(list(rng.random(world) * 3 + 0.01))
+
+
+@pytest.mark.parametrize("n_bands", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("rows,y0", [(1080, 0), (150, 7), (5, 0), (33, -2)])
+def test_group_band_cut_covers_the_film_and_balances_cost(n_bands, rows, y0):
+    """pbrtb200_cut_bands (the host arithmetic inside pbrtb200_group_render): contiguous bands that
+    cover every row once, boundaries on multiples of 4 rows, summed cost per band within one quantum
+    of the ideal share — for flat, ramped and spiky cost profiles, more bands than rows included."""
+    import ctypes as C
+    from pbrt_rust_b200 import _ffi
+    L = _ffi.lib()
+    rng = np.random.default_rng(rows * 10 + n_bands)
+    for cost in (np.ones(rows), np.linspace(1.0, 9.0, rows), rng.random(rows) ** 4 + 0.01, np.zeros(rows)):
+        cost = np.ascontiguousarray(cost, np.float32)
+        b = (C.c_int32 * (n_bands + 1))()
+        assert L.pbrtb200_cut_bands(cost.ctypes.data_as(C.POINTER(C.c_float)), rows, y0, n_bands, b) == 0
+        b = list(b)
+        assert b[0] == y0 and b[-1] == y0 + rows and all(x <= y for x, y in zip(b, b[1:]))
+        assert all((x - y0) % 4 == 0 for x in b[1:-1] if x != y0 + rows)
+        if cost.sum() > 0 and rows >= 16 * n_bands:
+            share = [cost[b[k] - y0:b[k + 1] - y0].sum() for k in range(n_bands)]
+            ideal = cost.sum() / n_bands
+            slack = 4 * cost.max() + 1e-6          # one quantum of the most expensive rows on either side
+            assert max(abs(s_ - ideal) for s_ in share) <= 2 * slack, (share, ideal)

@@ -2,6 +2,7 @@
 hot path.  Each test names the reference test it transcribes (file:line)."""
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import pytest
@@ -1429,3 +1430,23 @@ def test_area_light_is_one_sided_and_emits_its_radiance(orc):
     cfg = scenes.irradiance_probe(target=(0.0, 8.0, 0.0), eye=(0.5, 1.0, 0.3), emit_down=False, res=8, spp=2)
     ref = orc.render(orc.OracleScene(cfg["scene"]), orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0))
     assert ref["rgb"].max() == 0.0
+
+
+def test_reference_arm_scene_equals_the_api_scene_and_needs_no_product_code(orc):
+    """bench.py --impl reference builds config 3 from oracle/refscene.py (liborc.so + numpy only).  It
+    must describe the very same frame as pbrt_rust_b200.scenes.config3, and loading it must not pull
+    libpbrtb200.so into the process (the two arms share no code)."""
+    import subprocess
+    import sys
+    from oracle import refscene
+    from pbrt_rust_b200 import scenes
+    h, c = refscene.config3(nx=60, nz=30, xres=96, yres=64, xs=2, ys=2, mode=0)
+    a = orc.render(h, c)
+    cfg = scenes.config3(nx=60, nz=30, xres=96, yres=64, xs=2, ys=2)
+    b = orc.render(orc.OracleScene(cfg["scene"]), orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0))
+    assert np.array_equal(a["film"].view(np.uint32), b["film"].view(np.uint32))
+    code = ("import sys; sys.path.insert(0, %r)\nfrom oracle import orc, refscene\n"
+            "h, c = refscene.config3(nx=8, nz=4, xres=16, yres=16, xs=1, ys=1)\norc.render(h, c)\n"
+            "maps = open('/proc/self/maps').read()\nassert 'liborc' in maps and 'libpbrtb200' not in maps and 'pbrt_rust_b200' not in sys.modules\n"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    subprocess.check_call([sys.executable, "-c", code])
