@@ -79,6 +79,7 @@ struct pbrtb200_ctx {
   std::vector<uint32_t> rows_ready;   // per sampler row: list pixels that must be done (prefix max)
   std::vector<uint32_t> row_first;    // per sampler row r: smallest list index of any pixel in rows >= r
   std::string err;
+  CtrlBlock* h_ctrl = nullptr;  // page-locked mirror of the device control block (read back once per call)
   // scene
   bool has_scene = false, has_spheres = false, multi_leaf = false;
   bool shade_ext = false;  // the scene needs k_shade's general texture evaluator / bump mapping
@@ -528,6 +529,7 @@ int pbrtb200_create(int device, pbrtb200_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail("cudaStreamCreate", e);
   if ((e = ctx->d_ctrl.ensure(sizeof(CtrlBlock))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMallocHost(&ctx->h_ctrl, sizeof(CtrlBlock))) != cudaSuccess) return bail("cudaMallocHost", e);
   *out = ctx;
   return PBRTB200_OK;
 }
@@ -540,6 +542,7 @@ void pbrtb200_destroy(pbrtb200_ctx* ctx) {
   cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (void* p : ctx->peer_films) cudaFree(p);
+  if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
   for (cudaEvent_t ev : ctx->band_events) cudaEventDestroy(ev);
   delete ctx;
 }
@@ -783,8 +786,9 @@ static int run_trace_buffer(pbrtb200_ctx* ctx, bool any, const pbrtb200_ray32* d
 }
 
 static int finish_flags(pbrtb200_ctx* ctx, CtrlBlock* h) {
-  CK(cudaMemcpyAsync(h, ctx->d_ctrl.p, sizeof(CtrlBlock), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl.p, sizeof(CtrlBlock), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  *h = *ctx->h_ctrl;
   if (h->flags & 1u) FAIL(PBRTB200_ESTACK, "BVH traversal stack overflow (depth > 64)");
   return 0;
 }
@@ -1492,6 +1496,17 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
                            cudaMemcpyDeviceToHost, ctx->copy_stream));
       }
       CK(cudaStreamSynchronize(ctx->copy_stream));
+    } else if (tiles && (tiles->flags & PBRTB200_TILES_KEEP_OTHERS)) {
+      // only the rects this call owns travel to the host film (a group's devices each send their own
+      // rows over their own PCIe link); the rest of the caller's buffer is left alone
+      for (uint32_t q = 0; q < tiles->n_rects; ++q) {
+        const int32_t* rc4 = tiles->rects + 4 * q;
+        const size_t x0 = (size_t)(rc4[0] - film->x_pixel_start), y0r = (size_t)(rc4[1] - film->y_pixel_start);
+        const size_t wr = (size_t)(rc4[2] - rc4[0]), hr = (size_t)(rc4[3] - rc4[1]);
+        const size_t pitch = (size_t)film->x_pixel_count * sizeof(float4), off = y0r * (size_t)film->x_pixel_count + x0;
+        CK(cudaMemcpy2DAsync(out_xyzw + 4 * off, pitch, d_film + off, pitch, wr * sizeof(float4), hr,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+      }
     } else {
       CK(cudaMemcpyAsync(out_xyzw, d_film, film_px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -26,9 +26,6 @@ thread_local std::string g_group_create_err;
 struct Worker {
   int device = 0;
   pbrtb200_ctx* ctx = nullptr;
-  cudaStream_t copy = nullptr;  // this device's D2H rows
-  float* d_band = nullptr;      // this device's rows of the film (host-output frames)
-  size_t d_band_cap = 0;
   std::thread th;
   int rc = 0;
   pbrtb200_stats st{};
@@ -79,12 +76,24 @@ struct pbrtb200_group {
   void* reg_ptr = nullptr;
   size_t reg_bytes = 0;
 
+  // Hand-off: workers and the caller first SPIN on the atomics for a short while (back-to-back frames
+  // of an interactive / benchmark loop: a condition-variable wake-up costs 20-50 us of a ~1 ms frame),
+  // then sleep on the condition variables.
+  std::atomic<uint64_t> a_epoch{0};
+  std::atomic<int> a_pending{0};
+  static constexpr int kSpin = 20000;
   void run(const std::function<void(int)>& f) {
-    std::unique_lock<std::mutex> lk(mu);
-    job = f;
-    pending = (int)w.size();
-    ++epoch;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      job = f;
+      pending = (int)w.size();
+      a_pending.store(pending, std::memory_order_release);
+      ++epoch;
+      a_epoch.store(epoch, std::memory_order_release);
+    }
     cv_go.notify_all();
+    for (int k = 0; k < kSpin * 50 && a_pending.load(std::memory_order_acquire) != 0; ++k) std::this_thread::yield();
+    std::unique_lock<std::mutex> lk(mu);
     cv_done.wait(lk, [&] { return pending == 0; });
   }
   void loop(int i) {
@@ -92,6 +101,7 @@ struct pbrtb200_group {
     uint64_t seen = 0;
     for (;;) {
       std::function<void(int)> f;
+      for (int k = 0; k < kSpin && a_epoch.load(std::memory_order_acquire) == seen; ++k) std::this_thread::yield();
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_go.wait(lk, [&] { return quit || epoch != seen; });
@@ -102,7 +112,9 @@ struct pbrtb200_group {
       f(i);
       {
         std::lock_guard<std::mutex> lk(mu);
-        if (--pending == 0) cv_done.notify_all();
+        --pending;
+        a_pending.store(pending, std::memory_order_release);
+        if (pending == 0) cv_done.notify_all();
       }
     }
   }
@@ -168,13 +180,6 @@ int pbrtb200_group_create(const int* devices, int n_devices, pbrtb200_group** ou
       pbrtb200_group_destroy(g);
       return rc;
     }
-    cudaSetDevice(w.device);
-    if (cudaStreamCreateWithFlags(&w.copy, cudaStreamNonBlocking) != cudaSuccess) {
-      (void)cudaGetLastError();
-      g_group_create_err = "cudaStreamCreate failed";
-      pbrtb200_group_destroy(g);
-      return PBRTB200_ENODEV;
-    }
   }
   // peer access towards the first device (device-resident films); absent peer access only disables
   // that output mode
@@ -207,12 +212,6 @@ void pbrtb200_group_destroy(pbrtb200_group* g) {
     if (w.th.joinable()) w.th.join();
   if (g->reg_ptr) cudaHostUnregister(g->reg_ptr);
   for (Worker& w : g->w) {
-    if (w.ctx || w.copy || w.d_band) cudaSetDevice(w.device);
-    if (w.copy) {
-      cudaStreamSynchronize(w.copy);
-      cudaStreamDestroy(w.copy);
-    }
-    if (w.d_band) cudaFree(w.d_band);
     if (w.ctx) pbrtb200_destroy(w.ctx);
   }
   (void)cudaGetLastError();
@@ -276,15 +275,16 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
     g->view.yw = film->filter_yw;
     g->view.valid = true;
     g->frames_in_view = 0;
-  } else if (n > 1 && g->frames_in_view < 16 && g->device_ms.size() == (size_t)n) {
+  } else if (n > 1 && g->frames_in_view < 10 && g->device_ms.size() == (size_t)n) {
     // same view again: rescale each band's cost density by the time its device needed last frame
-    // and cut again (damped), until the slowest device is within 2 % of the mean
+    // and cut again (damped), until the slowest device is within 3 % of the mean (or 10 frames: every
+    // move rebuilds the devices' pixel lists, tens of milliseconds of host work)
     double mean = 0, mx = 0;
     for (float t : g->device_ms) {
       mean += t / n;
       mx = std::max<double>(mx, t);
     }
-    if (mean > 0 && mx > 1.02 * mean) {
+    if (mean > 0 && mx > 1.03 * mean) {
       double total_cost = 0;
       for (double c : g->row_cost) total_cost += c;
       for (int k = 0; k < n; ++k) {
@@ -335,28 +335,9 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
       w.rc = pbrtb200_render(w.ctx, cam, smp, film, integ, &ts, out_xyzw, 1, &w.st);
       return;
     }
-    // Host film: render into a full-size device film (only this band's rows are written), then copy
-    // exactly those rows into the caller's buffer.
-    if (w.d_band_cap < film_bytes) {
-      if (w.d_band) cudaFree(w.d_band);
-      w.d_band = nullptr;
-      w.d_band_cap = 0;
-      if (cudaMalloc(&w.d_band, film_bytes) != cudaSuccess) {
-        (void)cudaGetLastError();
-        w.rc = PBRTB200_ENOMEM;
-        return;
-      }
-      w.d_band_cap = film_bytes;
-    }
-    w.rc = pbrtb200_render(w.ctx, cam, smp, film, integ, &ts, w.d_band, 1, &w.st);
-    if (w.rc != PBRTB200_OK && w.rc != PBRTB200_ENAN) return;
-    const size_t off = (size_t)(a - y0) * (size_t)W * 4;
-    const cudaError_t e = cudaMemcpyAsync(out_xyzw + off, w.d_band + off, (size_t)(b - a) * (size_t)W * 4 * sizeof(float),
-                                          cudaMemcpyDeviceToHost, w.copy);
-    if (e != cudaSuccess || cudaStreamSynchronize(w.copy) != cudaSuccess) {
-      (void)cudaGetLastError();
-      w.rc = PBRTB200_ENODEV;
-    }
+    // Host film: pbrtb200_render with KEEP_OTHERS copies exactly this band's rows into the caller's
+    // buffer, on this device's own stream (one synchronisation per device and frame).
+    w.rc = pbrtb200_render(w.ctx, cam, smp, film, integ, &ts, out_xyzw, 0, &w.st);
   });
 
   g->device_ms.assign((size_t)n, 0.f);
