@@ -82,9 +82,31 @@ PB_DEV f3 mip_ewa(const float4* __restrict__ texels, const pbrtb200_mipmap& mm, 
   const int t0 = f2i_sat(ceilf(t - 2.0f * inv_det * v_sqrt)), t1 = f2i_sat(floorf(t + 2.0f * inv_det * v_sqrt));
   f3 sum = mk3(0.f, 0.f, 0.f);
   float sum_wts = 0.0f;
+  // The reference walks the ellipse's whole bounding box (mipmap.rs:281-296) and adds the texels with
+  // r2 < 1 in row-major order.  As written it picks the level from the UNCLAMPED minor axis
+  // (mipmap.rs:335), so at grazing angles the box holds 10^6 .. 10^8 texels.  Texels outside the
+  // ellipse add nothing, so each row is cut to the interval where r2 < 1 can hold: the roots of
+  // a ss^2 + (b tt) ss + (c tt^2 - 1) = 0, evaluated in double and widened by two texels plus 1e-5 of
+  // their magnitude — far more than the band in which float rounding of r2 can flip the comparison
+  // (|r2 - 1| < ~1e-6 spans |ss| * 1e-6 texels).  The exact float test still decides every texel
+  // inside the interval, so the accepted set, the order and hence the sums are unchanged bit for bit;
+  // the work drops from the box to the ellipse (a rotated 8:1 ellipse fills ~1/6 of its box).
+  const bool cut = a > 0.0f && a < PB_F32_MAX && b == b && c == c && fabsf(b) < PB_F32_MAX && fabsf(c) < PB_F32_MAX;
   for (long long it = t0; it <= (long long)t1; ++it) {
     const float tt = (float)(int)it - t;
-    for (long long is = s0; is <= (long long)s1; ++is) {
+    long long is0 = s0, is1 = s1;
+    if (cut) {
+      const double bt = (double)b * (double)tt, ct = (double)c * (double)tt * (double)tt - 1.0;
+      const double disc = bt * bt - 4.0 * (double)a * ct;
+      if (disc < -1e-9 * (bt * bt + 4.0 * fabs((double)a * ct))) continue;  // the row misses the ellipse
+      const double half = sqrt(disc > 0.0 ? disc : 0.0) / (2.0 * (double)a), mid = -bt / (2.0 * (double)a);
+      const double lo = (double)s + mid - half, hi = (double)s + mid + half;
+      const double m = 2.0 + 1e-5 * (fabs(lo) + fabs(hi) + fabs((double)s));
+      const double lo2 = floor(lo - m), hi2 = ceil(hi + m);
+      if (lo2 > (double)is0) is0 = lo2 < 9.2e18 ? (long long)lo2 : is1 + 1;
+      if (hi2 < (double)is1) is1 = hi2 > -9.2e18 ? (long long)hi2 : is0 - 1;
+    }
+    for (long long is = is0; is <= is1; ++is) {
       const float ss = (float)(int)is - s;
       const float r2 = a * ss * ss + b * ss * tt + c * tt * tt;
       if (r2 < 1.0f) {
