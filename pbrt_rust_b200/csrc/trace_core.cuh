@@ -210,6 +210,7 @@ struct TStack {
 // in the same order):
 //   0  if-if        : each iteration a lane does one node step OR one leaf        (best for any-hit)
 //   1  while-while  : lanes run node steps until every lane of the warp holds a leaf (best closest)
+//   4 (ANY only)    : unordered, with postponed leaves (see below)
 //   2, 3 (ANY only) : shapes 0 / 1 without the near/far child ordering.  An any-hit query is a
 //                     boolean over the set of leaves whose boxes pass; no accepted hit shrinks maxt
 //                     before it returns, so that set does not depend on the visiting order and the
@@ -349,6 +350,29 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, floa
            sc.root_bmax[2], &T0root))
     return res;
   uint32_t cur = sc.root_ref;
+  if (ANY && MODE == 4) {
+    // Postponed leaves (any-hit only: the answer does not depend on the visiting order).  A lane that
+    // reaches a leaf PARKS it and goes on with its stack; it only stops when it reaches a second leaf
+    // or runs out of nodes.  The warp therefore tests triangles when every lane holds a parked leaf
+    // (or is finished) instead of whenever any single lane does: in the lock-step model of
+    // scripts/simt_cost.py the leaf rounds of a config-3 shadow packet drop from 4.7 to 2.8 and run
+    // with 14 instead of 8 lanes.
+    constexpr uint32_t NONE = PB_DONE;
+    uint32_t pend = NONE;
+    for (;;) {
+      for (;;) {
+        while (!(cur & PB_LEAF_BIT)) cur = node_step(cur);
+        if (cur >= PB_DONE_OVF || pend != NONE) break;
+        pend = cur;
+        cur = pop();
+      }
+      if (pend == NONE) break;
+      if (leaf(pend)) return res;
+      pend = NONE;
+    }
+    if (cur == PB_DONE_OVF) res.prim = PB_OVERFLOW;
+    return res;
+  }
   if (SHAPE == 0) {
     while (cur < PB_DONE_OVF) {
       if (!(cur & PB_LEAF_BIT)) {

@@ -6,7 +6,7 @@ from collections import Counter, defaultdict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 GP = os.path.join(ROOT, "gpurun_out")
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 os.makedirs(OUT, exist_ok=True)
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -81,31 +81,35 @@ for j in ("bench.json", "bench_ref.json"):
         import shutil
         shutil.copy(os.path.join(GP, j), os.path.join(OUT, f"{TAG}_{j}"))
 
-# traffic for bench.py's roofline.traffic: DRAM bytes of the closest-hit kernel per frame
+# counters for bench.py's roofline: warp instructions per ray and DRAM bytes per launch of the two traversal
+# kernels, from the ncu --set full capture of the SAME command (scripts/gpu_profile.sh)
 try:
     b = json.load(open(os.path.join(GP, "bench.json")))
-    launches_per_frame = max(1, round((b["gpu_launches"] / b["steps"] - 1) / 4))  # closest-hit launches = chunks per frame
-    for k, ds in summary.items():
-        if "k_trace<(bool)0" in k or "k_trace<0" in k:
-            def tob(s, u):
-                return float(s)
-            rep = os.path.join(GP, "prof_k_trace.ncu-rep")
-            hdr, units, rows = raw(rep)
-            ci = {h: i for i, h in enumerate(hdr)}
-            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            tot = 0.0
-            for r in rows:
-                if r[ci["Kernel Name"]] != k:
-                    continue
-                for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    tot += float(r[ci[m]]) * scale[units[ci[m]]]
-                break
-            json.dump({"k_trace_closest_bytes_per_launch": tot,
-                       "k_trace_closest_bytes_per_frame": tot * launches_per_frame,
-                       "source": f"profiles/{TAG}_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum)"},
-                      open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+    n_cam = 1921 * 1081 * 16                       # config 3: sampler extent x 16 spp
+    n_sh = b["config"]["rays_per_frame"] - n_cam
+    hdr, units, rows = raw(os.path.join(GP, "prof_k_trace.ncu-rep"))
+    ci = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = {"source": f"profiles/{TAG}_ncu_full.md (ncu --set full --clock-control none of scripts/prof_frame.py, one launch each)"}
+    for r in rows:
+        k = r[ci["Kernel Name"]]
+        anyhit = "k_trace<(bool)1" in k or "k_trace<1" in k
+        inst = float(r[ci["smsp__inst_executed.sum"]].replace(",", ""))
+        dram = sum(float(r[ci[m]].replace(",", "")) * scale[units[ci[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        key = "any" if anyhit else "closest"
+        out[f"{key}_warp_inst_per_ray"] = inst / (n_sh if anyhit else n_cam)
+        out[f"{key}_warp_inst_per_launch"] = inst
+        out[f"{key}_dram_bytes_per_launch"] = dram
+        out[f"{key}_kernel"] = k
+        out[f"{key}_issue_active_pct"] = float(r[ci["sm__issue_active.avg.pct_of_peak_sustained_elapsed"]])
+        out[f"{key}_l1tex_data_pipe_pct"] = float(r[ci["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"]])
+        out[f"{key}_lanes_per_inst"] = float(r[ci["smsp__thread_inst_executed_per_inst_executed.ratio"]])
+    cpath = os.path.join(OUT, f"{TAG}_counters.json")
+    allc = json.load(open(cpath)) if os.path.exists(cpath) else {}
+    allc["c3"] = out
+    json.dump(allc, open(cpath, "w"), indent=1)
 except Exception as e:
-    print("traffic:", e)
+    print("counters:", e)
 
 # SASS listings
 sass_dir = os.path.join(OUT, "sass")
@@ -120,12 +124,16 @@ keep = {"k_raygen_groups": "k_raygen_groups", "k_raygen_full": "k_raygen_full",
         "k_halton_binILi0": "k_halton_bin_count", "k_halton_binILi1": "k_halton_bin_scatter",
         "k_halton_samples": "k_halton_samples",
         "_Z6k_film5DFilm": "k_film", "k_film_develop": "k_film_develop", "k_area_tri_setup": "k_area_tri_setup", "k_scatter_raster": "k_scatter_raster",
-        "_Z7k_traceILb0ELb0ELb1ELi1ELi1EE": "k_trace_closest_tri_multi_camera_whilewhile",
-        "_Z7k_traceILb1ELb0ELb1ELi0ELi2EE": "k_trace_any_tri_multi_queue_ifif_unordered",
-        "_Z7k_traceILb1ELb0ELb0ELi0ELi2EE": "k_trace_any_tri_single_queue_ifif_unordered",
-        "_Z7k_traceILb0ELb0ELb0ELi1ELi1EE": "k_trace_closest_tri_single_camera_whilewhile",
-        "_Z7k_traceILb0ELb1ELb1ELi1ELi1EE": "k_trace_closest_spheres_multi_camera_whilewhile",
-        "_Z7k_traceILb0ELb0ELb0ELi0ELi1EE": "k_trace_closest_tri_single_buffer_whilewhile"}
+        "_Z6k_fold5DFold": "k_fold", "k_cost_probeILb0ELb0": "k_cost_probe_tri_single",
+        "_Z7k_traceILb0ELb0ELb1ELi1ELi1ELi2EE": "k_trace_closest_tri_multi_camera_box2",
+        "_Z7k_traceILb1ELb0ELb1ELi0ELi2ELi2EE": "k_trace_any_tri_multi_queue_box2",
+        "_Z7k_traceILb1ELb0ELb0ELi0ELi2ELi2EE": "k_trace_any_tri_single_queue_box2",
+        "_Z7k_traceILb0ELb0ELb0ELi1ELi1ELi2EE": "k_trace_closest_tri_single_camera_box2",
+        "_Z7k_traceILb0ELb1ELb1ELi1ELi1ELi2EE": "k_trace_closest_spheres_multi_camera_box2",
+        "_Z7k_traceILb0ELb0ELb0ELi0ELi1ELi2EE": "k_trace_closest_tri_single_buffer_box2",
+        "_Z7k_traceILb0ELb0ELb0ELi1ELi1ELi3EE": "k_trace_closest_tri_single_camera_box3_ffma",
+        "_Z7k_traceILb1ELb0ELb0ELi0ELi2ELi3EE": "k_trace_any_tri_single_queue_box3_ffma",
+        "_Z7k_traceILb0ELb0ELb0ELi1ELi1ELi1EE": "k_trace_closest_tri_single_camera_box1"}
 index = []
 for p in parts[1:]:
     fn = p.split("\n", 1)[0].strip()

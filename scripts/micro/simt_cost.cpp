@@ -336,5 +336,128 @@ void simt_bottom_up(void* tree, const float* rays8, const uint32_t* from_prim, u
   c4[2] = loads;
   c4[3] = fallback;
 }
+// Any-hit with POSTPONED leaves: a lane that reaches a leaf parks it (`slots` pending leaves per lane)
+// and goes on with its stack; the warp runs a leaf round when `threshold` lanes hold a parked leaf, when
+// a lane must park a leaf and has no free slot, or when no lane has node work left.  Order-free, hence
+// legal for any-hit queries.  c: node_rounds, node_lanes, leaf_rounds, leaf_lanes, packets, rays, extra
+// node steps done by lanes whose parked leaf turned out to be a hit.
+void simt_postponed(void* tree, const float* rays8, uint64_t n, int threshold, int slots, uint8_t* occ_out, double* c8) {
+  Tree& T = *static_cast<Tree*>(tree);
+  const DScene& sc = T.sc;
+  double node_rounds = 0, node_lanes = 0, leaf_rounds = 0, leaf_lanes = 0, packets = 0, nrays = 0, wasted = 0, tri = 0;
+  struct PL {
+    Lane L;
+    std::vector<uint32_t> st;
+    uint32_t pend[4];
+    int np;
+    bool occ, done;
+    uint32_t cur;
+  };
+  std::vector<PL> W(32);
+  for (uint64_t base = 0; base < n; base += 32) {
+    const int nl = (int)std::min<uint64_t>(32, n - base);
+    for (int l = 0; l < nl; ++l) {
+      PL& P = W[l];
+      const float* r = rays8 + 8 * (base + l);
+      P.L.o = mk3(r[0], r[1], r[2]);
+      P.L.d = mk3(r[4], r[5], r[6]);
+      P.L.mint = r[3];
+      P.L.maxt = r[7];
+      P.L.rb.inv = mk3(1.f / P.L.d.x, 1.f / P.L.d.y, 1.f / P.L.d.z);
+      P.st.clear();
+      P.np = 0;
+      P.occ = false;
+      float T0;
+      P.done = !box_exact(P.L, sc.root_bmin[0], sc.root_bmin[1], sc.root_bmin[2], sc.root_bmax[0], sc.root_bmax[1], sc.root_bmax[2], &T0);
+      P.cur = P.done ? PB_DONE : sc.root_ref;
+    }
+    packets += 1;
+    nrays += nl;
+    auto popn = [&](PL& P) {
+      if (P.st.empty()) return (uint32_t)PB_DONE;
+      uint32_t r = P.st.back();
+      P.st.pop_back();
+      return r;
+    };
+    for (;;) {
+      // node phase: every lane with an inner node does one step; a lane holding a leaf parks it
+      int kn = 0, parked = 0, must_flush = 0, any_work = 0;
+      for (int l = 0; l < nl; ++l) {
+        PL& P = W[l];
+        if (P.occ) continue;
+        if (P.cur != PB_DONE && (P.cur & PB_LEAF_BIT)) {
+          if (P.np < slots) {
+            P.pend[P.np++] = P.cur;
+            P.cur = popn(P);
+          } else {
+            must_flush = 1;
+          }
+        }
+      }
+      for (int l = 0; l < nl; ++l) {
+        PL& P = W[l];
+        if (P.occ || P.cur == PB_DONE || (P.cur & PB_LEAF_BIT)) continue;
+        const pbh::F4* q = &T.pn.pairs[4ull * P.cur];
+        float T00, T01;
+        const bool h0 = box_exact(P.L, q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, &T00);
+        const bool h1 = box_exact(P.L, q[1].z, q[1].w, q[2].x, q[2].y, q[2].z, q[2].w, &T01);
+        uint32_t r0, r1;
+        std::memcpy(&r0, &q[3].x, 4);
+        std::memcpy(&r1, &q[3].y, 4);
+        if (h0 && h1) {
+          P.st.push_back(r1);
+          P.cur = r0;
+        } else if (h0)
+          P.cur = r0;
+        else if (h1)
+          P.cur = r1;
+        else
+          P.cur = popn(P);
+        ++kn;
+      }
+      if (kn) {
+        node_rounds += 1;
+        node_lanes += kn;
+      }
+      for (int l = 0; l < nl; ++l) {
+        PL& P = W[l];
+        if (P.occ) continue;
+        if (P.np) ++parked;
+        if (P.cur != PB_DONE && !(P.cur & PB_LEAF_BIT)) any_work = 1;
+        if (P.cur != PB_DONE && (P.cur & PB_LEAF_BIT) && P.np < slots) any_work = 1;  // can still park
+      }
+      if (parked && (must_flush || parked >= threshold || !any_work)) {
+        int k = 0;
+        for (int l = 0; l < nl; ++l) {
+          PL& P = W[l];
+          if (P.occ || !P.np) continue;
+          ++k;
+          // one leaf round tests ONE parked leaf per lane (the code path is one triangle test)
+          const uint32_t ref = P.pend[--P.np];
+          const uint32_t off = ref & PB_LEAF_OFF_MASK, cnt = ((ref >> PB_LEAF_CNT_SHIFT) & 0xFu) + 1u;
+          for (uint32_t i = 0; i < cnt && !P.occ; ++i) {
+            const float4* tp = sc.tris + 3ull * (off + i);
+            float t, b1, b2;
+            tri += 1;
+            if (tri_hit(mk3(tp[0].x, tp[0].y, tp[0].z), mk3(tp[1].x, tp[1].y, tp[1].z), mk3(tp[2].x, tp[2].y, tp[2].z), P.L.o,
+                        P.L.d, P.L.mint, P.L.maxt, &t, &b1, &b2))
+              P.occ = true;
+          }
+        }
+        leaf_rounds += 1;
+        leaf_lanes += k;
+      }
+      bool alive = false;
+      for (int l = 0; l < nl; ++l) {
+        PL& P = W[l];
+        if (!P.occ && (P.cur != PB_DONE || P.np)) alive = true;
+      }
+      if (!alive) break;
+    }
+    for (int l = 0; l < nl; ++l)
+      if (occ_out) occ_out[base + l] = W[l].occ ? 1 : 0;
+  }
+  c8[0] = node_rounds; c8[1] = node_lanes; c8[2] = leaf_rounds; c8[3] = leaf_lanes; c8[4] = packets; c8[5] = nrays; c8[6] = wasted; c8[7] = tri;
+}
 void simt_free(void* t) { delete static_cast<Tree*>(t); }
 }

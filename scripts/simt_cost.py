@@ -28,6 +28,7 @@ def lib():
     L.simt_tree.argtypes = [C.c_void_p]
     L.simt_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.simt_bottom_up.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.simt_postponed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -109,6 +110,15 @@ def main():
     print(f"  shadow warps with one octant: {(w.min(1) == w.max(1)).mean():.3f};  x uniform "
           f"{((inv[:(m // 32) * 32, 0] < 0).reshape(-1, 32).std(1) == 0).mean():.3f}, z uniform "
           f"{((inv[:(m // 32) * 32, 2] < 0).reshape(-1, 32).std(1) == 0).mean():.3f}")
+    for slots in (1, 2):
+        for thr in (8, 16, 24, 32):
+            c8 = np.zeros(8)
+            occ2 = np.zeros(m, np.uint8)
+            L.simt_postponed(tree, _p(sh), m, thr, slots, _p(occ2), _p(c8))
+            pk = c8[4]
+            print(f"any-hit postponed leaves (slots {slots}, vote threshold {thr}): per packet: node rounds {c8[0] / pk:.1f} (lanes "
+                  f"{c8[1] / max(1, c8[0]):.1f}), leaf rounds {c8[2] / pk:.1f} (lanes {c8[3] / max(1, c8[2]):.1f}), tri tests per ray "
+                  f"{c8[7] / c8[5]:.2f}; same answers: {np.array_equal(occ2.astype(bool), occ_td)}")
     c4 = np.zeros(4)
     occ = np.zeros(m, np.uint8)
     fp = np.ascontiguousarray(prim[hit])

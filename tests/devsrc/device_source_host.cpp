@@ -322,7 +322,7 @@ void devsrc_force_mixed_axes(int mask) { pb_host_force_mixed = mask; }
 // Scene::intersect / intersect_p for n rays (ray8 = o, mint, d, maxt) through the device traversal source,
 // with the pair nodes packed by the product's own build_pair_nodes and the kernel variant the library
 // would launch.  any_mode: -1 closest hit (hit4 = prim, t, b1, b2 per ray), else the any-hit SIMT mode
-// 0..3 (hit4[0] = prim or MISS).  Returns 0, or -1 with a bad scene / -2 on a stack overflow.
+// 0..4 (hit4[0] = prim or MISS).  Returns 0, or -1 with a bad scene / -2 on a stack overflow.
 int devsrc_trace(const pbrtb200_scene* s, const float* rays8, unsigned long long n, int any_mode, float* hit4) {
   pbh::PairNodes pn;
   DScene sc{};
@@ -343,7 +343,8 @@ int devsrc_trace(const pbrtb200_scene* s, const float* rays8, unsigned long long
       case 0: PB_T(true, 0); break;
       case 1: PB_T(true, 1); break;
       case 2: PB_T(true, 2); break;
-      default: PB_T(true, 3); break;
+      case 3: PB_T(true, 3); break;
+      default: PB_T(true, 4); break;
     }
 #undef PB_T
     if (t.prim == PB_OVERFLOW) rc = -2;

@@ -682,7 +682,7 @@ def test_device_traversal_matches_the_oracle(dev, orc, kind, box, mixed):
     paths) run on the CPU over the host mirror's flattened scene with the product's own pair-node
     packing, against BVHAccelerator::intersect / intersect_p of the oracle: hit ids, t and the
     barycentrics bit for bit (phi of quadrics within the libm-free tolerance 0 here: same libm), the
-    occlusion bit for all four any-hit loop shapes, ordered and unordered.  `box` = the box-test family
+    occlusion bit for all five any-hit loop shapes (ordered, unordered, postponed leaves).  `box` = the box-test family
     (trace_core.cuh child_box): exact min / max, exact per octant, and conservative FFMA inner tests with
     the reference's exact test applied in the leaf phase — all three must give the same bits.  `mixed`
     forces the per-axis "the warp mixes signs" form of the specialised tests (a single emulated lane
@@ -725,7 +725,7 @@ def test_device_traversal_matches_the_oracle(dev, orc, kind, box, mixed):
         assert np.array_equal(got[ok, 1].view(np.uint32), tbb[ok, 0].view(np.uint32))
         assert np.array_equal(got[ok, 2:4].view(np.uint32), tbb[ok, 1:3].view(np.uint32))
         occ, _ = osc.trace_any(rays)
-        for mode in range(4):
+        for mode in range(5):
             g = np.zeros((rays.shape[0], 4), np.float32)
             assert dev.devsrc_trace(C.byref(f), _p(rays), rays.shape[0], mode, _p(g)) == 0
             assert np.array_equal((g[:, 0].copy().view(np.uint32) != 0xFFFFFFFF).astype(np.uint8), occ), mode
