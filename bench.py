@@ -300,7 +300,7 @@ def main():
     while clk.proc and not clk.rows and time.perf_counter() - t_wait < 3.0:
         time.sleep(0.02)  # nvidia-smi needs a moment before its first sample
     # warm-up frames also let the group settle its row bands on measured device times
-    ms, rays_per_frame, acc = timed(True, args.steps, max(args.warmup, 12) if world > 1 else args.warmup)
+    ms, rays_per_frame, acc = timed(True, args.steps, max(args.warmup, 16) if world > 1 else args.warmup)
     clocks = clk.stop()
     bands = r.ctx.bands() if world > 1 else None
     ms_e2e, rays_e2e, acc_e = timed(False, args.steps, 2)

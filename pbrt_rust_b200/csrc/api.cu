@@ -293,9 +293,31 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
 
   const int32_t ext[4] = {smp->x_start, smp->x_end, smp->y_start, smp->y_end};
   const int sw = ext[1] - ext[0], sh = ext[3] - ext[2];
-  const size_t n_ext = (size_t)sw * (size_t)sh;
-  std::vector<uint16_t> task_of(n_ext, 0xFFFF);
-  std::vector<uint32_t> k_of(n_ext, 0);
+  // Only the sampler rows this call can need are touched (row index relative to ext[2]): a row band of
+  // a multi-GPU frame costs its share of the list build, not the whole frame's.  (A HaltonSampler bins
+  // candidates that land anywhere: it keeps every row.)
+  int r0 = 0, r1 = sh;
+  auto rect_rows = [&](const int32_t* q, int* qy0, int* qy1) {
+    *qy0 = std::max((int)std::ceil(((float)q[1] - 0.5f) - yw) - 1, ext[2]);
+    *qy1 = std::min((int)std::floor(((float)(q[3] - 1) + 0.5f) + yw) + 1, ext[3] - 1);
+  };
+  if (!whole && smp->kind != PBRTB200_SAMPLER_HALTON) {
+    r0 = sh;
+    r1 = 0;
+    for (size_t r = 0; r < rects.size() / 4; ++r) {
+      int qy0, qy1;
+      rect_rows(&rects[4 * r], &qy0, &qy1);
+      r0 = std::min(r0, qy0 - ext[2]);
+      r1 = std::max(r1, qy1 - ext[2] + 1);
+    }
+    r0 = std::max(0, std::min(r0, sh));
+    r1 = std::max(r0, std::min(r1, sh));
+  }
+  const int rows_n = r1 - r0;
+  const size_t n_loc = (size_t)sw * (size_t)rows_n;
+  auto loc = [&](int yy, int xx) { return (size_t)(yy - r0) * (size_t)sw + (size_t)xx; };  // yy, xx relative to the extent
+  std::vector<uint16_t> task_of(n_loc, 0xFFFF);
+  std::vector<uint32_t> k_of(n_loc, 0);
   std::vector<uint32_t> keys(8 * (size_t)smp->num_tasks);
   for (int t = 0; t < smp->num_tasks; ++t) {
     pbh::task_key((uint64_t)t, &keys[8 * (size_t)t]);
@@ -305,28 +327,29 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
     if (w[0] < ext[0] || w[1] > ext[1] || w[2] < ext[2] || w[3] > ext[3] || w[1] < w[0] || w[3] < w[2])
       FAIL(PBRTB200_EINVAL, "task window outside the sampler extent");
     const uint32_t tw = (uint32_t)(w[1] - w[0]);
-    for (int y = w[2]; y < w[3]; ++y)
+    for (int y = std::max(w[2], ext[2] + r0); y < std::min(w[3], ext[2] + r1); ++y)
       for (int x = w[0]; x < w[1]; ++x) {
-        const size_t e = (size_t)(y - ext[2]) * sw + (size_t)(x - ext[0]);
+        const size_t e = loc(y - ext[2], x - ext[0]);
         task_of[e] = (uint16_t)t;
         k_of[e] = (uint32_t)(y - w[2]) * tw + (uint32_t)(x - w[0]);
       }
   }
   // which sampler pixels are needed
-  std::vector<uint8_t> need(n_ext, whole ? 1 : 0);
-  std::vector<uint8_t> owned(whole ? 0 : n_ext, 0);  // sampler pixel lies inside a rect of this call
+  std::vector<uint8_t> need(n_loc, whole ? 1 : 0);
+  std::vector<uint8_t> owned(whole ? 0 : n_loc, 0);  // sampler pixel lies inside a rect of this call
   if (!whole) {
     for (size_t r = 0; r < rects.size() / 4; ++r) {
       const int32_t* q = &rects[4 * r];
-      for (int y = std::max(q[1], ext[2]); y < std::min(q[3], ext[3]); ++y)
+      for (int y = std::max(q[1], ext[2] + r0); y < std::min(q[3], ext[2] + r1); ++y)
         for (int x = std::max(q[0], ext[0]); x < std::min(q[2], ext[1]); ++x)
-          owned[(size_t)(y - ext[2]) * sw + (size_t)(x - ext[0])] = 1;
+          owned[loc(y - ext[2], x - ext[0])] = 1;
       int qx0 = (int)std::ceil(((float)q[0] - 0.5f) - xw) - 1, qx1 = (int)std::floor(((float)(q[2] - 1) + 0.5f) + xw) + 1;
-      int qy0 = (int)std::ceil(((float)q[1] - 0.5f) - yw) - 1, qy1 = (int)std::floor(((float)(q[3] - 1) + 0.5f) + yw) + 1;
+      int qy0, qy1;
+      rect_rows(q, &qy0, &qy1);
       qx0 = std::max(qx0, ext[0]);
       qx1 = std::min(qx1, ext[1] - 1);
-      qy0 = std::max(qy0, ext[2]);
-      qy1 = std::min(qy1, ext[3] - 1);
+      qy0 = std::max(qy0, ext[2] + r0);
+      qy1 = std::min(qy1, ext[2] + r1 - 1);
       // Within that padded range keep exactly the sampler pixels k_film will accept for some pixel
       // of the rect: a sample of pixel p has image coordinate in [p, p + 1], and add_sample's
       // extent arithmetic is monotonic, so it can only reach [ceil((p-0.5)-w), floor((p+0.5)+w)]
@@ -339,19 +362,19 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
       for (int y = qy0; y <= qy1; ++y) {
         if (!reaches(y, yw, q[1], q[3] - 1)) continue;
         for (int x = qx0; x <= qx1; ++x)
-          if (reaches(x, xw, q[0], q[2] - 1)) need[(size_t)(y - ext[2]) * sw + (size_t)(x - ext[0])] = 1;
+          if (reaches(x, xw, q[0], q[2] - 1)) need[loc(y - ext[2], x - ext[0])] = 1;
       }
     }
   }
   std::vector<DPixel> list;
-  list.reserve(n_ext);
-  std::vector<int32_t> index(n_ext, -1);
+  list.reserve(n_loc);
+  std::vector<int32_t> index(n_loc, -1);
   const int TW = 8, TH = 4;
-  for (int ty = 0; ty < sh; ty += TH)
+  for (int ty = (r0 / TH) * TH; ty < r1; ty += TH)
     for (int tx = 0; tx < sw; tx += TW)
-      for (int yy = ty; yy < std::min(ty + TH, sh); ++yy)
+      for (int yy = std::max(ty, r0); yy < std::min(ty + TH, r1); ++yy)
         for (int xx = tx; xx < std::min(tx + TW, sw); ++xx) {
-          const size_t e = (size_t)yy * sw + (size_t)xx;
+          const size_t e = loc(yy, xx);
           if (!need[e] || task_of[e] == 0xFFFF) continue;
           DPixel p;
           const int x = ext[0] + xx, y = ext[2] + yy;
@@ -368,24 +391,31 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
   ctx->rows_ready.assign((size_t)sh, 0u);
   for (int yy = 0; yy < sh; ++yy) {
     uint32_t m = yy ? ctx->rows_ready[(size_t)yy - 1] : 0u;
-    for (int xx = 0; xx < sw; ++xx) {
-      const int32_t li = index[(size_t)yy * sw + (size_t)xx];
-      if (li >= 0) m = std::max(m, (uint32_t)li + 1u);
-    }
+    if (yy >= r0 && yy < r1)
+      for (int xx = 0; xx < sw; ++xx) {
+        const int32_t li = index[loc(yy, xx)];
+        if (li >= 0) m = std::max(m, (uint32_t)li + 1u);
+      }
     ctx->rows_ready[(size_t)yy] = m;
   }
   // row_first[r] = first list pixel still needed once everything above sampler row r is filtered
   ctx->row_first.assign((size_t)sh + 1, (uint32_t)list.size());
   for (int yy = sh - 1; yy >= 0; --yy) {
     uint32_t m = ctx->row_first[(size_t)yy + 1];
-    for (int xx = 0; xx < sw; ++xx) {
-      const int32_t li = index[(size_t)yy * sw + (size_t)xx];
-      if (li >= 0) m = std::min(m, (uint32_t)li);
-    }
+    if (yy >= r0 && yy < r1)
+      for (int xx = 0; xx < sw; ++xx) {
+        const int32_t li = index[loc(yy, xx)];
+        if (li >= 0) m = std::min(m, (uint32_t)li);
+      }
     ctx->row_first[(size_t)yy] = m;
   }
   if (upload(ctx, ctx->d_pixels, list.data(), list.size())) return PBRTB200_ENODEV;
-  if (upload(ctx, ctx->d_pix_index, index.data(), index.size())) return PBRTB200_ENODEV;
+  // the index keeps its full-extent layout on the device (k_film / the Halton binning address it by
+  // sampler row); only the rows of this list are rewritten — no other row is read with this list
+  CK(ctx->d_pix_index.ensure((size_t)sw * (size_t)sh * sizeof(int32_t)));
+  if (n_loc)
+    CK(cudaMemcpyAsync(ctx->d_pix_index.as<int32_t>() + (size_t)r0 * (size_t)sw, index.data(), n_loc * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, ctx->stream));
   if (upload(ctx, ctx->d_task_keys, keys.data(), keys.size())) return PBRTB200_ENODEV;
   std::vector<DHaltonTask> htasks;
   if (smp->kind == PBRTB200_SAMPLER_HALTON) {  // HaltonSampler::new per sub-window (halton.rs:18-29, 36-47)

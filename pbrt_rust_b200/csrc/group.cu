@@ -275,10 +275,10 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
     g->view.yw = film->filter_yw;
     g->view.valid = true;
     g->frames_in_view = 0;
-  } else if (n > 1 && g->frames_in_view < 10 && g->device_ms.size() == (size_t)n) {
+  } else if (n > 1 && g->frames_in_view < 14 && g->device_ms.size() == (size_t)n) {
     // same view again: rescale each band's cost density by the time its device needed last frame
-    // and cut again (damped), until the slowest device is within 3 % of the mean (or 10 frames: every
-    // move rebuilds the devices' pixel lists, tens of milliseconds of host work)
+    // and cut again (damped), until the slowest device is within 3 % of the mean (or 14 frames: every
+    // move rebuilds the devices' pixel lists — milliseconds of host work per device)
     double mean = 0, mx = 0;
     for (float t : g->device_ms) {
       mean += t / n;

@@ -1,16 +1,23 @@
 #!/bin/bash
-# usage: gpu_multi.sh N [N ...]   (on a box with >= max N GPUs): P2P gather check + bench in both gather modes
+# N-GPU validation of pbrtb200_group_render: parity test (film bit-identical to one GPU), then bench at N (torchrun) and N=1.
+N=${1:-2}
 mkdir -p gpurun_out
-for N in "$@"; do
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-timeout 300 $TR scripts/multigpu_check.py 2>&1 | grep -v "^W\|^\*\*\*\|OMP_NUM" | tail -5
-for mode in p2p nccl; do
-  PBRTB200_GATHER=$mode timeout 600 $TR bench.py --gpus $N --steps 20 --warmup 3 --no-cpu 2> gpurun_out/bench_n${N}_$mode.err | tail -1 > gpurun_out/bench_n${N}_$mode.json
-  python - <<PY
+python -m pytest tests/test_gpu_parity.py -q -k "group_render or cost_profile" > gpurun_out/r2_group_tests_n$N.log 2>&1
+tail -5 gpurun_out/r2_group_tests_n$N.log
+for n in 1 2 4 8; do
+  if [ $n -le $N ]; then
+    if [ $n -eq 1 ]; then
+      python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_scale_$n.json 2> gpurun_out/r2_scale_$n.err
+    else
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_scale_$n.json 2> gpurun_out/r2_scale_$n.err
+    fi
+    python - <<PY
 import json
-d=json.load(open("gpurun_out/bench_n${N}_$mode.json"))
-print("N=${N} $mode: ms/frame %.3f  Mrays/s %.0f  e2e %.0f (%.3f ms)  gather=%s" % (d["ms_per_step"], d["value"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["config"]["film_gather"][:40]))
+try:
+    d=json.loads(open('gpurun_out/r2_scale_$n.json').read().strip().splitlines()[-1])
+    print('N=$n value %.0f Mrays/s  ms %.3f | e2e %.0f ms %.3f | bands %s | per-device ms %s' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['config']['band_rows'], d['config']['per_device_ms']))
+except Exception as e:
+    print('N=$n failed', e); print(open('gpurun_out/r2_scale_$n.err').read()[-1500:])
 PY
-  grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/bench_n${N}_$mode.err | tail -3
-done
+  fi
 done

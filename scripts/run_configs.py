@@ -67,7 +67,7 @@ if args.config == "c2":
         stats = dict(r.last_stats)
     times_e2e = times
 else:
-    warm = 6 if N > 1 else 1
+    warm = 15 if N > 1 else 1
     for i in range(args.frames + warm):
         t0 = time.perf_counter()
         r.render(cfg["scene"], out=d_film)

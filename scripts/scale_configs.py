@@ -42,7 +42,7 @@ for config in args.configs:
         r = pb.GpuRenderer(cfg["sampler"], cfg["camera"], cfg["integrator"], num_cpus=8, ctx=ctx)
         d_film = torch.zeros(h * w * 4, dtype=torch.float32, device="cuda:0")
         h_film = torch.zeros(h * w * 4, dtype=torch.float32).pin_memory().numpy().reshape(h, w, 4)
-        warm = 6 if n > 1 else 1
+        warm = 15 if n > 1 else 1
         ts = []
         for i in range(warm + args.frames):
             t0 = time.perf_counter()
