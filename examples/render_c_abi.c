@@ -3,7 +3,9 @@
  * mirror, renders it through the C ABI, develops the film on the device and writes
  *   <out>.png   the 8-bit image `Film::write_image` would leave behind
  *   <out>.film  the raw film (float4 per pixel: sum w*XYZ, sum w), for the parity test
- * usage: render_c_abi <xres> <yres> <out-prefix>
+ * usage: render_c_abi <xres> <yres> <out-prefix> [--gpus N]
+ * With --gpus N (N > 1) the frame goes through pbrtb200_group_render: one call in, the finished film
+ * out, row bands over N devices inside the library (same film, bit for bit).
  * This is the call sequence a `GpuRenderer: Renderer` inside the Rust crate makes. */
 #include <stdio.h>
 #include <stdlib.h>
@@ -16,7 +18,8 @@
   do {                                                                         \
     int rc_ = (call);                                                          \
     if (rc_ < 0) {                                                             \
-      fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, pbrtb200_last_error(ctx)); \
+      fprintf(stderr, "%s failed (%d): %s\n", #call, rc_,                      \
+              grp ? pbrtb200_group_last_error(grp) : pbrtb200_last_error(ctx));  \
       return 1;                                                                \
     }                                                                          \
   } while (0)
@@ -24,7 +27,11 @@
 int main(int argc, char** argv) {
   const int xres = argc > 1 ? atoi(argv[1]) : 160, yres = argc > 2 ? atoi(argv[2]) : 120;
   const char* prefix = argc > 3 ? argv[3] : "frame";
+  int n_gpus = 1;
+  for (int i = 4; i + 1 < argc; ++i)
+    if (strcmp(argv[i], "--gpus") == 0) n_gpus = atoi(argv[i + 1]);
   pbrtb200_ctx* ctx = NULL;
+  pbrtb200_group* grp = NULL;
 
   /* scene: Primitive::bvh(8 x Primitive::geometric(Shape::sphere(translate(v), ..), matte), 1, "sah") */
   pbh_scene* hs = pbh_scene_new();
@@ -76,16 +83,28 @@ int main(int argc, char** argv) {
   integ.max_depth = 1;
 
   /* the back end */
-  CHECK(pbrtb200_create(0, &ctx));
-  CHECK(pbrtb200_upload_scene(ctx, pbh_flat_scene(hs)));
+  if (n_gpus > 1) { /* devices 0 .. N-1, one context and host thread each, scene replicated */
+    if (pbrtb200_group_create(NULL, n_gpus, &grp) < 0) {
+      fprintf(stderr, "pbrtb200_group_create: %s\n", pbrtb200_group_last_error(NULL));
+      return 1;
+    }
+    CHECK(pbrtb200_group_upload_scene(grp, pbh_flat_scene(hs)));
+    ctx = pbrtb200_group_ctx(grp, 0); /* borrowed: film_develop below runs on the first device */
+  } else {
+    CHECK(pbrtb200_create(0, &ctx));
+    CHECK(pbrtb200_upload_scene(ctx, pbh_flat_scene(hs)));
+  }
   const size_t npx = (size_t)film.x_pixel_count * (size_t)film.y_pixel_count;
   float* xyzw = (float*)malloc(npx * 4 * sizeof(float));
   uint8_t* rgb8 = (uint8_t*)malloc(npx * 3);
   pbrtb200_stats st;
-  CHECK(pbrtb200_render(ctx, &cam, &smp, &film, &integ, NULL, xyzw, 0, &st));
+  if (grp)
+    CHECK(pbrtb200_group_render(grp, &cam, &smp, &film, &integ, xyzw, 0, &st));
+  else
+    CHECK(pbrtb200_render(ctx, &cam, &smp, &film, &integ, NULL, xyzw, 0, &st));
   CHECK(pbrtb200_film_develop(ctx, xyzw, 0, npx, NULL, rgb8, 0));
-  printf("render_c_abi: %dx%d, %llu camera rays, %llu shadow rays, %u kernel launches, %.3f ms on the device\n",
-         film.x_pixel_count, film.y_pixel_count, (unsigned long long)st.camera_rays,
+  printf("render_c_abi: %d GPU(s), %dx%d, %llu camera rays, %llu shadow rays, %u kernel launches, %.3f ms on the device\n",
+         n_gpus, film.x_pixel_count, film.y_pixel_count, (unsigned long long)st.camera_rays,
          (unsigned long long)st.shadow_rays, st.kernel_launches, st.ms_total);
 
   char path[1024];
@@ -97,7 +116,10 @@ int main(int argc, char** argv) {
   fclose(f);
   free(xyzw);
   free(rgb8);
-  pbrtb200_destroy(ctx);
+  if (grp)
+    pbrtb200_group_destroy(grp);
+  else
+    pbrtb200_destroy(ctx);
   pbh_scene_free(hs);
   return 0;
 }

@@ -70,7 +70,7 @@ struct pbrtb200_group {
   std::vector<int> bounds;        // n + 1 film rows
   std::vector<double> row_cost;   // per film row: cost density estimate (probe, then measured)
   std::vector<float> device_ms;
-  int frames_in_view = 0;
+  int frames_in_view = 0, moves_in_view = 0, over_streak = 0;
   bool peers_enabled = false;
   // pinned registration of the caller's host film
   void* reg_ptr = nullptr;
@@ -275,16 +275,22 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
     g->view.yw = film->filter_yw;
     g->view.valid = true;
     g->frames_in_view = 0;
-  } else if (n > 1 && g->frames_in_view < 14 && g->device_ms.size() == (size_t)n) {
-    // same view again: rescale each band's cost density by the time its device needed last frame
-    // and cut again (damped), until the slowest device is within 3 % of the mean (or 14 frames: every
-    // move rebuilds the devices' pixel lists — milliseconds of host work per device)
+    g->moves_in_view = 0;
+    g->over_streak = 0;
+  } else if (n > 1 && g->moves_in_view < 20 && g->device_ms.size() == (size_t)n) {
+    // same view again: rescale each band's cost density by the time its device needed last frame and
+    // cut again (damped) while the slowest device is more than 3 % above the mean.  Every move rebuilds
+    // the devices' pixel lists (milliseconds of host work per device), so: at most 20 moves per view,
+    // and after the first 8 frames only when two frames in a row say so (a single frame's device
+    // times carry ~2 % of noise).
     double mean = 0, mx = 0;
     for (float t : g->device_ms) {
       mean += t / n;
       mx = std::max<double>(mx, t);
     }
-    if (mean > 0 && mx > 1.03 * mean) {
+    const bool over = mean > 0 && mx > 1.03 * mean;
+    g->over_streak = over ? g->over_streak + 1 : 0;
+    if (over && (g->frames_in_view < 8 || g->over_streak >= 2)) {
       double total_cost = 0;
       for (double c : g->row_cost) total_cost += c;
       for (int k = 0; k < n; ++k) {
@@ -297,7 +303,10 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
         const double scale = std::pow(measured / predicted, 0.8);
         for (int y = a; y < b; ++y) g->row_cost[(size_t)y] *= scale;
       }
+      const std::vector<int> before = g->bounds;
       cut_bands(g->row_cost, y0, n, quantum, &g->bounds);
+      if (g->bounds != before) ++g->moves_in_view;
+      g->over_streak = 0;
     }
   }
   ++g->frames_in_view;

@@ -1,11 +1,14 @@
-"""Diagnostic: per-device stats of pbrtb200_group_render over a few frames of config 3 (GPU box)."""
+"""Diagnostic: per-device stats of pbrtb200_group_render over a few frames (GPU box).
+usage: python scripts/group_probe.py [n_gpus] [config] [frames]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pbrt_rust_b200 as pb
 import bench
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-cfg = bench.make_cfg()
+config = sys.argv[2] if len(sys.argv) > 2 else "c3"
+frames = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+cfg = bench.make_cfg(config)
 grp = pb.Group(list(range(n)))
 r = pb.GpuRenderer(cfg["sampler"], cfg["camera"], cfg["integrator"], num_cpus=8, ctx=grp)
 r.preprocess(cfg["scene"])
@@ -13,7 +16,7 @@ h, w = cfg["film"].shape
 host = torch.zeros(h * w * 4, dtype=torch.float32).pin_memory().numpy().reshape(h, w, 4)
 dev = torch.zeros(h * w * 4, dtype=torch.float32, device="cuda:0")
 for mode, out in (("host", host), ("device", dev)):
-    for f in range(10):
+    for f in range(frames):
         t0 = time.perf_counter(); r.render(cfg["scene"], out=out); dt = (time.perf_counter() - t0) * 1e3
         b, ms = grp.bands()
         ds = grp.device_stats()

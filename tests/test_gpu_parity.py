@@ -957,3 +957,12 @@ def test_c_abi_from_plain_c(orc, tmp_path):
     assert np.array_equal(read_png_rgb8(prefix + ".png"), r.develop(film_py))
     ref = orc.render(orc.OracleScene(cfg["scene"]), orc.render_config(cfg["camera"], cfg["sampler"], num_cpus=8, mode=0))
     assert float(np.sqrt(np.mean((pb.film_to_rgb(film_c) - ref["rgb"]) ** 2))) <= 1e-5
+    # the same program over every GPU of the box (pbrtb200_group_render): same film, bit for bit
+    import torch
+    n_dev = torch.cuda.device_count()
+    if n_dev >= 2:
+        out = subprocess.run([exe, "160", "120", prefix + "_g", "--gpus", str(n_dev)], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        assert f"{n_dev} GPU(s)" in out.stdout
+        film_g = np.fromfile(prefix + "_g.film", np.float32).reshape(120, 160, 4)
+        assert np.array_equal(film_g.view(np.uint32), film_c.view(np.uint32))
