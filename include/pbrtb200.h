@@ -284,7 +284,10 @@ int pbrtb200_upload_scene(pbrtb200_ctx* ctx, const pbrtb200_scene* scene);
 
 /* Renderer::render.  out_xyzw: 4 floats per film pixel (x_pixel_count*y_pixel_count, row-major):
  * sum(w*X), sum(w*Y), sum(w*Z), sum(w) — the contents of Film::Image.pixels (film.rs:35-41).
- * `out_is_device` != 0: out_xyzw is a device pointer on the ctx's device (no D2H copy).        */
+ * `out_is_device` != 0: out_xyzw is a device pointer on the ctx's device (no D2H copy).
+ * `out_is_device` == 0: a host buffer.  Pageable memory is filled by a copy from a staging film in
+ * HBM; a page-locked, mapped buffer (cudaHostAlloc, cudaHostRegister(.., cudaHostRegisterMapped))
+ * is written by the film kernel directly, which is faster (the transfer overlaps the kernels).   */
 int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb200_sampler* smp,
                     const pbrtb200_film* film, const pbrtb200_integrator* integ,
                     const pbrtb200_tileset* tiles, float* out_xyzw, int out_is_device,
@@ -322,8 +325,9 @@ int pbrtb200_peer_film_close(pbrtb200_ctx* ctx, void* dev_ptr);
  * row bands of equal COST (first frame of a view: pbrtb200_cost_profile; later frames of the same
  * view: the bands follow each device's measured time), every device renders its band with
  * pbrtb200_render's own pipeline and
- *   - out_is_device == 0: copies ITS OWN rows straight into the caller's host film over its own PCIe
- *     link (N links in parallel, no gather, no collective);
+ *   - out_is_device == 0: sends ITS OWN rows straight into the caller's host film over its own PCIe
+ *     link (N links in parallel, no gather, no collective; the group page-locks and maps the buffer
+ *     once, so the film kernels store into it directly);
  *   - out_is_device != 0: out_xyzw is a buffer on the group's FIRST device; the other devices' film
  *     kernels store their rows into it over NVLink (peer access).
  * Every film pixel is produced by exactly one device with the summation order of a single-GPU

@@ -1281,11 +1281,33 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   }
   const size_t film_px = (size_t)film->x_pixel_count * (size_t)film->y_pixel_count;
   float4* d_film = nullptr;
+  // Host film that is page-locked and mapped (cudaHostAlloc, or cudaHostRegister with the Mapped flag
+  // as pbrtb200_group_render does for its caller): k_film stores the pixels it owns straight into it
+  // over PCIe — the transfer rides under the film kernels (and, for frames of several chunks, under the
+  // later chunks) instead of following them as a copy.  Measured on config 3: e2e 8.47 -> 8.35 ms on one
+  // GPU, 1.52 -> 1.43 ms on eight.  Pageable buffers, and tile sets that zero the rest of the film, keep
+  // the staged copy.  PBRTB200_HOST_FILM_STORES=0 turns it off, =1 limits it to KEEP_OTHERS tile sets.
+  static const int host_stores_on = [] {
+    const char* v = std::getenv("PBRTB200_HOST_FILM_STORES");
+    return v && *v ? std::atoi(v) : 2;
+  }();
+  bool host_stores = false;
   if (out_is_device) {
     d_film = reinterpret_cast<float4*>(out_xyzw);
   } else {
-    CK(ctx->d_film.ensure(film_px * sizeof(float4)));
-    d_film = ctx->d_film.as<float4>();
+    if ((host_stores_on >= 1 && tiles && (tiles->flags & PBRTB200_TILES_KEEP_OTHERS)) || (host_stores_on >= 2 && !tiles)) {
+      void* dp = nullptr;
+      if (cudaHostGetDevicePointer(&dp, out_xyzw, 0) == cudaSuccess && dp) {
+        d_film = reinterpret_cast<float4*>(dp);
+        host_stores = true;
+      }
+      (void)cudaGetLastError();
+    }
+
+    if (!host_stores) {
+      CK(ctx->d_film.ensure(film_px * sizeof(float4)));
+      d_film = ctx->d_film.as<float4>();
+    }
   }
 
   CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
@@ -1323,8 +1345,9 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     const char* v = std::getenv("PBRTB200_FILM_BANDS");
     return v && *v ? std::atoi(v) : 2;
   }();
-  const bool banded = whole_film && !halton && (ring || (band_mode > 0 && !out_is_device));
-  const bool band_copies = banded && !out_is_device;
+  const bool staged = !out_is_device && !host_stores;  // the film is built in HBM and copied out
+  const bool banded = whole_film && !halton && (ring || (band_mode > 0 && staged));
+  const bool band_copies = banded && staged;
   struct Band {
     uint32_t y0, y1;
     size_t event;
@@ -1515,7 +1538,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       if (int rc = film_rows(film_done, std::min(H, film_done + step))) return rc;
   }
   tm.span(eA, tm.mark(), 5);
-  if (!out_is_device) {
+  if (staged) {
     if (band_copies) {
       // every band: wait for its film launch on the copy stream, then move its rows to the host
       for (const Band& b : bands) {

@@ -319,7 +319,7 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
     cudaPointerAttributes at{};
     const bool already = cudaPointerGetAttributes(&at, out_xyzw) == cudaSuccess && at.type == cudaMemoryTypeHost;
     (void)cudaGetLastError();
-    if (!already && cudaHostRegister(out_xyzw, film_bytes, cudaHostRegisterPortable) == cudaSuccess) {
+    if (!already && cudaHostRegister(out_xyzw, film_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
       g->reg_ptr = out_xyzw;
       g->reg_bytes = film_bytes;
     }

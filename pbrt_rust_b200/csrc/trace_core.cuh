@@ -8,6 +8,24 @@
 #include "trace_math.cuh"
 
 PB_DEV float4 ldg4(const float4* p) { return __ldg(p); }
+// Two consecutive float4 (32-byte aligned), optionally in ONE 256-bit load (sm_100: LDG.E.256,
+// -DPB_LDG256=1).  Measured (profiles/r02_notes.md §10): L1 requests and fetched sectors of the
+// closest-hit kernel halve (145 M -> 80 M, 220 M -> 126 M), instructions -2.3 %, but the L1 data pipe
+// stays at 79 % — it is busy delivering the 64 bytes per lane, not taking requests — and the kernel
+// times do not move (2.926 -> 2.919 ms, any-hit 3.051 -> 3.075 ms).  Off by default.
+#ifndef PB_LDG256
+#define PB_LDG256 0
+#endif
+PB_DEV void ldg8(const float4* p, float4* a, float4* b) {
+#if PB_LDG256 && !defined(PB_HOST_CHECK)
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w)
+      : "l"(p));
+#else
+  *a = ldg4(p);
+  *b = ldg4(p + 1);
+#endif
+}
 
 // sphere.rs:46-107 (+ the world->object ray transform of sphere.rs:137)
 PB_DEV bool sphere_hit(const pbrtb200_sphere80* __restrict__ sp, f3 ow, f3 dw, float mint,
@@ -265,7 +283,9 @@ PB_DEV TraceResult traverse(const DScene& sc, f3 o, f3 d, const RayBox& rb, floa
   auto node_step = [&](uint32_t cur) -> uint32_t {
     if (COUNT) ++res.steps;
     const float4* n = sc.nodes + 4ull * cur;
-    const float4 q0 = ldg4(n), q1 = ldg4(n + 1), q2 = ldg4(n + 2), q3 = ldg4(n + 3);
+    float4 q0, q1, q2, q3;
+    ldg8(n, &q0, &q1);
+    ldg8(n + 2, &q2, &q3);
     float T00, T01;
     const bool h0 = box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &T00);
     const bool h1 = box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &T01);

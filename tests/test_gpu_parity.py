@@ -284,6 +284,33 @@ def test_group_render_is_bit_identical_to_one_gpu(orc, n_dev):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+def test_page_locked_host_film_takes_direct_stores(orc):
+    """A page-locked, mapped host film is written by k_film itself (stores over PCIe instead of a
+    staged copy): whole films and a tile set with KEEP_OTHERS give the bytes of the staged path, also
+    when the frame runs in several chunks through the sample ring."""
+    import os
+    cfg = scenes.config3(nx=120, nz=60, xres=200, yres=150, xs=2, ys=2, n_lights=2, light_samples=2)
+    r = _renderer(cfg)
+    want = r.render(cfg["scene"]).copy()            # pageable numpy film: staged copy
+    pinned = torch.zeros(want.size, dtype=torch.float32).pin_memory()
+    host = pinned.numpy().reshape(want.shape)
+    r.render(cfg["scene"], out=host)
+    assert np.array_equal(host.view(np.uint32), want.view(np.uint32))
+    os.environ["PBRTB200_CHUNK_LOG2"] = "12"
+    os.environ["PBRTB200_FRAME_BUDGET_MB"] = "1"
+    try:
+        host[:] = -1.0
+        r.render(cfg["scene"], out=host)
+        assert r.last_stats["kernel_launches"] > 20
+        assert np.array_equal(host.view(np.uint32), want.view(np.uint32))
+    finally:
+        del os.environ["PBRTB200_CHUNK_LOG2"], os.environ["PBRTB200_FRAME_BUDGET_MB"]
+    host[:] = 7.0                                   # a band with KEEP_OTHERS: only its rows change
+    r.render(cfg["scene"], out=host, tiles=[(0, 40, 200, 90)], keep_others=True)
+    assert np.array_equal(host[40:90].view(np.uint32), want[40:90].view(np.uint32))
+    assert (host[:40] == 7.0).all() and (host[90:] == 7.0).all()
+
+
 def test_cost_profile_follows_the_scene(orc):
     """pbrtb200_cost_profile: rows that see geometry cost more than rows that see nothing, and the
     probe rows repeat over their stride."""
