@@ -1296,12 +1296,13 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     d_film = reinterpret_cast<float4*>(out_xyzw);
   } else {
     if ((host_stores_on >= 1 && tiles && (tiles->flags & PBRTB200_TILES_KEEP_OTHERS)) || (host_stores_on >= 2 && !tiles)) {
-      void* dp = nullptr;
-      if (cudaHostGetDevicePointer(&dp, out_xyzw, 0) == cudaSuccess && dp) {
-        d_film = reinterpret_cast<float4*>(dp);
+      cudaPointerAttributes at{};  // (pageable memory: success, type Unregistered — no error to clear)
+      if (cudaPointerGetAttributes(&at, out_xyzw) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+        d_film = reinterpret_cast<float4*>(at.devicePointer);
         host_stores = true;
+      } else {
+        (void)cudaGetLastError();
       }
-      (void)cudaGetLastError();
     }
 
     if (!host_stores) {

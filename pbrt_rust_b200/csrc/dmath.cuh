@@ -91,6 +91,25 @@ inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, int c) {
 #define PB_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #define PB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
+// Streaming accesses: the per-sample wavefront buffers (image samples, hit records, shadow rays, radiance
+// terms: 0.5 - 1 GB each per config-3 frame) are written once and read once, a kernel later.
+// -DPB_STREAM_HINTS=1 marks them evict-first (ld / st .cs).  Measured (profiles/r02_notes.md §12): the L2
+// hit rates and DRAM bytes of the traversal kernels do not move — their DRAM reads ARE the streamed
+// samples / rays, the scene already stays in L2 — and k_shade gets slower (config 3 1.338 -> 1.361 ms,
+// config 5 63 -> 75 ms).  Off.
+#ifndef PB_STREAM_HINTS
+#define PB_STREAM_HINTS 0
+#endif
+#ifdef PB_HOST_CHECK
+template <class T> PB_DEV T ld_stream(const T* p) { return *p; }
+template <class T> PB_DEV void st_stream(T* p, const T& v) { *p = v; }
+#elif PB_STREAM_HINTS
+template <class T> PB_DEV T ld_stream(const T* p) { return __ldcs(p); }
+template <class T> PB_DEV void st_stream(T* p, const T& v) { __stcs(p, v); }
+#else
+template <class T> PB_DEV T ld_stream(const T* p) { return __ldg(p); }
+template <class T> PB_DEV void st_stream(T* p, const T& v) { *p = v; }
+#endif
 #define PB_F32_MAX 3.402823466e+38f
 #define PB_PI 3.14159265358979323846f
 

@@ -67,7 +67,7 @@ PB_DEV void record_xyz(const FilmArgs& a, float4 r, float* X, float* Y, float* Z
 // terms: `slots` float4 per sample, term j = (c_j, j == 0 ? bits(e) : 0).  Returns true if L has a NaN
 // (sampler_renderer.rs:105 intent).
 PB_DEV bool fold_terms(const DFold& fd, const pbrtb200_light* __restrict__ lights, const float4* __restrict__ r, float4* out) {
-  const float4 first = r[0];
+  const float4 first = ld_stream(r);
   f3 L = mk3(0.f, 0.f, 0.f);
   const uint32_t e = __float_as_uint(first.w);
   if (e) L = mk3(lights[e - 1u].intensity[0], lights[e - 1u].intensity[1], lights[e - 1u].intensity[2]);
@@ -77,13 +77,13 @@ PB_DEV bool fold_terms(const DFold& fd, const pbrtb200_light* __restrict__ light
       const uint32_t ns = fd.ns[li];
       f3 Ld = mk3(0.f, 0.f, 0.f);
       for (uint32_t s = 0; s < ns; ++s) {
-        const float4 c = r[slot++];
+        const float4 c = ld_stream(r + slot++);
         Ld = Ld + mk3(c.x, c.y, c.z);
       }
       const float fns = (float)ns;
       L = L + mk3(Ld.x / fns, Ld.y / fns, Ld.z / fns);
     } else {
-      const float4 c = r[slot++];
+      const float4 c = ld_stream(r + slot++);
       L = L + mk3(c.x, c.y, c.z);
     }
   }
@@ -149,8 +149,7 @@ PB_DEV void film_pixel(const DFilm& f, const FilmArgs& a, uint32_t gid) {
       }
     }
   }
-  a.out[(size_t)(y - f.y_start) * (size_t)f.x_count + (size_t)(x - f.x_start)] =
-      make_float4(X, Y, Z, Wt);
+  st_stream(a.out + ((size_t)(y - f.y_start) * (size_t)f.x_count + (size_t)(x - f.x_start)), make_float4(X, Y, Z, Wt));
 }
 
 #ifndef PB_HOST_CHECK

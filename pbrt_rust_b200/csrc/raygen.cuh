@@ -90,7 +90,7 @@ k_raygen_groups(const DSampler smp, const RaygenArgs a) {
     float vy = ((float)sy + jy) * dy;
     vx += (float)pxx;  // stratified.rs:79-82
     vy += (float)pxy;
-    a.img[p * spp + i] = make_float2(vx, vy);
+    st_stream(a.img + (p * spp + i), make_float2(vx, vy));
     if (a.edge) edge |= sample_leaves_own_pixel(a, vx, vy, pxx, pxy);
   }
   if (edge && a.edge) atomicOr(&a.edge[p], 1u);
@@ -187,7 +187,7 @@ k_raygen_full(const DSampler smp, const RaygenArgs a) {
     for (uint32_t q = 0; q < tot; ++q) {
       const float u1 = ws.random_float();
       const float u2 = ws.random_float();
-      a.lightu[p * tot + q] = make_float2(u1, u2);
+      st_stream(a.lightu + (p * tot + q), make_float2(u1, u2));
     }
   }
 }

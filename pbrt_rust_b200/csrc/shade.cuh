@@ -154,7 +154,7 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   const bool in_range = idx < a.n;
   float4 hraw = make_float4(__uint_as_float(PBRTB200_MISS), 0.f, 0.f, 0.f);
   if (in_range) {
-    hraw = __ldg(reinterpret_cast<const float4*>(a.hits) + idx);
+    hraw = ld_stream(reinterpret_cast<const float4*>(a.hits) + idx);
     // independent streams this thread will need later: start them now (no register cost)
     PB_PREFETCH_L2(a.img + idx);
     if (a.lightu) PB_PREFETCH_L2(a.lightu + idx * sc.area_sample_pairs);
@@ -182,7 +182,7 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
   const bool alive = in_range && prim != PBRTB200_MISS;
   float4* terms = a.terms + (in_range ? idx : 0) * a.slots;
   if (in_range && !alive)  // miss: sum of light.le(ray) = 0 (light/mod.rs:50-52)
-    for (uint32_t q = 0; q < a.slots; ++q) terms[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t q = 0; q < a.slots; ++q) st_stream(terms + q, make_float4(0.f, 0.f, 0.f, 0.f));
   DBSDF bs;
   uint32_t le_bits = 0u;
   f3 p = mk3(0.f, 0.f, 0.f), n = p, wo = p;
@@ -199,9 +199,9 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
 
   // Regenerate the camera ray and its differentials (camera/mod.rs:212-271, ray.rs:107-112;
   // D15: the differential origins/directions stay in camera space).
-  const float2 im = __ldg(a.img + idx);
+  const float2 im = ld_stream(a.img + idx);
   float2 ln = make_float2(0.f, 0.f);
-  if (a.lens) ln = __ldg(a.lens + idx);
+  if (a.lens) ln = ld_stream(a.lens + idx);
   f3 o, d, p_camera;
   camera_ray(cam, im.x, im.y, ln.x, ln.y, &o, &d, &p_camera);
   // The screen-space differentials (dpdx, dudx, ...) feed texture mappings only; a material whose
@@ -346,7 +346,7 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
         Li = div3s(I, len2(wi));
       } else {
         // Diffuse area light over emissive triangles (extension; pbrt-v2 semantics, A13)
-        const float2 uu = __ldg(lu++);
+        const float2 uu = ld_stream(lu++);
         const float u1 = uu.x, u2 = uu.y;
         uint32_t k = 0;
         while (k + 1 < lt.n_tris && u1 >= a.area_tris[lt.first_tri + k].cdf_hi) ++k;
@@ -378,7 +378,7 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
         }
       }
       term_nan = isnan(c.x) || isnan(c.y) || isnan(c.z);
-      terms[slot] = make_float4(c.x, c.y, c.z, slot == 0u ? __uint_as_float(le_bits) : 0.f);
+      st_stream(terms + slot, make_float4(c.x, c.y, c.z, slot == 0u ? __uint_as_float(le_bits) : 0.f));
       }  // alive
       // block-aggregated push: ballot per warp, one global atomic per block and slot
       const unsigned sm = __ballot_sync(0xffffffffu, shadow);
@@ -394,9 +394,9 @@ k_shade(const DScene sc, const DCamera cam, const ShadeArgs a) {
         uint32_t q = s_block_base[slot & 1u] + (uint32_t)__popc(sm & ((1u << lane) - 1u));
         for (int w = 0; w < warp; ++w) q += wc[w];
         float4* rq = reinterpret_cast<float4*>(a.sq_rays + q);
-        rq[0] = make_float4(vis.o[0], vis.o[1], vis.o[2], vis.mint);
-        rq[1] = make_float4(vis.d[0], vis.d[1], vis.d[2], vis.maxt);
-        a.sq_slots[q] = (gslot0 + slot) | (term_nan ? PB_SQ_NAN : 0u) | ((slot == 0u && le_bits) ? PB_SQ_KEEPW : 0u);
+        st_stream(rq, make_float4(vis.o[0], vis.o[1], vis.o[2], vis.mint));
+        st_stream(rq + 1, make_float4(vis.d[0], vis.d[1], vis.d[2], vis.maxt));
+        st_stream(a.sq_slots + q, (gslot0 + slot) | (term_nan ? PB_SQ_NAN : 0u) | ((slot == 0u && le_bits) ? PB_SQ_KEEPW : 0u));
       }
     }
   }

@@ -76,7 +76,7 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
       float mint, maxt;
       if (SRC == 0) {
         const float4* rp = reinterpret_cast<const float4*>(a.rays + idx);
-        const float4 r0 = ldg4(rp), r1 = ldg4(rp + 1);
+        const float4 r0 = ld_stream(rp), r1 = ld_stream(rp + 1);
         o = mk3(r0.x, r0.y, r0.z);
         mint = r0.w;
         d = mk3(r1.x, r1.y, r1.z);
@@ -85,13 +85,13 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
         if (a.pixels) {
           const uint64_t pix = idx / a.spp;
           if ((__ldg(&a.pixels[pix].task) & PB_PIXEL_HALO_BIT) && __ldg(&a.edge[pix]) == 0u) {
-            reinterpret_cast<float4*>(a.hits)[idx] = make_float4(__uint_as_float(PBRTB200_MISS), 0.f, 0.f, 0.f);
+            st_stream(reinterpret_cast<float4*>(a.hits) + idx, make_float4(__uint_as_float(PBRTB200_MISS), 0.f, 0.f, 0.f));
             continue;
           }
         }
-        const float2 im = __ldg(a.img + idx);
+        const float2 im = ld_stream(a.img + idx);
         float2 ln = make_float2(0.f, 0.f);
-        if (a.lens) ln = __ldg(a.lens + idx);
+        if (a.lens) ln = ld_stream(a.lens + idx);
         camera_ray(cam, im.x, im.y, ln.x, ln.y, &o, &d, nullptr);
         mint = 0.0f;         // ray.rs:30-38 Ray::new_with(.., start = 0)
         maxt = PB_F32_MAX;
@@ -105,7 +105,7 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
         const bool occ = r.prim != PBRTB200_MISS;
         if (a.occluded) a.occluded[idx] = occ ? 1 : 0;
         if (a.contrib) {  // render pipeline: the guarded radiance term (shade.cuh PB_SQ_*)
-          const uint32_t sl = __ldg(a.slots + idx);
+          const uint32_t sl = ld_stream(a.slots + idx);
           float4* term = a.contrib + (sl & PB_SQ_INDEX);
           if (occ) {
             if (sl & PB_SQ_KEEPW) {  // w carries an emitter index
@@ -126,7 +126,7 @@ k_trace(const DScene sc, const DCamera cam, const TraceArgs a) {
         h.y = r.t;
         h.z = r.b1;
         h.w = r.b2;
-        reinterpret_cast<float4*>(a.hits)[oi] = h;
+        st_stream(reinterpret_cast<float4*>(a.hits) + oi, h);
       }
     }
    }

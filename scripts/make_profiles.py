@@ -18,7 +18,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__sass_average_branch_targets_threads_uniform.pct",
-        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 
 
@@ -31,13 +32,14 @@ def raw(rep):
 summary = {}
 lines = [f"# ncu --set full summaries ({TAG}; B200, --clock-control none)\n"]
 for name in sorted(os.listdir(GP)):
-    if not name.endswith(".ncu-rep"):
+    if not (name.endswith(".ncu-rep") and name.startswith("prof_")):
         continue
     hdr, units, rows = raw(os.path.join(GP, name))
     ci = {h: i for i, h in enumerate(hdr)}
+    workload = "config 5 (50 M triangles, 7.6 GB of nodes + triangles: the scene does not fit the 126 MB L2)" if "_c5_" in name else "config 3"
     for r in rows:
         k = r[ci["Kernel Name"]]
-        lines.append(f"\n## {k}\n\n| metric | value |\n|---|---|")
+        lines.append(f"\n## {k} — {workload} ({name})\n\n| metric | value |\n|---|---|")
         d = {}
         for w in WANT:
             if w in ci:

@@ -1,7 +1,8 @@
 """Small frames that cover every kernel of the render path, for compute-sanitizer (scripts/gpu_sanitize.sh):
 the smoke frame, a wide-filter frame, a multi-light / multi-sample frame (k_fold), a mixed sphere /
 triangle textured frame, a frame forced through the sample ring and banded film, a Halton frame, the
-trace hooks, and one frame through a (single-device) group."""
+trace hooks, and one frame through a (single-device) group, whose page-locked host film the film
+kernel writes directly (PBRTB200_HOST_FILM_STORES)."""
 import os
 import sys
 
