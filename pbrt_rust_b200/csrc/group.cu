@@ -71,6 +71,7 @@ struct pbrtb200_group {
   std::vector<double> row_cost;   // per film row: cost density estimate (probe, then measured)
   std::vector<float> device_ms;
   int frames_in_view = 0, moves_in_view = 0, over_streak = 0;
+  bool settled = false;  // the bands of this view have been within 3 % once
   bool peers_enabled = false;
   // pinned registration of the caller's host film
   void* reg_ptr = nullptr;
@@ -277,20 +278,26 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
     g->frames_in_view = 0;
     g->moves_in_view = 0;
     g->over_streak = 0;
+    g->settled = false;
   } else if (n > 1 && g->moves_in_view < 20 && g->device_ms.size() == (size_t)n) {
     // same view again: rescale each band's cost density by the time its device needed last frame and
     // cut again (damped) while the slowest device is more than 3 % above the mean.  Every move rebuilds
-    // the devices' pixel lists (milliseconds of host work per device), so: at most 20 moves per view,
-    // and after the first 8 frames only when two frames in a row say so (a single frame's device
-    // times carry ~2 % of noise).
+    // the devices' pixel lists (a few ms of host work — several frames' worth at 8 GPUs), so: at most 20
+    // moves per view; after the first 8 frames only when two frames in a row say so (a single frame's
+    // device times carry ~2 % of noise); and once the bands have been within 3 % they are SETTLED: only
+    // three frames in a row more than 6 % off (the scene's cost really changed, e.g. host instead of
+    // device film) start a new round — 3 % is one 4-row quantum of a 1080p band at 8 GPUs.
     double mean = 0, mx = 0;
     for (float t : g->device_ms) {
       mean += t / n;
       mx = std::max<double>(mx, t);
     }
-    const bool over = mean > 0 && mx > 1.03 * mean;
+    if (mean > 0 && mx <= 1.03 * mean) g->settled = true;
+    const bool over = mean > 0 && mx > (g->settled ? 1.06 : 1.03) * mean;
     g->over_streak = over ? g->over_streak + 1 : 0;
-    if (over && (g->frames_in_view < 8 || g->over_streak >= 2)) {
+    const int need = g->settled ? 3 : (g->frames_in_view < 8 ? 1 : 2);
+    if (over && g->over_streak >= need) {
+      g->settled = false;
       double total_cost = 0;
       for (double c : g->row_cost) total_cost += c;
       for (int k = 0; k < n; ++k) {
