@@ -351,6 +351,19 @@ int pbrtb200_group_device_stats(const pbrtb200_group* g, int i, pbrtb200_stats* 
  * summed cost over film rows y0 .. y0 + n_rows, boundaries snapped to 4 rows (sampler pixels are
  * listed in 8 x 4 tiles), non-decreasing, bounds[0] = y0, bounds[n_bands] = y0 + n_rows. */
 int pbrtb200_cut_bands(const float* row_cost, int n_rows, int y0, int n_bands, int32_t* bounds);
+/* The balancer pbrtb200_group_render keeps per view, as a plain host object (no device needed): for a
+ * launcher that owns one process per GPU and wants the same partition, and for the CPU tests.
+ * _new: bands of equal summed row_cost (NULL = uniform) over film rows y0 .. y0 + n_rows (NULL on bad
+ * sizes).  _update: feed the time each band needed last frame; the boundaries follow (damped) while
+ * the slowest band is more than 3 % above the mean, with a two-frame confirmation after the first 8
+ * frames, at most 20 moves, and hysteresis once the bands have been within 3 % (three frames in a row
+ * more than 6 % off) — a move makes every device rebuild its pixel list.  Returns 1 if the boundaries
+ * moved, 0 if not, < 0 on bad arguments.  _get: bounds[0 .. n_bands]. */
+typedef struct pbrtb200_bands pbrtb200_bands;
+pbrtb200_bands* pbrtb200_bands_new(const float* row_cost, int n_rows, int y0, int n_bands);
+void pbrtb200_bands_free(pbrtb200_bands* b);
+int pbrtb200_bands_update(pbrtb200_bands* b, const float* device_ms);
+int pbrtb200_bands_get(const pbrtb200_bands* b, int32_t* bounds);
 /* Row bands of the last frame: bounds[0 .. n_devices] (film rows, bounds[i] .. bounds[i+1] on device i)
  * and each device's device time in ms; either pointer may be NULL. */
 int pbrtb200_group_bands(const pbrtb200_group* g, int32_t* bounds, float* device_ms);

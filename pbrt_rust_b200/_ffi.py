@@ -181,6 +181,10 @@ SYMBOLS = [
     ("pbrtb200_group_bands", i32, [_vp, P(i32), _fp]),
     ("pbrtb200_group_device_stats", i32, [_vp, C.c_int, P(Stats)]),
     ("pbrtb200_cut_bands", i32, [_fp, C.c_int, C.c_int, C.c_int, P(i32)]),
+    ("pbrtb200_bands_new", _vp, [_fp, C.c_int, C.c_int, C.c_int]),
+    ("pbrtb200_bands_free", None, [_vp]),
+    ("pbrtb200_bands_update", i32, [_vp, _fp]),
+    ("pbrtb200_bands_get", i32, [_vp, P(i32)]),
 ]
 
 _lib = None

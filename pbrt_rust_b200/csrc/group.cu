@@ -49,6 +49,68 @@ void cut_bands(const std::vector<double>& cost, int y0, int n, int quantum, std:
 }
 }  // namespace
 
+// The band balancer of a view (pure host arithmetic; also reachable through pbrtb200_bands_*).
+// First frame: bands of equal summed cost from a per-row estimate (the cost probe).  Later frames:
+// each band's cost density is rescaled by the time its device really needed (damped, exponent 0.8)
+// and the bands are cut again while the slowest device is more than 3 % above the mean.  Every move
+// makes the devices rebuild their pixel lists (a few ms of host work — several frames' worth at 8
+// GPUs), so: at most 20 moves per view; after the first 8 frames only when two frames in a row say so
+// (a single frame's device times carry ~2 % of noise); and once the bands have been within 3 % they
+// are SETTLED: only three frames in a row more than 6 % off (the cost really changed, e.g. host
+// instead of device film) start a new round — 3 % is one 4-row quantum of a 1080p band at 8 GPUs.
+struct pbrtb200_bands {
+  std::vector<double> row_cost;  // per film row: cost density estimate (probe, then measured)
+  std::vector<int> bounds;       // n + 1 film rows
+  int y0 = 0, n = 1, quantum = 4;
+  int frames = 0, moves = 0, over_streak = 0;
+  bool settled = false;  // the bands have been within 3 % once
+
+  void reset(const std::vector<double>& cost, int y0_, int n_) {
+    row_cost = cost;
+    y0 = y0_;
+    n = n_;
+    frames = 1;
+    moves = over_streak = 0;
+    settled = false;
+    cut_bands(row_cost, y0, n, quantum, &bounds);
+  }
+  // device_ms[k]: the time band k needed last frame.  Returns true when the boundaries moved.
+  bool update(const float* device_ms) {
+    ++frames;
+    if (n < 2 || moves >= 20) return false;
+    double mean = 0, mx = 0;
+    for (int k = 0; k < n; ++k) {
+      mean += device_ms[k] / n;
+      mx = std::max<double>(mx, device_ms[k]);
+    }
+    if (!(mean > 0)) return false;
+    if (mx <= 1.03 * mean) settled = true;
+    const bool over = mx > (settled ? 1.06 : 1.03) * mean;
+    over_streak = over ? over_streak + 1 : 0;
+    const int need = settled ? 3 : (frames <= 9 ? 1 : 2);
+    if (!over || over_streak < need) return false;
+    settled = false;
+    over_streak = 0;
+    double total_cost = 0;
+    for (double c : row_cost) total_cost += c;
+    for (int k = 0; k < n; ++k) {
+      const int a = bounds[(size_t)k] - y0, b = bounds[(size_t)k + 1] - y0;
+      double band_cost = 0;
+      for (int y = a; y < b; ++y) band_cost += row_cost[(size_t)y];
+      if (b <= a || band_cost <= 0 || total_cost <= 0) continue;
+      // predicted share of the frame vs the share of the time the device really needed
+      const double predicted = band_cost / total_cost, measured = device_ms[k] / (mean * n);
+      const double scale = std::pow(measured / predicted, 0.8);
+      for (int y = a; y < b; ++y) row_cost[(size_t)y] *= scale;
+    }
+    const std::vector<int> before = bounds;
+    cut_bands(row_cost, y0, n, quantum, &bounds);
+    if (bounds == before) return false;
+    ++moves;
+    return true;
+  }
+};
+
 struct pbrtb200_group {
   std::vector<Worker> w;
   std::string err;
@@ -67,11 +129,8 @@ struct pbrtb200_group {
     float xw = 0, yw = 0;
     bool valid = false;
   } view;
-  std::vector<int> bounds;        // n + 1 film rows
-  std::vector<double> row_cost;   // per film row: cost density estimate (probe, then measured)
+  pbrtb200_bands bal;             // row bands of the current view
   std::vector<float> device_ms;
-  int frames_in_view = 0, moves_in_view = 0, over_streak = 0;
-  bool settled = false;  // the bands of this view have been within 3 % once
   bool peers_enabled = false;
   // pinned registration of the caller's host film
   void* reg_ptr = nullptr;
@@ -148,6 +207,26 @@ int pbrtb200_cut_bands(const float* row_cost, int n_rows, int y0, int n_bands, i
   std::vector<int> b;
   cut_bands(c, y0, n_bands, 4, &b);
   for (int i = 0; i <= n_bands; ++i) bounds[i] = b[(size_t)i];
+  return PBRTB200_OK;
+}
+
+pbrtb200_bands* pbrtb200_bands_new(const float* row_cost, int n_rows, int y0, int n_bands) {
+  if (n_rows < 1 || n_bands < 1) return nullptr;
+  std::vector<double> c((size_t)n_rows, 1.0);
+  if (row_cost)
+    for (int y = 0; y < n_rows; ++y) c[(size_t)y] = row_cost[y];
+  pbrtb200_bands* b = new pbrtb200_bands();
+  b->reset(c, y0, n_bands);
+  return b;
+}
+void pbrtb200_bands_free(pbrtb200_bands* b) { delete b; }
+int pbrtb200_bands_update(pbrtb200_bands* b, const float* device_ms) {
+  if (!b || !device_ms) return PBRTB200_EINVAL;
+  return b->update(device_ms) ? 1 : 0;
+}
+int pbrtb200_bands_get(const pbrtb200_bands* b, int32_t* bounds) {
+  if (!b || !bounds) return PBRTB200_EINVAL;
+  for (size_t i = 0; i < b->bounds.size(); ++i) bounds[i] = b->bounds[i];
   return PBRTB200_OK;
 }
 
@@ -234,9 +313,9 @@ int pbrtb200_group_device_stats(const pbrtb200_group* g, int i, pbrtb200_stats* 
 }
 
 int pbrtb200_group_bands(const pbrtb200_group* g, int32_t* bounds, float* device_ms) {
-  if (!g || g->bounds.size() != g->w.size() + 1) return PBRTB200_EINVAL;
+  if (!g || g->bal.bounds.size() != g->w.size() + 1) return PBRTB200_EINVAL;
   if (bounds)
-    for (size_t i = 0; i < g->bounds.size(); ++i) bounds[i] = g->bounds[i];
+    for (size_t i = 0; i < g->bal.bounds.size(); ++i) bounds[i] = g->bal.bounds[i];
   if (device_ms)
     for (size_t i = 0; i < g->w.size(); ++i) device_ms[i] = i < g->device_ms.size() ? g->device_ms[i] : 0.f;
   return PBRTB200_OK;
@@ -259,64 +338,24 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
   const bool same_view = g->view.valid && std::memcmp(&g->view.cam, cam, sizeof *cam) == 0 &&
                          std::memcmp(&g->view.smp, smp, sizeof *smp) == 0 && std::memcmp(g->view.film_ext, ext, sizeof ext) == 0 &&
                          g->view.xw == film->filter_xw && g->view.yw == film->filter_yw;
-  const int quantum = 4;  // sampler pixels are listed in 8 x 4 tiles
   if (!same_view) {
-    g->row_cost.assign((size_t)H, 1.0);
+    std::vector<double> cost((size_t)H, 1.0);
     if (n > 1) {  // one-shot balance: the cost probe, on the first device
       std::vector<float> rc((size_t)H, 1.f);
       const int stride = std::max(1, std::min(W, H) / 256);
       if (pbrtb200_cost_profile(g->w[0].ctx, cam, film, stride, rc.data()) == PBRTB200_OK)
-        for (int y = 0; y < H; ++y) g->row_cost[(size_t)y] = rc[(size_t)y];
+        for (int y = 0; y < H; ++y) cost[(size_t)y] = rc[(size_t)y];
     }
-    cut_bands(g->row_cost, y0, n, quantum, &g->bounds);
+    g->bal.reset(cost, y0, n);
     g->view.cam = *cam;
     g->view.smp = *smp;
     std::memcpy(g->view.film_ext, ext, sizeof ext);
     g->view.xw = film->filter_xw;
     g->view.yw = film->filter_yw;
     g->view.valid = true;
-    g->frames_in_view = 0;
-    g->moves_in_view = 0;
-    g->over_streak = 0;
-    g->settled = false;
-  } else if (n > 1 && g->moves_in_view < 20 && g->device_ms.size() == (size_t)n) {
-    // same view again: rescale each band's cost density by the time its device needed last frame and
-    // cut again (damped) while the slowest device is more than 3 % above the mean.  Every move rebuilds
-    // the devices' pixel lists (a few ms of host work — several frames' worth at 8 GPUs), so: at most 20
-    // moves per view; after the first 8 frames only when two frames in a row say so (a single frame's
-    // device times carry ~2 % of noise); and once the bands have been within 3 % they are SETTLED: only
-    // three frames in a row more than 6 % off (the scene's cost really changed, e.g. host instead of
-    // device film) start a new round — 3 % is one 4-row quantum of a 1080p band at 8 GPUs.
-    double mean = 0, mx = 0;
-    for (float t : g->device_ms) {
-      mean += t / n;
-      mx = std::max<double>(mx, t);
-    }
-    if (mean > 0 && mx <= 1.03 * mean) g->settled = true;
-    const bool over = mean > 0 && mx > (g->settled ? 1.06 : 1.03) * mean;
-    g->over_streak = over ? g->over_streak + 1 : 0;
-    const int need = g->settled ? 3 : (g->frames_in_view < 8 ? 1 : 2);
-    if (over && g->over_streak >= need) {
-      g->settled = false;
-      double total_cost = 0;
-      for (double c : g->row_cost) total_cost += c;
-      for (int k = 0; k < n; ++k) {
-        const int a = g->bounds[(size_t)k] - y0, b = g->bounds[(size_t)k + 1] - y0;
-        double band_cost = 0;
-        for (int y = a; y < b; ++y) band_cost += g->row_cost[(size_t)y];
-        if (b <= a || band_cost <= 0 || total_cost <= 0) continue;
-        // predicted share of the frame vs the share of the time the device really needed
-        const double predicted = band_cost / total_cost, measured = g->device_ms[(size_t)k] / (mean * n);
-        const double scale = std::pow(measured / predicted, 0.8);
-        for (int y = a; y < b; ++y) g->row_cost[(size_t)y] *= scale;
-      }
-      const std::vector<int> before = g->bounds;
-      cut_bands(g->row_cost, y0, n, quantum, &g->bounds);
-      if (g->bounds != before) ++g->moves_in_view;
-      g->over_streak = 0;
-    }
+  } else if (g->device_ms.size() == (size_t)n) {
+    g->bal.update(g->device_ms.data());  // same view again: follow the measured device times
   }
-  ++g->frames_in_view;
 
   // ---- the caller's host film: page-locked once, so that every device's rows travel by DMA ------
   const size_t film_bytes = (size_t)W * (size_t)H * 4 * sizeof(float);
@@ -338,7 +377,7 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
     Worker& w = g->w[(size_t)i];
     w.rc = PBRTB200_OK;
     std::memset(&w.st, 0, sizeof w.st);
-    const int a = g->bounds[(size_t)i], b = g->bounds[(size_t)i + 1];
+    const int a = g->bal.bounds[(size_t)i], b = g->bal.bounds[(size_t)i + 1];
     if (b <= a) return;  // empty band: nothing to render, nothing to copy
     const int32_t rect[4] = {film->x_pixel_start, a, film->x_pixel_start + W, b};
     pbrtb200_tileset ts{rect, 1u, PBRTB200_TILES_KEEP_OTHERS};

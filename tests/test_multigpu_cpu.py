@@ -124,3 +124,70 @@ def test_group_band_cut_covers_the_film_and_balances_cost(n_bands, rows, y0):
             ideal = cost.sum() / n_bands
             slack = 4 * cost.max() + 1e-6          # one quantum of the most expensive rows on either side
             assert max(abs(s_ - ideal) for s_ in share) <= 2 * slack, (share, ideal)
+
+
+def _simulate_bands(n, seed, frames=40, noise=0.01, change_at=None):
+    """Drives pbrtb200_bands_* with a hidden per-row cost (a horizon peak the probe only half sees), a
+    fixed per-device overhead and per-frame timing noise.  Returns per frame (max / mean of the
+    device times, moved?)."""
+    import ctypes as C
+    from pbrt_rust_b200 import _ffi
+    L = _ffi.lib()
+    rng = np.random.default_rng(seed)
+    H, y0 = 1080, 0
+    y = np.arange(H)
+    true = 1 + 4 * np.exp(-((y - 300) / 60.0) ** 2) + 0.5 * (y > 300)
+    true *= 7.9 / true.sum()
+    probe = np.ascontiguousarray(true * (1 + 0.3 * np.sin(y / 50.0)), np.float32)
+    bal = L.pbrtb200_bands_new(probe.ctypes.data_as(C.POINTER(C.c_float)), H, y0, n)
+    assert bal
+    try:
+        b = (C.c_int32 * (n + 1))()
+        hist = []
+        for f in range(frames):
+            assert L.pbrtb200_bands_get(bal, b) == 0
+            bb = list(b)
+            assert bb[0] == y0 and bb[-1] == y0 + H and all(p <= q for p, q in zip(bb, bb[1:]))
+            extra = np.zeros(n)
+            if change_at is not None and f >= change_at:   # e.g. host film: half the devices pay 15 % more
+                extra[: n // 2] = 0.15
+            t = np.array([0.15 + true[bb[k]:bb[k + 1]].sum() for k in range(n)]) * (1 + extra)
+            t = np.ascontiguousarray(t * (1 + noise * rng.standard_normal(n)), np.float32)
+            moved = L.pbrtb200_bands_update(bal, t.ctypes.data_as(C.POINTER(C.c_float)))
+            assert moved in (0, 1)
+            hist.append((float(t.max() / t.mean()), moved))
+        return hist
+    finally:
+        L.pbrtb200_bands_free(bal)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_band_balancer_converges_and_then_holds_still(n):
+    """The balancer of pbrtb200_group_render (pbrtb200_bands_*): from a half-wrong cost probe it gets
+    the slowest device within ~3 % of the mean in a few frames, and once settled it does not move
+    again under 1 % timing noise (a move costs the devices a pixel-list rebuild)."""
+    for seed in range(4):
+        hist = _simulate_bands(n, seed)
+        assert max(r for r, _ in hist[8:]) <= 1.06, (seed, hist)     # settled within 3 %, plus noise: below the 6 % that would move them
+        assert sum(m for _, m in hist) <= 8, hist                    # a handful of moves in total
+        assert sum(m for _, m in hist[12:]) == 0, hist               # none once settled
+
+
+def test_band_balancer_follows_a_real_change_but_not_noise():
+    """Settled bands start a new round only when the devices stay more than 6 % apart for three frames
+    (here: half the devices become 15 % slower at frame 20) — and settle again."""
+    hist = _simulate_bands(8, 11, frames=60, change_at=20)
+    assert sum(m for _, m in hist[12:20]) == 0
+    assert hist[20][0] > 1.06 and sum(m for _, m in hist[20:30]) >= 1
+    assert max(r for r, _ in hist[34:]) <= 1.06 and sum(m for _, m in hist[40:]) == 0, hist
+    # bad arguments
+    import ctypes as C
+    from pbrt_rust_b200 import _ffi
+    L = _ffi.lib()
+    assert not L.pbrtb200_bands_new(None, 0, 0, 2)
+    assert L.pbrtb200_bands_update(None, None) < 0
+    one = L.pbrtb200_bands_new(None, 10, 5, 1)    # uniform cost, one band: nothing to balance
+    b = (C.c_int32 * 2)()
+    t = (C.c_float * 1)(1.0)
+    assert L.pbrtb200_bands_update(one, t) == 0 and L.pbrtb200_bands_get(one, b) == 0 and list(b) == [5, 15]
+    L.pbrtb200_bands_free(one)
