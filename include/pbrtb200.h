@@ -351,6 +351,15 @@ int pbrtb200_group_device_stats(const pbrtb200_group* g, int i, pbrtb200_stats* 
  * summed cost over film rows y0 .. y0 + n_rows, boundaries snapped to 4 rows (sampler pixels are
  * listed in 8 x 4 tiles), non-decreasing, bounds[0] = y0, bounds[n_bands] = y0 + n_rows. */
 int pbrtb200_cut_bands(const float* row_cost, int n_rows, int y0, int n_bands, int32_t* bounds);
+/* The pixel work list pbrtb200_render derives from a sampler, a film and a tile set, as host arithmetic
+ * (no device needed; for tools and the CPU tests): the sampler pixels whose samples can reach the film
+ * pixels of the tile set (tiles == NULL: the whole film), in the order the kernels process them (8 x 4
+ * tiles, row-major), each with its owning task (the reference's sub-window split) and its raster index
+ * k inside that task's window; task bit 31 marks a halo pixel (outside the rects of this call).
+ * Call with the arrays NULL to get *n_pixels, then with arrays of that size.  index (may be NULL):
+ * one entry per pixel of the sampler extent, row-major: its list position or -1. */
+int pbrtb200_work_list(const pbrtb200_sampler* smp, const pbrtb200_film* film, const pbrtb200_tileset* tiles,
+                       uint32_t* n_pixels, int32_t* xy, uint32_t* k, uint32_t* task, int32_t* index);
 /* The balancer pbrtb200_group_render keeps per view, as a plain host object (no device needed): for a
  * launcher that owns one process per GPU and wants the same partition, and for the CPU tests.
  * _new: bands of equal summed row_cost (NULL = uniform) over film rows y0 .. y0 + n_rows (NULL on bad

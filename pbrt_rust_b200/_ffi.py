@@ -181,6 +181,7 @@ SYMBOLS = [
     ("pbrtb200_group_bands", i32, [_vp, P(i32), _fp]),
     ("pbrtb200_group_device_stats", i32, [_vp, C.c_int, P(Stats)]),
     ("pbrtb200_cut_bands", i32, [_fp, C.c_int, C.c_int, C.c_int, P(i32)]),
+    ("pbrtb200_work_list", i32, [P(Sampler), P(Film), P(TileSet), P(u32), P(i32), P(u32), P(u32), P(i32)]),
     ("pbrtb200_bands_new", _vp, [_fp, C.c_int, C.c_int, C.c_int]),
     ("pbrtb200_bands_free", None, [_vp]),
     ("pbrtb200_bands_update", i32, [_vp, _fp]),

@@ -3,6 +3,8 @@
 // There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 
+#include <chrono>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -76,6 +78,7 @@ struct pbrtb200_ctx {
   cudaStream_t own_stream = nullptr;  // created by the ctx
   cudaStream_t copy_stream = nullptr; // film bands travel to the host while later chunks render
   std::vector<cudaEvent_t> band_events;
+  pbh::PixelList pixel_list;          // host copy of the work list (storage reused when the tile set changes)
   std::vector<uint32_t> rows_ready;   // per sampler row: list pixels that must be done (prefix max)
   std::vector<uint32_t> row_first;    // per sampler row r: smallest list index of any pixel in rows >= r
   std::string err;
@@ -293,123 +296,17 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
 
   const int32_t ext[4] = {smp->x_start, smp->x_end, smp->y_start, smp->y_end};
   const int sw = ext[1] - ext[0], sh = ext[3] - ext[2];
-  // Only the sampler rows this call can need are touched (row index relative to ext[2]): a row band of
-  // a multi-GPU frame costs its share of the list build, not the whole frame's.  (A HaltonSampler bins
-  // candidates that land anywhere: it keeps every row.)
-  int r0 = 0, r1 = sh;
-  auto rect_rows = [&](const int32_t* q, int* qy0, int* qy1) {
-    *qy0 = std::max((int)std::ceil(((float)q[1] - 0.5f) - yw) - 1, ext[2]);
-    *qy1 = std::min((int)std::floor(((float)(q[3] - 1) + 0.5f) + yw) + 1, ext[3] - 1);
-  };
-  if (!whole && smp->kind != PBRTB200_SAMPLER_HALTON) {
-    r0 = sh;
-    r1 = 0;
-    for (size_t r = 0; r < rects.size() / 4; ++r) {
-      int qy0, qy1;
-      rect_rows(&rects[4 * r], &qy0, &qy1);
-      r0 = std::min(r0, qy0 - ext[2]);
-      r1 = std::max(r1, qy1 - ext[2] + 1);
-    }
-    r0 = std::max(0, std::min(r0, sh));
-    r1 = std::max(r0, std::min(r1, sh));
-  }
-  const int rows_n = r1 - r0;
-  const size_t n_loc = (size_t)sw * (size_t)rows_n;
-  auto loc = [&](int yy, int xx) { return (size_t)(yy - r0) * (size_t)sw + (size_t)xx; };  // yy, xx relative to the extent
-  std::vector<uint16_t> task_of(n_loc, 0xFFFF);
-  std::vector<uint32_t> k_of(n_loc, 0);
-  std::vector<uint32_t> keys(8 * (size_t)smp->num_tasks);
-  for (int t = 0; t < smp->num_tasks; ++t) {
-    pbh::task_key((uint64_t)t, &keys[8 * (size_t)t]);
-    int32_t w[4];
-    pbh::sampler_sub_window(ext, (uint64_t)t, (uint64_t)smp->num_tasks, w);
-    if (w[0] == w[1] || w[2] == w[3]) continue;  // get_sub_sampler -> None
-    if (w[0] < ext[0] || w[1] > ext[1] || w[2] < ext[2] || w[3] > ext[3] || w[1] < w[0] || w[3] < w[2])
-      FAIL(PBRTB200_EINVAL, "task window outside the sampler extent");
-    const uint32_t tw = (uint32_t)(w[1] - w[0]);
-    for (int y = std::max(w[2], ext[2] + r0); y < std::min(w[3], ext[2] + r1); ++y)
-      for (int x = w[0]; x < w[1]; ++x) {
-        const size_t e = loc(y - ext[2], x - ext[0]);
-        task_of[e] = (uint16_t)t;
-        k_of[e] = (uint32_t)(y - w[2]) * tw + (uint32_t)(x - w[0]);
-      }
-  }
-  // which sampler pixels are needed
-  std::vector<uint8_t> need(n_loc, whole ? 1 : 0);
-  std::vector<uint8_t> owned(whole ? 0 : n_loc, 0);  // sampler pixel lies inside a rect of this call
-  if (!whole) {
-    for (size_t r = 0; r < rects.size() / 4; ++r) {
-      const int32_t* q = &rects[4 * r];
-      for (int y = std::max(q[1], ext[2] + r0); y < std::min(q[3], ext[2] + r1); ++y)
-        for (int x = std::max(q[0], ext[0]); x < std::min(q[2], ext[1]); ++x)
-          owned[loc(y - ext[2], x - ext[0])] = 1;
-      int qx0 = (int)std::ceil(((float)q[0] - 0.5f) - xw) - 1, qx1 = (int)std::floor(((float)(q[2] - 1) + 0.5f) + xw) + 1;
-      int qy0, qy1;
-      rect_rows(q, &qy0, &qy1);
-      qx0 = std::max(qx0, ext[0]);
-      qx1 = std::min(qx1, ext[1] - 1);
-      qy0 = std::max(qy0, ext[2] + r0);
-      qy1 = std::min(qy1, ext[2] + r1 - 1);
-      // Within that padded range keep exactly the sampler pixels k_film will accept for some pixel
-      // of the rect: a sample of pixel p has image coordinate in [p, p + 1], and add_sample's
-      // extent arithmetic is monotonic, so it can only reach [ceil((p-0.5)-w), floor((p+0.5)+w)]
-      // (the same float expressions k_film evaluates).
-      auto reaches = [](int p, float w, int lo, int hi) {  // can pixel column/row p reach [lo, hi]?
-        const int a = pbh::sat_i32(std::ceil(((float)p - 0.5f) - w));
-        const int b = pbh::sat_i32(std::floor((((float)p + 1.0f) - 0.5f) + w));
-        return a <= hi && b >= lo;
-      };
-      for (int y = qy0; y <= qy1; ++y) {
-        if (!reaches(y, yw, q[1], q[3] - 1)) continue;
-        for (int x = qx0; x <= qx1; ++x)
-          if (reaches(x, xw, q[0], q[2] - 1)) need[loc(y - ext[2], x - ext[0])] = 1;
-      }
-    }
-  }
-  std::vector<DPixel> list;
-  list.reserve(n_loc);
-  std::vector<int32_t> index(n_loc, -1);
-  const int TW = 8, TH = 4;
-  for (int ty = (r0 / TH) * TH; ty < r1; ty += TH)
-    for (int tx = 0; tx < sw; tx += TW)
-      for (int yy = std::max(ty, r0); yy < std::min(ty + TH, r1); ++yy)
-        for (int xx = tx; xx < std::min(tx + TW, sw); ++xx) {
-          const size_t e = loc(yy, xx);
-          if (!need[e] || task_of[e] == 0xFFFF) continue;
-          DPixel p;
-          const int x = ext[0] + xx, y = ext[2] + yy;
-          p.xy = (int32_t)(((uint32_t)(uint16_t)(int16_t)x) | ((uint32_t)(uint16_t)(int16_t)y << 16));
-          p.k = k_of[e];
-          p.task = task_of[e];
-          if (!whole && !owned[e]) p.task |= PB_PIXEL_HALO_BIT;
-          index[e] = (int32_t)list.size();
-          list.push_back(p);
-        }
-  if (list.empty()) FAIL(PBRTB200_EINVAL, "no sampler pixel to evaluate");
-  // rows_ready[r] = how many list pixels must be finished before every sample of sampler rows
-  // 0..r exists (lets k_film run on the finished top of the image while later chunks render)
-  ctx->rows_ready.assign((size_t)sh, 0u);
-  for (int yy = 0; yy < sh; ++yy) {
-    uint32_t m = yy ? ctx->rows_ready[(size_t)yy - 1] : 0u;
-    if (yy >= r0 && yy < r1)
-      for (int xx = 0; xx < sw; ++xx) {
-        const int32_t li = index[loc(yy, xx)];
-        if (li >= 0) m = std::max(m, (uint32_t)li + 1u);
-      }
-    ctx->rows_ready[(size_t)yy] = m;
-  }
-  // row_first[r] = first list pixel still needed once everything above sampler row r is filtered
-  ctx->row_first.assign((size_t)sh + 1, (uint32_t)list.size());
-  for (int yy = sh - 1; yy >= 0; --yy) {
-    uint32_t m = ctx->row_first[(size_t)yy + 1];
-    if (yy >= r0 && yy < r1)
-      for (int xx = 0; xx < sw; ++xx) {
-        const int32_t li = index[loc(yy, xx)];
-        if (li >= 0) m = std::min(m, (uint32_t)li);
-      }
-    ctx->row_first[(size_t)yy] = m;
-  }
-  if (upload(ctx, ctx->d_pixels, list.data(), list.size())) return PBRTB200_ENODEV;
+  pbh::PixelList& pl = ctx->pixel_list;  // kept: a later list (a moved band) reuses the storage
+  if (const char* why = pbh::build_pixel_list(*smp, rects.data(), rects.size() / 4, whole, xw, yw, &pl)) FAIL(PBRTB200_EINVAL, why);
+  static_assert(sizeof(pbh::PixelRec) == sizeof(DPixel), "PixelRec is DPixel's host twin");
+  const pbh::RawBuf<pbh::PixelRec>& list = pl.list;
+  const pbh::RawBuf<int32_t>& index = pl.index;
+  const std::vector<uint32_t>& keys = pl.keys;
+  const int r0 = pl.r0;
+  const size_t n_loc = index.size();
+  ctx->rows_ready = pl.rows_ready;
+  ctx->row_first = pl.row_first;
+  if (upload(ctx, ctx->d_pixels, reinterpret_cast<const DPixel*>(list.data()), list.size())) return PBRTB200_ENODEV;
   // the index keeps its full-extent layout on the device (k_film / the Halton binning address it by
   // sampler row); only the rows of this list are rewritten — no other row is read with this list
   CK(ctx->d_pix_index.ensure((size_t)sw * (size_t)sh * sizeof(int32_t)));
@@ -462,6 +359,38 @@ int build_pixel_list(pbrtb200_ctx* ctx, const pbrtb200_sampler* smp, const pbrtb
   key.valid = true;
   return 0;
 }
+
+}  // namespace
+extern "C" int pbrtb200_work_list(const pbrtb200_sampler* smp, const pbrtb200_film* film, const pbrtb200_tileset* tiles,
+                                  uint32_t* n_pixels, int32_t* xy, uint32_t* k, uint32_t* task, int32_t* index) {
+  if (!smp || !film || !n_pixels || smp->x_end <= smp->x_start || smp->y_end <= smp->y_start || smp->num_tasks < 1)
+    return PBRTB200_EINVAL;
+  if (tiles && (tiles->n_rects == 0 || !tiles->rects)) return PBRTB200_EINVAL;
+  std::vector<int32_t> rects;
+  if (tiles)
+    rects.assign(tiles->rects, tiles->rects + 4 * (size_t)tiles->n_rects);
+  else
+    rects = {film->x_pixel_start, film->y_pixel_start, film->x_pixel_start + film->x_pixel_count,
+             film->y_pixel_start + film->y_pixel_count};
+  pbh::PixelList pl;
+  if (pbh::build_pixel_list(*smp, rects.data(), rects.size() / 4, tiles == nullptr, film->filter_xw, film->filter_yw, &pl))
+    return PBRTB200_EINVAL;
+  const bool fill = xy || k || task;
+  if (fill && *n_pixels < pl.list.size()) return PBRTB200_EINVAL;
+  *n_pixels = (uint32_t)pl.list.size();
+  for (size_t i = 0; fill && i < pl.list.size(); ++i) {
+    if (xy) xy[i] = pl.list[i].xy;
+    if (k) k[i] = pl.list[i].k;
+    if (task) task[i] = pl.list[i].task;
+  }
+  if (index) {
+    const size_t sw = (size_t)(smp->x_end - smp->x_start), sh = (size_t)(smp->y_end - smp->y_start);
+    std::fill(index, index + sw * sh, -1);
+    std::copy(pl.index.begin(), pl.index.end(), index + (size_t)pl.r0 * sw);
+  }
+  return PBRTB200_OK;
+}
+namespace {
 
 struct StageTimer {
   pbrtb200_ctx* ctx;
@@ -1196,7 +1125,22 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     }
     return PBRTB200_OK;
   }
+  // PBRTB200_DEBUG_TIMING=1: host wall time of the phases of this call on stderr (each phase ends with a
+  // stream synchronisation, so the frame itself gets slower: a diagnostic, e.g. for first-frame latency)
+  static const bool dbg_on = [] {
+    const char* v = std::getenv("PBRTB200_DEBUG_TIMING");
+    return v && *v == '1';
+  }();
+  auto dbg_t0 = std::chrono::steady_clock::now();
+  auto dbg = [&](const char* what) {
+    if (!dbg_on) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[pbrtb200 timing] %-14s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - dbg_t0).count());
+    dbg_t0 = t1;
+  };
   if (int rc = build_pixel_list(ctx, smp, film, tiles)) return rc;
+  dbg("pixel list");
 
   DSampler ds;
   fill_sampler(ctx, smp, &ds);
@@ -1311,6 +1255,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     }
   }
 
+  dbg("buffers");
   CK(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(CtrlBlock), ctx->stream));
   CK(cudaMemsetAsync(ctx->d_edge.p, 0, npix * sizeof(uint32_t), ctx->stream));
   if (tiles && !(tiles->flags & PBRTB200_TILES_KEEP_OTHERS))
@@ -1448,6 +1393,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     if (!halton)
       if (int rc = run_raygen(ctx, ds, full, p0, cp, s0, film)) return rc;
     size_t e1 = tm.mark();
+    dbg("raygen");
     CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(&ctrl(ctx)->sq_count, 0, sizeof(uint32_t), ctx->stream));
     TraceArgs ta{};
@@ -1464,6 +1410,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
     }
     if (int rc = launch_trace_t<false, 1>(ctx, dc, ta)) return rc;
     size_t e2 = tm.mark();
+    dbg("closest hit");
     launches += 2;
     tm.span(e0, e1, 0);
     tm.span(e1, e2, 1);
@@ -1492,6 +1439,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
         k_shade<PB_SHADE_MIN_BLOCKS, false><<<(unsigned)((cn + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, dc, sa);
       CK(cudaGetLastError());
       size_t e3 = tm.mark();
+      dbg("shade");
       CK(cudaMemsetAsync(&ctrl(ctx)->counter, 0, sizeof(unsigned long long), ctx->stream));
       TraceArgs sh{};
       sh.rays = sa.sq_rays;
@@ -1504,6 +1452,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       sh.flags = &ctrl(ctx)->flags;
       if (int rc = launch_trace_t<true, 0>(ctx, dc, sh)) return rc;
       size_t e4 = tm.mark();
+      dbg("any hit");
       tm.span(e2, e3, 2);
       tm.span(e3, e4, 3);
       launches += 2;
@@ -1539,6 +1488,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
       if (int rc = film_rows(film_done, std::min(H, film_done + step))) return rc;
   }
   tm.span(eA, tm.mark(), 5);
+  dbg("film");
   if (staged) {
     if (band_copies) {
       // every band: wait for its film launch on the copy stream, then move its rows to the host
@@ -1567,6 +1517,7 @@ int pbrtb200_render(pbrtb200_ctx* ctx, const pbrtb200_camera* cam, const pbrtb20
   }
   CtrlBlock h;
   if (int rc = finish_flags(ctx, &h)) return rc;
+  dbg("copy + finish");
   if (stats) {
     float ms[6];
     tm.collect(ms);

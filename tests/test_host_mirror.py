@@ -357,3 +357,61 @@ def test_host_mipmap_unreadable_file_and_png_reader(orc, tmp_path):
 def test_upload_rejects_bad_mipmap_tables():
     """Validation happens before any device call is needed for the table itself."""
     assert C.sizeof(_ffi.MipMap) == 32
+
+
+def test_pixel_work_list_builder_equals_the_per_pixel_construction(tmp_path):
+    """pbh::build_pixel_list (per-interval task tables, separable need masks, threaded tile-major fill)
+    against the straightforward per-pixel construction, on 800 random (film, filter, task count, tile
+    set) cases including threaded 1080p-sized ones: tests/devsrc/pixel_list_check.cpp."""
+    import subprocess
+    exe = str(tmp_path / "pixel_list_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "devsrc", "pixel_list_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout[-2000:]
+
+
+def test_work_list_hook_lists_every_needed_pixel_once_in_tile_order():
+    """pbrtb200_work_list (the list pbrtb200_render uploads, as host arithmetic): the whole film visits
+    every sampler pixel once, 8 x 4 tiles row-major; a band lists its rows plus the filter halo, halo
+    pixels flagged; k is the raster index inside the owning task's window and the index inverts the list."""
+    L = _ffi.lib()
+    cfg = scenes.config1(xres=50, yres=30, filt=pb.Filter.gaussian(2.0, 2.0, 2.0))
+    film, s = cfg["camera"].film, cfg["sampler"]
+    nt = int(L.pbh_num_tasks(8, film.x_res * film.y_res))
+    smp = _ffi.Sampler(s.kind, s.ext[0], s.ext[1], s.ext[2], s.ext[3], s.xs, s.ys, int(s.jitter), s.sopen, s.sclose, nt)
+    sw, sh = s.ext[1] - s.ext[0], s.ext[3] - s.ext[2]
+
+    def work_list(tiles):
+        ts = None
+        if tiles is not None:
+            rects = np.ascontiguousarray(tiles, np.int32)
+            ts = _ffi.TileSet(rects.ctypes.data_as(C.POINTER(C.c_int32)), rects.shape[0], 1)
+        n = C.c_uint32(0)
+        assert L.pbrtb200_work_list(C.byref(smp), C.byref(film.desc), C.byref(ts) if ts else None, C.byref(n), None, None, None, None) == 0
+        xy, k, task = np.zeros(n.value, np.int32), np.zeros(n.value, np.uint32), np.zeros(n.value, np.uint32)
+        index = np.zeros(sw * sh, np.int32)
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        assert L.pbrtb200_work_list(C.byref(smp), C.byref(film.desc), C.byref(ts) if ts else None, C.byref(n), p(xy, C.c_int32),
+                                    p(k, C.c_uint32), p(task, C.c_uint32), p(index, C.c_int32)) == 0
+        x = (xy & 0xFFFF).astype(np.int16).astype(int)
+        y = ((xy >> 16) & 0xFFFF).astype(np.int16).astype(int)
+        return x, y, k, task, index.reshape(sh, sw)
+
+    x, y, k, task, index = work_list(None)
+    assert x.size == sw * sh and (task >> 31).max() == 0
+    assert np.array_equal(index[y - s.ext[2], x - s.ext[0]], np.arange(x.size))          # the index inverts the list
+    tile = ((y - s.ext[2]) // 4) * ((sw + 7) // 8) + (x - s.ext[0]) // 8
+    assert (np.diff(tile) >= 0).all()                                                      # tiles in row-major order
+    for t in np.unique(task):                                                              # k: raster index in the task window
+        w = (C.c_int32 * 4)()
+        m = task == t
+        x0, y0, tw = x[m].min(), y[m].min(), x[m].max() - x[m].min() + 1
+        assert np.array_equal(k[m], (y[m] - y0) * tw + (x[m] - x0))
+    xb, yb, kb, taskb, indexb = work_list([(0, 8, 50, 16)])                                # a band of film rows 8..15
+    halo = (taskb >> 31) == 1
+    assert ((yb[~halo] >= 8) & (yb[~halo] < 16) & (xb[~halo] >= 0) & (xb[~halo] < 50)).all()
+    assert halo.any() and yb.min() < 8 and yb.max() >= 16 and yb.min() >= 8 - 4 and yb.max() <= 16 + 3
+    whole_k = {(a, b): c for a, b, c in zip(x, y, k)}
+    assert all(whole_k[(a, b)] == c for a, b, c in zip(xb, yb, kb))                       # same RNG offsets as the whole film
+    assert (indexb >= 0).sum() == xb.size
