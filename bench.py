@@ -365,7 +365,7 @@ def main():
                    "band_rows": bands[0] if bands else None, "per_device_ms": bands[1] if bands else None,
                    "film_gather": "single GPU" if world == 1 else
                                   "value: film kernels store their rows into GPU 0's film over NVLink (peer access); "
-                                  "e2e: every GPU copies its own rows into the host film over its own PCIe link",
+                                  "e2e: every GPU's film kernel stores its own rows into the pinned host film over its own PCIe link",
                    "driver": "one process drives all GPUs (pbrtb200_group_render); ranks > 0 only join the barriers" if world > 1 else "single context"},
         "clocks": clocks,
         "e2e": {"value": e2e_v, "unit": "Mrays/s", "ms_per_step": ms_e2e,
