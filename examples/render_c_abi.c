@@ -98,8 +98,13 @@ int main(int argc, char** argv) {
   float* xyzw = (float*)malloc(npx * 4 * sizeof(float));
   uint8_t* rgb8 = (uint8_t*)malloc(npx * 3);
   pbrtb200_stats st;
-  if (grp)
+  if (grp) {
+    /* optional: page-lock the film for the group, so that every GPU's film kernel stores its rows straight
+     * into it; the caller owns the buffer's lifetime, so the caller pins and unpins */
+    CHECK(pbrtb200_group_pin_host_film(grp, xyzw, (uint64_t)npx * 4 * sizeof(float)));
     CHECK(pbrtb200_group_render(grp, &cam, &smp, &film, &integ, xyzw, 0, &st));
+    CHECK(pbrtb200_group_unpin_host_film(grp));
+  }
   else
     CHECK(pbrtb200_render(ctx, &cam, &smp, &film, &integ, NULL, xyzw, 0, &st));
   CHECK(pbrtb200_film_develop(ctx, xyzw, 0, npx, NULL, rgb8, 0));

@@ -213,7 +213,18 @@ impl Renderer for GpuRenderer {
         let rc = unsafe {
             match &self.backend {
                 &Backend::Single(ctx) => pbrtb200_render(ctx, &cam, &smp, &fd, &integ, ::std::ptr::null(), xyzw.as_mut_ptr(), 0, &mut st),
-                &Backend::Group(g) => pbrtb200_group_render(g, &cam, &smp, &fd, &integ, xyzw.as_mut_ptr(), 0, &mut st),
+                &Backend::Group(g) => {
+                    // `xyzw` lives exactly as long as this call, so it is pinned here and unpinned below:
+                    // the group never page-locks a buffer on its own (its lifetime is ours).  Pinned, every
+                    // GPU's film kernel stores its rows straight into the Vec; a failed pin only means
+                    // staged copies.
+                    let pinned = pbrtb200_group_pin_host_film(g, xyzw.as_mut_ptr(), (xyzw.len() * 4) as u64) == PBRTB200_OK;
+                    let rc = pbrtb200_group_render(g, &cam, &smp, &fd, &integ, xyzw.as_mut_ptr(), 0, &mut st);
+                    if pinned {
+                        pbrtb200_group_unpin_host_film(g);
+                    }
+                    rc
+                }
             }
         };
         self.last_stats = st;

@@ -178,6 +178,8 @@ SYMBOLS = [
     ("pbrtb200_group_ctx", _vp, [_vp, C.c_int]),
     ("pbrtb200_group_upload_scene", i32, [_vp, P(Scene)]),
     ("pbrtb200_group_render", i32, [_vp, P(Camera), P(Sampler), P(Film), P(Integrator), _vp, C.c_int, P(Stats)]),
+    ("pbrtb200_group_pin_host_film", i32, [_vp, _vp, u64]),
+    ("pbrtb200_group_unpin_host_film", i32, [_vp]),
     ("pbrtb200_group_bands", i32, [_vp, P(i32), _fp]),
     ("pbrtb200_group_device_stats", i32, [_vp, C.c_int, P(Stats)]),
     ("pbrtb200_cut_bands", i32, [_fp, C.c_int, C.c_int, C.c_int, P(i32)]),

@@ -607,6 +607,7 @@ class Group:
         if rc:
             raise PbrtError(rc, lib().pbrtb200_group_last_error(None).decode())
         self.scene_key, self.host_scene = None, None
+        self._pinned = None
 
     def check(self, rc):
         if rc:
@@ -633,10 +634,22 @@ class Group:
             out.append(st.as_dict())
         return out
 
+    def pin_host_film(self, film):
+        """Page-locks and maps `film` (a numpy array) for every device, so that the film kernels store
+        into it directly.  The group holds a reference until unpin_host_film() / close(): the buffer
+        cannot be freed while it is registered."""
+        self.check(lib().pbrtb200_group_pin_host_film(self.h, C.c_void_p(film.ctypes.data), film.nbytes))
+        self._pinned = film
+
+    def unpin_host_film(self):
+        self.check(lib().pbrtb200_group_unpin_host_film(self.h))
+        self._pinned = None
+
     def close(self):
         if self.h:
-            lib().pbrtb200_group_destroy(self.h)
+            lib().pbrtb200_group_destroy(self.h)   # (unpins)
             self.h = None
+        self._pinned = None
 
     def __del__(self):
         try:

@@ -132,7 +132,7 @@ struct pbrtb200_group {
   pbrtb200_bands bal;             // row bands of the current view
   std::vector<float> device_ms;
   bool peers_enabled = false;
-  // pinned registration of the caller's host film
+  // host film page-locked on the caller's request (pbrtb200_group_pin_host_film)
   void* reg_ptr = nullptr;
   size_t reg_bytes = 0;
 
@@ -306,6 +306,35 @@ int pbrtb200_group_upload_scene(pbrtb200_group* g, const pbrtb200_scene* scene) 
   return g->collect("upload_scene");
 }
 
+// The group never page-locks a buffer on its own: a registration that outlives the caller's buffer
+// would keep the OLD physical pages pinned, and a new buffer that malloc places at the same address
+// would silently never receive its film.  The caller, who owns the buffer's lifetime, pins it.
+int pbrtb200_group_pin_host_film(pbrtb200_group* g, float* xyzw, uint64_t bytes) {
+  if (!g) return PBRTB200_EINVAL;
+  if (!xyzw || bytes == 0) return g->fail(PBRTB200_EINVAL, "pin_host_film: NULL buffer or no bytes");
+  pbrtb200_group_unpin_host_film(g);
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, xyzw) == cudaSuccess && at.type == cudaMemoryTypeHost) return PBRTB200_OK;  // already is
+  (void)cudaGetLastError();
+  if (cudaHostRegister(xyzw, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return g->fail(PBRTB200_ENOMEM, "pin_host_film: cudaHostRegister failed");
+  }
+  g->reg_ptr = xyzw;
+  g->reg_bytes = (size_t)bytes;
+  return PBRTB200_OK;
+}
+int pbrtb200_group_unpin_host_film(pbrtb200_group* g) {
+  if (!g) return PBRTB200_EINVAL;
+  if (g->reg_ptr) {
+    cudaHostUnregister(g->reg_ptr);
+    (void)cudaGetLastError();
+  }
+  g->reg_ptr = nullptr;
+  g->reg_bytes = 0;
+  return PBRTB200_OK;
+}
+
 int pbrtb200_group_device_stats(const pbrtb200_group* g, int i, pbrtb200_stats* out) {
   if (!g || !out || i < 0 || i >= (int)g->w.size()) return PBRTB200_EINVAL;
   *out = g->w[(size_t)i].st;
@@ -357,21 +386,6 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
     g->bal.update(g->device_ms.data());  // same view again: follow the measured device times
   }
 
-  // ---- the caller's host film: page-locked once, so that every device's rows travel by DMA ------
-  const size_t film_bytes = (size_t)W * (size_t)H * 4 * sizeof(float);
-  if (!out_is_device && (g->reg_ptr != out_xyzw || g->reg_bytes != film_bytes)) {
-    if (g->reg_ptr) cudaHostUnregister(g->reg_ptr);
-    g->reg_ptr = nullptr;
-    cudaPointerAttributes at{};
-    const bool already = cudaPointerGetAttributes(&at, out_xyzw) == cudaSuccess && at.type == cudaMemoryTypeHost;
-    (void)cudaGetLastError();
-    if (!already && cudaHostRegister(out_xyzw, film_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
-      g->reg_ptr = out_xyzw;
-      g->reg_bytes = film_bytes;
-    }
-    (void)cudaGetLastError();  // registration is an optimisation: pageable copies still work
-  }
-
   // ---- one band per device -----------------------------------------------------------------------
   g->run([&](int i) {
     Worker& w = g->w[(size_t)i];
@@ -390,8 +404,9 @@ int pbrtb200_group_render(pbrtb200_group* g, const pbrtb200_camera* cam, const p
       w.rc = pbrtb200_render(w.ctx, cam, smp, film, integ, &ts, out_xyzw, 1, &w.st);
       return;
     }
-    // Host film: pbrtb200_render with KEEP_OTHERS copies exactly this band's rows into the caller's
-    // buffer, on this device's own stream (one synchronisation per device and frame).
+    // Host film: pbrtb200_render with KEEP_OTHERS delivers exactly this band's rows into the caller's
+    // buffer on this device's own stream — stored by k_film itself when the buffer is page-locked and
+    // mapped (pbrtb200_group_pin_host_film, cudaHostAlloc), else staged in HBM and copied.
     w.rc = pbrtb200_render(w.ctx, cam, smp, film, integ, &ts, out_xyzw, 0, &w.st);
   });
 

@@ -1,8 +1,8 @@
 """Small frames that cover every kernel of the render path, for compute-sanitizer (scripts/gpu_sanitize.sh):
 the smoke frame, a wide-filter frame, a multi-light / multi-sample frame (k_fold), a mixed sphere /
 triangle textured frame, a frame forced through the sample ring and banded film, a Halton frame, the
-trace hooks, and one frame through a (single-device) group, whose page-locked host film the film
-kernel writes directly (PBRTB200_HOST_FILM_STORES)."""
+trace hooks, and frames through a (single-device) group: staged host film, then a host film pinned with
+pbrtb200_group_pin_host_film, which the film kernel writes directly (PBRTB200_HOST_FILM_STORES)."""
 import os
 import sys
 
@@ -39,5 +39,11 @@ rays[:, 4:7] = rng.uniform(-1, 1, (4096, 3))
 rays[:, 7] = 1e30
 rr.intersect(cfg["scene"], rays)
 rr.intersect_p(cfg["scene"], rays)
-render(scenes.config3(nx=40, nz=20, xres=64, yres=48, xs=2, ys=2), ctx=pb.Group([0]))
+grp = pb.Group([0])
+cfg = scenes.config3(nx=40, nz=20, xres=64, yres=48, xs=2, ys=2)
+r, film = render(cfg, ctx=grp)
+grp.pin_host_film(film)             # page-locked + mapped: k_film stores straight into host memory
+r.render(cfg["scene"], out=film)
+assert np.isfinite(film).all()
+grp.unpin_host_film()
 print("sanitize_frames: done")

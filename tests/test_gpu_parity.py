@@ -278,6 +278,15 @@ def test_group_render_is_bit_identical_to_one_gpu(orc, n_dev):
     dev = torch.zeros(want.size, dtype=torch.float32, device="cuda:0")
     r.render(cfg["scene"], out=dev)
     assert np.array_equal(dev.cpu().numpy().reshape(want.shape).view(np.uint32), want.view(np.uint32))
+    # a host film the caller pinned for the group: the film kernels of all devices store into it
+    host = np.full(want.shape, -1.0, np.float32)
+    grp.pin_host_film(host)
+    r.render(cfg["scene"], out=host)
+    assert np.array_equal(host.view(np.uint32), want.view(np.uint32))
+    grp.unpin_host_film()
+    host[:] = -1.0
+    r.render(cfg["scene"], out=host)                 # pageable again: staged copies, same film
+    assert np.array_equal(host.view(np.uint32), want.view(np.uint32))
     wide = scenes.config1(xres=96, yres=64, filt=pb.Filter.gaussian(2.0, 2.0, 2.0))
     want = _renderer(wide).render(wide["scene"]).copy()
     got = _renderer(wide, ctx=pb.Group(list(range(n_dev)))).render(wide["scene"])
